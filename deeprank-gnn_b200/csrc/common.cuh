@@ -1,0 +1,104 @@
+// Shared helpers for libdrgnn (sm_100a).  Internal header, not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/drgnn.h"
+
+namespace drgnn {
+
+// ---- error plumbing (thread-local message, C-ABI returns an int) ----
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define DRGNN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return drgnn::fail(DRGNN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                               \
+  } while (0)
+#define DRGNN_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return drgnn::fail(DRGNN_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+#define DRGNN_REQUIRE(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return drgnn::fail(DRGNN_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceInfo {
+  int sms;
+  int smem_optin;
+  int device;
+};
+const DeviceInfo& device_info();
+
+// ---- device helpers ----
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// inclusive warp scan
+__device__ __forceinline__ int warp_scan_incl(int v) {
+  const int l = lane_id();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (l >= o) v += t;
+  }
+  return v;
+}
+
+// In-place exclusive scan of a shared-memory int array by the whole CTA.
+// `wsum` is a 33-int shared scratch.  Returns the total.  All threads must call.
+__device__ inline int block_exclusive_scan(int* a, int len, int* wsum) {
+  const int T = blockDim.x, t = threadIdx.x;
+  const int chunk = (len + T - 1) / T;
+  const int beg = min(t * chunk, len), end = min(beg + chunk, len);
+  int s = 0;
+  for (int i = beg; i < end; ++i) s += a[i];
+  int incl = warp_scan_incl(s);
+  if (lane_id() == 31) wsum[warp_id()] = incl;
+  __syncthreads();
+  if (warp_id() == 0) {
+    int nw = T >> 5;
+    int v = lane_id() < nw ? wsum[lane_id()] : 0;
+    int vi = warp_scan_incl(v);
+    wsum[lane_id()] = vi - v;  // exclusive warp offsets
+    if (lane_id() == 31) wsum[32] = vi;
+  }
+  __syncthreads();
+  int run = wsum[warp_id()] + incl - s;
+  for (int i = beg; i < end; ++i) {
+    int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  int total = wsum[32];
+  __syncthreads();
+  return total;
+}
+
+}  // namespace drgnn

@@ -1,0 +1,629 @@
+// Structure pass: all integer work that depends only on the batch, one CTA per graph.
+//
+// Replaces (bit-exact) for a whole mini-batch:
+//   get_preloaded_cluster               deeprank_gnn/community_pooling.py:25-30
+//   PyG consecutive_cluster             community_pooling.py:197, max_pool_x (ginet.py:114,129)
+//   PyG pool_edge + torch_sparse coalesce   community_pooling.py:204-205
+//   PyG pool_batch                      community_pooling.py:222-224
+// and builds the dst-sorted CSR / src-sorted CSC the aggregation kernels use instead of
+// x[col] gathers + scatter_add (ginet.py:57-71).
+//
+// Kernel A (graph_local_kernel): everything local to a graph, in shared memory:
+//   stable counting sorts (CSR, CSC, members-of-cluster), dense relabel of cluster ids via
+//   a presence bitmap + popcount prefix, coarsened edge list via a per-warp column bitmap
+//   (emits each pooled row sorted & unique, so no sort / dedupe pass is needed), summed
+//   edge attributes in a fixed order (deterministic), level-1 relabel.
+// Kernel B (graph_finalize_kernel): cross-graph exclusive offsets (K0, E1, K1) and the
+//   compaction of the locally-indexed results into their final global positions.
+#include "common.cuh"
+
+namespace drgnn {
+
+static constexpr int kThreads = 512;
+static constexpr int kWarps = kThreads / 32;
+static constexpr int kCapWords = 1024;  // presence bitmap: cluster-id range per graph <= 32768
+
+struct SmemPlan {
+  // byte offsets into dynamic shared memory
+  int erow, ecol, slotR, slotC, prow, ptrR, ptrC, dense0, mptr, mem, rowptr1, cbits, cpre, wbits, wpre,
+      dense1, mptr1, mem1, total;
+  int W1;  // words per warp bitmap
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) {
+  SmemPlan p;
+  int o = 0;
+  const int n1 = max_n + 1, c1 = max_c1 + 1;
+  p.W1 = (max_n + 31) / 32;
+  p.erow = o;    o = align16(o + 2 * max_e);
+  p.ecol = o;    o = align16(o + 2 * max_e);
+  p.slotR = o;   o = align16(o + 2 * max_e);
+  p.slotC = o;   o = align16(o + 2 * max_e);   // later reused as pooled col list
+  p.prow = o;    o = align16(o + 2 * max_e);
+  p.ptrR = o;    o = align16(o + 4 * n1);
+  p.ptrC = o;    o = align16(o + 4 * n1);      // later reused for the pooled CSC pointers
+  p.dense0 = o;  o = align16(o + 2 * max_n);
+  p.mptr = o;    o = align16(o + 4 * n1);
+  p.mem = o;     o = align16(o + 2 * max_n);
+  p.rowptr1 = o; o = align16(o + 4 * n1);
+  p.cbits = o;   o = align16(o + 4 * kCapWords);
+  p.cpre = o;    o = align16(o + 4 * kCapWords);
+  p.wbits = o;   o = align16(o + 4 * kWarps * p.W1);
+  p.wpre = o;    o = align16(o + 4 * kWarps * p.W1);
+  p.dense1 = o;  o = align16(o + 2 * max_c1);
+  p.mptr1 = o;   o = align16(o + 4 * c1);
+  p.mem1 = o;    o = align16(o + 2 * max_c1);
+  p.total = o;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stable counting sort: slot[ptr[k] .. ptr[k+1]) = indices e (ascending) with key[e] == k.
+// ---------------------------------------------------------------------------------------
+__device__ void csr_build(const uint16_t* key, int m, int n, int* ptr, uint16_t* slot, int* wsum) {
+  const int T = blockDim.x, t = threadIdx.x;
+  for (int i = t; i <= n; i += T) ptr[i] = 0;
+  __syncthreads();
+  for (int e = t; e < m; e += T) atomicAdd(&ptr[key[e]], 1);
+  __syncthreads();
+  block_exclusive_scan(ptr, n + 1, wsum);
+  for (int e = t; e < m; e += T) {
+    int p = atomicAdd(&ptr[key[e]], 1);
+    slot[p] = (uint16_t)e;
+  }
+  __syncthreads();
+  // ptr[k] now holds end(k) == start(k+1): shift right by one, highest chunk first
+  for (int base = ((n) / T) * T; base >= 0; base -= T) {
+    int i = base + t;
+    int v = 0;
+    if (i >= 1 && i <= n) v = ptr[i - 1];
+    __syncthreads();
+    if (i <= n) ptr[i] = v;
+    __syncthreads();
+  }
+  // make every segment ascending in e (atomics placed them in arbitrary order)
+  for (int k = t; k < n; k += T) {
+    int s = ptr[k], d = ptr[k + 1] - s;
+    if (d > 1 && d <= 32) {
+      for (int i = 1; i < d; ++i) {
+        uint16_t v = slot[s + i];
+        int j = i - 1;
+        while (j >= 0 && slot[s + j] > v) {
+          slot[s + j + 1] = slot[s + j];
+          --j;
+        }
+        slot[s + j + 1] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // long segments: odd-even transposition sort by a warp
+  for (int k = warp_id(); k < n; k += (T >> 5)) {
+    int s = ptr[k], d = ptr[k + 1] - s;
+    if (d > 32) {
+      for (int pass = 0; pass < d; ++pass) {
+        for (int j = 2 * lane_id() + (pass & 1); j + 1 < d; j += 64) {
+          uint16_t a = slot[s + j], b = slot[s + j + 1];
+          if (a > b) {
+            slot[s + j] = b;
+            slot[s + j + 1] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense relabel of `n` int64 ids (sorted-unique rank, i.e. consecutive_cluster's inverse
+// restricted to one graph).  Returns K; writes min / max of the raw ids.
+// ---------------------------------------------------------------------------------------
+__device__ int relabel(const int64_t* ids, int n, uint16_t* dense, uint32_t* cbits, int* cpre, int* wsum,
+                       long long* red, int32_t* status, long long* out_min, long long* out_max) {
+  const int T = blockDim.x, t = threadIdx.x;
+  long long mn = LLONG_MAX, mx = LLONG_MIN;
+  for (int i = t; i < n; i += T) {
+    long long v = ids[i];
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+  }
+  if (lane_id() == 0) {
+    red[2 * warp_id()] = mn;
+    red[2 * warp_id() + 1] = mx;
+  }
+  __syncthreads();
+  mn = LLONG_MAX;
+  mx = LLONG_MIN;
+  for (int w = 0; w < (T >> 5); ++w) {
+    mn = red[2 * w] < mn ? red[2 * w] : mn;
+    mx = red[2 * w + 1] > mx ? red[2 * w + 1] : mx;
+  }
+  __syncthreads();
+  *out_min = mn;
+  *out_max = mx;
+  if (n == 0) return 0;
+  long long range = mx - mn + 1;
+  if (mn < 0 && t == 0) atomicOr(status, DRGNN_ST_NEGATIVE_ID);
+  if (range > (long long)kCapWords * 32) {
+    if (t == 0) atomicOr(status, DRGNN_ST_CLUSTER_RANGE);
+    for (int i = t; i < n; i += T) dense[i] = 0;
+    __syncthreads();
+    return 1;
+  }
+  const int W = (int)((range + 31) >> 5);
+  for (int w = t; w < W; w += T) cbits[w] = 0u;
+  __syncthreads();
+  for (int i = t; i < n; i += T) {
+    int v = (int)(ids[i] - mn);
+    atomicOr(&cbits[v >> 5], 1u << (v & 31));
+  }
+  __syncthreads();
+  for (int w = t; w < W; w += T) cpre[w] = __popc(cbits[w]);
+  __syncthreads();
+  int K = block_exclusive_scan(cpre, W, wsum);
+  for (int i = t; i < n; i += T) {
+    int v = (int)(ids[i] - mn);
+    dense[i] = (uint16_t)(cpre[v >> 5] + __popc(cbits[v >> 5] & ((1u << (v & 31)) - 1u)));
+  }
+  __syncthreads();
+  return K;
+}
+
+// scratch layout helpers (must match host side)
+struct Scratch {
+  int32_t *mptr0, *rowptr1, *cscptr1, *mptr1, *mem1;  // node-indexed
+  int32_t *col1, *row1, *cscrow1, *csceid1;           // edge-indexed
+};
+__host__ __device__ inline Scratch make_scratch(const drgnn_structure_io& io) {
+  Scratch s;
+  const int64_t nb = (int64_t)io.N + io.B + 1;
+  s.mptr0 = io.scratch_n;
+  s.rowptr1 = io.scratch_n + nb;
+  s.cscptr1 = io.scratch_n + 2 * nb;
+  s.mptr1 = io.scratch_n + 3 * nb;
+  s.mem1 = io.scratch_n + 4 * nb;
+  s.col1 = io.scratch_e;
+  s.row1 = io.scratch_e + io.E;
+  s.cscrow1 = io.scratch_e + 2 * (int64_t)io.E;
+  s.csceid1 = io.scratch_e + 3 * (int64_t)io.E;
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_structure_io io) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int wsum[33];
+  __shared__ long long red[2 * kWarps];
+  const int T = blockDim.x, t = threadIdx.x;
+  const int g = blockIdx.x;
+  const SmemPlan P = make_plan(io.max_n, io.max_e, io.L1 > 0 ? io.max_n : 0);
+  uint16_t* erow = (uint16_t*)(smem + P.erow);
+  uint16_t* ecol = (uint16_t*)(smem + P.ecol);
+  uint16_t* slotR = (uint16_t*)(smem + P.slotR);
+  uint16_t* slotC = (uint16_t*)(smem + P.slotC);
+  uint16_t* prow = (uint16_t*)(smem + P.prow);
+  int* ptrR = (int*)(smem + P.ptrR);
+  int* ptrC = (int*)(smem + P.ptrC);
+  uint16_t* dense0 = (uint16_t*)(smem + P.dense0);
+  int* mptr = (int*)(smem + P.mptr);
+  uint16_t* mem = (uint16_t*)(smem + P.mem);
+  int* rowptr1 = (int*)(smem + P.rowptr1);
+  uint32_t* cbits = (uint32_t*)(smem + P.cbits);
+  int* cpre = (int*)(smem + P.cpre);
+  uint32_t* wbits = (uint32_t*)(smem + P.wbits) + warp_id() * P.W1;
+  int* wpre = (int*)(smem + P.wpre) + warp_id() * P.W1;
+  uint16_t* dense1 = (uint16_t*)(smem + P.dense1);
+  int* mptr1 = (int*)(smem + P.mptr1);
+  uint16_t* mem1 = (uint16_t*)(smem + P.mem1);
+  const Scratch S = make_scratch(io);
+
+  const int n0 = io.node_ptr[g], n = io.node_ptr[g + 1] - n0;
+  const int e0 = io.edge_ptr[g], m = io.edge_ptr[g + 1] - e0;
+  const int ne = io.ne;
+
+  // ---- 1. local edge list ----
+  for (int e = t; e < m; e += T) {
+    long long r = io.edge_index[e0 + e] - n0;
+    long long c = io.edge_index[(int64_t)io.E + e0 + e] - n0;
+    if (r < 0 || r >= n || c < 0 || c >= n) {
+      atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
+      r = 0;
+      c = 0;
+    }
+    erow[e] = (uint16_t)r;
+    ecol[e] = (uint16_t)c;
+  }
+  __syncthreads();
+
+  // ---- 2. CSR by destination (row) ----
+  csr_build(erow, m, n, ptrR, slotR, wsum);
+  for (int i = t; i <= n; i += T) io.rowptr0[n0 + i] = e0 + ptrR[i];
+  for (int p = t; p < m; p += T) {
+    int e = slotR[p];
+    io.col0[e0 + p] = n0 + ecol[e];
+    io.eid0[e0 + p] = e0 + e;
+    if (io.w0csr) io.w0csr[e0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
+  }
+  // ---- 3. CSC (transposed graph) ----
+  csr_build(ecol, m, n, ptrC, slotC, wsum);
+  for (int i = t; i <= n; i += T) io.cscptr0[n0 + i] = e0 + ptrC[i];
+  for (int p = t; p < m; p += T) {
+    int e = slotC[p];
+    io.cscrow0[e0 + p] = n0 + erow[e];
+    io.csceid0[e0 + p] = e0 + e;
+    if (io.w0csc) io.w0csc[e0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
+  }
+  __syncthreads();
+
+  // ---- 4. relabel level-0 clusters ----
+  long long cmin, cmax;
+  const int K = relabel(io.cluster0 + n0, n, dense0, cbits, cpre, wsum, red, io.status, &cmin, &cmax);
+  for (int i = t; i < n; i += T) io.cl0[n0 + i] = dense0[i];  // local; finalize adds the graph offset
+
+  // ---- 5. members of every cluster (ascending node id) ----
+  csr_build(dense0, n, K, mptr, mem, wsum);
+  for (int k = t; k <= K; k += T) S.mptr0[n0 + g + k] = mptr[k];
+  for (int p = t; p < n; p += T) io.cmem0[n0 + p] = n0 + mem[p];
+
+  // ---- 6. coarsened edges: per pooled row a column bitmap -> sorted unique columns ----
+  uint16_t* pcol = slotC;  // CSC slots are dead now
+  const int W1 = (K + 31) >> 5;
+  const int lane = lane_id();
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int r = warp_id(); r < K; r += kWarps) {
+      for (int w = lane; w < W1; w += 32) wbits[w] = 0u;
+      __syncwarp();
+      for (int mi = mptr[r]; mi < mptr[r + 1]; ++mi) {
+        int i = mem[mi];
+        for (int p = ptrR[i] + lane; p < ptrR[i + 1]; p += 32) {
+          int pc = dense0[ecol[slotR[p]]];
+          if (pc != r) atomicOr(&wbits[pc >> 5], 1u << (pc & 31));  // remove_self_loops
+        }
+      }
+      __syncwarp();
+      if (pass == 0) {
+        int cnt = 0;
+        for (int w = lane; w < W1; w += 32) cnt += __popc(wbits[w]);
+        cnt = warp_sum(cnt);
+        if (lane == 0) rowptr1[r] = cnt;
+      } else {
+        // exclusive popcount prefix over the words of this row
+        int run = 0;
+        for (int wb = 0; wb < W1; wb += 32) {
+          int w = wb + lane;
+          int c = w < W1 ? __popc(wbits[w]) : 0;
+          int inc = warp_scan_incl(c);
+          if (w < W1) wpre[w] = run + inc - c;
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        const int base = rowptr1[r];
+        const int cnt = rowptr1[r + 1] - base;
+        for (int w = lane; w < W1; w += 32) {
+          uint32_t bits = wbits[w];
+          int q = base + wpre[w];
+          while (bits) {
+            int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            pcol[q] = (uint16_t)(w * 32 + b);
+            prow[q] = (uint16_t)r;
+            ++q;
+          }
+        }
+        __syncwarp();
+        // summed attributes of merged edges: fixed order (members ascending, then edge id)
+        if (io.edge_attr1 != nullptr) {
+          for (int f = 0; f < ne; ++f) {
+            for (int s = lane; s < cnt; s += 32) {
+              const int tc = pcol[base + s];
+              float acc = 0.f;
+              for (int mi = mptr[r]; mi < mptr[r + 1]; ++mi) {
+                int i = mem[mi];
+                for (int p = ptrR[i]; p < ptrR[i + 1]; ++p) {
+                  int e = slotR[p];
+                  if (dense0[ecol[e]] == tc) acc += io.edge_attr[(int64_t)(e0 + e) * ne + f];
+                }
+              }
+              io.scratch_f[(int64_t)(e0 + base + s) * ne + f] = acc;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (pass == 0) {
+      if (t == 0) rowptr1[K] = 0;
+      __syncthreads();
+      block_exclusive_scan(rowptr1, K + 1, wsum);
+    }
+  }
+  const int E1 = rowptr1[K];
+  for (int r = t; r <= K; r += T) S.rowptr1[n0 + g + r] = rowptr1[r];
+  for (int p = t; p < E1; p += T) {
+    S.col1[e0 + p] = pcol[p];
+    S.row1[e0 + p] = prow[p];
+  }
+  __syncthreads();
+
+  // ---- 7. CSC of the coarsened graph ----
+  int* ptrC1 = ptrC;
+  uint16_t* slotC1 = slotR;  // level-0 CSR slots are dead now
+  csr_build(pcol, E1, K, ptrC1, slotC1, wsum);
+  for (int r = t; r <= K; r += T) S.cscptr1[n0 + g + r] = ptrC1[r];
+  for (int p = t; p < E1; p += T) {
+    int q = slotC1[p];
+    S.cscrow1[e0 + p] = prow[q];
+    S.csceid1[e0 + p] = q;
+  }
+  __syncthreads();
+
+  // ---- 8. level-1 clustering ----
+  int K1 = 0, c1len = 0;
+  if (io.cluster1 != nullptr) {
+    const int c0 = io.c1_ptr[g];
+    c1len = io.c1_ptr[g + 1] - c0;
+    if (c1len != K) {
+      if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER1_LENGTH);
+    }
+    c1len = min(c1len, io.max_n);  // shared-memory bound (only reachable for invalid input)
+    long long mn1, mx1;
+    K1 = relabel(io.cluster1 + c0, c1len, dense1, cbits, cpre, wsum, red, io.status, &mn1, &mx1);
+    for (int k = t; k < c1len; k += T) io.cl1[c0 + k] = dense1[k];
+    csr_build(dense1, c1len, K1, mptr1, mem1, wsum);
+    for (int q = t; q <= K1; q += T) S.mptr1[c0 + g + q] = mptr1[q];
+    for (int p = t; p < c1len; p += T) S.mem1[c0 + p] = mem1[p];
+  }
+
+  if (t == 0) {
+    int32_t* gs = io.gstat + 8 * g;
+    gs[0] = K;
+    gs[1] = E1;
+    gs[2] = K1;
+    gs[3] = (int32_t)(cmin & 0xffffffffll);
+    gs[4] = (int32_t)(cmin >> 32);
+    gs[5] = (int32_t)(cmax & 0xffffffffll);
+    gs[6] = (int32_t)(cmax >> 32);
+    gs[7] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) graph_finalize_kernel(const drgnn_structure_io io) {
+  __shared__ int red[3][8];
+  __shared__ int offs[3];
+  const int T = blockDim.x, t = threadIdx.x;
+  const int g = blockIdx.x;
+  const Scratch S = make_scratch(io);
+  // exclusive offsets over the preceding graphs
+  int a = 0, b = 0, c = 0;
+  for (int h = t; h < g; h += T) {
+    a += io.gstat[8 * h];
+    b += io.gstat[8 * h + 1];
+    c += io.gstat[8 * h + 2];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  if (lane_id() == 0) {
+    red[0][warp_id()] = a;
+    red[1][warp_id()] = b;
+    red[2][warp_id()] = c;
+  }
+  __syncthreads();
+  if (t < 3) {
+    int s = 0;
+    for (int w = 0; w < (T >> 5); ++w) s += red[t][w];
+    offs[t] = s;
+  }
+  __syncthreads();
+  const int Koff = offs[0], E1off = offs[1], K1off = offs[2];
+  const int32_t* gs = io.gstat + 8 * g;
+  const int K = gs[0], E1 = gs[1], K1 = gs[2];
+  const int n0 = io.node_ptr[g], n = io.node_ptr[g + 1] - n0;
+  const int e0 = io.edge_ptr[g];
+  const int ne = io.ne;
+
+  if (!io.clusters_are_local && g > 0 && n > 0 && t == 0) {
+    // global ids must increase with the graph id, else sorted-unique order != graph-major order
+    int h = g - 1;
+    while (h >= 0 && io.gstat[8 * h + 7] == 0) --h;
+    if (h >= 0) {
+      long long pmax = ((long long)io.gstat[8 * h + 6] << 32) | (uint32_t)io.gstat[8 * h + 5];
+      long long cmin = ((long long)gs[4] << 32) | (uint32_t)gs[3];
+      if (cmin <= pmax) atomicOr(io.status, DRGNN_ST_CLUSTER_ORDER);
+    }
+  }
+
+  for (int i = t; i < n; i += T) {
+    int v = io.cl0[n0 + i] + Koff;
+    io.cl0[n0 + i] = v;
+    if (io.cl0_i64) io.cl0_i64[n0 + i] = v;
+  }
+  for (int k = t; k <= K; k += T) {
+    io.cmptr0[Koff + k] = n0 + S.mptr0[n0 + g + k];
+    io.rowptr1[Koff + k] = E1off + S.rowptr1[n0 + g + k];
+    io.cscptr1[Koff + k] = E1off + S.cscptr1[n0 + g + k];
+  }
+  for (int k = t; k < K; k += T) {
+    io.batch1[Koff + k] = g;
+    if (io.batch1_i64) io.batch1_i64[Koff + k] = g;
+  }
+  for (int p = t; p < E1; p += T) {
+    const int row = Koff + S.row1[e0 + p], col = Koff + S.col1[e0 + p];
+    io.col1[E1off + p] = col;
+    if (io.edge_index1) {
+      io.edge_index1[E1off + p] = row;
+      io.edge_index1[(int64_t)io.E + E1off + p] = col;
+    }
+    if (io.edge_attr1)
+      for (int f = 0; f < ne; ++f)
+        io.edge_attr1[(int64_t)(E1off + p) * ne + f] = io.scratch_f[(int64_t)(e0 + p) * ne + f];
+    const int q = S.csceid1[e0 + p];
+    io.cscrow1[E1off + p] = Koff + S.cscrow1[e0 + p];
+    io.csceid1[E1off + p] = E1off + q;
+    if (io.w1csc) io.w1csc[E1off + p] = io.scratch_f[(int64_t)(e0 + q) * ne];
+  }
+  if (t == 0) io.kptr0[g] = Koff;
+
+  if (io.cluster1 != nullptr) {
+    const int c0 = io.c1_ptr[g], c1len = io.c1_ptr[g + 1] - c0;
+    for (int k = t; k < c1len; k += T) io.cl1[c0 + k] += K1off;
+    for (int q = t; q <= K1; q += T) io.cmptr1[K1off + q] = Koff + S.mptr1[c0 + g + q];
+    for (int p = t; p < c1len; p += T) io.cmem1[Koff + p] = Koff + S.mem1[c0 + p];
+    for (int q = t; q < K1; q += T) {
+      io.batch2[K1off + q] = g;
+      if (io.batch2_i64) io.batch2_i64[K1off + q] = g;
+    }
+    if (t == 0) io.kptr1[g] = K1off;
+  }
+  if (g == io.B - 1 && t == 0) {
+    io.kptr0[io.B] = Koff + K;
+    if (io.cluster1 != nullptr) io.kptr1[io.B] = K1off + K1;
+    io.counts[0] = Koff + K;
+    io.counts[1] = E1off + E1;
+    io.counts[2] = K1off + K1;
+    io.counts[3] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// get_preloaded_cluster stand-alone (community_pooling.py:25-30)
+// ---------------------------------------------------------------------------------------
+__global__ void seg_max_kernel(const int64_t* cluster, const int32_t* seg_ptr, int B, int64_t* segmax1) {
+  __shared__ long long red[8];
+  const int g = blockIdx.x;
+  long long mx = LLONG_MIN;
+  for (int i = seg_ptr[g] + threadIdx.x; i < seg_ptr[g + 1]; i += blockDim.x) {
+    long long v = cluster[i];
+    mx = v > mx ? v : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long a = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = a > mx ? a : mx;
+  }
+  if (lane_id() == 0) red[warp_id()] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = red[w] > mx ? red[w] : mx;
+    // torch.max of an empty selection raises in the reference; an empty graph contributes 0 here
+    segmax1[g] = (seg_ptr[g + 1] > seg_ptr[g]) ? mx + 1 : 0;
+  }
+}
+__global__ void seg_offset_add_kernel(int64_t* cluster, const int32_t* seg_ptr, int B, const int64_t* segmax1) {
+  __shared__ long long red[8];
+  __shared__ long long off_s;
+  const int g = blockIdx.x;
+  long long s = 0;
+  for (int h = threadIdx.x; h < g; h += blockDim.x) s += segmax1[h];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) red[warp_id()] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+    off_s = tot;
+  }
+  __syncthreads();
+  const long long off = off_s;
+  for (int i = seg_ptr[g] + threadIdx.x; i < seg_ptr[g + 1]; i += blockDim.x) cluster[i] += off;
+}
+
+__global__ void ptr_from_sorted_ids_kernel(const int64_t* ids, int n, int B, int32_t* ptr, int32_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  // boundaries: ptr[g] = first index whose id >= g
+  long long prev = (i == 0) ? -1 : ids[i - 1];
+  long long cur = (i == n) ? B : ids[i];
+  if (i < n && (cur < 0 || cur >= B)) {
+    atomicOr(status, 1);
+    return;
+  }
+  if (cur < prev) {
+    atomicOr(status, 1);
+    return;
+  }
+  for (long long gidx = prev + 1; gidx <= cur; ++gidx) ptr[gidx] = i;
+}
+
+}  // namespace drgnn
+
+using namespace drgnn;
+
+extern "C" int64_t drgnn_structure_smem_bytes(int32_t max_n, int32_t max_e, int32_t max_c1) {
+  if (max_n < 0 || max_e < 0) return DRGNN_ERR_INVALID;
+  if (max_n > 65535 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;
+  SmemPlan p = make_plan(max_n, max_e, max_c1);
+  if (p.total > device_info().smem_optin) return DRGNN_ERR_UNSUPPORTED;
+  return p.total;
+}
+
+extern "C" int drgnn_structure_build(const drgnn_structure_io* io, void* stream) {
+  DRGNN_REQUIRE(io != nullptr, "structure_build: io is NULL");
+  DRGNN_REQUIRE(io->B >= 0 && io->N >= 0 && io->E >= 0, "structure_build: negative size");
+  if (io->B == 0) return DRGNN_OK;
+  DRGNN_REQUIRE(io->node_ptr && io->edge_ptr && io->edge_index && io->cluster0, "structure_build: NULL input");
+  DRGNN_REQUIRE(io->rowptr0 && io->col0 && io->eid0 && io->cscptr0 && io->cscrow0 && io->csceid0 && io->cl0 &&
+                    io->cmptr0 && io->cmem0 && io->kptr0 && io->batch1 && io->rowptr1 && io->col1 && io->cscptr1 &&
+                    io->cscrow1 && io->csceid1 && io->counts && io->status && io->gstat && io->scratch_n &&
+                    io->scratch_e,
+                "structure_build: NULL output / workspace");
+  if (io->cluster1) {
+    DRGNN_REQUIRE(io->c1_ptr && io->cl1 && io->cmptr1 && io->cmem1 && io->kptr1 && io->batch2,
+                  "structure_build: cluster1 given but level-1 outputs are NULL");
+  }
+  if (io->ne > 0) DRGNN_REQUIRE(io->edge_attr != nullptr, "structure_build: ne > 0 but edge_attr is NULL");
+  if (io->w0csr || io->w0csc || io->w1csc || io->edge_attr1) {
+    DRGNN_REQUIRE(io->edge_attr != nullptr && io->ne >= 1, "structure_build: edge weights requested without edge_attr");
+    DRGNN_REQUIRE(io->scratch_f != nullptr, "structure_build: scratch_f is NULL");
+  }
+  if (io->w1csc) DRGNN_REQUIRE(io->edge_attr1 != nullptr, "structure_build: w1csc needs edge_attr1");
+  const int max_c1 = io->L1 > 0 ? io->max_n : 0;
+  int64_t smem = drgnn_structure_smem_bytes(io->max_n, io->max_e, max_c1);
+  if (smem < 0)
+    return fail(DRGNN_ERR_UNSUPPORTED,
+                "structure_build: a graph with %d nodes / %d edges does not fit one CTA's shared memory",
+                io->max_n, io->max_e);
+  static thread_local int64_t configured = -1;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(graph_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)device_info().smem_optin));
+    configured = device_info().smem_optin;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  graph_local_kernel<<<io->B, kThreads, smem, st>>>(*io);
+  DRGNN_CHECK_LAUNCH("graph_local_kernel");
+  graph_finalize_kernel<<<io->B, 256, 0, st>>>(*io);
+  DRGNN_CHECK_LAUNCH("graph_finalize_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_cluster_offset(int64_t* cluster, const int32_t* seg_ptr, int32_t B, int64_t* work, void* stream) {
+  DRGNN_REQUIRE(cluster && seg_ptr && work, "cluster_offset: NULL pointer");
+  if (B <= 1) return DRGNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  seg_max_kernel<<<B, 256, 0, st>>>(cluster, seg_ptr, B, work);
+  DRGNN_CHECK_LAUNCH("seg_max_kernel");
+  seg_offset_add_kernel<<<B, 256, 0, st>>>(cluster, seg_ptr, B, work);
+  DRGNN_CHECK_LAUNCH("seg_offset_add_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_ptr_from_sorted_ids(const int64_t* ids, int32_t n, int32_t B, int32_t* ptr, int32_t* status,
+                                         void* stream) {
+  DRGNN_REQUIRE(ptr && status && (ids || n == 0), "ptr_from_sorted_ids: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  ptr_from_sorted_ids_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ids, n, B, ptr, status);
+  DRGNN_CHECK_LAUNCH("ptr_from_sorted_ids_kernel");
+  return DRGNN_OK;
+}

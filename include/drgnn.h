@@ -1,0 +1,271 @@
+/*
+ * drgnn.h - C-ABI of the B200-native DeepRank-GNN hot path (libdrgnn.so).
+ *
+ * The reference (DeepRank/Deeprank-GNN v0.1.4) is pure Python and has no FFI of its
+ * own; its native work happens inside torch_scatter / torch_sparse / torch_geometric /
+ * ATen.  Each entry point below replaces one of those third-party kernels at the
+ * reference call site cited next to it (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    parameter name starts with h_;  float = fp32, indices = int32 unless stated
+ *  - the caller owns every buffer (inputs, outputs, workspaces); the library never
+ *    allocates or frees device memory and keeps no pointer after return
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit
+ *    synchronisation, no host read-back
+ *  - return 0 on success, <0 on error; drgnn_last_error() gives the message of the
+ *    last failing call of the calling thread
+ *  - row-major [rows, cols] matrices with an explicit leading dimension (ld*) in
+ *    elements, so column slices of wider buffers can be used in place
+ */
+#ifndef DRGNN_H
+#define DRGNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRGNN_OK 0
+#define DRGNN_ERR_INVALID (-1)
+#define DRGNN_ERR_CUDA (-2)
+#define DRGNN_ERR_UNSUPPORTED (-3)
+
+/* status bits written (OR-ed) by the structure kernels into io->status[0] */
+#define DRGNN_ST_EDGE_OUTSIDE_GRAPH 1   /* an edge endpoint is not a node of its graph          */
+#define DRGNN_ST_CLUSTER_RANGE 2        /* max-min cluster id of one graph exceeds the bitmap cap */
+#define DRGNN_ST_CLUSTER1_LENGTH 4      /* len(cluster1 of graph g) != n_unique(cluster0 of g)   */
+#define DRGNN_ST_CLUSTER_ORDER 8        /* global cluster ids are not increasing with graph id   */
+#define DRGNN_ST_NEGATIVE_ID 16         /* negative cluster id                                   */
+
+const char* drgnn_last_error(void);
+int drgnn_version(void);
+/* multiprocessor count / max opt-in shared memory of the current device (cached) */
+int drgnn_device_sms(void);
+int drgnn_device_smem_optin(void);
+
+/* ------------------------------------------------------------------------------------
+ * 1. Structure pass (integer, bit-exact): everything that depends only on the batch.
+ *    Replaces, for a whole mini-batch in two launches:
+ *      get_preloaded_cluster            deeprank_gnn/community_pooling.py:25-30
+ *      PyG consecutive_cluster          community_pooling.py:197 (and inside max_pool_x,
+ *                                       ginet.py:114,129 sGAT.py:130 foutnet.py:117)
+ *      PyG pool_edge (+torch_sparse coalesce)   community_pooling.py:204-205
+ *      PyG pool_batch                   community_pooling.py:222-224
+ *    and builds the CSR / CSC forms the aggregation kernels consume instead of the
+ *    reference's x[col] / x[row] gathers and scatter_add (ginet.py:57-71, sGAT.py:70-81,
+ *    foutnet.py:71-73).
+ *    One CTA per graph; graphs are contiguous node / edge ranges given by node_ptr /
+ *    edge_ptr (as produced by Batch.from_data_list).
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_structure_io {
+  /* ---- sizes ---- */
+  int32_t B;            /* graphs                                                        */
+  int32_t N;            /* nodes  (= node_ptr[B])                                        */
+  int32_t E;            /* directed edges (= edge_ptr[B])                                */
+  int32_t L1;           /* len(cluster1) (0 if absent); must equal K0 for valid data      */
+  int32_t ne;           /* edge_attr width (0 if edge_attr == NULL)                       */
+  int32_t max_n;        /* max nodes of one graph   (host-known from node_ptr)            */
+  int32_t max_e;        /* max edges of one graph   (host-known from edge_ptr)            */
+  int32_t clusters_are_local; /* 1: ids are per-graph local (un-offset, DataSet.py:348-357);
+                                 0: ids are already global (must increase with graph id)  */
+  /* ---- inputs ---- */
+  const int32_t* node_ptr;   /* [B+1] */
+  const int32_t* edge_ptr;   /* [B+1] */
+  const int32_t* c1_ptr;     /* [B+1] segment pointers of cluster1 (NULL if L1 == 0)       */
+  const int64_t* edge_index; /* [2,E]  row = edge_index[0] = destination / segment id,
+                                        col = edge_index[1] = gathered source (ginet.py:52) */
+  const float* edge_attr;    /* [E,ne] or NULL                                            */
+  const int64_t* cluster0;   /* [N]                                                       */
+  const int64_t* cluster1;   /* [L1] or NULL                                              */
+  /* ---- level-0 graph: final outputs ---- */
+  int32_t* rowptr0;  /* [N+1] CSR by destination; within a row ascending original edge id */
+  int32_t* col0;     /* [E]   source node of CSR slot                                     */
+  int32_t* eid0;     /* [E]   original edge id of CSR slot                                */
+  int32_t* cscptr0;  /* [N+1] CSR of the transposed graph (by source)                     */
+  int32_t* cscrow0;  /* [E]   destination node of CSC slot                                */
+  int32_t* csceid0;  /* [E]   original edge id of CSC slot                                */
+  float* w0csr;      /* [E]   edge_attr[eid0[p],0]    (NULL to skip; needs ne >= 1)       */
+  float* w0csc;      /* [E]   edge_attr[csceid0[p],0] (NULL to skip)                      */
+  /* ---- level-0 clustering ---- */
+  int32_t* cl0;      /* [N]   dense pooled-node id of every node (consecutive_cluster inv) */
+  int64_t* cl0_i64;  /* [N]   same as int64 (API mirror; NULL to skip)                    */
+  int32_t* cmptr0;   /* [N+1] members-of-cluster CSR: pointers (first K0+1 entries valid)  */
+  int32_t* cmem0;    /* [N]   member node ids, ascending inside a cluster                 */
+  int32_t* kptr0;    /* [B+1] pooled-node range of every graph                            */
+  int32_t* batch1;   /* [N]   graph id of pooled node (first K0 valid)  (pool_batch)       */
+  int64_t* batch1_i64;/* [N]  API mirror, NULL to skip                                     */
+  /* ---- level-1 (pooled) graph ---- */
+  int32_t* rowptr1;  /* [N+1] (first K0+1 valid) CSR of the coarsened graph               */
+  int32_t* col1;     /* [E]   (first E1 valid)                                            */
+  int64_t* edge_index1; /* [2,E] int64 mirror laid out with row stride E (first E1 columns
+                           valid): sorted by (row,col), unique, no self loops; NULL to skip */
+  float* edge_attr1; /* [E,ne] summed attrs of merged edges (first E1 rows); NULL to skip  */
+  int32_t* cscptr1;  /* [N+1] */
+  int32_t* cscrow1;  /* [E]   */
+  int32_t* csceid1;  /* [E]   pooled-edge id (position in col1) of CSC slot                */
+  float* w1csc;      /* [E]   edge_attr1[csceid1[p],0] (NULL to skip)                      */
+  /* ---- level-1 clustering (only if cluster1 != NULL) ---- */
+  int32_t* cl1;      /* [L1]  dense id of pooled node -> second-level cluster             */
+  int32_t* cmptr1;   /* [L1+1] */
+  int32_t* cmem1;    /* [L1]  */
+  int32_t* kptr1;    /* [B+1] second-level node range per graph (readout segments)        */
+  int32_t* batch2;   /* [L1]  (first K1 valid) */
+  int64_t* batch2_i64;
+  /* ---- counts / status ---- */
+  int32_t* counts;   /* [4]: K0, E1, K1, reserved                                         */
+  int32_t* status;   /* [1]: OR of DRGNN_ST_* bits (caller zeroes before the call)        */
+  /* ---- workspaces ---- */
+  int32_t* gstat;    /* [8*B] per-graph counts                                            */
+  int32_t* scratch_n;/* [6*(N+B)+L1+8] node-indexed scratch                               */
+  int32_t* scratch_e;/* [4*E+8] edge-indexed scratch                                      */
+  float* scratch_f;  /* [E*max(ne,1)] pooled attr scratch                                 */
+} drgnn_structure_io;
+
+/* Dynamic shared memory the per-graph kernel needs for (max_n, max_e); <0 if a graph is
+ * too large for one CTA (DRGNN_ERR_UNSUPPORTED). */
+int64_t drgnn_structure_smem_bytes(int32_t max_n, int32_t max_e, int32_t max_c1);
+int drgnn_structure_build(const drgnn_structure_io* io, void* stream);
+
+/* get_preloaded_cluster as a stand-alone op (community_pooling.py:25-30):
+ * cluster[i] += sum_{g < graph(i)} (max(cluster of g) + 1), in place, int64.
+ * seg_ptr [B+1] gives the contiguous segment of every graph. work: [B] int64. */
+int drgnn_cluster_offset(int64_t* cluster, const int32_t* seg_ptr, int32_t B, int64_t* work, void* stream);
+
+/* segment pointers from a sorted int64 id vector (`batch`): ptr[g] = first i with ids[i] >= g.
+ * status bit0 is set if ids is not sorted ascending or holds a value outside [0,B). */
+int drgnn_ptr_from_sorted_ids(const int64_t* ids, int32_t n, int32_t B, int32_t* ptr, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Aggregation: the edge gather -> (weight) -> segmented reduction that replaces
+ *    x[col] + scatter_sum (ginet.py:57-71), scatter_mean (sGAT.py:70-81) and the per-node
+ *    Python loop of FoutLayer (foutnet.py:71-73); the same kernel on the CSC form is the
+ *    backward.  No atomics: one sub-warp per destination row, deterministic.
+ *
+ *    out[i, 0:C] = act( selfc_i * self_src[i, 0:C]
+ *                       + post_i * sum_{p in [rowptr[i], rowptr[i+1])} ew[p] * sscale[col[p]] * src[col[p], 0:C]
+ *                       + bias[0:C] )
+ *    post_mode : 0 -> post_i = 1 (sum) ; 1 -> 1/max(deg_i,1) (scatter_mean) ;
+ *                2 -> 1/deg_i, deg_i = 0 gives NaN (torch.mean of an empty set, foutnet.py:73)
+ *    self_mode : 0 -> no self term ; 1 -> selfc_i = 1 ; 2 -> selfc_i = post_i * sum_p ew[p]
+ *                (also stored to selfc_out[i] when selfc_out != NULL) ; 3 -> selfc_i = selfc_in[i]
+ *    ew, sscale, bias, self_src may be NULL.  relu != 0 applies max(.,0).
+ *    self_out != NULL additionally stores selfc_i * self_src[i,:] there (ld = ld_self_out)
+ *    INSTEAD of adding the self term to out.
+ *    n_rows_dev (may be NULL) holds the live row count on the device (<= n_rows).
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_aggregate_args {
+  const float* src; int32_t ld_src;
+  float* out; int32_t ld_out;
+  const int32_t* rowptr; const int32_t* col;
+  const float* ew; const float* sscale;
+  const float* self_src; int32_t ld_self;
+  float* self_out; int32_t ld_self_out;
+  const float* selfc_in; float* selfc_out;
+  const float* bias;
+  int32_t n_rows; const int32_t* n_rows_dev;
+  int32_t C; int32_t post_mode; int32_t self_mode; int32_t relu;
+} drgnn_aggregate_args;
+int drgnn_aggregate(const drgnn_aggregate_args* a, void* stream);
+
+/* Same contract, per-graph tiles: the source rows of one graph (node_ptr[g]..node_ptr[g+1])
+ * are staged in shared memory with bulk async copies (cp.async.bulk + mbarrier), so neighbour
+ * re-reads never leave the SM and HBM traffic is compulsory-only.  Requires every col[p] of a
+ * row of graph g to lie inside graph g and ld_src == C.  tile_ptr: [n_tiles+1]. */
+int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr, int32_t n_tiles,
+                          int32_t max_tile_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Dense per-node transform (the nn.Linear / torch.mm of ginet.py:57-58,137-139,
+ *    sGAT.py:73,134-135, foutnet.py:62,65,121-122), done on N rows instead of E rows.
+ *    Y[r, g*Fout + o] = act( sum_k X[r, g*Fin + k] * Wg[k,o] + bias[g*Fout+o] )
+ *    w_layout 0: W stored [groups][Fout][Fin] (nn.Linear.weight) ; 1: [groups][Fin][Fout]
+ *    (sGAT weight / Fout Wc,Wn / transposed use in backward).
+ *    mask != NULL: the INPUT gradient convention for backward: X is replaced by
+ *    X * (mask > 0) (fused ReLU backward, mask has X's shape and ld_mask).
+ *    math: 0 = fp32 FMA, 1 = 3xTF32 tensor cores (error-compensated, ~fp32 accuracy)
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_linear_args {
+  const float* X; int32_t ldx;
+  const float* W; const float* bias;
+  float* Y; int32_t ldy;
+  const float* mask; int32_t ld_mask;
+  int32_t rows; const int32_t* rows_dev;
+  int32_t Fin; int32_t Fout; int32_t groups;
+  int32_t w_layout; int32_t relu; int32_t math;
+  /* dropout (ginet.py:138): keep_mask [rows, groups*Fout] of 0/1 floats, scaled by
+   * 1/(1-p) after the activation; NULL = no dropout */
+  const float* keep_mask; float keep_scale;
+} drgnn_linear_args;
+int drgnn_linear(const drgnn_linear_args* a, void* stream);
+
+/* Weight / bias gradient of the transform: dW[g][o][k] (w_layout 0) or dW[g][k][o]
+ * (w_layout 1) (+)= sum_r G[r, g*Fout+o] * X[r, g*Fin+k], dbias[g*Fout+o] (+)= sum_r G[r,..].
+ * G may be masked by (mask > 0) (fused ReLU backward).  Two-phase deterministic reduction:
+ * partials [n_chunks, groups*Fout*(Fin+1)] in `work`, then a fixed-order sum.
+ * accumulate != 0 adds into dW / dbias, else overwrites. */
+typedef struct drgnn_linear_wgrad_args {
+  const float* X; int32_t ldx;
+  const float* G; int32_t ldg;
+  const float* mask; int32_t ld_mask;
+  float* dW; float* dbias;
+  int32_t rows; const int32_t* rows_dev;
+  int32_t Fin; int32_t Fout; int32_t groups;
+  int32_t w_layout; int32_t accumulate;
+  float* work; int64_t work_floats;
+} drgnn_linear_wgrad_args;
+int64_t drgnn_linear_wgrad_work_floats(int32_t rows, int32_t Fin, int32_t Fout, int32_t groups);
+int drgnn_linear_wgrad(const drgnn_linear_wgrad_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Cluster max-pool (torch_scatter.scatter_max, community_pooling.py:201; PyG max_pool_x)
+ *    y[k,c] = max_{i in members(k)} x[i,c]; argmax[k,c] = FIRST member attaining it.
+ *    Backward routes the gradient to argmax only:
+ *    dx[i,c] = (argmax[cl[i],c] == i) ? g[cl[i],c] : 0, optionally times (relu_out[i,c] > 0).
+ * ---------------------------------------------------------------------------------- */
+int drgnn_maxpool_fwd(const float* x, int32_t ldx, const int32_t* cmptr, const int32_t* cmem,
+                      int32_t n_clusters, const int32_t* n_clusters_dev, int32_t C,
+                      float* y, int32_t ldy, int32_t* argmax, void* stream);
+int drgnn_maxpool_bwd(const float* g, int32_t ldg, const int32_t* argmax, const int32_t* cl,
+                      const float* relu_out, int32_t ld_relu, int32_t n_nodes,
+                      const int32_t* n_nodes_dev, int32_t C, float* dx, int32_t lddx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 5. Graph read-out (torch_scatter.scatter_mean(x, batch), ginet.py:133-134, sGAT.py:133,
+ *    foutnet.py:120): r[b,:] = mean of rows seg_ptr[b]..seg_ptr[b+1] (0 for empty).
+ *    Backward: dx[k,:] = g[b(k),:] / max(count_b,1).
+ * ---------------------------------------------------------------------------------- */
+int drgnn_segment_mean_fwd(const float* x, int32_t ldx, const int32_t* seg_ptr, int32_t B, int32_t C,
+                           float* r, int32_t ldr, void* stream);
+int drgnn_segment_mean_bwd(const float* g, int32_t ldg, const int32_t* seg_ptr, int32_t B, int32_t C,
+                           float* dx, int32_t lddx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 6. Loss, optimiser (NeuralNet.py:239-263, 500-503): fused loss + dLoss/dpred, flat Adam.
+ *    mse:  loss = mean_b (pred_b - y_b)^2 over B_global ;   dpred = 2 (pred - y) / B_global
+ *    ce :  weighted CrossEntropyLoss(reduction='mean'); dlogits accordingly.
+ *    loss_out[0] receives the LOCAL contribution sum_b(...)/B_global (all-reduce it to get
+ *    the global mean when the batch is sharded over ranks).
+ * ---------------------------------------------------------------------------------- */
+int drgnn_mse_loss(const float* pred, const float* y, int32_t B_local, float inv_B_global,
+                   int32_t sigmoid, float* loss_out, float* dpred, void* stream);
+int drgnn_ce_loss(const float* logits, int32_t ld, const int64_t* target, const float* class_w,
+                  int32_t B_local, int32_t n_classes, float inv_norm_global, float* loss_out,
+                  float* dlogits, void* stream);
+/* torch.optim.Adam (no weight decay, no amsgrad): step_dev[0] holds the step count (float,
+ * incremented on the device so the call is CUDA-graph replayable). grad_scale multiplies g. */
+int drgnn_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    float* step_dev, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float grad_scale, void* stream);
+
+/* small utilities used by the host layer */
+int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,
+                    const int32_t* rows_dev, int32_t C, float* gz, int32_t ldgz, void* stream);
+int drgnn_fill_f32(float* p, float v, int64_t n, void* stream);
+int drgnn_fill_i32(int32_t* p, int32_t v, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRGNN_H */
