@@ -1,0 +1,172 @@
+"""ctypes binding of ``libdrgnn.so`` (C-ABI declared in ``include/drgnn.h``).
+
+There is no CPU fallback: if the library is missing or does not export a symbol the
+import of anything that computes raises.  Structures mirror the header field by field.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libdrgnn.so')
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f32p = C.POINTER(C.c_float)
+VP = C.c_void_p
+
+ST_EDGE_OUTSIDE_GRAPH = 1
+ST_CLUSTER_RANGE = 2
+ST_CLUSTER1_LENGTH = 4
+ST_CLUSTER_ORDER = 8
+ST_NEGATIVE_ID = 16
+STATUS_TEXT = {
+    ST_EDGE_OUTSIDE_GRAPH: 'an edge endpoint lies outside its graph',
+    ST_CLUSTER_RANGE: 'cluster-id range of one graph exceeds 32768',
+    ST_CLUSTER1_LENGTH: 'len(cluster1) of a graph differs from its number of level-0 clusters',
+    ST_CLUSTER_ORDER: 'global cluster ids do not increase with the graph id',
+    ST_NEGATIVE_ID: 'negative cluster id',
+}
+
+
+class StructureIO(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('N', C.c_int32), ('E', C.c_int32), ('L1', C.c_int32), ('ne', C.c_int32),
+        ('max_n', C.c_int32), ('max_e', C.c_int32), ('clusters_are_local', C.c_int32),
+        ('idx32', C.c_int32), ('reserved0', C.c_int32),
+        ('node_ptr', VP), ('edge_ptr', VP), ('c1_ptr', VP), ('edge_index', VP), ('edge_attr', VP),
+        ('cluster0', VP), ('cluster1', VP),
+        ('rowptr0', VP), ('col0', VP), ('eid0', VP), ('cscptr0', VP), ('cscrow0', VP), ('csceid0', VP),
+        ('w0csr', VP), ('w0csc', VP),
+        ('cl0', VP), ('cl0_i64', VP), ('cmptr0', VP), ('cmem0', VP), ('kptr0', VP), ('batch1', VP),
+        ('batch1_i64', VP),
+        ('rowptr1', VP), ('col1', VP), ('edge_index1', VP), ('edge_attr1', VP), ('cscptr1', VP),
+        ('cscrow1', VP), ('csceid1', VP), ('w1csc', VP),
+        ('cl1', VP), ('cmptr1', VP), ('cmem1', VP), ('kptr1', VP), ('batch2', VP), ('batch2_i64', VP),
+        ('counts', VP), ('status', VP),
+        ('gstat', VP), ('scratch_n', VP), ('scratch_e', VP), ('scratch_f', VP),
+    ]
+
+
+class AggregateArgs(C.Structure):
+    _fields_ = [
+        ('src', VP), ('ld_src', C.c_int32),
+        ('out', VP), ('ld_out', C.c_int32),
+        ('rowptr', VP), ('col', VP),
+        ('ew', VP), ('sscale', VP),
+        ('self_src', VP), ('ld_self', C.c_int32),
+        ('self_out', VP), ('ld_self_out', C.c_int32),
+        ('selfc_in', VP), ('selfc_out', VP),
+        ('post_out', VP),
+        ('bias', VP),
+        ('n_rows', C.c_int32), ('n_rows_dev', VP),
+        ('C', C.c_int32), ('post_mode', C.c_int32), ('self_mode', C.c_int32), ('relu', C.c_int32),
+    ]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ('X', VP), ('ldx', C.c_int32),
+        ('W', VP), ('bias', VP),
+        ('Y', VP), ('ldy', C.c_int32),
+        ('out_mask', VP), ('ld_mask', C.c_int32), ('mask_scale', C.c_float),
+        ('rows', C.c_int32), ('rows_dev', VP),
+        ('Fin', C.c_int32), ('Fout', C.c_int32), ('groups', C.c_int32),
+        ('w_layout', C.c_int32), ('relu', C.c_int32), ('math', C.c_int32),
+    ]
+
+
+class LinearWgradArgs(C.Structure):
+    _fields_ = [
+        ('X', VP), ('ldx', C.c_int32),
+        ('G', VP), ('ldg', C.c_int32),
+        ('dW', VP), ('dbias', VP),
+        ('rows', C.c_int32), ('rows_dev', VP),
+        ('Fin', C.c_int32), ('Fout', C.c_int32), ('groups', C.c_int32),
+        ('w_layout', C.c_int32), ('accumulate', C.c_int32),
+        ('work', VP), ('work_floats', C.c_int64),
+    ]
+
+
+_i32, _i64, _f32 = C.c_int32, C.c_int64, C.c_float
+_SIGNATURES = {
+    'drgnn_last_error': (C.c_char_p, []),
+    'drgnn_version': (C.c_int, []),
+    'drgnn_device_sms': (C.c_int, []),
+    'drgnn_device_smem_optin': (C.c_int, []),
+    'drgnn_structure_smem_bytes': (_i64, [_i32, _i32, _i32]),
+    'drgnn_structure_build': (C.c_int, [C.POINTER(StructureIO), VP]),
+    'drgnn_cluster_offset': (C.c_int, [VP, VP, _i32, VP, VP]),
+    'drgnn_ptr_from_sorted_ids': (C.c_int, [VP, _i32, _i32, VP, VP, VP]),
+    'drgnn_aggregate': (C.c_int, [C.POINTER(AggregateArgs), VP]),
+    'drgnn_aggregate_tiled': (C.c_int, [C.POINTER(AggregateArgs), VP, _i32, _i32, VP]),
+    'drgnn_linear': (C.c_int, [C.POINTER(LinearArgs), VP]),
+    'drgnn_linear_wgrad_work_floats': (_i64, [_i32, _i32, _i32, _i32]),
+    'drgnn_linear_wgrad': (C.c_int, [C.POINTER(LinearWgradArgs), VP]),
+    'drgnn_maxpool_fwd': (C.c_int, [VP, _i32, VP, VP, _i32, VP, _i32, VP, _i32, VP, VP]),
+    'drgnn_maxpool_bwd': (C.c_int, [VP, _i32, VP, VP, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
+    'drgnn_segment_mean_fwd': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP]),
+    'drgnn_segment_mean_bwd': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP]),
+    'drgnn_mse_loss': (C.c_int, [VP, VP, _i32, _f32, _i32, VP, VP, VP]),
+    'drgnn_ce_loss': (C.c_int, [VP, _i32, VP, VP, _i32, _i32, _f32, VP, VP, VP]),
+    'drgnn_adam_flat': (C.c_int, [VP, VP, VP, VP, VP, _i64, _f32, _f32, _f32, _f32, _f32, VP]),
+    'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
+    'drgnn_fill_f32': (C.c_int, [VP, _f32, _i64, VP]),
+    'drgnn_fill_i32': (C.c_int, [VP, _i32, _i64, VP]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+_lib = None
+launch_count = 0           # number of C-ABI compute calls made by this process (bench: gpu_launches)
+
+
+class DrgnnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdrgnn.so (once).  Raises if it has not been built - there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DrgnnError('libdrgnn.so is missing (%s): build it with `python -m deeprank_gnn_b200.build` '
+                         'or __graft_entry__.build(); this package has no CPU / eager fallback' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().drgnn_last_error()
+        raise DrgnnError('%s failed (code %d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DrgnnError('the hot path runs on CUDA only (got a %s tensor); there is no CPU fallback' % t.device)
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point, raising DrgnnError on a non-zero status."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    launch_count += 1
+    check(rc, name)

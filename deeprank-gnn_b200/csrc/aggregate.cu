@@ -83,6 +83,7 @@ __device__ __forceinline__ void aggregate_row(const drgnn_aggregate_args& a, int
   else if (a.self_mode == 2) selfc = post * wsum;
   else if (a.self_mode == 3) selfc = __ldg(a.selfc_in + row);
   if (a.self_mode == 2 && a.selfc_out && sl == 0) a.selfc_out[row] = selfc;
+  if (a.post_out && sl == 0) a.post_out[row] = post;
   if (!on) return;
   if (a.self_mode != 0 && a.self_src) {
     const float4 sv = *reinterpret_cast<const float4*>(a.self_src + (int64_t)row * a.ld_self + sl * 4);
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_scalar_kernel(const drgnn_
     else if (a.self_mode == 2) selfc = post * wsum;
     else if (a.self_mode == 3) selfc = a.selfc_in[row];
     if (a.self_mode == 2 && a.selfc_out && lane == 0) a.selfc_out[row] = selfc;
+    if (a.post_out && lane == 0) a.post_out[row] = post;
     for (int ch = lane; ch < a.C; ch += 32) {
       float acc = 0.f;
       for (int p = s; p < e; ++p) {
@@ -296,8 +298,8 @@ static int launch_tiled(const AggParams& P, int blocks, size_t smem, cudaStream_
   static thread_local size_t configured = 0;
   if (smem > configured) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tiled_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)device_info().smem_optin));
-    configured = device_info().smem_optin;
+                                          (int)device_info().smem_optin - 2048));
+    configured = device_info().smem_optin - 2048;
   }
   aggregate_tiled_kernel<G><<<blocks, 256, smem, st>>>(P);
   DRGNN_CHECK_LAUNCH("aggregate_tiled_kernel");
@@ -314,7 +316,7 @@ extern "C" int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_
   if (!vector_ok(*a) || a->ld_src != a->C)
     return fail(DRGNN_ERR_UNSUPPORTED, "aggregate_tiled: needs C %% 4 == 0, C <= 128, ld_src == C, 16-byte alignment");
   const size_t smem = (size_t)2 * max_tile_rows * a->C * sizeof(float);
-  if (smem > (size_t)device_info().smem_optin - 1024)
+  if (smem > (size_t)device_info().smem_optin - 2048)
     return fail(DRGNN_ERR_UNSUPPORTED, "aggregate_tiled: tile of %d rows x %d channels does not fit shared memory",
                 max_tile_rows, a->C);
   AggParams P;
@@ -324,7 +326,7 @@ extern "C" int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_
   P.max_tile_rows = max_tile_rows;
   const int sms = device_info().sms;
   // CTAs per SM limited by the double buffer; 227 KB usable per SM
-  int per_sm = (int)min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024));
+  int per_sm = (int)min_i64(8, (size_t)(227 * 1024) / (smem + 1024));
   per_sm = max(per_sm, 1);
   const int blocks = min(n_tiles, sms * per_sm);
   cudaStream_t st = (cudaStream_t)stream;

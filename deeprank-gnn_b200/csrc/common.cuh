@@ -39,6 +39,8 @@ inline int fail(int code, const char* fmt, ...) {
     if (!(cond)) return drgnn::fail(DRGNN_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+static inline int64_t min_i64(int64_t a, int64_t b) { return a < b ? a : b; }
+
 struct DeviceInfo {
   int sms;
   int smem_optin;

@@ -21,7 +21,8 @@ namespace drgnn {
 
 static constexpr int kThreads = 512;
 static constexpr int kWarps = kThreads / 32;
-static constexpr int kCapWords = 1024;  // presence bitmap: cluster-id range per graph <= 32768
+static constexpr int kCapWords = 1024;
+static constexpr int kStaticSmemReserve = 2048;  // static __shared__ of the kernels counts against the opt-in limit  // presence bitmap: cluster-id range per graph <= 32768
 
 struct SmemPlan {
   // byte offsets into dynamic shared memory
@@ -31,6 +32,11 @@ struct SmemPlan {
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+// edge_index / cluster ids arrive as int64 (reference tensors) or int32 (packed feeder batches)
+__device__ __forceinline__ long long ld_id(const void* base, int64_t i, int idx32) {
+  return idx32 ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
+}
 
 __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) {
   SmemPlan p;
@@ -122,12 +128,12 @@ __device__ void csr_build(const uint16_t* key, int m, int n, int* ptr, uint16_t*
 // Dense relabel of `n` int64 ids (sorted-unique rank, i.e. consecutive_cluster's inverse
 // restricted to one graph).  Returns K; writes min / max of the raw ids.
 // ---------------------------------------------------------------------------------------
-__device__ int relabel(const int64_t* ids, int n, uint16_t* dense, uint32_t* cbits, int* cpre, int* wsum,
+__device__ int relabel(const void* ids_base, int64_t ids_off, int idx32, int n, uint16_t* dense, uint32_t* cbits, int* cpre, int* wsum,
                        long long* red, int32_t* status, long long* out_min, long long* out_max) {
   const int T = blockDim.x, t = threadIdx.x;
   long long mn = LLONG_MAX, mx = LLONG_MIN;
   for (int i = t; i < n; i += T) {
-    long long v = ids[i];
+    long long v = ld_id(ids_base, ids_off + i, idx32);
     mn = v < mn ? v : mn;
     mx = v > mx ? v : mx;
   }
@@ -164,7 +170,7 @@ __device__ int relabel(const int64_t* ids, int n, uint16_t* dense, uint32_t* cbi
   for (int w = t; w < W; w += T) cbits[w] = 0u;
   __syncthreads();
   for (int i = t; i < n; i += T) {
-    int v = (int)(ids[i] - mn);
+    int v = (int)(ld_id(ids_base, ids_off + i, idx32) - mn);
     atomicOr(&cbits[v >> 5], 1u << (v & 31));
   }
   __syncthreads();
@@ -172,7 +178,7 @@ __device__ int relabel(const int64_t* ids, int n, uint16_t* dense, uint32_t* cbi
   __syncthreads();
   int K = block_exclusive_scan(cpre, W, wsum);
   for (int i = t; i < n; i += T) {
-    int v = (int)(ids[i] - mn);
+    int v = (int)(ld_id(ids_base, ids_off + i, idx32) - mn);
     dense[i] = (uint16_t)(cpre[v >> 5] + __popc(cbits[v >> 5] & ((1u << (v & 31)) - 1u)));
   }
   __syncthreads();
@@ -232,8 +238,8 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
 
   // ---- 1. local edge list ----
   for (int e = t; e < m; e += T) {
-    long long r = io.edge_index[e0 + e] - n0;
-    long long c = io.edge_index[(int64_t)io.E + e0 + e] - n0;
+    long long r = ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
+    long long c = ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
     if (r < 0 || r >= n || c < 0 || c >= n) {
       atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
       r = 0;
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
 
   // ---- 4. relabel level-0 clusters ----
   long long cmin, cmax;
-  const int K = relabel(io.cluster0 + n0, n, dense0, cbits, cpre, wsum, red, io.status, &cmin, &cmax);
+  const int K = relabel(io.cluster0, n0, io.idx32, n, dense0, cbits, cpre, wsum, red, io.status, &cmin, &cmax);
   for (int i = t; i < n; i += T) io.cl0[n0 + i] = dense0[i];  // local; finalize adds the graph offset
 
   // ---- 5. members of every cluster (ascending node id) ----
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     }
     c1len = min(c1len, io.max_n);  // shared-memory bound (only reachable for invalid input)
     long long mn1, mx1;
-    K1 = relabel(io.cluster1 + c0, c1len, dense1, cbits, cpre, wsum, red, io.status, &mn1, &mx1);
+    K1 = relabel(io.cluster1, c0, io.idx32, c1len, dense1, cbits, cpre, wsum, red, io.status, &mn1, &mx1);
     for (int k = t; k < c1len; k += T) io.cl1[c0 + k] = dense1[k];
     csr_build(dense1, c1len, K1, mptr1, mem1, wsum);
     for (int q = t; q <= K1; q += T) S.mptr1[c0 + g + q] = mptr1[q];
@@ -564,7 +570,7 @@ extern "C" int64_t drgnn_structure_smem_bytes(int32_t max_n, int32_t max_e, int3
   if (max_n < 0 || max_e < 0) return DRGNN_ERR_INVALID;
   if (max_n > 65535 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;
   SmemPlan p = make_plan(max_n, max_e, max_c1);
-  if (p.total > device_info().smem_optin) return DRGNN_ERR_UNSUPPORTED;
+  if (p.total > device_info().smem_optin - kStaticSmemReserve) return DRGNN_ERR_UNSUPPORTED;
   return p.total;
 }
 
@@ -597,8 +603,8 @@ extern "C" int drgnn_structure_build(const drgnn_structure_io* io, void* stream)
   static thread_local int64_t configured = -1;
   if (smem > configured) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(graph_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)device_info().smem_optin));
-    configured = device_info().smem_optin;
+                                          (int)device_info().smem_optin - kStaticSmemReserve));
+    configured = device_info().smem_optin - kStaticSmemReserve;
   }
   cudaStream_t st = (cudaStream_t)stream;
   graph_local_kernel<<<io->B, kThreads, smem, st>>>(*io);

@@ -97,6 +97,9 @@ class Batch(Data):
         self._num_graphs = None
         self._node_ptr = None      # int32 [B+1], same device as the tensors
         self._edge_ptr = None      # int32 [B+1]
+        self._c1_ptr = None        # int32 [B+1] segments of cluster1 (None without clusters)
+        self._max_n = None         # host ints: largest graph (nodes / directed edges)
+        self._max_e = None
 
     @property
     def num_graphs(self):
@@ -113,8 +116,9 @@ class Batch(Data):
         keys = data_list[0].keys
         out = Batch()
         cols = {k: [] for k in keys}
-        batch, node_ptr, edge_ptr = [], [0], [0]
+        batch, node_ptr, edge_ptr, c1_ptr = [], [0], [0], [0]
         cum = 0
+        has_c1 = 'cluster1' in keys
         for i, d in enumerate(data_list):
             n = d.num_nodes
             for k in keys:
@@ -126,6 +130,8 @@ class Batch(Data):
             cum += n
             node_ptr.append(cum)
             edge_ptr.append(edge_ptr[-1] + d.num_edges)
+            if has_c1:
+                c1_ptr.append(c1_ptr[-1] + d['cluster1'].numel())
         for k in keys:
             items = cols[k]
             if torch.is_tensor(items[0]):
@@ -136,7 +142,109 @@ class Batch(Data):
         out._num_graphs = len(data_list)
         out._node_ptr = torch.tensor(node_ptr, dtype=torch.int32)
         out._edge_ptr = torch.tensor(edge_ptr, dtype=torch.int32)
+        out._c1_ptr = torch.tensor(c1_ptr, dtype=torch.int32) if has_c1 else None
+        out._max_n = max(b - a for a, b in zip(node_ptr[:-1], node_ptr[1:]))
+        out._max_e = max(b - a for a, b in zip(edge_ptr[:-1], edge_ptr[1:]))
         return out
+
+
+def _pad4(n):
+    return (n + 3) & ~3
+
+
+class PackedBatch(object):
+    """One mini-batch in a single contiguous host block (pinned when a GPU is present), ready
+    for ONE host->device copy: the feeder-side replacement of ``data_batch.to(device)``
+    (``NeuralNet.py:491``), which moves ~10 tensors separately.  Indices are int32.
+
+    Sections (each padded to 16 bytes), all 4-byte elements viewed from one float32 buffer:
+    ``x[N,F] edge_attr[E,ne] y[B] | edge_index[2,E] cluster0[N] cluster1[L1] node_ptr[B+1]
+    edge_ptr[B+1] c1_ptr[B+1] | y_class[B] (int64, classification only)``.
+    """
+    FLOAT_SECTIONS = ('x', 'edge_attr', 'y')
+    INT_SECTIONS = ('edge_index', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr')
+
+    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False):
+        self.B, self.N, self.E, self.L1, self.F, self.ne = B, N, E, L1, F, ne
+        self.max_n, self.max_e = max_n, max_e
+        self.with_class = with_class
+        sizes = dict(x=N * F, edge_attr=E * ne, y=B, edge_index=2 * E, cluster0=N, cluster1=L1, node_ptr=B + 1,
+                     edge_ptr=B + 1, c1_ptr=B + 1)
+        self.offsets = {}
+        o = 0
+        for k in self.FLOAT_SECTIONS + self.INT_SECTIONS:
+            self.offsets[k] = (o, sizes[k])
+            o += _pad4(sizes[k])
+        if with_class:
+            self.offsets['y_class'] = (o, 2 * B)
+            o += _pad4(2 * B)
+        self.numel = o
+        self.buf = None
+        self.mol = None
+
+    def key(self):
+        return (self.B, self.N, self.E, self.L1, self.F, self.ne, self.max_n, self.max_e, self.with_class)
+
+    @property
+    def nbytes(self):
+        return 4 * self.numel
+
+    def views(self, buf):
+        """Typed views of the sections inside ``buf`` (a float32 tensor of ``numel`` elements,
+        host or device)."""
+        v = {}
+        for k in self.FLOAT_SECTIONS:
+            o, n = self.offsets[k]
+            v[k] = buf[o:o + n]
+        ibuf = buf.view(torch.int32)
+        for k in self.INT_SECTIONS:
+            o, n = self.offsets[k]
+            v[k] = ibuf[o:o + n]
+        v['x'] = v['x'].view(self.N, self.F)
+        v['edge_attr'] = v['edge_attr'].view(self.E, self.ne) if self.ne else None
+        v['edge_index'] = v['edge_index'].view(2, self.E)
+        if self.with_class:
+            o, n = self.offsets['y_class']
+            v['y_class'] = ibuf[o:o + n].view(torch.int64)
+        else:
+            v['y_class'] = None
+        return v
+
+    @staticmethod
+    def from_batch(batch, pin=None, classes=None):
+        """Pack a collated ``Batch``.  ``classes``: for classification, the class list used to
+        map targets to class indices (``format_output``, NeuralNet.py:616-631)."""
+        if batch._node_ptr is None or batch._c1_ptr is None:
+            raise ValueError('PackedBatch needs a Batch collated by Batch.from_data_list with cluster0/cluster1')
+        x = batch.x
+        ea = getattr(batch, 'edge_attr', None)
+        if ea is not None and ea.dim() == 1:
+            ea = ea.unsqueeze(-1)
+        N, F = x.size(0), (x.size(1) if x.dim() == 2 else 1)
+        E = batch.edge_index.size(1)
+        ne = 0 if ea is None else ea.size(1)
+        pb = PackedBatch(batch.num_graphs, N, E, batch.cluster1.numel(), F, ne, batch._max_n, batch._max_e,
+                         with_class=classes is not None)
+        pin = torch.cuda.is_available() if pin is None else pin
+        pb.buf = torch.zeros(pb.numel, dtype=torch.float32, pin_memory=bool(pin))
+        v = pb.views(pb.buf)
+        v['x'].copy_(x.reshape(N, F))
+        if ne:
+            v['edge_attr'].copy_(ea)
+        y = getattr(batch, 'y', None)
+        if y is not None:
+            v['y'].copy_(y.reshape(-1))
+            if classes is not None:
+                c2i = {int(c): i for i, c in enumerate(classes)}
+                v['y_class'].copy_(torch.tensor([c2i[int(t)] for t in y.reshape(-1).tolist()], dtype=torch.int64))
+        v['edge_index'].copy_(batch.edge_index)
+        v['cluster0'].copy_(batch.cluster0)
+        v['cluster1'].copy_(batch.cluster1)
+        v['node_ptr'].copy_(batch._node_ptr)
+        v['edge_ptr'].copy_(batch._edge_ptr)
+        v['c1_ptr'].copy_(batch._c1_ptr)
+        pb.mol = getattr(batch, 'mol', None)
+        return pb
 
 
 class DataLoader(object):

@@ -1,0 +1,576 @@
+"""Fused training / scoring engine for the reference networks (GINet, sGAT, FoutNet).
+
+It replaces the body of the reference's per-batch loop (``NeuralNet._epoch``,
+``deeprank_gnn/NeuralNet.py:490-503``: zero_grad, ``model(batch)``, ``format_output``,
+loss, ``backward``, ``Adam.step``) by a fixed sequence of C-ABI kernel launches over flat,
+pre-allocated buffers:
+
+    structure pass (2 launches, integer)        get_preloaded_cluster / consecutive_cluster /
+                                                 pool_edge / pool_batch   community_pooling.py:25-30,197-224
+    conv1 = aggregate -> transform(+ReLU)       ginet.py:50-73 | sGAT.py:62-93 | foutnet.py:56-82
+    cluster max-pool (level 0)                  community_pooling.py:201
+    conv2 = aggregate -> transform(+ReLU)       on the coarsened graph
+    cluster max-pool (level 1)                  max_pool_x (ginet.py:114,129)
+    graph mean read-out, fc1(+ReLU,+dropout), fc2   ginet.py:133-139
+    loss + dLoss/dpred, hand-written backward, [NCCL all-reduce], flat Adam
+
+Both GINet branches run in the same launches (their graphs are identical):
+conv1 shares the aggregated input and concatenates the two weights, conv2 is a 2-group
+transform.  No host synchronisation happens inside a step, so the launch sequence can be
+captured in a CUDA graph (``graph=True``) and replayed.
+
+Parameters live in one flat fp32 buffer; ``state_dict()`` / ``load_state_dict()`` use the
+reference's names and shapes, so reference checkpoints load unchanged.
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from ._lib import DrgnnError
+
+F32, I32, I64 = torch.float32, torch.int32, torch.int64
+
+
+class NetSpec(object):
+    """Architecture description of one of the reference networks."""
+
+    def __init__(self, kind, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), dropout=None):
+        kind = {'GINet': 'ginet', 'sGAT': 'sgat', 'FoutNet': 'fout'}.get(kind, kind).lower()
+        if kind not in ('ginet', 'sgat', 'fout'):
+            raise ValueError('unknown network %r (GINet, sGAT or FoutNet)' % kind)
+        self.kind = kind
+        self.F = int(input_shape)
+        self.out = int(output_shape)
+        self.ne = int(input_shape_edge) if input_shape_edge else 1
+        self.h1, self.h2 = int(hidden[0]), int(hidden[1])
+        if self.h1 % 4 or self.h2 % 4:
+            raise ValueError('hidden widths must be multiples of 4')
+        self.nb = 2 if kind == 'ginet' else 1                 # branches
+        self.C1, self.C2 = self.nb * self.h1, self.nb * self.h2
+        self.Kin1 = self.F if kind == 'ginet' else 2 * self.F
+        self.Kin2 = self.C1 if kind == 'ginet' else 2 * self.h1
+        self.Hd = 4 * self.h2 if kind == 'ginet' else 2 * self.h2     # fc1 width (ginet.py:94, sGAT.py:109)
+        self.dropout = (0.4 if kind == 'ginet' else 0.0) if dropout is None else float(dropout)   # ginet.py:97
+        self.w_layout = 0 if kind == 'ginet' else 1
+
+    def param_shapes(self):
+        """Flat layout: (reference state_dict name, shape, live?) in storage order."""
+        F, h1, h2, out, ne, Hd = self.F, self.h1, self.h2, self.out, self.ne, self.Hd
+        if self.kind == 'ginet':
+            p = [('conv1.fc.weight', (h1, F), True), ('conv1_ext.fc.weight', (h1, F), True),
+                 ('conv2.fc.weight', (h2, h1), True), ('conv2_ext.fc.weight', (h2, h1), True),
+                 ('fc1.weight', (Hd, 2 * h2), True), ('fc1.bias', (Hd,), True),
+                 ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
+            # parameters of the dead attention path (alpha == 1): zero gradient
+            for name, cin, cout in (('conv1', F, h1), ('conv2', h1, h2), ('conv1_ext', F, h1), ('conv2_ext', h1, h2)):
+                p.append((name + '.fc_edge_attr.weight', (ne, ne), False))
+                p.append((name + '.fc_attention.weight', (1, 2 * cout + ne), False))
+        elif self.kind == 'sgat':
+            p = [('conv1.weight', (2 * F, h1), True), ('conv1.bias', (h1,), True),
+                 ('conv2.weight', (2 * h1, h2), True), ('conv2.bias', (h2,), True),
+                 ('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
+                 ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
+        else:
+            p = [('conv1.Wc', (F, h1), True), ('conv1.Wn', (F, h1), True), ('conv1.bias', (h1,), True),
+                 ('conv2.Wc', (h1, h2), True), ('conv2.Wn', (h1, h2), True), ('conv2.bias', (h2,), True),
+                 ('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
+                 ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
+        return p
+
+    # names in the order the reference's nn.Module registers them (state_dict order)
+    def reference_order(self):
+        if self.kind == 'ginet':
+            names = []
+            for c in ('conv1', 'conv2', 'conv1_ext', 'conv2_ext'):
+                names += [c + '.fc.weight', c + '.fc_edge_attr.weight', c + '.fc_attention.weight']
+            return names + ['fc1.weight', 'fc1.bias', 'fc2.weight', 'fc2.bias']
+        if self.kind == 'sgat':
+            return ['conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'fc1.weight', 'fc1.bias',
+                    'fc2.weight', 'fc2.bias']
+        return ['conv1.Wc', 'conv1.Wn', 'conv1.bias', 'conv2.Wc', 'conv2.Wn', 'conv2.bias', 'fc1.weight', 'fc1.bias',
+                'fc2.weight', 'fc2.bias']
+
+
+def _pad4(n):
+    return (n + 3) & ~3
+
+
+class FlatParams(object):
+    """One fp32 buffer holding every parameter, with named views."""
+
+    def __init__(self, spec, device):
+        self.spec = spec
+        self.slots = OrderedDict()
+        o = 0
+        for name, shape, live in spec.param_shapes():
+            n = 1
+            for s in shape:
+                n *= s
+            self.slots[name] = (o, n, shape, live)
+            # conv weight pairs (GINet branches, Fout Wc/Wn) are consumed as ONE matrix and must stay
+            # adjacent: their sizes are multiples of 4 (hidden widths are), so the padding is a no-op
+            if name.split('.')[0].startswith('conv') and live and len(shape) == 2:
+                assert n % 4 == 0
+            o += _pad4(n)
+        self.numel = _pad4(o)
+        self.data = torch.zeros(self.numel, dtype=F32, device=device)
+
+    def view(self, buf, name):
+        o, n, shape, _ = self.slots[name]
+        return buf[o:o + n].view(shape)
+
+    def offset(self, name):
+        return self.slots[name][0]
+
+
+class Workspace(object):
+    """Activation / gradient buffers for batches up to (B, N, E) - allocated once, reused."""
+
+    def __init__(self, spec, B, N, E, device):
+        s = spec
+        self.B, self.N, self.E = B, N, E
+        z = lambda *shape: torch.zeros(*shape, dtype=F32, device=device)
+        self.Zin1 = z(N, s.Kin1)
+        self.Z1 = z(N, s.C1)
+        self.P1 = z(N, s.C1)
+        self.arg0 = torch.zeros(N, s.C1, dtype=I32, device=device)
+        self.Zin2 = z(N, s.Kin2)
+        self.Z2 = z(N, s.C2)
+        self.P2 = z(N, s.C2)
+        self.arg1 = torch.zeros(N, s.C2, dtype=I32, device=device)
+        self.R = z(B, s.C2)
+        self.H = z(B, s.Hd)
+        self.pred = z(B, s.out)
+        self.keep = z(B, s.Hd)
+        self.loss = z(1)
+        # per-row scalars of the mean aggregations (sGAT / Fout)
+        self.s0, self.post0, self.s1, self.post1 = z(N), z(N), z(N), z(N)
+        # gradients
+        self.dpred = z(B, s.out)
+        self.dH = z(B, s.Hd)
+        self.dR = z(B, s.C2)
+        self.dP2 = z(N, s.C2)
+        self.dZ2 = z(N, s.C2)
+        self.dZin2 = z(N, s.Kin2)
+        self.dP1 = z(N, s.C1)
+        self.dZ1 = z(N, s.C1)
+        need = max(ops.linear_wgrad_work_floats(N, s.Kin1, s.C1, 1),
+                   ops.linear_wgrad_work_floats(N, s.Kin2 // (s.nb if s.kind == 'ginet' else 1), s.h2, s.nb),
+                   ops.linear_wgrad_work_floats(B, s.C2, s.Hd, 1),
+                   ops.linear_wgrad_work_floats(B, s.Hd, s.out, 1))
+        self.wwork = z(need)
+
+
+class DeviceBatch(object):
+    """The tensors of one mini-batch the engine consumes, resident on the device."""
+    __slots__ = ('x', 'edge_index', 'edge_attr', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr', 'y',
+                 'y_class', 'B', 'N', 'E', 'L1', 'max_n', 'max_e', 'mol', 'key')
+
+    @staticmethod
+    def from_batch(batch, device, classes=None):
+        """From a collated ``Batch`` (``data.Batch.from_data_list``), reference dtypes (int64
+        indices).  ``classes``: class list for classification targets (NeuralNet.py:616-631)."""
+        d = DeviceBatch()
+        if getattr(batch, '_node_ptr', None) is None or getattr(batch, '_edge_ptr', None) is None:
+            raise DrgnnError('the engine needs a Batch collated by Batch.from_data_list (graph pointers)')
+        if getattr(batch, 'cluster0', None) is None or getattr(batch, 'cluster1', None) is None:
+            raise DrgnnError('the batch carries no cluster0 / cluster1 (run PreCluster first, DataSet.py:45-88)')
+        mv = lambda t: None if t is None else t.to(device, non_blocking=True)
+        x = batch.x if batch.x.dim() == 2 else batch.x.unsqueeze(-1)
+        d.x = mv(x).float().contiguous()
+        d.edge_index = mv(batch.edge_index).contiguous()
+        ea = getattr(batch, 'edge_attr', None)
+        if ea is not None:
+            ea = mv(ea).float()
+            ea = ea.unsqueeze(-1) if ea.dim() == 1 else ea
+            ea = ea.contiguous()
+        d.edge_attr = ea
+        d.cluster0, d.cluster1 = mv(batch.cluster0).contiguous(), mv(batch.cluster1).contiguous()
+        d.node_ptr, d.edge_ptr = mv(batch._node_ptr), mv(batch._edge_ptr)
+        d.c1_ptr = mv(batch._c1_ptr)
+        y = getattr(batch, 'y', None)
+        d.y = None if y is None else mv(y.float().reshape(-1).contiguous())
+        d.y_class = None
+        if classes is not None and y is not None:
+            c2i = {int(c): i for i, c in enumerate(classes)}
+            d.y_class = mv(torch.tensor([c2i[int(t)] for t in y.reshape(-1).tolist()], dtype=I64))
+        d.B, d.N, d.E, d.L1 = batch.num_graphs, d.x.size(0), d.edge_index.size(1), d.cluster1.numel()
+        d.max_n, d.max_e = int(batch._max_n), int(batch._max_e)
+        d.mol = getattr(batch, 'mol', None)
+        d.key = None
+        return d
+
+    @staticmethod
+    def from_packed(pb, dev_buf):
+        """Views into ``dev_buf`` (device float32 buffer holding a copy of ``pb.buf``)."""
+        d = DeviceBatch()
+        v = pb.views(dev_buf)
+        d.x, d.edge_attr, d.y, d.y_class = v['x'], v['edge_attr'], v['y'], v['y_class']
+        d.edge_index, d.cluster0, d.cluster1 = v['edge_index'], v['cluster0'], v['cluster1']
+        d.node_ptr, d.edge_ptr, d.c1_ptr = v['node_ptr'], v['edge_ptr'], v['c1_ptr']
+        d.B, d.N, d.E, d.L1, d.max_n, d.max_e = pb.B, pb.N, pb.E, pb.L1, pb.max_n, pb.max_e
+        d.mol = pb.mol
+        d.key = pb.key()
+        return d
+
+
+class Engine(object):
+    def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
+                 task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
+                 dropout=None, graph=False, tiled=False, process_group=None, seed=None):
+        self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise DrgnnError('the engine runs on a CUDA device only (no CPU fallback)')
+        self.task = task
+        if task not in ('reg', 'class'):
+            raise ValueError("task must be 'reg' or 'class'")
+        self.transform_sigmoid = bool(transform_sigmoid)
+        self.class_weights = None if class_weights is None else \
+            torch.as_tensor(class_weights, dtype=F32).to(self.device).contiguous()
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.training = True
+        self.use_graph = bool(graph)
+        self.tiled = bool(tiled)
+        self.pg = process_group
+        dist = torch.distributed
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.params = FlatParams(self.spec, self.device)
+        self.grads = torch.zeros_like(self.params.data)
+        self.exp_avg = torch.zeros_like(self.params.data)
+        self.exp_avg_sq = torch.zeros_like(self.params.data)
+        self.step_dev = torch.zeros(1, dtype=F32, device=self.device)
+        self.ws = None
+        self.struct = None
+        self._graphs = {}
+        self._staging = {}
+        self.launches_per_step = 0
+        self.reset_parameters(seed)
+
+    # ---------------------------------------------------------------- parameters
+    def reset_parameters(self, seed=None):
+        """Reference initialisation: U(+-1/sqrt(size)) for the conv parameters (ginet.py:43-48,
+        sGAT.py:57-60, foutnet.py:50-54), nn.Linear defaults for the heads."""
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        s = self.spec
+        sd = OrderedDict()
+        for name, shape, _live in s.param_shapes():
+            layer = name.split('.')[0]
+            if layer.startswith('conv'):
+                cin = s.F if layer.startswith('conv1') else s.h1
+                size = 2 * cin if s.kind == 'sgat' else cin
+                bound = 1.0 / (size ** 0.5)
+            else:   # nn.Linear default: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)), same for bias
+                fan_in = (2 * s.h2 if s.kind == 'ginet' else s.h2) if layer == 'fc1' else s.Hd
+                bound = 1.0 / (fan_in ** 0.5)
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        self.load_state_dict(sd)
+
+    def state_dict(self):
+        out = OrderedDict()
+        for name in self.spec.reference_order():
+            out[name] = self.params.view(self.params.data, name).detach().clone()
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [n for n in self.params.slots if n not in sd]
+        extra = [n for n in sd if n not in self.params.slots]
+        if strict and (missing or extra):
+            raise KeyError('state_dict mismatch: missing %s, unexpected %s' % (missing, extra))
+        for name, t in sd.items():
+            if name in self.params.slots:
+                v = self.params.view(self.params.data, name)
+                if tuple(t.shape) != tuple(v.shape):
+                    raise ValueError('shape mismatch for %s: %s vs %s' % (name, tuple(t.shape), tuple(v.shape)))
+                v.copy_(t.to(self.device, F32))
+
+    def named_grads(self):
+        return OrderedDict((n, self.params.view(self.grads, n)) for n in self.spec.reference_order())
+
+    def optimizer_state_dict(self):
+        """torch.optim.Adam-shaped state (NeuralNet.py:776 stores optimizer.state_dict())."""
+        state = {}
+        for i, name in enumerate(self.spec.reference_order()):
+            state[i] = {'step': self.step_dev.detach().cpu().clone().reshape(()),
+                        'exp_avg': self.params.view(self.exp_avg, name).detach().clone(),
+                        'exp_avg_sq': self.params.view(self.exp_avg_sq, name).detach().clone()}
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': 0, 'amsgrad': False,
+                 'params': list(range(len(state)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_optimizer_state_dict(self, osd):
+        names = self.spec.reference_order()
+        for i, name in enumerate(names):
+            st = osd['state'].get(i)
+            if st is None:
+                continue
+            self.params.view(self.exp_avg, name).copy_(st['exp_avg'].to(self.device, F32))
+            self.params.view(self.exp_avg_sq, name).copy_(st['exp_avg_sq'].to(self.device, F32))
+            self.step_dev.fill_(float(st['step']))
+        if osd.get('param_groups'):
+            g = osd['param_groups'][0]
+            self.lr, self.betas, self.eps = float(g['lr']), tuple(g['betas']), float(g['eps'])
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    # ---------------------------------------------------------------- buffers
+    def _ensure(self, B, N, E):
+        """Workspace + structure buffers for batches up to (B, N, E); growing them moves every
+        buffer, so captured graphs are dropped."""
+        ws = self.ws
+        if ws is None or ws.B < B or ws.N < N or ws.E < E:
+            nb = max(B, ws.B if ws else 0)
+            nn_ = max(N, ws.N if ws else 0)
+            ne_ = max(E, ws.E if ws else 0)
+            self.ws = Workspace(self.spec, nb, nn_, ne_, self.device)
+            self.struct = ops.Structure(nb, nn_, ne_, nn_, 1 if self.spec.kind == 'sgat' else 0, self.device)
+            self._graphs.clear()
+        return self.ws
+
+    # ---------------------------------------------------------------- forward
+    def _structure(self, d):
+        need_w = self.spec.kind == 'sgat'
+        if need_w and d.edge_attr is None:
+            raise DrgnnError('sGAT needs edge_attr')
+        if need_w and d.edge_attr.size(1) != 1:
+            raise DrgnnError('sGAT supports one edge feature (the reference broadcast needs ne in {1, Fout})')
+        st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
+                                 c1_ptr=d.c1_ptr, cluster1=d.cluster1, edge_attr=d.edge_attr if need_w else None,
+                                 clusters_are_local=True, mirrors=False, out=self.struct)
+        assert st is self.struct
+        return st
+
+    def _conv_aggregate(self, level, src, rowptr, col, Zin, n_rows, n_rows_dev, ew, s_out, post_out, tile_ptr, max_rows):
+        s = self.spec
+        cin = s.F if level == 0 else s.h1
+        tile = dict(tile_ptr=tile_ptr, max_tile_rows=max_rows) if (tile_ptr is not None and src.stride(0) == src.size(1)
+                                                                  and src.size(1) % 4 == 0) else {}
+        if s.kind == 'ginet':
+            ops.aggregate(src, rowptr, col, Zin, n_rows=n_rows, n_rows_dev=n_rows_dev, **tile)
+        elif s.kind == 'sgat':
+            ops.aggregate(src, rowptr, col, Zin[:, cin:], C_=cin, ew=ew, self_src=src, self_out=Zin[:, :cin],
+                          selfc_out=s_out, post_out=post_out, n_rows=n_rows, n_rows_dev=n_rows_dev, post_mode=1,
+                          self_mode=2, **tile)
+        else:
+            ops.aggregate(src, rowptr, col, Zin[:, cin:], C_=cin, self_src=src, self_out=Zin[:, :cin],
+                          post_out=post_out, n_rows=n_rows, n_rows_dev=n_rows_dev, post_mode=2, self_mode=1, **tile)
+
+    def _forward(self, d, keep_mask=None):
+        s, ws, st, P = self.spec, self._ensure(d.B, d.N, d.E), self._structure(d), self.params
+        N, B = d.N, d.B
+        K0d, K1d = st.K0_dev, st.K1_dev
+        pv = lambda name: P.view(P.data, name)
+        flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
+        tiled = self.tiled and d.max_n * s.F * 8 <= 200 * 1024
+        # conv1: aggregate on the level-0 graph, then transform (+bias, ReLU)
+        self._conv_aggregate(0, d.x, st.rowptr0, st.col0, ws.Zin1[:N], N, None, st.w0csr, ws.s0, ws.post0,
+                             d.node_ptr if tiled else None, d.max_n)
+        if s.kind == 'ginet':
+            W1, b1 = flat('conv1.fc.weight', s.C1 * s.F), None
+            W2, b2 = flat('conv2.fc.weight', s.nb * s.h2 * s.h1), None
+        elif s.kind == 'sgat':
+            W1, b1 = flat('conv1.weight', 2 * s.F * s.h1), pv('conv1.bias')
+            W2, b2 = flat('conv2.weight', 2 * s.h1 * s.h2), pv('conv2.bias')
+        else:
+            W1, b1 = flat('conv1.Wc', 2 * s.F * s.h1), pv('conv1.bias')
+            W2, b2 = flat('conv2.Wc', 2 * s.h1 * s.h2), pv('conv2.bias')
+        self._W1, self._W2 = W1, W2
+        ops.linear(ws.Zin1[:N], W1, s.Kin1, s.C1, ws.Z1[:N], bias=b1, w_layout=s.w_layout, relu=True)
+        # level-0 cluster max-pool (community_pooling.py:201)
+        ops.maxpool_fwd(ws.Z1[:N], st.cmptr0, st.cmem0, ws.P1[:d.L1], ws.arg0[:d.L1], n_clusters_dev=K0d)
+        # conv2 on the coarsened graph
+        ew1 = st.edge_attr1.view(-1) if s.kind == 'sgat' else None
+        L1 = d.L1
+        self._conv_aggregate(1, ws.P1[:L1], st.rowptr1, st.col1, ws.Zin2[:L1], L1, K0d, ew1, ws.s1, ws.post1, None, 0)
+        g2 = s.nb if s.kind == 'ginet' else 1
+        ops.linear(ws.Zin2[:L1], W2, s.Kin2 // g2, s.h2, ws.Z2[:L1], bias=b2, groups=g2, w_layout=s.w_layout, relu=True,
+                   rows_dev=K0d)
+        # level-1 max-pool (max_pool_x) and graph read-out (scatter_mean by batch)
+        ops.maxpool_fwd(ws.Z2[:L1], st.cmptr1, st.cmem1, ws.P2[:L1], ws.arg1[:L1], n_clusters_dev=K1d)
+        ops.segment_mean_fwd(ws.P2[:L1], st.kptr1, ws.R[:B])
+        # heads
+        drop = self.training and s.dropout > 0
+        if drop:
+            if keep_mask is not None:
+                ws.keep[:B].copy_(keep_mask.to(self.device, F32))
+            else:
+                ws.keep[:B].bernoulli_(1.0 - s.dropout)
+        ops.linear(ws.R[:B], pv('fc1.weight'), s.C2, s.Hd, ws.H[:B], bias=pv('fc1.bias'), relu=True,
+                   out_mask=ws.keep[:B] if drop else None, mask_scale=1.0 / (1.0 - s.dropout) if drop else 1.0)
+        ops.linear(ws.H[:B], pv('fc2.weight'), s.Hd, s.out, ws.pred[:B], bias=pv('fc2.bias'))
+        return ws.pred[:B]
+
+    # ---------------------------------------------------------------- backward
+    def _backward(self, d):
+        s, ws, st, P = self.spec, self.ws, self.struct, self.params
+        N, B, L1 = d.N, d.B, d.L1
+        K0d = st.K0_dev
+        pv = lambda name: P.view(P.data, name)
+        gv = lambda name: P.view(self.grads, name)
+        gflat = lambda name, n: self.grads[P.offset(name):P.offset(name) + n]
+        drop = self.training and s.dropout > 0
+        scale = 1.0 / (1.0 - s.dropout) if drop else 1.0
+        # heads
+        ops.linear_wgrad(ws.H[:B], ws.dpred[:B], s.Hd, s.out, gv('fc2.weight'), gv('fc2.bias'), work=ws.wwork)
+        ops.linear(ws.dpred[:B], pv('fc2.weight'), s.out, s.Hd, ws.dH[:B], w_layout=1, out_mask=ws.H[:B],
+                   mask_scale=scale)
+        ops.linear_wgrad(ws.R[:B], ws.dH[:B], s.C2, s.Hd, gv('fc1.weight'), gv('fc1.bias'), work=ws.wwork)
+        ops.linear(ws.dH[:B], pv('fc1.weight'), s.Hd, s.C2, ws.dR[:B], w_layout=1)
+        # read-out and level-1 pool
+        ops.segment_mean_bwd(ws.dR[:B], st.kptr1, ws.dP2[:L1])
+        ops.maxpool_bwd(ws.dP2[:L1], ws.arg1[:L1], st.cl1, ws.dZ2[:L1], relu_out=ws.Z2[:L1], n_nodes_dev=K0d)
+        # conv2
+        g2 = s.nb if s.kind == 'ginet' else 1
+        kin2 = s.Kin2 // g2
+        if s.kind == 'ginet':
+            dW2, db2 = gflat('conv2.fc.weight', s.nb * s.h2 * s.h1), None
+            dW1, db1 = gflat('conv1.fc.weight', s.C1 * s.F), None
+        elif s.kind == 'sgat':
+            dW2, db2 = gflat('conv2.weight', 2 * s.h1 * s.h2), gv('conv2.bias')
+            dW1, db1 = gflat('conv1.weight', 2 * s.F * s.h1), gv('conv1.bias')
+        else:
+            dW2, db2 = gflat('conv2.Wc', 2 * s.h1 * s.h2), gv('conv2.bias')
+            dW1, db1 = gflat('conv1.Wc', 2 * s.F * s.h1), gv('conv1.bias')
+        ops.linear_wgrad(ws.Zin2[:L1], ws.dZ2[:L1], kin2, s.h2, dW2, db2, groups=g2, w_layout=s.w_layout, rows_dev=K0d,
+                         work=ws.wwork)
+        ops.linear(ws.dZ2[:L1], self._W2, s.h2, kin2, ws.dZin2[:L1], groups=g2, w_layout=1 - s.w_layout, rows_dev=K0d)
+        # transposed aggregation on the coarsened graph -> gradient of the pooled features
+        if s.kind == 'ginet':
+            ops.aggregate(ws.dZin2[:L1], st.cscptr1, st.cscrow1, ws.dP1[:L1], n_rows_dev=K0d)
+        elif s.kind == 'sgat':
+            ops.aggregate(ws.dZin2[:L1, s.h1:], st.cscptr1, st.cscrow1, ws.dP1[:L1], C_=s.h1, ew=st.w1csc,
+                          sscale=ws.post1, self_src=ws.dZin2[:L1, :s.h1], selfc_in=ws.s1, self_mode=3, n_rows_dev=K0d)
+        else:
+            ops.aggregate(ws.dZin2[:L1, s.h1:], st.cscptr1, st.cscrow1, ws.dP1[:L1], C_=s.h1, sscale=ws.post1,
+                          self_src=ws.dZin2[:L1, :s.h1], self_mode=1, n_rows_dev=K0d)
+        # level-0 pool, conv1 (its input is data: only the weight gradient is needed)
+        ops.maxpool_bwd(ws.dP1[:L1], ws.arg0[:L1], st.cl0, ws.dZ1[:N], relu_out=ws.Z1[:N])
+        ops.linear_wgrad(ws.Zin1[:N], ws.dZ1[:N], s.Kin1, s.C1, dW1, db1, w_layout=s.w_layout, work=ws.wwork)
+
+    def _adam(self):
+        ops.adam_flat(self.params.data, self.grads, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr,
+                      self.betas[0], self.betas[1], self.eps)
+
+    # ---------------------------------------------------------------- public API
+    def _inv_norm(self, d, B_global, inv_norm):
+        if inv_norm is not None:
+            return float(inv_norm)
+        if self.task == 'reg':
+            return 1.0 / float(d.B if B_global is None else B_global)
+        raise DrgnnError("classification needs inv_norm = 1 / sum_b class_weight[target_b] over the GLOBAL batch "
+                         "(CrossEntropyLoss(reduction='mean') normaliser, NeuralNet.py:258-263)")
+
+    def _loss(self, d, inv_norm, with_grad=True):
+        ws, B = self.ws, d.B
+        if d.y is None and d.y_class is None:
+            raise DrgnnError('the batch has no target')
+        if self.task == 'reg':
+            ops.mse_loss(ws.pred[:B].view(-1), d.y, inv_norm, ws.loss, ws.dpred[:B].view(-1) if with_grad else None,
+                         sigmoid=self.transform_sigmoid)
+        else:
+            if d.y_class is None:
+                raise DrgnnError('classification needs class-index targets (pass `classes` when building the batch)')
+            ops.ce_loss(ws.pred[:B], d.y_class, inv_norm, ws.loss, ws.dpred[:B] if with_grad else None,
+                        class_w=self.class_weights)
+        return ws.loss
+
+    def _all_reduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+            torch.distributed.all_reduce(self.ws.loss, group=self.pg)
+
+    def forward(self, d, keep_mask=None):
+        """Forward only (``model(batch)``): returns the ``[B, out]`` prediction (a view of an
+        engine buffer, overwritten by the next call)."""
+        return self._forward(d, keep_mask)
+
+    def loss_and_grads(self, d, B_global=None, inv_norm=None, keep_mask=None):
+        """Forward + loss + backward, no optimiser (parity tests).  Gradients in ``named_grads()``."""
+        inv = self._inv_norm(d, B_global, inv_norm)
+        self._forward(d, keep_mask)
+        self._loss(d, inv)
+        self._backward(d)
+        return self.ws.loss, self.ws.pred[:d.B]
+
+    def step(self, d, B_global=None, inv_norm=None, keep_mask=None):
+        """One training step on a ``DeviceBatch``: forward, loss, backward, [all-reduce], Adam
+        (the body of ``NeuralNet._epoch``'s loop, NeuralNet.py:490-503).  Returns (loss, pred)
+        device tensors that the next step overwrites.  ``B_global`` = graphs in the global
+        batch when it is sharded over ranks: the local loss is sum/B_global so the all-reduced
+        (summed) gradient is the gradient of the global mean."""
+        inv = self._inv_norm(d, B_global, inv_norm)
+        if self.use_graph and d.key is not None and keep_mask is None:
+            return self._step_graph(d, inv)
+        self._forward(d, keep_mask)
+        self._loss(d, inv)
+        self._backward(d)
+        self._all_reduce()
+        self._adam()
+        return self.ws.loss, self.ws.pred[:d.B]
+
+    # ---------------------------------------------------------------- packed batches / CUDA graphs
+    def upload(self, pb, slot=0):
+        """ONE host->device copy of a ``PackedBatch`` into a persistent device staging buffer
+        (per shape and slot, so CUDA-graph replays see fixed addresses).  Returns a DeviceBatch."""
+        key = (pb.key(), slot)
+        ent = self._staging.get(key)
+        if ent is None:
+            dev = torch.empty(pb.numel, dtype=F32, device=self.device)
+            ent = (dev, DeviceBatch.from_packed(pb, dev))
+            self._staging[key] = ent
+        dev, d = ent
+        dev.copy_(pb.buf, non_blocking=True)
+        d.mol = pb.mol
+        return d
+
+    def _step_graph(self, d, inv):
+        """Replay (capture on first use) the whole step as one CUDA graph.  The graph is tied to
+        the staging buffer of the batch's shape; with several ranks the gradient all-reduce sits
+        between the two captured halves."""
+        key = (d.key, id(d), round(inv, 12), self.training)
+        ent = self._graphs.get(key)
+        if ent is None:
+            # warm up un-captured (first-use attribute setup, workspace growth), then capture
+            self._ensure(d.B, d.N, d.E)
+            snap = [t.clone() for t in (self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev)]
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._forward(d)
+                self._loss(d, inv)
+                self._backward(d)
+                self._adam()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
+                t.copy_(c)
+            g1, g2 = torch.cuda.CUDAGraph(), None
+            with torch.cuda.graph(g1):
+                self._forward(d)
+                self._loss(d, inv)
+                self._backward(d)
+                if self.world == 1:
+                    self._adam()
+            if self.world > 1:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    self._adam()
+            ent = (g1, g2)
+            self._graphs[key] = ent
+        g1, g2 = ent
+        g1.replay()
+        if g2 is not None:
+            self._all_reduce()
+            g2.replay()
+        return self.ws.loss, self.ws.pred[:d.B]
+
+    def validate(self):
+        """Raise if the last structure pass flagged invalid input (ONE host sync)."""
+        if self.struct is not None:
+            self.struct._counts_host = None
+            self.struct.sync_counts()

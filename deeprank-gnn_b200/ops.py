@@ -1,0 +1,412 @@
+"""Tensor-level wrappers of the C-ABI (``include/drgnn.h``): PyTorch tensors in, PyTorch
+tensors out, every call enqueued on the current CUDA stream, no host synchronisation
+unless a function says so.  Matrices may be column slices of wider buffers (row stride =
+leading dimension, unit column stride).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (AggregateArgs, DrgnnError, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
+                   require_cuda, stream_ptr)
+
+I32, I64, F32 = torch.int32, torch.int64, torch.float32
+
+
+def _ld(t):
+    if t.dim() == 1:
+        return t.numel() if t.numel() else 1
+    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+        raise DrgnnError('expected a row-major 2-D tensor with unit column stride, got shape %s strides %s'
+                         % (tuple(t.shape), tuple(t.stride())))
+    return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != F32:
+        raise DrgnnError('%s must be float32 (got %s)' % (name, t.dtype))
+    return t
+
+
+def _i32(t, name):
+    if t is not None and (t.dtype != I32 or not t.is_contiguous()):
+        raise DrgnnError('%s must be a contiguous int32 tensor' % name)
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+# Structure pass
+# ------------------------------------------------------------------------------------------
+_INT_FIELDS = ('rowptr0', 'col0', 'eid0', 'cscptr0', 'cscrow0', 'csceid0', 'cl0', 'cmptr0', 'cmem0', 'kptr0',
+               'batch1', 'rowptr1', 'col1', 'cscptr1', 'cscrow1', 'csceid1', 'cl1', 'cmptr1', 'cmem1', 'kptr1',
+               'batch2', 'counts', 'status', 'gstat', 'scratch_n', 'scratch_e')
+_FLOAT_FIELDS = ('w0csr', 'w0csc', 'edge_attr1', 'w1csc', 'scratch_f')
+_I64_FIELDS = ('cl0_i64', 'batch1_i64', 'edge_index1', 'batch2_i64')
+
+
+def _structure_sizes(B, N, E, L1, ne):
+    n1, l1 = N + 1, L1 + 1
+    ints = dict(rowptr0=n1, col0=E, eid0=E, cscptr0=n1, cscrow0=E, csceid0=E, cl0=N, cmptr0=n1, cmem0=N,
+                kptr0=B + 1, batch1=N, rowptr1=n1, col1=E, cscptr1=n1, cscrow1=E, csceid1=E, cl1=L1, cmptr1=l1,
+                cmem1=L1, kptr1=B + 1, batch2=L1, counts=4, status=1, gstat=8 * B,
+                scratch_n=5 * (N + B + 1) + 8, scratch_e=4 * E + 8)
+    floats = dict(w0csr=E if ne else 0, w0csc=E if ne else 0, edge_attr1=E * ne, w1csc=E if ne else 0,
+                  scratch_f=E * max(ne, 1) if ne else 0)
+    i64 = dict(cl0_i64=N, batch1_i64=N, edge_index1=2 * E, batch2_i64=L1)
+    return ints, floats, i64
+
+
+class Structure(object):
+    """Everything integer that depends only on the batch: CSR/CSC of the
+    level-0 graph, relabelled clusters, cluster->members CSR, pooled graph CSR/CSC, pooled
+    batch vectors, level-1 clustering and the device-side counts ``[K0, E1, K1]``.
+    Built by two kernel launches (``drgnn_structure_build``); shared by forward, backward
+    and both GINet branches.
+
+    The constructor sizes are CAPACITIES: one object serves every batch with
+    ``B <= cap_B, N <= cap_N, E <= cap_E, L1 <= cap_L1`` at fixed device addresses (so
+    captured CUDA graphs stay valid); ``B, N, E, L1`` hold the sizes of the current batch."""
+
+    def __init__(self, B, N, E, L1, ne, device, mirrors=False):
+        self.cap = (int(B), int(N), int(E), int(L1))
+        self.B, self.N, self.E, self.L1, self.ne = int(B), int(N), int(E), int(L1), int(ne)
+        self.device = device
+        self.mirrors = mirrors
+        ints, floats, i64 = _structure_sizes(self.B, self.N, self.E, self.L1, self.ne)
+        pad = lambda n: (n + 3) & ~3
+        tot_i = sum(pad(v) for v in ints.values())
+        tot_f = sum(pad(v) for v in floats.values())
+        tot_l = sum(pad(v) for v in i64.values()) if mirrors else 0
+        self._iarena = torch.empty(max(tot_i, 4), dtype=I32, device=device)
+        self._farena = torch.empty(max(tot_f, 4), dtype=F32, device=device)
+        self._larena = torch.empty(max(tot_l, 4), dtype=I64, device=device) if mirrors else None
+        o = 0
+        for k, v in ints.items():
+            setattr(self, k, self._iarena[o:o + v])
+            o += pad(v)
+        o = 0
+        for k, v in floats.items():
+            setattr(self, k, self._farena[o:o + v] if v else None)
+            o += pad(v)
+        o = 0
+        for k, v in i64.items():
+            setattr(self, k, self._larena[o:o + v] if mirrors else None)
+            o += pad(v) if mirrors else 0
+        self._edge_attr1_flat, self._edge_index1_flat = self.edge_attr1, self.edge_index1
+        self.io = StructureIO()
+        for k in _INT_FIELDS + _FLOAT_FIELDS + _I64_FIELDS:
+            setattr(self.io, k, ptr(getattr(self, k)))
+        self._counts_host = None
+        self._keep = None
+        self._shape_views()
+
+    def fits(self, B, N, E, L1, ne, mirrors):
+        cb, cn, ce, cl = self.cap
+        return B <= cb and N <= cn and E <= ce and L1 <= cl and ne == self.ne and mirrors == self.mirrors
+
+    def _shape_views(self):
+        """edge_attr1 ``[E, ne]`` and the int64 edge_index mirror ``[2, E]`` are laid out with
+        the CURRENT batch's E (the kernel strides by io.E)."""
+        if self.ne:
+            self.edge_attr1 = self._edge_attr1_flat[:self.E * self.ne].view(self.E, self.ne)
+        if self.mirrors:
+            self.edge_index1 = self._edge_index1_flat[:2 * self.E].view(2, self.E)
+
+    # device-side live counts (no sync)
+    @property
+    def K0_dev(self):
+        return self.counts[0:1]
+
+    @property
+    def E1_dev(self):
+        return self.counts[1:2]
+
+    @property
+    def K1_dev(self):
+        return self.counts[2:3]
+
+    def sync_counts(self):
+        """Host copy of (K0, E1, K1) and validation of the status word.  ONE host sync."""
+        if self._counts_host is None:
+            host = torch.cat([self.counts, self.status]).cpu().tolist()
+            st = host[4]
+            if st:
+                msgs = [t for bit, t in _lib.STATUS_TEXT.items() if st & bit]
+                raise DrgnnError('invalid batch structure: ' + '; '.join(msgs))
+            self._counts_host = tuple(host[:3])
+        return self._counts_host
+
+    @property
+    def K0(self):
+        return self.sync_counts()[0]
+
+    @property
+    def E1(self):
+        return self.sync_counts()[1]
+
+    @property
+    def K1(self):
+        return self.sync_counts()[2]
+
+
+def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr=None, cluster1=None,
+                    edge_attr=None, clusters_are_local=True, mirrors=False, out=None):
+    """Run the structure pass for one mini-batch.  ``node_ptr/edge_ptr/c1_ptr`` are int32
+    ``[B+1]`` device tensors; ``edge_index`` ``[2,E]`` and ``cluster0/1`` are int64 (reference
+    layout) or int32.  Returns a ``Structure`` (``out`` is reused if given)."""
+    require_cuda(node_ptr, edge_ptr, edge_index, cluster0, c1_ptr, cluster1, edge_attr)
+    _i32(node_ptr, 'node_ptr'), _i32(edge_ptr, 'edge_ptr'), _i32(c1_ptr, 'c1_ptr')
+    B = node_ptr.numel() - 1
+    N = cluster0.numel()
+    E = edge_index.size(1) if edge_index.dim() == 2 else 0
+    L1 = 0 if cluster1 is None else cluster1.numel()
+    if edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or \
+            (cluster1 is not None and cluster1.dtype != edge_index.dtype):
+        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32)')
+    if not edge_index.is_contiguous() or not cluster0.is_contiguous() or \
+            (cluster1 is not None and not cluster1.is_contiguous()):
+        raise DrgnnError('edge_index / cluster tensors must be contiguous')
+    if L1 > N:
+        raise DrgnnError('len(cluster1)=%d exceeds the number of nodes %d' % (L1, N))
+    if cluster1 is not None and c1_ptr is None:
+        raise DrgnnError('cluster1 given without c1_ptr')
+    ne = 0
+    if edge_attr is not None:
+        _f32(edge_attr, 'edge_attr')
+        if edge_attr.dim() == 1:
+            edge_attr = edge_attr.unsqueeze(-1)          # ginet.py:54-55, sGAT.py:66-67
+        if not edge_attr.is_contiguous():
+            edge_attr = edge_attr.contiguous()
+        ne = edge_attr.size(1)
+        if edge_attr.size(0) != E:
+            raise DrgnnError('edge_attr has %d rows for %d edges' % (edge_attr.size(0), E))
+    s = out
+    if s is None or not s.fits(B, N, E, L1, ne, mirrors):
+        s = Structure(B, N, E, L1, ne, cluster0.device, mirrors)
+    s.B, s.N, s.E, s.L1 = B, N, E, L1
+    s._shape_views()
+    s._counts_host = None
+    s._keep = (node_ptr, edge_ptr, c1_ptr, edge_index, edge_attr, cluster0, cluster1)
+    s.node_ptr, s.edge_ptr, s.c1_ptr = node_ptr, edge_ptr, c1_ptr
+    s.max_n, s.max_e = int(max_n), int(max_e)
+    io = s.io
+    io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, ne
+    io.max_n, io.max_e = int(max_n), int(max_e)
+    io.clusters_are_local = 1 if clusters_are_local else 0
+    io.idx32 = 1 if edge_index.dtype == I32 else 0
+    io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
+    io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
+    io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
+    if B == 0:
+        s.counts.zero_()
+        s.status.zero_()
+        return s
+    st = stream_ptr()
+    call('drgnn_fill_i32', ptr(s.status), 0, 1, st)
+    call('drgnn_structure_build', C.byref(io), st)
+    return s
+
+
+def cluster_offset_(cluster, seg_ptr):
+    """In-place ``get_preloaded_cluster`` (community_pooling.py:25-30) on an int64 vector."""
+    require_cuda(cluster, seg_ptr)
+    if cluster.dtype != I64 or not cluster.is_contiguous():
+        raise DrgnnError('cluster must be a contiguous int64 tensor')
+    _i32(seg_ptr, 'seg_ptr')
+    B = seg_ptr.numel() - 1
+    work = torch.empty(max(B, 1), dtype=I64, device=cluster.device)
+    call('drgnn_cluster_offset', ptr(cluster), ptr(seg_ptr), B, ptr(work), stream_ptr())
+    return cluster
+
+
+def ptr_from_sorted_ids(ids, B):
+    """int32 ``[B+1]`` segment pointers of a sorted int64 id vector (``batch``).  Raises (one
+    host sync) if ``ids`` is not sorted or out of range."""
+    require_cuda(ids)
+    if ids.dtype != I64 or not ids.is_contiguous():
+        raise DrgnnError('ids must be a contiguous int64 tensor')
+    out = torch.empty(B + 1, dtype=I32, device=ids.device)
+    status = torch.zeros(1, dtype=I32, device=ids.device)
+    call('drgnn_ptr_from_sorted_ids', ptr(ids), ids.numel(), B, ptr(out), ptr(status), stream_ptr())
+    if int(status.item()) != 0:
+        raise DrgnnError('`batch` must be sorted ascending with values in [0, %d)' % B)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Aggregation
+# ------------------------------------------------------------------------------------------
+def aggregate(src, rowptr, col, out, C_=None, ew=None, sscale=None, self_src=None, self_out=None, selfc_in=None,
+              selfc_out=None, post_out=None, bias=None, n_rows=None, n_rows_dev=None, post_mode=0, self_mode=0,
+              relu=False, tile_ptr=None, max_tile_rows=0):
+    """out[i] = act(selfc_i * self_src[i] + post_i * sum_p ew[p] * sscale[col[p]] * src[col[p]] + bias)
+    over CSR rows (see ``drgnn_aggregate`` in include/drgnn.h).  With ``tile_ptr`` the
+    shared-memory staged per-graph kernel (``drgnn_aggregate_tiled``) is used."""
+    require_cuda(src, rowptr, col, out, ew, sscale, self_src, self_out, selfc_in, selfc_out, post_out, bias)
+    _f32(src, 'src'), _f32(out, 'out'), _i32(rowptr, 'rowptr'), _i32(col, 'col')
+    a = AggregateArgs()
+    a.src, a.ld_src = ptr(src), _ld(src)
+    a.out, a.ld_out = ptr(out), _ld(out)
+    a.rowptr, a.col = ptr(rowptr), ptr(col)
+    a.ew, a.sscale = ptr(_f32(ew, 'ew')), ptr(_f32(sscale, 'sscale'))
+    a.self_src, a.ld_self = ptr(_f32(self_src, 'self_src')), (_ld(self_src) if self_src is not None else 0)
+    a.self_out, a.ld_self_out = ptr(_f32(self_out, 'self_out')), (_ld(self_out) if self_out is not None else 0)
+    a.selfc_in, a.selfc_out = ptr(_f32(selfc_in, 'selfc_in')), ptr(_f32(selfc_out, 'selfc_out'))
+    a.post_out = ptr(_f32(post_out, 'post_out'))
+    a.bias = ptr(_f32(bias, 'bias'))
+    a.n_rows = int(out.size(0) if n_rows is None else n_rows)
+    a.n_rows_dev = ptr(n_rows_dev)
+    a.C = int(out.size(1) if C_ is None else C_)
+    a.post_mode, a.self_mode, a.relu = int(post_mode), int(self_mode), 1 if relu else 0
+    if tile_ptr is not None:
+        call('drgnn_aggregate_tiled', C.byref(a), ptr(_i32(tile_ptr, 'tile_ptr')), tile_ptr.numel() - 1,
+             int(max_tile_rows), stream_ptr())
+    else:
+        call('drgnn_aggregate', C.byref(a), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Dense transform
+# ------------------------------------------------------------------------------------------
+MATH_FMA, MATH_TF32X3 = 0, 1
+default_math = MATH_FMA
+
+
+def linear(X, W, Fin, Fout, out, bias=None, groups=1, w_layout=0, relu=False, out_mask=None, mask_scale=1.0,
+           rows=None, rows_dev=None, math=None):
+    """Y[r, g*Fout+o] = act(sum_k X[r, g*Fin+k] * W_g[k,o] + bias) (* mask) - ``drgnn_linear``."""
+    require_cuda(X, W, out, bias, out_mask)
+    _f32(X, 'X'), _f32(W, 'W'), _f32(out, 'out'), _f32(bias, 'bias'), _f32(out_mask, 'out_mask')
+    if not W.is_contiguous() or W.numel() != groups * Fin * Fout:
+        raise DrgnnError('W must be contiguous with groups*Fin*Fout = %d elements (got %d)'
+                         % (groups * Fin * Fout, W.numel()))
+    a = LinearArgs()
+    a.X, a.ldx = ptr(X), _ld(X)
+    a.W, a.bias = ptr(W), ptr(bias)
+    a.Y, a.ldy = ptr(out), _ld(out)
+    a.out_mask, a.ld_mask = ptr(out_mask), (_ld(out_mask) if out_mask is not None else 0)
+    a.mask_scale = float(mask_scale)
+    a.rows = int(out.size(0) if rows is None else rows)
+    a.rows_dev = ptr(rows_dev)
+    a.Fin, a.Fout, a.groups = int(Fin), int(Fout), int(groups)
+    a.w_layout, a.relu = int(w_layout), 1 if relu else 0
+    a.math = int(default_math if math is None else math)
+    call('drgnn_linear', C.byref(a), stream_ptr())
+    return out
+
+
+def linear_wgrad_work_floats(rows, Fin, Fout, groups=1):
+    return int(_lib.load().drgnn_linear_wgrad_work_floats(int(rows), int(Fin), int(Fout), int(groups)))
+
+
+def linear_wgrad(X, G, Fin, Fout, dW, dbias=None, groups=1, w_layout=0, rows=None, rows_dev=None, accumulate=False,
+                 work=None):
+    """dW (+)= G^T X (layout as the weight), dbias (+)= column sums of G - ``drgnn_linear_wgrad``."""
+    require_cuda(X, G, dW, dbias, work)
+    _f32(X, 'X'), _f32(G, 'G'), _f32(dW, 'dW'), _f32(dbias, 'dbias')
+    rows = int(G.size(0) if rows is None else rows)
+    need = linear_wgrad_work_floats(rows, Fin, Fout, groups)
+    if work is None:
+        work = torch.empty(need, dtype=F32, device=G.device)
+    if not dW.is_contiguous() or dW.numel() != groups * Fin * Fout:
+        raise DrgnnError('dW must be contiguous with groups*Fin*Fout elements')
+    a = LinearWgradArgs()
+    a.X, a.ldx = ptr(X), _ld(X)
+    a.G, a.ldg = ptr(G), _ld(G)
+    a.dW, a.dbias = ptr(dW), ptr(dbias)
+    a.rows, a.rows_dev = rows, ptr(rows_dev)
+    a.Fin, a.Fout, a.groups = int(Fin), int(Fout), int(groups)
+    a.w_layout, a.accumulate = int(w_layout), 1 if accumulate else 0
+    a.work, a.work_floats = ptr(work), work.numel()
+    call('drgnn_linear_wgrad', C.byref(a), stream_ptr())
+    return dW
+
+
+# ------------------------------------------------------------------------------------------
+# Pooling / read-out
+# ------------------------------------------------------------------------------------------
+def maxpool_fwd(x, cmptr, cmem, out, argmax, n_clusters=None, n_clusters_dev=None):
+    require_cuda(x, cmptr, cmem, out, argmax)
+    _f32(x, 'x'), _f32(out, 'out'), _i32(cmptr, 'cmptr'), _i32(cmem, 'cmem'), _i32(argmax, 'argmax')
+    Cc = x.size(1)
+    n = int(out.size(0) if n_clusters is None else n_clusters)
+    call('drgnn_maxpool_fwd', ptr(x), _ld(x), ptr(cmptr), ptr(cmem), n, ptr(n_clusters_dev), Cc, ptr(out), _ld(out),
+         ptr(argmax), stream_ptr())
+    return out, argmax
+
+
+def maxpool_bwd(g, argmax, cl, dx, relu_out=None, n_nodes=None, n_nodes_dev=None):
+    require_cuda(g, argmax, cl, dx, relu_out)
+    _f32(g, 'g'), _f32(dx, 'dx'), _f32(relu_out, 'relu_out'), _i32(argmax, 'argmax'), _i32(cl, 'cl')
+    Cc = g.size(1)
+    n = int(dx.size(0) if n_nodes is None else n_nodes)
+    call('drgnn_maxpool_bwd', ptr(g), _ld(g), ptr(argmax), ptr(cl), ptr(relu_out),
+         _ld(relu_out) if relu_out is not None else 0, n, ptr(n_nodes_dev), Cc, ptr(dx), _ld(dx), stream_ptr())
+    return dx
+
+
+def segment_mean_fwd(x, seg_ptr, out):
+    require_cuda(x, seg_ptr, out)
+    _f32(x, 'x'), _f32(out, 'out'), _i32(seg_ptr, 'seg_ptr')
+    call('drgnn_segment_mean_fwd', ptr(x), _ld(x), ptr(seg_ptr), seg_ptr.numel() - 1, x.size(1), ptr(out), _ld(out),
+         stream_ptr())
+    return out
+
+
+def segment_mean_bwd(g, seg_ptr, dx):
+    require_cuda(g, seg_ptr, dx)
+    _f32(g, 'g'), _f32(dx, 'dx'), _i32(seg_ptr, 'seg_ptr')
+    call('drgnn_segment_mean_bwd', ptr(g), _ld(g), ptr(seg_ptr), seg_ptr.numel() - 1, g.size(1), ptr(dx), _ld(dx),
+         stream_ptr())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------
+# Loss / optimiser / utilities
+# ------------------------------------------------------------------------------------------
+def mse_loss(pred, y, inv_B_global, loss_out, dpred=None, sigmoid=False):
+    require_cuda(pred, y, loss_out, dpred)
+    call('drgnn_mse_loss', ptr(_f32(pred, 'pred')), ptr(_f32(y, 'y')), pred.numel(), float(inv_B_global),
+         1 if sigmoid else 0, ptr(loss_out), ptr(dpred), stream_ptr())
+    return loss_out
+
+
+def ce_loss(logits, target, inv_norm_global, loss_out, dlogits=None, class_w=None):
+    require_cuda(logits, target, loss_out, dlogits, class_w)
+    if target.dtype != I64:
+        raise DrgnnError('target must be int64 class indices')
+    call('drgnn_ce_loss', ptr(_f32(logits, 'logits')), _ld(logits), ptr(target), ptr(_f32(class_w, 'class_w')),
+         logits.size(0), logits.size(1), float(inv_norm_global), ptr(loss_out), ptr(dlogits), stream_ptr())
+    return loss_out
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    require_cuda(param, grad, exp_avg, exp_avg_sq, step_dev)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != F32 or not t.is_contiguous():
+            raise DrgnnError('adam_flat works on contiguous float32 buffers')
+    call('drgnn_adam_flat', ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_dev), param.numel(),
+         float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), stream_ptr())
+
+
+def relu_mask(g, out, gz, rows=None, rows_dev=None):
+    require_cuda(g, out, gz)
+    n = int(g.size(0) if rows is None else rows)
+    call('drgnn_relu_mask', ptr(_f32(g, 'g')), _ld(g), ptr(_f32(out, 'out')), _ld(out), n, ptr(rows_dev), g.size(1),
+         ptr(_f32(gz, 'gz')), _ld(gz), stream_ptr())
+    return gz
+
+
+def fill_(t, value):
+    require_cuda(t)
+    if not t.is_contiguous():
+        raise DrgnnError('fill_ needs a contiguous tensor')
+    if t.dtype == F32:
+        call('drgnn_fill_f32', ptr(t), float(value), t.numel(), stream_ptr())
+    elif t.dtype == I32:
+        call('drgnn_fill_i32', ptr(t), int(value), t.numel(), stream_ptr())
+    else:
+        raise DrgnnError('fill_ supports float32 / int32')
+    return t

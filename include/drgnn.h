@@ -70,15 +70,18 @@ typedef struct drgnn_structure_io {
   int32_t max_e;        /* max edges of one graph   (host-known from edge_ptr)            */
   int32_t clusters_are_local; /* 1: ids are per-graph local (un-offset, DataSet.py:348-357);
                                  0: ids are already global (must increase with graph id)  */
+  int32_t idx32;        /* 0: edge_index / cluster0 / cluster1 are int64 (reference tensors);
+                           1: they are int32 (packed feeder batches)                       */
+  int32_t reserved0;
   /* ---- inputs ---- */
   const int32_t* node_ptr;   /* [B+1] */
   const int32_t* edge_ptr;   /* [B+1] */
   const int32_t* c1_ptr;     /* [B+1] segment pointers of cluster1 (NULL if L1 == 0)       */
-  const int64_t* edge_index; /* [2,E]  row = edge_index[0] = destination / segment id,
+  const void* edge_index;    /* [2,E]  row = edge_index[0] = destination / segment id,
                                         col = edge_index[1] = gathered source (ginet.py:52) */
   const float* edge_attr;    /* [E,ne] or NULL                                            */
-  const int64_t* cluster0;   /* [N]                                                       */
-  const int64_t* cluster1;   /* [L1] or NULL                                              */
+  const void* cluster0;      /* [N]                                                       */
+  const void* cluster1;      /* [L1] or NULL                                              */
   /* ---- level-0 graph: final outputs ---- */
   int32_t* rowptr0;  /* [N+1] CSR by destination; within a row ascending original edge id */
   int32_t* col0;     /* [E]   source node of CSR slot                                     */
@@ -153,6 +156,7 @@ int drgnn_ptr_from_sorted_ids(const int64_t* ids, int32_t n, int32_t B, int32_t*
  *    ew, sscale, bias, self_src may be NULL.  relu != 0 applies max(.,0).
  *    self_out != NULL additionally stores selfc_i * self_src[i,:] there (ld = ld_self_out)
  *    INSTEAD of adding the self term to out.
+ *    post_out != NULL stores post_i (the backward on the CSC form uses it as sscale).
  *    n_rows_dev (may be NULL) holds the live row count on the device (<= n_rows).
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_aggregate_args {
@@ -163,6 +167,7 @@ typedef struct drgnn_aggregate_args {
   const float* self_src; int32_t ld_self;
   float* self_out; int32_t ld_self_out;
   const float* selfc_in; float* selfc_out;
+  float* post_out;
   const float* bias;
   int32_t n_rows; const int32_t* n_rows_dev;
   int32_t C; int32_t post_mode; int32_t self_mode; int32_t relu;
@@ -182,33 +187,31 @@ int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr
  *    Y[r, g*Fout + o] = act( sum_k X[r, g*Fin + k] * Wg[k,o] + bias[g*Fout+o] )
  *    w_layout 0: W stored [groups][Fout][Fin] (nn.Linear.weight) ; 1: [groups][Fin][Fout]
  *    (sGAT weight / Fout Wc,Wn / transposed use in backward).
- *    mask != NULL: the INPUT gradient convention for backward: X is replaced by
- *    X * (mask > 0) (fused ReLU backward, mask has X's shape and ld_mask).
+ *    out_mask != NULL: Y is multiplied by (out_mask[r,c] > 0) * mask_scale after the
+ *    activation (out_mask has Y's shape, leading dimension ld_mask).  One mechanism, two uses:
+ *    train-mode dropout (ginet.py:138; out_mask = 0/1 keep mask, mask_scale = 1/(1-p)) and
+ *    the fused ReLU / dropout backward (out_mask = the forward activation).
  *    math: 0 = fp32 FMA, 1 = 3xTF32 tensor cores (error-compensated, ~fp32 accuracy)
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_linear_args {
   const float* X; int32_t ldx;
   const float* W; const float* bias;
   float* Y; int32_t ldy;
-  const float* mask; int32_t ld_mask;
+  const float* out_mask; int32_t ld_mask; float mask_scale;
   int32_t rows; const int32_t* rows_dev;
   int32_t Fin; int32_t Fout; int32_t groups;
   int32_t w_layout; int32_t relu; int32_t math;
-  /* dropout (ginet.py:138): keep_mask [rows, groups*Fout] of 0/1 floats, scaled by
-   * 1/(1-p) after the activation; NULL = no dropout */
-  const float* keep_mask; float keep_scale;
 } drgnn_linear_args;
 int drgnn_linear(const drgnn_linear_args* a, void* stream);
 
 /* Weight / bias gradient of the transform: dW[g][o][k] (w_layout 0) or dW[g][k][o]
  * (w_layout 1) (+)= sum_r G[r, g*Fout+o] * X[r, g*Fin+k], dbias[g*Fout+o] (+)= sum_r G[r,..].
- * G may be masked by (mask > 0) (fused ReLU backward).  Two-phase deterministic reduction:
- * partials [n_chunks, groups*Fout*(Fin+1)] in `work`, then a fixed-order sum.
- * accumulate != 0 adds into dW / dbias, else overwrites. */
+ * Two-phase deterministic reduction: partials [n_chunks, groups*Fout*(Fin+1)] in `work`,
+ * then a fixed-order sum.  accumulate != 0 adds into dW / dbias, else overwrites.
+ * dbias may be NULL. */
 typedef struct drgnn_linear_wgrad_args {
   const float* X; int32_t ldx;
   const float* G; int32_t ldg;
-  const float* mask; int32_t ld_mask;
   float* dW; float* dbias;
   int32_t rows; const int32_t* rows_dev;
   int32_t Fin; int32_t Fout; int32_t groups;

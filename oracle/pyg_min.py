@@ -130,21 +130,28 @@ def scatter_mean(src, index, dim=0, out=None, dim_size=None):
 
 class _ScatterMax(torch.autograd.Function):
     """torch_scatter.scatter_max - community_pooling.py:201 and PyG max_pool_x.
-    Forward: per-segment max, argmax = FIRST occurrence (CPU kernel updates on strict >),
-    empty segments -> 0 with arg = src.size(0).  Backward: gradient routed only to argmax."""
+
+    Published CPU algorithm (torch_scatter 2.0.x ``scatter_cpu`` + ``Reducer<MAX>``): ``out`` is
+    filled with ``numeric_limits::lowest()``, ``arg`` with ``src.size(0)``; entries are visited
+    in index order and replace the running value only on a strict ``>`` (so the FIRST
+    occurrence of the maximum wins and a NaN never wins); afterwards entries still equal to
+    ``lowest()`` (empty segments) are set to 0.  Backward: the gradient is routed only to
+    ``arg`` (no tie splitting)."""
 
     @staticmethod
     def forward(ctx, src, index, dim_size):
         n, c = src.shape
+        lowest = torch.finfo(src.dtype).min
         idx = index.view(-1, 1).expand(n, c)
-        neg = torch.full((dim_size, c), float('-inf'), dtype=src.dtype)
-        out = neg.scatter_reduce(0, idx, src, reduce='amax', include_self=True)
-        is_max = src == out[index]
+        cand_val = torch.where(torch.isnan(src), torch.full_like(src, lowest), src)
+        out = torch.full((dim_size, c), lowest, dtype=src.dtype)
+        out = out.scatter_reduce(0, idx, cand_val, reduce='amax', include_self=True)
+        is_max = (cand_val == out[index]) & (cand_val > lowest)
         pos = torch.arange(n).view(-1, 1).expand(n, c)
         cand = torch.where(is_max, pos, torch.full_like(pos, n))
         arg = torch.full((dim_size, c), n, dtype=torch.long).scatter_reduce(
             0, idx, cand, reduce='amin', include_self=True)
-        out = torch.where(arg == n, torch.zeros_like(out), out)
+        out = torch.where(out == lowest, torch.zeros_like(out), out)
         ctx.save_for_backward(arg)
         ctx.n = n
         ctx.mark_non_differentiable(arg)
@@ -155,7 +162,7 @@ class _ScatterMax(torch.autograd.Function):
         arg, = ctx.saved_tensors
         n = ctx.n
         gs = torch.zeros((n + 1, g.size(1)), dtype=g.dtype)
-        gs.scatter_(0, arg, g)       # each (segment, channel) has one winner row
+        gs.scatter_(0, arg, g)       # each (segment, channel) has at most one winner row
         return gs[:n], None, None
 
 

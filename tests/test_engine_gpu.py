@@ -1,0 +1,212 @@
+"""End-to-end parity of the fused engine (forward, loss, backward, Adam) against the CPU
+oracle restatement of the reference networks, on the real fixture and on synthetic batches
+of the BASELINE shapes.  Tolerance: 1e-4 absolute on outputs and on every parameter
+gradient (BASELINE.json north_star), checked relative to the tensor's scale for the large
+gradients."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import to_oracle_batch
+from oracle import nets as onets
+from oracle import step as ostep
+
+pytestmark = pytest.mark.gpu
+
+NETS = {'GINet': onets.GINet, 'sGAT': onets.sGAT, 'FoutNet': onets.FoutNet}
+
+
+def _fixture_graphs(features=('type', 'polarity', 'bsa'), target='irmsd'):
+    from deeprank_gnn_b200.DataSet import HDF5DataSet
+    from conftest import FIXTURE
+    ds = HDF5DataSet(database=FIXTURE, node_feature=list(features), target=target)
+    return [ds.get(i) for i in range(ds.len())]
+
+
+def _close(a, b, name, tol=1e-4):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, '%s: shape %s vs %s' % (name, tuple(a.shape), tuple(b.shape))
+    scale = max(1.0, float(b.abs().max()))
+    err = float((a - b).abs().max())
+    assert err <= tol * scale, '%s: max|diff| = %.3e (scale %.3e)' % (name, err, scale)
+
+
+def _oracle_run(net, graphs, hidden, out, task='reg', classes=(0, 1), weights=None, keep_mask=None, train=True, seed=0,
+                lr=0.01, literal=True):
+    torch.manual_seed(seed)
+    onets.LITERAL = literal
+    F_in = graphs[0].x.size(1)
+    model = NETS[net](F_in, out, 1, hidden=hidden)
+    sd0 = copy.deepcopy(model.state_dict())
+    model.train(train)
+    batch = to_oracle_batch(graphs)
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    loss_fn = ostep.make_loss(task, weights)
+    real_dropout = F.dropout
+    if keep_mask is not None:
+        onets.F.dropout = lambda x, p, training=True: x * keep_mask / (1 - p) if training else x
+    try:
+        loss, pred = ostep.train_step(model, opt, loss_fn, batch, task, classes)
+    finally:
+        onets.F.dropout = real_dropout
+        onets.LITERAL = True
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    return sd0, loss, pred, grads, copy.deepcopy(model.state_dict())
+
+
+def _engine(net, graphs, hidden, out, sd0, task='reg', weights=None, lr=0.01, **kw):
+    from deeprank_gnn_b200.engine import Engine
+    eng = Engine(net, graphs[0].x.size(1), out, 1, hidden=hidden, device='cuda:0', task=task, class_weights=weights,
+                 lr=lr, **kw)
+    eng.load_state_dict(sd0)
+    return eng
+
+
+def _device_batch(graphs, classes=None):
+    from deeprank_gnn_b200.data import Batch
+    from deeprank_gnn_b200.engine import DeviceBatch
+    return DeviceBatch.from_batch(Batch.from_data_list(graphs), 'cuda:0', classes=classes)
+
+
+@pytest.mark.parametrize('net', ['GINet', 'sGAT', 'FoutNet'])
+@pytest.mark.parametrize('data', ['fixture', 'cfg2'])
+def test_train_step_matches_oracle(lib, net, data):
+    from deeprank_gnn_b200 import synthetic
+    if data == 'fixture':
+        graphs = _fixture_graphs()[:8]                  # BASELINE config 1: batch of 8, F = 3
+    else:
+        graphs = synthetic.make_graphs('cfg2', count=6 if net == 'FoutNet' else 16, seed=1)
+    hidden = (16, 32)
+    keep = None
+    if net == 'GINet':
+        keep = (torch.rand(len(graphs), 4 * hidden[1], generator=torch.Generator().manual_seed(5)) > 0.4).float()
+    sd0, loss, pred, grads, sd1 = _oracle_run(net, graphs, hidden, 1, keep_mask=keep)
+    eng = _engine(net, graphs, hidden, 1, sd0)
+    d = _device_batch(graphs)
+    eloss, epred = eng.step(d, keep_mask=keep)
+    eng.validate()
+    _close(epred.view(-1), pred, 'pred')
+    _close(eloss[0], loss, 'loss')
+    for name, g in eng.named_grads().items():
+        _close(g, grads[name], 'grad ' + name)
+    # Adam at step 1 moves every parameter by ~lr * sign(grad): compare where the gradient is not
+    # vanishing (a sign flip of a ~1e-9 gradient is not a parity failure)
+    for name, p in eng.state_dict().items():
+        solid = grads[name].abs() > 1e-5
+        if solid.any():
+            _close(p.cpu()[solid], sd1[name][solid], 'param ' + name)
+
+
+def test_ginet_dead_attention_parameters_keep_zero_grad(lib):
+    from deeprank_gnn_b200 import synthetic
+    graphs = synthetic.make_graphs('cfg2', count=4, seed=2)
+    sd0, loss, pred, grads, sd1 = _oracle_run('GINet', graphs, (16, 32), 1, train=False)
+    eng = _engine('GINet', graphs, (16, 32), 1, sd0).eval()
+    eng.step(_device_batch(graphs))
+    for name, g in eng.named_grads().items():
+        if 'attention' in name or 'edge_attr' in name:
+            assert float(g.abs().max()) == 0.0 and float(grads[name].abs().max()) == 0.0
+            assert torch.equal(eng.state_dict()[name].cpu(), sd0[name])
+
+
+def test_classification_with_class_weights(lib):
+    graphs = _fixture_graphs(target='binclass')
+    for i, g in enumerate(graphs):                      # the fixture is all class 0: make it two-class
+        g.y = torch.tensor([float(i % 2)])
+    w = torch.tensor([0.3, 1.7])
+    sd0, loss, pred, grads, sd1 = _oracle_run('GINet', graphs, (16, 32), 2, task='class', weights=w, train=False)
+    eng = _engine('GINet', graphs, (16, 32), 2, sd0, task='class', weights=w).eval()
+    d = _device_batch(graphs, classes=[0, 1])
+    inv = 1.0 / float(w[d.y_class.cpu()].sum())
+    eloss, epred = eng.step(d, inv_norm=inv)
+    _close(epred, pred, 'logits')
+    _close(eloss[0], loss, 'loss')
+    for name, g in eng.named_grads().items():
+        _close(g, grads[name], 'grad ' + name)
+
+
+@pytest.mark.parametrize('net,cfg,count', [('GINet', 'cfg4', 4), ('FoutNet', 'cfg5', 3), ('sGAT', 'cfg3', 8)])
+def test_wider_configs_match_vectorised_oracle(lib, net, cfg, count):
+    """cfg4 (hidden 32/64) and cfg5 (mixed sizes, FoutNet) against the loop-free oracle forms
+    (proven equal to the literal loops in tests/test_oracle.py)."""
+    from deeprank_gnn_b200 import synthetic
+    c = synthetic.CONFIGS[cfg]
+    graphs = synthetic.make_graphs(cfg, count=count, seed=4)
+    sd0, loss, pred, grads, sd1 = _oracle_run(net, graphs, c['hidden'], 1, train=False, literal=False)
+    eng = _engine(net, graphs, c['hidden'], 1, sd0).eval()
+    eloss, epred = eng.step(_device_batch(graphs))
+    eng.validate()
+    _close(epred.view(-1), pred, 'pred')
+    _close(eloss[0], loss, 'loss')
+    for name, g in eng.named_grads().items():
+        _close(g, grads[name], 'grad ' + name)
+
+
+def test_fout_isolated_node_follows_reference_nan_rule(lib):
+    """A node without neighbour gives a NaN FoutLayer row (foutnet.py:73); scatter_max never
+    selects a NaN, so the network output and all gradients stay finite and equal the oracle's."""
+    from deeprank_gnn_b200 import synthetic
+    graphs = synthetic.make_graphs('cfg2', count=3, seed=6)
+    g0 = graphs[0]
+    victim = 17
+    keep = (g0.edge_index[0] != victim) & (g0.edge_index[1] != victim)
+    g0.edge_index = g0.edge_index[:, keep].contiguous()
+    g0.edge_attr = g0.edge_attr[keep].contiguous()
+    sd0, loss, pred, grads, sd1 = _oracle_run('FoutNet', graphs, (16, 32), 1, train=False)
+    assert torch.isfinite(pred).all()
+    eng = _engine('FoutNet', graphs, (16, 32), 1, sd0).eval()
+    eloss, epred = eng.step(_device_batch(graphs))
+    _close(epred.view(-1), pred, 'pred')
+    for name, g in eng.named_grads().items():
+        assert torch.isfinite(g).all(), name
+        _close(g, grads[name], 'grad ' + name)
+
+
+def test_single_graph_batch(lib):
+    graphs = _fixture_graphs()[3:4]
+    sd0, loss, pred, grads, sd1 = _oracle_run('sGAT', graphs, (16, 32), 1)
+    eng = _engine('sGAT', graphs, (16, 32), 1, sd0)
+    eloss, epred = eng.step(_device_batch(graphs))
+    _close(epred.view(-1), pred, 'pred')
+    for name, g in eng.named_grads().items():
+        _close(g, grads[name], 'grad ' + name)
+
+
+@pytest.mark.parametrize('net', ['GINet', 'sGAT'])
+def test_packed_graph_replay_equals_eager(lib, net):
+    """PackedBatch (int32, one H2D copy) + CUDA-graph replay == eager int64 path, several steps."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch
+    from deeprank_gnn_b200.engine import Engine
+    batches = [synthetic.make_graphs('cfg2', count=8, seed=s) for s in (1, 2, 3)]
+    e1 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0)
+    e2 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0, graph=True)
+    e3 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0, tiled=True)
+    for rep in range(2):
+        for graphs in batches:
+            l1, p1 = e1.step(_device_batch(graphs))
+            pb = PackedBatch.from_batch(Batch.from_data_list(graphs))
+            l2, p2 = e2.step(e2.upload(pb))
+            l3, p3 = e3.step(e3.upload(pb))
+            assert torch.equal(p1, p2) and torch.equal(l1, l2)
+            assert torch.equal(p1, p3)
+    assert torch.equal(e1.params.data, e2.params.data)
+    assert torch.equal(e1.params.data, e3.params.data)
+
+
+def test_mathmode_tf32x3_within_tolerance(lib):
+    from deeprank_gnn_b200 import ops, synthetic
+    graphs = synthetic.make_graphs('cfg2', count=8, seed=8)
+    sd0, loss, pred, grads, sd1 = _oracle_run('GINet', graphs, (16, 32), 1, train=False)
+    eng = _engine('GINet', graphs, (16, 32), 1, sd0).eval()
+    old = ops.default_math
+    ops.default_math = ops.MATH_TF32X3
+    try:
+        eloss, epred = eng.step(_device_batch(graphs))
+        _close(epred.view(-1), pred, 'pred')
+        for name, g in eng.named_grads().items():
+            _close(g, grads[name], 'grad ' + name)
+    finally:
+        ops.default_math = old
