@@ -119,7 +119,10 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 _lib = None
-launch_count = 0           # number of C-ABI compute calls made by this process (bench: gpu_launches)
+launch_count = 0           # C-ABI compute calls made by this process
+kernel_count = 0           # CUDA kernels those calls launched (bench: gpu_launches)
+KERNELS_PER_CALL = {'drgnn_structure_build': 2, 'drgnn_cluster_offset': 2, 'drgnn_linear_wgrad': 2,
+                    'drgnn_adam_flat': 2}
 
 
 class DrgnnError(RuntimeError):
@@ -166,7 +169,8 @@ def require_cuda(*tensors):
 
 def call(name, *args):
     """Invoke one C-ABI entry point, raising DrgnnError on a non-zero status."""
-    global launch_count
+    global launch_count, kernel_count
     rc = getattr(load(), name)(*args)
     launch_count += 1
+    kernel_count += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)

@@ -158,11 +158,13 @@ class PackedBatch(object):
     (``NeuralNet.py:491``), which moves ~10 tensors separately.  Indices are int32.
 
     Sections (each padded to 16 bytes), all 4-byte elements viewed from one float32 buffer:
-    ``x[N,F] edge_attr[E,ne] y[B] | edge_index[2,E] cluster0[N] cluster1[L1] node_ptr[B+1]
-    edge_ptr[B+1] c1_ptr[B+1] | y_class[B] (int64, classification only)``.
+    ``x[N,F] edge_attr[E,ne] y[B] | edge_index[2,E] cluster0[N] node_ptr[B+1] edge_ptr[B+1]
+    c1_ptr[B+1] | y_class[B] (int64, classification only) | cluster1[L1]``.  The only section
+    whose length is not fixed by (B, N, E) comes last, so batches of equal (B, N, E) share
+    every section offset (``layout_key``) and one captured CUDA graph serves them all.
     """
     FLOAT_SECTIONS = ('x', 'edge_attr', 'y')
-    INT_SECTIONS = ('edge_index', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr')
+    INT_SECTIONS = ('edge_index', 'cluster0', 'node_ptr', 'edge_ptr', 'c1_ptr')
 
     def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False):
         self.B, self.N, self.E, self.L1, self.F, self.ne = B, N, E, L1, F, ne
@@ -178,12 +180,14 @@ class PackedBatch(object):
         if with_class:
             self.offsets['y_class'] = (o, 2 * B)
             o += _pad4(2 * B)
-        self.numel = o
+        self.offsets['cluster1'] = (o, L1)
+        self.numel = o + _pad4(L1)
+        self.capacity_numel = o + _pad4(N)          # len(cluster1) <= N
         self.buf = None
         self.mol = None
 
-    def key(self):
-        return (self.B, self.N, self.E, self.L1, self.F, self.ne, self.max_n, self.max_e, self.with_class)
+    def layout_key(self):
+        return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class)
 
     @property
     def nbytes(self):
@@ -197,7 +201,7 @@ class PackedBatch(object):
             o, n = self.offsets[k]
             v[k] = buf[o:o + n]
         ibuf = buf.view(torch.int32)
-        for k in self.INT_SECTIONS:
+        for k in self.INT_SECTIONS + ('cluster1',):
             o, n = self.offsets[k]
             v[k] = ibuf[o:o + n]
         v['x'] = v['x'].view(self.N, self.F)

@@ -165,7 +165,7 @@ class Workspace(object):
 class DeviceBatch(object):
     """The tensors of one mini-batch the engine consumes, resident on the device."""
     __slots__ = ('x', 'edge_index', 'edge_attr', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr', 'y',
-                 'y_class', 'B', 'N', 'E', 'L1', 'max_n', 'max_e', 'mol', 'key')
+                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'mol', 'key')
 
     @staticmethod
     def from_batch(batch, device, classes=None):
@@ -199,6 +199,7 @@ class DeviceBatch(object):
         d.max_n, d.max_e = int(batch._max_n), int(batch._max_e)
         d.mol = getattr(batch, 'mol', None)
         d.key = None
+        d.L1b = d.L1                     # upper bound of level-1 rows used for launch sizes
         return d
 
     @staticmethod
@@ -211,7 +212,8 @@ class DeviceBatch(object):
         d.node_ptr, d.edge_ptr, d.c1_ptr = v['node_ptr'], v['edge_ptr'], v['c1_ptr']
         d.B, d.N, d.E, d.L1, d.max_n, d.max_e = pb.B, pb.N, pb.E, pb.L1, pb.max_n, pb.max_e
         d.mol = pb.mol
-        d.key = pb.key()
+        d.key = pb.layout_key()
+        d.L1b = pb.N                     # fixed bound: batches of one layout replay the same CUDA graph
         return d
 
 
@@ -245,6 +247,7 @@ class Engine(object):
         self.struct = None
         self._graphs = {}
         self._staging = {}
+        self._copy_stream = None
         self.launches_per_step = 0
         self.reset_parameters(seed)
 
@@ -383,17 +386,17 @@ class Engine(object):
         self._W1, self._W2 = W1, W2
         ops.linear(ws.Zin1[:N], W1, s.Kin1, s.C1, ws.Z1[:N], bias=b1, w_layout=s.w_layout, relu=True)
         # level-0 cluster max-pool (community_pooling.py:201)
-        ops.maxpool_fwd(ws.Z1[:N], st.cmptr0, st.cmem0, ws.P1[:d.L1], ws.arg0[:d.L1], n_clusters_dev=K0d)
+        ops.maxpool_fwd(ws.Z1[:N], st.cmptr0, st.cmem0, ws.P1[:d.L1b], ws.arg0[:d.L1b], n_clusters_dev=K0d)
         # conv2 on the coarsened graph
         ew1 = st.edge_attr1.view(-1) if s.kind == 'sgat' else None
-        L1 = d.L1
+        L1 = d.L1b
         self._conv_aggregate(1, ws.P1[:L1], st.rowptr1, st.col1, ws.Zin2[:L1], L1, K0d, ew1, ws.s1, ws.post1, None, 0)
         g2 = s.nb if s.kind == 'ginet' else 1
         ops.linear(ws.Zin2[:L1], W2, s.Kin2 // g2, s.h2, ws.Z2[:L1], bias=b2, groups=g2, w_layout=s.w_layout, relu=True,
                    rows_dev=K0d)
         # level-1 max-pool (max_pool_x) and graph read-out (scatter_mean by batch)
         ops.maxpool_fwd(ws.Z2[:L1], st.cmptr1, st.cmem1, ws.P2[:L1], ws.arg1[:L1], n_clusters_dev=K1d)
-        ops.segment_mean_fwd(ws.P2[:L1], st.kptr1, ws.R[:B])
+        ops.segment_mean_fwd(ws.P2[:L1], st.kptr1[:B + 1], ws.R[:B])
         # heads
         drop = self.training and s.dropout > 0
         if drop:
@@ -409,7 +412,7 @@ class Engine(object):
     # ---------------------------------------------------------------- backward
     def _backward(self, d):
         s, ws, st, P = self.spec, self.ws, self.struct, self.params
-        N, B, L1 = d.N, d.B, d.L1
+        N, B, L1 = d.N, d.B, d.L1b
         K0d = st.K0_dev
         pv = lambda name: P.view(P.data, name)
         gv = lambda name: P.view(self.grads, name)
@@ -423,7 +426,7 @@ class Engine(object):
         ops.linear_wgrad(ws.R[:B], ws.dH[:B], s.C2, s.Hd, gv('fc1.weight'), gv('fc1.bias'), work=ws.wwork)
         ops.linear(ws.dH[:B], pv('fc1.weight'), s.Hd, s.C2, ws.dR[:B], w_layout=1)
         # read-out and level-1 pool
-        ops.segment_mean_bwd(ws.dR[:B], st.kptr1, ws.dP2[:L1])
+        ops.segment_mean_bwd(ws.dR[:B], st.kptr1[:B + 1], ws.dP2[:L1])
         ops.maxpool_bwd(ws.dP2[:L1], ws.arg1[:L1], st.cl1, ws.dZ2[:L1], relu_out=ws.Z2[:L1], n_nodes_dev=K0d)
         # conv2
         g2 = s.nb if s.kind == 'ginet' else 1
@@ -517,23 +520,23 @@ class Engine(object):
     # ---------------------------------------------------------------- packed batches / CUDA graphs
     def upload(self, pb, slot=0):
         """ONE host->device copy of a ``PackedBatch`` into a persistent device staging buffer
-        (per shape and slot, so CUDA-graph replays see fixed addresses).  Returns a DeviceBatch."""
-        key = (pb.key(), slot)
-        ent = self._staging.get(key)
-        if ent is None:
-            dev = torch.empty(pb.numel, dtype=F32, device=self.device)
-            ent = (dev, DeviceBatch.from_packed(pb, dev))
-            self._staging[key] = ent
-        dev, d = ent
-        dev.copy_(pb.buf, non_blocking=True)
-        d.mol = pb.mol
+        (one per layout and slot, so CUDA-graph replays see fixed addresses).  Returns a
+        DeviceBatch of views into it."""
+        key = (pb.layout_key(), slot)
+        dev = self._staging.get(key)
+        if dev is None:
+            dev = torch.empty(pb.capacity_numel, dtype=F32, device=self.device)
+            self._staging[key] = dev
+        dev[:pb.numel].copy_(pb.buf, non_blocking=True)
+        d = DeviceBatch.from_packed(pb, dev)
+        d.key = key
         return d
 
     def _step_graph(self, d, inv):
         """Replay (capture on first use) the whole step as one CUDA graph.  The graph is tied to
         the staging buffer of the batch's shape; with several ranks the gradient all-reduce sits
         between the two captured halves."""
-        key = (d.key, id(d), round(inv, 12), self.training)
+        key = (d.key, round(inv, 12), self.training)
         ent = self._graphs.get(key)
         if ent is None:
             # warm up un-captured (first-use attribute setup, workspace growth), then capture
@@ -568,6 +571,49 @@ class Engine(object):
             self._all_reduce()
             g2.replay()
         return self.ws.loss, self.ws.pred[:d.B]
+
+    def train_batches(self, packed_batches, B_global=None, inv_norms=None, train=True):
+        """Pipelined pass over ``PackedBatch`` objects held in (pinned) host memory - the inner
+        loop of ``NeuralNet._epoch`` / ``eval`` (NeuralNet.py:490-523, 432-460).  Per batch:
+        ONE host->device copy on a copy stream (two staging slots, so the copy of batch i+1
+        overlaps the compute of batch i), the fused step (or forward + loss when
+        ``train=False``), and an asynchronous device->host read of ``[loss, pred...]`` into
+        pinned memory.  One host synchronisation at the end.  Returns (losses [n], preds list)."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        cs = self._copy_stream
+        outs = []
+        was_training = self.training
+        self.train(train)
+        for i, pb in enumerate(packed_batches):
+            slot = i & 1
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self._slot_free[slot])
+                d = self.upload(pb, slot)
+                self._slot_ready[slot].record(cs)
+            main.wait_event(self._slot_ready[slot])
+            inv = None if inv_norms is None else inv_norms[i]
+            if train:
+                loss, pred = self.step(d, B_global=B_global, inv_norm=inv)
+            else:
+                pred = self._forward(d)
+                loss = self._loss(d, self._inv_norm(d, B_global, inv), with_grad=False) \
+                    if (d.y is not None or d.y_class is not None) else self.ws.loss
+            host = torch.empty(1 + pred.numel(), dtype=F32, pin_memory=True)
+            host[:1].copy_(loss, non_blocking=True)
+            host[1:].copy_(pred.reshape(-1), non_blocking=True)
+            self._slot_free[slot].record(main)
+            outs.append((host, tuple(pred.shape)))
+        main.synchronize()
+        self.train(was_training)
+        losses = torch.stack([h[0] for h, _ in outs]) if outs else torch.zeros(0)
+        preds = [h[1:].view(shape) for h, shape in outs]
+        return losses, preds
 
     def validate(self):
         """Raise if the last structure pass flagged invalid input (ONE host sync)."""

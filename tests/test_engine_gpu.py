@@ -190,10 +190,13 @@ def test_packed_graph_replay_equals_eager(lib, net):
             pb = PackedBatch.from_batch(Batch.from_data_list(graphs))
             l2, p2 = e2.step(e2.upload(pb))
             l3, p3 = e3.step(e3.upload(pb))
-            assert torch.equal(p1, p2) and torch.equal(l1, l2)
-            assert torch.equal(p1, p3)
-    assert torch.equal(e1.params.data, e2.params.data)
-    assert torch.equal(e1.params.data, e3.params.data)
+            # same kernels, but the packed path sizes level-1 launches by the fixed bound N instead of
+            # len(cluster1): the weight-gradient reduction is chunked differently (fp32 summation order)
+            torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(l2, l1, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(p3, p1, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(e2.params.data, e1.params.data, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(e3.params.data, e1.params.data, rtol=1e-3, atol=1e-4)
 
 
 def test_mathmode_tf32x3_within_tolerance(lib):
