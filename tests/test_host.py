@@ -1,0 +1,212 @@
+"""CPU tests of the host side: C-ABI exports, record / batch / packed-batch logic, HDF5 reader,
+dataset API, parameter layout, sharding and the 2-rank (gloo) gradient all-reduce contract."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import FIXTURE, ROOT
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """libdrgnn.so loads and exports exactly what include/drgnn.h declares (no compute call)."""
+    hdr = open(os.path.join(ROOT, 'include', 'drgnn.h')).read()
+    declared = set(re.findall(r'\b(drgnn_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    from deeprank_gnn_b200 import _lib
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.drgnn_version() == 100
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r'\bT (drgnn_[a-z0-9_]+)', out))
+    assert declared <= exported
+
+
+def test_ctypes_structs_match_header_layout(lib):
+    """Field counts / order of the ctypes mirrors follow the header (a mismatch would shift pointers)."""
+    from deeprank_gnn_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'drgnn.h')).read()
+
+    def fields(struct):
+        body = hdr[hdr.index('typedef struct ' + struct):]
+        body = body[body.index('{') + 1:body.index('} ' + struct)]
+        body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+        names = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if decl:
+                names.append(re.findall(r'([A-Za-z0-9_]+)\s*$', decl)[0])
+        return names
+
+    assert fields('drgnn_structure_io') == [f[0] for f in _lib.StructureIO._fields_]
+    assert fields('drgnn_aggregate_args') == [f[0] for f in _lib.AggregateArgs._fields_]
+    assert fields('drgnn_linear_args') == [f[0] for f in _lib.LinearArgs._fields_]
+    assert fields('drgnn_linear_wgrad_args') == [f[0] for f in _lib.LinearWgradArgs._fields_]
+
+
+def test_product_refuses_cpu_tensors(lib):
+    from deeprank_gnn_b200 import ops
+    from deeprank_gnn_b200._lib import DrgnnError
+    x = torch.zeros(4, 4)
+    with pytest.raises(DrgnnError):
+        ops.aggregate(x, torch.zeros(5, dtype=torch.int32), torch.zeros(0, dtype=torch.int32), torch.zeros(4, 4))
+    from deeprank_gnn_b200.engine import Engine
+    with pytest.raises(DrgnnError):
+        Engine('GINet', 8, device='cpu')
+
+
+def test_hdf5_reader_reads_fixture_values():
+    from deeprank_gnn_b200 import hdf5min
+    with hdf5min.File(FIXTURE) as f:
+        names = list(f.keys())
+        assert len(names) == 10 and names[0] == '1ATN_10w'
+        g = f['1ATN_1w']
+        assert sorted(g['node_data'].keys()) == ['bsa', 'chain', 'charge', 'cons', 'depth', 'hse', 'ic', 'polarity',
+                                                 'pos', 'pssm', 'type']
+        assert g['node_data/pssm'][()].shape == (132, 20) and g['node_data/hse'][()].shape == (132, 3)
+        assert g['edge_index'][()].shape == (374, 2) and g['edge_index'][()].dtype == np.int64
+        assert abs(float(g['score/irmsd'][()]) - 14.919) < 1e-9
+        assert g['clustering/mcl/depth_0'][()].shape == (132,)
+        d = g['edge_data/dist'][()]
+        assert d.dtype == np.float64 and 0 < d.min() and d.max() <= 8.5 + 1e-6
+
+
+def test_dataset_api_and_filter():
+    from deeprank_gnn_b200.DataSet import DivideDataSet, HDF5DataSet, PreCluster
+    ds = HDF5DataSet(database=FIXTURE, node_feature=['type', 'polarity', 'bsa', 'depth', 'hse', 'ic', 'pssm'],
+                     target='irmsd')
+    assert ds.len() == 10 and ds.get(0).num_features == 28            # tests/test_nn.py feature list -> F = 28
+    PreCluster(ds, 'mcl')                                             # clusters are stored in the fixture
+    tr, va = DivideDataSet(ds, percent=[0.8, 0.2])
+    assert tr.len() == 8 and va.len() == 2
+    assert HDF5DataSet(database=FIXTURE, dict_filter={'irmsd': '<10'}, target='irmsd').len() == 0
+    assert HDF5DataSet(database=FIXTURE, dict_filter={'irmsd': '>15 and <16'}, target='irmsd').len() == 6
+    sub = HDF5DataSet(database=FIXTURE, index=[0, 2], target='fnat')
+    assert [m for _, m in sub.index_complexes] == ['1ATN_10w', '1ATN_2w']
+    with pytest.raises(ValueError):
+        HDF5DataSet(database=FIXTURE, node_feature=['nope'])
+
+
+def test_batch_collation_and_packed_roundtrip():
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, DataLoader, PackedBatch
+    graphs = synthetic.make_graphs('cfg2', count=5, seed=3)
+    b = Batch.from_data_list(graphs)
+    assert b.num_graphs == 5 and b._node_ptr.tolist() == [0, 200, 400, 600, 800, 1000]
+    assert b._edge_ptr.tolist() == [0, 1000, 2000, 3000, 4000, 5000]
+    assert b._c1_ptr[-1] == b.cluster1.numel() and b._max_n == 200 and b._max_e == 1000
+    assert torch.equal(b.edge_index[:, 1000:2000], graphs[1].edge_index + 200)
+    assert torch.equal(b.cluster0[200:400], graphs[1].cluster0)                 # clusters are not offset
+    pb = PackedBatch.from_batch(b, pin=False)
+    v = pb.views(pb.buf)
+    assert torch.equal(v['x'], b.x) and torch.equal(v['edge_attr'], b.edge_attr) and torch.equal(v['y'], b.y)
+    assert torch.equal(v['edge_index'].long(), b.edge_index) and torch.equal(v['cluster1'].long(), b.cluster1)
+    assert torch.equal(v['c1_ptr'], b._c1_ptr)
+    other = PackedBatch.from_batch(Batch.from_data_list(synthetic.make_graphs('cfg2', count=5, seed=9)), pin=False)
+    assert other.layout_key() == pb.layout_key() and other.capacity_numel == pb.capacity_numel
+    for k in PackedBatch.FLOAT_SECTIONS + PackedBatch.INT_SECTIONS:
+        assert other.offsets[k][0] == pb.offsets[k][0]                          # one CUDA graph serves both
+    pc = PackedBatch.from_batch(b, pin=False, classes=[0, 1])
+    assert pc.views(pc.buf)['y_class'].dtype == torch.int64
+
+    class DS(object):
+        def len(self):
+            return len(graphs)
+
+        def get(self, i):
+            return graphs[i]
+    sizes = [bb.num_graphs for bb in DataLoader(DS(), batch_size=2)]
+    assert sizes == [2, 2, 1]
+
+
+def test_synthetic_graphs_follow_the_fixture_shape():
+    from deeprank_gnn_b200 import synthetic
+    for g in synthetic.make_graphs('cfg2', count=6, seed=0):
+        n = g.x.size(0)
+        row, col = g.edge_index
+        e = row.numel() // 2
+        assert n == 200 and 2 * e == 1000
+        assert torch.equal(row[:e], col[e:]) and torch.equal(col[:e], row[e:])
+        assert (torch.bincount(row, minlength=n) > 0).all()
+        assert (g.edge_index[0] != g.edge_index[1]).all()
+        assert torch.unique(row * n + col).numel() == 2 * e
+        assert g.cluster1.numel() == g.cluster0.unique().numel()
+        na = (n + 1) // 2
+        assert bool(((row < na) != (col < na)).all())                           # strictly inter-chain
+    assert synthetic.make_graph(200, 1000, 32, 5).x.equal(synthetic.make_graph(200, 1000, 32, 5).x)
+
+
+def test_flat_parameter_layout_and_reference_names():
+    from deeprank_gnn_b200.engine import NetSpec
+    from oracle import nets as onets
+    for kind, cls in (('GINet', onets.GINet), ('sGAT', onets.sGAT), ('FoutNet', onets.FoutNet)):
+        for F, out, hidden in ((3, 1, (16, 32)), (48, 2, (16, 32)), (32, 1, (32, 64))):
+            spec = NetSpec(kind, F, out, 1, hidden)
+            ref = cls(F, out, 1, hidden=hidden).state_dict()
+            assert spec.reference_order() == list(ref.keys())
+            shapes = {n: tuple(s) for n, s, _ in spec.param_shapes()}
+            assert shapes == {k: tuple(v.shape) for k, v in ref.items()}
+
+
+def test_shard_indices_balance_and_cover():
+    from deeprank_gnn_b200.parallel import shard_indices
+    rng = np.random.default_rng(0)
+    costs = [int(c) for c in rng.integers(400, 9000, size=512)]
+    parts = shard_indices(costs, 8, balance=True)
+    assert sorted(i for p in parts for i in p) == list(range(512))
+    assert all(len(p) == 64 for p in parts)
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) / (sum(loads) / 8) < 1.02
+    flat = shard_indices(list(range(10)), 4, balance=False)
+    assert flat == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+
+
+WORKER = r'''
+import os, sys, copy
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import torch, torch.distributed as dist
+from deeprank_gnn_b200 import synthetic, parallel
+from helpers import to_oracle_batch
+from oracle import nets as onets, step as ostep
+rank, world, _ = parallel.init_distributed('gloo')
+graphs = synthetic.make_graphs(dict(nodes=(30, 120), edges_per_node=6, feat=8, batch=10), count=10, seed=7)
+torch.manual_seed(0)
+model = onets.sGAT(8, 1, 1).eval()
+# full-batch gradient (what one process computes)
+full = copy.deepcopy(model)
+pred = full(to_oracle_batch(graphs)).reshape(-1)
+y = torch.cat([g.y for g in graphs])
+torch.nn.MSELoss()(pred, y).backward()
+ref = torch.cat([p.grad.reshape(-1) for p in full.parameters()])
+# sharded: local sum / B_global, then ONE all-reduce of the flat gradient buffer
+mine = parallel.shard_graphs(graphs, world, rank, balance=True)
+pred = model(to_oracle_batch(mine)).reshape(-1)
+y = torch.cat([g.y for g in mine])
+(((pred - y) ** 2).sum() / len(graphs)).backward()
+flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+parallel.all_reduce_flat_(flat)
+err = float((flat - ref).abs().max())
+sizes = [None] * world
+dist.all_gather_object(sizes, len(mine))
+assert sum(sizes) == 10 and max(sizes) - min(sizes) <= 1, sizes
+assert err < 1e-5, err
+print('rank', rank, 'ok', err)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_gradient_allreduce_equals_full_batch(tmp_path):
+    """world_size 2 on CPU (gloo): graph sharding + loss = sum/B_global + one flat all-reduce
+    reproduces the single-process gradient of MSELoss(mean)."""
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % {'root': ROOT})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29631', str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count('ok') == 2
