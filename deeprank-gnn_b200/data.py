@@ -65,6 +65,9 @@ class Data(object):
     def clone(self):
         out = self.__class__.__new__(self.__class__)
         for k, v in self.__dict__.items():
+            if k == '_structure':           # device-side cache of the structure pass: shared, read-only
+                out.__dict__[k] = v
+                continue
             out.__dict__[k] = v.clone() if torch.is_tensor(v) else copy.deepcopy(v)
         return out
 
@@ -185,6 +188,7 @@ class PackedBatch(object):
         self.capacity_numel = o + _pad4(N)          # len(cluster1) <= N
         self.buf = None
         self.mol = None
+        self.has_y = False
 
     def layout_key(self):
         return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class)
@@ -237,6 +241,7 @@ class PackedBatch(object):
             v['edge_attr'].copy_(ea)
         y = getattr(batch, 'y', None)
         if y is not None:
+            pb.has_y = True
             v['y'].copy_(y.reshape(-1))
             if classes is not None:
                 c2i = {int(c): i for i, c in enumerate(classes)}

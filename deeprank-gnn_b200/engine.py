@@ -207,7 +207,7 @@ class DeviceBatch(object):
         """Views into ``dev_buf`` (device float32 buffer holding a copy of ``pb.buf``)."""
         d = DeviceBatch()
         v = pb.views(dev_buf)
-        d.x, d.edge_attr, d.y, d.y_class = v['x'], v['edge_attr'], v['y'], v['y_class']
+        d.x, d.edge_attr, d.y, d.y_class = v['x'], v['edge_attr'], (v['y'] if pb.has_y else None), v['y_class']
         d.edge_index, d.cluster0, d.cluster1 = v['edge_index'], v['cluster0'], v['cluster1']
         d.node_ptr, d.edge_ptr, d.c1_ptr = v['node_ptr'], v['edge_ptr'], v['c1_ptr']
         d.B, d.N, d.E, d.L1, d.max_n, d.max_e = pb.B, pb.N, pb.E, pb.L1, pb.max_n, pb.max_e
