@@ -252,6 +252,8 @@ def aggregation_roofline(cfg, graphs, n_nodes_target, hbm_gbs, peak_src, in_situ
     nb = base.num_graphs
     tile_ptr = torch.cat([(base._node_ptr[:nb].to(dev).view(1, -1) + off_n).reshape(-1),
                           torch.tensor([N], dtype=torch.int32, device=dev)])
+    tile_eptr = torch.cat([(base._edge_ptr[:nb].to(dev).view(1, -1) + off_e).reshape(-1),
+                           torch.tensor([E], dtype=torch.int32, device=dev)])
     x = torch.randn(N, C, device=dev)
     out = torch.empty(N, C, device=dev)
     alg_bytes = 4.0 * N * C * 2 + 4.0 * E + 4.0 * (N + 1)
@@ -269,7 +271,8 @@ def aggregation_roofline(cfg, graphs, n_nodes_target, hbm_gbs, peak_src, in_situ
         return s.elapsed_time(e) / iters      # ms
 
     t_rows = timed(lambda: ops.aggregate(x, rowptr, col, out))
-    t_tiled = timed(lambda: ops.aggregate(x, rowptr, col, out, tile_ptr=tile_ptr, max_tile_rows=base._max_n))
+    t_tiled = timed(lambda: ops.aggregate(x, rowptr, col, out, tile_ptr=tile_ptr, tile_eptr=tile_eptr,
+                                          max_tile_rows=base._max_n, max_tile_edges=base._max_e))
     best, t_best = ('aggregate_tiled_kernel', t_tiled) if t_tiled < t_rows else ('aggregate_rows_kernel', t_rows)
     achieved = alg_bytes / (t_best * 1e-3) / 1e9
     # in situ: the same kernel on ONE step-sized batch, averaged over back-to-back launches

@@ -100,7 +100,7 @@ _SIGNATURES = {
     'drgnn_cluster_offset': (C.c_int, [VP, VP, _i32, VP, VP]),
     'drgnn_ptr_from_sorted_ids': (C.c_int, [VP, _i32, _i32, VP, VP, VP]),
     'drgnn_aggregate': (C.c_int, [C.POINTER(AggregateArgs), VP]),
-    'drgnn_aggregate_tiled': (C.c_int, [C.POINTER(AggregateArgs), VP, _i32, _i32, VP]),
+    'drgnn_aggregate_tiled': (C.c_int, [C.POINTER(AggregateArgs), VP, VP, _i32, _i32, _i32, VP]),
     'drgnn_linear': (C.c_int, [C.POINTER(LinearArgs), VP]),
     'drgnn_linear_wgrad_work_floats': (_i64, [_i32, _i32, _i32, _i32]),
     'drgnn_linear_wgrad': (C.c_int, [C.POINTER(LinearWgradArgs), VP]),

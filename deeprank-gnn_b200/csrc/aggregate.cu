@@ -17,10 +17,18 @@ namespace drgnn {
 
 struct AggParams {
   drgnn_aggregate_args a;
-  const int32_t* tile_ptr;
+  const int32_t* tile_ptr;   // [n_tiles+1] row range of every tile
+  const int32_t* tile_eptr;  // [n_tiles+1] CSR slot range of every tile (= rowptr[tile_ptr[t]])
   int32_t n_tiles;
   int32_t max_tile_rows;
+  int32_t max_tile_edges;
 };
+
+__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+// shared-memory floats (4-byte words) of one staging buffer: x tile | rowptr slice | col slice | ew slice
+__host__ __device__ inline int tile_buf_words(int max_rows, int max_edges, int C, bool weights) {
+  return max_rows * C + round4(max_rows + 1 + 4) + round4(max_edges + 4) * (weights ? 2 : 1);
+}
 
 __device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
 
@@ -32,56 +40,91 @@ __device__ __forceinline__ float post_scale(int mode, int deg) {
 
 // One sub-warp of G lanes per row; lane `sl` owns channels [4*sl, 4*sl+4).
 // SrcFn maps a source node id to a pointer to its row (global or shared memory).
-template <int G, typename SrcFn>
-__device__ __forceinline__ void aggregate_row(const drgnn_aggregate_args& a, int row, int sl, SrcFn src_row) {
-  const int C = a.C;
-  const bool on = (sl * 4) < C;
-  const int s = a.rowptr[row], e = a.rowptr[row + 1];
+//
+// Inner loop (the part that has to run at HBM speed): the G lanes of the sub-warp load G
+// consecutive `col` entries (and weights) with ONE coalesced instruction, then broadcast them
+// with shuffles and issue up to U independent 16-byte row loads before accumulating, in
+// ascending edge order.  WEIGHTED / EPI are compile-time so the plain sum (GINet forward and
+// backward, the headline case) carries no per-edge branch, no weight traffic and no epilogue.
+//
+// rp / cl / ew point at the CSR arrays such that rp[row], cl[p], ew[p] are valid for the absolute
+// row / slot ids used here: the global arrays themselves, or shared-memory copies of one tile's
+// slices (pre-offset), in which case nothing in the loop touches global memory but `sscale`.
+template <int G, bool WEIGHTED, bool EPI, typename SrcFn>
+__device__ __forceinline__ void aggregate_row(const drgnn_aggregate_args& a, const int32_t* __restrict__ rp,
+                                              const int32_t* __restrict__ cl, const float* __restrict__ ew, int row,
+                                              bool valid, int sl, bool on, SrcFn src_row) {
+  // Called by ALL 32 lanes of the warp (control flow below is warp-uniform so every shuffle uses
+  // the full mask and compiles to one SHFL); `valid` = this sub-warp owns a real row.
+  constexpr int U = G < 8 ? G : 8;
+  constexpr unsigned FULL = 0xffffffffu;
+  int s = 0, e = 0;
+  if (valid) {
+    s = rp[row];
+    e = rp[row + 1];
+  }
+  const int maxdeg = __reduce_max_sync(FULL, e - s);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float wsum = 0.f;
-  int p = s;
-  for (; p + 4 <= e; p += 4) {
-    int c[4];
-    float w[4];
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) c[u] = __ldg(a.col + p + u);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float we = a.ew ? __ldg(a.ew + p + u) : 1.f;
-      wsum += we;
-      w[u] = a.sscale ? we * __ldg(a.sscale + c[u]) : we;
+  for (int base = 0; base < maxdeg; base += G) {
+    const int my = s + base + sl;
+    int c = 0;
+    float w = 0.f;
+    if (my < e) {
+      c = cl[my];
+      if (WEIGHTED) {
+        const float we = ew ? ew[my] : 1.f;
+        wsum += we;
+        w = a.sscale ? we * __ldg(a.sscale + c) : we;
+      }
     }
+    const int cnt = e - s - base;              // edges left in this sub-warp's row (may be <= 0)
+    const int wcnt = min(G, maxdeg - base);    // warp-uniform trip count
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      v[u] = on ? *reinterpret_cast<const float4*>(src_row(c[u]) + sl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < G; j0 += U) {
+      if (j0 >= wcnt) break;
+      float4 v[U];
+      float wj[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc.x = fmaf(w[u], v[u].x, acc.x);
-      acc.y = fmaf(w[u], v[u].y, acc.y);
-      acc.z = fmaf(w[u], v[u].z, acc.z);
-      acc.w = fmaf(w[u], v[u].w, acc.w);
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(FULL, c, j0 + u, G);
+        if (WEIGHTED) wj[u] = __shfl_sync(FULL, w, j0 + u, G);
+        v[u] = (on && (j0 + u) < cnt) ? *reinterpret_cast<const float4*>(src_row(cj) + sl * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (WEIGHTED) {
+          acc.x = fmaf(wj[u], v[u].x, acc.x);
+          acc.y = fmaf(wj[u], v[u].y, acc.y);
+          acc.z = fmaf(wj[u], v[u].z, acc.z);
+          acc.w = fmaf(wj[u], v[u].w, acc.w);
+        } else {
+          acc.x += v[u].x;
+          acc.y += v[u].y;
+          acc.z += v[u].z;
+          acc.w += v[u].w;
+        }
+      }
     }
   }
-  for (; p < e; ++p) {
-    const int c = __ldg(a.col + p);
-    float we = a.ew ? __ldg(a.ew + p) : 1.f;
-    wsum += we;
-    const float w = a.sscale ? we * __ldg(a.sscale + c) : we;
-    if (on) {
-      const float4 v = *reinterpret_cast<const float4*>(src_row(c) + sl * 4);
-      acc.x = fmaf(w, v.x, acc.x);
-      acc.y = fmaf(w, v.y, acc.y);
-      acc.z = fmaf(w, v.z, acc.z);
-      acc.w = fmaf(w, v.w, acc.w);
-    }
+  if (EPI && WEIGHTED && a.self_mode == 2) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) wsum += __shfl_xor_sync(FULL, wsum, o, G);
+  }
+  if (!valid) return;
+  if (!EPI) {
+    if (on) *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ld_out + sl * 4) = acc;
+    return;
   }
   const float post = post_scale(a.post_mode, e - s);
   acc.x *= post; acc.y *= post; acc.z *= post; acc.w *= post;
   float selfc = 0.f;
   if (a.self_mode == 1) selfc = 1.f;
-  else if (a.self_mode == 2) selfc = post * wsum;
-  else if (a.self_mode == 3) selfc = __ldg(a.selfc_in + row);
+  else if (a.self_mode == 2) {
+    if (!WEIGHTED) wsum = (float)(e - s);
+    selfc = post * wsum;
+  } else if (a.self_mode == 3) selfc = __ldg(a.selfc_in + row);
   if (a.self_mode == 2 && a.selfc_out && sl == 0) a.selfc_out[row] = selfc;
   if (a.post_out && sl == 0) a.post_out[row] = post;
   if (!on) return;
@@ -108,18 +151,26 @@ __device__ __forceinline__ void aggregate_row(const drgnn_aggregate_args& a, int
   *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ld_out + sl * 4) = acc;
 }
 
-template <int G>
-__global__ void __launch_bounds__(256) aggregate_rows_kernel(const drgnn_aggregate_args a) {
+// Each CTA walks contiguous chunks of `chunk_rows` rows (graphs are contiguous row ranges, so the
+// neighbour rows a chunk gathers stay in this SM's L1), chunks are dealt round-robin to CTAs.
+template <int G, bool WEIGHTED, bool EPI>
+__global__ void __launch_bounds__(256) aggregate_rows_kernel(const drgnn_aggregate_args a, int chunk_rows) {
   const int n = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   constexpr int RPW = 32 / G;
   const int lane = lane_id();
   const int sub = lane / G, sl = lane % G;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const bool on = (sl * 4) < a.C;
+  const int warp = warp_id(), nwarps = blockDim.x >> 5;
   const float* src = a.src;
   const int ld = a.ld_src;
-  for (int row = wg * RPW + sub; row < n; row += warps_total * RPW)
-    aggregate_row<G>(a, row, sl, [src, ld](int c) { return src + (int64_t)c * ld; });
+  for (int c0 = blockIdx.x * chunk_rows; c0 < n; c0 += gridDim.x * chunk_rows) {
+    const int c1 = min(c0 + chunk_rows, n);
+    for (int rbase = c0 + warp * RPW; rbase < c1; rbase += nwarps * RPW) {  // warp-uniform
+      const int row = rbase + sub;
+      aggregate_row<G, WEIGHTED, EPI>(a, a.rowptr, a.col, a.ew, row, row < c1, sl, on,
+                                      [src, ld](int c) { return src + (int64_t)c * ld; });
+    }
+  }
 }
 
 // generic scalar fallback (any C, any alignment): one warp per row, lanes stride over channels
@@ -187,17 +238,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-template <int G>
+template <int G, bool WEIGHTED, bool EPI>
 __global__ void __launch_bounds__(256) aggregate_tiled_kernel(const AggParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bars[2];
+  __shared__ int tinfo[2][4];  // per buffer: r0, r1, aligned rowptr start, aligned slot start
   const drgnn_aggregate_args& a = P.a;
   const int C = a.C;
-  const int buf_floats = P.max_tile_rows * C;
+  const bool has_w = WEIGHTED && a.ew != nullptr;
+  const int rp_words = round4(P.max_tile_rows + 1 + 4), cl_words = round4(P.max_tile_edges + 4);
+  const int buf_words = tile_buf_words(P.max_tile_rows, P.max_tile_edges, C, has_w);
   float* bufs = reinterpret_cast<float*>(smem_raw);
   constexpr int RPW = 32 / G;
   const int lane = lane_id(), sub = lane / G, sl = lane % G;
   const int warp = warp_id(), nwarps = blockDim.x >> 5;
+  const bool on = (sl * 4) < C;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
@@ -206,31 +261,49 @@ __global__ void __launch_bounds__(256) aggregate_tiled_kernel(const AggParams P)
   }
   __syncthreads();
 
-  // static round-robin over tiles: tile = blockIdx.x + it * gridDim.x
+  // One elected thread streams a whole tile (feature rows + its rowptr / col / weight slices) into
+  // buffer b with bulk async copies that complete on one mbarrier.  Slices start at 16-byte aligned
+  // element ids (the arrays are readable up to the next multiple of 4 elements, see drgnn.h).
   auto issue = [&](int tile, int b) {
-    const int r0 = P.tile_ptr[tile], r1 = P.tile_ptr[tile + 1];
-    const uint32_t bytes = (uint32_t)(r1 - r0) * C * 4u;
-    if (bytes) {
-      mbar_expect_tx(&bars[b], bytes);
-      bulk_g2s(bufs + (size_t)b * buf_floats, a.src + (int64_t)r0 * C, bytes, &bars[b]);
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[b])) : "memory");
+    const int r0 = __ldg(P.tile_ptr + tile), r1 = __ldg(P.tile_ptr + tile + 1);
+    const int e0 = __ldg(P.tile_eptr + tile), e1 = __ldg(P.tile_eptr + tile + 1);
+    const int ra = r0 & ~3, rb = round4(r1 + 1);
+    const int ea = e0 & ~3, eb = round4(e1);
+    float* xs = bufs + (size_t)b * buf_words;
+    int32_t* rps = reinterpret_cast<int32_t*>(xs + P.max_tile_rows * C);
+    int32_t* cls = rps + rp_words;
+    float* ews = reinterpret_cast<float*>(cls + cl_words);
+    const uint32_t bx = (uint32_t)(r1 - r0) * C * 4u, br = (uint32_t)(rb - ra) * 4u, be = (uint32_t)(eb - ea) * 4u;
+    tinfo[b][0] = r0; tinfo[b][1] = r1; tinfo[b][2] = ra; tinfo[b][3] = ea;
+    mbar_expect_tx(&bars[b], bx + br + be * (has_w ? 2u : 1u));
+    if (bx) bulk_g2s(xs, a.src + (int64_t)r0 * C, bx, &bars[b]);
+    bulk_g2s(rps, a.rowptr + ra, br, &bars[b]);
+    if (be) {
+      bulk_g2s(cls, a.col + ea, be, &bars[b]);
+      if (has_w) bulk_g2s(ews, a.ew + ea, be, &bars[b]);
     }
   };
   int tile = blockIdx.x;
   if (tile < P.n_tiles && threadIdx.x == 0) issue(tile, 0);
+  __syncthreads();  // tinfo[0] visible to every warp
   uint32_t phase[2] = {0u, 0u};
   for (int it = 0; tile < P.n_tiles; ++it, tile += gridDim.x) {
     const int b = it & 1;
     const int next = tile + gridDim.x;
-    if (next < P.n_tiles && threadIdx.x == 0) issue(next, b ^ 1);  // buffer b^1 was released by the
-                                                                   // __syncthreads() closing tile it-1
+    if (next < P.n_tiles && threadIdx.x == 0) issue(next, b ^ 1);  // buffer b^1 (and tinfo[b^1]) was released
+                                                                   // by the __syncthreads() closing tile it-1
     mbar_wait(&bars[b], phase[b]);
     phase[b] ^= 1u;
-    const int r0 = P.tile_ptr[tile], r1 = P.tile_ptr[tile + 1];
-    const float* sbuf = bufs + (size_t)b * buf_floats;
-    for (int row = r0 + warp * RPW + sub; row < r1; row += nwarps * RPW)
-      aggregate_row<G>(a, row, sl, [sbuf, r0, C](int c) { return sbuf + (size_t)(c - r0) * C; });
+    const int r0 = tinfo[b][0], r1 = tinfo[b][1], ra = tinfo[b][2], ea = tinfo[b][3];
+    const float* xs = bufs + (size_t)b * buf_words;
+    const int32_t* rps = reinterpret_cast<const int32_t*>(xs + P.max_tile_rows * C);
+    const int32_t* cls = rps + rp_words;
+    const float* ews = has_w ? reinterpret_cast<const float*>(cls + cl_words) - ea : nullptr;
+    for (int rbase = r0 + warp * RPW; rbase < r1; rbase += nwarps * RPW) {  // warp-uniform
+      const int row = rbase + sub;
+      aggregate_row<G, WEIGHTED, EPI>(a, rps - ra, cls - ea, ews, row, row < r1, sl, on,
+                                      [xs, r0, C](int c) { return xs + (size_t)(c - r0) * C; });
+    }
     __syncthreads();
   }
 }
@@ -264,6 +337,20 @@ static int check_args(const drgnn_aggregate_args* a) {
 
 using namespace drgnn;
 
+static inline bool is_weighted(const drgnn_aggregate_args& a) { return a.ew != nullptr || a.sscale != nullptr; }
+static inline bool has_epilogue(const drgnn_aggregate_args& a) {
+  return a.post_mode != 0 || a.self_mode != 0 || a.bias != nullptr || a.relu != 0 || a.post_out != nullptr;
+}
+
+template <int G>
+static void launch_rows(const drgnn_aggregate_args& a, int blocks, int chunk_rows, cudaStream_t st) {
+  const bool w = is_weighted(a), e = has_epilogue(a);
+  if (w && e) aggregate_rows_kernel<G, true, true><<<blocks, 256, 0, st>>>(a, chunk_rows);
+  else if (w) aggregate_rows_kernel<G, true, false><<<blocks, 256, 0, st>>>(a, chunk_rows);
+  else if (e) aggregate_rows_kernel<G, false, true><<<blocks, 256, 0, st>>>(a, chunk_rows);
+  else aggregate_rows_kernel<G, false, false><<<blocks, 256, 0, st>>>(a, chunk_rows);
+}
+
 extern "C" int drgnn_aggregate(const drgnn_aggregate_args* a, void* stream) {
   int rc = check_args(a);
   if (rc) return rc;
@@ -279,54 +366,71 @@ extern "C" int drgnn_aggregate(const drgnn_aggregate_args* a, void* stream) {
   const int lanes = a->C / 4;
   int G = 1;
   while (G < lanes) G <<= 1;
-  const int rows_per_block = 8 * (32 / G);
-  int blocks = min((a->n_rows + rows_per_block - 1) / rows_per_block, sms * 16);
+  const int rows_per_pass = 8 * (32 / G);  // rows one CTA covers per pass (8 warps)
+  // small launches: one pass per CTA (spread over all SMs, latency); large launches: up to 8 passes
+  // of contiguous rows per CTA visit (neighbour rows stay in that SM's L1)
+  int passes = (int)min_i64(8, (int64_t)a->n_rows / ((int64_t)rows_per_pass * sms * 8));
+  if (passes < 1) passes = 1;
+  const int chunk_rows = rows_per_pass * passes;
+  int blocks = (int)min_i64(((int64_t)a->n_rows + chunk_rows - 1) / chunk_rows, (int64_t)sms * 8);
   switch (G) {
-    case 1: aggregate_rows_kernel<1><<<blocks, 256, 0, st>>>(*a); break;
-    case 2: aggregate_rows_kernel<2><<<blocks, 256, 0, st>>>(*a); break;
-    case 4: aggregate_rows_kernel<4><<<blocks, 256, 0, st>>>(*a); break;
-    case 8: aggregate_rows_kernel<8><<<blocks, 256, 0, st>>>(*a); break;
-    case 16: aggregate_rows_kernel<16><<<blocks, 256, 0, st>>>(*a); break;
-    default: aggregate_rows_kernel<32><<<blocks, 256, 0, st>>>(*a); break;
+    case 1: launch_rows<1>(*a, blocks, chunk_rows, st); break;
+    case 2: launch_rows<2>(*a, blocks, chunk_rows, st); break;
+    case 4: launch_rows<4>(*a, blocks, chunk_rows, st); break;
+    case 8: launch_rows<8>(*a, blocks, chunk_rows, st); break;
+    case 16: launch_rows<16>(*a, blocks, chunk_rows, st); break;
+    default: launch_rows<32>(*a, blocks, chunk_rows, st); break;
   }
   DRGNN_CHECK_LAUNCH("aggregate_rows_kernel");
   return DRGNN_OK;
 }
 
-template <int G>
-static int launch_tiled(const AggParams& P, int blocks, size_t smem, cudaStream_t st) {
+template <int G, bool W, bool E>
+static int launch_tiled_v(const AggParams& P, int blocks, size_t smem, cudaStream_t st) {
   static thread_local size_t configured = 0;
   if (smem > configured) {
-    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tiled_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tiled_kernel<G, W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)device_info().smem_optin - 2048));
     configured = device_info().smem_optin - 2048;
   }
-  aggregate_tiled_kernel<G><<<blocks, 256, smem, st>>>(P);
+  aggregate_tiled_kernel<G, W, E><<<blocks, 256, smem, st>>>(P);
   DRGNN_CHECK_LAUNCH("aggregate_tiled_kernel");
   return DRGNN_OK;
 }
 
-extern "C" int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr, int32_t n_tiles,
-                                     int32_t max_tile_rows, void* stream) {
+template <int G>
+static int launch_tiled(const AggParams& P, int blocks, size_t smem, cudaStream_t st) {
+  const bool w = is_weighted(P.a), e = has_epilogue(P.a);
+  if (w && e) return launch_tiled_v<G, true, true>(P, blocks, smem, st);
+  if (w) return launch_tiled_v<G, true, false>(P, blocks, smem, st);
+  if (e) return launch_tiled_v<G, false, true>(P, blocks, smem, st);
+  return launch_tiled_v<G, false, false>(P, blocks, smem, st);
+}
+
+extern "C" int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr, const int32_t* tile_eptr,
+                                     int32_t n_tiles, int32_t max_tile_rows, int32_t max_tile_edges, void* stream) {
   int rc = check_args(a);
   if (rc) return rc;
-  DRGNN_REQUIRE(tile_ptr != nullptr && n_tiles >= 0 && max_tile_rows > 0, "aggregate_tiled: bad tiles");
+  DRGNN_REQUIRE(tile_ptr != nullptr && tile_eptr != nullptr && n_tiles >= 0 && max_tile_rows > 0 && max_tile_edges >= 0,
+                "aggregate_tiled: bad tiles");
   DRGNN_REQUIRE(a->n_rows_dev == nullptr, "aggregate_tiled: n_rows_dev is not supported (tiles define the rows)");
   if (n_tiles == 0) return DRGNN_OK;
-  if (!vector_ok(*a) || a->ld_src != a->C)
+  if (!vector_ok(*a) || a->ld_src != a->C || !aligned16(a->rowptr) || !aligned16(a->col) || (a->ew && !aligned16(a->ew)))
     return fail(DRGNN_ERR_UNSUPPORTED, "aggregate_tiled: needs C %% 4 == 0, C <= 128, ld_src == C, 16-byte alignment");
-  const size_t smem = (size_t)2 * max_tile_rows * a->C * sizeof(float);
+  const size_t smem = (size_t)2 * 4 * tile_buf_words(max_tile_rows, max_tile_edges, a->C, a->ew != nullptr);
   if (smem > (size_t)device_info().smem_optin - 2048)
-    return fail(DRGNN_ERR_UNSUPPORTED, "aggregate_tiled: tile of %d rows x %d channels does not fit shared memory",
-                max_tile_rows, a->C);
+    return fail(DRGNN_ERR_UNSUPPORTED, "aggregate_tiled: tile of %d rows x %d channels / %d edges does not fit shared memory",
+                max_tile_rows, a->C, max_tile_edges);
   AggParams P;
   P.a = *a;
   P.tile_ptr = tile_ptr;
+  P.tile_eptr = tile_eptr;
   P.n_tiles = n_tiles;
   P.max_tile_rows = max_tile_rows;
+  P.max_tile_edges = max_tile_edges;
   const int sms = device_info().sms;
   // CTAs per SM limited by the double buffer; 227 KB usable per SM
-  int per_sm = (int)min_i64(8, (size_t)(227 * 1024) / (smem + 1024));
+  int per_sm = (int)min_i64(8, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
   per_sm = max(per_sm, 1);
   const int blocks = min(n_tiles, sms * per_sm);
   cudaStream_t st = (cudaStream_t)stream;

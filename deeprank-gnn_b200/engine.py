@@ -349,11 +349,12 @@ class Engine(object):
         assert st is self.struct
         return st
 
-    def _conv_aggregate(self, level, src, rowptr, col, Zin, n_rows, n_rows_dev, ew, s_out, post_out, tile_ptr, max_rows):
+    def _conv_aggregate(self, level, src, rowptr, col, Zin, n_rows, n_rows_dev, ew, s_out, post_out, tiles):
         s = self.spec
         cin = s.F if level == 0 else s.h1
-        tile = dict(tile_ptr=tile_ptr, max_tile_rows=max_rows) if (tile_ptr is not None and src.stride(0) == src.size(1)
-                                                                  and src.size(1) % 4 == 0) else {}
+        tile = {}
+        if tiles is not None and src.stride(0) == src.size(1) and src.size(1) % 4 == 0:
+            tile = dict(tile_ptr=tiles[0], tile_eptr=tiles[1], max_tile_rows=tiles[2], max_tile_edges=tiles[3])
         if s.kind == 'ginet':
             ops.aggregate(src, rowptr, col, Zin, n_rows=n_rows, n_rows_dev=n_rows_dev, **tile)
         elif s.kind == 'sgat':
@@ -370,10 +371,10 @@ class Engine(object):
         K0d, K1d = st.K0_dev, st.K1_dev
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
-        tiled = self.tiled and d.max_n * s.F * 8 <= 200 * 1024
+        tiled = self.tiled and 8 * (d.max_n * s.F + d.max_n + 2 * d.max_e + 32) <= 200 * 1024
         # conv1: aggregate on the level-0 graph, then transform (+bias, ReLU)
         self._conv_aggregate(0, d.x, st.rowptr0, st.col0, ws.Zin1[:N], N, None, st.w0csr, ws.s0, ws.post0,
-                             d.node_ptr if tiled else None, d.max_n)
+                             (d.node_ptr, d.edge_ptr, d.max_n, d.max_e) if tiled else None)
         if s.kind == 'ginet':
             W1, b1 = flat('conv1.fc.weight', s.C1 * s.F), None
             W2, b2 = flat('conv2.fc.weight', s.nb * s.h2 * s.h1), None
@@ -390,7 +391,7 @@ class Engine(object):
         # conv2 on the coarsened graph
         ew1 = st.edge_attr1.view(-1) if s.kind == 'sgat' else None
         L1 = d.L1b
-        self._conv_aggregate(1, ws.P1[:L1], st.rowptr1, st.col1, ws.Zin2[:L1], L1, K0d, ew1, ws.s1, ws.post1, None, 0)
+        self._conv_aggregate(1, ws.P1[:L1], st.rowptr1, st.col1, ws.Zin2[:L1], L1, K0d, ew1, ws.s1, ws.post1, None)
         g2 = s.nb if s.kind == 'ginet' else 1
         ops.linear(ws.Zin2[:L1], W2, s.Kin2 // g2, s.h2, ws.Z2[:L1], bias=b2, groups=g2, w_layout=s.w_layout, relu=True,
                    rows_dev=K0d)

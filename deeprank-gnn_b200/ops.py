@@ -239,10 +239,11 @@ def ptr_from_sorted_ids(ids, B):
 # ------------------------------------------------------------------------------------------
 def aggregate(src, rowptr, col, out, C_=None, ew=None, sscale=None, self_src=None, self_out=None, selfc_in=None,
               selfc_out=None, post_out=None, bias=None, n_rows=None, n_rows_dev=None, post_mode=0, self_mode=0,
-              relu=False, tile_ptr=None, max_tile_rows=0):
+              relu=False, tile_ptr=None, tile_eptr=None, max_tile_rows=0, max_tile_edges=0):
     """out[i] = act(selfc_i * self_src[i] + post_i * sum_p ew[p] * sscale[col[p]] * src[col[p]] + bias)
-    over CSR rows (see ``drgnn_aggregate`` in include/drgnn.h).  With ``tile_ptr`` the
-    shared-memory staged per-graph kernel (``drgnn_aggregate_tiled``) is used."""
+    over CSR rows (see ``drgnn_aggregate`` in include/drgnn.h).  With ``tile_ptr`` / ``tile_eptr``
+    (row and CSR-slot range of every graph) the shared-memory staged per-graph kernel
+    (``drgnn_aggregate_tiled``) is used."""
     require_cuda(src, rowptr, col, out, ew, sscale, self_src, self_out, selfc_in, selfc_out, post_out, bias)
     _f32(src, 'src'), _f32(out, 'out'), _i32(rowptr, 'rowptr'), _i32(col, 'col')
     a = AggregateArgs()
@@ -260,8 +261,8 @@ def aggregate(src, rowptr, col, out, C_=None, ew=None, sscale=None, self_src=Non
     a.C = int(out.size(1) if C_ is None else C_)
     a.post_mode, a.self_mode, a.relu = int(post_mode), int(self_mode), 1 if relu else 0
     if tile_ptr is not None:
-        call('drgnn_aggregate_tiled', C.byref(a), ptr(_i32(tile_ptr, 'tile_ptr')), tile_ptr.numel() - 1,
-             int(max_tile_rows), stream_ptr())
+        call('drgnn_aggregate_tiled', C.byref(a), ptr(_i32(tile_ptr, 'tile_ptr')), ptr(_i32(tile_eptr, 'tile_eptr')),
+             tile_ptr.numel() - 1, int(max_tile_rows), int(max_tile_edges), stream_ptr())
     else:
         call('drgnn_aggregate', C.byref(a), stream_ptr())
     return out

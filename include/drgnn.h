@@ -174,12 +174,15 @@ typedef struct drgnn_aggregate_args {
 } drgnn_aggregate_args;
 int drgnn_aggregate(const drgnn_aggregate_args* a, void* stream);
 
-/* Same contract, per-graph tiles: the source rows of one graph (node_ptr[g]..node_ptr[g+1])
- * are staged in shared memory with bulk async copies (cp.async.bulk + mbarrier), so neighbour
- * re-reads never leave the SM and HBM traffic is compulsory-only.  Requires every col[p] of a
- * row of graph g to lie inside graph g and ld_src == C.  tile_ptr: [n_tiles+1]. */
-int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr, int32_t n_tiles,
-                          int32_t max_tile_rows, void* stream);
+/* Same contract, per-graph tiles: everything one graph (tile) needs - its source rows
+ * tile_ptr[t]..tile_ptr[t+1], its rowptr slice and its col / ew slices tile_eptr[t]..tile_eptr[t+1]
+ * (tile_eptr[t] == rowptr[tile_ptr[t]]) - is streamed into shared memory with bulk async copies
+ * (cp.async.bulk + mbarrier), double buffered by persistent CTAs, so neighbour gathers and
+ * index reads never leave the SM and HBM traffic is compulsory-only.
+ * Requires every col[p] of a tile to lie inside the tile, ld_src == C, and rowptr / col / ew to
+ * be 16-byte aligned and READABLE up to the next multiple of 4 elements past their end. */
+int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr, const int32_t* tile_eptr,
+                          int32_t n_tiles, int32_t max_tile_rows, int32_t max_tile_edges, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 3. Dense per-node transform (the nn.Linear / torch.mm of ginet.py:57-58,137-139,

@@ -233,7 +233,7 @@ def test_aggregate_tiled_equals_rows_kernel(lib, C):
     from deeprank_gnn_b200 import ops, synthetic
     from deeprank_gnn_b200.data import Batch
     dev = _dev()
-    graphs = synthetic.make_graphs(dict(nodes=(40, 400), edges_per_node=6, feat=C), count=37, seed=9)
+    graphs = synthetic.make_graphs(dict(nodes=(40, 300), edges_per_node=6, feat=C), count=37, seed=9)
     b = Batch.from_data_list(graphs)
     st = ops.structure_build(b._node_ptr.to(dev), b._edge_ptr.to(dev), b.edge_index.to(dev), b.cluster0.to(dev),
                              b._max_n, b._max_e, edge_attr=b.edge_attr.to(dev))
@@ -241,8 +241,13 @@ def test_aggregate_tiled_equals_rows_kernel(lib, C):
     o1, o2 = torch.empty_like(x), torch.empty_like(x)
     ops.aggregate(x, st.rowptr0, st.col0, o1, ew=st.w0csr, post_mode=1)
     ops.aggregate(x, st.rowptr0, st.col0, o2, ew=st.w0csr, post_mode=1, tile_ptr=b._node_ptr.to(dev),
-                  max_tile_rows=b._max_n)
+                  tile_eptr=b._edge_ptr.to(dev), max_tile_rows=b._max_n, max_tile_edges=b._max_e)
     assert torch.equal(o1, o2)
+    o3, o4 = torch.empty_like(x), torch.empty_like(x)
+    ops.aggregate(x, st.rowptr0, st.col0, o3)
+    ops.aggregate(x, st.rowptr0, st.col0, o4, tile_ptr=b._node_ptr.to(dev), tile_eptr=b._edge_ptr.to(dev),
+                  max_tile_rows=b._max_n, max_tile_edges=b._max_e)
+    assert torch.equal(o3, o4)
     row, col = b.edge_index
     deg = torch.bincount(row, minlength=x.size(0))
     ref = torch.zeros_like(b.x).index_add_(0, row, b.x[col] * b.edge_attr) / deg.clamp(min=1).view(-1, 1)

@@ -26,7 +26,9 @@ def build_stream(n_nodes, C, dev, seed=0):
     col = (st.col0[:e0].view(1, -1) + off_n).reshape(-1).contiguous()
     tile_ptr = torch.cat([(base._node_ptr[:-1].to(dev).view(1, -1) + off_n).reshape(-1),
                           torch.tensor([N], dtype=torch.int32, device=dev)])
-    return N, E, rowptr, col, tile_ptr, base._max_n
+    tile_eptr = torch.cat([(base._edge_ptr[:-1].to(dev).view(1, -1) + off_e).reshape(-1),
+                           torch.tensor([E], dtype=torch.int32, device=dev)])
+    return N, E, rowptr, col, (tile_ptr, tile_eptr, base._max_n, base._max_e)
 
 
 def main():
@@ -34,11 +36,12 @@ def main():
     C = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     launches = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     dev = torch.device('cuda:0')
-    N, E, rowptr, col, tile_ptr, max_n = build_stream(n_nodes, C, dev)
+    N, E, rowptr, col, tiles = build_stream(n_nodes, C, dev)
     x = torch.randn(N, C, device=dev)
     out = torch.empty(N, C, device=dev)
     alg = 8.0 * N * C + 4.0 * E + 4.0 * (N + 1)
-    for name, kw in (('rows', {}), ('tiled', dict(tile_ptr=tile_ptr, max_tile_rows=max_n))):
+    for name, kw in (('rows', {}), ('tiled', dict(tile_ptr=tiles[0], tile_eptr=tiles[1], max_tile_rows=tiles[2],
+                                                   max_tile_edges=tiles[3]))):
         ops.aggregate(x, rowptr, col, out, **kw)
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
