@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('DRGNN_NVCC_EXTRA', '').split() + ['-c', src, '-o', obj]
         if verbose:
             print(' '.join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

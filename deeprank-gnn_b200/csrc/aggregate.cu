@@ -313,9 +313,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   warps 1..kConsumers = consumers: wait on FULL, process their share of the tile's rows entirely
 //     out of shared memory (explicit ld.shared with 32-bit addresses), arrive on EMPTY.  No CTA-wide
 //     barrier in the loop; row groups are dealt to warps from a per-tile rotating offset.
-static constexpr int kConsumers = 16;
+#ifndef DRGNN_CONSUMERS
+#define DRGNN_CONSUMERS 31
+#endif
+#ifndef DRGNN_MAX_STAGES
+#define DRGNN_MAX_STAGES 8
+#endif
+static constexpr int kConsumers = DRGNN_CONSUMERS;
 static constexpr int kTiledThreads = 32 * (1 + kConsumers);
-static constexpr int kMaxStages = 8;
+static constexpr int kMaxStages = DRGNN_MAX_STAGES;
 
 template <int G, bool WEIGHTED, bool EPI>
 __global__ void __launch_bounds__(kTiledThreads, 1) aggregate_tiled_kernel(const AggParams P) {

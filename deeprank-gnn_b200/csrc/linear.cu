@@ -45,16 +45,18 @@ __device__ __forceinline__ float finish(const drgnn_linear_args& a, float v, int
   return v;
 }
 
-// blockDim.x = 16 * cgt (cgt = 4-column groups of the tile, <= 16); grid = (row tiles, groups * col tiles)
-__global__ void __launch_bounds__(256) linear_fma_kernel(const drgnn_linear_args a, int col_tiles) {
+// 16 * cgt compute threads (cgt = 4-column groups of the tile, <= 16); blockDim.x >= 16 * cgt, the
+// surplus threads only help staging the tiles (narrow outputs such as fc2 would otherwise stage a
+// 32 x 64 weight chunk with 16 threads); grid = (row tiles, groups * col tiles)
+__global__ void __launch_bounds__(256) linear_fma_kernel(const drgnn_linear_args a, int col_tiles, int cgt) {
   __shared__ float Xs[LT_R][LT_K + 1];
   __shared__ __align__(16) float Ws[LT_K][LT_C];
   const int rows = live_rows(a.rows, a.rows_dev);
   const int r0 = blockIdx.x * LT_R;
   if (r0 >= rows) return;
   const int g = blockIdx.y / col_tiles, o0 = (blockIdx.y % col_tiles) * LT_C;
-  const int cgt = blockDim.x >> 4;
-  const int rg = threadIdx.x / cgt, cg = threadIdx.x % cgt;
+  const bool worker = threadIdx.x < 16 * cgt;
+  const int rg = worker ? threadIdx.x / cgt : 0, cg = worker ? threadIdx.x % cgt : 0;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(256) linear_fma_kernel(const drgnn_linear_args
     }
     __syncthreads();
   }
+  if (!worker) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + rg * 4 + i;
@@ -309,7 +312,8 @@ extern "C" int drgnn_linear(const drgnn_linear_args* a, void* stream) {
   } else {
     const int tile_cols = a->Fout < LT_C ? a->Fout : LT_C;
     const int cgt = (tile_cols + 3) / 4;
-    linear_fma_kernel<<<grid, 16 * cgt, 0, st>>>(*a, col_tiles);
+    const int threads = 16 * cgt < 128 ? 128 : 16 * cgt;
+    linear_fma_kernel<<<grid, threads, 0, st>>>(*a, col_tiles, cgt);
     DRGNN_CHECK_LAUNCH("linear_fma_kernel");
   }
   return DRGNN_OK;

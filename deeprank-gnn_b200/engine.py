@@ -165,7 +165,7 @@ class Workspace(object):
 class DeviceBatch(object):
     """The tensors of one mini-batch the engine consumes, resident on the device."""
     __slots__ = ('x', 'edge_index', 'edge_attr', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr', 'y',
-                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'mol', 'key')
+                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'mol', 'key', 'sslot')
 
     @staticmethod
     def from_batch(batch, device, classes=None):
@@ -199,6 +199,7 @@ class DeviceBatch(object):
         d.max_n, d.max_e = int(batch._max_n), int(batch._max_e)
         d.mol = getattr(batch, 'mol', None)
         d.key = None
+        d.sslot = 0
         d.L1b = d.L1                     # upper bound of level-1 rows used for launch sizes
         return d
 
@@ -213,6 +214,7 @@ class DeviceBatch(object):
         d.B, d.N, d.E, d.L1, d.max_n, d.max_e = pb.B, pb.N, pb.E, pb.L1, pb.max_n, pb.max_e
         d.mol = pb.mol
         d.key = pb.layout_key()
+        d.sslot = 0
         d.L1b = pb.N                     # fixed bound: batches of one layout replay the same CUDA graph
         return d
 
@@ -220,7 +222,7 @@ class DeviceBatch(object):
 class Engine(object):
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=None, graph=False, tiled=False, process_group=None, seed=None):
+                 dropout=None, graph=False, tiled=True, process_group=None, seed=None):
         self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -234,7 +236,7 @@ class Engine(object):
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.training = True
         self.use_graph = bool(graph)
-        self.tiled = bool(tiled)
+        self.tiled = tiled             # True: per-graph TMA kernel for large batches; 'force': always; False: never
         self.pg = process_group
         dist = torch.distributed
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -244,10 +246,13 @@ class Engine(object):
         self.exp_avg_sq = torch.zeros_like(self.params.data)
         self.step_dev = torch.zeros(1, dtype=F32, device=self.device)
         self.ws = None
-        self.struct = None
+        self.structs = [None, None]      # two structure slots: the pass for batch i+1 overlaps step i
+        self._last_struct = None
         self._graphs = {}
         self._staging = {}
         self._copy_stream = None
+        from . import _lib
+        self._sms = int(_lib.load().drgnn_device_sms())
         self.launches_per_step = 0
         self.reset_parameters(seed)
 
@@ -332,21 +337,28 @@ class Engine(object):
             nn_ = max(N, ws.N if ws else 0)
             ne_ = max(E, ws.E if ws else 0)
             self.ws = Workspace(self.spec, nb, nn_, ne_, self.device)
-            self.struct = ops.Structure(nb, nn_, ne_, nn_, 1 if self.spec.kind == 'sgat' else 0, self.device)
+            ne_attr = 1 if self.spec.kind == 'sgat' else 0
+            self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(2)]
             self._graphs.clear()
         return self.ws
 
-    # ---------------------------------------------------------------- forward
-    def _structure(self, d):
+    # ---------------------------------------------------------------- structure pass
+    def prepare(self, d):
+        """Run the structure pass of batch ``d`` into structure slot ``d.sslot`` on the current
+        stream.  It depends on the batch only (not on the weights), so callers may run it on a
+        side stream while the previous step computes (``train_batches`` / ``train_resident`` do)."""
+        self._ensure(d.B, d.N, d.E)
         need_w = self.spec.kind == 'sgat'
         if need_w and d.edge_attr is None:
             raise DrgnnError('sGAT needs edge_attr')
         if need_w and d.edge_attr.size(1) != 1:
             raise DrgnnError('sGAT supports one edge feature (the reference broadcast needs ne in {1, Fout})')
+        slot = self.structs[d.sslot]
         st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
                                  c1_ptr=d.c1_ptr, cluster1=d.cluster1, edge_attr=d.edge_attr if need_w else None,
-                                 clusters_are_local=True, mirrors=False, out=self.struct)
-        assert st is self.struct
+                                 clusters_are_local=True, mirrors=False, out=slot)
+        assert st is slot
+        self._last_struct = st
         return st
 
     def _conv_aggregate(self, level, src, rowptr, col, Zin, n_rows, n_rows_dev, ew, s_out, post_out, tiles):
@@ -366,12 +378,14 @@ class Engine(object):
                           post_out=post_out, n_rows=n_rows, n_rows_dev=n_rows_dev, post_mode=2, self_mode=1, **tile)
 
     def _forward(self, d, keep_mask=None):
-        s, ws, st, P = self.spec, self._ensure(d.B, d.N, d.E), self._structure(d), self.params
+        s, ws, st, P = self.spec, self._ensure(d.B, d.N, d.E), self.structs[d.sslot], self.params
         N, B = d.N, d.B
         K0d, K1d = st.K0_dev, st.K1_dev
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
-        tiled = self.tiled and 8 * (d.max_n * s.F + d.max_n + 2 * d.max_e + 32) <= 200 * 1024
+        # per-graph TMA pipeline for batches that fill the machine (>= 2 graphs per SM); small batches use
+        # the L1-resident row kernel, whose launch latency is lower (3.0 us vs 4.1 us at B = 64)
+        tiled = self.tiled and (d.B >= 2 * self._sms or self.tiled == 'force') and 8 * (d.max_n * s.F + d.max_n + 2 * d.max_e + 32) <= 200 * 1024
         # conv1: aggregate on the level-0 graph, then transform (+bias, ReLU)
         self._conv_aggregate(0, d.x, st.rowptr0, st.col0, ws.Zin1[:N], N, None, st.w0csr, ws.s0, ws.post0,
                              (d.node_ptr, d.edge_ptr, d.max_n, d.max_e) if tiled else None)
@@ -412,7 +426,7 @@ class Engine(object):
 
     # ---------------------------------------------------------------- backward
     def _backward(self, d):
-        s, ws, st, P = self.spec, self.ws, self.struct, self.params
+        s, ws, st, P = self.spec, self.ws, self.structs[d.sslot], self.params
         N, B, L1 = d.N, d.B, d.L1b
         K0d = st.K0_dev
         pv = lambda name: P.view(P.data, name)
@@ -489,28 +503,36 @@ class Engine(object):
             torch.distributed.all_reduce(self.grads, group=self.pg)
             torch.distributed.all_reduce(self.ws.loss, group=self.pg)
 
-    def forward(self, d, keep_mask=None):
+    def forward(self, d, keep_mask=None, prepared=False):
         """Forward only (``model(batch)``): returns the ``[B, out]`` prediction (a view of an
         engine buffer, overwritten by the next call)."""
+        if not prepared:
+            self.prepare(d)
         return self._forward(d, keep_mask)
 
     def loss_and_grads(self, d, B_global=None, inv_norm=None, keep_mask=None):
         """Forward + loss + backward, no optimiser (parity tests).  Gradients in ``named_grads()``."""
         inv = self._inv_norm(d, B_global, inv_norm)
+        self.prepare(d)
         self._forward(d, keep_mask)
         self._loss(d, inv)
         self._backward(d)
         return self.ws.loss, self.ws.pred[:d.B]
 
-    def step(self, d, B_global=None, inv_norm=None, keep_mask=None):
-        """One training step on a ``DeviceBatch``: forward, loss, backward, [all-reduce], Adam
-        (the body of ``NeuralNet._epoch``'s loop, NeuralNet.py:490-503).  Returns (loss, pred)
-        device tensors that the next step overwrites.  ``B_global`` = graphs in the global
-        batch when it is sharded over ranks: the local loss is sum/B_global so the all-reduced
-        (summed) gradient is the gradient of the global mean."""
+    def step(self, d, B_global=None, inv_norm=None, keep_mask=None, prepared=False):
+        """One training step on a ``DeviceBatch``: structure pass (unless ``prepared``), forward,
+        loss, backward, [all-reduce], Adam (the body of ``NeuralNet._epoch``'s loop,
+        NeuralNet.py:490-503).  Returns (loss, pred) device tensors that the next step overwrites.
+        ``B_global`` = graphs in the global batch when it is sharded over ranks: the local loss
+        is sum/B_global so the all-reduced (summed) gradient is the gradient of the global mean
+        (SURVEY 8e)."""
         inv = self._inv_norm(d, B_global, inv_norm)
         if self.use_graph and d.key is not None and keep_mask is None:
+            if not prepared:
+                self.prepare_graph(d)
             return self._step_graph(d, inv)
+        if not prepared:
+            self.prepare(d)
         self._forward(d, keep_mask)
         self._loss(d, inv)
         self._backward(d)
@@ -522,7 +544,7 @@ class Engine(object):
     def upload(self, pb, slot=0):
         """ONE host->device copy of a ``PackedBatch`` into a persistent device staging buffer
         (one per layout and slot, so CUDA-graph replays see fixed addresses).  Returns a
-        DeviceBatch of views into it."""
+        DeviceBatch of views into it; its structure slot is ``slot & 1``."""
         key = (pb.layout_key(), slot)
         dev = self._staging.get(key)
         if dev is None:
@@ -531,17 +553,37 @@ class Engine(object):
         dev[:pb.numel].copy_(pb.buf, non_blocking=True)
         d = DeviceBatch.from_packed(pb, dev)
         d.key = key
+        d.sslot = slot & 1
         return d
 
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def prepare_graph(self, d):
+        """``prepare`` replayed from a CUDA graph (captured on first use for the batch's layout)."""
+        key = ('prep', d.key)
+        g = self._graphs.get(key)
+        if g is None:
+            self.prepare(d)                     # eager warm-up (first-use attribute setup, buffer growth)
+            if self._graphs.get(key) is None:   # growth clears the cache; the warm-up result stays valid
+                cur = torch.cuda.current_stream(self.device)
+                g = self._capture(lambda: self.prepare(d))
+                cur.synchronize()
+                self._graphs[key] = g
+            return
+        g.replay()
+
     def _step_graph(self, d, inv):
-        """Replay (capture on first use) the whole step as one CUDA graph.  The graph is tied to
-        the staging buffer of the batch's shape; with several ranks the gradient all-reduce sits
-        between the two captured halves."""
-        key = (d.key, round(inv, 12), self.training)
+        """Replay (capture on first use) everything after the structure pass as one CUDA graph.
+        The graph is tied to the staging buffer / structure slot of the batch; with several ranks
+        the gradient all-reduce sits between the two captured halves."""
+        key = ('step', d.key, round(inv, 12), self.training)
         ent = self._graphs.get(key)
         if ent is None:
-            # warm up un-captured (first-use attribute setup, workspace growth), then capture
-            self._ensure(d.B, d.N, d.E)
+            # warm up un-captured (first-use attribute setup), then capture
             snap = [t.clone() for t in (self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev)]
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -553,17 +595,15 @@ class Engine(object):
             torch.cuda.current_stream(self.device).wait_stream(side)
             for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
                 t.copy_(c)
-            g1, g2 = torch.cuda.CUDAGraph(), None
-            with torch.cuda.graph(g1):
+
+            def body():
                 self._forward(d)
                 self._loss(d, inv)
                 self._backward(d)
                 if self.world == 1:
                     self._adam()
-            if self.world > 1:
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
-                    self._adam()
+            g1 = self._capture(body)
+            g2 = self._capture(self._adam) if self.world > 1 else None
             ent = (g1, g2)
             self._graphs[key] = ent
         g1, g2 = ent
@@ -573,20 +613,30 @@ class Engine(object):
             g2.replay()
         return self.ws.loss, self.ws.pred[:d.B]
 
-    def train_batches(self, packed_batches, B_global=None, inv_norms=None, train=True):
-        """Pipelined pass over ``PackedBatch`` objects held in (pinned) host memory - the inner
-        loop of ``NeuralNet._epoch`` / ``eval`` (NeuralNet.py:490-523, 432-460).  Per batch:
-        ONE host->device copy on a copy stream (two staging slots, so the copy of batch i+1
-        overlaps the compute of batch i), the fused step (or forward + loss when
-        ``train=False``), and an asynchronous device->host read of ``[loss, pred...]`` into
-        pinned memory.  One host synchronisation at the end.  Returns (losses [n], preds list)."""
-        dev = self.device
-        main = torch.cuda.current_stream(dev)
+    def _pipeline_state(self):
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream = torch.cuda.Stream(self.device)
             self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
-        cs = self._copy_stream
+        return self._copy_stream
+
+    def _prepare_any(self, d):
+        if self.use_graph and d.key is not None:
+            self.prepare_graph(d)
+        else:
+            self.prepare(d)
+
+    def train_batches(self, packed_batches, B_global=None, inv_norms=None, train=True):
+        """Pipelined pass over ``PackedBatch`` objects held in (pinned) host memory - the inner
+        loop of ``NeuralNet._epoch`` / ``eval`` (NeuralNet.py:490-523, 432-460).  Per batch, on a
+        side stream: ONE host->device copy and the structure pass (two staging / structure slots,
+        so both overlap the compute of the previous batch); on the main stream: the fused step
+        (or forward + loss when ``train=False``) and an asynchronous device->host read of
+        ``[loss, pred...]`` into pinned memory.  One host synchronisation at the end.
+        Returns (losses [n], preds list)."""
+        main = torch.cuda.current_stream(self.device)
+        cs = self._pipeline_state()
+        cs.wait_stream(main)
         outs = []
         was_training = self.training
         self.train(train)
@@ -596,11 +646,12 @@ class Engine(object):
                 if i >= 2:
                     cs.wait_event(self._slot_free[slot])
                 d = self.upload(pb, slot)
+                self._prepare_any(d)
                 self._slot_ready[slot].record(cs)
             main.wait_event(self._slot_ready[slot])
             inv = None if inv_norms is None else inv_norms[i]
             if train:
-                loss, pred = self.step(d, B_global=B_global, inv_norm=inv)
+                loss, pred = self.step(d, B_global=B_global, inv_norm=inv, prepared=True)
             else:
                 pred = self._forward(d)
                 loss = self._loss(d, self._inv_norm(d, B_global, inv), with_grad=False) \
@@ -616,8 +667,34 @@ class Engine(object):
         preds = [h[1:].view(shape) for h, shape in outs]
         return losses, preds
 
+    def train_resident(self, dbatches, steps=None, B_global=None):
+        """Training steps over batches already resident in HBM (``upload``-ed DeviceBatches, e.g. a
+        data set cached on the device across epochs), cycling through ``dbatches`` for ``steps``
+        steps.  The structure pass of step i+1 runs on a side stream while step i computes;
+        consecutive batches must sit in different structure slots (``upload(pb, slot)`` with
+        alternating slot parity).  No host synchronisation.  Returns (loss, pred) of the last step."""
+        n = len(dbatches) if steps is None else steps
+        main = torch.cuda.current_stream(self.device)
+        cs = self._pipeline_state()
+        cs.wait_stream(main)
+        out = None
+        for i in range(n):
+            d = dbatches[i % len(dbatches)]
+            slot = d.sslot
+            if i > 0 and dbatches[(i - 1) % len(dbatches)].sslot == slot:
+                raise DrgnnError('train_resident: consecutive batches share a structure slot')
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self._slot_free[slot])
+                self._prepare_any(d)
+                self._slot_ready[slot].record(cs)
+            main.wait_event(self._slot_ready[slot])
+            out = self.step(d, B_global=B_global, prepared=True)
+            self._slot_free[slot].record(main)
+        return out
+
     def validate(self):
         """Raise if the last structure pass flagged invalid input (ONE host sync)."""
-        if self.struct is not None:
-            self.struct._counts_host = None
-            self.struct.sync_counts()
+        if self._last_struct is not None:
+            self._last_struct._counts_host = None
+            self._last_struct.sync_counts()

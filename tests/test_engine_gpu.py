@@ -183,7 +183,7 @@ def test_packed_graph_replay_equals_eager(lib, net):
     batches = [synthetic.make_graphs('cfg2', count=8, seed=s) for s in (1, 2, 3)]
     e1 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0)
     e2 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0, graph=True)
-    e3 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0, tiled=True)
+    e3 = Engine(net, 32, 1, 1, device='cuda:0', seed=3, dropout=0.0, tiled='force')
     for rep in range(2):
         for graphs in batches:
             l1, p1 = e1.step(_device_batch(graphs))
