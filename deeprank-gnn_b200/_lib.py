@@ -89,6 +89,21 @@ class LinearWgradArgs(C.Structure):
     ]
 
 
+class HeadArgs(C.Structure):
+    _fields_ = [
+        ('R', VP), ('ldr', C.c_int32),
+        ('W1', VP), ('b1', VP),
+        ('W2', VP), ('b2', VP),
+        ('keep', VP), ('keep_scale', C.c_float),
+        ('y', VP), ('y_class', VP), ('class_w', VP),
+        ('B', C.c_int32), ('C', C.c_int32), ('Hd', C.c_int32), ('out', C.c_int32),
+        ('task', C.c_int32), ('inv_norm', C.c_float),
+        ('pred', VP), ('loss', VP), ('H', VP),
+        ('dW1', VP), ('db1', VP), ('dW2', VP), ('db2', VP),
+        ('dR', VP), ('lddr', C.c_int32),
+    ]
+
+
 _i32, _i64, _f32 = C.c_int32, C.c_int64, C.c_float
 _SIGNATURES = {
     'drgnn_last_error': (C.c_char_p, []),
@@ -111,6 +126,8 @@ _SIGNATURES = {
     'drgnn_mse_loss': (C.c_int, [VP, VP, _i32, _f32, _i32, VP, VP, VP]),
     'drgnn_ce_loss': (C.c_int, [VP, _i32, VP, VP, _i32, _i32, _f32, VP, VP, VP]),
     'drgnn_adam_flat': (C.c_int, [VP, VP, VP, VP, VP, _i64, _f32, _f32, _f32, _f32, _f32, VP]),
+    'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
+    'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
     'drgnn_fill_f32': (C.c_int, [VP, _f32, _i64, VP]),
     'drgnn_fill_i32': (C.c_int, [VP, _i32, _i64, VP]),

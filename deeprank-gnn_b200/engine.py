@@ -222,7 +222,7 @@ class DeviceBatch(object):
 class Engine(object):
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=None, graph=False, tiled=True, process_group=None, seed=None):
+                 dropout=None, graph=False, tiled=True, fused_head=True, process_group=None, seed=None):
         self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -253,6 +253,9 @@ class Engine(object):
         self._copy_stream = None
         from . import _lib
         self._sms = int(_lib.load().drgnn_device_sms())
+        self.fused_head = bool(fused_head)
+        self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
+        self._head_done = False
         self.launches_per_step = 0
         self.reset_parameters(seed)
 
@@ -377,7 +380,9 @@ class Engine(object):
             ops.aggregate(src, rowptr, col, Zin[:, cin:], C_=cin, self_src=src, self_out=Zin[:, :cin],
                           post_out=post_out, n_rows=n_rows, n_rows_dev=n_rows_dev, post_mode=2, self_mode=1, **tile)
 
-    def _forward(self, d, keep_mask=None):
+    def _forward(self, d, keep_mask=None, loss_inv=None):
+        """``loss_inv``: when given (training step) the fused head also computes the loss and the
+        gradients of fc1 / fc2 / the read-out (``_head_done``)."""
         s, ws, st, P = self.spec, self._ensure(d.B, d.N, d.E), self.structs[d.sslot], self.params
         N, B = d.N, d.B
         K0d, K1d = st.K0_dev, st.K1_dev
@@ -414,13 +419,35 @@ class Engine(object):
         ops.segment_mean_fwd(ws.P2[:L1], st.kptr1[:B + 1], ws.R[:B])
         # heads
         drop = self.training and s.dropout > 0
+        scale = 1.0 / (1.0 - s.dropout) if drop else 1.0
         if drop:
             if keep_mask is not None:
                 ws.keep[:B].copy_(keep_mask.to(self.device, F32))
             else:
                 ws.keep[:B].bernoulli_(1.0 - s.dropout)
+        self._head_done = False
+        if self.fused_head and B <= 256 and self._head_fits:
+            # ONE launch: fc1 -> fc2 -> loss -> backward of both (csrc/head.cu)
+            task, grads = ops.TASK_NONE, {}
+            if loss_inv is not None:
+                task = ops.TASK_CE if self.task == 'class' else \
+                    (ops.TASK_MSE_SIGMOID if self.transform_sigmoid else ops.TASK_MSE)
+                if self.task == 'class' and d.y_class is None:
+                    raise DrgnnError('classification needs class-index targets (pass `classes` when building the batch)')
+                if self.task == 'reg' and d.y is None:
+                    raise DrgnnError('the batch has no target')
+                gv = lambda name: P.view(self.grads, name)
+                grads = dict(dW1=gv('fc1.weight'), db1=gv('fc1.bias'), dW2=gv('fc2.weight'), db2=gv('fc2.bias'),
+                             dR=ws.dR[:B])
+            ops.head(ws.R[:B], pv('fc1.weight'), pv('fc1.bias'), pv('fc2.weight'), pv('fc2.bias'), ws.pred[:B],
+                     task=task, inv_norm=loss_inv if loss_inv is not None else 1.0,
+                     y=d.y if self.task == 'reg' else None, y_class=d.y_class if self.task == 'class' else None,
+                     class_w=self.class_weights, keep=ws.keep[:B] if drop else None, keep_scale=scale,
+                     loss=ws.loss if loss_inv is not None else None, **grads)
+            self._head_done = loss_inv is not None
+            return ws.pred[:B]
         ops.linear(ws.R[:B], pv('fc1.weight'), s.C2, s.Hd, ws.H[:B], bias=pv('fc1.bias'), relu=True,
-                   out_mask=ws.keep[:B] if drop else None, mask_scale=1.0 / (1.0 - s.dropout) if drop else 1.0)
+                   out_mask=ws.keep[:B] if drop else None, mask_scale=scale)
         ops.linear(ws.H[:B], pv('fc2.weight'), s.Hd, s.out, ws.pred[:B], bias=pv('fc2.bias'))
         return ws.pred[:B]
 
@@ -434,12 +461,13 @@ class Engine(object):
         gflat = lambda name, n: self.grads[P.offset(name):P.offset(name) + n]
         drop = self.training and s.dropout > 0
         scale = 1.0 / (1.0 - s.dropout) if drop else 1.0
-        # heads
-        ops.linear_wgrad(ws.H[:B], ws.dpred[:B], s.Hd, s.out, gv('fc2.weight'), gv('fc2.bias'), work=ws.wwork)
-        ops.linear(ws.dpred[:B], pv('fc2.weight'), s.out, s.Hd, ws.dH[:B], w_layout=1, out_mask=ws.H[:B],
-                   mask_scale=scale)
-        ops.linear_wgrad(ws.R[:B], ws.dH[:B], s.C2, s.Hd, gv('fc1.weight'), gv('fc1.bias'), work=ws.wwork)
-        ops.linear(ws.dH[:B], pv('fc1.weight'), s.Hd, s.C2, ws.dR[:B], w_layout=1)
+        # heads (already done by the fused head kernel in the forward when it applies)
+        if not self._head_done:
+            ops.linear_wgrad(ws.H[:B], ws.dpred[:B], s.Hd, s.out, gv('fc2.weight'), gv('fc2.bias'), work=ws.wwork)
+            ops.linear(ws.dpred[:B], pv('fc2.weight'), s.out, s.Hd, ws.dH[:B], w_layout=1, out_mask=ws.H[:B],
+                       mask_scale=scale)
+            ops.linear_wgrad(ws.R[:B], ws.dH[:B], s.C2, s.Hd, gv('fc1.weight'), gv('fc1.bias'), work=ws.wwork)
+            ops.linear(ws.dH[:B], pv('fc1.weight'), s.Hd, s.C2, ws.dR[:B], w_layout=1)
         # read-out and level-1 pool
         ops.segment_mean_bwd(ws.dR[:B], st.kptr1[:B + 1], ws.dP2[:L1])
         ops.maxpool_bwd(ws.dP2[:L1], ws.arg1[:L1], st.cl1, ws.dZ2[:L1], relu_out=ws.Z2[:L1], n_nodes_dev=K0d)
@@ -514,8 +542,9 @@ class Engine(object):
         """Forward + loss + backward, no optimiser (parity tests).  Gradients in ``named_grads()``."""
         inv = self._inv_norm(d, B_global, inv_norm)
         self.prepare(d)
-        self._forward(d, keep_mask)
-        self._loss(d, inv)
+        self._forward(d, keep_mask, loss_inv=inv)
+        if not self._head_done:
+            self._loss(d, inv)
         self._backward(d)
         return self.ws.loss, self.ws.pred[:d.B]
 
@@ -533,8 +562,9 @@ class Engine(object):
             return self._step_graph(d, inv)
         if not prepared:
             self.prepare(d)
-        self._forward(d, keep_mask)
-        self._loss(d, inv)
+        self._forward(d, keep_mask, loss_inv=inv)
+        if not self._head_done:
+            self._loss(d, inv)
         self._backward(d)
         self._all_reduce()
         self._adam()
@@ -588,8 +618,9 @@ class Engine(object):
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                self._forward(d)
-                self._loss(d, inv)
+                self._forward(d, loss_inv=inv)
+                if not self._head_done:
+                    self._loss(d, inv)
                 self._backward(d)
                 self._adam()
             torch.cuda.current_stream(self.device).wait_stream(side)
@@ -597,8 +628,9 @@ class Engine(object):
                 t.copy_(c)
 
             def body():
-                self._forward(d)
-                self._loss(d, inv)
+                self._forward(d, loss_inv=inv)
+                if not self._head_done:
+                    self._loss(d, inv)
                 self._backward(d)
                 if self.world == 1:
                     self._adam()

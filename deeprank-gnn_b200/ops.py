@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AggregateArgs, DrgnnError, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
+from ._lib import (AggregateArgs, DrgnnError, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
                    require_cuda, stream_ptr)
 
 I32, I64, F32 = torch.int32, torch.int64, torch.float32
@@ -390,6 +390,33 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0
             raise DrgnnError('adam_flat works on contiguous float32 buffers')
     call('drgnn_adam_flat', ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_dev), param.numel(),
          float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), stream_ptr())
+
+
+TASK_NONE, TASK_MSE, TASK_MSE_SIGMOID, TASK_CE = 0, 1, 2, 3
+
+
+def head_fits(C_, Hd, out):
+    return int(_lib.load().drgnn_head_smem_bytes(int(C_), int(Hd), int(out))) >= 0
+
+
+def head(R, W1, b1, W2, b2, pred, task=TASK_NONE, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
+         keep_scale=1.0, loss=None, dW1=None, db1=None, dW2=None, db2=None, dR=None, H=None):
+    """Fused fc1 -> fc2 -> loss -> backward of both on the B read-out rows (``drgnn_head``)."""
+    require_cuda(R, W1, b1, W2, b2, pred, y, y_class, class_w, keep, loss, dW1, db1, dW2, db2, dR, H)
+    for t_, n_ in ((R, 'R'), (W1, 'W1'), (b1, 'b1'), (W2, 'W2'), (b2, 'b2'), (pred, 'pred'), (y, 'y'), (keep, 'keep')):
+        _f32(t_, n_)
+    a = HeadArgs()
+    a.R, a.ldr = ptr(R), _ld(R)
+    a.W1, a.b1, a.W2, a.b2 = ptr(W1), ptr(b1), ptr(W2), ptr(b2)
+    a.keep, a.keep_scale = ptr(keep), float(keep_scale) if keep is not None else 1.0
+    a.y, a.y_class, a.class_w = ptr(y), ptr(y_class), ptr(class_w)
+    a.B, a.C, a.Hd, a.out = R.size(0), W1.size(1), W1.size(0), W2.size(0)
+    a.task, a.inv_norm = int(task), float(inv_norm)
+    a.pred, a.loss, a.H = ptr(pred), ptr(loss), ptr(H)
+    a.dW1, a.db1, a.dW2, a.db2 = ptr(dW1), ptr(db1), ptr(dW2), ptr(db2)
+    a.dR, a.lddr = ptr(dR), (_ld(dR) if dR is not None else 0)
+    call('drgnn_head', C.byref(a), stream_ptr())
+    return pred
 
 
 def relu_mask(g, out, gz, rows=None, rows_dev=None):

@@ -265,6 +265,31 @@ int drgnn_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_
                     float* step_dev, int64_t n, float lr, float beta1, float beta2, float eps,
                     float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * 7. Fused network head (ginet.py:136-139, sGAT.py:134-135, foutnet.py:121-122 + the loss of
+ *    NeuralNet.py:500 + the backward of both): ONE launch for
+ *      H = relu(R W1^T + b1) [* keep * keep_scale],  pred = H W2^T + b2,
+ *      loss / dLoss/dpred (task 1: MSE, 2: MSE of sigmoid(pred), 3: class-weighted cross entropy,
+ *      0: forward only), dW2, db2, dW1, db1 (overwritten), dR = dLoss/dR.
+ *    W1 [Hd, C] and W2 [out, Hd] are nn.Linear weights.  keep: [B, Hd] 0/1 floats or NULL (then
+ *    keep_scale must be 1).  Gradient pointers may all be NULL (no backward).  H (optional):
+ *    [B, Hd] copy of the hidden activation.  Meant for B up to a few hundred rows (one CTA).
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_head_args {
+  const float* R; int32_t ldr;
+  const float* W1; const float* b1;
+  const float* W2; const float* b2;
+  const float* keep; float keep_scale;
+  const float* y; const int64_t* y_class; const float* class_w;
+  int32_t B; int32_t C; int32_t Hd; int32_t out;
+  int32_t task; float inv_norm;
+  float* pred; float* loss; float* H;
+  float* dW1; float* db1; float* dW2; float* db2;
+  float* dR; int32_t lddr;
+} drgnn_head_args;
+int64_t drgnn_head_smem_bytes(int32_t C, int32_t Hd, int32_t out);   /* <0: does not fit one CTA */
+int drgnn_head(const drgnn_head_args* a, void* stream);
+
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,
                     const int32_t* rows_dev, int32_t C, float* gz, int32_t ldgz, void* stream);

@@ -431,3 +431,55 @@ def test_adam_flat_matches_torch_adam(lib):
         ops.adam_flat(p, grad.to(dev), m, v, step, 0.01)
     torch.testing.assert_close(p.cpu(), ref_p.detach(), rtol=1e-5, atol=1e-6)
     assert float(step.item()) == 5.0
+
+
+@pytest.mark.parametrize('task', ['mse', 'mse_sigmoid', 'ce', 'none'])
+@pytest.mark.parametrize('B,C,Hd,out', [(64, 64, 128, 1), (77, 32, 64, 1), (5, 128, 256, 1), (40, 64, 128, 3)])
+def test_fused_head_matches_torch(lib, task, B, C, Hd, out):
+    from deeprank_gnn_b200 import ops
+    if task == 'ce' and out == 1:
+        pytest.skip('cross entropy needs several classes')
+    if task in ('mse', 'mse_sigmoid') and out != 1:
+        pytest.skip('regression head has one output')
+    dev = _dev()
+    g = torch.Generator().manual_seed(B + C)
+    R = torch.randn(B, C, generator=g, requires_grad=True)
+    fc1, fc2 = torch.nn.Linear(C, Hd), torch.nn.Linear(Hd, out)
+    keep = (torch.rand(B, Hd, generator=g) > 0.4).float()
+    H = torch.relu(fc1(R)) * keep / 0.6
+    pred = fc2(H)
+    if task == 'ce':
+        tgt = torch.randint(0, out, (B,), generator=g)
+        w = torch.rand(out, generator=g) + 0.5
+        loss = torch.nn.CrossEntropyLoss(weight=w, reduction='mean')(pred, tgt)
+        inv = 1.0 / float(w[tgt].sum())
+    elif task == 'none':
+        loss = None
+    else:
+        y = torch.rand(B, generator=g)
+        p = torch.sigmoid(pred.reshape(-1)) if task == 'mse_sigmoid' else pred.reshape(-1)
+        loss = torch.nn.MSELoss()(p, y)
+        inv = 1.0 / B
+    if loss is not None:
+        loss.backward()
+    d = lambda t_: t_.detach().to(dev).contiguous()
+    o_pred = torch.empty(B, out, device=dev)
+    if task == 'none':
+        ops.head(d(R), d(fc1.weight), d(fc1.bias), d(fc2.weight), d(fc2.bias), o_pred, keep=d(keep), keep_scale=1 / 0.6)
+        torch.testing.assert_close(o_pred.cpu(), pred.detach(), rtol=1e-4, atol=1e-5)
+        return
+    o_loss = torch.empty(1, device=dev)
+    dW1, db1 = torch.empty(Hd, C, device=dev), torch.empty(Hd, device=dev)
+    dW2, db2 = torch.empty(out, Hd, device=dev), torch.empty(out, device=dev)
+    dR = torch.empty(B, C, device=dev)
+    kw = dict(y_class=tgt.to(dev), class_w=w.to(dev)) if task == 'ce' else dict(y=y.to(dev))
+    ops.head(d(R), d(fc1.weight), d(fc1.bias), d(fc2.weight), d(fc2.bias), o_pred,
+             task={'mse': ops.TASK_MSE, 'mse_sigmoid': ops.TASK_MSE_SIGMOID, 'ce': ops.TASK_CE}[task], inv_norm=inv,
+             keep=d(keep), keep_scale=1 / 0.6, loss=o_loss, dW1=dW1, db1=db1, dW2=dW2, db2=db2, dR=dR, **kw)
+    torch.testing.assert_close(o_pred.cpu(), pred.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(o_loss.cpu()[0], loss.detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dW2.cpu(), fc2.weight.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(db2.cpu(), fc2.bias.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dW1.cpu(), fc1.weight.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(db1.cpu(), fc1.bias.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dR.cpu(), R.grad, rtol=1e-4, atol=1e-6)

@@ -1,0 +1,57 @@
+"""Where does a training step go?  Times (CUDA events, graph replay) on one GPU:
+  prep only   - structure pass of one batch, repeated
+  step only   - everything after the structure pass, repeated on one prepared batch
+  pipelined   - Engine.train_resident (prep of i+1 on a side stream while step i computes)
+  serial      - prep + step on one stream
+Usage: python tools/step_breakdown.py [cfg2] [steps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from deeprank_gnn_b200.data import PackedBatch  # noqa: E402
+from deeprank_gnn_b200.engine import Engine  # noqa: E402
+
+
+def timed(fn, n):
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(n):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return 1e3 * s.elapsed_time(e) / n
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+    cfg = bench.workload_config(name, None)
+    _graphs, batches = bench.make_pool(cfg, 8, seed=0)
+    packed = [PackedBatch.from_batch(b) for b in batches]
+    for graph in (True, False):
+        eng = Engine(cfg['net'], cfg['feat'], 1, 1, hidden=cfg['hidden'], device='cuda:0', lr=1e-3, graph=graph, seed=0)
+        ds = [eng.upload(pb, slot=i) for i, pb in enumerate(packed)]
+        for d in ds:
+            eng.step(d)
+        eng.train_resident(ds, steps=16)
+        t_prep = timed(lambda i: eng._prepare_any(ds[i % 8]), n)
+        eng._prepare_any(ds[0])
+        t_step = timed(lambda i: eng.step(ds[0], prepared=True), n)
+        t_serial = timed(lambda i: eng.step(ds[i % 8]), n)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        eng.train_resident(ds, steps=n)
+        e.record()
+        torch.cuda.synchronize()
+        t_pipe = 1e3 * s.elapsed_time(e) / n
+        print('%s graph=%s: prep %.1f us | step (after prep) %.1f us | serial %.1f us | pipelined %.1f us'
+              % (name, graph, t_prep, t_step, t_serial, t_pipe))
+
+
+if __name__ == '__main__':
+    main()
