@@ -18,102 +18,134 @@
 
 namespace drgnn {
 
-static constexpr int HD_ROWS = 32;    // rows per chunk
 static constexpr int HD_THREADS = 512;
 
+// shared-memory plan (float offsets).  Operands are kept in the layout each product wants:
+//   C[m][n] = sum_k At[k][m] * Bm[k][n]   with an 8 (m) x 4 (n) register tile per thread, so every
+// k step is two 16-byte loads of At (broadcast inside a warp), one of Bm and 32 FMAs.
 struct HeadSmem {
-  int w1, w2, r, h, dh, dp, total;  // float offsets
-  int ldw1, ldr, ldh;
+  int w1, w1t, w2, r, rt, h, dh, dht, dp, total;
+  int RB;  // rows per chunk (64, or 32 when shared memory is short)
 };
 
-__host__ __device__ inline HeadSmem head_plan(int C, int Hd, int out) {
+__host__ __device__ inline HeadSmem head_plan(int C, int Hd, int out, int RB) {
   HeadSmem p;
-  p.ldw1 = C + 1;   // W1s[h][k], stride C+1: conflict-free for thread-varying h and for thread-varying k
-  p.ldr = C + 4;    // Rs[r][k]  (16-byte aligned rows)
-  p.ldh = Hd + 4;   // Hs / dHs[r][h]
+  p.RB = RB;
   int o = 0;
-  p.w1 = o; o += Hd * p.ldw1;
-  p.w2 = o; o += out * Hd;
-  o = (o + 3) & ~3;
-  p.r = o;  o += HD_ROWS * p.ldr;
-  p.h = o;  o += HD_ROWS * p.ldh;
-  p.dh = o; o += HD_ROWS * p.ldh;
-  p.dp = o; o += HD_ROWS * (out + 1) * 2;   // pred and dpred of the chunk
+  p.w1 = o;  o += Hd * C;        // W1 [Hd][C]    (Bm of dR = dH W1)
+  p.w1t = o; o += C * (Hd + 4);  // W1^T [C][Hd+4] (Bm of H = R W1^T; +4: transposing stores spread over banks)
+  p.w2 = o;  o += ((out * Hd + 3) & ~3);
+  p.r = o;   o += RB * C;        // R [r][c]      (Bm of dW1 = dH^T R)
+  p.rt = o;  o += C * (RB + 4);  // R^T [c][RB+4] (At of H)
+  p.h = o;   o += RB * Hd;       // H [r][h]      (ReLU / dropout mask, fc2, dW2)
+  p.dh = o;  o += RB * Hd;       // dH [r][h]     (At of dW1)
+  p.dht = o; o += Hd * (RB + 4); // dH^T [h][RB+4] (At of dR)
+  p.dp = o;  o += 2 * RB * (out + 1);
   p.total = o;
   return p;
 }
 
-// acc[i] = sum_k A(m0+i, k) * Bv(k, n) for i < 8; one (8-row group, column) item per thread visit
-template <typename FA, typename FB, typename FO>
-__device__ __forceinline__ void mini_gemm(int M, int N, int K, FA a, FB b, FO out) {
-  const int mgroups = (M + 7) >> 3;
-  for (int item = threadIdx.x; item < mgroups * N; item += blockDim.x) {
-    const int mg = item / N, n = item % N;
-    float acc[8];
+template <typename FO>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb,
+                                          int M, int N, int K, FO out) {
+  const int mt = M >> 3, nt = N >> 2;  // M % 8 == 0, N % 4 == 0 (checked on the host)
+  for (int item = threadIdx.x; item < mt * nt; item += blockDim.x) {
+    const int mg = item / nt, ng = item - mg * nt;
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* ap = At + mg * 8;
+    const float* bp = Bm + ng * 4;
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float bv = b(k, n);
+      const float4 a0 = *reinterpret_cast<const float4*>(ap + k * lda);
+      const float4 a1 = *reinterpret_cast<const float4*>(ap + k * lda + 4);
+      const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a(mg * 8 + i, k), bv, acc[i]);
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (mg * 8 + i < M) out(mg * 8 + i, n, acc[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out(mg * 8 + i, ng * 4 + j, acc[i][j]);
   }
 }
 
-__global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const drgnn_head_args a) {
+__global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const drgnn_head_args a, int RB) {
   extern __shared__ __align__(16) float hs[];
-  __shared__ float red[HD_THREADS / 32];
   const int C = a.C, Hd = a.Hd, out = a.out, B = a.B;
-  const HeadSmem P = head_plan(C, Hd, out);
+  const HeadSmem P = head_plan(C, Hd, out, RB);
   float* W1s = hs + P.w1;
+  float* W1t = hs + P.w1t;
   float* W2s = hs + P.w2;
   float* Rs = hs + P.r;
+  float* Rt = hs + P.rt;
   float* Hs = hs + P.h;
   float* dHs = hs + P.dh;
+  float* dHt = hs + P.dht;
   float* preds = hs + P.dp;
-  float* dps = preds + HD_ROWS * (out + 1);
+  const int ldp = out + 1;
+  float* dps = preds + RB * ldp;
   const int t = threadIdx.x, T = blockDim.x;
+  const int lane = t & 31, warp = t >> 5, nwarps = T >> 5;
   const bool bwd = a.task != 0 && a.dW1 != nullptr;
-  const int ldw1 = P.ldw1, ldr = P.ldr, ldh = P.ldh, ldp = out + 1;
 
-  for (int i = t; i < Hd * C; i += T) W1s[(i / C) * ldw1 + (i % C)] = a.W1[i];
+  for (int i = t; i < Hd * C; i += T) {
+    const float w = a.W1[i];
+    const int h = i / C, c = i - h * C;
+    W1s[i] = w;
+    W1t[c * (Hd + 4) + h] = w;
+  }
   for (int i = t; i < out * Hd; i += T) W2s[i] = a.W2[i];
-  float loss_acc = 0.f;
+  float loss_acc = 0.f;  // thread r < RB accumulates the loss of row r of every chunk
 
-  for (int r0 = 0; r0 < B; r0 += HD_ROWS) {
-    const int rows = min(HD_ROWS, B - r0);
+  for (int r0 = 0; r0 < B; r0 += RB) {
+    const int rows = min(RB, B - r0);
     __syncthreads();  // weights staged / previous chunk fully consumed
-    for (int i = t; i < HD_ROWS * C; i += T) {
-      const int r = i / C, k = i % C;
-      Rs[r * ldr + k] = r < rows ? a.R[(int64_t)(r0 + r) * a.ldr + k] : 0.f;
+    for (int i = t; i < RB * C; i += T) {
+      const int r = i / C, c = i - r * C;
+      const float v = r < rows ? a.R[(int64_t)(r0 + r) * a.ldr + c] : 0.f;
+      Rs[i] = v;
+      Rt[c * (RB + 4) + r] = v;
     }
     __syncthreads();
-    // ---- H = relu(R W1^T + b1) * keep
-    mini_gemm(HD_ROWS, Hd, C, [&](int m, int k) { return Rs[m * ldr + k]; },
-              [&](int k, int n) { return W1s[n * ldw1 + k]; },
-              [&](int m, int n, float v) {
-                v += a.b1 ? __ldg(a.b1 + n) : 0.f;
-                v = v < 0.f ? 0.f : v;
-                if (a.keep && m < rows) v = a.keep[(int64_t)(r0 + m) * Hd + n] > 0.f ? v * a.keep_scale : 0.f;
-                Hs[m * ldh + n] = m < rows ? v : 0.f;
-                if (a.H && m < rows) a.H[(int64_t)(r0 + m) * Hd + n] = v;
-              });
+    // ---- H = relu(R W1^T + b1) * keep                                   [RB x Hd]
+    tile_gemm(Rt, RB + 4, W1t, Hd + 4, RB, Hd, C, [&](int m, int n, float v) {
+      v += a.b1 ? __ldg(a.b1 + n) : 0.f;
+      v = v < 0.f ? 0.f : v;
+      if (m < rows) {
+        if (a.keep) v = a.keep[(int64_t)(r0 + m) * Hd + n] > 0.f ? v * a.keep_scale : 0.f;
+        if (a.H) a.H[(int64_t)(r0 + m) * Hd + n] = v;
+      } else {
+        v = 0.f;
+      }
+      Hs[m * Hd + n] = v;
+    });
     __syncthreads();
-    // ---- pred = H W2^T + b2
-    mini_gemm(HD_ROWS, out, Hd, [&](int m, int k) { return Hs[m * ldh + k]; },
-              [&](int k, int n) { return W2s[n * Hd + k]; },
-              [&](int m, int n, float v) {
-                v += a.b2 ? __ldg(a.b2 + n) : 0.f;
-                preds[m * ldp + n] = v;
-                if (m < rows) a.pred[(int64_t)(r0 + m) * out + n] = v;
-              });
+    // ---- pred = H W2^T + b2: one warp per (row, output), lanes over the hidden units
+    for (int item = warp; item < RB * out; item += nwarps) {
+      const int r = item / out, o = item - r * out;
+      float sacc = 0.f;
+      for (int h = lane; h < Hd; h += 32) sacc = fmaf(Hs[r * Hd + h], W2s[o * Hd + h], sacc);
+      sacc = warp_sum(sacc);
+      if (lane == 0) {
+        sacc += a.b2 ? __ldg(a.b2 + o) : 0.f;
+        preds[r * ldp + o] = sacc;
+        if (r < rows) a.pred[(int64_t)(r0 + r) * out + o] = sacc;
+      }
+    }
     __syncthreads();
     if (a.task == 0) continue;
     // ---- loss and dLoss/dpred of the chunk (one thread per row)
-    if (t < HD_ROWS) {
+    if (t < RB) {
       const int r = t;
       if (r < rows) {
         if (a.task == 3) {
@@ -146,51 +178,63 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const drgnn_head_ar
     }
     __syncthreads();
     if (!bwd) continue;
-    // ---- dW2 (+)= dpred^T H, db2 (+)= sum dpred      [out x Hd]
-    mini_gemm(out, Hd, HD_ROWS, [&](int m, int k) { return dps[k * ldp + min(m, out - 1)]; },
-              [&](int k, int n) { return Hs[k * ldh + n]; },
-              [&](int m, int n, float v) {
-                float* g = a.dW2 + (int64_t)m * Hd + n;
-                *g = r0 == 0 ? v : *g + v;
-              });
+    // ---- dW2 (+)= dpred^T H, db2 (+)= sum dpred: one thread per (output, hidden unit)
+    for (int item = t; item < out * Hd; item += T) {
+      const int o = item / Hd, h = item - o * Hd;
+      float sacc = 0.f;
+      for (int r = 0; r < RB; ++r) sacc = fmaf(dps[r * ldp + o], Hs[r * Hd + h], sacc);
+      float* g = a.dW2 + item;
+      *g = r0 == 0 ? sacc : *g + sacc;
+    }
     if (t < out && a.db2) {
       float sacc = 0.f;
-      for (int r = 0; r < HD_ROWS; ++r) sacc += dps[r * ldp + t];
+      for (int r = 0; r < RB; ++r) sacc += dps[r * ldp + t];
       a.db2[t] = r0 == 0 ? sacc : a.db2[t] + sacc;
     }
-    // ---- dH = (dpred W2) * (H > 0) * keep_scale
-    mini_gemm(HD_ROWS, Hd, out, [&](int m, int k) { return dps[m * ldp + k]; },
-              [&](int k, int n) { return W2s[k * Hd + n]; },
-              [&](int m, int n, float v) { dHs[m * ldh + n] = Hs[m * ldh + n] > 0.f ? v * a.keep_scale : 0.f; });
+    // ---- dH = (dpred W2) * (H > 0) * keep_scale, stored in both layouts
+    for (int item = t; item < RB * Hd; item += T) {
+      const int r = item / Hd, h = item - r * Hd;
+      float sacc = 0.f;
+      for (int o = 0; o < out; ++o) sacc = fmaf(dps[r * ldp + o], W2s[o * Hd + h], sacc);
+      sacc = Hs[item] > 0.f ? sacc * a.keep_scale : 0.f;
+      dHs[item] = sacc;
+      dHt[h * (RB + 4) + r] = sacc;
+    }
     __syncthreads();
-    // ---- dW1 (+)= dH^T R, db1 (+)= sum dH             [Hd x C]
-    mini_gemm(Hd, C, HD_ROWS, [&](int m, int k) { return dHs[k * ldh + min(m, Hd - 1)]; },
-              [&](int k, int n) { return Rs[k * ldr + n]; },
-              [&](int m, int n, float v) {
-                float* g = a.dW1 + (int64_t)m * C + n;
-                *g = r0 == 0 ? v : *g + v;
-              });
+    // ---- dW1 (+)= dH^T R                                                [Hd x C]
+    tile_gemm(dHs, Hd, Rs, C, Hd, C, RB, [&](int m, int n, float v) {
+      float* g = a.dW1 + (int64_t)m * C + n;
+      *g = r0 == 0 ? v : *g + v;
+    });
     if (a.db1) {
       for (int h = t; h < Hd; h += T) {
         float sacc = 0.f;
-        for (int r = 0; r < HD_ROWS; ++r) sacc += dHs[r * ldh + h];
+        for (int r = 0; r < RB; ++r) sacc += dHs[r * Hd + h];
         a.db1[h] = r0 == 0 ? sacc : a.db1[h] + sacc;
       }
     }
-    // ---- dR = dH W1                                   [rows x C]
+    // ---- dR = dH W1                                                     [RB x C]
     if (a.dR) {
-      mini_gemm(HD_ROWS, C, Hd, [&](int m, int k) { return dHs[m * ldh + k]; },
-                [&](int k, int n) { return W1s[k * ldw1 + n]; },
-                [&](int m, int n, float v) {
-                  if (m < rows) a.dR[(int64_t)(r0 + m) * a.lddr + n] = v;
-                });
+      tile_gemm(dHt, RB + 4, W1s, C, RB, C, Hd, [&](int m, int n, float v) {
+        if (m < rows) a.dR[(int64_t)(r0 + m) * a.lddr + n] = v;
+      });
     }
   }
   if (a.task != 0 && a.loss) {
-    float s = warp_sum(t < HD_ROWS ? loss_acc : 0.f);
-    if (t == 0) a.loss[0] = s * a.inv_norm;   // only warp 0 holds row losses (HD_ROWS == 32)
+    // rows live in threads 0..RB-1 (warps 0 and 1 when RB = 64)
+    __shared__ float lred[2];
+    const float s = warp_sum(t < RB ? loss_acc : 0.f);
+    if (lane == 0 && warp < 2) lred[warp] = s;
+    __syncthreads();
+    if (t == 0) a.loss[0] = (lred[0] + lred[1]) * a.inv_norm;
   }
-  (void)red;
+}
+
+static inline int head_rows_per_chunk(int C, int Hd, int out) {
+  const int64_t budget = (int64_t)device_info().smem_optin - 2048;
+  if ((int64_t)head_plan(C, Hd, out, 64).total * 4 <= budget) return 64;
+  if ((int64_t)head_plan(C, Hd, out, 32).total * 4 <= budget) return 32;
+  return 0;
 }
 
 }  // namespace drgnn
@@ -199,9 +243,10 @@ using namespace drgnn;
 
 extern "C" int64_t drgnn_head_smem_bytes(int32_t C, int32_t Hd, int32_t out) {
   if (C <= 0 || Hd <= 0 || out <= 0) return DRGNN_ERR_INVALID;
-  const int64_t bytes = (int64_t)head_plan(C, Hd, out).total * 4;
-  if (bytes > device_info().smem_optin - 2048) return DRGNN_ERR_UNSUPPORTED;
-  return bytes;
+  if (C % 4 != 0 || Hd % 8 != 0) return DRGNN_ERR_UNSUPPORTED;
+  const int rb = head_rows_per_chunk(C, Hd, out);
+  if (rb == 0) return DRGNN_ERR_UNSUPPORTED;
+  return (int64_t)head_plan(C, Hd, out, rb).total * 4;
 }
 
 extern "C" int drgnn_head(const drgnn_head_args* a, void* stream) {
@@ -215,14 +260,16 @@ extern "C" int drgnn_head(const drgnn_head_args* a, void* stream) {
   DRGNN_REQUIRE(a->ldr >= a->C && (!a->dR || a->lddr >= a->C), "head: leading dimension too small");
   if (a->B == 0) return DRGNN_OK;
   const int64_t smem = drgnn_head_smem_bytes(a->C, a->Hd, a->out);
-  if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "head: fc1 %d x %d does not fit shared memory", a->Hd, a->C);
+  if (smem < 0)
+    return fail(DRGNN_ERR_UNSUPPORTED, "head: fc1 %d x %d does not fit one CTA (needs C %% 4 == 0, Hd %% 8 == 0)", a->Hd, a->C);
+  const int rb = head_rows_per_chunk(a->C, a->Hd, a->out);
   static thread_local int64_t configured = -1;
   if (smem > configured) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)device_info().smem_optin - 2048));
     configured = device_info().smem_optin - 2048;
   }
-  head_kernel<<<1, HD_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  head_kernel<<<1, HD_THREADS, smem, (cudaStream_t)stream>>>(*a, rb);
   DRGNN_CHECK_LAUNCH("head_kernel");
   return DRGNN_OK;
 }

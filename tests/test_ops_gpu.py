@@ -434,13 +434,19 @@ def test_adam_flat_matches_torch_adam(lib):
 
 
 @pytest.mark.parametrize('task', ['mse', 'mse_sigmoid', 'ce', 'none'])
-@pytest.mark.parametrize('B,C,Hd,out', [(64, 64, 128, 1), (77, 32, 64, 1), (5, 128, 256, 1), (40, 64, 128, 3)])
+@pytest.mark.parametrize('B,C,Hd,out', [(64, 64, 128, 1), (77, 32, 64, 1), (5, 128, 256, 1), (40, 64, 128, 3), (130, 64, 64, 2)])
 def test_fused_head_matches_torch(lib, task, B, C, Hd, out):
     from deeprank_gnn_b200 import ops
     if task == 'ce' and out == 1:
         pytest.skip('cross entropy needs several classes')
     if task in ('mse', 'mse_sigmoid') and out != 1:
         pytest.skip('regression head has one output')
+    if not ops.head_fits(C, Hd, out):
+        from deeprank_gnn_b200._lib import DrgnnError
+        with pytest.raises(DrgnnError):       # too large for one CTA: the engine falls back to the op-by-op path
+            ops.head(torch.zeros(B, C, device=_dev()), torch.zeros(Hd, C, device=_dev()), None,
+                     torch.zeros(out, Hd, device=_dev()), None, torch.zeros(B, out, device=_dev()))
+        return
     dev = _dev()
     g = torch.Generator().manual_seed(B + C)
     R = torch.randn(B, C, generator=g, requires_grad=True)
