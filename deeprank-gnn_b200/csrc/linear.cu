@@ -289,6 +289,156 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const drgnn_linear_wg
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Weight gradient, small-matrix fast path (every conv layer of the reference networks):
+// per group Fout <= 64 and Fout * ceil(Fin / 32) <= 64 accumulators per lane.
+//   * a warp owns a contiguous slice of rows; lane l owns column l (and l + 32) of X and keeps the
+//     whole Fout x {1,2} strip of dW in registers; the G row is loaded once, coalesced, and its
+//     entries are broadcast with shuffles: Fout SHFL + Fout FMA per row, no shared memory;
+//   * the 8 warp strips of a CTA are summed in shared memory in warp order, the CTA partial goes
+//     to scratch, and the LAST CTA to arrive (ticket counter) sums the partials in CTA order and
+//     writes dW / dbias: one launch, fixed summation order (deterministic), counter self-resets.
+// ---------------------------------------------------------------------------------------
+static constexpr int WGF_MAX_CTAS = 64;
+
+template <int FOUT, int NC, int NT>
+__global__ void __launch_bounds__(NT) wgrad_warp_kernel(const drgnn_linear_wgrad_args a, float* scratch, unsigned* ticket) {
+  extern __shared__ float wsm[];  // [NT / 32 warps][E]
+  constexpr int NW = NT / 32;
+  __shared__ bool is_last;
+  const int Fin = a.Fin, Fout = a.Fout, groups = a.groups;
+  const int nW = groups * Fout * Fin, E = nW + groups * Fout;
+  const int rows = live_rows(a.rows, a.rows_dev);
+  const int lane = lane_id(), warp = warp_id();
+  const int nwg = gridDim.x * NW, wg = blockIdx.x * NW + warp;
+  const int rpw = (rows + nwg - 1) / nwg;
+  const int rbeg = min(wg * rpw, rows), rend = min(rbeg + rpw, rows);
+  float* mine = wsm + (size_t)warp * E;
+  for (int g = 0; g < groups; ++g) {
+    float acc[FOUT][NC];
+    float bacc[(FOUT + 31) / 32];
+#pragma unroll
+    for (int o = 0; o < FOUT; ++o)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[o][c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < (FOUT + 31) / 32; ++q) bacc[q] = 0.f;
+    constexpr int RU = 8;  // rows in flight per warp: their loads are issued together (latency), then consumed
+    constexpr int NQ = (FOUT + 31) / 32;
+    for (int r0 = rbeg; r0 < rend; r0 += RU) {
+      float gl[RU][NQ], xv[RU][NC];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const int r = r0 + u;
+        const bool live = r < rend;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int o = q * 32 + lane;
+          gl[u][q] = (live && o < Fout) ? a.G[(int64_t)r * a.ldg + (int64_t)g * Fout + o] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int i = c * 32 + lane;
+          xv[u][c] = (live && i < Fin) ? a.X[(int64_t)r * a.ldx + (int64_t)g * Fin + i] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) bacc[q] += gl[u][q];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xv[u][c] = (xv[u][c] == xv[u][c]) ? xv[u][c] : 0.f;  // NaN input row <=> zero
+                                                                // gradient row (Fout rule): drop instead of 0 * NaN
+#pragma unroll
+        for (int o = 0; o < FOUT; ++o) {
+          const float gv = __shfl_sync(0xffffffffu, gl[u][o / 32], o % 32);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[o][c] = fmaf(gv, xv[u][c], acc[o][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < FOUT; ++o) {
+      if (o < Fout) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int i = c * 32 + lane;
+          if (i < Fin) {
+            const int e = a.w_layout == 0 ? (g * Fout + o) * Fin + i : (g * Fin + i) * Fout + o;
+            mine[e] = acc[o][c];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < (FOUT + 31) / 32; ++q) {
+      const int o = q * 32 + lane;
+      if (o < Fout) mine[nW + g * Fout + o] = bacc[q];
+    }
+  }
+  __syncthreads();
+  float* part = scratch + (size_t)blockIdx.x * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < NW; ++w) s += wsm[(size_t)w * E + e];
+    part[e] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 4
+    for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(scratch + (size_t)c * E + e);
+    if (e < nW) {
+      a.dW[e] = a.accumulate ? a.dW[e] + s : s;
+    } else if (a.dbias) {
+      a.dbias[e - nW] = a.accumulate ? a.dbias[e - nW] + s : s;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch / graph replay
+}
+
+static inline int wgrad_fast_threads(const drgnn_linear_wgrad_args& a) {
+  // 0: not eligible.  1024 threads (32 warp strips) when the strips fit shared memory and 64 registers
+  // hold the strip; 512 threads for the 64-accumulator shapes
+  if (a.Fout > 64 || a.Fin > 64) return 0;
+  const int nc = (a.Fin + 31) / 32;
+  const int fo = a.Fout <= 16 ? 16 : (a.Fout <= 32 ? 32 : 64);
+  if (fo * nc > 64) return 0;
+  const int64_t E = (int64_t)a.groups * a.Fout * (a.Fin + 1);
+  const int nt = 256;  // measured on B200 (N = 12800, 32 x 32): 256 threads x 64 CTAs 19.6 us; 1024 x 16: 24.6 us
+  if (E * (nt / 32) * 4 > 200 * 1024) return 0;
+  return nt;
+}
+static inline int wgrad_fast_ctas(int rows) {
+  int c = (rows + 127) / 128;  // >= 16 rows per warp before another CTA is worth its partial
+  if (c > WGF_MAX_CTAS) c = WGF_MAX_CTAS;
+  if (c < 1) c = 1;
+  return c;
+}
+
+template <int FOUT, int NC, int NT>
+static int launch_wgrad_fast(const drgnn_linear_wgrad_args& a, int ctas, float* scratch, unsigned* ticket, cudaStream_t st) {
+  const size_t smem = (size_t)(NT / 32) * a.groups * a.Fout * (a.Fin + 1) * sizeof(float);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_warp_kernel<FOUT, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          204 * 1024));
+    configured = 204 * 1024;
+  }
+  wgrad_warp_kernel<FOUT, NC, NT><<<ctas, NT, smem, st>>>(a, scratch, ticket);
+  DRGNN_CHECK_LAUNCH("wgrad_warp_kernel");
+  return DRGNN_OK;
+}
+
 }  // namespace drgnn
 
 using namespace drgnn;
@@ -321,7 +471,10 @@ extern "C" int drgnn_linear(const drgnn_linear_args* a, void* stream) {
 
 extern "C" int64_t drgnn_linear_wgrad_work_floats(int32_t rows, int32_t Fin, int32_t Fout, int32_t groups) {
   if (rows < 0 || Fin <= 0 || Fout <= 0 || groups <= 0) return DRGNN_ERR_INVALID;
-  return (int64_t)wgrad_chunks(rows) * groups * Fout * ((int64_t)Fin + 1);
+  const int64_t E = (int64_t)groups * Fout * ((int64_t)Fin + 1);
+  const int64_t general = (int64_t)wgrad_chunks(rows) * E;
+  const int64_t fast = (int64_t)WGF_MAX_CTAS * E;
+  return (general > fast ? general : fast) + 4;  // + the ticket counter of the fast path (last 4 floats)
 }
 
 extern "C" int drgnn_linear_wgrad(const drgnn_linear_wgrad_args* a, void* stream) {
@@ -334,6 +487,18 @@ extern "C" int drgnn_linear_wgrad(const drgnn_linear_wgrad_args* a, void* stream
   DRGNN_REQUIRE(a->work_floats >= need, "linear_wgrad: workspace too small (%lld < %lld floats)", (long long)a->work_floats,
                 (long long)need);
   cudaStream_t st = (cudaStream_t)stream;
+  if (wgrad_fast_threads(*a) != 0) {
+    // the ticket lives in the last 4 floats of the workspace: zero before the first use (the caller
+    // allocates the workspace zero-filled), reset by the kernel itself afterwards
+    unsigned* ticket = reinterpret_cast<unsigned*>(a->work + a->work_floats - 4);
+    const int ctas = wgrad_fast_ctas(a->rows);
+    const int nc = (a->Fin + 31) / 32;
+    if (a->Fout <= 16) return nc == 1 ? launch_wgrad_fast<16, 1, 256>(*a, ctas, a->work, ticket, st)
+                                      : launch_wgrad_fast<16, 2, 256>(*a, ctas, a->work, ticket, st);
+    if (a->Fout <= 32) return nc == 1 ? launch_wgrad_fast<32, 1, 256>(*a, ctas, a->work, ticket, st)
+                                      : launch_wgrad_fast<32, 2, 256>(*a, ctas, a->work, ticket, st);
+    return launch_wgrad_fast<64, 1, 256>(*a, ctas, a->work, ticket, st);
+  }
   const int n_chunks = wgrad_chunks(a->rows);
   const int o_tiles = (a->Fout + WG_O - 1) / WG_O, k_tiles = (a->Fin + WG_K - 1) / WG_K;
   dim3 grid(n_chunks, a->groups * o_tiles * k_tiles);

@@ -88,11 +88,17 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         const float* __restrict__ step_dev, int64_t n, float lr, float beta1,
                                                         float beta2, float eps, float grad_scale) {
-  const float step = step_dev[0] + 1.f;
-  const float bc1 = 1.f - (float)pow((double)beta1, (double)step);
-  const float bc2 = 1.f - (float)pow((double)beta2, (double)step);
-  const float step_size = lr / bc1;
-  const float bc2_sqrt = sqrtf(bc2);
+  __shared__ float sh[3];
+  if (threadIdx.x == 0) {  // one thread does the double-precision powers (FP64 is slow on this part)
+    const float st = step_dev[0] + 1.f;
+    sh[0] = st;
+    sh[1] = 1.f - (float)pow((double)beta1, (double)st);
+    sh[2] = 1.f - (float)pow((double)beta2, (double)st);
+  }
+  __syncthreads();
+  const float step = sh[0];
+  const float step_size = lr / sh[1];
+  const float bc2_sqrt = sqrtf(sh[2]);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     float mi = m[i], vi = v[i];
@@ -105,6 +111,37 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   }
 }
 __global__ void step_increment_kernel(float* step_dev) { step_dev[0] += 1.f; }
+
+// Small parameter sets (every reference network: ~4-11 k floats): ONE block does the update and
+// bumps the step counter itself (all threads read it, barrier, thread 0 writes) - one launch less.
+__global__ void __launch_bounds__(1024) adam_flat_small_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                               float* __restrict__ m, float* __restrict__ v,
+                                                               float* step_dev, int n, float lr, float beta1, float beta2,
+                                                               float eps, float grad_scale) {
+  __shared__ float sh[3];
+  if (threadIdx.x == 0) {  // one thread does the double-precision powers (FP64 is slow on this part)
+    const float st = step_dev[0] + 1.f;
+    sh[0] = st;
+    sh[1] = 1.f - (float)pow((double)beta1, (double)st);
+    sh[2] = 1.f - (float)pow((double)beta2, (double)st);
+  }
+  __syncthreads();
+  const float step = sh[0];
+  const float step_size = lr / sh[1];
+  const float bc2_sqrt = sqrtf(sh[2]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.f - beta1);
+    vi = vi * beta2 + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) step_dev[0] = step;
+}
 
 __global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ out,
                                                         int ldo, int rows, const int32_t* rows_dev, int C,
@@ -155,6 +192,12 @@ extern "C" int drgnn_adam_flat(float* param, const float* grad, float* exp_avg, 
   DRGNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev, "adam_flat: NULL pointer");
   DRGNN_REQUIRE(n >= 0, "adam_flat: negative size");
   cudaStream_t st = (cudaStream_t)stream;
+  if (false && n > 0 && n <= 32768) {  // measured slower on B200 (12.5 us vs 4.2 + 1.9 us): one block serialises the memory round trips
+    adam_flat_small_kernel<<<1, 1024, 0, st>>>(param, grad, exp_avg, exp_avg_sq, step_dev, (int)n, lr, beta1, beta2, eps,
+                                               grad_scale);
+    DRGNN_CHECK_LAUNCH("adam_flat_small_kernel");
+    return DRGNN_OK;
+  }
   if (n > 0) {
     const int blocks = (int)min_i64((n + 255) / 256, (int64_t)device_info().sms * 8);
     adam_flat_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, step_dev, n, lr, beta1, beta2, eps, grad_scale);

@@ -310,7 +310,7 @@ def linear_wgrad(X, G, Fin, Fout, dW, dbias=None, groups=1, w_layout=0, rows=Non
     rows = int(G.size(0) if rows is None else rows)
     need = linear_wgrad_work_floats(rows, Fin, Fout, groups)
     if work is None:
-        work = torch.empty(need, dtype=F32, device=G.device)
+        work = torch.zeros(need, dtype=F32, device=G.device)      # zero: the fast path keeps a ticket counter in it
     if not dW.is_contiguous() or dW.numel() != groups * Fin * Fout:
         raise DrgnnError('dW must be contiguous with groups*Fin*Fout elements')
     a = LinearWgradArgs()

@@ -209,9 +209,11 @@ int drgnn_linear(const drgnn_linear_args* a, void* stream);
 
 /* Weight / bias gradient of the transform: dW[g][o][k] (w_layout 0) or dW[g][k][o]
  * (w_layout 1) (+)= sum_r G[r, g*Fout+o] * X[r, g*Fin+k], dbias[g*Fout+o] (+)= sum_r G[r,..].
- * Two-phase deterministic reduction: partials [n_chunks, groups*Fout*(Fin+1)] in `work`,
- * then a fixed-order sum.  accumulate != 0 adds into dW / dbias, else overwrites.
- * dbias may be NULL. */
+ * Deterministic reduction over row chunks: partials in `work`, summed in a fixed order (small
+ * matrices: one launch, the last CTA to finish does the sum; large ones: a second launch).
+ * `work` must be ZERO-FILLED before its first use (its last 4 floats hold a ticket counter that
+ * the kernel resets itself) and must not be shared by launches that may run concurrently.
+ * accumulate != 0 adds into dW / dbias, else overwrites.  dbias may be NULL. */
 typedef struct drgnn_linear_wgrad_args {
   const float* X; int32_t ldx;
   const float* G; int32_t ldg;

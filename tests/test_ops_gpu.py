@@ -412,10 +412,10 @@ def test_mse_and_ce_loss(lib):
     torch.testing.assert_close(dl.cpu(), logits.grad, rtol=1e-5, atol=1e-7)
 
 
-def test_adam_flat_matches_torch_adam(lib):
+@pytest.mark.parametrize('n', [10701, 70001])
+def test_adam_flat_matches_torch_adam(lib, n):
     from deeprank_gnn_b200 import ops
     dev = _dev()
-    n = 10701
     p0 = torch.randn(n)
     ref_p = torch.nn.Parameter(p0.clone())
     opt = torch.optim.Adam([ref_p], lr=0.01)
