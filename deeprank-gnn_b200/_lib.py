@@ -21,12 +21,14 @@ ST_CLUSTER_RANGE = 2
 ST_CLUSTER1_LENGTH = 4
 ST_CLUSTER_ORDER = 8
 ST_NEGATIVE_ID = 16
+ST_FUSED_BOUNDS = 64
 STATUS_TEXT = {
     ST_EDGE_OUTSIDE_GRAPH: 'an edge endpoint lies outside its graph',
     ST_CLUSTER_RANGE: 'cluster-id range of one graph exceeds 32768',
     ST_CLUSTER1_LENGTH: 'len(cluster1) of a graph differs from its number of level-0 clusters',
     ST_CLUSTER_ORDER: 'global cluster ids do not increase with the graph id',
     ST_NEGATIVE_ID: 'negative cluster id',
+    ST_FUSED_BOUNDS: 'a graph exceeds the per-graph bounds given to the fused kernels',
 }
 
 
@@ -89,6 +91,26 @@ class LinearWgradArgs(C.Structure):
     ]
 
 
+class GinetFusedArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('F', C.c_int32), ('h1', C.c_int32), ('h2', C.c_int32), ('nb', C.c_int32),
+        ('max_n', C.c_int32), ('max_k', C.c_int32), ('max_q', C.c_int32),
+        ('node_ptr', VP),
+        ('rowptr0', VP), ('col0', VP),
+        ('rowptr1', VP), ('col1', VP),
+        ('cscptr1', VP), ('cscrow1', VP),
+        ('cmptr0', VP), ('cmem0', VP), ('cl0', VP), ('kptr0', VP),
+        ('cmptr1', VP), ('cmem1', VP), ('cl1', VP), ('kptr1', VP),
+        ('status', VP),
+        ('W1', VP), ('W2', VP),
+        ('x', VP),
+        ('Zin1', VP), ('Z1', VP), ('arg0', VP),
+        ('Zin2', VP), ('Z2', VP), ('arg1', VP),
+        ('R', VP),
+        ('dR', VP), ('partial', VP), ('dW1', VP), ('dW2', VP),
+    ]
+
+
 class HeadArgs(C.Structure):
     _fields_ = [
         ('R', VP), ('ldr', C.c_int32),
@@ -126,6 +148,9 @@ _SIGNATURES = {
     'drgnn_mse_loss': (C.c_int, [VP, VP, _i32, _f32, _i32, VP, VP, VP]),
     'drgnn_ce_loss': (C.c_int, [VP, _i32, VP, VP, _i32, _i32, _f32, VP, VP, VP]),
     'drgnn_adam_flat': (C.c_int, [VP, VP, VP, VP, VP, _i64, _f32, _f32, _f32, _f32, _f32, VP]),
+    'drgnn_ginet_fused_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    'drgnn_ginet_fused_fwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
+    'drgnn_ginet_fused_bwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
@@ -138,7 +163,7 @@ EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 _lib = None
 launch_count = 0           # C-ABI compute calls made by this process
 kernel_count = 0           # CUDA kernels those calls launched (bench: gpu_launches)
-KERNELS_PER_CALL = {'drgnn_structure_build': 2, 'drgnn_cluster_offset': 2}   # lower bounds for the others
+KERNELS_PER_CALL = {'drgnn_structure_build': 2, 'drgnn_cluster_offset': 2, 'drgnn_ginet_fused_bwd': 2}   # lower bounds for the others
 
 
 class DrgnnError(RuntimeError):

@@ -103,4 +103,43 @@ __device__ inline int block_exclusive_scan(int* a, int len, int* wsum) {
   return total;
 }
 
+// CTA-wide small GEMM out of shared memory:  C[m][n] = sum_k At[k * lda + m] * Bm[k * ldb + n]
+// (A is held TRANSPOSED so the 8 rows of a thread tile are two 16-byte loads, broadcast inside a
+// warp; Bm rows are contiguous in n).  8 (m) x 4 (n) register tile per thread: 3 LDS.128 + 32 FMA per
+// k step.  M % 8 == 0 and N % 4 == 0 (pad the buffers), lda % 4 == 0, ldb % 4 == 0, 16-byte aligned
+// bases.  out(m, n, value) is called for every element of the padded tile.
+template <typename FO>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb,
+                                          int M, int N, int K, FO out) {
+  const int mt = M >> 3, nt = N >> 2;  // M % 8 == 0, N % 4 == 0 (checked on the host)
+  for (int item = threadIdx.x; item < mt * nt; item += blockDim.x) {
+    const int mg = item / nt, ng = item - mg * nt;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* ap = At + mg * 8;
+    const float* bp = Bm + ng * 4;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ap + k * lda);
+      const float4 a1 = *reinterpret_cast<const float4*>(ap + k * lda + 4);
+      const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out(mg * 8 + i, ng * 4 + j, acc[i][j]);
+  }
+}
+
 }  // namespace drgnn

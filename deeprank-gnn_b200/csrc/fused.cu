@@ -1,0 +1,396 @@
+// Per-graph fused GINet forward and backward: ONE CTA per protein-interface graph.
+//
+// The op-by-op path (aggregate / linear / maxpool / segment_mean launches, engine.py) spends a
+// training step of the headline configuration (64 graphs of 200 nodes) in ~15 launches that are
+// each a handful of dependent memory round trips: pure latency.  Graphs are independent and a
+// whole graph (200 x 32 fp32 = 25.6 KB) fits shared memory, so these kernels keep
+// every intermediate of a graph on the SM:
+//
+//   ginet_graph_fwd_kernel  (ginet.py:105-134, both branches at once)
+//     x tile -> AX = A x -> Z1 = relu(AX W1cat^T) -> P1 = cluster max (+argmax)
+//            -> AP = A1 P1 -> Z2 = relu(grouped AP W2^T) -> P2 = cluster max (+argmax) -> R = mean P2
+//     what the backward needs goes to global memory once (AX, Z1, argmax0, AP, Z2, argmax1).
+//   ginet_graph_bwd_kernel  (autograd of the above)
+//     dR -> dZ2 (mean bwd, argmax routing, ReLU mask) -> per-graph dW2 partial, dAP = dZ2 W2
+//        -> dP1 = A1^T dAP -> dZ1 (argmax routing, ReLU mask) -> per-graph dW1 partial
+//   ginet_wgrad_reduce_kernel: sum of the per-graph partials in graph order (deterministic).
+//
+// Dense products use the CTA-level tile_gemm (8 x 4 register tiles over transposed shared-memory
+// operands); gathers read neighbour rows from shared memory; indices come from the structure pass
+// (L2 resident, just written).  GINet has no bias, no self term, unit edge weights (alpha == 1).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace drgnn {
+
+static constexpr int FU_THREADS = 512;
+
+__host__ __device__ inline int up8(int x) { return (x + 7) & ~7; }
+
+struct FwdSmem {
+  int xs, axT, z1, w1t, w2t, p1, apT, z2, p2, total;
+  int n_p, k_p, q_p;
+};
+__host__ __device__ inline FwdSmem fwd_plan(int F, int C1, int C2, int h1, int h2, int nb, int max_n, int max_k, int max_q) {
+  FwdSmem p;
+  p.n_p = up8(max_n) + 4;   // +4: transposing stores of consecutive rows spread over banks
+  p.k_p = up8(max_k) + 4;
+  p.q_p = up8(max_q);
+  int o = 0;
+  p.xs = o;  o += up8(max_n) * F;
+  p.axT = o; o += F * p.n_p;
+  p.z1 = o;  o += up8(max_n) * C1;
+  p.w1t = o; o += F * C1;
+  p.w2t = o; o += nb * h1 * h2;
+  p.p1 = o;  o += up8(max_k) * C1;
+  p.apT = o; o += C1 * p.k_p;
+  p.z2 = o;  o += up8(max_k) * C2;
+  p.p2 = o;  o += p.q_p * C2;
+  p.total = o;
+  return p;
+}
+
+struct BwdSmem {
+  int dz2, dz2T, ap, dap, dp1, dz1, ax, w2, total;
+  int k_p;
+};
+__host__ __device__ inline BwdSmem bwd_plan(int F, int C1, int C2, int h1, int h2, int nb, int max_n, int max_k) {
+  BwdSmem p;
+  p.k_p = up8(max_k) + 4;
+  int o = 0;
+  p.dz2 = o;  o += up8(max_k) * C2;
+  p.dz2T = o; o += C2 * p.k_p;
+  p.ap = o;   o += up8(max_k) * C1;
+  p.dap = o;  o += up8(max_k) * C1;
+  p.dp1 = o;  o += up8(max_k) * C1;
+  p.dz1 = o;  o += up8(max_n) * C1;
+  p.ax = o;   o += up8(max_n) * F;
+  p.w2 = o;   o += nb * h2 * h1;
+  p.total = o;
+  return p;
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_fwd_kernel(const drgnn_ginet_fused_args a) {
+  extern __shared__ __align__(16) float fs[];
+  const int F = a.F, h1 = a.h1, h2 = a.h2, nb = a.nb;
+  const int C1 = nb * h1, C2 = nb * h2;
+  const FwdSmem P = fwd_plan(F, C1, C2, h1, h2, nb, a.max_n, a.max_k, a.max_q);
+  float* xs = fs + P.xs;
+  float* axT = fs + P.axT;
+  float* z1 = fs + P.z1;
+  float* w1t = fs + P.w1t;
+  float* w2t = fs + P.w2t;
+  float* p1 = fs + P.p1;
+  float* apT = fs + P.apT;
+  float* z2 = fs + P.z2;
+  float* p2 = fs + P.p2;
+  const int t = threadIdx.x, T = blockDim.x;
+  const int g = blockIdx.x;
+  const int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
+  const int k0 = a.kptr0[g], K = a.kptr0[g + 1] - k0;
+  const int q0 = a.kptr1[g], Q = a.kptr1[g + 1] - q0;
+  if (n > a.max_n || K > a.max_k || Q > a.max_q) {  // host bounds violated: flag and leave (checked by validate())
+    if (t == 0) atomicOr(a.status, 64);
+    return;
+  }
+  const int n8 = up8(n), K8 = up8(K);
+  const int F4 = F >> 2, C14 = C1 >> 2, C24 = C2 >> 2;
+
+  // ---- stage the graph's features and the (transposed) weights
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.x + (int64_t)n0 * F);
+    float4* dst = reinterpret_cast<float4*>(xs);
+    for (int i = t; i < n * F4; i += T) dst[i] = src[i];
+    for (int i = t; i < C1 * F; i += T) {      // W1 [C1][F] -> w1t [F][C1]
+      const int c = i / F, f = i - c * F;
+      w1t[f * C1 + c] = a.W1[i];
+    }
+    for (int i = t; i < nb * h2 * h1; i += T) {  // W2 [nb][h2][h1] -> w2t [nb][h1][h2]
+      const int gg = i / (h2 * h1), r = i - gg * h2 * h1;
+      const int o = r / h1, j = r - o * h1;
+      w2t[(gg * h1 + j) * h2 + o] = a.W2[i];
+    }
+  }
+  __syncthreads();
+  // ---- AX = A x   (thread per (row, 4 channels); row index fastest => conflict-free transposed stores)
+  for (int item = t; item < n8 * F4; item += T) {
+    const int q4 = item / n8, i = item - q4 * n8;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      const int s = __ldg(a.rowptr0 + n0 + i), e = __ldg(a.rowptr0 + n0 + i + 1);
+      for (int p = s; p < e; ++p) {
+        const int c = __ldg(a.col0 + p) - n0;
+        const float4 v = *reinterpret_cast<const float4*>(xs + c * F + q4 * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(a.Zin1 + (int64_t)(n0 + i) * F + q4 * 4) = acc;
+    }
+    axT[(q4 * 4 + 0) * P.n_p + i] = acc.x;
+    axT[(q4 * 4 + 1) * P.n_p + i] = acc.y;
+    axT[(q4 * 4 + 2) * P.n_p + i] = acc.z;
+    axT[(q4 * 4 + 3) * P.n_p + i] = acc.w;
+  }
+  __syncthreads();
+  // ---- Z1 = relu(AX W1cat^T)
+  tile_gemm(axT, P.n_p, w1t, C1, n8, C1, F, [&](int m, int c, float v) {
+    v = v < 0.f ? 0.f : v;
+    z1[m * C1 + c] = v;
+    if (m < n) a.Z1[(int64_t)(n0 + m) * C1 + c] = v;
+  });
+  __syncthreads();
+  // ---- P1 = cluster max of Z1 (first member wins ties, a NaN never wins; community_pooling.py:201)
+  for (int item = t; item < K * C14; item += T) {
+    const int k = item / C14, q4 = item - k * C14;
+    const int s = __ldg(a.cmptr0 + k0 + k), e = __ldg(a.cmptr0 + k0 + k + 1);
+    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int4 arg = make_int4(-1, -1, -1, -1);
+    for (int p = s; p < e; ++p) {
+      const int i = __ldg(a.cmem0 + p);
+      const float4 v = *reinterpret_cast<const float4*>(z1 + (i - n0) * C1 + q4 * 4);
+      if (v.x > best.x) { best.x = v.x; arg.x = i; }
+      if (v.y > best.y) { best.y = v.y; arg.y = i; }
+      if (v.z > best.z) { best.z = v.z; arg.z = i; }
+      if (v.w > best.w) { best.w = v.w; arg.w = i; }
+    }
+    if (arg.x < 0) best.x = 0.f;
+    if (arg.y < 0) best.y = 0.f;
+    if (arg.z < 0) best.z = 0.f;
+    if (arg.w < 0) best.w = 0.f;
+    *reinterpret_cast<float4*>(p1 + k * C1 + q4 * 4) = best;
+    *reinterpret_cast<int4*>(a.arg0 + (int64_t)(k0 + k) * C1 + q4 * 4) = arg;
+  }
+  __syncthreads();
+  // ---- AP = A1 P1 on the coarsened graph
+  for (int item = t; item < K8 * C14; item += T) {
+    const int q4 = item / K8, k = item - q4 * K8;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) {
+      const int s = __ldg(a.rowptr1 + k0 + k), e = __ldg(a.rowptr1 + k0 + k + 1);
+      for (int p = s; p < e; ++p) {
+        const int c = __ldg(a.col1 + p) - k0;
+        const float4 v = *reinterpret_cast<const float4*>(p1 + c * C1 + q4 * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(a.Zin2 + (int64_t)(k0 + k) * C1 + q4 * 4) = acc;
+    }
+    apT[(q4 * 4 + 0) * P.k_p + k] = acc.x;
+    apT[(q4 * 4 + 1) * P.k_p + k] = acc.y;
+    apT[(q4 * 4 + 2) * P.k_p + k] = acc.z;
+    apT[(q4 * 4 + 3) * P.k_p + k] = acc.w;
+  }
+  __syncthreads();
+  // ---- Z2 = relu(AP_g W2_g^T) per branch g
+  for (int gg = 0; gg < nb; ++gg) {
+    tile_gemm(apT + gg * h1 * P.k_p, P.k_p, w2t + gg * h1 * h2, h2, K8, h2, h1, [&](int m, int o, float v) {
+      v = v < 0.f ? 0.f : v;
+      z2[m * C2 + gg * h2 + o] = v;
+      if (m < K) a.Z2[(int64_t)(k0 + m) * C2 + gg * h2 + o] = v;
+    });
+  }
+  __syncthreads();
+  // ---- P2 = level-1 cluster max (max_pool_x)
+  for (int item = t; item < Q * C24; item += T) {
+    const int q = item / C24, q4 = item - q * C24;
+    const int s = __ldg(a.cmptr1 + q0 + q), e = __ldg(a.cmptr1 + q0 + q + 1);
+    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int4 arg = make_int4(-1, -1, -1, -1);
+    for (int p = s; p < e; ++p) {
+      const int k = __ldg(a.cmem1 + p);
+      const float4 v = *reinterpret_cast<const float4*>(z2 + (k - k0) * C2 + q4 * 4);
+      if (v.x > best.x) { best.x = v.x; arg.x = k; }
+      if (v.y > best.y) { best.y = v.y; arg.y = k; }
+      if (v.z > best.z) { best.z = v.z; arg.z = k; }
+      if (v.w > best.w) { best.w = v.w; arg.w = k; }
+    }
+    if (arg.x < 0) best.x = 0.f;
+    if (arg.y < 0) best.y = 0.f;
+    if (arg.z < 0) best.z = 0.f;
+    if (arg.w < 0) best.w = 0.f;
+    *reinterpret_cast<float4*>(p2 + q * C2 + q4 * 4) = best;
+    *reinterpret_cast<int4*>(a.arg1 + (int64_t)(q0 + q) * C2 + q4 * 4) = arg;
+  }
+  __syncthreads();
+  // ---- R[g] = mean over the graph's level-1 clusters (scatter_mean by batch, ascending order)
+  for (int c = t; c < C2; c += T) {
+    float acc = 0.f;
+    for (int q = 0; q < Q; ++q) acc += p2[q * C2 + c];
+    a.R[(int64_t)g * C2 + c] = acc * (1.f / (float)max(Q, 1));
+  }
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const drgnn_ginet_fused_args a) {
+  extern __shared__ __align__(16) float bs[];
+  const int F = a.F, h1 = a.h1, h2 = a.h2, nb = a.nb;
+  const int C1 = nb * h1, C2 = nb * h2;
+  const BwdSmem P = bwd_plan(F, C1, C2, h1, h2, nb, a.max_n, a.max_k);
+  float* dz2 = bs + P.dz2;
+  float* dz2T = bs + P.dz2T;
+  float* ap = bs + P.ap;
+  float* dap = bs + P.dap;
+  float* dp1 = bs + P.dp1;
+  float* dz1 = bs + P.dz1;
+  float* ax = bs + P.ax;
+  float* w2 = bs + P.w2;
+  const int t = threadIdx.x, T = blockDim.x;
+  const int g = blockIdx.x;
+  const int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
+  const int k0 = a.kptr0[g], K = a.kptr0[g + 1] - k0;
+  const int q0 = a.kptr1[g], Q = a.kptr1[g + 1] - q0;
+  const int E1 = C1 * F, E2 = nb * h2 * h1;
+  float* part = a.partial + (int64_t)g * (E1 + E2);
+  if (n > a.max_n || K > a.max_k) {
+    for (int i = t; i < E1 + E2; i += T) part[i] = 0.f;
+    return;
+  }
+  const int n8 = up8(n), K8 = up8(K);
+  const float invQ = 1.f / (float)max(Q, 1);
+
+  for (int i = t; i < E2; i += T) w2[i] = a.W2[i];
+  // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU; both layouts
+  for (int item = t; item < K8 * C2; item += T) {
+    const int k = item / C2, c = item - k * C2;
+    float v = 0.f;
+    if (k < K) {
+      const int q = __ldg(a.cl1 + k0 + k);
+      if (__ldg(a.arg1 + (int64_t)q * C2 + c) == k0 + k) v = __ldg(a.dR + (int64_t)g * C2 + c) * invQ;
+      if (!(__ldg(a.Z2 + (int64_t)(k0 + k) * C2 + c) > 0.f)) v = 0.f;
+    }
+    dz2[item] = v;
+    dz2T[c * P.k_p + k] = v;
+  }
+  for (int item = t; item < K8 * C1; item += T) {
+    const int k = item / C1;
+    ap[item] = k < K ? a.Zin2[(int64_t)k0 * C1 + item] : 0.f;
+  }
+  __syncthreads();
+  // ---- per-graph dW2 partial [nb][h2][h1] = dZ2_g^T AP_g ; dAP = dZ2_g W2_g
+  for (int gg = 0; gg < nb; ++gg) {
+    tile_gemm(dz2 + gg * h2, C2, ap + gg * h1, C1, h2, h1, K8, [&](int o, int j, float v) {
+      part[E1 + (gg * h2 + o) * h1 + j] = v;
+    });
+    tile_gemm(dz2T + gg * h2 * P.k_p, P.k_p, w2 + gg * h2 * h1, h1, K8, h1, h2, [&](int m, int j, float v) {
+      dap[m * C1 + gg * h1 + j] = v;
+    });
+  }
+  __syncthreads();
+  // ---- dP1 = A1^T dAP  (CSC of the coarsened graph)
+  const int C14 = C1 >> 2;
+  for (int item = t; item < K * C14; item += T) {
+    const int k = item / C14, q4 = item - k * C14;
+    const int s = __ldg(a.cscptr1 + k0 + k), e = __ldg(a.cscptr1 + k0 + k + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = s; p < e; ++p) {
+      const int r = __ldg(a.cscrow1 + p) - k0;
+      const float4 v = *reinterpret_cast<const float4*>(dap + r * C1 + q4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dp1 + k * C1 + q4 * 4) = acc;
+  }
+  __syncthreads();
+  // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU; stage AX
+  for (int item = t; item < n8 * C1; item += T) {
+    const int i = item / C1, c = item - i * C1;
+    float v = 0.f;
+    if (i < n) {
+      const int k = __ldg(a.cl0 + n0 + i);
+      if (__ldg(a.arg0 + (int64_t)k * C1 + c) == n0 + i) v = dp1[(k - k0) * C1 + c];
+      if (!(__ldg(a.Z1 + (int64_t)(n0 + i) * C1 + c) > 0.f)) v = 0.f;
+    }
+    dz1[item] = v;
+  }
+  for (int item = t; item < n8 * F; item += T) {
+    const int i = item / F;
+    float v = i < n ? a.Zin1[(int64_t)n0 * F + item] : 0.f;
+    ax[item] = (v == v) ? v : 0.f;
+  }
+  __syncthreads();
+  // ---- per-graph dW1 partial [C1][F] = dZ1^T AX
+  tile_gemm(dz1, C1, ax, F, C1, F, n8, [&](int c, int f, float v) { part[c * F + f] = v; });
+}
+
+// dW[e] = sum over graphs (ascending) of partial[g][e]; E = C1*F + nb*h2*h1 contiguous outputs
+__global__ void __launch_bounds__(256) ginet_wgrad_reduce_kernel(const float* __restrict__ partial, int B, int E1, int E2,
+                                                                 float* __restrict__ dW1, float* __restrict__ dW2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = E1 + E2;
+  if (e >= E) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int g = 0; g < B; ++g) s += partial[(int64_t)g * E + e];
+  if (e < E1) dW1[e] = s;
+  else dW2[e - E1] = s;
+}
+
+static inline bool fused_shapes_ok(const drgnn_ginet_fused_args& a) {
+  const int C1 = a.nb * a.h1, C2 = a.nb * a.h2;
+  return a.F % 4 == 0 && a.h1 % 4 == 0 && a.h2 % 8 == 0 && C1 % 8 == 0 && C2 % 4 == 0 && a.nb >= 1 && a.max_n > 0 &&
+         a.max_k > 0 && a.max_q > 0;
+}
+
+}  // namespace drgnn
+
+using namespace drgnn;
+
+extern "C" int64_t drgnn_ginet_fused_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
+                                                int32_t max_q, int32_t backward) {
+  if (F <= 0 || h1 <= 0 || h2 <= 0 || nb <= 0 || max_n <= 0 || max_k <= 0 || max_q <= 0) return DRGNN_ERR_INVALID;
+  if (F % 4 || h1 % 4 || h2 % 8 || (nb * h1) % 8) return DRGNN_ERR_UNSUPPORTED;
+  const int C1 = nb * h1, C2 = nb * h2;
+  const int64_t bytes = 4 * (int64_t)(backward ? bwd_plan(F, C1, C2, h1, h2, nb, max_n, max_k).total
+                                                : fwd_plan(F, C1, C2, h1, h2, nb, max_n, max_k, max_q).total);
+  if (bytes > device_info().smem_optin - 2048) return DRGNN_ERR_UNSUPPORTED;
+  return bytes;
+}
+
+static int check_fused(const drgnn_ginet_fused_args* a) {
+  DRGNN_REQUIRE(a != nullptr, "ginet_fused: args is NULL");
+  DRGNN_REQUIRE(a->B >= 0, "ginet_fused: negative batch");
+  DRGNN_REQUIRE(fused_shapes_ok(*a), "ginet_fused: unsupported shape (F %% 4, h1 %% 4, h2 %% 8, nb*h1 %% 8)");
+  DRGNN_REQUIRE(a->node_ptr && a->kptr0 && a->kptr1 && a->status, "ginet_fused: NULL structure pointer");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_ginet_fused_fwd(const drgnn_ginet_fused_args* a, void* stream) {
+  int rc = check_fused(a);
+  if (rc) return rc;
+  DRGNN_REQUIRE(a->x && a->W1 && a->W2 && a->rowptr0 && a->col0 && a->rowptr1 && a->col1 && a->cmptr0 && a->cmem0 &&
+                    a->cmptr1 && a->cmem1 && a->Zin1 && a->Z1 && a->arg0 && a->Zin2 && a->Z2 && a->arg1 && a->R,
+                "ginet_fused_fwd: NULL pointer");
+  if (a->B == 0) return DRGNN_OK;
+  const int64_t smem = drgnn_ginet_fused_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, 0);
+  if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_fused_fwd: a graph of %d nodes does not fit shared memory", a->max_n);
+  static thread_local int64_t configured = -1;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(ginet_graph_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)device_info().smem_optin - 2048));
+    configured = device_info().smem_optin - 2048;
+  }
+  ginet_graph_fwd_kernel<<<a->B, FU_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  DRGNN_CHECK_LAUNCH("ginet_graph_fwd_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stream) {
+  int rc = check_fused(a);
+  if (rc) return rc;
+  DRGNN_REQUIRE(a->W2 && a->cscptr1 && a->cscrow1 && a->cl0 && a->cl1 && a->Zin1 && a->Z1 && a->arg0 && a->Zin2 && a->Z2 &&
+                    a->arg1 && a->dR && a->partial && a->dW1 && a->dW2,
+                "ginet_fused_bwd: NULL pointer");
+  if (a->B == 0) return DRGNN_OK;
+  const int64_t smem = drgnn_ginet_fused_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, 1);
+  if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_fused_bwd: a graph of %d nodes does not fit shared memory", a->max_n);
+  static thread_local int64_t configured = -1;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(ginet_graph_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)device_info().smem_optin - 2048));
+    configured = device_info().smem_optin - 2048;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ginet_graph_bwd_kernel<<<a->B, FU_THREADS, smem, st>>>(*a);
+  DRGNN_CHECK_LAUNCH("ginet_graph_bwd_kernel");
+  const int E1 = a->nb * a->h1 * a->F, E2 = a->nb * a->h2 * a->h1;
+  ginet_wgrad_reduce_kernel<<<(E1 + E2 + 255) / 256, 256, 0, st>>>(a->partial, a->B, E1, E2, a->dW1, a->dW2);
+  DRGNN_CHECK_LAUNCH("ginet_wgrad_reduce_kernel");
+  return DRGNN_OK;
+}

@@ -45,40 +45,6 @@ __host__ __device__ inline HeadSmem head_plan(int C, int Hd, int out, int RB) {
   return p;
 }
 
-template <typename FO>
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb,
-                                          int M, int N, int K, FO out) {
-  const int mt = M >> 3, nt = N >> 2;  // M % 8 == 0, N % 4 == 0 (checked on the host)
-  for (int item = threadIdx.x; item < mt * nt; item += blockDim.x) {
-    const int mg = item / nt, ng = item - mg * nt;
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* ap = At + mg * 8;
-    const float* bp = Bm + ng * 4;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(ap + k * lda);
-      const float4 a1 = *reinterpret_cast<const float4*>(ap + k * lda + 4);
-      const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
-        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
-        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out(mg * 8 + i, ng * 4 + j, acc[i][j]);
-  }
-}
-
 __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const drgnn_head_args a, int RB) {
   extern __shared__ __align__(16) float hs[];
   const int C = a.C, Hd = a.Hd, out = a.out, B = a.B;

@@ -103,6 +103,8 @@ class Batch(Data):
         self._c1_ptr = None        # int32 [B+1] segments of cluster1 (None without clusters)
         self._max_n = None         # host ints: largest graph (nodes / directed edges)
         self._max_e = None
+        self._max_k0 = None        # host ints: most level-0 / level-1 clusters in one graph (None: unknown)
+        self._max_k1 = None
 
     @property
     def num_graphs(self):
@@ -122,6 +124,7 @@ class Batch(Data):
         batch, node_ptr, edge_ptr, c1_ptr = [], [0], [0], [0]
         cum = 0
         has_c1 = 'cluster1' in keys
+        max_k0 = max_k1 = 0
         for i, d in enumerate(data_list):
             n = d.num_nodes
             for k in keys:
@@ -135,6 +138,9 @@ class Batch(Data):
             edge_ptr.append(edge_ptr[-1] + d.num_edges)
             if has_c1:
                 c1_ptr.append(c1_ptr[-1] + d['cluster1'].numel())
+                # exact per-graph cluster counts (shared-memory sizing of the per-graph fused kernels)
+                max_k0 = max(max_k0, int(torch.unique(d['cluster0']).numel()))
+                max_k1 = max(max_k1, int(torch.unique(d['cluster1']).numel()))
         for k in keys:
             items = cols[k]
             if torch.is_tensor(items[0]):
@@ -148,6 +154,7 @@ class Batch(Data):
         out._c1_ptr = torch.tensor(c1_ptr, dtype=torch.int32) if has_c1 else None
         out._max_n = max(b - a for a, b in zip(node_ptr[:-1], node_ptr[1:]))
         out._max_e = max(b - a for a, b in zip(edge_ptr[:-1], edge_ptr[1:]))
+        out._max_k0, out._max_k1 = (max_k0, max_k1) if has_c1 else (None, None)
         return out
 
 
@@ -169,9 +176,13 @@ class PackedBatch(object):
     FLOAT_SECTIONS = ('x', 'edge_attr', 'y')
     INT_SECTIONS = ('edge_index', 'cluster0', 'node_ptr', 'edge_ptr', 'c1_ptr')
 
-    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False):
+    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False, max_k0=None, max_k1=None):
         self.B, self.N, self.E, self.L1, self.F, self.ne = B, N, E, L1, F, ne
         self.max_n, self.max_e = max_n, max_e
+        # per-graph cluster-count bounds, rounded up so that batches of one shape share a layout key
+        # (and therefore one captured CUDA graph) although their exact counts differ
+        self.max_k0 = None if not max_k0 else min(max_n, (max_k0 + 31) // 32 * 32)
+        self.max_k1 = None if not max_k1 else min(max_n, (max_k1 + 15) // 16 * 16)
         self.with_class = with_class
         sizes = dict(x=N * F, edge_attr=E * ne, y=B, edge_index=2 * E, cluster0=N, cluster1=L1, node_ptr=B + 1,
                      edge_ptr=B + 1, c1_ptr=B + 1)
@@ -191,7 +202,7 @@ class PackedBatch(object):
         self.has_y = False
 
     def layout_key(self):
-        return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class)
+        return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class, self.max_k0, self.max_k1)
 
     @property
     def nbytes(self):
@@ -232,7 +243,7 @@ class PackedBatch(object):
         E = batch.edge_index.size(1)
         ne = 0 if ea is None else ea.size(1)
         pb = PackedBatch(batch.num_graphs, N, E, batch.cluster1.numel(), F, ne, batch._max_n, batch._max_e,
-                         with_class=classes is not None)
+                         with_class=classes is not None, max_k0=batch._max_k0, max_k1=batch._max_k1)
         pin = torch.cuda.is_available() if pin is None else pin
         pb.buf = torch.zeros(pb.numel, dtype=torch.float32, pin_memory=bool(pin))
         v = pb.views(pb.buf)

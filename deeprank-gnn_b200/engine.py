@@ -160,12 +160,14 @@ class Workspace(object):
                    ops.linear_wgrad_work_floats(B, s.C2, s.Hd, 1),
                    ops.linear_wgrad_work_floats(B, s.Hd, s.out, 1))
         self.wwork = z(need)
+        # per-graph weight-gradient partials of the fused per-graph backward (GINet)
+        self.partial = z(B, s.C1 * s.F + s.nb * s.h2 * s.h1) if s.kind == 'ginet' else None
 
 
 class DeviceBatch(object):
     """The tensors of one mini-batch the engine consumes, resident on the device."""
     __slots__ = ('x', 'edge_index', 'edge_attr', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr', 'y',
-                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'mol', 'key', 'sslot')
+                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'max_k0', 'max_k1', 'mol', 'key', 'sslot')
 
     @staticmethod
     def from_batch(batch, device, classes=None):
@@ -197,6 +199,7 @@ class DeviceBatch(object):
             d.y_class = mv(torch.tensor([c2i[int(t)] for t in y.reshape(-1).tolist()], dtype=I64))
         d.B, d.N, d.E, d.L1 = batch.num_graphs, d.x.size(0), d.edge_index.size(1), d.cluster1.numel()
         d.max_n, d.max_e = int(batch._max_n), int(batch._max_e)
+        d.max_k0, d.max_k1 = getattr(batch, '_max_k0', None), getattr(batch, '_max_k1', None)
         d.mol = getattr(batch, 'mol', None)
         d.key = None
         d.sslot = 0
@@ -212,6 +215,7 @@ class DeviceBatch(object):
         d.edge_index, d.cluster0, d.cluster1 = v['edge_index'], v['cluster0'], v['cluster1']
         d.node_ptr, d.edge_ptr, d.c1_ptr = v['node_ptr'], v['edge_ptr'], v['c1_ptr']
         d.B, d.N, d.E, d.L1, d.max_n, d.max_e = pb.B, pb.N, pb.E, pb.L1, pb.max_n, pb.max_e
+        d.max_k0, d.max_k1 = pb.max_k0, pb.max_k1
         d.mol = pb.mol
         d.key = pb.layout_key()
         d.sslot = 0
@@ -222,7 +226,7 @@ class DeviceBatch(object):
 class Engine(object):
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=None, graph=False, tiled=True, fused_head=True, process_group=None, seed=None):
+                 dropout=None, graph=False, tiled=True, fused_head=True, fused_graph=True, process_group=None, seed=None):
         self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -254,6 +258,9 @@ class Engine(object):
         from . import _lib
         self._sms = int(_lib.load().drgnn_device_sms())
         self.fused_head = bool(fused_head)
+        self.fused_graph = bool(fused_graph)     # per-graph fused GINet forward / backward kernels
+        self._fused_fit = {}
+        self._graph_done = False
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
         self.launches_per_step = 0
@@ -364,6 +371,17 @@ class Engine(object):
         self._last_struct = st
         return st
 
+    def _use_fused_graph(self, d):
+        s = self.spec
+        if not (self.fused_graph and s.kind == 'ginet' and d.max_k0 and d.max_k1 and d.x.size(1) == s.F):
+            return False
+        key = (d.max_n, d.max_k0, d.max_k1)
+        fit = self._fused_fit.get(key)
+        if fit is None:
+            fit = ops.ginet_fused_fits(s.F, s.h1, s.h2, s.nb, d.max_n, d.max_k0, d.max_k1)
+            self._fused_fit[key] = fit
+        return fit
+
     def _conv_aggregate(self, level, src, rowptr, col, Zin, n_rows, n_rows_dev, ew, s_out, post_out, tiles):
         s = self.spec
         cin = s.F if level == 0 else s.h1
@@ -388,6 +406,18 @@ class Engine(object):
         K0d, K1d = st.K0_dev, st.K1_dev
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
+        self._graph_done = False
+        if self._use_fused_graph(d):
+            # ONE launch: conv1 -> pool -> conv2 -> pool -> read-out, one CTA per graph (csrc/fused.cu)
+            self._fa = ops.ginet_fused_args(st, d.x, flat('conv1.fc.weight', s.C1 * s.F),
+                                            flat('conv2.fc.weight', s.nb * s.h2 * s.h1), ws.Zin1[:N], ws.Z1[:N],
+                                            ws.arg0, ws.Zin2, ws.Z2, ws.arg1, ws.R[:B], d.node_ptr, B, s.F, s.h1, s.h2,
+                                            s.nb, d.max_n, d.max_k0, d.max_k1, dR=ws.dR[:B], partial=ws.partial,
+                                            dW1=self.grads[P.offset('conv1.fc.weight'):P.offset('conv1.fc.weight') + s.C1 * s.F],
+                                            dW2=self.grads[P.offset('conv2.fc.weight'):P.offset('conv2.fc.weight') + s.nb * s.h2 * s.h1])
+            ops.ginet_fused_fwd(self._fa)
+            self._graph_done = True
+            return self._heads(d, keep_mask, loss_inv)
         # per-graph TMA pipeline for batches that fill the machine (>= 2 graphs per SM); small batches use
         # the L1-resident row kernel, whose launch latency is lower (3.0 us vs 4.1 us at B = 64)
         tiled = self.tiled and (d.B >= 2 * self._sms or self.tiled == 'force') and 8 * (d.max_n * s.F + d.max_n + 2 * d.max_e + 32) <= 200 * 1024
@@ -417,6 +447,11 @@ class Engine(object):
         # level-1 max-pool (max_pool_x) and graph read-out (scatter_mean by batch)
         ops.maxpool_fwd(ws.Z2[:L1], st.cmptr1, st.cmem1, ws.P2[:L1], ws.arg1[:L1], n_clusters_dev=K1d)
         ops.segment_mean_fwd(ws.P2[:L1], st.kptr1[:B + 1], ws.R[:B])
+        return self._heads(d, keep_mask, loss_inv)
+
+    def _heads(self, d, keep_mask, loss_inv):
+        s, ws, P, B = self.spec, self.ws, self.params, d.B
+        pv = lambda name: P.view(P.data, name)
         # heads
         drop = self.training and s.dropout > 0
         scale = 1.0 / (1.0 - s.dropout) if drop else 1.0
@@ -468,6 +503,10 @@ class Engine(object):
                        mask_scale=scale)
             ops.linear_wgrad(ws.R[:B], ws.dH[:B], s.C2, s.Hd, gv('fc1.weight'), gv('fc1.bias'), work=ws.wwork)
             ops.linear(ws.dH[:B], pv('fc1.weight'), s.Hd, s.C2, ws.dR[:B], w_layout=1)
+        if self._graph_done:
+            # ONE launch (+ the partial sum): everything from dR down to dW1 / dW2, one CTA per graph
+            ops.ginet_fused_bwd(self._fa)
+            return
         # read-out and level-1 pool
         ops.segment_mean_bwd(ws.dR[:B], st.kptr1[:B + 1], ws.dP2[:L1])
         ops.maxpool_bwd(ws.dP2[:L1], ws.arg1[:L1], st.cl1, ws.dZ2[:L1], relu_out=ws.Z2[:L1], n_nodes_dev=K0d)

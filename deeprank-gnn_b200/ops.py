@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AggregateArgs, DrgnnError, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
+from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
                    require_cuda, stream_ptr)
 
 I32, I64, F32 = torch.int32, torch.int64, torch.float32
@@ -390,6 +390,43 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0
             raise DrgnnError('adam_flat works on contiguous float32 buffers')
     call('drgnn_adam_flat', ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_dev), param.numel(),
          float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), stream_ptr())
+
+
+def ginet_fused_fits(F, h1, h2, nb, max_n, max_k, max_q):
+    """True if one graph of these bounds fits the shared memory of the fused forward AND backward."""
+    f = _lib.load().drgnn_ginet_fused_smem_bytes
+    a = [int(v) for v in (F, h1, h2, nb, max_n, max_k, max_q)]
+    return int(f(*a, 0)) >= 0 and int(f(*a, 1)) >= 0
+
+
+def ginet_fused_args(st, x, W1, W2, Zin1, Z1, arg0, Zin2, Z2, arg1, R, node_ptr, B, F, h1, h2, nb, max_n, max_k, max_q,
+                     dR=None, partial=None, dW1=None, dW2=None):
+    """Build the argument block of ``drgnn_ginet_fused_{fwd,bwd}`` from a ``Structure``."""
+    require_cuda(x, W1, W2, Zin1, Z1, arg0, Zin2, Z2, arg1, R, node_ptr, dR, partial, dW1, dW2)
+    for t_, n_ in ((x, 'x'), (Zin1, 'Zin1'), (Z1, 'Z1'), (Zin2, 'Zin2'), (Z2, 'Z2'), (R, 'R')):
+        if not t_.is_contiguous() or t_.dtype != F32:
+            raise DrgnnError('%s must be a contiguous float32 tensor' % n_)
+    a = GinetFusedArgs()
+    a.B, a.F, a.h1, a.h2, a.nb = int(B), int(F), int(h1), int(h2), int(nb)
+    a.max_n, a.max_k, a.max_q = int(max_n), int(max_k), int(max_q)
+    a.node_ptr = ptr(node_ptr)
+    a.rowptr0, a.col0, a.rowptr1, a.col1 = ptr(st.rowptr0), ptr(st.col0), ptr(st.rowptr1), ptr(st.col1)
+    a.cscptr1, a.cscrow1 = ptr(st.cscptr1), ptr(st.cscrow1)
+    a.cmptr0, a.cmem0, a.cl0, a.kptr0 = ptr(st.cmptr0), ptr(st.cmem0), ptr(st.cl0), ptr(st.kptr0)
+    a.cmptr1, a.cmem1, a.cl1, a.kptr1 = ptr(st.cmptr1), ptr(st.cmem1), ptr(st.cl1), ptr(st.kptr1)
+    a.status = ptr(st.status)
+    a.W1, a.W2, a.x = ptr(W1), ptr(W2), ptr(x)
+    a.Zin1, a.Z1, a.arg0, a.Zin2, a.Z2, a.arg1, a.R = ptr(Zin1), ptr(Z1), ptr(arg0), ptr(Zin2), ptr(Z2), ptr(arg1), ptr(R)
+    a.dR, a.partial, a.dW1, a.dW2 = ptr(dR), ptr(partial), ptr(dW1), ptr(dW2)
+    return a
+
+
+def ginet_fused_fwd(a):
+    call('drgnn_ginet_fused_fwd', C.byref(a), stream_ptr())
+
+
+def ginet_fused_bwd(a):
+    call('drgnn_ginet_fused_bwd', C.byref(a), stream_ptr())
 
 
 TASK_NONE, TASK_MSE, TASK_MSE_SIGMOID, TASK_CE = 0, 1, 2, 3

@@ -38,6 +38,7 @@ extern "C" {
 #define DRGNN_ST_CLUSTER1_LENGTH 4      /* len(cluster1 of graph g) != n_unique(cluster0 of g)   */
 #define DRGNN_ST_CLUSTER_ORDER 8        /* global cluster ids are not increasing with graph id   */
 #define DRGNN_ST_NEGATIVE_ID 16         /* negative cluster id                                   */
+#define DRGNN_ST_FUSED_BOUNDS 64        /* a graph exceeds the max_n / max_k / max_q given to the fused kernels */
 
 const char* drgnn_last_error(void);
 int drgnn_version(void);
@@ -291,6 +292,41 @@ typedef struct drgnn_head_args {
 } drgnn_head_args;
 int64_t drgnn_head_smem_bytes(int32_t C, int32_t Hd, int32_t out);   /* <0: does not fit one CTA */
 int drgnn_head(const drgnn_head_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 8. Per-graph fused GINet (ginet.py:99-134 and its autograd backward): ONE CTA per graph keeps
+ *    every intermediate of the graph in shared memory.
+ *      fwd: x -> AX = A x -> Z1 = relu(AX W1^T) -> cluster max -> AP = A1 P1 -> Z2 = relu(AP W2^T)
+ *           -> level-1 cluster max -> R = per-graph mean           (both branches: W1 [nb*h1, F],
+ *           W2 [nb][h2][h1]); stores Zin1 = AX [N,F], Z1 [N,nb*h1], arg0, Zin2 = AP, Z2, arg1, R.
+ *      bwd: dR [B, nb*h2] -> dW1 [nb*h1, F], dW2 [nb][h2][h1] (per-graph partials in `partial`
+ *           [B, nb*h1*F + nb*h2*h1], summed in graph order: deterministic).
+ *    Structure arrays are the outputs of drgnn_structure_build.  max_n / max_k / max_q: host-known
+ *    upper bounds of nodes, level-0 clusters and level-1 clusters of ONE graph (shared-memory
+ *    sizing; a violation sets DRGNN_ST_FUSED_BOUNDS in status[0]).  Needs F % 4 == 0, h1 % 4 == 0,
+ *    h2 % 8 == 0, (nb*h1) % 8 == 0.
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_ginet_fused_args {
+  int32_t B; int32_t F; int32_t h1; int32_t h2; int32_t nb;
+  int32_t max_n; int32_t max_k; int32_t max_q;
+  const int32_t* node_ptr;
+  const int32_t* rowptr0; const int32_t* col0;
+  const int32_t* rowptr1; const int32_t* col1;
+  const int32_t* cscptr1; const int32_t* cscrow1;
+  const int32_t* cmptr0; const int32_t* cmem0; const int32_t* cl0; const int32_t* kptr0;
+  const int32_t* cmptr1; const int32_t* cmem1; const int32_t* cl1; const int32_t* kptr1;
+  int32_t* status;
+  const float* W1; const float* W2;
+  const float* x;
+  float* Zin1; float* Z1; int32_t* arg0;
+  float* Zin2; float* Z2; int32_t* arg1;
+  float* R;
+  const float* dR; float* partial; float* dW1; float* dW2;
+} drgnn_ginet_fused_args;
+int64_t drgnn_ginet_fused_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
+                                     int32_t max_q, int32_t backward);   /* <0: does not fit one CTA */
+int drgnn_ginet_fused_fwd(const drgnn_ginet_fused_args* a, void* stream);
+int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stream);
 
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,
