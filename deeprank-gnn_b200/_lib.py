@@ -111,6 +111,24 @@ class GinetFusedArgs(C.Structure):
     ]
 
 
+class GinetStepArgs(C.Structure):
+    _fields_ = [
+        ('g', GinetFusedArgs),
+        ('fc1_w', VP), ('fc1_b', VP), ('fc2_w', VP), ('fc2_b', VP),
+        ('Hd', C.c_int32), ('out', C.c_int32),
+        ('keep', VP), ('keep_scale', C.c_float),
+        ('y', VP), ('y_class', VP), ('class_w', VP),
+        ('task', C.c_int32), ('inv_norm', C.c_float),
+        ('pred', VP), ('loss', VP),
+        ('partial', VP), ('partial_ld', C.c_int64),
+        ('grads', VP), ('n_params', C.c_int32),
+        ('off_w1', C.c_int32), ('off_w2', C.c_int32), ('off_fc1w', C.c_int32), ('off_fc1b', C.c_int32),
+        ('off_fc2w', C.c_int32), ('off_fc2b', C.c_int32),
+        ('forward_only', C.c_int32),
+        ('head_off', C.c_int32),
+    ]
+
+
 class HeadArgs(C.Structure):
     _fields_ = [
         ('R', VP), ('ldr', C.c_int32),
@@ -151,6 +169,8 @@ _SIGNATURES = {
     'drgnn_ginet_fused_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     'drgnn_ginet_fused_fwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
     'drgnn_ginet_fused_bwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
+    'drgnn_ginet_step_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    'drgnn_ginet_step': (C.c_int, [C.POINTER(GinetStepArgs), VP]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
@@ -163,7 +183,8 @@ EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 _lib = None
 launch_count = 0           # C-ABI compute calls made by this process
 kernel_count = 0           # CUDA kernels those calls launched (bench: gpu_launches)
-KERNELS_PER_CALL = {'drgnn_structure_build': 2, 'drgnn_cluster_offset': 2, 'drgnn_ginet_fused_bwd': 2}   # lower bounds for the others
+KERNELS_PER_CALL = {'drgnn_structure_build': 2, 'drgnn_cluster_offset': 2, 'drgnn_ginet_fused_bwd': 2, 'drgnn_ginet_step': 2,
+                    'drgnn_adam_flat': 2}   # lower bounds for the others
 
 
 class DrgnnError(RuntimeError):

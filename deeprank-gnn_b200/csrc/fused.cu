@@ -71,8 +71,9 @@ __host__ __device__ inline BwdSmem bwd_plan(int F, int C1, int C2, int h1, int h
   return p;
 }
 
-__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_fwd_kernel(const drgnn_ginet_fused_args a) {
-  extern __shared__ __align__(16) float fs[];
+// Forward of graph g out of the shared-memory workspace `fs`.  Returns false (after flagging) if the
+// graph exceeds the host bounds.  `rrow` (shared, C2 floats) receives the graph's read-out row.
+__device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, float* fs, int g, float* rrow) {
   const int F = a.F, h1 = a.h1, h2 = a.h2, nb = a.nb;
   const int C1 = nb * h1, C2 = nb * h2;
   const FwdSmem P = fwd_plan(F, C1, C2, h1, h2, nb, a.max_n, a.max_k, a.max_q);
@@ -86,13 +87,12 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_fwd_kernel(const dr
   float* z2 = fs + P.z2;
   float* p2 = fs + P.p2;
   const int t = threadIdx.x, T = blockDim.x;
-  const int g = blockIdx.x;
   const int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
   const int k0 = a.kptr0[g], K = a.kptr0[g + 1] - k0;
   const int q0 = a.kptr1[g], Q = a.kptr1[g + 1] - q0;
   if (n > a.max_n || K > a.max_k || Q > a.max_q) {  // host bounds violated: flag and leave (checked by validate())
     if (t == 0) atomicOr(a.status, 64);
-    return;
+    return false;
   }
   const int n8 = up8(n), K8 = up8(K);
   const int F4 = F >> 2, C14 = C1 >> 2, C24 = C2 >> 2;
@@ -215,12 +215,22 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_fwd_kernel(const dr
   for (int c = t; c < C2; c += T) {
     float acc = 0.f;
     for (int q = 0; q < Q; ++q) acc += p2[q * C2 + c];
-    a.R[(int64_t)g * C2 + c] = acc * (1.f / (float)max(Q, 1));
+    acc *= 1.f / (float)max(Q, 1);
+    a.R[(int64_t)g * C2 + c] = acc;
+    if (rrow) rrow[c] = acc;
   }
+  return true;
 }
 
-__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const drgnn_ginet_fused_args a) {
-  extern __shared__ __align__(16) float bs[];
+__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_fwd_kernel(const drgnn_ginet_fused_args a) {
+  extern __shared__ __align__(16) float fs[];
+  graph_fwd_body(a, fs, blockIdx.x, nullptr);
+}
+
+// Backward of graph g: dR row (global or shared) -> per-graph partials of dW1 (`part1`, [C1][F]) and dW2
+// (`part2`, [nb][h2][h1]).
+__device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, float* bs, int g, const float* dRrow,
+                                               float* part1, float* part2) {
   const int F = a.F, h1 = a.h1, h2 = a.h2, nb = a.nb;
   const int C1 = nb * h1, C2 = nb * h2;
   const BwdSmem P = bwd_plan(F, C1, C2, h1, h2, nb, a.max_n, a.max_k);
@@ -233,14 +243,13 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
   float* ax = bs + P.ax;
   float* w2 = bs + P.w2;
   const int t = threadIdx.x, T = blockDim.x;
-  const int g = blockIdx.x;
   const int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
   const int k0 = a.kptr0[g], K = a.kptr0[g + 1] - k0;
   const int q0 = a.kptr1[g], Q = a.kptr1[g + 1] - q0;
   const int E1 = C1 * F, E2 = nb * h2 * h1;
-  float* part = a.partial + (int64_t)g * (E1 + E2);
   if (n > a.max_n || K > a.max_k) {
-    for (int i = t; i < E1 + E2; i += T) part[i] = 0.f;
+    for (int i = t; i < E1; i += T) part1[i] = 0.f;
+    for (int i = t; i < E2; i += T) part2[i] = 0.f;
     return;
   }
   const int n8 = up8(n), K8 = up8(K);
@@ -253,8 +262,8 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
     float v = 0.f;
     if (k < K) {
       const int q = __ldg(a.cl1 + k0 + k);
-      if (__ldg(a.arg1 + (int64_t)q * C2 + c) == k0 + k) v = __ldg(a.dR + (int64_t)g * C2 + c) * invQ;
-      if (!(__ldg(a.Z2 + (int64_t)(k0 + k) * C2 + c) > 0.f)) v = 0.f;
+      if (a.arg1[(int64_t)q * C2 + c] == k0 + k) v = dRrow[c] * invQ;   // plain loads: written by this CTA
+      if (!(a.Z2[(int64_t)(k0 + k) * C2 + c] > 0.f)) v = 0.f;
     }
     dz2[item] = v;
     dz2T[c * P.k_p + k] = v;
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
   // ---- per-graph dW2 partial [nb][h2][h1] = dZ2_g^T AP_g ; dAP = dZ2_g W2_g
   for (int gg = 0; gg < nb; ++gg) {
     tile_gemm(dz2 + gg * h2, C2, ap + gg * h1, C1, h2, h1, K8, [&](int o, int j, float v) {
-      part[E1 + (gg * h2 + o) * h1 + j] = v;
+      part2[(gg * h2 + o) * h1 + j] = v;
     });
     tile_gemm(dz2T + gg * h2 * P.k_p, P.k_p, w2 + gg * h2 * h1, h1, K8, h1, h2, [&](int m, int j, float v) {
       dap[m * C1 + gg * h1 + j] = v;
@@ -294,8 +303,8 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
     float v = 0.f;
     if (i < n) {
       const int k = __ldg(a.cl0 + n0 + i);
-      if (__ldg(a.arg0 + (int64_t)k * C1 + c) == n0 + i) v = dp1[(k - k0) * C1 + c];
-      if (!(__ldg(a.Z1 + (int64_t)(n0 + i) * C1 + c) > 0.f)) v = 0.f;
+      if (a.arg0[(int64_t)k * C1 + c] == n0 + i) v = dp1[(k - k0) * C1 + c];
+      if (!(a.Z1[(int64_t)(n0 + i) * C1 + c] > 0.f)) v = 0.f;
     }
     dz1[item] = v;
   }
@@ -306,7 +315,139 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
   }
   __syncthreads();
   // ---- per-graph dW1 partial [C1][F] = dZ1^T AX
-  tile_gemm(dz1, C1, ax, F, C1, F, n8, [&](int c, int f, float v) { part[c * F + f] = v; });
+  tile_gemm(dz1, C1, ax, F, C1, F, n8, [&](int c, int f, float v) { part1[c * F + f] = v; });
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const drgnn_ginet_fused_args a) {
+  extern __shared__ __align__(16) float bs[];
+  const int g = blockIdx.x;
+  const int E1 = a.nb * a.h1 * a.F, E2 = a.nb * a.h2 * a.h1;
+  float* part = a.partial + (int64_t)g * (E1 + E2);
+  graph_bwd_body(a, bs, g, a.dR + (int64_t)g * a.nb * a.h2, part, part + E1);
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole training step of one graph in ONE launch: forward, the network head on the graph's own
+// read-out row (fc1 / ReLU / dropout / fc2 are row-wise, the loss is a sum of per-graph terms),
+// and the backward down to per-graph gradient partials of EVERY parameter, laid out like the flat
+// gradient buffer.  ginet_step_reduce_kernel then sums the partial rows in graph order.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const drgnn_ginet_step_args s) {
+  extern __shared__ __align__(16) float ws[];
+  const drgnn_ginet_fused_args& a = s.g;
+  const int g = blockIdx.x;
+  const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, nwarps = T >> 5;
+  const int C2 = a.nb * a.h2, Hd = s.Hd, out = s.out;
+  // head scratch lives behind the graph workspace
+  float* rrow = ws + s.head_off;         // [C2]  read-out row R[g]
+  float* hrow = rrow + C2;               // [Hd]  hidden activation (after ReLU / dropout)
+  float* dhrow = hrow + Hd;              // [Hd]
+  float* drrow = dhrow + Hd;             // [C2]  dLoss / dR[g]
+  float* prow = drrow + C2;              // [out] prediction, then dLoss / dpred
+  float* part = s.partial + (int64_t)g * s.partial_ld;
+  const bool ok = graph_fwd_body(a, ws, g, rrow);
+  __syncthreads();
+  if (!ok) {
+    if (!s.forward_only)
+      for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
+    return;
+  }
+  // ---- fc1: warp per hidden unit, lanes over the read-out channels
+  for (int j = warp; j < Hd; j += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < C2; c += 32) acc = fmaf(rrow[c], __ldg(s.fc1_w + (int64_t)j * C2 + c), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += s.fc1_b ? __ldg(s.fc1_b + j) : 0.f;
+      acc = acc < 0.f ? 0.f : acc;
+      if (s.keep) acc = s.keep[(int64_t)g * Hd + j] > 0.f ? acc * s.keep_scale : 0.f;
+      hrow[j] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- fc2: warp per output
+  for (int o = warp; o < out; o += nwarps) {
+    float acc = 0.f;
+    for (int j = lane; j < Hd; j += 32) acc = fmaf(hrow[j], __ldg(s.fc2_w + (int64_t)o * Hd + j), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += s.fc2_b ? __ldg(s.fc2_b + o) : 0.f;
+      prow[o] = acc;
+      s.pred[(int64_t)g * out + o] = acc;
+    }
+  }
+  __syncthreads();
+  if (s.forward_only || s.task == 0) return;
+  // ---- loss term of this graph and dLoss/dpred (one thread)
+  if (t == 0) {
+    float lg = 0.f;
+    if (s.task == 3) {
+      float mx = prow[0];
+      for (int c = 1; c < out; ++c) mx = fmaxf(mx, prow[c]);
+      float se = 0.f;
+      for (int c = 0; c < out; ++c) se += expf(prow[c] - mx);
+      const float lse = mx + logf(se);
+      const int tc = (int)s.y_class[g];
+      const float w = s.class_w ? s.class_w[tc] : 1.f;
+      lg = w * (lse - prow[tc]);
+      for (int c = 0; c < out; ++c) prow[c] = w * (expf(prow[c] - lse) - (c == tc ? 1.f : 0.f)) * s.inv_norm;
+    } else {
+      for (int c = 0; c < out; ++c) {
+        float p = prow[c], dp = 1.f;
+        if (s.task == 2) {
+          p = 1.f / (1.f + expf(-p));
+          dp = p * (1.f - p);
+        }
+        const float d = p - s.y[(int64_t)g * out + c];
+        lg += d * d;
+        prow[c] = 2.f * d * s.inv_norm * dp;
+      }
+    }
+    part[s.n_params] = lg * s.inv_norm;   // summed into the loss by the reduce kernel
+  }
+  __syncthreads();
+  // ---- head backward: fc2 partials, dh, fc1 partials, dR row
+  for (int i = t; i < out * Hd; i += T) part[s.off_fc2w + i] = prow[i / Hd] * hrow[i % Hd];
+  for (int o = t; o < out; o += T) part[s.off_fc2b + o] = prow[o];
+  for (int j = t; j < Hd; j += T) {
+    float acc = 0.f;
+    for (int o = 0; o < out; ++o) acc = fmaf(prow[o], __ldg(s.fc2_w + (int64_t)o * Hd + j), acc);
+    acc = hrow[j] > 0.f ? acc * s.keep_scale : 0.f;
+    dhrow[j] = acc;
+    part[s.off_fc1b + j] = acc;
+  }
+  __syncthreads();
+  for (int i = t; i < Hd * C2; i += T) part[s.off_fc1w + i] = dhrow[i / C2] * rrow[i % C2];
+  // dR[c] = sum_j dh[j] W1[j][c]: warps split the hidden units, lanes over channels, partial sums in shared memory
+  {
+    float* red = ws;  // the graph workspace is free again: [nwarps][C2]
+    for (int c = lane; c < C2; c += 32) {
+      float acc = 0.f;
+      for (int j = warp; j < Hd; j += nwarps) acc = fmaf(dhrow[j], __ldg(s.fc1_w + (int64_t)j * C2 + c), acc);
+      red[warp * C2 + c] = acc;
+    }
+    __syncthreads();
+    for (int c = t; c < C2; c += T) {
+      float acc = 0.f;
+      for (int w = 0; w < nwarps; ++w) acc += red[w * C2 + c];
+      drrow[c] = acc;
+    }
+  }
+  __syncthreads();
+  graph_bwd_body(a, ws, g, drrow, part + s.off_w1, part + s.off_w2);
+}
+
+// grads[e] = sum over graphs (ascending) of partial[g][e]; the slot behind the parameters is the loss
+__global__ void __launch_bounds__(256) ginet_step_reduce_kernel(const float* __restrict__ partial, int64_t ld, int B,
+                                                                int n_params, float* __restrict__ grads,
+                                                                float* __restrict__ loss) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > n_params) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int g = 0; g < B; ++g) s += partial[(int64_t)g * ld + e];
+  if (e < n_params) grads[e] = s;
+  else if (loss) loss[0] = s;
 }
 
 // dW[e] = sum over graphs (ascending) of partial[g][e]; E = C1*F + nb*h2*h1 contiguous outputs
@@ -392,5 +533,59 @@ extern "C" int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stre
   const int E1 = a->nb * a->h1 * a->F, E2 = a->nb * a->h2 * a->h1;
   ginet_wgrad_reduce_kernel<<<(E1 + E2 + 255) / 256, 256, 0, st>>>(a->partial, a->B, E1, E2, a->dW1, a->dW2);
   DRGNN_CHECK_LAUNCH("ginet_wgrad_reduce_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
+                                               int32_t max_q, int32_t Hd, int32_t out) {
+  const int64_t f = drgnn_ginet_fused_smem_bytes(F, h1, h2, nb, max_n, max_k, max_q, 0);
+  const int64_t b = drgnn_ginet_fused_smem_bytes(F, h1, h2, nb, max_n, max_k, max_q, 1);
+  if (f < 0) return f;
+  if (b < 0) return b;
+  if (Hd <= 0 || out <= 0) return DRGNN_ERR_INVALID;
+  const int64_t head = 4 * (int64_t)(2 * nb * h2 + 2 * Hd + out + 8);
+  const int64_t red = 4 * (int64_t)(FU_THREADS / 32) * nb * h2;
+  int64_t bytes = (f > b ? f : b);
+  if (bytes < red) bytes = red;
+  bytes = ((bytes + 15) & ~(int64_t)15) + head;
+  if (bytes > device_info().smem_optin - 2048) return DRGNN_ERR_UNSUPPORTED;
+  return bytes;
+}
+
+extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
+  DRGNN_REQUIRE(s != nullptr, "ginet_step: args is NULL");
+  const drgnn_ginet_fused_args* a = &s->g;
+  int rc = check_fused(a);
+  if (rc) return rc;
+  DRGNN_REQUIRE(a->x && a->W1 && a->W2 && a->rowptr0 && a->col0 && a->rowptr1 && a->col1 && a->cmptr0 && a->cmem0 &&
+                    a->cmptr1 && a->cmem1 && a->cscptr1 && a->cscrow1 && a->cl0 && a->cl1 && a->Zin1 && a->Z1 && a->arg0 &&
+                    a->Zin2 && a->Z2 && a->arg1 && a->R,
+                "ginet_step: NULL graph pointer");
+  DRGNN_REQUIRE(s->fc1_w && s->fc2_w && s->pred && s->Hd > 0 && s->out > 0, "ginet_step: NULL / bad head arguments");
+  DRGNN_REQUIRE(s->task >= 0 && s->task <= 3, "ginet_step: bad task %d", s->task);
+  if (!s->forward_only && s->task != 0) {
+    DRGNN_REQUIRE(s->partial && s->grads && s->n_params > 0 && s->partial_ld > s->n_params, "ginet_step: bad gradient buffers");
+    DRGNN_REQUIRE(s->task == 3 ? (s->y_class != nullptr) : (s->y != nullptr), "ginet_step: missing targets");
+  }
+  if (a->B == 0) return DRGNN_OK;
+  const int64_t smem = drgnn_ginet_step_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, s->Hd, s->out);
+  if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: a graph of %d nodes does not fit shared memory", a->max_n);
+  static thread_local int64_t configured = -1;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(ginet_graph_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)device_info().smem_optin - 2048));
+    configured = device_info().smem_optin - 2048;
+  }
+  drgnn_ginet_step_args k = *s;
+  const int64_t head = 4 * (int64_t)(2 * a->nb * a->h2 + 2 * s->Hd + s->out + 8);
+  k.head_off = (int32_t)((smem - head) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  ginet_graph_step_kernel<<<a->B, FU_THREADS, smem, st>>>(k);
+  DRGNN_CHECK_LAUNCH("ginet_graph_step_kernel");
+  if (!s->forward_only && s->task != 0) {
+    ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(s->partial, s->partial_ld, a->B, s->n_params,
+                                                                           s->grads, s->loss);
+    DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
+  }
   return DRGNN_OK;
 }

@@ -127,7 +127,7 @@ class FlatParams(object):
 class Workspace(object):
     """Activation / gradient buffers for batches up to (B, N, E) - allocated once, reused."""
 
-    def __init__(self, spec, B, N, E, device):
+    def __init__(self, spec, B, N, E, device, n_params=0):
         s = spec
         self.B, self.N, self.E = B, N, E
         z = lambda *shape: torch.zeros(*shape, dtype=F32, device=device)
@@ -162,6 +162,8 @@ class Workspace(object):
         self.wwork = z(need)
         # per-graph weight-gradient partials of the fused per-graph backward (GINet)
         self.partial = z(B, s.C1 * s.F + s.nb * s.h2 * s.h1) if s.kind == 'ginet' else None
+        # per-graph rows shaped like the flat gradient buffer (+ the loss slot) for the whole-step kernel
+        self.partial_full = z(B, n_params + 4) if s.kind == 'ginet' else None
 
 
 class DeviceBatch(object):
@@ -261,6 +263,7 @@ class Engine(object):
         self.fused_graph = bool(fused_graph)     # per-graph fused GINet forward / backward kernels
         self._fused_fit = {}
         self._graph_done = False
+        self._all_done = False
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
         self.launches_per_step = 0
@@ -346,7 +349,7 @@ class Engine(object):
             nb = max(B, ws.B if ws else 0)
             nn_ = max(N, ws.N if ws else 0)
             ne_ = max(E, ws.E if ws else 0)
-            self.ws = Workspace(self.spec, nb, nn_, ne_, self.device)
+            self.ws = Workspace(self.spec, nb, nn_, ne_, self.device, self.params.numel)
             ne_attr = 1 if self.spec.kind == 'sgat' else 0
             self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(2)]
             self._graphs.clear()
@@ -406,7 +409,7 @@ class Engine(object):
         K0d, K1d = st.K0_dev, st.K1_dev
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
-        self._graph_done = False
+        self._graph_done = self._all_done = False
         if self._use_fused_graph(d):
             # ONE launch: conv1 -> pool -> conv2 -> pool -> read-out, one CTA per graph (csrc/fused.cu)
             self._fa = ops.ginet_fused_args(st, d.x, flat('conv1.fc.weight', s.C1 * s.F),
@@ -415,6 +418,40 @@ class Engine(object):
                                             s.nb, d.max_n, d.max_k0, d.max_k1, dR=ws.dR[:B], partial=ws.partial,
                                             dW1=self.grads[P.offset('conv1.fc.weight'):P.offset('conv1.fc.weight') + s.C1 * s.F],
                                             dW2=self.grads[P.offset('conv2.fc.weight'):P.offset('conv2.fc.weight') + s.nb * s.h2 * s.h1])
+            key = (d.max_n, d.max_k0, d.max_k1, 'step')
+            whole = self._fused_fit.get(key)
+            if whole is None:
+                whole = self.fused_head and ops.ginet_step_fits(s.F, s.h1, s.h2, s.nb, d.max_n, d.max_k0, d.max_k1,
+                                                                  s.Hd, s.out)
+                self._fused_fit[key] = whole
+            if whole:
+                # the whole step of every graph in ONE launch: forward, head, loss, backward (+ one reduction)
+                drop = self.training and s.dropout > 0
+                if drop:
+                    if keep_mask is not None:
+                        ws.keep[:B].copy_(keep_mask.to(self.device, F32))
+                    else:
+                        ws.keep[:B].bernoulli_(1.0 - s.dropout)
+                train_step = loss_inv is not None
+                task = ops.TASK_NONE
+                if train_step:
+                    task = ops.TASK_CE if self.task == 'class' else \
+                        (ops.TASK_MSE_SIGMOID if self.transform_sigmoid else ops.TASK_MSE)
+                    if self.task == 'class' and d.y_class is None:
+                        raise DrgnnError('classification needs class-index targets (pass `classes` when building the batch)')
+                    if self.task == 'reg' and d.y is None:
+                        raise DrgnnError('the batch has no target')
+                offs = [P.offset(nm) for nm in ('conv1.fc.weight', 'conv2.fc.weight', 'fc1.weight', 'fc1.bias',
+                                                'fc2.weight', 'fc2.bias')]
+                ops.ginet_step(self._fa, pv('fc1.weight'), pv('fc1.bias'), pv('fc2.weight'), pv('fc2.bias'), ws.pred[:B],
+                               task=task, inv_norm=loss_inv if train_step else 1.0,
+                               y=d.y if self.task == 'reg' else None, y_class=d.y_class if self.task == 'class' else None,
+                               class_w=self.class_weights, keep=ws.keep[:B] if drop else None,
+                               keep_scale=1.0 / (1.0 - s.dropout) if drop else 1.0, loss=ws.loss,
+                               partial=ws.partial_full, grads=self.grads, n_params=P.numel, offsets=offs,
+                               forward_only=not train_step)
+                self._graph_done = self._head_done = self._all_done = train_step
+                return ws.pred[:B]
             ops.ginet_fused_fwd(self._fa)
             self._graph_done = True
             return self._heads(d, keep_mask, loss_inv)
@@ -488,6 +525,8 @@ class Engine(object):
 
     # ---------------------------------------------------------------- backward
     def _backward(self, d):
+        if self._all_done:          # the whole-step kernel already produced every gradient
+            return
         s, ws, st, P = self.spec, self.ws, self.structs[d.sslot], self.params
         N, B, L1 = d.N, d.B, d.L1b
         K0d = st.K0_dev

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
+from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, GinetStepArgs, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
                    require_cuda, stream_ptr)
 
 I32, I64, F32 = torch.int32, torch.int64, torch.float32
@@ -427,6 +427,32 @@ def ginet_fused_fwd(a):
 
 def ginet_fused_bwd(a):
     call('drgnn_ginet_fused_bwd', C.byref(a), stream_ptr())
+
+
+def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
+    a = [int(v) for v in (F, h1, h2, nb, max_n, max_k, max_q, Hd, out)]
+    return int(_lib.load().drgnn_ginet_step_smem_bytes(*a)) >= 0
+
+
+def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
+               keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False):
+    """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
+    ``ginet_fused_args``."""
+    require_cuda(fc1_w, fc1_b, fc2_w, fc2_b, pred, y, y_class, class_w, keep, loss, partial, grads)
+    s = GinetStepArgs()
+    s.g = fa
+    s.fc1_w, s.fc1_b, s.fc2_w, s.fc2_b = ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b)
+    s.Hd, s.out = fc1_w.size(0), fc2_w.size(0)
+    s.keep, s.keep_scale = ptr(keep), float(keep_scale) if keep is not None else 1.0
+    s.y, s.y_class, s.class_w = ptr(y), ptr(y_class), ptr(class_w)
+    s.task, s.inv_norm = int(task), float(inv_norm)
+    s.pred, s.loss = ptr(pred), ptr(loss)
+    s.partial, s.partial_ld = ptr(partial), (partial.stride(0) if partial is not None else 0)
+    s.grads, s.n_params = ptr(grads), int(n_params)
+    if offsets is not None:
+        s.off_w1, s.off_w2, s.off_fc1w, s.off_fc1b, s.off_fc2w, s.off_fc2b = [int(o) for o in offsets]
+    s.forward_only = 1 if forward_only else 0
+    call('drgnn_ginet_step', C.byref(s), stream_ptr())
 
 
 TASK_NONE, TASK_MSE, TASK_MSE_SIGMOID, TASK_CE = 0, 1, 2, 3

@@ -328,6 +328,32 @@ int64_t drgnn_ginet_fused_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t 
 int drgnn_ginet_fused_fwd(const drgnn_ginet_fused_args* a, void* stream);
 int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stream);
 
+/* Whole GINet training step of every graph in ONE launch (+ one reduction launch): forward as
+ * above, the network head on the graph's own read-out row (fc1 [Hd, nb*h2] / ReLU / dropout keep
+ * mask / fc2 [out, Hd] are row-wise, the loss is a sum of per-graph terms: task 1 MSE, 2 MSE of
+ * sigmoid, 3 class-weighted cross entropy, see drgnn_head), and the backward down to per-graph
+ * partials of EVERY parameter gradient.  partial [B, partial_ld] rows are laid out like the flat
+ * gradient buffer `grads` [n_params] (offsets off_*; slot n_params of a row holds the graph's loss
+ * term); rows must be ZERO in the slots no live parameter owns.  The reduction sums the rows in
+ * graph order (deterministic) into grads and loss.  forward_only != 0: predictions only. */
+typedef struct drgnn_ginet_step_args {
+  drgnn_ginet_fused_args g;            /* dR / partial / dW1 / dW2 of the embedded block are unused */
+  const float* fc1_w; const float* fc1_b; const float* fc2_w; const float* fc2_b;
+  int32_t Hd; int32_t out;
+  const float* keep; float keep_scale;
+  const float* y; const int64_t* y_class; const float* class_w;
+  int32_t task; float inv_norm;
+  float* pred; float* loss;
+  float* partial; int64_t partial_ld;
+  float* grads; int32_t n_params;
+  int32_t off_w1; int32_t off_w2; int32_t off_fc1w; int32_t off_fc1b; int32_t off_fc2w; int32_t off_fc2b;
+  int32_t forward_only;
+  int32_t head_off;                    /* set by the library */
+} drgnn_ginet_step_args;
+int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
+                                    int32_t max_q, int32_t Hd, int32_t out);
+int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream);
+
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,
                     const int32_t* rows_dev, int32_t C, float* gz, int32_t ldgz, void* stream);

@@ -215,27 +215,29 @@ def test_mathmode_tf32x3_within_tolerance(lib):
         ops.default_math = old
 
 
-def test_fused_per_graph_kernels_equal_op_by_op_path(lib):
-    """GINet: per-graph fused forward / backward (csrc/fused.cu) vs the op-by-op launches: same
-    intermediates bit for bit (same summation orders), weight gradients to fp32 summation order."""
+@pytest.mark.parametrize('fused_head', [True, False])
+def test_fused_per_graph_kernels_equal_op_by_op_path(lib, fused_head):
+    """GINet: per-graph fused kernels (csrc/fused.cu) vs the op-by-op launches.  fused_head=True is
+    the whole-step kernel (forward + head + loss + backward in one launch), False the fused forward /
+    backward kernels around the op-level head.  Intermediates are bit-identical (same summation
+    orders); weight gradients agree to fp32 summation order."""
     from deeprank_gnn_b200 import synthetic
     from deeprank_gnn_b200.engine import Engine
     graphs = synthetic.make_graphs(dict(nodes=(30, 260), edges_per_node=5, feat=32), count=21, seed=13)
-    e_f = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0)
-    e_o = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_graph=False, fused_head=False)
     d = _device_batch(graphs)
+    e_o = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_graph=False, fused_head=False)
+    e_f = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_head=fused_head)
     assert e_f._use_fused_graph(d) and not e_o._use_fused_graph(d)
     for step in range(3):
-        lf, pf = e_f.step(d)
         lo, po = e_o.step(d)
+        lf, pf = e_f.step(d)
         e_f.validate()
-        N, K0 = d.N, e_o.structs[0].K0
         if step == 0:
+            N, (K0, _E1, K1) = d.N, e_o.structs[0].sync_counts()
             for name in ('Zin1', 'Z1'):
                 assert torch.equal(getattr(e_f.ws, name)[:N], getattr(e_o.ws, name)[:N]), name
             for name in ('arg0', 'Zin2', 'Z2'):
                 assert torch.equal(getattr(e_f.ws, name)[:K0], getattr(e_o.ws, name)[:K0]), name
-            K1 = e_o.structs[0].K1
             assert torch.equal(e_f.ws.arg1[:K1], e_o.ws.arg1[:K1])
             torch.testing.assert_close(e_f.ws.R[:d.B], e_o.ws.R[:d.B], rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(pf, po, rtol=1e-4, atol=1e-5)
@@ -243,3 +245,30 @@ def test_fused_per_graph_kernels_equal_op_by_op_path(lib):
         gf, go = e_f.named_grads(), e_o.named_grads()
         for name in gf:
             torch.testing.assert_close(gf[name], go[name], rtol=1e-3, atol=1e-5, msg=name)
+
+
+def test_whole_step_kernel_classification_and_dropout(lib):
+    """Whole-step kernel with class weights + injected dropout mask vs the op-by-op path."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs('cfg2', count=12, seed=21)
+    for i, g in enumerate(graphs):
+        g.y = torch.tensor([float(i % 3)])
+    w = torch.tensor([0.5, 1.5, 1.0])
+    d = _device_batch(graphs, classes=[0, 1, 2])
+    inv = 1.0 / float(w[d.y_class.cpu()].sum())
+    keep = (torch.rand(12, 128, generator=torch.Generator().manual_seed(1)) > 0.4).float()
+    kw = dict(device='cuda:0', seed=9, task='class', class_weights=w)
+    e_o = Engine('GINet', 32, 3, 1, fused_graph=False, fused_head=False, **kw)
+    e_f = Engine('GINet', 32, 3, 1, **kw)
+    lo, po = e_o.step(d, inv_norm=inv, keep_mask=keep)
+    lf, pf = e_f.step(d, inv_norm=inv, keep_mask=keep)
+    assert e_f._all_done
+    torch.testing.assert_close(pf, po, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(lf, lo, rtol=1e-4, atol=1e-6)
+    for name, gfv in e_f.named_grads().items():
+        torch.testing.assert_close(gfv, e_o.named_grads()[name], rtol=1e-3, atol=1e-5, msg=name)
+    # forward only (scoring) through the same kernel
+    pe = e_f.eval().forward(d)
+    po2 = e_o.eval().forward(d)
+    torch.testing.assert_close(pe, po2, rtol=1e-4, atol=1e-5)

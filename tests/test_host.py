@@ -49,6 +49,7 @@ def test_ctypes_structs_match_header_layout(lib):
     assert fields('drgnn_linear_wgrad_args') == [f[0] for f in _lib.LinearWgradArgs._fields_]
     assert fields('drgnn_head_args') == [f[0] for f in _lib.HeadArgs._fields_]
     assert fields('drgnn_ginet_fused_args') == [f[0] for f in _lib.GinetFusedArgs._fields_]
+    assert fields('drgnn_ginet_step_args') == [f[0] for f in _lib.GinetStepArgs._fields_]
 
 
 def test_product_refuses_cpu_tensors(lib):
