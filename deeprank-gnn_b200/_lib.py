@@ -126,6 +126,9 @@ class GinetStepArgs(C.Structure):
         ('off_fc2w', C.c_int32), ('off_fc2b', C.c_int32),
         ('forward_only', C.c_int32),
         ('head_off', C.c_int32),
+        ('drop_p', C.c_float), ('seed', C.c_uint32),
+        ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+        ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
     ]
 
 

@@ -332,6 +332,14 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_bwd_kernel(const dr
 // and the backward down to per-graph gradient partials of EVERY parameter, laid out like the flat
 // gradient buffer.  ginet_step_reduce_kernel then sums the partial rows in graph order.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float hash_uniform(uint32_t seed, uint32_t ctr, uint32_t idx) {
+  uint32_t x = idx * 0x9E3779B1u ^ (ctr * 0x85EBCA77u) ^ (seed * 0xC2B2AE3Du);
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
 __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const drgnn_ginet_step_args s) {
   extern __shared__ __align__(16) float ws[];
   const drgnn_ginet_fused_args& a = s.g;
@@ -360,7 +368,13 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
     if (lane == 0) {
       acc += s.fc1_b ? __ldg(s.fc1_b + j) : 0.f;
       acc = acc < 0.f ? 0.f : acc;
-      if (s.keep) acc = s.keep[(int64_t)g * Hd + j] > 0.f ? acc * s.keep_scale : 0.f;
+      if (s.keep) {
+        acc = s.keep[(int64_t)g * Hd + j] > 0.f ? acc * s.keep_scale : 0.f;
+      } else if (s.drop_p > 0.f) {
+        // counter-based dropout mask: hash of (seed, optimiser step, graph, unit) -> uniform in [0,1)
+        const uint32_t ctr = (uint32_t)s.step_dev[0];
+        acc = hash_uniform(s.seed, ctr, (uint32_t)(g * Hd + j)) >= s.drop_p ? acc * s.keep_scale : 0.f;
+      }
       hrow[j] = acc;
     }
   }
@@ -437,17 +451,51 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
   graph_bwd_body(a, ws, g, drrow, part + s.off_w1, part + s.off_w2);
 }
 
-// grads[e] = sum over graphs (ascending) of partial[g][e]; the slot behind the parameters is the loss
-__global__ void __launch_bounds__(256) ginet_step_reduce_kernel(const float* __restrict__ partial, int64_t ld, int B,
-                                                                int n_params, float* __restrict__ grads,
-                                                                float* __restrict__ loss) {
+// grads[e] = sum over graphs (ascending) of partial[g][e]; the slot behind the parameters is the loss.
+// With fuse_adam the torch.optim.Adam update of element e follows in the same thread (single-GPU
+// runs: no all-reduce sits between the two); the last block to finish bumps the step counter
+// (ticket in step_dev[1]) so that no thread of this launch can observe the new value.
+__global__ void __launch_bounds__(256) ginet_step_reduce_kernel(const drgnn_ginet_step_args s) {
+  __shared__ float sh[3];
+  __shared__ bool is_last;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e > n_params) return;
-  float s = 0.f;
+  const int B = s.g.B, n = s.n_params;
+  if (s.fuse_adam && threadIdx.x == 0) {
+    const float st = s.step_dev[0] + 1.f;
+    sh[0] = st;
+    sh[1] = 1.f - (float)pow((double)s.beta1, (double)st);
+    sh[2] = 1.f - (float)pow((double)s.beta2, (double)st);
+  }
+  __syncthreads();
+  if (e <= n) {
+    float acc = 0.f;
 #pragma unroll 8
-  for (int g = 0; g < B; ++g) s += partial[(int64_t)g * ld + e];
-  if (e < n_params) grads[e] = s;
-  else if (loss) loss[0] = s;
+    for (int g = 0; g < B; ++g) acc += s.partial[(int64_t)g * s.partial_ld + e];
+    if (e < n) {
+      s.grads[e] = acc;
+      if (s.fuse_adam) {
+        float mi = s.adam_m[e], vi = s.adam_v[e];
+        mi = mi + (acc - mi) * (1.f - s.beta1);
+        vi = vi * s.beta2 + (1.f - s.beta2) * acc * acc;
+        s.adam_m[e] = mi;
+        s.adam_v[e] = vi;
+        const float denom = sqrtf(vi) / sqrtf(sh[2]) + s.eps;
+        s.adam_p[e] = s.adam_p[e] - (s.lr / sh[1]) * (mi / denom);
+      }
+    } else if (s.loss) {
+      s.loss[0] = acc;
+    }
+  }
+  if (!s.fuse_adam) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(s.step_dev + 1);
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (is_last) {
+      *ticket = 0u;
+      s.step_dev[0] = sh[0];
+    }
+  }
 }
 
 // dW[e] = sum over graphs (ascending) of partial[g][e]; E = C1*F + nb*h2*h1 contiguous outputs
@@ -566,7 +614,9 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   if (!s->forward_only && s->task != 0) {
     DRGNN_REQUIRE(s->partial && s->grads && s->n_params > 0 && s->partial_ld > s->n_params, "ginet_step: bad gradient buffers");
     DRGNN_REQUIRE(s->task == 3 ? (s->y_class != nullptr) : (s->y != nullptr), "ginet_step: missing targets");
+    DRGNN_REQUIRE(!s->fuse_adam || (s->adam_p && s->adam_m && s->adam_v && s->step_dev), "ginet_step: fuse_adam needs the Adam buffers");
   }
+  DRGNN_REQUIRE(s->keep || s->drop_p <= 0.f || s->step_dev, "ginet_step: hashed dropout needs step_dev");
   if (a->B == 0) return DRGNN_OK;
   const int64_t smem = drgnn_ginet_step_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, s->Hd, s->out);
   if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: a graph of %d nodes does not fit shared memory", a->max_n);
@@ -583,8 +633,7 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   ginet_graph_step_kernel<<<a->B, FU_THREADS, smem, st>>>(k);
   DRGNN_CHECK_LAUNCH("ginet_graph_step_kernel");
   if (!s->forward_only && s->task != 0) {
-    ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(s->partial, s->partial_ld, a->B, s->n_params,
-                                                                           s->grads, s->loss);
+    ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(k);
     DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
   }
   return DRGNN_OK;

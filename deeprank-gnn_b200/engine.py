@@ -250,7 +250,7 @@ class Engine(object):
         self.grads = torch.zeros_like(self.params.data)
         self.exp_avg = torch.zeros_like(self.params.data)
         self.exp_avg_sq = torch.zeros_like(self.params.data)
-        self.step_dev = torch.zeros(1, dtype=F32, device=self.device)
+        self.step_dev = torch.zeros(4, dtype=F32, device=self.device)      # [0] Adam step count, [1] ticket of the fused optimiser
         self.ws = None
         self.structs = [None, None]      # two structure slots: the pass for batch i+1 overlaps step i
         self._last_struct = None
@@ -264,6 +264,9 @@ class Engine(object):
         self._fused_fit = {}
         self._graph_done = False
         self._all_done = False
+        self._adam_done = False
+        self.fuse_adam = True
+        self.seed = 0x5EED if seed is None else int(seed)
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
         self.launches_per_step = 0
@@ -313,7 +316,7 @@ class Engine(object):
         """torch.optim.Adam-shaped state (NeuralNet.py:776 stores optimizer.state_dict())."""
         state = {}
         for i, name in enumerate(self.spec.reference_order()):
-            state[i] = {'step': self.step_dev.detach().cpu().clone().reshape(()),
+            state[i] = {'step': self.step_dev[0].detach().cpu().clone().reshape(()),
                         'exp_avg': self.params.view(self.exp_avg, name).detach().clone(),
                         'exp_avg_sq': self.params.view(self.exp_avg_sq, name).detach().clone()}
         group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': 0, 'amsgrad': False,
@@ -328,7 +331,7 @@ class Engine(object):
                 continue
             self.params.view(self.exp_avg, name).copy_(st['exp_avg'].to(self.device, F32))
             self.params.view(self.exp_avg_sq, name).copy_(st['exp_avg_sq'].to(self.device, F32))
-            self.step_dev.fill_(float(st['step']))
+            self.step_dev[0] = float(st['step'])
         if osd.get('param_groups'):
             g = osd['param_groups'][0]
             self.lr, self.betas, self.eps = float(g['lr']), tuple(g['betas']), float(g['eps'])
@@ -409,7 +412,7 @@ class Engine(object):
         K0d, K1d = st.K0_dev, st.K1_dev
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
-        self._graph_done = self._all_done = False
+        self._graph_done = self._all_done = self._adam_done = False
         if self._use_fused_graph(d):
             # ONE launch: conv1 -> pool -> conv2 -> pool -> read-out, one CTA per graph (csrc/fused.cu)
             self._fa = ops.ginet_fused_args(st, d.x, flat('conv1.fc.weight', s.C1 * s.F),
@@ -427,12 +430,11 @@ class Engine(object):
             if whole:
                 # the whole step of every graph in ONE launch: forward, head, loss, backward (+ one reduction)
                 drop = self.training and s.dropout > 0
-                if drop:
-                    if keep_mask is not None:
-                        ws.keep[:B].copy_(keep_mask.to(self.device, F32))
-                    else:
-                        ws.keep[:B].bernoulli_(1.0 - s.dropout)
+                if drop and keep_mask is not None:
+                    ws.keep[:B].copy_(keep_mask.to(self.device, F32))
+                hashed = drop and keep_mask is None          # mask generated inside the kernel (counter-based hash)
                 train_step = loss_inv is not None
+                fuse_adam = train_step and self.world == 1 and self.fuse_adam
                 task = ops.TASK_NONE
                 if train_step:
                     task = ops.TASK_CE if self.task == 'class' else \
@@ -446,11 +448,15 @@ class Engine(object):
                 ops.ginet_step(self._fa, pv('fc1.weight'), pv('fc1.bias'), pv('fc2.weight'), pv('fc2.bias'), ws.pred[:B],
                                task=task, inv_norm=loss_inv if train_step else 1.0,
                                y=d.y if self.task == 'reg' else None, y_class=d.y_class if self.task == 'class' else None,
-                               class_w=self.class_weights, keep=ws.keep[:B] if drop else None,
+                               class_w=self.class_weights, keep=ws.keep[:B] if (drop and not hashed) else None,
                                keep_scale=1.0 / (1.0 - s.dropout) if drop else 1.0, loss=ws.loss,
                                partial=ws.partial_full, grads=self.grads, n_params=P.numel, offsets=offs,
-                               forward_only=not train_step)
+                               forward_only=not train_step, drop_p=s.dropout if hashed else 0.0, seed=self.seed,
+                               step_dev=self.step_dev,
+                               adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
+                                         beta2=self.betas[1], eps=self.eps) if fuse_adam else None)
                 self._graph_done = self._head_done = self._all_done = train_step
+                self._adam_done = fuse_adam
                 return ws.pred[:B]
             ops.ginet_fused_fwd(self._fa)
             self._graph_done = True
@@ -578,6 +584,9 @@ class Engine(object):
         ops.linear_wgrad(ws.Zin1[:N], ws.dZ1[:N], s.Kin1, s.C1, dW1, db1, w_layout=s.w_layout, work=ws.wwork)
 
     def _adam(self):
+        if self._adam_done:         # already applied by the fused reduction launch of the whole-step kernel
+            self._adam_done = False
+            return
         ops.adam_flat(self.params.data, self.grads, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr,
                       self.betas[0], self.betas[1], self.eps)
 

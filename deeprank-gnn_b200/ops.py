@@ -435,7 +435,8 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 
 
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
-               keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False):
+               keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
+               drop_p=0.0, seed=0, step_dev=None, adam=None):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``."""
     require_cuda(fc1_w, fc1_b, fc2_w, fc2_b, pred, y, y_class, class_w, keep, loss, partial, grads)
@@ -452,6 +453,14 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     if offsets is not None:
         s.off_w1, s.off_w2, s.off_fc1w, s.off_fc1b, s.off_fc2w, s.off_fc2b = [int(o) for o in offsets]
     s.forward_only = 1 if forward_only else 0
+    s.drop_p, s.seed, s.step_dev = float(drop_p), int(seed) & 0xffffffff, ptr(step_dev)
+    if keep is None and drop_p > 0:
+        s.keep_scale = float(keep_scale)
+    if adam is not None:        # dict(p, m, v, lr, beta1, beta2, eps): fuse the optimiser into the reduction launch
+        require_cuda(adam['p'], adam['m'], adam['v'], step_dev)
+        s.fuse_adam = 1
+        s.adam_p, s.adam_m, s.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
+        s.lr, s.beta1, s.beta2, s.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
 
 

@@ -349,6 +349,13 @@ typedef struct drgnn_ginet_step_args {
   int32_t off_w1; int32_t off_w2; int32_t off_fc1w; int32_t off_fc1b; int32_t off_fc2w; int32_t off_fc2b;
   int32_t forward_only;
   int32_t head_off;                    /* set by the library */
+  /* dropout without a mask tensor: keep == NULL and drop_p > 0 -> unit j of graph g is kept iff
+   * hash(seed, (uint)step_dev[0], g*Hd+j) >= drop_p (counter-based, replayable from a CUDA graph) */
+  float drop_p; uint32_t seed;
+  /* fuse_adam != 0: the reduction launch also applies torch.optim.Adam to adam_p (m, v in adam_m /
+   * adam_v) and increments step_dev[0]; step_dev is [4] floats ([1] is a ticket counter, zero it once) */
+  int32_t fuse_adam; float lr; float beta1; float beta2; float eps;
+  float* adam_p; float* adam_m; float* adam_v; float* step_dev;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
