@@ -658,19 +658,18 @@ class Engine(object):
         return self.ws.loss, self.ws.pred[:d.B]
 
     # ---------------------------------------------------------------- packed batches / CUDA graphs
-    def upload(self, pb, slot=0):
+    def upload(self, pb, slot=0, sslot=None):
         """ONE host->device copy of a ``PackedBatch`` into a persistent device staging buffer
         (one per layout and slot, so CUDA-graph replays see fixed addresses).  Returns a
-        DeviceBatch of views into it; its structure slot is ``slot & 1``."""
-        key = (pb.layout_key(), slot)
-        dev = self._staging.get(key)
+        DeviceBatch of views into it; its structure slot is ``sslot`` (default ``slot & 1``)."""
+        dev = self._staging.get((pb.layout_key(), slot))
         if dev is None:
             dev = torch.empty(pb.capacity_numel, dtype=F32, device=self.device)
-            self._staging[key] = dev
+            self._staging[(pb.layout_key(), slot)] = dev
         dev[:pb.numel].copy_(pb.buf, non_blocking=True)
         d = DeviceBatch.from_packed(pb, dev)
-        d.key = key
-        d.sslot = slot & 1
+        d.sslot = (slot & 1) if sslot is None else int(sslot)
+        d.key = (pb.layout_key(), slot, d.sslot)
         return d
 
     def _capture(self, fn):
@@ -735,8 +734,12 @@ class Engine(object):
     def _pipeline_state(self):
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-            self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
-            self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._prep_stream = torch.cuda.Stream(self.device)
+            ev = torch.cuda.Event
+            self._slot_free = [ev(), ev()]                  # structure slot released by the step that read it
+            self._slot_ready = [ev(), ev()]                 # structure pass of the slot finished
+            self._stage_free = [ev(), ev(), ev()]           # staging buffer released by the step that read it
+            self._stage_copied = [ev(), ev(), ev()]         # H2D copy into the staging buffer finished
         return self._copy_stream
 
     def _prepare_any(self, d):
@@ -755,18 +758,30 @@ class Engine(object):
         Returns (losses [n], preds list)."""
         main = torch.cuda.current_stream(self.device)
         cs = self._pipeline_state()
+        ps = self._prep_stream
         cs.wait_stream(main)
+        ps.wait_stream(main)
         outs = []
         was_training = self.training
         self.train(train)
+        packed_batches = list(packed_batches)
+        # one pinned read-back block for the whole pass (a pinned allocation per step would cost more than the step)
+        width = 1 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
+        host_all = torch.empty(max(len(packed_batches), 1), width, dtype=F32, pin_memory=True)
         for i, pb in enumerate(packed_batches):
-            slot = i & 1
+            # three-stage pipeline: H2D copy of batch i+2 | structure pass of batch i+1 | step of batch i
+            stg, slot = i % 3, i & 1
             with torch.cuda.stream(cs):
+                if i >= 3:
+                    cs.wait_event(self._stage_free[stg])
+                d = self.upload(pb, stg, slot)
+                self._stage_copied[stg].record(cs)
+            with torch.cuda.stream(ps):
+                ps.wait_event(self._stage_copied[stg])
                 if i >= 2:
-                    cs.wait_event(self._slot_free[slot])
-                d = self.upload(pb, slot)
+                    ps.wait_event(self._slot_free[slot])
                 self._prepare_any(d)
-                self._slot_ready[slot].record(cs)
+                self._slot_ready[slot].record(ps)
             main.wait_event(self._slot_ready[slot])
             inv = None if inv_norms is None else inv_norms[i]
             if train:
@@ -775,10 +790,11 @@ class Engine(object):
                 pred = self._forward(d)
                 loss = self._loss(d, self._inv_norm(d, B_global, inv), with_grad=False) \
                     if (d.y is not None or d.y_class is not None) else self.ws.loss
-            host = torch.empty(1 + pred.numel(), dtype=F32, pin_memory=True)
+            host = host_all[i, :1 + pred.numel()]
             host[:1].copy_(loss, non_blocking=True)
             host[1:].copy_(pred.reshape(-1), non_blocking=True)
             self._slot_free[slot].record(main)
+            self._stage_free[stg].record(main)
             outs.append((host, tuple(pred.shape)))
         main.synchronize()
         self.train(was_training)
