@@ -423,7 +423,7 @@ def run_b200(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': describe(cfg, args),
         'e2e': {'value': B_global * args.steps / (t_e2e * 1e-3), 'unit': UNIT,
-                'h2d_bytes_per_step': int(pool_bytes / len(packed)), 'd2h_bytes_per_step': 4 * (1 + B),
+                'h2d_bytes_per_step': int(pool_bytes / len(packed)), 'd2h_bytes_per_step': 4 * (4 + B),
                 'ms_per_step': t_e2e / args.steps,
                 'api': 'Engine.train_batches(PackedBatch[...]) - pinned host batch, one H2D copy, fused step, '
                        'D2H of loss + predictions'},

@@ -219,6 +219,9 @@ class PackedBatch(object):
         for k in self.INT_SECTIONS + ('cluster1',):
             o, n = self.offsets[k]
             v[k] = ibuf[o:o + n]
+        if buf.numel() >= self.capacity_numel:      # staging buffers: capacity-sized view, live length = L1
+            o, _n = self.offsets['cluster1']
+            v['cluster1'] = ibuf[o:o + self.N]
         v['x'] = v['x'].view(self.N, self.F)
         v['edge_attr'] = v['edge_attr'].view(self.E, self.ne) if self.ne else None
         v['edge_index'] = v['edge_index'].view(2, self.E)

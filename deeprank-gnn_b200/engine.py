@@ -259,6 +259,7 @@ class Engine(object):
         self._last_struct = None
         self._graphs = {}
         self._staging = {}
+        self._dbatch = {}
         self._copy_stream = None
         from . import _lib
         self._sms = int(_lib.load().drgnn_device_sms())
@@ -356,7 +357,14 @@ class Engine(object):
             nn_ = max(N, ws.N if ws else 0)
             ne_ = max(E, ws.E if ws else 0)
             self.ws = Workspace(self.spec, nb, nn_, ne_, self.device, self.params.numel)
-            self.ws.loss = self._loss_slot      # the loss lives right behind the flat gradients (one all-reduce)
+            # one buffer [flat gradients | loss, pad | predictions]: a multi-GPU step all-reduces the first
+            # numel + 4 floats in ONE call, the host read-back of [loss | predictions] is ONE copy
+            n = self.params.numel
+            self._grads_full = torch.zeros(n + 4 + nb * self.spec.out, dtype=F32, device=self.device)
+            self.grads = self._grads_full[:n]
+            self._loss_slot = self._grads_full[n:n + 1]
+            self.ws.loss = self._loss_slot
+            self.ws.pred = self._grads_full[n + 4:].view(nb, self.spec.out)
             ne_attr = 1 if self.spec.kind == 'sgat' else 0
             self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(2)]
             self._graphs.clear()
@@ -376,7 +384,7 @@ class Engine(object):
         slot = self.structs[d.sslot]
         st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
                                  c1_ptr=d.c1_ptr, cluster1=d.cluster1, edge_attr=d.edge_attr if need_w else None,
-                                 clusters_are_local=True, mirrors=False, out=slot)
+                                 clusters_are_local=True, mirrors=False, out=slot, L1=d.L1)
         assert st is slot
         self._last_struct = st
         return st
@@ -621,7 +629,7 @@ class Engine(object):
         if self.world > 1:
             # the path's only collective: one sum over ranks of [flat gradients | loss] (NCCL over NVLink)
             # (ws.loss IS the slot behind the gradients, see _ensure)
-            torch.distributed.all_reduce(self._grads_full, group=self.pg)
+            torch.distributed.all_reduce(self._grads_full[:self.params.numel + 4], group=self.pg)
 
     def forward(self, d, keep_mask=None, prepared=False):
         """Forward only (``model(batch)``): returns the ``[B, out]`` prediction (a view of an
@@ -672,9 +680,18 @@ class Engine(object):
             dev = torch.empty(pb.capacity_numel, dtype=F32, device=self.device)
             self._staging[(pb.layout_key(), slot)] = dev
         dev[:pb.numel].copy_(pb.buf, non_blocking=True)
-        d = DeviceBatch.from_packed(pb, dev)
-        d.sslot = (slot & 1) if sslot is None else int(sslot)
-        d.key = (pb.layout_key(), slot, d.sslot)
+        sslot = (slot & 1) if sslot is None else int(sslot)
+        ck = (pb.layout_key(), slot, sslot, pb.has_y)
+        d = self._dbatch.get(ck)
+        if d is None:
+            # the views depend on the layout only (cluster1 is a capacity-sized view, its live length is
+            # d.L1), so one DeviceBatch per staging slot is built once and re-used: no per-step tensor views
+            d = DeviceBatch.from_packed(pb, dev)
+            d.sslot = sslot
+            d.key = (pb.layout_key(), slot, sslot)
+            self._dbatch[ck] = d
+        d.L1 = pb.L1
+        d.mol = pb.mol
         return d
 
     def _capture(self, fn):
@@ -771,7 +788,7 @@ class Engine(object):
         self.train(train)
         packed_batches = list(packed_batches)
         # one pinned read-back block for the whole pass (a pinned allocation per step would cost more than the step)
-        width = 1 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
+        width = 4 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
         host_all = torch.empty(max(len(packed_batches), 1), width, dtype=F32, pin_memory=True)
         for i, pb in enumerate(packed_batches):
             # three-stage pipeline: H2D copy of batch i+2 | structure pass of batch i+1 | step of batch i
@@ -795,16 +812,17 @@ class Engine(object):
                 pred = self._forward(d)
                 loss = self._loss(d, self._inv_norm(d, B_global, inv), with_grad=False) \
                     if (d.y is not None or d.y_class is not None) else self.ws.loss
-            host = host_all[i, :1 + pred.numel()]
-            host[:1].copy_(loss, non_blocking=True)
-            host[1:].copy_(pred.reshape(-1), non_blocking=True)
+            # [loss, pad(3), pred...] is contiguous behind the flat gradients: ONE device->host copy
+            n0 = self.params.numel
+            host = host_all[i, :4 + pred.numel()]
+            host.copy_(self._grads_full[n0:n0 + 4 + pred.numel()], non_blocking=True)
             self._slot_free[slot].record(main)
             self._stage_free[stg].record(main)
             outs.append((host, tuple(pred.shape)))
         main.synchronize()
         self.train(was_training)
         losses = torch.stack([h[0] for h, _ in outs]) if outs else torch.zeros(0)
-        preds = [h[1:].view(shape) for h, shape in outs]
+        preds = [h[4:].view(shape) for h, shape in outs]
         return losses, preds
 
     def train_resident(self, dbatches, steps=None, B_global=None):

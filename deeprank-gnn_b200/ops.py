@@ -151,7 +151,7 @@ class Structure(object):
 
 
 def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr=None, cluster1=None,
-                    edge_attr=None, clusters_are_local=True, mirrors=False, out=None):
+                    edge_attr=None, clusters_are_local=True, mirrors=False, out=None, L1=None):
     """Run the structure pass for one mini-batch.  ``node_ptr/edge_ptr/c1_ptr`` are int32
     ``[B+1]`` device tensors; ``edge_index`` ``[2,E]`` and ``cluster0/1`` are int64 (reference
     layout) or int32.  Returns a ``Structure`` (``out`` is reused if given)."""
@@ -160,7 +160,8 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     B = node_ptr.numel() - 1
     N = cluster0.numel()
     E = edge_index.size(1) if edge_index.dim() == 2 else 0
-    L1 = 0 if cluster1 is None else cluster1.numel()
+    # L1: live length of cluster1 when the tensor is a capacity-sized view (packed staging buffers)
+    L1 = (0 if cluster1 is None else cluster1.numel()) if L1 is None else int(L1)
     if edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or \
             (cluster1 is not None and cluster1.dtype != edge_index.dtype):
         raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32)')
