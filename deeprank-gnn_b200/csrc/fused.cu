@@ -256,21 +256,37 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
   const float invQ = 1.f / (float)max(Q, 1);
 
   for (int i = t; i < E2; i += T) w2[i] = a.W2[i];
-  // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU; both layouts
-  for (int item = t; item < K8 * C2; item += T) {
-    const int k = item / C2, c = item - k * C2;
-    float v = 0.f;
-    if (k < K) {
-      const int q = __ldg(a.cl1 + k0 + k);
-      if (a.arg1[(int64_t)q * C2 + c] == k0 + k) v = dRrow[c] * invQ;   // plain loads: written by this CTA
-      if (!(a.Z2[(int64_t)(k0 + k) * C2 + c] > 0.f)) v = 0.f;
+  // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU; both layouts.
+  // One item = 4 channels of one pooled node: the dependent chain cl1 -> arg1 is paid once per 16 bytes
+  // and the unrolled loop keeps several items' loads in flight.
+  {
+    const int C24 = C2 >> 2;
+#pragma unroll 2
+    for (int item = t; item < K8 * C24; item += T) {
+      const int k = item / C24, q4 = item - k * C24;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const int q = __ldg(a.cl1 + k0 + k);
+        const int4 am = *reinterpret_cast<const int4*>(a.arg1 + (int64_t)q * C2 + q4 * 4);   // plain loads: written
+        const float4 z = *reinterpret_cast<const float4*>(a.Z2 + (int64_t)(k0 + k) * C2 + q4 * 4);  // by this CTA
+        const float4 d = *reinterpret_cast<const float4*>(dRrow + q4 * 4);
+        const int me = k0 + k;
+        v.x = (am.x == me && z.x > 0.f) ? d.x * invQ : 0.f;
+        v.y = (am.y == me && z.y > 0.f) ? d.y * invQ : 0.f;
+        v.z = (am.z == me && z.z > 0.f) ? d.z * invQ : 0.f;
+        v.w = (am.w == me && z.w > 0.f) ? d.w * invQ : 0.f;
+      }
+      *reinterpret_cast<float4*>(dz2 + k * C2 + q4 * 4) = v;
+      dz2T[(q4 * 4 + 0) * P.k_p + k] = v.x;
+      dz2T[(q4 * 4 + 1) * P.k_p + k] = v.y;
+      dz2T[(q4 * 4 + 2) * P.k_p + k] = v.z;
+      dz2T[(q4 * 4 + 3) * P.k_p + k] = v.w;
     }
-    dz2[item] = v;
-    dz2T[c * P.k_p + k] = v;
-  }
-  for (int item = t; item < K8 * C1; item += T) {
-    const int k = item / C1;
-    ap[item] = k < K ? a.Zin2[(int64_t)k0 * C1 + item] : 0.f;
+    const int C14v = C1 >> 2;
+    const float4* src = reinterpret_cast<const float4*>(a.Zin2 + (int64_t)k0 * C1);
+    float4* dst = reinterpret_cast<float4*>(ap);
+    for (int item = t; item < K8 * C14v; item += T)
+      dst[item] = (item / C14v) < K ? src[item] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   // ---- per-graph dW2 partial [nb][h2][h1] = dZ2_g^T AP_g ; dAP = dZ2_g W2_g
@@ -297,21 +313,35 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
     *reinterpret_cast<float4*>(dp1 + k * C1 + q4 * 4) = acc;
   }
   __syncthreads();
-  // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU; stage AX
-  for (int item = t; item < n8 * C1; item += T) {
-    const int i = item / C1, c = item - i * C1;
-    float v = 0.f;
-    if (i < n) {
-      const int k = __ldg(a.cl0 + n0 + i);
-      if (a.arg0[(int64_t)k * C1 + c] == n0 + i) v = dp1[(k - k0) * C1 + c];
-      if (!(a.Z1[(int64_t)(n0 + i) * C1 + c] > 0.f)) v = 0.f;
+  // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU (4 channels per item); stage AX
+  {
+#pragma unroll 4
+    for (int item = t; item < n8 * C14; item += T) {
+      const int i = item / C14, q4 = item - i * C14;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n) {
+        const int k = __ldg(a.cl0 + n0 + i);
+        const int4 am = *reinterpret_cast<const int4*>(a.arg0 + (int64_t)k * C1 + q4 * 4);
+        const float4 z = *reinterpret_cast<const float4*>(a.Z1 + (int64_t)(n0 + i) * C1 + q4 * 4);
+        const float4 d = *reinterpret_cast<const float4*>(dp1 + (k - k0) * C1 + q4 * 4);
+        const int me = n0 + i;
+        v.x = (am.x == me && z.x > 0.f) ? d.x : 0.f;
+        v.y = (am.y == me && z.y > 0.f) ? d.y : 0.f;
+        v.z = (am.z == me && z.z > 0.f) ? d.z : 0.f;
+        v.w = (am.w == me && z.w > 0.f) ? d.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(dz1 + i * C1 + q4 * 4) = v;
     }
-    dz1[item] = v;
-  }
-  for (int item = t; item < n8 * F; item += T) {
-    const int i = item / F;
-    float v = i < n ? a.Zin1[(int64_t)n0 * F + item] : 0.f;
-    ax[item] = (v == v) ? v : 0.f;
+    const int F4 = F >> 2;
+    const float4* src = reinterpret_cast<const float4*>(a.Zin1 + (int64_t)n0 * F);
+    float4* dst = reinterpret_cast<float4*>(ax);
+#pragma unroll 4
+    for (int item = t; item < n8 * F4; item += T) {
+      float4 v = (item / F4) < n ? src[item] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = (v.x == v.x) ? v.x : 0.f; v.y = (v.y == v.y) ? v.y : 0.f;
+      v.z = (v.z == v.z) ? v.z : 0.f; v.w = (v.w == v.w) ? v.w : 0.f;
+      dst[item] = v;
+    }
   }
   __syncthreads();
   // ---- per-graph dW1 partial [C1][F] = dZ1^T AX
