@@ -430,6 +430,7 @@ def run_b200(args):
         'gpu_launches': kernels_per_step * args.steps,
         'kernels_per_step': kernels_per_step,
         'cuda_graph': not args.no_graph,
+        'collective': eng.collective() + ('' if eng.comm_error is None else ' (peer memory unavailable: %s)' % eng.comm_error),
         'final_loss': final_loss,
         'clocks': clocks,
     }

@@ -129,6 +129,30 @@ class GinetStepArgs(C.Structure):
         ('drop_p', C.c_float), ('seed', C.c_uint32),
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
+        ('skip_reduce', C.c_int32), ('reserved1', C.c_int32),
+    ]
+
+
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class PeerComm(C.Structure):
+    _fields_ = [
+        ('world', C.c_int32), ('rank', C.c_int32),
+        ('xbuf', VP * MAX_PEERS), ('xflag', VP * MAX_PEERS),
+        ('ctr', VP), ('stride', C.c_int64), ('max_blocks', C.c_int32), ('reserved', C.c_int32),
+        ('timeout_ns', C.c_uint64),
+    ]
+
+
+class PeerAdamArgs(C.Structure):
+    _fields_ = [
+        ('partial', VP), ('B', C.c_int32), ('reserved0', C.c_int32), ('partial_ld', C.c_int64),
+        ('grads', VP), ('n_params', C.c_int32), ('n_sum', C.c_int32),
+        ('apply_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+        ('reserved1', C.c_int32),
+        ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
     ]
 
 
@@ -179,6 +203,12 @@ _SIGNATURES = {
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),
     'drgnn_fill_f32': (C.c_int, [VP, _f32, _i64, VP]),
     'drgnn_fill_i32': (C.c_int, [VP, _i32, _i64, VP]),
+    'drgnn_comm_alloc': (C.c_int, [_i64, C.POINTER(VP), C.c_char_p]),
+    'drgnn_comm_open': (C.c_int, [C.c_char_p, C.POINTER(VP)]),
+    'drgnn_comm_close': (C.c_int, [VP]),
+    'drgnn_comm_free': (C.c_int, [VP]),
+    'drgnn_comm_status': (C.c_int, [VP, C.POINTER(C.c_uint32)]),
+    'drgnn_peer_reduce_adam': (C.c_int, [C.POINTER(PeerComm), C.POINTER(PeerAdamArgs), VP]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

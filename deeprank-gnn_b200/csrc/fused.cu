@@ -662,7 +662,7 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ginet_graph_step_kernel<<<a->B, FU_THREADS, smem, st>>>(k);
   DRGNN_CHECK_LAUNCH("ginet_graph_step_kernel");
-  if (!s->forward_only && s->task != 0) {
+  if (!s->forward_only && s->task != 0 && !s->skip_reduce) {
     ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(k);
     DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
   }

@@ -22,6 +22,7 @@ captured in a CUDA graph (``graph=True``) and replayed.
 Parameters live in one flat fp32 buffer; ``state_dict()`` / ``load_state_dict()`` use the
 reference's names and shapes, so reference checkpoints load unchanged.
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -228,7 +229,8 @@ class DeviceBatch(object):
 class Engine(object):
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=None, graph=False, tiled=True, fused_head=True, fused_graph=True, process_group=None, seed=None):
+                 dropout=None, graph=False, tiled=True, fused_head=True, fused_graph=True, process_group=None, seed=None,
+                 peer_comm=True):
         self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -246,6 +248,11 @@ class Engine(object):
         self.pg = process_group
         dist = torch.distributed
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.comm = None                 # parallel.PeerComm: fused exchange + Adam over NVLink peer memory
+        self.comm_error = None
+        self._no_exchange = False        # CUDA-graph warm-up: run the kernels without talking to the peers
+        self._want_adam = True
+        self._reduced = False
         self.params = FlatParams(self.spec, self.device)
         # gradients and the loss share one buffer so that a multi-GPU step needs ONE all-reduce
         self._grads_full = torch.zeros(self.params.numel + 4, dtype=F32, device=self.device)
@@ -275,6 +282,23 @@ class Engine(object):
         self._head_done = False
         self.launches_per_step = 0
         self.reset_parameters(seed)
+        if self.world > 1 and peer_comm and os.environ.get('DRGNN_PEER_COMM', '1') != '0':
+            self._open_comm()
+
+    def _open_comm(self):
+        """Map the peers' exchange regions (CUDA IPC).  Symmetric on all ranks: either every rank
+        gets a communicator or none does (then the step falls back to ONE NCCL all-reduce)."""
+        from .parallel import PeerComm
+        try:
+            self.comm = PeerComm(self.params.numel + 4, group=self.pg)
+        except DrgnnError as e:
+            self.comm, self.comm_error = None, str(e)
+
+    def collective(self):
+        """Name of the gradient exchange this engine uses (reported by bench.py)."""
+        if self.world == 1:
+            return 'none'
+        return 'peer-memory exchange fused with reduce+Adam (1 launch)' if self.comm is not None else 'nccl all_reduce'
 
     # ---------------------------------------------------------------- parameters
     def reset_parameters(self, seed=None):
@@ -447,6 +471,7 @@ class Engine(object):
                 hashed = drop and keep_mask is None          # mask generated inside the kernel (counter-based hash)
                 train_step = loss_inv is not None
                 fuse_adam = train_step and self.world == 1 and self.fuse_adam
+                use_comm = train_step and self.comm is not None and self._want_adam
                 task = ops.TASK_NONE
                 if train_step:
                     task = ops.TASK_CE if self.task == 'class' else \
@@ -466,9 +491,13 @@ class Engine(object):
                                forward_only=not train_step, drop_p=s.dropout if hashed else 0.0, seed=self.seed,
                                step_dev=self.step_dev,
                                adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
-                                         beta2=self.betas[1], eps=self.eps) if fuse_adam else None)
+                                         beta2=self.betas[1], eps=self.eps) if fuse_adam else None,
+                               skip_reduce=use_comm)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._adam_done = fuse_adam
+                if use_comm:
+                    # per-graph rows -> rank-local sum -> peers -> rank-ordered sum -> Adam: ONE launch
+                    self._peer_exchange(partial=ws.partial_full, B=B)
                 return ws.pred[:B]
             ops.ginet_fused_fwd(self._fa)
             self._graph_done = True
@@ -625,7 +654,22 @@ class Engine(object):
                         class_w=self.class_weights)
         return ws.loss
 
+    def _peer_exchange(self, partial=None, B=0):
+        if not self._no_exchange:
+            ops.peer_reduce_adam(self.comm, self._grads_full, self.params.numel, self.params.numel + 4, partial=partial,
+                                 B=B, step_dev=self.step_dev,
+                                 adam=dict(p=self.params.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr,
+                                           beta1=self.betas[0], beta2=self.betas[1], eps=self.eps))
+        self._reduced = self._adam_done = True
+
     def _all_reduce(self):
+        if self._reduced:               # the whole-step path already exchanged
+            self._reduced = False
+            return
+        if self.world > 1 and self.comm is not None and self._want_adam:
+            self._peer_exchange()
+            self._reduced = False
+            return
         if self.world > 1:
             # the path's only collective: one sum over ranks of [flat gradients | loss] (NCCL over NVLink)
             # (ws.loss IS the slot behind the gradients, see _ensure)
@@ -642,10 +686,14 @@ class Engine(object):
         """Forward + loss + backward, no optimiser (parity tests).  Gradients in ``named_grads()``."""
         inv = self._inv_norm(d, B_global, inv_norm)
         self.prepare(d)
-        self._forward(d, keep_mask, loss_inv=inv)
-        if not self._head_done:
-            self._loss(d, inv)
-        self._backward(d)
+        self._want_adam = False
+        try:
+            self._forward(d, keep_mask, loss_inv=inv)
+            if not self._head_done:
+                self._loss(d, inv)
+            self._backward(d)
+        finally:
+            self._want_adam = True
         return self.ws.loss, self.ws.pred[:d.B]
 
     def step(self, d, B_global=None, inv_norm=None, keep_mask=None, prepared=False):
@@ -725,12 +773,19 @@ class Engine(object):
             snap = [t.clone() for t in (self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev)]
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
+            split = self.world > 1 and self.comm is None      # NCCL path: the all-reduce sits between two graphs
             with torch.cuda.stream(side):
-                self._forward(d, loss_inv=inv)
-                if not self._head_done:
-                    self._loss(d, inv)
-                self._backward(d)
-                self._adam()
+                self._no_exchange = True                      # ranks may warm up at different steps: stay local
+                try:
+                    self._forward(d, loss_inv=inv)
+                    if not self._head_done:
+                        self._loss(d, inv)
+                    self._backward(d)
+                    if not split:
+                        self._all_reduce()
+                    self._adam()
+                finally:
+                    self._no_exchange = False
             torch.cuda.current_stream(self.device).wait_stream(side)
             for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
                 t.copy_(c)
@@ -740,10 +795,11 @@ class Engine(object):
                 if not self._head_done:
                     self._loss(d, inv)
                 self._backward(d)
-                if self.world == 1:
+                if not split:
+                    self._all_reduce()
                     self._adam()
             g1 = self._capture(body)
-            g2 = self._capture(self._adam) if self.world > 1 else None
+            g2 = self._capture(self._adam) if split else None
             ent = (g1, g2)
             self._graphs[key] = ent
         g1, g2 = ent
@@ -856,3 +912,6 @@ class Engine(object):
         if self._last_struct is not None:
             self._last_struct._counts_host = None
             self._last_struct.sync_counts()
+        if self.comm is not None and self.comm.status() != 0:
+            raise DrgnnError('gradient exchange: a peer rank did not deliver its gradients within the watchdog '
+                             '(DRGNN_PEER_TIMEOUT_S); the weights of this rank are no longer valid')

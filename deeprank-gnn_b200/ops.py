@@ -437,7 +437,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
-               drop_p=0.0, seed=0, step_dev=None, adam=None):
+               drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``."""
     require_cuda(fc1_w, fc1_b, fc2_w, fc2_b, pred, y, y_class, class_w, keep, loss, partial, grads)
@@ -462,7 +462,29 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
         s.fuse_adam = 1
         s.adam_p, s.adam_m, s.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
         s.lr, s.beta1, s.beta2, s.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
+    s.skip_reduce = 1 if skip_reduce else 0
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
+    if skip_reduce or forward_only:
+        _lib.kernel_count -= 1          # only the per-graph kernel was launched
+
+
+def peer_reduce_adam(comm, grads, n_params, n_sum, partial=None, B=0, adam=None, step_dev=None):
+    """Gradient exchange over NVLink peer memory + rank-ordered sum + Adam in ONE launch
+    (``drgnn_peer_reduce_adam``).  ``comm``: ``parallel.PeerComm``; ``partial``: optional per-graph
+    rows of the whole-step kernel (summed in graph order first); ``grads [>= n_sum]`` receives the
+    global sums (gradients | loss)."""
+    require_cuda(grads, partial, step_dev)
+    a = _lib.PeerAdamArgs()
+    a.partial, a.B = ptr(partial), int(B)
+    a.partial_ld = partial.stride(0) if partial is not None else 0
+    a.grads, a.n_params, a.n_sum = ptr(grads), int(n_params), int(n_sum)
+    a.step_dev = ptr(step_dev)
+    if adam is not None:
+        require_cuda(adam['p'], adam['m'], adam['v'])
+        a.apply_adam = 1
+        a.adam_p, a.adam_m, a.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
+        a.lr, a.beta1, a.beta2, a.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
+    call('drgnn_peer_reduce_adam', C.byref(comm.struct), C.byref(a), stream_ptr())
 
 
 TASK_NONE, TASK_MSE, TASK_MSE_SIGMOID, TASK_CE = 0, 1, 2, 3

@@ -74,3 +74,101 @@ def all_reduce_flat_(flat, group=None):
             torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(flat, group=group)
     return flat
+
+
+class PeerComm(object):
+    """Exchange region of the fused gradient all-reduce (``csrc/comm.cu``, ``include/drgnn.h``).
+
+    Every rank allocates one region through the library (cudaMalloc + CUDA IPC handle), the
+    handles are exchanged with ``all_gather_object`` and every rank maps the regions of its peers,
+    after which ``ops.peer_reduce_adam`` moves gradients with plain stores over NVLink - no NCCL
+    call on the step.  ``regions`` (same-process pointers) builds a communicator without IPC: used
+    by the single-GPU protocol test, where two "ranks" run on two streams of one device.
+    Region layout: ctr[16] u32 | flags [2][world][max_blocks] u32 | buffers [2][world][stride] f32."""
+
+    THREADS = 256
+
+    @staticmethod
+    def layout(world, n_sum):
+        stride = (int(n_sum) + 3) // 4 * 4
+        max_blocks = (int(n_sum) + PeerComm.THREADS - 1) // PeerComm.THREADS
+        flags_off = 64
+        buf_off = (flags_off + 4 * 2 * world * max_blocks + 255) // 256 * 256
+        return stride, max_blocks, flags_off, buf_off, buf_off + 4 * 2 * world * stride
+
+    def __init__(self, n_sum, rank=None, world=None, group=None, regions=None, timeout_s=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        dist = torch.distributed
+        if regions is None:
+            world = dist.get_world_size(group)
+            rank = dist.get_rank(group)
+        if world > _lib.MAX_PEERS:
+            raise _lib.DrgnnError('PeerComm supports up to %d ranks (one NVSwitch domain)' % _lib.MAX_PEERS)
+        self.world, self.rank, self.n_sum = int(world), int(rank), int(n_sum)
+        stride, max_blocks, flags_off, buf_off, nbytes = self.layout(world, n_sum)
+        self.nbytes = nbytes
+        self._own = None
+        self._opened = []
+        if regions is None:
+            # every collective below is entered by ALL ranks whatever failed locally, and the outcome is
+            # agreed on: either every rank ends up with a communicator or every rank raises
+            own = _lib.VP()
+            handle = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            err = None
+            if lib.drgnn_comm_alloc(nbytes, C.byref(own), handle) != 0:
+                err = 'rank %d: %s' % (rank, lib.drgnn_last_error().decode())
+            else:
+                self._own = own.value
+            handles = [None] * world
+            dist.all_gather_object(handles, None if err else handle.raw, group=group)
+            regions = []
+            if all(h is not None for h in handles):
+                for r in range(world):
+                    if r == rank:
+                        regions.append(self._own)
+                        continue
+                    p = _lib.VP()
+                    if lib.drgnn_comm_open(handles[r], C.byref(p)) != 0:
+                        err = 'rank %d -> %d: %s' % (rank, r, lib.drgnn_last_error().decode())
+                        break
+                    self._opened.append(p.value)
+                    regions.append(p.value)
+            else:
+                err = err or 'a peer could not allocate its exchange region'
+            errs = [None] * world
+            dist.all_gather_object(errs, err, group=group)
+            if any(e is not None for e in errs):
+                self.close()
+                raise _lib.DrgnnError('peer-memory exchange unavailable: ' + '; '.join(e for e in errs if e))
+        self.regions = list(regions)
+        st = _lib.PeerComm()
+        st.world, st.rank = self.world, self.rank
+        for r in range(self.world):
+            st.xflag[r] = self.regions[r] + flags_off
+            st.xbuf[r] = self.regions[r] + buf_off
+        st.ctr = self.regions[self.rank]
+        st.stride, st.max_blocks = stride, max_blocks
+        if timeout_s is None:
+            timeout_s = float(os.environ.get('DRGNN_PEER_TIMEOUT_S', '20'))
+        st.timeout_ns = int(timeout_s * 1e9)
+        self.struct = st
+
+    def status(self):
+        """ctr[2] of the own region: non-zero if a peer failed to deliver within the watchdog."""
+        import ctypes as C
+        from . import _lib
+        out = (C.c_uint32 * 4)()
+        _lib.check(_lib.load().drgnn_comm_status(self.regions[self.rank], out), 'drgnn_comm_status')
+        return int(out[2])
+
+    def close(self):
+        from . import _lib
+        lib = _lib.load()
+        for p in self._opened:
+            lib.drgnn_comm_close(p)
+        self._opened = []
+        if self._own is not None:
+            lib.drgnn_comm_free(self._own)
+            self._own = None

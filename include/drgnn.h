@@ -356,10 +356,51 @@ typedef struct drgnn_ginet_step_args {
    * adam_v) and increments step_dev[0]; step_dev is [4] floats ([1] is a ticket counter, zero it once) */
   int32_t fuse_adam; float lr; float beta1; float beta2; float eps;
   float* adam_p; float* adam_m; float* adam_v; float* step_dev;
+  /* skip_reduce != 0: stop after the per-graph launch (partial rows written); the caller reduces
+   * them itself, e.g. with drgnn_peer_reduce_adam on several GPUs */
+  int32_t skip_reduce; int32_t reserved1;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
 int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream);
+
+/* ---- multi-GPU: gradient exchange over NVLink peer memory fused with the optimiser ----
+ * Replaces, on every rank, the sequence  [reduce per-graph rows] -> torch.distributed.all_reduce(flat
+ * gradients | loss) -> torch.optim.Adam.step()  (the data-parallel form of NeuralNet.py:502-503)
+ * by ONE launch: each rank stores its local sums into every rank's exchange buffer (plain P2P
+ * stores), releases a per-block flag, waits for the same block of every peer, sums the `world`
+ * slots in rank order (bit-identical on all ranks) and applies Adam.
+ *
+ * Exception to the ownership rule: the exchange region must be shareable between processes, so the
+ * library allocates it (cudaMalloc, zero-filled) and exports a 64-byte CUDA IPC handle; the host
+ * exchanges handles (torch.distributed.all_gather_object) and opens the peers' regions.
+ * Region layout (the host computes the pointers): ctr[16] u32 (local: [0] epoch, [1] ticket,
+ * [2] error status, 1 = a peer did not deliver within timeout_ns) | flags [2][world][max_blocks] u32
+ * | buffers [2][world][stride] f32. */
+#define DRGNN_MAX_PEERS 8
+#define DRGNN_IPC_HANDLE_BYTES 64
+typedef struct drgnn_peer_comm {
+  int32_t world; int32_t rank;
+  float* xbuf[DRGNN_MAX_PEERS];        /* buffers of rank r as mapped in THIS process ([rank] = own)  */
+  uint32_t* xflag[DRGNN_MAX_PEERS];    /* flags of rank r as mapped in THIS process                   */
+  uint32_t* ctr;                       /* own counters                                                */
+  int64_t stride;                      /* floats per slot (>= n_sum)                                  */
+  int32_t max_blocks; int32_t reserved;
+  uint64_t timeout_ns;                 /* watchdog of the wait (0 = 20 s)                             */
+} drgnn_peer_comm;
+typedef struct drgnn_peer_adam_args {
+  const float* partial; int32_t B; int32_t reserved0; int64_t partial_ld;  /* optional per-graph rows, summed in
+                                          graph order (drgnn_ginet_step with skip_reduce); NULL: local value = grads */
+  float* grads; int32_t n_params; int32_t n_sum;   /* n_sum >= n_params elements are exchanged (gradients | loss) */
+  int32_t apply_adam; float lr; float beta1; float beta2; float eps; int32_t reserved1;
+  float* adam_p; float* adam_m; float* adam_v; float* step_dev;
+} drgnn_peer_adam_args;
+int drgnn_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int drgnn_comm_open(const unsigned char* handle64, void** peer_ptr);
+int drgnn_comm_close(void* peer_ptr);
+int drgnn_comm_free(void* dev_ptr);
+int drgnn_comm_status(const void* region, uint32_t* ctr4);   /* host copy of ctr[0..3] (synchronises the device) */
+int drgnn_peer_reduce_adam(const drgnn_peer_comm* c, const drgnn_peer_adam_args* a, void* stream);
 
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,

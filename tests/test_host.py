@@ -39,6 +39,7 @@ def test_ctypes_structs_match_header_layout(lib):
         names = []
         for decl in body.split(';'):
             decl = decl.strip()
+            decl = re.sub(r'\[[^\]]*\]\s*$', '', decl)          # array members: name[DRGNN_MAX_PEERS]
             if decl:
                 names.append(re.findall(r'([A-Za-z0-9_]+)\s*$', decl)[0])
         return names
@@ -50,6 +51,8 @@ def test_ctypes_structs_match_header_layout(lib):
     assert fields('drgnn_head_args') == [f[0] for f in _lib.HeadArgs._fields_]
     assert fields('drgnn_ginet_fused_args') == [f[0] for f in _lib.GinetFusedArgs._fields_]
     assert fields('drgnn_ginet_step_args') == [f[0] for f in _lib.GinetStepArgs._fields_]
+    assert fields('drgnn_peer_comm') == [f[0] for f in _lib.PeerComm._fields_]
+    assert fields('drgnn_peer_adam_args') == [f[0] for f in _lib.PeerAdamArgs._fields_]
 
 
 def test_product_refuses_cpu_tensors(lib):
