@@ -198,6 +198,7 @@ _SIGNATURES = {
     'drgnn_ginet_fused_bwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
     'drgnn_ginet_step_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     'drgnn_ginet_step': (C.c_int, [C.POINTER(GinetStepArgs), VP]),
+    'drgnn_debug_phase_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),

@@ -26,6 +26,13 @@ namespace drgnn {
 
 static constexpr int FU_THREADS = 512;
 
+// Diagnostic: SM clock at the phase boundaries of the CTA that runs graph 0 (drgnn_debug_phase_cycles).
+__device__ unsigned long long g_phase[32];
+#define DRGNN_PHASE(i)                                                         \
+  do {                                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_phase[i] = (unsigned long long)clock64(); \
+  } while (0)
+
 __host__ __device__ inline int up8(int x) { return (x + 7) & ~7; }
 
 struct FwdSmem {
@@ -113,6 +120,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     }
   }
   __syncthreads();
+  DRGNN_PHASE(1);
   // ---- AX = A x   (thread per (row, 4 channels); row index fastest => conflict-free transposed stores)
   for (int item = t; item < n8 * F4; item += T) {
     const int q4 = item / n8, i = item - q4 * n8;
@@ -132,6 +140,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     axT[(q4 * 4 + 3) * P.n_p + i] = acc.w;
   }
   __syncthreads();
+  DRGNN_PHASE(2);
   // ---- Z1 = relu(AX W1cat^T)
   tile_gemm(axT, P.n_p, w1t, C1, n8, C1, F, [&](int m, int c, float v) {
     v = v < 0.f ? 0.f : v;
@@ -139,6 +148,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     if (m < n) a.Z1[(int64_t)(n0 + m) * C1 + c] = v;
   });
   __syncthreads();
+  DRGNN_PHASE(3);
   // ---- P1 = cluster max of Z1 (first member wins ties, a NaN never wins; community_pooling.py:201)
   for (int item = t; item < K * C14; item += T) {
     const int k = item / C14, q4 = item - k * C14;
@@ -161,6 +171,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     *reinterpret_cast<int4*>(a.arg0 + (int64_t)(k0 + k) * C1 + q4 * 4) = arg;
   }
   __syncthreads();
+  DRGNN_PHASE(4);
   // ---- AP = A1 P1 on the coarsened graph
   for (int item = t; item < K8 * C14; item += T) {
     const int q4 = item / K8, k = item - q4 * K8;
@@ -180,6 +191,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     apT[(q4 * 4 + 3) * P.k_p + k] = acc.w;
   }
   __syncthreads();
+  DRGNN_PHASE(5);
   // ---- Z2 = relu(AP_g W2_g^T) per branch g
   for (int gg = 0; gg < nb; ++gg) {
     tile_gemm(apT + gg * h1 * P.k_p, P.k_p, w2t + gg * h1 * h2, h2, K8, h2, h1, [&](int m, int o, float v) {
@@ -189,6 +201,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     });
   }
   __syncthreads();
+  DRGNN_PHASE(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
   for (int item = t; item < Q * C24; item += T) {
     const int q = item / C24, q4 = item - q * C24;
@@ -211,6 +224,7 @@ __device__ __forceinline__ bool graph_fwd_body(const drgnn_ginet_fused_args& a, 
     *reinterpret_cast<int4*>(a.arg1 + (int64_t)(q0 + q) * C2 + q4 * 4) = arg;
   }
   __syncthreads();
+  DRGNN_PHASE(7);
   // ---- R[g] = mean over the graph's level-1 clusters (scatter_mean by batch, ascending order)
   for (int c = t; c < C2; c += T) {
     float acc = 0.f;
@@ -289,6 +303,7 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
       dst[item] = (item / C14v) < K ? src[item] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  DRGNN_PHASE(12);
   // ---- per-graph dW2 partial [nb][h2][h1] = dZ2_g^T AP_g ; dAP = dZ2_g W2_g
   for (int gg = 0; gg < nb; ++gg) {
     tile_gemm(dz2 + gg * h2, C2, ap + gg * h1, C1, h2, h1, K8, [&](int o, int j, float v) {
@@ -299,6 +314,7 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
     });
   }
   __syncthreads();
+  DRGNN_PHASE(13);
   // ---- dP1 = A1^T dAP  (CSC of the coarsened graph)
   const int C14 = C1 >> 2;
   for (int item = t; item < K * C14; item += T) {
@@ -313,6 +329,7 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
     *reinterpret_cast<float4*>(dp1 + k * C1 + q4 * 4) = acc;
   }
   __syncthreads();
+  DRGNN_PHASE(14);
   // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU (4 channels per item); stage AX
   {
 #pragma unroll 4
@@ -344,6 +361,7 @@ __device__ __forceinline__ void graph_bwd_body(const drgnn_ginet_fused_args& a, 
     }
   }
   __syncthreads();
+  DRGNN_PHASE(15);
   // ---- per-graph dW1 partial [C1][F] = dZ1^T AX
   tile_gemm(dz1, C1, ax, F, C1, F, n8, [&](int c, int f, float v) { part1[c * F + f] = v; });
 }
@@ -376,6 +394,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
   const int g = blockIdx.x;
   const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, nwarps = T >> 5;
   const int C2 = a.nb * a.h2, Hd = s.Hd, out = s.out;
+  DRGNN_PHASE(0);
   // head scratch lives behind the graph workspace
   float* rrow = ws + s.head_off;         // [C2]  read-out row R[g]
   float* hrow = rrow + C2;               // [Hd]  hidden activation (after ReLU / dropout)
@@ -385,6 +404,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
   float* part = s.partial + (int64_t)g * s.partial_ld;
   const bool ok = graph_fwd_body(a, ws, g, rrow);
   __syncthreads();
+  DRGNN_PHASE(8);
   if (!ok) {
     if (!s.forward_only)
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
@@ -409,6 +429,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
     }
   }
   __syncthreads();
+  DRGNN_PHASE(9);
   // ---- fc2: warp per output
   for (int o = warp; o < out; o += nwarps) {
     float acc = 0.f;
@@ -421,6 +442,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
     }
   }
   __syncthreads();
+  DRGNN_PHASE(10);
   if (s.forward_only || s.task == 0) return;
   // ---- loss term of this graph and dLoss/dpred (one thread)
   if (t == 0) {
@@ -450,6 +472,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
     part[s.n_params] = lg * s.inv_norm;   // summed into the loss by the reduce kernel
   }
   __syncthreads();
+  DRGNN_PHASE(11);
   // ---- head backward: fc2 partials, dh, fc1 partials, dR row
   for (int i = t; i < out * Hd; i += T) part[s.off_fc2w + i] = prow[i / Hd] * hrow[i % Hd];
   for (int o = t; o < out; o += T) part[s.off_fc2b + o] = prow[o];
@@ -478,7 +501,10 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
     }
   }
   __syncthreads();
+  DRGNN_PHASE(11);
   graph_bwd_body(a, ws, g, drrow, part + s.off_w1, part + s.off_w2);
+  __syncthreads();
+  DRGNN_PHASE(16);
 }
 
 // grads[e] = sum over graphs (ascending) of partial[g][e]; the slot behind the parameters is the loss.
@@ -611,6 +637,12 @@ extern "C" int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stre
   const int E1 = a->nb * a->h1 * a->F, E2 = a->nb * a->h2 * a->h1;
   ginet_wgrad_reduce_kernel<<<(E1 + E2 + 255) / 256, 256, 0, st>>>(a->partial, a->B, E1, E2, a->dW1, a->dW2);
   DRGNN_CHECK_LAUNCH("ginet_wgrad_reduce_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_debug_phase_cycles(uint64_t* out32) {
+  DRGNN_REQUIRE(out32 != nullptr, "debug_phase_cycles: NULL");
+  DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_phase, sizeof(unsigned long long) * 32));
   return DRGNN_OK;
 }
 

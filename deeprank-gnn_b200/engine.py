@@ -227,6 +227,8 @@ class DeviceBatch(object):
 
 
 class Engine(object):
+    STRUCT_SLOTS = 4      # structure passes may run this many batches ahead of the step (weight-independent work)
+
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
                  dropout=None, graph=False, tiled=True, fused_head=True, fused_graph=True, process_group=None, seed=None,
@@ -262,7 +264,7 @@ class Engine(object):
         self.exp_avg_sq = torch.zeros_like(self.params.data)
         self.step_dev = torch.zeros(4, dtype=F32, device=self.device)      # [0] Adam step count, [1] ticket of the fused optimiser
         self.ws = None
-        self.structs = [None, None]      # two structure slots: the pass for batch i+1 overlaps step i
+        self.structs = [None] * self.STRUCT_SLOTS     # structure slots: passes of the next batches overlap step i
         self._last_struct = None
         self._graphs = {}
         self._staging = {}
@@ -390,7 +392,7 @@ class Engine(object):
             self.ws.loss = self._loss_slot
             self.ws.pred = self._grads_full[n + 4:].view(nb, self.spec.out)
             ne_attr = 1 if self.spec.kind == 'sgat' else 0
-            self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(2)]
+            self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(self.STRUCT_SLOTS)]
             self._graphs.clear()
         return self.ws
 
@@ -722,13 +724,13 @@ class Engine(object):
     def upload(self, pb, slot=0, sslot=None):
         """ONE host->device copy of a ``PackedBatch`` into a persistent device staging buffer
         (one per layout and slot, so CUDA-graph replays see fixed addresses).  Returns a
-        DeviceBatch of views into it; its structure slot is ``sslot`` (default ``slot & 1``)."""
+        DeviceBatch of views into it; its structure slot is ``sslot`` (default ``slot % STRUCT_SLOTS``)."""
         dev = self._staging.get((pb.layout_key(), slot))
         if dev is None:
             dev = torch.empty(pb.capacity_numel, dtype=F32, device=self.device)
             self._staging[(pb.layout_key(), slot)] = dev
         dev[:pb.numel].copy_(pb.buf, non_blocking=True)
-        sslot = (slot & 1) if sslot is None else int(sslot)
+        sslot = (slot % self.STRUCT_SLOTS) if sslot is None else int(sslot)
         ck = (pb.layout_key(), slot, sslot, pb.has_y)
         d = self._dbatch.get(ck)
         if d is None:
@@ -811,13 +813,17 @@ class Engine(object):
 
     def _pipeline_state(self):
         if self._copy_stream is None:
+            ns = self.STRUCT_SLOTS
             self._copy_stream = torch.cuda.Stream(self.device)
-            self._prep_stream = torch.cuda.Stream(self.device)
+            # two structure streams: the passes of batches i+1 and i+2 run side by side (they are latency
+            # bound, one CTA per graph, and leave most SMs idle)
+            self._prep_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            self._prep_stream = self._prep_streams[0]
             ev = torch.cuda.Event
-            self._slot_free = [ev(), ev()]                  # structure slot released by the step that read it
-            self._slot_ready = [ev(), ev()]                 # structure pass of the slot finished
-            self._stage_free = [ev(), ev(), ev()]           # staging buffer released by the step that read it
-            self._stage_copied = [ev(), ev(), ev()]         # H2D copy into the staging buffer finished
+            self._slot_free = [ev() for _ in range(ns)]     # structure slot released by the step that read it
+            self._slot_ready = [ev() for _ in range(ns)]    # structure pass of the slot finished
+            self._stage_free = [ev() for _ in range(ns)]    # staging buffer released by the step that read it
+            self._stage_copied = [ev() for _ in range(ns)]  # H2D copy into the staging buffer finished
         return self._copy_stream
 
     def _prepare_any(self, d):
@@ -836,9 +842,10 @@ class Engine(object):
         Returns (losses [n], preds list)."""
         main = torch.cuda.current_stream(self.device)
         cs = self._pipeline_state()
-        ps = self._prep_stream
+        ns = self.STRUCT_SLOTS
         cs.wait_stream(main)
-        ps.wait_stream(main)
+        for ps in self._prep_streams:
+            ps.wait_stream(main)
         outs = []
         was_training = self.training
         self.train(train)
@@ -847,16 +854,18 @@ class Engine(object):
         width = 4 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
         host_all = torch.empty(max(len(packed_batches), 1), width, dtype=F32, pin_memory=True)
         for i, pb in enumerate(packed_batches):
-            # three-stage pipeline: H2D copy of batch i+2 | structure pass of batch i+1 | step of batch i
-            stg, slot = i % 3, i & 1
+            # pipeline: H2D copies and structure passes of the next batches (up to STRUCT_SLOTS - 1 ahead, on the
+            # copy stream and two alternating structure streams) | step of batch i
+            stg = slot = i % ns
+            ps = self._prep_streams[i & 1]
             with torch.cuda.stream(cs):
-                if i >= 3:
+                if i >= ns:
                     cs.wait_event(self._stage_free[stg])
                 d = self.upload(pb, stg, slot)
                 self._stage_copied[stg].record(cs)
             with torch.cuda.stream(ps):
                 ps.wait_event(self._stage_copied[stg])
-                if i >= 2:
+                if i >= ns:
                     ps.wait_event(self._slot_free[slot])
                 self._prepare_any(d)
                 self._slot_ready[slot].record(ps)
@@ -884,27 +893,30 @@ class Engine(object):
     def train_resident(self, dbatches, steps=None, B_global=None):
         """Training steps over batches already resident in HBM (``upload``-ed DeviceBatches, e.g. a
         data set cached on the device across epochs), cycling through ``dbatches`` for ``steps``
-        steps.  The structure pass of step i+1 runs on a side stream while step i computes;
-        consecutive batches must sit in different structure slots (``upload(pb, slot)`` with
-        alternating slot parity).  No host synchronisation.  Returns (loss, pred) of the last step."""
+        steps.  The structure passes of the next batches run on two side streams while step i
+        computes (``upload(pb, slot)`` spreads the batches over ``STRUCT_SLOTS`` structure slots;
+        a slot is rewritten only after the step that read it).  No host synchronisation.  Returns
+        (loss, pred) of the last step."""
         n = len(dbatches) if steps is None else steps
         main = torch.cuda.current_stream(self.device)
-        cs = self._pipeline_state()
-        cs.wait_stream(main)
+        self._pipeline_state()
+        for ps in self._prep_streams:
+            ps.wait_stream(main)
+        used = set()
         out = None
         for i in range(n):
             d = dbatches[i % len(dbatches)]
             slot = d.sslot
-            if i > 0 and dbatches[(i - 1) % len(dbatches)].sslot == slot:
-                raise DrgnnError('train_resident: consecutive batches share a structure slot')
-            with torch.cuda.stream(cs):
-                if i >= 2:
-                    cs.wait_event(self._slot_free[slot])
+            ps = self._prep_streams[i & 1]
+            with torch.cuda.stream(ps):
+                if slot in used:
+                    ps.wait_event(self._slot_free[slot])       # the step that last read this slot has finished
                 self._prepare_any(d)
-                self._slot_ready[slot].record(cs)
+                self._slot_ready[slot].record(ps)
             main.wait_event(self._slot_ready[slot])
             out = self.step(d, B_global=B_global, prepared=True)
             self._slot_free[slot].record(main)
+            used.add(slot)
         return out
 
     def validate(self):

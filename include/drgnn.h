@@ -363,6 +363,11 @@ typedef struct drgnn_ginet_step_args {
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
 int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream);
+/* diagnostic: SM clock (clock64) at the phase boundaries of the CTA that ran graph 0 in the last
+ * per-graph launch: [0] start, [1] staged, [2] AX, [3] Z1, [4] P1, [5] AP, [6] Z2, [7] P2, [8] R+fc1,
+ * [9] fc2, [10] loss, [11] head backward, [12] dZ2 staged, [13] dW2/dAP, [14] dP1, [15] dZ1 staged,
+ * [16] dW1 (end).  Synchronises the device. */
+int drgnn_debug_phase_cycles(uint64_t* out32);
 
 /* ---- multi-GPU: gradient exchange over NVLink peer memory fused with the optimiser ----
  * Replaces, on every rank, the sequence  [reduce per-graph rows] -> torch.distributed.all_reduce(flat

@@ -49,6 +49,17 @@ def main():
         e.record()
         torch.cuda.synchronize()
         t_pipe = 1e3 * s.elapsed_time(e) / n
+        if graph:
+            import ctypes
+            from deeprank_gnn_b200 import _lib
+            eng.step(ds[0], prepared=True)
+            ph = (ctypes.c_uint64 * 32)()
+            _lib.check(_lib.load().drgnn_debug_phase_cycles(ph), 'phase')
+            names = ['stage', 'AX', 'Z1', 'P1', 'AP', 'Z2', 'P2', 'R', 'fc1', 'fc2', 'loss+headbwd+dR', 'dZ2stage',
+                     'dW2/dAP', 'dP1', 'dZ1stage', 'dW1']
+            tot = ph[16] - ph[0]
+            print('graph-step kernel, CTA of graph 0: %d cycles total' % tot)
+            print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
         print('%s graph=%s: prep %.1f us | step (after prep) %.1f us | serial %.1f us | pipelined %.1f us'
               % (name, graph, t_prep, t_step, t_serial, t_pipe))
 
