@@ -129,7 +129,7 @@ class GinetStepArgs(C.Structure):
         ('drop_p', C.c_float), ('seed', C.c_uint32),
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
-        ('skip_reduce', C.c_int32), ('reserved1', C.c_int32),
+        ('skip_reduce', C.c_int32), ('flags', C.c_int32), ('max_e', C.c_int32), ('variant', C.c_int32),
     ]
 
 
@@ -198,7 +198,10 @@ _SIGNATURES = {
     'drgnn_ginet_fused_bwd': (C.c_int, [C.POINTER(GinetFusedArgs), VP]),
     'drgnn_ginet_step_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     'drgnn_ginet_step': (C.c_int, [C.POINTER(GinetStepArgs), VP]),
+    'drgnn_ginet_step2_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    'drgnn_ginet_step_last_variant': (C.c_int, []),
     'drgnn_debug_phase_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
+    'drgnn_debug_structure_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),
     'drgnn_relu_mask': (C.c_int, [VP, _i32, VP, _i32, _i32, VP, _i32, VP, _i32, VP]),

@@ -18,6 +18,7 @@
 // Dense products use the CTA-level tile_gemm (8 x 4 register tiles over transposed shared-memory
 // operands); gathers read neighbour rows from shared memory; indices come from the structure pass
 // (L2 resident, just written).  GINet has no bias, no self term, unit edge weights (alpha == 1).
+#include <cooperative_groups.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -567,6 +568,8 @@ __global__ void __launch_bounds__(256) ginet_wgrad_reduce_kernel(const float* __
   else dW2[e - E1] = s;
 }
 
+#include "fused_step2.cuh"
+
 static inline bool fused_shapes_ok(const drgnn_ginet_fused_args& a) {
   const int C1 = a.nb * a.h1, C2 = a.nb * a.h2;
   return a.F % 4 == 0 && a.h1 % 4 == 0 && a.h2 % 8 == 0 && C1 % 8 == 0 && C2 % 4 == 0 && a.nb >= 1 && a.max_n > 0 &&
@@ -662,6 +665,21 @@ extern "C" int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2
   return bytes;
 }
 
+extern "C" int64_t drgnn_ginet_step2_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
+                                                int32_t max_e, int32_t Hd, int32_t out) {
+  if (F <= 0 || h1 <= 0 || h2 <= 0 || max_n <= 0 || max_k <= 0 || max_q <= 0 || max_e <= 0 || Hd <= 0 || out <= 0)
+    return DRGNN_ERR_INVALID;
+  if (F % 4 || h1 % 4 || h2 % 4 || (2 * h2 * Hd) % 4) return DRGNN_ERR_UNSUPPORTED;
+  // keep the word count far from int overflow before planning
+  if ((int64_t)max_n * (F + h1) > (1 << 24) || max_e > (1 << 24) || (int64_t)Hd * h2 > (1 << 22)) return DRGNN_ERR_UNSUPPORTED;
+  const int64_t bytes = 4 * (int64_t)step2_plan(F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
+  if (bytes > device_info().smem_optin - 1024) return DRGNN_ERR_UNSUPPORTED;
+  return bytes;
+}
+
+static thread_local int g_step_variant = 0;
+extern "C" int drgnn_ginet_step_last_variant(void) { return g_step_variant; }
+
 extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   DRGNN_REQUIRE(s != nullptr, "ginet_step: args is NULL");
   const drgnn_ginet_fused_args* a = &s->g;
@@ -679,7 +697,33 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
     DRGNN_REQUIRE(!s->fuse_adam || (s->adam_p && s->adam_m && s->adam_v && s->step_dev), "ginet_step: fuse_adam needs the Adam buffers");
   }
   DRGNN_REQUIRE(s->keep || s->drop_p <= 0.f || s->step_dev, "ginet_step: hashed dropout needs step_dev");
+  DRGNN_REQUIRE(s->variant >= 0 && s->variant <= 2, "ginet_step: bad variant %d", s->variant);
   if (a->B == 0) return DRGNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- cluster kernel: a pair of CTAs per graph, one branch each, everything in shared memory
+  int64_t smem2 = -1;
+  if (s->variant != 1 && step2_shapes_ok(*s) && ((uintptr_t)a->x % 16) == 0 && ((uintptr_t)s->fc1_w % 16) == 0)
+    smem2 = drgnn_ginet_step2_smem_bytes(a->F, a->h1, a->h2, a->max_n, a->max_k, a->max_q, s->max_e, s->Hd, s->out);
+  if (s->variant == 2 && smem2 < 0)
+    return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: the cluster kernel does not support this shape (nb %d, max_n %d, max_e %d)",
+                a->nb, a->max_n, s->max_e);
+  if (smem2 >= 0) {
+    static thread_local int64_t configured2 = -1;
+    if (smem2 > configured2) {
+      DRGNN_CHECK_CUDA(cudaFuncSetAttribute(ginet_graph_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)device_info().smem_optin - 1024));
+      configured2 = device_info().smem_optin - 1024;
+    }
+    ginet_graph_step2_kernel<<<2 * a->B, S2_THREADS, smem2, st>>>(*s);
+    DRGNN_CHECK_LAUNCH("ginet_graph_step2_kernel");
+    g_step_variant = 2;
+    if (!s->forward_only && s->task != 0 && !s->skip_reduce) {
+      ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(*s);
+      DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
+    }
+    return DRGNN_OK;
+  }
+  g_step_variant = 1;
   const int64_t smem = drgnn_ginet_step_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, s->Hd, s->out);
   if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: a graph of %d nodes does not fit shared memory", a->max_n);
   static thread_local int64_t configured = -1;
@@ -691,7 +735,6 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   drgnn_ginet_step_args k = *s;
   const int64_t head = 4 * (int64_t)(2 * a->nb * a->h2 + 2 * s->Hd + s->out + 8);
   k.head_off = (int32_t)((smem - head) / 4);
-  cudaStream_t st = (cudaStream_t)stream;
   ginet_graph_step_kernel<<<a->B, FU_THREADS, smem, st>>>(k);
   DRGNN_CHECK_LAUNCH("ginet_graph_step_kernel");
   if (!s->forward_only && s->task != 0 && !s->skip_reduce) {

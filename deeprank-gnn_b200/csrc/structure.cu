@@ -19,6 +19,13 @@
 
 namespace drgnn {
 
+// Diagnostic: SM clock at the section boundaries of the CTA of graph 0 (drgnn_debug_structure_cycles).
+__device__ unsigned long long g_sphase[32];
+#define DRGNN_SPHASE(i)                                                         \
+  do {                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_sphase[i] = (unsigned long long)clock64(); \
+  } while (0)
+
 static constexpr int kThreads = 512;
 static constexpr int kWarps = kThreads / 32;
 static constexpr int kCapWords = 1024;
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   const int e0 = io.edge_ptr[g], m = io.edge_ptr[g + 1] - e0;
   const int ne = io.ne;
 
+  DRGNN_SPHASE(0);
   // ---- 1. local edge list ----
   for (int e = t; e < m; e += T) {
     long long r = ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
@@ -250,6 +258,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   }
   __syncthreads();
 
+  DRGNN_SPHASE(1);
   // ---- 2. CSR by destination (row) ----
   csr_build(erow, m, n, ptrR, slotR, wsum);
   for (int i = t; i <= n; i += T) io.rowptr0[n0 + i] = e0 + ptrR[i];
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     io.eid0[e0 + p] = e0 + e;
     if (io.w0csr) io.w0csr[e0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
   }
+  DRGNN_SPHASE(2);
   // ---- 3. CSC (transposed graph) ----
   csr_build(ecol, m, n, ptrC, slotC, wsum);
   for (int i = t; i <= n; i += T) io.cscptr0[n0 + i] = e0 + ptrC[i];
@@ -270,16 +280,19 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   }
   __syncthreads();
 
+  DRGNN_SPHASE(3);
   // ---- 4. relabel level-0 clusters ----
   long long cmin, cmax;
   const int K = relabel(io.cluster0, n0, io.idx32, n, dense0, cbits, cpre, wsum, red, io.status, &cmin, &cmax);
   for (int i = t; i < n; i += T) io.cl0[n0 + i] = dense0[i];  // local; finalize adds the graph offset
 
+  DRGNN_SPHASE(4);
   // ---- 5. members of every cluster (ascending node id) ----
   csr_build(dense0, n, K, mptr, mem, wsum);
   for (int k = t; k <= K; k += T) S.mptr0[n0 + g + k] = mptr[k];
   for (int p = t; p < n; p += T) io.cmem0[n0 + p] = n0 + mem[p];
 
+  DRGNN_SPHASE(5);
   // ---- 6. coarsened edges: per pooled row a column bitmap -> sorted unique columns ----
   uint16_t* pcol = slotC;  // CSC slots are dead now
   const int W1 = (K + 31) >> 5;
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   }
   __syncthreads();
 
+  DRGNN_SPHASE(6);
   // ---- 7. CSC of the coarsened graph ----
   int* ptrC1 = ptrC;
   uint16_t* slotC1 = slotR;  // level-0 CSR slots are dead now
@@ -373,6 +387,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   }
   __syncthreads();
 
+  DRGNN_SPHASE(7);
   // ---- 8. level-1 clustering ----
   int K1 = 0, c1len = 0;
   if (io.cluster1 != nullptr) {
@@ -390,6 +405,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     for (int p = t; p < c1len; p += T) S.mem1[c0 + p] = mem1[p];
   }
 
+  DRGNN_SPHASE(8);
   if (t == 0) {
     int32_t* gs = io.gstat + 8 * g;
     gs[0] = K;
@@ -611,6 +627,12 @@ extern "C" int drgnn_structure_build(const drgnn_structure_io* io, void* stream)
   DRGNN_CHECK_LAUNCH("graph_local_kernel");
   graph_finalize_kernel<<<io->B, 256, 0, st>>>(*io);
   DRGNN_CHECK_LAUNCH("graph_finalize_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_debug_structure_cycles(uint64_t* out32) {
+  DRGNN_REQUIRE(out32 != nullptr, "debug_structure_cycles: NULL");
+  DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_sphase, sizeof(unsigned long long) * 32));
   return DRGNN_OK;
 }
 

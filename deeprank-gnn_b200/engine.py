@@ -279,6 +279,8 @@ class Engine(object):
         self._all_done = False
         self._adam_done = False
         self.fuse_adam = True
+        self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
+        self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
         self.seed = 0x5EED if seed is None else int(seed)
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
@@ -494,7 +496,8 @@ class Engine(object):
                                step_dev=self.step_dev,
                                adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
                                          beta2=self.betas[1], eps=self.eps) if fuse_adam else None,
-                               skip_reduce=use_comm)
+                               skip_reduce=use_comm, max_e=d.max_e, mirror=self.keep_intermediates,
+                               variant=self.step_variant)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._adam_done = fuse_adam
                 if use_comm:

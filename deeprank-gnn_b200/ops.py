@@ -437,9 +437,11 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
-               drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False):
+               drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
-    ``ginet_fused_args``."""
+    ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
+    kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
+    intermediates to global memory too; ``variant`` 1 / 2 forces the single-CTA / cluster kernel."""
     require_cuda(fc1_w, fc1_b, fc2_w, fc2_b, pred, y, y_class, class_w, keep, loss, partial, grads)
     s = GinetStepArgs()
     s.g = fa
@@ -463,9 +465,19 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
         s.adam_p, s.adam_m, s.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
         s.lr, s.beta1, s.beta2, s.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
     s.skip_reduce = 1 if skip_reduce else 0
+    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0), int(variant)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     if skip_reduce or forward_only:
         _lib.kernel_count -= 1          # only the per-graph kernel was launched
+
+
+def ginet_step_last_variant():
+    """1 = single-CTA kernel, 2 = cluster kernel: what the last ``ginet_step`` of this thread launched."""
+    return int(_lib.load().drgnn_ginet_step_last_variant())
+
+
+def ginet_step2_smem_bytes(F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
+    return int(_lib.load().drgnn_ginet_step2_smem_bytes(*[int(v) for v in (F, h1, h2, max_n, max_k, max_q, max_e, Hd, out)]))
 
 
 def peer_reduce_adam(comm, grads, n_params, n_sum, partial=None, B=0, adam=None, step_dev=None):

@@ -358,16 +358,31 @@ typedef struct drgnn_ginet_step_args {
   float* adam_p; float* adam_m; float* adam_v; float* step_dev;
   /* skip_reduce != 0: stop after the per-graph launch (partial rows written); the caller reduces
    * them itself, e.g. with drgnn_peer_reduce_adam on several GPUs */
-  int32_t skip_reduce; int32_t reserved1;
+  int32_t skip_reduce;
+  /* flags bit 0: the cluster kernel also mirrors the intermediates (Zin1, Z1, arg0, Zin2, Z2, arg1)
+   * to global memory (it keeps them in shared memory; the single-CTA kernel always stores them) */
+  int32_t flags;
+  /* max_e: host bound of the directed edges of one graph (> 0 enables the cluster kernel: a pair of
+   * CTAs per graph, one GINet branch each, nb == 2).  variant: 0 = pick (cluster kernel when it
+   * fits shared memory, else single CTA), 1 = single-CTA kernel, 2 = cluster kernel or error. */
+  int32_t max_e; int32_t variant;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
 int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream);
+/* shared memory of one CTA of the cluster kernel (<0: unsupported shape / does not fit) and the
+ * variant (1 / 2) the last drgnn_ginet_step call of this thread launched (0: none yet) */
+int64_t drgnn_ginet_step2_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
+                                     int32_t max_e, int32_t Hd, int32_t out);
+int drgnn_ginet_step_last_variant(void);
 /* diagnostic: SM clock (clock64) at the phase boundaries of the CTA that ran graph 0 in the last
  * per-graph launch: [0] start, [1] staged, [2] AX, [3] Z1, [4] P1, [5] AP, [6] Z2, [7] P2, [8] R+fc1,
  * [9] fc2, [10] loss, [11] head backward, [12] dZ2 staged, [13] dW2/dAP, [14] dP1, [15] dZ1 staged,
  * [16] dW1 (end).  Synchronises the device. */
 int drgnn_debug_phase_cycles(uint64_t* out32);
+/* same for the structure pass (graph_local_kernel): [0] start, [1] edge list, [2] CSR, [3] CSC,
+ * [4] relabel, [5] members, [6] coarsened edges, [7] coarsened CSC, [8] level-1 clustering (end) */
+int drgnn_debug_structure_cycles(uint64_t* out32);
 
 /* ---- multi-GPU: gradient exchange over NVLink peer memory fused with the optimiser ----
  * Replaces, on every rank, the sequence  [reduce per-graph rows] -> torch.distributed.all_reduce(flat

@@ -215,23 +215,28 @@ def test_mathmode_tf32x3_within_tolerance(lib):
         ops.default_math = old
 
 
-@pytest.mark.parametrize('fused_head', [True, False])
-def test_fused_per_graph_kernels_equal_op_by_op_path(lib, fused_head):
+@pytest.mark.parametrize('fused_head,variant', [(True, 1), (True, 2), (False, 1)])
+def test_fused_per_graph_kernels_equal_op_by_op_path(lib, fused_head, variant):
     """GINet: per-graph fused kernels (csrc/fused.cu) vs the op-by-op launches.  fused_head=True is
-    the whole-step kernel (forward + head + loss + backward in one launch), False the fused forward /
-    backward kernels around the op-level head.  Intermediates are bit-identical (same summation
-    orders); weight gradients agree to fp32 summation order."""
-    from deeprank_gnn_b200 import synthetic
+    the whole-step kernel (forward + head + loss + backward in one launch; variant 1 = one CTA per
+    graph, variant 2 = a cluster of two CTAs per graph, one branch each, everything in shared
+    memory), False the fused forward / backward kernels around the op-level head.  Intermediates
+    are bit-identical (same summation orders); weight gradients agree to fp32 summation order."""
+    from deeprank_gnn_b200 import ops, synthetic
     from deeprank_gnn_b200.engine import Engine
-    graphs = synthetic.make_graphs(dict(nodes=(30, 260), edges_per_node=5, feat=32), count=21, seed=13)
+    nodes = (30, 260) if variant == 1 else (5, 200)
+    graphs = synthetic.make_graphs(dict(nodes=nodes, edges_per_node=5, feat=32), count=21, seed=13)
     d = _device_batch(graphs)
     e_o = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_graph=False, fused_head=False)
     e_f = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_head=fused_head)
+    e_f.step_variant, e_f.keep_intermediates = variant, True
     assert e_f._use_fused_graph(d) and not e_o._use_fused_graph(d)
     for step in range(3):
         lo, po = e_o.step(d)
         lf, pf = e_f.step(d)
         e_f.validate()
+        if fused_head:
+            assert ops.ginet_step_last_variant() == variant
         if step == 0:
             N, (K0, _E1, K1) = d.N, e_o.structs[0].sync_counts()
             for name in ('Zin1', 'Z1'):
@@ -272,3 +277,58 @@ def test_whole_step_kernel_classification_and_dropout(lib):
     pe = e_f.eval().forward(d)
     po2 = e_o.eval().forward(d)
     torch.testing.assert_close(pe, po2, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('task', ['reg', 'class'])
+def test_cluster_step_kernel_equals_single_cta_kernel(lib, task):
+    """The two whole-step kernels on the same batch: predictions / loss bit-identical (the forward
+    and the head keep every summation order), gradients to fp32 summation order (split-K weight
+    gradients), hashed dropout identical, several optimiser steps stay together."""
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs('cfg2', count=16, seed=77)
+    kw = dict(device='cuda:0', seed=11, lr=1e-3)
+    classes = None
+    if task == 'class':
+        for i, g in enumerate(graphs):
+            g.y = torch.tensor([float(i % 2)])
+        kw.update(task='class', class_weights=torch.tensor([0.7, 1.3]))
+        classes = [0, 1]
+    d = _device_batch(graphs, classes=classes)
+    out = 2 if task == 'class' else 1
+    inv = None if task == 'reg' else 1.0 / float(kw['class_weights'][d.y_class.cpu()].sum())
+    e1 = Engine('GINet', 32, out, 1, **kw)
+    e2 = Engine('GINet', 32, out, 1, **kw)
+    e1.step_variant, e2.step_variant = 1, 2
+    for step in range(4):
+        l1, p1 = e1.step(d, inv_norm=inv)
+        assert ops.ginet_step_last_variant() == 1
+        l2, p2 = e2.step(d, inv_norm=inv)
+        assert ops.ginet_step_last_variant() == 2
+        e1.validate(), e2.validate()
+        if step == 0:
+            assert torch.equal(p1, p2)
+            torch.testing.assert_close(l1, l2, rtol=1e-6, atol=1e-7)
+            g1, g2 = e1.named_grads(), e2.named_grads()
+            for name in g1:
+                torch.testing.assert_close(g2[name], g1[name], rtol=1e-3, atol=1e-6, msg=name)
+        torch.testing.assert_close(p2, p1, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(e2.params.data, e1.params.data, rtol=1e-3, atol=1e-4)
+    # scoring (forward only) through the cluster kernel
+    s1, s2 = e1.eval().forward(d), e2.eval().forward(d)
+    torch.testing.assert_close(s2, s1, rtol=1e-3, atol=1e-4)
+
+
+def test_cluster_step_kernel_falls_back_when_a_graph_does_not_fit(lib):
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.engine import Engine
+    from deeprank_gnn_b200._lib import DrgnnError
+    graphs = synthetic.make_graphs(dict(nodes=(250, 300), edges_per_node=5, feat=32), count=4, seed=3)
+    d = _device_batch(graphs)
+    assert ops.ginet_step2_smem_bytes(32, 16, 32, d.max_n, d.max_k0, d.max_k1, d.max_e, 128, 1) < 0
+    e = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1)
+    e.step(d)
+    assert ops.ginet_step_last_variant() == 1
+    e.step_variant = 2
+    with pytest.raises(DrgnnError):
+        e.step(d)

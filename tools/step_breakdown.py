@@ -60,6 +60,10 @@ def main():
             tot = ph[16] - ph[0]
             print('graph-step kernel, CTA of graph 0: %d cycles total' % tot)
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
+            _lib.check(_lib.load().drgnn_debug_structure_cycles(ph), 'sphase')
+            snames = ['edges', 'CSR', 'CSC', 'relabel', 'members', 'coarsen', 'CSC1', 'level1']
+            print('structure kernel, CTA of graph 0: %d cycles total' % (ph[8] - ph[0]))
+            print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(snames)))
         print('%s graph=%s: prep %.1f us | step (after prep) %.1f us | serial %.1f us | pipelined %.1f us'
               % (name, graph, t_prep, t_step, t_serial, t_pipe))
 
