@@ -508,14 +508,20 @@ __global__ void __launch_bounds__(FU_THREADS, 1) ginet_graph_step_kernel(const d
   DRGNN_PHASE(16);
 }
 
-// grads[e] = sum over graphs (ascending) of partial[g][e]; the slot behind the parameters is the loss.
+// grads[e] = sum over graphs of partial[g][e]; the slot behind the parameters is the loss.
+// A block owns 32 consecutive elements; its 8 warps each sum one contiguous eighth of the graphs
+// (ascending, all loads of a thread independent and in flight together), the eight partial sums are
+// combined in ascending order: a fixed summation tree, deterministic for a given batch size.
 // With fuse_adam the torch.optim.Adam update of element e follows in the same thread (single-GPU
 // runs: no all-reduce sits between the two); the last block to finish bumps the step counter
 // (ticket in step_dev[1]) so that no thread of this launch can observe the new value.
-__global__ void __launch_bounds__(256) ginet_step_reduce_kernel(const drgnn_ginet_step_args s) {
+static constexpr int RED_SPLITS = 8;
+__global__ void __launch_bounds__(32 * RED_SPLITS) ginet_step_reduce_kernel(const drgnn_ginet_step_args s) {
   __shared__ float sh[3];
+  __shared__ float psum[RED_SPLITS][32];
   __shared__ bool is_last;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
   const int B = s.g.B, n = s.n_params;
   if (s.fuse_adam && threadIdx.x == 0) {
     const float st = s.step_dev[0] + 1.f;
@@ -523,11 +529,29 @@ __global__ void __launch_bounds__(256) ginet_step_reduce_kernel(const drgnn_gine
     sh[1] = 1.f - (float)pow((double)s.beta1, (double)st);
     sh[2] = 1.f - (float)pow((double)s.beta2, (double)st);
   }
-  __syncthreads();
-  if (e <= n) {
+  {
+    const int gs = (B + RED_SPLITS - 1) / RED_SPLITS;
+    const int g0 = q * gs, g1 = min(B, g0 + gs);
     float acc = 0.f;
-#pragma unroll 8
-    for (int g = 0; g < B; ++g) acc += s.partial[(int64_t)g * s.partial_ld + e];
+    if (e <= n) {
+      const float* src = s.partial + e;
+      int g = g0;
+      for (; g + 8 <= g1; g += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[(int64_t)(g + u) * s.partial_ld];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; g < g1; ++g) acc += src[(int64_t)g * s.partial_ld];
+    }
+    psum[q][lane] = acc;
+  }
+  __syncthreads();
+  if (q == 0 && e <= n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < RED_SPLITS; ++u) acc += psum[u][lane];
     if (e < n) {
       s.grads[e] = acc;
       if (s.fuse_adam) {
@@ -718,7 +742,7 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
     DRGNN_CHECK_LAUNCH("ginet_graph_step2_kernel");
     g_step_variant = 2;
     if (!s->forward_only && s->task != 0 && !s->skip_reduce) {
-      ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(*s);
+      ginet_step_reduce_kernel<<<(s->n_params + 1 + 31) / 32, 32 * RED_SPLITS, 0, st>>>(*s);
       DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
     }
     return DRGNN_OK;
@@ -738,7 +762,7 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   ginet_graph_step_kernel<<<a->B, FU_THREADS, smem, st>>>(k);
   DRGNN_CHECK_LAUNCH("ginet_graph_step_kernel");
   if (!s->forward_only && s->task != 0 && !s->skip_reduce) {
-    ginet_step_reduce_kernel<<<(s->n_params + 1 + 255) / 256, 256, 0, st>>>(k);
+    ginet_step_reduce_kernel<<<(s->n_params + 1 + 31) / 32, 32 * RED_SPLITS, 0, st>>>(k);
     DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
   }
   return DRGNN_OK;

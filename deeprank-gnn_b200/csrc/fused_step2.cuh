@@ -113,52 +113,128 @@ __host__ __device__ inline Step2Plan step2_plan(int F, int h1, int h2, int max_n
   return p;
 }
 
-// C[m][n0..n0+3] = sum_k A[m*lda + k] * Bm[k*ldb + n]   (A row-major, K % 4 == 0, N % 4 == 0).
-// TM x 4 register tile; threads [t0, t0+nth) of the CTA take part.  Each output element is one fmaf
-// chain over ascending k.  out(m, n0, float4) is called for rows m < M only.
-template <int TM, typename FO>
-__device__ __forceinline__ void s2_gemm_rowA(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, int M,
-                                             int N, int K, int tid, int nth, FO out) {
-  const int mt = (M + TM - 1) / TM, nt = N >> 2;
+// The phases below are __noinline__ on purpose: the kernel runs every phase ONCE per CTA, so
+// straight-line inlined code is paid for in instruction-cache misses (the inlined version of this
+// kernel was 9.5 k SASS instructions = 150 KB, about 5 cycles per instruction, every phase fetch
+// bound).  Shared routines keep the code small and warm: the second and third use run from cache.
+
+// C[m][n..n+3] = (relu) sum_k A[m*lda + k] * Bm[k*ldb + n]   (A row-major, K % 4 == 0, N % 4 == 0).
+// 2 x 4 register tile; threads tid in [0, nth) take part.  Each output element is one fmaf chain
+// over ascending k (bit-identical to the op-level linear kernel).  Rows m >= M are not written.
+__device__ __noinline__ void s2_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, int M, int N, int K,
+                                     float* __restrict__ C, int ldc, int relu, int tid, int nth) {
+  const int mt = (M + 1) >> 1, nt = N >> 2;
+#pragma unroll 1
   for (int item = tid; item < mt * nt; item += nth) {
     const int mg = item / nt, ng = item - mg * nt;
-    float4 acc[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* ap = A + (mg * TM) * lda;
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    const float* ap = A + (mg * 2) * lda;
     const float* bp = Bm + ng * 4;
-#pragma unroll 2
+#pragma unroll 1
     for (int k = 0; k < K; k += 4) {
       const float4 b0 = *reinterpret_cast<const float4*>(bp + (k + 0) * ldb);
       const float4 b1 = *reinterpret_cast<const float4*>(bp + (k + 1) * ldb);
       const float4 b2 = *reinterpret_cast<const float4*>(bp + (k + 2) * ldb);
       const float4 b3 = *reinterpret_cast<const float4*>(bp + (k + 3) * ldb);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(ap + i * lda + k);
-        acc[i].x = fmaf(a.x, b0.x, acc[i].x); acc[i].y = fmaf(a.x, b0.y, acc[i].y);
-        acc[i].z = fmaf(a.x, b0.z, acc[i].z); acc[i].w = fmaf(a.x, b0.w, acc[i].w);
-        acc[i].x = fmaf(a.y, b1.x, acc[i].x); acc[i].y = fmaf(a.y, b1.y, acc[i].y);
-        acc[i].z = fmaf(a.y, b1.z, acc[i].z); acc[i].w = fmaf(a.y, b1.w, acc[i].w);
-        acc[i].x = fmaf(a.z, b2.x, acc[i].x); acc[i].y = fmaf(a.z, b2.y, acc[i].y);
-        acc[i].z = fmaf(a.z, b2.z, acc[i].z); acc[i].w = fmaf(a.z, b2.w, acc[i].w);
-        acc[i].x = fmaf(a.w, b3.x, acc[i].x); acc[i].y = fmaf(a.w, b3.y, acc[i].y);
-        acc[i].z = fmaf(a.w, b3.z, acc[i].z); acc[i].w = fmaf(a.w, b3.w, acc[i].w);
-      }
+      const float4 a0 = *reinterpret_cast<const float4*>(ap + k);
+      const float4 a1 = *reinterpret_cast<const float4*>(ap + lda + k);
+      acc0.x = fmaf(a0.x, b0.x, acc0.x); acc0.y = fmaf(a0.x, b0.y, acc0.y); acc0.z = fmaf(a0.x, b0.z, acc0.z); acc0.w = fmaf(a0.x, b0.w, acc0.w);
+      acc1.x = fmaf(a1.x, b0.x, acc1.x); acc1.y = fmaf(a1.x, b0.y, acc1.y); acc1.z = fmaf(a1.x, b0.z, acc1.z); acc1.w = fmaf(a1.x, b0.w, acc1.w);
+      acc0.x = fmaf(a0.y, b1.x, acc0.x); acc0.y = fmaf(a0.y, b1.y, acc0.y); acc0.z = fmaf(a0.y, b1.z, acc0.z); acc0.w = fmaf(a0.y, b1.w, acc0.w);
+      acc1.x = fmaf(a1.y, b1.x, acc1.x); acc1.y = fmaf(a1.y, b1.y, acc1.y); acc1.z = fmaf(a1.y, b1.z, acc1.z); acc1.w = fmaf(a1.y, b1.w, acc1.w);
+      acc0.x = fmaf(a0.z, b2.x, acc0.x); acc0.y = fmaf(a0.z, b2.y, acc0.y); acc0.z = fmaf(a0.z, b2.z, acc0.z); acc0.w = fmaf(a0.z, b2.w, acc0.w);
+      acc1.x = fmaf(a1.z, b2.x, acc1.x); acc1.y = fmaf(a1.z, b2.y, acc1.y); acc1.z = fmaf(a1.z, b2.z, acc1.z); acc1.w = fmaf(a1.z, b2.w, acc1.w);
+      acc0.x = fmaf(a0.w, b3.x, acc0.x); acc0.y = fmaf(a0.w, b3.y, acc0.y); acc0.z = fmaf(a0.w, b3.z, acc0.z); acc0.w = fmaf(a0.w, b3.w, acc0.w);
+      acc1.x = fmaf(a1.w, b3.x, acc1.x); acc1.y = fmaf(a1.w, b3.y, acc1.y); acc1.z = fmaf(a1.w, b3.z, acc1.z); acc1.w = fmaf(a1.w, b3.w, acc1.w);
     }
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-      if (mg * TM + i < M) out(mg * TM + i, ng * 4, acc[i]);
+    if (relu) {
+      acc0.x = acc0.x < 0.f ? 0.f : acc0.x; acc0.y = acc0.y < 0.f ? 0.f : acc0.y; acc0.z = acc0.z < 0.f ? 0.f : acc0.z; acc0.w = acc0.w < 0.f ? 0.f : acc0.w;
+      acc1.x = acc1.x < 0.f ? 0.f : acc1.x; acc1.y = acc1.y < 0.f ? 0.f : acc1.y; acc1.z = acc1.z < 0.f ? 0.f : acc1.z; acc1.w = acc1.w < 0.f ? 0.f : acc1.w;
+    }
+    const int m = mg * 2;
+    *reinterpret_cast<float4*>(C + m * ldc + ng * 4) = acc0;
+    if (m + 1 < M) *reinterpret_cast<float4*>(C + (m + 1) * ldc + ng * 4) = acc1;
+  }
+}
+
+// dst[i][4q..4q+3] = sum over the CSR entries p of row i of src[col[p] - nbase][4q..4q+3]  (ascending p:
+// the CPU scatter order).  The W4 lanes of a row share its index loads; rowptr / col hold global ids.
+__device__ __noinline__ void s2_gather(const int* __restrict__ rp, const int* __restrict__ col, int ebase, int nbase,
+                                       const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int W4,
+                                       int tid, int nth) {
+#pragma unroll 1
+  for (int item = tid; item < rows * W4; item += nth) {
+    const int i = item / W4, q4 = item - i * W4;
+    const int sb = rp[i] - ebase, se = rp[i + 1] - ebase;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int p = sb; p < se; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (col[p] - nbase) * lds + q4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dst + i * ldd + q4 * 4) = acc;
+  }
+}
+
+// Cluster max + argmax (global member id): first member wins ties, a NaN never wins, empty -> 0
+// (torch_scatter's CPU scatter_max; community_pooling.py:201, max_pool_x).
+__device__ __noinline__ void s2_cluster_max(const int* __restrict__ cmp, const int* __restrict__ cmem, int mbase, int nbase,
+                                            const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                            int* __restrict__ arg, int ldarg, int rows, int W4, int tid, int nth) {
+#pragma unroll 1
+  for (int item = tid; item < rows * W4; item += nth) {
+    const int k = item / W4, q4 = item - k * W4;
+    const int sb = cmp[k] - mbase, se = cmp[k + 1] - mbase;
+    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int4 am = make_int4(-1, -1, -1, -1);
+#pragma unroll 1
+    for (int p = sb; p < se; ++p) {
+      const int i = cmem[p];
+      const float4 v = *reinterpret_cast<const float4*>(src + (i - nbase) * lds + q4 * 4);
+      if (v.x > best.x) { best.x = v.x; am.x = i; }
+      if (v.y > best.y) { best.y = v.y; am.y = i; }
+      if (v.z > best.z) { best.z = v.z; am.z = i; }
+      if (v.w > best.w) { best.w = v.w; am.w = i; }
+    }
+    if (am.x < 0) best.x = 0.f;
+    if (am.y < 0) best.y = 0.f;
+    if (am.z < 0) best.z = 0.f;
+    if (am.w < 0) best.w = 0.f;
+    *reinterpret_cast<float4*>(dst + k * ldd + q4 * 4) = best;
+    *reinterpret_cast<int4*>(arg + k * ldarg + q4 * 4) = am;
+  }
+}
+
+// Backward of cluster max + ReLU: dst[i][c] = (arg[cl[i] - kbase][c] == self0 + i && z[i][c] > 0) ?
+// d[(cl[i] - kbase) * ldd + c] * scale : 0.   ldd == 0: one gradient row for every cluster (read-out mean).
+__device__ __noinline__ void s2_route(const int* __restrict__ cl, int kbase, const int* __restrict__ arg, int ldarg,
+                                      const float* __restrict__ z, int ldz, const float* __restrict__ d, int ldd, float scale,
+                                      float* __restrict__ dst, int lddst, int rows, int W4, int self0, int tid, int nth) {
+#pragma unroll 1
+  for (int item = tid; item < rows * W4; item += nth) {
+    const int i = item / W4, q4 = item - i * W4;
+    const int k = cl[i] - kbase;
+    const int4 am = *reinterpret_cast<const int4*>(arg + k * ldarg + q4 * 4);
+    const float4 zz = *reinterpret_cast<const float4*>(z + i * ldz + q4 * 4);
+    const float4 dd = *reinterpret_cast<const float4*>(d + k * ldd + q4 * 4);
+    const int me = self0 + i;
+    float4 v;
+    v.x = (am.x == me && zz.x > 0.f) ? dd.x * scale : 0.f;
+    v.y = (am.y == me && zz.y > 0.f) ? dd.y * scale : 0.f;
+    v.z = (am.z == me && zz.z > 0.f) ? dd.z * scale : 0.f;
+    v.w = (am.w == me && zz.w > 0.f) ? dd.w * scale : 0.f;
+    *reinterpret_cast<float4*>(dst + i * lddst + q4 * 4) = v;
   }
 }
 
 // Split-K partial products of C[m][n] = sum_{k<K} At[k*lda + m] * Bm[k*ldb + n]  (M % 4 == 0, N % 4 == 0):
 // split s in [0, KS) covers k in [s*chunk, min(K, (s+1)*chunk)) and stores its 4x4 tiles to
 // scratch[s][M][N].  s2_splitk_reduce sums the KS slices in ascending s.
-__device__ __forceinline__ void s2_splitk_partial(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb, int M,
-                                                  int N, int K, int KS, float* __restrict__ scratch, int tid, int nth) {
+__device__ __noinline__ void s2_splitk_partial(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb, int M,
+                                               int N, int K, int KS, float* __restrict__ scratch, int tid, int nth) {
   const int mt = M >> 2, nt = N >> 2, tiles = mt * nt;
   const int chunk = (K + KS - 1) / KS;
+#pragma unroll 1
   for (int item = tid; item < tiles * KS; item += nth) {
     const int s = item / tiles, tile = item - s * tiles;
     const int mg = tile / nt, ng = tile - mg * nt;
@@ -168,7 +244,7 @@ __device__ __forceinline__ void s2_splitk_partial(const float* __restrict__ At, 
     for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* ap = At + mg * 4;
     const float* bp = Bm + ng * 4;
-#pragma unroll 4
+#pragma unroll 2
     for (int k = kb; k < ke; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(ap + k * lda);
       const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
@@ -186,12 +262,41 @@ __device__ __forceinline__ void s2_splitk_partial(const float* __restrict__ At, 
     for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sp + i * N) = acc[i];
   }
 }
-__device__ __forceinline__ void s2_splitk_reduce(const float* __restrict__ scratch, int MN, int KS, float* __restrict__ dst, int tid,
-                                                 int nth) {
+__device__ __noinline__ void s2_splitk_reduce(const float* __restrict__ scratch, int MN, int KS, float* __restrict__ dst, int tid,
+                                              int nth) {
+#pragma unroll 1
   for (int e = tid; e < MN; e += nth) {
     float acc = 0.f;
+#pragma unroll 4
     for (int s = 0; s < KS; ++s) acc += scratch[(size_t)s * MN + e];
     dst[e] = acc;
+  }
+}
+
+// asynchronous copy of `count` 4-byte words global -> shared (any alignment)
+__device__ __noinline__ void s2_stage32(void* dst, const void* src, int count, int tid, int nth) {
+  const uint32_t d = s2_smem_u32(dst);
+  const char* g = reinterpret_cast<const char*>(src);
+#pragma unroll 1
+  for (int i = tid; i < count; i += nth)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * i), "l"(g + 4 * (size_t)i) : "memory");
+}
+// ... of `count` 16-byte words (both sides 16-byte aligned)
+__device__ __noinline__ void s2_stage128(void* dst, const void* src, int count, int tid, int nth) {
+  const uint32_t d = s2_smem_u32(dst);
+  const char* g = reinterpret_cast<const char*>(src);
+#pragma unroll 1
+  for (int i = tid; i < count; i += nth)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * i), "l"(g + 16 * (size_t)i) : "memory");
+}
+// rows x W4 float4 words of shared memory -> global memory (test mirror of the intermediates)
+__device__ __noinline__ void s2_mirror(const void* src, int lds, void* dst, int64_t ldd, int rows, int W4, int tid, int nth) {
+  const float* sp = reinterpret_cast<const float*>(src);
+  float* dp = reinterpret_cast<float*>(dst);
+#pragma unroll 1
+  for (int item = tid; item < rows * W4; item += nth) {
+    const int i = item / W4, q4 = item - i * W4;
+    *reinterpret_cast<float4*>(dp + i * ldd + q4 * 4) = *reinterpret_cast<const float4*>(sp + i * lds + q4 * 4);
   }
 }
 
@@ -248,12 +353,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   bool ok = n >= 0 && K >= 0 && Q >= 0 && n <= a.max_n && K <= a.max_k && Q <= a.max_q;
   int e00 = 0, E0 = 0, e10 = 0, E1 = 0, c10 = 0, m00 = 0, m10 = 0;
   if (ok) {
-    // feature tile and head weights first: they need nothing but n0 / n
-    {
-      const float4* src = reinterpret_cast<const float4*>(a.x + (int64_t)n0 * F);
-      float4* dst = reinterpret_cast<float4*>(xs);
-      for (int i = t; i < n * (F >> 2); i += T) s2_cp16(dst + i, src + i);
-    }
+    // the feature tile first: it needs nothing but n0 / n
+    s2_stage128(xs, a.x + (int64_t)n0 * F, n * (F >> 2), t, T);
     e00 = __ldg(a.rowptr0 + n0); E0 = __ldg(a.rowptr0 + n0 + n) - e00;
     e10 = __ldg(a.rowptr1 + k0); E1 = __ldg(a.rowptr1 + k0 + K) - e10;
     c10 = __ldg(a.cscptr1 + k0);
@@ -264,6 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     s2_wait<0>();
     if (t == 0) atomicOr(a.status, 64);
     if (train && r == 0)
+#pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
     return;
   }
@@ -271,38 +373,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   // arrive now, wait just before the exchange, so the barrier costs nothing.
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   // ---- group 0 (forward): index slices of both levels
-  for (int i = t; i <= n; i += T) s2_cp4(rp0 + i, a.rowptr0 + n0 + i);
-  for (int i = t; i < E0; i += T) s2_cp4(col0 + i, a.col0 + e00 + i);
-  for (int i = t; i <= K; i += T) s2_cp4(rp1 + i, a.rowptr1 + k0 + i);
-  for (int i = t; i < E1; i += T) s2_cp4(col1 + i, a.col1 + e10 + i);
-  for (int i = t; i <= K; i += T) s2_cp4(cmp0 + i, a.cmptr0 + k0 + i);
-  for (int i = t; i < n; i += T) s2_cp4(cmem0 + i, a.cmem0 + m00 + i);
-  for (int i = t; i <= Q; i += T) s2_cp4(cmp1 + i, a.cmptr1 + q0 + i);
-  for (int i = t; i < K; i += T) s2_cp4(cmem1 + i, a.cmem1 + m10 + i);
+  s2_stage32(rp0, a.rowptr0 + n0, n + 1, t, T);
+  s2_stage32(col0, a.col0 + e00, E0, t, T);
+  s2_stage32(rp1, a.rowptr1 + k0, K + 1, t, T);
+  s2_stage32(col1, a.col1 + e10, E1, t, T);
+  s2_stage32(cmp0, a.cmptr0 + k0, K + 1, t, T);
+  s2_stage32(cmem0, a.cmem0 + m00, n, t, T);
+  s2_stage32(cmp1, a.cmptr1 + q0, Q + 1, t, T);
+  s2_stage32(cmem1, a.cmem1 + m10, K, t, T);
   s2_commit();
   // ---- group 1 (head + backward): head weights, cluster ids, CSC of the coarsened graph
-  {
-    const float4* src = reinterpret_cast<const float4*>(s.fc1_w);
-    float4* dst = reinterpret_cast<float4*>(fc1w);
-    for (int i = t; i < (Hd * C2) >> 2; i += T) s2_cp16(dst + i, src + i);
-    for (int i = t; i < out * Hd; i += T) s2_cp4(fc2w + i, s.fc2_w + i);
-    if (s.fc1_b)
-      for (int i = t; i < Hd; i += T) s2_cp4(fc1b + i, s.fc1_b + i);
-    if (s.fc2_b)
-      for (int i = t; i < out; i += T) s2_cp4(fc2b + i, s.fc2_b + i);
-    if (train) {
-      for (int i = t; i < n; i += T) s2_cp4(cl0 + i, a.cl0 + n0 + i);
-      for (int i = t; i < K; i += T) s2_cp4(cl1 + i, a.cl1 + k0 + i);
-      for (int i = t; i <= K; i += T) s2_cp4(cscp1 + i, a.cscptr1 + k0 + i);
-      for (int i = t; i < E1; i += T) s2_cp4(cscr1 + i, a.cscrow1 + c10 + i);
-    }
+  s2_stage128(fc1w, s.fc1_w, (Hd * C2) >> 2, t, T);
+  s2_stage32(fc2w, s.fc2_w, out * Hd, t, T);
+  if (s.fc1_b) s2_stage32(fc1b, s.fc1_b, Hd, t, T);
+  if (s.fc2_b) s2_stage32(fc2b, s.fc2_b, out, t, T);
+  if (train) {
+    s2_stage32(cl0, a.cl0 + n0, n, t, T);
+    s2_stage32(cl1, a.cl1 + k0, K, t, T);
+    s2_stage32(cscp1, a.cscptr1 + k0, K + 1, t, T);
+    s2_stage32(cscr1, a.cscrow1 + c10, E1, t, T);
   }
   s2_commit();
   // ---- this branch's weights, transposed through registers
+#pragma unroll 1
   for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. -> w1t [F][H1]
     const int c = i / F, f = i - c * F;
     w1t[f * H1 + c] = __ldg(a.W1 + (int64_t)(co1 + c) * F + f);
   }
+#pragma unroll 1
   for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] group r -> w2 [H2][H1], w2t [H1][H2]
     const int o = i / H1, j = i - o * H1;
     const float v = __ldg(a.W2 + (int64_t)r * H2 * H1 + i);
@@ -310,8 +408,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     w2t[j * H2 + o] = v;
   }
   if (!s.fc1_b)
+#pragma unroll 1
     for (int i = t; i < Hd; i += T) fc1b[i] = 0.f;
   if (!s.fc2_b)
+#pragma unroll 1
     for (int i = t; i < out; i += T) fc2b[i] = 0.f;
   s2_wait<1>();
   __syncthreads();
@@ -319,105 +419,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;
   // ---- AX = A x : the F/4 lanes of a row share its edge list and read whole 16-byte-aligned feature rows
-  for (int item = t; item < n * F4; item += T) {
-    const int i = item / F4, q4 = item - i * F4;
-    const int sb = rp0[i] - e00, se = rp0[i + 1] - e00;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int p = sb; p < se; ++p) {
-      const int c = col0[p] - n0;
-      const float4 v = *reinterpret_cast<const float4*>(xs + c * F + q4 * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    *reinterpret_cast<float4*>(ax + i * LDX + q4 * 4) = acc;
-    if (mirror && r == 0) *reinterpret_cast<float4*>(a.Zin1 + (int64_t)(n0 + i) * F + q4 * 4) = acc;
-  }
+  s2_gather(rp0, col0, e00, n0, xs, F, ax, LDX, n, F4, t, T);
   __syncthreads();
   DRGNN_PHASE(2);
   // ---- Z1 = relu(AX W1_r^T)
-  s2_gemm_rowA<2>(ax, LDX, w1t, H1, n, H1, F, t, T, [&](int m, int c, float4 v) {
-    v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y; v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
-    *reinterpret_cast<float4*>(z1 + m * LDZ1 + c) = v;
-    if (mirror) *reinterpret_cast<float4*>(a.Z1 + (int64_t)(n0 + m) * C1 + co1 + c) = v;
-  });
+  s2_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, 1, t, T);
   __syncthreads();
   DRGNN_PHASE(3);
-  // ---- P1 = cluster max of Z1 (first member wins ties, a NaN never wins; community_pooling.py:201)
-  for (int item = t; item < K * H14; item += T) {
-    const int k = item / H14, q4 = item - k * H14;
-    const int sb = cmp0[k] - m00, se = cmp0[k + 1] - m00;
-    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-    int4 arg = make_int4(-1, -1, -1, -1);
-    for (int p = sb; p < se; ++p) {
-      const int i = cmem0[p];
-      const float4 v = *reinterpret_cast<const float4*>(z1 + (i - n0) * LDZ1 + q4 * 4);
-      if (v.x > best.x) { best.x = v.x; arg.x = i; }
-      if (v.y > best.y) { best.y = v.y; arg.y = i; }
-      if (v.z > best.z) { best.z = v.z; arg.z = i; }
-      if (v.w > best.w) { best.w = v.w; arg.w = i; }
-    }
-    if (arg.x < 0) best.x = 0.f;
-    if (arg.y < 0) best.y = 0.f;
-    if (arg.z < 0) best.z = 0.f;
-    if (arg.w < 0) best.w = 0.f;
-    *reinterpret_cast<float4*>(p1 + k * LDP + q4 * 4) = best;
-    *reinterpret_cast<int4*>(arg0 + k * H1 + q4 * 4) = arg;
-    if (mirror) *reinterpret_cast<int4*>(a.arg0 + (int64_t)(k0 + k) * C1 + co1 + q4 * 4) = arg;
-  }
+  // ---- P1 = cluster max of Z1 (community_pooling.py:201)
+  s2_cluster_max(cmp0, cmem0, m00, n0, z1, LDZ1, p1, LDP, arg0, H1, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(4);
   // ---- AP = A1 P1 on the coarsened graph
-  for (int item = t; item < K * H14; item += T) {
-    const int k = item / H14, q4 = item - k * H14;
-    const int sb = rp1[k] - e10, se = rp1[k + 1] - e10;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int p = sb; p < se; ++p) {
-      const int c = col1[p] - k0;
-      const float4 v = *reinterpret_cast<const float4*>(p1 + c * LDP + q4 * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    *reinterpret_cast<float4*>(ap + k * LDP + q4 * 4) = acc;
-    if (mirror) *reinterpret_cast<float4*>(a.Zin2 + (int64_t)(k0 + k) * C1 + co1 + q4 * 4) = acc;
-  }
+  s2_gather(rp1, col1, e10, k0, p1, LDP, ap, LDP, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(5);
   // ---- Z2 = relu(AP W2_r^T)
-  s2_gemm_rowA<2>(ap, LDP, w2t, H2, K, H2, H1, t, T, [&](int m, int o, float4 v) {
-    v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y; v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
-    *reinterpret_cast<float4*>(z2 + m * LDZ2 + o) = v;
-    if (mirror) *reinterpret_cast<float4*>(a.Z2 + (int64_t)(k0 + m) * C2 + co2 + o) = v;
-  });
+  s2_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, 1, t, T);
   __syncthreads();
   DRGNN_PHASE(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
-  for (int item = t; item < Q * H24; item += T) {
-    const int q = item / H24, q4 = item - q * H24;
-    const int sb = cmp1[q] - m10, se = cmp1[q + 1] - m10;
-    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-    int4 arg = make_int4(-1, -1, -1, -1);
-    for (int p = sb; p < se; ++p) {
-      const int k = cmem1[p];
-      const float4 v = *reinterpret_cast<const float4*>(z2 + (k - k0) * LDZ2 + q4 * 4);
-      if (v.x > best.x) { best.x = v.x; arg.x = k; }
-      if (v.y > best.y) { best.y = v.y; arg.y = k; }
-      if (v.z > best.z) { best.z = v.z; arg.z = k; }
-      if (v.w > best.w) { best.w = v.w; arg.w = k; }
-    }
-    if (arg.x < 0) best.x = 0.f;
-    if (arg.y < 0) best.y = 0.f;
-    if (arg.z < 0) best.z = 0.f;
-    if (arg.w < 0) best.w = 0.f;
-    *reinterpret_cast<float4*>(p2 + q * H2 + q4 * 4) = best;
-    *reinterpret_cast<int4*>(arg1 + q * H2 + q4 * 4) = arg;
-    if (mirror) *reinterpret_cast<int4*>(a.arg1 + (int64_t)(q0 + q) * C2 + co2 + q4 * 4) = arg;
-  }
+  s2_cluster_max(cmp1, cmem1, m10, k0, z2, LDZ2, p2, H2, arg1, H2, Q, H24, t, T);
   __syncthreads();
   DRGNN_PHASE(7);
+  if (mirror) {   // parity tests: the intermediates the single-CTA kernel leaves in global memory
+    if (r == 0) s2_mirror(ax, LDX, a.Zin1 + (int64_t)n0 * F, F, n, F4, t, T);
+    s2_mirror(z1, LDZ1, a.Z1 + (int64_t)n0 * C1 + co1, C1, n, H14, t, T);
+    s2_mirror(arg0, H1, a.arg0 + (int64_t)k0 * C1 + co1, C1, K, H14, t, T);
+    s2_mirror(ap, LDP, a.Zin2 + (int64_t)k0 * C1 + co1, C1, K, H14, t, T);
+    s2_mirror(z2, LDZ2, a.Z2 + (int64_t)k0 * C2 + co2, C2, K, H24, t, T);
+    s2_mirror(arg1, H2, a.arg1 + (int64_t)q0 * C2 + co2, C2, Q, H24, t, T);
+  }
   // ---- R[g] half = mean over the graph's level-1 clusters; both halves land in both CTAs (DSMEM)
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   {
     float* peer_rrow = cluster.map_shared_rank(rrow, (unsigned)(r ^ 1));
+#pragma unroll 1
     for (int c = t; c < H2; c += T) {
       float acc = 0.f;
       for (int q = 0; q < Q; ++q) acc += p2[q * H2 + c];
@@ -430,27 +467,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   s2_wait<0>();      // head weights / backward indices have landed (this thread's copies)
   cluster.sync();    // ... everybody's, and the peer's half of the read-out row
   DRGNN_PHASE(8);
-  // ---- fc1: warp per hidden unit, lanes over the read-out channels (both CTAs, identical results)
-  for (int j = warp; j < Hd; j += NW) {
-    float acc = 0.f;
-    for (int c = lane; c < C2; c += 32) acc = fmaf(rrow[c], fc1w[j * C2 + c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      acc += fc1b[j];
-      acc = acc < 0.f ? 0.f : acc;
-      if (s.keep) {
-        acc = s.keep[(int64_t)g * Hd + j] > 0.f ? acc * s.keep_scale : 0.f;
-      } else if (s.drop_p > 0.f) {
-        acc = hash_uniform(s.seed, drop_ctr, (uint32_t)(g * Hd + j)) >= s.drop_p ? acc * s.keep_scale : 0.f;
+  // ---- fc1 (both CTAs, identical results): a warp reduces 8 hidden units at once - 8 independent
+  // shuffle trees in flight instead of 8 dependent ones; per unit the arithmetic is the v1 chain
+  // (lanes over the read-out channels, xor butterfly), so predictions stay bit-identical.
+#pragma unroll 1
+  for (int jb = warp * 8; jb < Hd; jb += NW * 8) {
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = jb + u;
+      float av = 0.f;
+      if (j < Hd) {
+#pragma unroll 1
+        for (int c = lane; c < C2; c += 32) av = fmaf(rrow[c], fc1w[j * C2 + c], av);
       }
-      hrow[j] = acc;
+      acc[u] = av;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) mine = (lane == u) ? acc[u] : mine;
+    const int j = jb + lane;
+    if (lane < 8 && j < Hd) {
+      float v = mine + fc1b[j];
+      v = v < 0.f ? 0.f : v;
+      if (s.keep) {
+        v = s.keep[(int64_t)g * Hd + j] > 0.f ? v * s.keep_scale : 0.f;
+      } else if (s.drop_p > 0.f) {
+        v = hash_uniform(s.seed, drop_ctr, (uint32_t)(g * Hd + j)) >= s.drop_p ? v * s.keep_scale : 0.f;
+      }
+      hrow[j] = v;
     }
   }
   __syncthreads();
   DRGNN_PHASE(9);
   // ---- fc2: warp per output
+#pragma unroll 1
   for (int o = warp; o < out; o += NW) {
     float acc = 0.f;
+#pragma unroll 1
     for (int j = lane; j < Hd; j += 32) acc = fmaf(hrow[j], fc2w[o * Hd + j], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -467,15 +526,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     float lg = 0.f;
     if (s.task == 3) {
       float mx = prow[0];
+#pragma unroll 1
       for (int c = 1; c < out; ++c) mx = fmaxf(mx, prow[c]);
       float se = 0.f;
+#pragma unroll 1
       for (int c = 0; c < out; ++c) se += expf(prow[c] - mx);
       const float lse = mx + logf(se);
       const int tc = y_cls;
       const float w = s.class_w ? s.class_w[tc] : 1.f;
       lg = w * (lse - prow[tc]);
+#pragma unroll 1
       for (int c = 0; c < out; ++c) prow[c] = w * (expf(prow[c] - lse) - (c == tc ? 1.f : 0.f)) * s.inv_norm;
     } else {
+#pragma unroll 1
       for (int c = 0; c < out; ++c) {
         float p = prow[c], dp = 1.f;
         if (s.task == 2) {
@@ -492,100 +555,67 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   // ---- head backward: dh (all units, both CTAs); gradient rows of the hidden units [j0, j1) by CTA r
   const int j0 = r ? (Hd >> 1) : 0, j1 = r ? Hd : (Hd >> 1), nj = j1 - j0;
+#pragma unroll 1
   for (int j = t; j < Hd; j += T) {
     float acc = 0.f;
+#pragma unroll 1
     for (int o = 0; o < out; ++o) acc = fmaf(prow[o], fc2w[o * Hd + j], acc);
     acc = hrow[j] > 0.f ? acc * s.keep_scale : 0.f;
     dhrow[j] = acc;
     if (j >= j0 && j < j1) part[s.off_fc1b + j] = acc;
   }
+#pragma unroll 1
   for (int i = t; i < out * nj; i += T) {
     const int o = i / nj, j = j0 + (i - o * nj);
     part[s.off_fc2w + o * Hd + j] = prow[o] * hrow[j];
   }
   if (r == 0)
+  {
+#pragma unroll 1
     for (int o = t; o < out; o += T) part[s.off_fc2b + o] = prow[o];
+  }
   __syncthreads();
+#pragma unroll 1
   for (int i = t; i < nj * C2; i += T) {
     const int j = j0 + i / C2, c = i % C2;
     part[s.off_fc1w + j * C2 + c] = dhrow[j] * rrow[c];
   }
   // dR[c] of this branch's channels = sum_j dh[j] W1[j][co2 + c]: warps split the hidden units, fixed-order sum
+#pragma unroll 1
   for (int c = lane; c < H2; c += 32) {
     float acc = 0.f;
+#pragma unroll 2
     for (int j = warp; j < Hd; j += NW) acc = fmaf(dhrow[j], fc1w[j * C2 + co2 + c], acc);
     red[warp * H2 + c] = acc;
   }
   __syncthreads();
+#pragma unroll 1
   for (int c = t; c < H2; c += T) {
     float acc = 0.f;
+#pragma unroll 4
     for (int w = 0; w < NW; ++w) acc += red[w * H2 + c];
     drrow[c] = acc;
   }
   __syncthreads();
   DRGNN_PHASE(11);
   // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU
-  {
-    const float invQ = 1.f / (float)max(Q, 1);
-    for (int item = t; item < K * H24; item += T) {
-      const int k = item / H24, q4 = item - k * H24;
-      const int q = cl1[k] - q0;
-      const int4 am = *reinterpret_cast<const int4*>(arg1 + q * H2 + q4 * 4);
-      const float4 z = *reinterpret_cast<const float4*>(z2 + k * LDZ2 + q4 * 4);
-      const float4 d = *reinterpret_cast<const float4*>(drrow + q4 * 4);
-      const int me = k0 + k;
-      float4 v;
-      v.x = (am.x == me && z.x > 0.f) ? d.x * invQ : 0.f;
-      v.y = (am.y == me && z.y > 0.f) ? d.y * invQ : 0.f;
-      v.z = (am.z == me && z.z > 0.f) ? d.z * invQ : 0.f;
-      v.w = (am.w == me && z.w > 0.f) ? d.w * invQ : 0.f;
-      *reinterpret_cast<float4*>(dz2 + k * LDZ2 + q4 * 4) = v;
-    }
-  }
+  s2_route(cl1, q0, arg1, H2, z2, LDZ2, drrow, 0, 1.f / (float)max(Q, 1), dz2, LDZ2, K, H24, k0, t, T);
   __syncthreads();
   DRGNN_PHASE(12);
   // ---- dW2_r = dZ2^T AP (split over the K0 rows, first half of the CTA)  ||  dAP = dZ2 W2_r (second half)
   const int KS2 = s2_split(P.xs_words, H2 * H1), KS1 = s2_split(P.xs_words, H1 * F);
   float* scratch = xs;   // the feature tile is dead since AX
-  if (t < (T >> 1)) {
-    s2_splitk_partial(dz2, LDZ2, ap, LDP, H2, H1, K, KS2, scratch, t, T >> 1);
-  } else {
-    s2_gemm_rowA<2>(dz2, LDZ2, w2, H1, K, H1, H2, t - (T >> 1), T >> 1,
-                    [&](int m, int j, float4 v) { *reinterpret_cast<float4*>(dap + m * LDP + j) = v; });
-  }
+  if (t < (T >> 1)) s2_splitk_partial(dz2, LDZ2, ap, LDP, H2, H1, K, KS2, scratch, t, T >> 1);
+  else s2_gemm(dz2, LDZ2, w2, H1, K, H1, H2, dap, LDP, 0, t - (T >> 1), T >> 1);
   __syncthreads();
   DRGNN_PHASE(13);
   s2_splitk_reduce(scratch, H2 * H1, KS2, part + s.off_w2 + r * H2 * H1, t, T);
   // ---- dP1 = A1^T dAP  (CSC of the coarsened graph)
-  for (int item = t; item < K * H14; item += T) {
-    const int k = item / H14, q4 = item - k * H14;
-    const int sb = cscp1[k] - c10, se = cscp1[k + 1] - c10;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int p = sb; p < se; ++p) {
-      const int rr = cscr1[p] - k0;
-      const float4 v = *reinterpret_cast<const float4*>(dap + rr * LDP + q4 * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    *reinterpret_cast<float4*>(dp1 + k * LDP + q4 * 4) = acc;
-  }
+  s2_gather(cscp1, cscr1, c10, k0, dap, LDP, dp1, LDP, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(14);
   // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU
-  for (int item = t; item < n * H14; item += T) {
-    const int i = item / H14, q4 = item - i * H14;
-    const int k = cl0[i] - k0;
-    const int4 am = *reinterpret_cast<const int4*>(arg0 + k * H1 + q4 * 4);
-    const float4 z = *reinterpret_cast<const float4*>(z1 + i * LDZ1 + q4 * 4);
-    const float4 d = *reinterpret_cast<const float4*>(dp1 + k * LDP + q4 * 4);
-    const int me = n0 + i;
-    float4 v;
-    v.x = (am.x == me && z.x > 0.f) ? d.x : 0.f;
-    v.y = (am.y == me && z.y > 0.f) ? d.y : 0.f;
-    v.z = (am.z == me && z.z > 0.f) ? d.z : 0.f;
-    v.w = (am.w == me && z.w > 0.f) ? d.w : 0.f;
-    *reinterpret_cast<float4*>(dz1 + i * LDZ1 + q4 * 4) = v;
-  }
+  s2_route(cl0, k0, arg0, H1, z1, LDZ1, dp1, LDP, 1.f, dz1, LDZ1, n, H14, n0, t, T);
   __syncthreads();
   DRGNN_PHASE(15);
   // ---- dW1_r [H1][F] = dZ1^T AX, split over the nodes

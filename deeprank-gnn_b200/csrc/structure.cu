@@ -15,6 +15,8 @@
 //   edge attributes in a fixed order (deterministic), level-1 relabel.
 // Kernel B (graph_finalize_kernel): cross-graph exclusive offsets (K0, E1, K1) and the
 //   compaction of the locally-indexed results into their final global positions.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace drgnn {
@@ -33,9 +35,10 @@ static constexpr int kStaticSmemReserve = 2048;  // static __shared__ of the ker
 
 struct SmemPlan {
   // byte offsets into dynamic shared memory
-  int erow, ecol, slotR, slotC, prow, ptrR, ptrC, dense0, mptr, mem, rowptr1, cbits, cpre, wbits, wpre,
+  int erow, ecol, slotR, slotC, prow, ptrR, ptrC, dense0, mptr, mem, rowptr1, cbits, cpre, bm, hist, idc,
       dense1, mptr1, mem1, total;
-  int W1;  // words per warp bitmap
+  int bm_words;  // capacity of the coarsening bitmap (rows of ceil(K/32) words, processed in rounds)
+  int nchunk;    // chunks (= participating warps) of the stable counting sort
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -49,7 +52,13 @@ __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) 
   SmemPlan p;
   int o = 0;
   const int n1 = max_n + 1, c1 = max_c1 + 1;
-  p.W1 = (max_n + 31) / 32;
+  const int w1 = (max_n + 31) / 32;
+  long long bmw = (long long)max_n * w1;       // every pooled row at once when it is small ...
+  if (bmw > 8192) bmw = 8192;                  // ... else rounds of 32 KB
+  if (bmw < w1) bmw = w1;
+  p.bm_words = (int)bmw;
+  p.nchunk = kWarps;                           // histogram [keys][chunks]: shrink the chunk count for huge graphs
+  while (p.nchunk > 1 && (long long)n1 * (p.nchunk + 1) * 4 > 48 * 1024) p.nchunk >>= 1;
   p.erow = o;    o = align16(o + 2 * max_e);
   p.ecol = o;    o = align16(o + 2 * max_e);
   p.slotR = o;   o = align16(o + 2 * max_e);
@@ -63,8 +72,9 @@ __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) 
   p.rowptr1 = o; o = align16(o + 4 * n1);
   p.cbits = o;   o = align16(o + 4 * kCapWords);
   p.cpre = o;    o = align16(o + 4 * kCapWords);
-  p.wbits = o;   o = align16(o + 4 * kWarps * p.W1);
-  p.wpre = o;    o = align16(o + 4 * kWarps * p.W1);
+  p.bm = o;      o = align16(o + 4 * p.bm_words);
+  p.hist = o;    o = align16(o + 4 * (n1 * (p.nchunk + 1) + 4));
+  p.idc = o;     o = align16(o + 8 * max_n);
   p.dense1 = o;  o = align16(o + 2 * max_c1);
   p.mptr1 = o;   o = align16(o + 4 * c1);
   p.mem1 = o;    o = align16(o + 2 * max_c1);
@@ -74,59 +84,85 @@ __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) 
 
 // ---------------------------------------------------------------------------------------
 // Stable counting sort: slot[ptr[k] .. ptr[k+1]) = indices e (ascending) with key[e] == k.
+// The elements are cut into `nchunk` contiguous chunks, one per warp.  Pass 1 counts the keys of a
+// chunk into hist[key][chunk] (lanes holding the same key are found with match.any, the lowest one
+// adds the group's size: no atomics), an exclusive scan in (key major, chunk minor) order turns
+// the counts into the first slot of every (key, chunk), pass 2 places element e at that slot plus
+// its rank among the equal keys before it in the warp.  Deterministic and stable by construction.
 // ---------------------------------------------------------------------------------------
-__device__ void csr_build(const uint16_t* key, int m, int n, int* ptr, uint16_t* slot, int* wsum) {
+// In-place exclusive scan of a[0..len) for len <= blockDim.x (one element per thread, two barriers);
+// longer arrays take the chunked block_exclusive_scan.  Returns the total.  All threads must call.
+__device__ __noinline__ int block_scan_small(int* a, int len, int* wsum) {
   const int T = blockDim.x, t = threadIdx.x;
-  for (int i = t; i <= n; i += T) ptr[i] = 0;
+  if (len > T) return block_exclusive_scan(a, len, wsum);
+  const int v = t < len ? a[t] : 0;
+  const int incl = warp_scan_incl(v);
+  if (lane_id() == 31) wsum[warp_id()] = incl;
   __syncthreads();
-  for (int e = t; e < m; e += T) atomicAdd(&ptr[key[e]], 1);
-  __syncthreads();
-  block_exclusive_scan(ptr, n + 1, wsum);
-  for (int e = t; e < m; e += T) {
-    int p = atomicAdd(&ptr[key[e]], 1);
-    slot[p] = (uint16_t)e;
+  if (warp_id() == 0) {
+    const int nw = T >> 5;
+    const int x = lane_id() < nw ? wsum[lane_id()] : 0;
+    const int xi = warp_scan_incl(x);
+    __syncwarp();
+    wsum[lane_id()] = xi - x;
+    if (lane_id() == 31) wsum[32] = xi;
   }
   __syncthreads();
-  // ptr[k] now holds end(k) == start(k+1): shift right by one, highest chunk first
-  for (int base = ((n) / T) * T; base >= 0; base -= T) {
-    int i = base + t;
-    int v = 0;
-    if (i >= 1 && i <= n) v = ptr[i - 1];
-    __syncthreads();
-    if (i <= n) ptr[i] = v;
-    __syncthreads();
+  if (t < len) a[t] = wsum[warp_id()] + incl - v;
+  const int total = wsum[32];
+  __syncthreads();
+  return total;
+}
+
+__device__ __noinline__ void csr_build(const uint16_t* key, int m, int n, int* ptr, uint16_t* slot, int* hist, int nchunk, int* wsum) {
+  const int T = blockDim.x, t = threadIdx.x, lane = lane_id(), w = warp_id();
+  const int hs = nchunk + 1;             // row stride of hist[key][chunk]: odd => conflict-free both ways
+  {
+    int4* h4 = reinterpret_cast<int4*>(hist);
+    const int H4 = (n * hs + 3) >> 2;
+#pragma unroll 1
+    for (int i = t; i < H4; i += T) h4[i] = make_int4(0, 0, 0, 0);
   }
-  // make every segment ascending in e (atomics placed them in arbitrary order)
+  __syncthreads();
+  int chunk = (m + nchunk - 1) / nchunk;
+  chunk = (chunk + 31) & ~31;
+  const int beg = min(m, w * chunk), end = (w < nchunk) ? min(m, beg + chunk) : beg;
+#pragma unroll 1
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const unsigned k = valid ? (unsigned)key[e] : 0xFFFFFFFFu;
+    const unsigned mask = __match_any_sync(0xffffffffu, k);
+    if (valid && lane == __ffs(mask) - 1) hist[k * hs + w] += __popc(mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per key (one thread): exclusive prefix of its chunk counts in place, total into ptr[key]
+#pragma unroll 1
   for (int k = t; k < n; k += T) {
-    int s = ptr[k], d = ptr[k + 1] - s;
-    if (d > 1 && d <= 32) {
-      for (int i = 1; i < d; ++i) {
-        uint16_t v = slot[s + i];
-        int j = i - 1;
-        while (j >= 0 && slot[s + j] > v) {
-          slot[s + j + 1] = slot[s + j];
-          --j;
-        }
-        slot[s + j + 1] = v;
-      }
+    int* hk = hist + k * hs;
+    int run = 0;
+#pragma unroll 4
+    for (int c = 0; c < nchunk; ++c) {
+      const int v = hk[c];
+      hk[c] = run;
+      run += v;
     }
+    ptr[k] = run;
   }
+  if (t == 0) ptr[n] = 0;
   __syncthreads();
-  // long segments: odd-even transposition sort by a warp
-  for (int k = warp_id(); k < n; k += (T >> 5)) {
-    int s = ptr[k], d = ptr[k + 1] - s;
-    if (d > 32) {
-      for (int pass = 0; pass < d; ++pass) {
-        for (int j = 2 * lane_id() + (pass & 1); j + 1 < d; j += 64) {
-          uint16_t a = slot[s + j], b = slot[s + j + 1];
-          if (a > b) {
-            slot[s + j] = b;
-            slot[s + j + 1] = a;
-          }
-        }
-        __syncwarp();
-      }
-    }
+  block_scan_small(ptr, n + 1, wsum);    // ptr[k] = first slot of key k, ptr[n] = m
+#pragma unroll 1
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const unsigned k = valid ? (unsigned)key[e] : 0xFFFFFFFFu;
+    const unsigned mask = __match_any_sync(0xffffffffu, k);
+    if (valid) slot[ptr[k] + hist[k * hs + w] + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)e;
+    __syncwarp();
+    if (valid && lane == __ffs(mask) - 1) hist[k * hs + w] += __popc(mask);
+    __syncwarp();
   }
   __syncthreads();
 }
@@ -135,57 +171,98 @@ __device__ void csr_build(const uint16_t* key, int m, int n, int* ptr, uint16_t*
 // Dense relabel of `n` int64 ids (sorted-unique rank, i.e. consecutive_cluster's inverse
 // restricted to one graph).  Returns K; writes min / max of the raw ids.
 // ---------------------------------------------------------------------------------------
-__device__ int relabel(const void* ids_base, int64_t ids_off, int idx32, int n, uint16_t* dense, uint32_t* cbits, int* cpre, int* wsum,
-                       long long* red, int32_t* status, long long* out_min, long long* out_max) {
-  const int T = blockDim.x, t = threadIdx.x;
+__device__ __noinline__ int relabel(const void* ids_base, int64_t ids_off, int idx32, int n, uint16_t* dense, uint32_t* cbits, int* cpre, int* wsum,
+                       long long* red, long long* idc, int32_t* status, long long* out_min, long long* out_max) {
+  const int T = blockDim.x, t = threadIdx.x, lane = lane_id(), w = warp_id(), NWARP = T >> 5;
   long long mn = LLONG_MAX, mx = LLONG_MIN;
-  for (int i = t; i < n; i += T) {
+#pragma unroll 1
+  for (int i = t; i < n; i += T) {   // the ids are read from global memory once; idc[i] is re-read by the same thread only
     long long v = ld_id(ids_base, ids_off + i, idx32);
+    idc[i] = v;
     mn = v < mn ? v : mn;
     mx = v > mx ? v : mx;
   }
+  if (idx32) {   // int32 ids (packed feeder batches): hardware warp reductions
+    const int a = __reduce_min_sync(0xffffffffu, (int)(mn > INT_MAX ? INT_MAX : mn));
+    const int b = __reduce_max_sync(0xffffffffu, (int)(mx < INT_MIN ? INT_MIN : mx));
+    mn = a;
+    mx = b;
+  } else {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-    mn = a < mn ? a : mn;
-    mx = b > mx ? b : mx;
+    for (int o = 16; o > 0; o >>= 1) {
+      long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
   }
-  if (lane_id() == 0) {
-    red[2 * warp_id()] = mn;
-    red[2 * warp_id() + 1] = mx;
-  }
-  __syncthreads();
-  mn = LLONG_MAX;
-  mx = LLONG_MIN;
-  for (int w = 0; w < (T >> 5); ++w) {
-    mn = red[2 * w] < mn ? red[2 * w] : mn;
-    mx = red[2 * w + 1] > mx ? red[2 * w + 1] : mx;
+  if (lane == 0) {
+    red[2 * w] = mn;
+    red[2 * w + 1] = mx;
   }
   __syncthreads();
+  if (w == 0) {   // warp 0 folds the per-warp extremes, result in red[0], red[1]
+    mn = lane < NWARP ? red[2 * lane] : LLONG_MAX;
+    mx = lane < NWARP ? red[2 * lane + 1] : LLONG_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      red[0] = mn;
+      red[1] = mx;
+    }
+  }
+  __syncthreads();
+  mn = red[0];
+  mx = red[1];
+  if (n == 0) { mn = LLONG_MAX; mx = LLONG_MIN; }
   *out_min = mn;
   *out_max = mx;
-  if (n == 0) return 0;
+  if (n == 0) {
+    __syncthreads();
+    return 0;
+  }
   long long range = mx - mn + 1;
   if (mn < 0 && t == 0) atomicOr(status, DRGNN_ST_NEGATIVE_ID);
   if (range > (long long)kCapWords * 32) {
     if (t == 0) atomicOr(status, DRGNN_ST_CLUSTER_RANGE);
+#pragma unroll 1
     for (int i = t; i < n; i += T) dense[i] = 0;
     __syncthreads();
     return 1;
   }
   const int W = (int)((range + 31) >> 5);
-  for (int w = t; w < W; w += T) cbits[w] = 0u;
+#pragma unroll 1
+  for (int i = t; i < W; i += T) cbits[i] = 0u;
   __syncthreads();
+#pragma unroll 1
   for (int i = t; i < n; i += T) {
-    int v = (int)(ld_id(ids_base, ids_off + i, idx32) - mn);
+    int v = (int)(idc[i] - mn);
     atomicOr(&cbits[v >> 5], 1u << (v & 31));
   }
   __syncthreads();
-  for (int w = t; w < W; w += T) cpre[w] = __popc(cbits[w]);
-  __syncthreads();
-  int K = block_exclusive_scan(cpre, W, wsum);
+  int K;
+  if (W <= 32) {   // the usual case (cluster ids of one graph span a few words): one warp, one barrier
+    if (w == 0) {
+      const int c = lane < W ? __popc(cbits[lane]) : 0;
+      const int incl = warp_scan_incl(c);
+      if (lane < W) cpre[lane] = incl - c;
+      if (lane == 31) wsum[32] = incl;
+    }
+    __syncthreads();
+    K = wsum[32];
+  } else {
+#pragma unroll 1
+    for (int i = t; i < W; i += T) cpre[i] = __popc(cbits[i]);
+    __syncthreads();
+    K = block_exclusive_scan(cpre, W, wsum);
+  }
+#pragma unroll 1
   for (int i = t; i < n; i += T) {
-    int v = (int)(ld_id(ids_base, ids_off + i, idx32) - mn);
+    int v = (int)(idc[i] - mn);
     dense[i] = (uint16_t)(cpre[v >> 5] + __popc(cbits[v >> 5] & ((1u << (v & 31)) - 1u)));
   }
   __syncthreads();
@@ -232,8 +309,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   int* rowptr1 = (int*)(smem + P.rowptr1);
   uint32_t* cbits = (uint32_t*)(smem + P.cbits);
   int* cpre = (int*)(smem + P.cpre);
-  uint32_t* wbits = (uint32_t*)(smem + P.wbits) + warp_id() * P.W1;
-  int* wpre = (int*)(smem + P.wpre) + warp_id() * P.W1;
+  uint32_t* bm = (uint32_t*)(smem + P.bm);
+  int* hist = (int*)(smem + P.hist);
+  long long* idc = (long long*)(smem + P.idc);
+  const int nchunk = P.nchunk;
   uint16_t* dense1 = (uint16_t*)(smem + P.dense1);
   int* mptr1 = (int*)(smem + P.mptr1);
   uint16_t* mem1 = (uint16_t*)(smem + P.mem1);
@@ -245,6 +324,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
 
   DRGNN_SPHASE(0);
   // ---- 1. local edge list ----
+#pragma unroll 1
   for (int e = t; e < m; e += T) {
     long long r = ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
     long long c = ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
@@ -260,8 +340,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
 
   DRGNN_SPHASE(1);
   // ---- 2. CSR by destination (row) ----
-  csr_build(erow, m, n, ptrR, slotR, wsum);
+  csr_build(erow, m, n, ptrR, slotR, hist, nchunk, wsum);
+#pragma unroll 1
   for (int i = t; i <= n; i += T) io.rowptr0[n0 + i] = e0 + ptrR[i];
+#pragma unroll 1
   for (int p = t; p < m; p += T) {
     int e = slotR[p];
     io.col0[e0 + p] = n0 + ecol[e];
@@ -270,8 +352,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   }
   DRGNN_SPHASE(2);
   // ---- 3. CSC (transposed graph) ----
-  csr_build(ecol, m, n, ptrC, slotC, wsum);
+  csr_build(ecol, m, n, ptrC, slotC, hist, nchunk, wsum);
+#pragma unroll 1
   for (int i = t; i <= n; i += T) io.cscptr0[n0 + i] = e0 + ptrC[i];
+#pragma unroll 1
   for (int p = t; p < m; p += T) {
     int e = slotC[p];
     io.cscrow0[e0 + p] = n0 + erow[e];
@@ -283,91 +367,101 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   DRGNN_SPHASE(3);
   // ---- 4. relabel level-0 clusters ----
   long long cmin, cmax;
-  const int K = relabel(io.cluster0, n0, io.idx32, n, dense0, cbits, cpre, wsum, red, io.status, &cmin, &cmax);
+  const int K = relabel(io.cluster0, n0, io.idx32, n, dense0, cbits, cpre, wsum, red, idc, io.status, &cmin, &cmax);
+#pragma unroll 1
   for (int i = t; i < n; i += T) io.cl0[n0 + i] = dense0[i];  // local; finalize adds the graph offset
 
   DRGNN_SPHASE(4);
   // ---- 5. members of every cluster (ascending node id) ----
-  csr_build(dense0, n, K, mptr, mem, wsum);
+  csr_build(dense0, n, K, mptr, mem, hist, nchunk, wsum);
+#pragma unroll 1
   for (int k = t; k <= K; k += T) S.mptr0[n0 + g + k] = mptr[k];
+#pragma unroll 1
   for (int p = t; p < n; p += T) io.cmem0[n0 + p] = n0 + mem[p];
 
   DRGNN_SPHASE(5);
   // ---- 6. coarsened edges: per pooled row a column bitmap -> sorted unique columns ----
   uint16_t* pcol = slotC;  // CSC slots are dead now
+  // Bitmap of pooled columns per pooled row, filled by ALL edges in parallel (one atomicOr each);
+  // rows are emitted sorted & unique straight from the bits.  When K rows x ceil(K/32) words exceed
+  // the bitmap capacity the rows are processed in rounds (count sweep, scan, emit sweep).
   const int W1 = (K + 31) >> 5;
-  const int lane = lane_id();
+  const int RB = W1 > 0 ? max(1, P.bm_words / W1) : 1;
+  const int nround = K > 0 ? (K + RB - 1) / RB : 0;
   for (int pass = 0; pass < 2; ++pass) {
-    for (int r = warp_id(); r < K; r += kWarps) {
-      for (int w = lane; w < W1; w += 32) wbits[w] = 0u;
-      __syncwarp();
-      for (int mi = mptr[r]; mi < mptr[r + 1]; ++mi) {
-        int i = mem[mi];
-        for (int p = ptrR[i] + lane; p < ptrR[i + 1]; p += 32) {
-          int pc = dense0[ecol[slotR[p]]];
-          if (pc != r) atomicOr(&wbits[pc >> 5], 1u << (pc & 31));  // remove_self_loops
+    for (int rd = 0; rd < nround; ++rd) {
+      const int r0 = rd * RB, rows = min(RB, K - r0);
+      if (pass == 0 || nround > 1) {
+#pragma unroll 1
+        for (int w = t; w < rows * W1; w += T) bm[w] = 0u;
+        __syncthreads();
+#pragma unroll 1
+        for (int e = t; e < m; e += T) {
+          const int pr = dense0[erow[e]], pc = dense0[ecol[e]];
+          if (pr != pc && pr >= r0 && pr < r0 + rows)   // remove_self_loops
+            atomicOr(&bm[(pr - r0) * W1 + (pc >> 5)], 1u << (pc & 31));
         }
+        __syncthreads();
       }
-      __syncwarp();
       if (pass == 0) {
-        int cnt = 0;
-        for (int w = lane; w < W1; w += 32) cnt += __popc(wbits[w]);
-        cnt = warp_sum(cnt);
-        if (lane == 0) rowptr1[r] = cnt;
+#pragma unroll 1
+        for (int r = t; r < rows; r += T) {
+          int cnt = 0;
+          for (int w = 0; w < W1; ++w) cnt += __popc(bm[r * W1 + w]);
+          rowptr1[r0 + r] = cnt;
+        }
       } else {
-        // exclusive popcount prefix over the words of this row
-        int run = 0;
-        for (int wb = 0; wb < W1; wb += 32) {
-          int w = wb + lane;
-          int c = w < W1 ? __popc(wbits[w]) : 0;
-          int inc = warp_scan_incl(c);
-          if (w < W1) wpre[w] = run + inc - c;
-          run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        __syncwarp();
-        const int base = rowptr1[r];
-        const int cnt = rowptr1[r + 1] - base;
-        for (int w = lane; w < W1; w += 32) {
-          uint32_t bits = wbits[w];
-          int q = base + wpre[w];
-          while (bits) {
-            int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            pcol[q] = (uint16_t)(w * 32 + b);
-            prow[q] = (uint16_t)r;
-            ++q;
-          }
-        }
-        __syncwarp();
-        // summed attributes of merged edges: fixed order (members ascending, then edge id)
-        if (io.edge_attr1 != nullptr) {
-          for (int f = 0; f < ne; ++f) {
-            for (int s = lane; s < cnt; s += 32) {
-              const int tc = pcol[base + s];
-              float acc = 0.f;
-              for (int mi = mptr[r]; mi < mptr[r + 1]; ++mi) {
-                int i = mem[mi];
-                for (int p = ptrR[i]; p < ptrR[i + 1]; ++p) {
-                  int e = slotR[p];
-                  if (dense0[ecol[e]] == tc) acc += io.edge_attr[(int64_t)(e0 + e) * ne + f];
-                }
-              }
-              io.scratch_f[(int64_t)(e0 + base + s) * ne + f] = acc;
+#pragma unroll 1
+        for (int r = t; r < rows; r += T) {
+          int q = rowptr1[r0 + r];
+          for (int w = 0; w < W1; ++w) {
+            uint32_t bits = bm[r * W1 + w];
+            while (bits) {
+              const int b = __ffs(bits) - 1;
+              bits &= bits - 1;
+              pcol[q] = (uint16_t)(w * 32 + b);
+              prow[q] = (uint16_t)(r0 + r);
+              ++q;
             }
           }
         }
-        __syncwarp();
       }
+      __syncthreads();
     }
-    __syncthreads();
     if (pass == 0) {
       if (t == 0) rowptr1[K] = 0;
       __syncthreads();
       block_exclusive_scan(rowptr1, K + 1, wsum);
     }
   }
+  // summed attributes of merged edges: fixed order (members ascending, then edge id); warp per pooled row
+  if (io.edge_attr1 != nullptr) {
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int r = warp_id(); r < K; r += kWarps) {
+      const int base = rowptr1[r];
+      const int cnt = rowptr1[r + 1] - base;
+      for (int f = 0; f < ne; ++f) {
+#pragma unroll 1
+        for (int sidx = lane; sidx < cnt; sidx += 32) {
+          const int tc = pcol[base + sidx];
+          float acc = 0.f;
+          for (int mi = mptr[r]; mi < mptr[r + 1]; ++mi) {
+            int i = mem[mi];
+            for (int p = ptrR[i]; p < ptrR[i + 1]; ++p) {
+              int e = slotR[p];
+              if (dense0[ecol[e]] == tc) acc += io.edge_attr[(int64_t)(e0 + e) * ne + f];
+            }
+          }
+          io.scratch_f[(int64_t)(e0 + base + sidx) * ne + f] = acc;
+        }
+      }
+    }
+  }
   const int E1 = rowptr1[K];
+#pragma unroll 1
   for (int r = t; r <= K; r += T) S.rowptr1[n0 + g + r] = rowptr1[r];
+#pragma unroll 1
   for (int p = t; p < E1; p += T) {
     S.col1[e0 + p] = pcol[p];
     S.row1[e0 + p] = prow[p];
@@ -378,8 +472,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   // ---- 7. CSC of the coarsened graph ----
   int* ptrC1 = ptrC;
   uint16_t* slotC1 = slotR;  // level-0 CSR slots are dead now
-  csr_build(pcol, E1, K, ptrC1, slotC1, wsum);
+  csr_build(pcol, E1, K, ptrC1, slotC1, hist, nchunk, wsum);
+#pragma unroll 1
   for (int r = t; r <= K; r += T) S.cscptr1[n0 + g + r] = ptrC1[r];
+#pragma unroll 1
   for (int p = t; p < E1; p += T) {
     int q = slotC1[p];
     S.cscrow1[e0 + p] = prow[q];
@@ -398,10 +494,13 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     }
     c1len = min(c1len, io.max_n);  // shared-memory bound (only reachable for invalid input)
     long long mn1, mx1;
-    K1 = relabel(io.cluster1, c0, io.idx32, c1len, dense1, cbits, cpre, wsum, red, io.status, &mn1, &mx1);
+    K1 = relabel(io.cluster1, c0, io.idx32, c1len, dense1, cbits, cpre, wsum, red, idc, io.status, &mn1, &mx1);
+#pragma unroll 1
     for (int k = t; k < c1len; k += T) io.cl1[c0 + k] = dense1[k];
-    csr_build(dense1, c1len, K1, mptr1, mem1, wsum);
+    csr_build(dense1, c1len, K1, mptr1, mem1, hist, nchunk, wsum);
+#pragma unroll 1
     for (int q = t; q <= K1; q += T) S.mptr1[c0 + g + q] = mptr1[q];
+#pragma unroll 1
     for (int p = t; p < c1len; p += T) S.mem1[c0 + p] = mem1[p];
   }
 
@@ -427,6 +526,7 @@ __global__ void __launch_bounds__(256) graph_finalize_kernel(const drgnn_structu
   const Scratch S = make_scratch(io);
   // exclusive offsets over the preceding graphs
   int a = 0, b = 0, c = 0;
+#pragma unroll 1
   for (int h = t; h < g; h += T) {
     a += io.gstat[8 * h];
     b += io.gstat[8 * h + 1];
@@ -465,20 +565,24 @@ __global__ void __launch_bounds__(256) graph_finalize_kernel(const drgnn_structu
     }
   }
 
+#pragma unroll 1
   for (int i = t; i < n; i += T) {
     int v = io.cl0[n0 + i] + Koff;
     io.cl0[n0 + i] = v;
     if (io.cl0_i64) io.cl0_i64[n0 + i] = v;
   }
+#pragma unroll 1
   for (int k = t; k <= K; k += T) {
     io.cmptr0[Koff + k] = n0 + S.mptr0[n0 + g + k];
     io.rowptr1[Koff + k] = E1off + S.rowptr1[n0 + g + k];
     io.cscptr1[Koff + k] = E1off + S.cscptr1[n0 + g + k];
   }
+#pragma unroll 1
   for (int k = t; k < K; k += T) {
     io.batch1[Koff + k] = g;
     if (io.batch1_i64) io.batch1_i64[Koff + k] = g;
   }
+#pragma unroll 1
   for (int p = t; p < E1; p += T) {
     const int row = Koff + S.row1[e0 + p], col = Koff + S.col1[e0 + p];
     io.col1[E1off + p] = col;
@@ -498,9 +602,13 @@ __global__ void __launch_bounds__(256) graph_finalize_kernel(const drgnn_structu
 
   if (io.cluster1 != nullptr) {
     const int c0 = io.c1_ptr[g], c1len = io.c1_ptr[g + 1] - c0;
+#pragma unroll 1
     for (int k = t; k < c1len; k += T) io.cl1[c0 + k] += K1off;
+#pragma unroll 1
     for (int q = t; q <= K1; q += T) io.cmptr1[K1off + q] = Koff + S.mptr1[c0 + g + q];
+#pragma unroll 1
     for (int p = t; p < c1len; p += T) io.cmem1[Koff + p] = Koff + S.mem1[c0 + p];
+#pragma unroll 1
     for (int q = t; q < K1; q += T) {
       io.batch2[K1off + q] = g;
       if (io.batch2_i64) io.batch2_i64[K1off + q] = g;
