@@ -29,6 +29,7 @@ STATUS_TEXT = {
     ST_CLUSTER_ORDER: 'global cluster ids do not increase with the graph id',
     ST_NEGATIVE_ID: 'negative cluster id',
     ST_FUSED_BOUNDS: 'a graph exceeds the per-graph bounds given to the fused kernels',
+    128: 'the grid barrier of the fused gradient reduction timed out (the step kernel was not co-resident)',
 }
 
 
@@ -48,6 +49,7 @@ class StructureIO(C.Structure):
         ('cl1', VP), ('cmptr1', VP), ('cmem1', VP), ('kptr1', VP), ('batch2', VP), ('batch2_i64', VP),
         ('counts', VP), ('status', VP),
         ('gstat', VP), ('scratch_n', VP), ('scratch_e', VP), ('scratch_f', VP),
+        ('blob', VP),
     ]
 
 
@@ -130,6 +132,7 @@ class GinetStepArgs(C.Structure):
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
         ('skip_reduce', C.c_int32), ('flags', C.c_int32), ('max_e', C.c_int32), ('variant', C.c_int32),
+        ('blob', VP), ('edge_ptr', VP),
     ]
 
 
@@ -200,7 +203,12 @@ _SIGNATURES = {
     'drgnn_ginet_step': (C.c_int, [C.POINTER(GinetStepArgs), VP]),
     'drgnn_ginet_step2_smem_bytes': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     'drgnn_ginet_step_last_variant': (C.c_int, []),
+    'drgnn_ginet_step_last_launches': (C.c_int, []),
+    'drgnn_ginet_step2_max_clusters': (C.c_int, [_i64]),
     'drgnn_debug_phase_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
+    'drgnn_debug_blob_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
+    'drgnn_structure_blob_smem_bytes': (_i64, [_i32, _i32]),
+    'drgnn_structure_blob': (C.c_int, [C.POINTER(StructureIO), VP]),
     'drgnn_debug_structure_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),

@@ -103,6 +103,29 @@ __device__ inline int block_exclusive_scan(int* a, int len, int* wsum) {
   return total;
 }
 
+// Word offsets of the arrays inside one graph's structure blob (include/drgnn.h, drgnn_structure_io.blob)
+struct BlobLayout {
+  int rp0, col0, rp1, col1, cmp0, cmem0, cl0, cmp1, cmem1, cl1, cscp1, cscr1, end;
+};
+__host__ __device__ inline BlobLayout blob_layout(int n, int m) {
+  BlobLayout b;
+  int o = DRGNN_BLOB_HEADER;
+  b.rp0 = o;   o += n + 1;
+  b.col0 = o;  o += m;
+  b.rp1 = o;   o += n + 1;
+  b.col1 = o;  o += m;
+  b.cmp0 = o;  o += n + 1;
+  b.cmem0 = o; o += n;
+  b.cl0 = o;   o += n;
+  b.cmp1 = o;  o += n + 1;
+  b.cmem1 = o; o += n;
+  b.cl1 = o;   o += n;
+  b.cscp1 = o; o += n + 1;
+  b.cscr1 = o; o += m;
+  b.end = o;
+  return b;
+}
+
 // CTA-wide small GEMM out of shared memory:  C[m][n] = sum_k At[k * lda + m] * Bm[k * ldb + n]
 // (A is held TRANSPOSED so the 8 rows of a thread tile are two 16-byte loads, broadcast inside a
 // warp; Bm rows are contiguous in n).  8 (m) x 4 (n) register tile per thread: 3 LDS.128 + 32 FMA per

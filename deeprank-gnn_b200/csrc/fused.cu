@@ -701,8 +701,51 @@ extern "C" int64_t drgnn_ginet_step2_smem_bytes(int32_t F, int32_t h1, int32_t h
   return bytes;
 }
 
+// How many 2-CTA clusters of ginet_graph_step2_kernel the device holds at once (cached per size).
+static int step2_max_clusters(int64_t smem) {
+  static thread_local int64_t cached_smem = -1;
+  static thread_local int cached = 0;
+  if (cached_smem == smem) return cached;
+  int best = 0;
+  for (int with_attr = 0; with_attr < 2 && best <= 0; ++with_attr) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)device_info().sms);
+    cfg.blockDim = dim3(S2_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = with_attr ? attr : nullptr;
+    cfg.numAttrs = with_attr ? 1 : 0;
+    int nc = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, ginet_graph_step2_kernel, &cfg);
+    if (e != cudaSuccess) {
+      fail(DRGNN_ERR_CUDA, "cudaOccupancyMaxActiveClusters(%s): %s", with_attr ? "attr" : "compile-time dims", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      nc = 0;
+    }
+    if (nc > best) best = nc;
+  }
+  cached = best;
+  cached_smem = smem;
+  return best;
+}
+extern "C" int drgnn_ginet_step2_max_clusters(int64_t smem_bytes) {
+  if (smem_bytes < 0 || smem_bytes > device_info().smem_optin - 1024) return DRGNN_ERR_INVALID;
+  if (cudaFuncSetAttribute(ginet_graph_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)device_info().smem_optin - 1024) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DRGNN_ERR_CUDA;
+  }
+  return step2_max_clusters(smem_bytes);
+}
+
 static thread_local int g_step_variant = 0;
+static thread_local int g_step_launches = 0;
 extern "C" int drgnn_ginet_step_last_variant(void) { return g_step_variant; }
+extern "C" int drgnn_ginet_step_last_launches(void) { return g_step_launches; }
 
 extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
   DRGNN_REQUIRE(s != nullptr, "ginet_step: args is NULL");
@@ -738,16 +781,25 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
                                             (int)device_info().smem_optin - 1024));
       configured2 = device_info().smem_optin - 1024;
     }
-    ginet_graph_step2_kernel<<<2 * a->B, S2_THREADS, smem2, st>>>(*s);
+    Step2Plan plan = step2_plan(a->F, a->h1, a->h2, a->max_n, a->max_k, a->max_q, s->max_e, s->Hd, s->out);
+    const bool train = !s->forward_only && s->task != 0;
+    // One CTA per SM (shared memory): with 2B <= SMs the whole grid is co-resident and the gradient
+    // reduction (+ Adam) can follow a grid barrier inside the same launch.  flags bit 1 disables it.
+    const int G = 2 * a->B;
+    const int occ_clusters = step2_max_clusters(smem2);   // co-resident 2-CTA clusters at this shared-memory size
+    plan.fused_reduce = (train && !s->skip_reduce && s->step_dev != nullptr && !(s->flags & 2) && a->B <= occ_clusters) ? 1 : 0;
+    ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(*s, plan);
     DRGNN_CHECK_LAUNCH("ginet_graph_step2_kernel");
     g_step_variant = 2;
-    if (!s->forward_only && s->task != 0 && !s->skip_reduce) {
+    g_step_launches = plan.fused_reduce ? 1 : ((train && !s->skip_reduce) ? 2 : 1);
+    if (train && !s->skip_reduce && !plan.fused_reduce) {
       ginet_step_reduce_kernel<<<(s->n_params + 1 + 31) / 32, 32 * RED_SPLITS, 0, st>>>(*s);
       DRGNN_CHECK_LAUNCH("ginet_step_reduce_kernel");
     }
     return DRGNN_OK;
   }
   g_step_variant = 1;
+  g_step_launches = (!s->forward_only && s->task != 0 && !s->skip_reduce) ? 2 : 1;
   const int64_t smem = drgnn_ginet_step_smem_bytes(a->F, a->h1, a->h2, a->nb, a->max_n, a->max_k, a->max_q, s->Hd, s->out);
   if (smem < 0) return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: a graph of %d nodes does not fit shared memory", a->max_n);
   static thread_local int64_t configured = -1;

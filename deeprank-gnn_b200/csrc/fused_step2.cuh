@@ -37,24 +37,75 @@ __device__ __forceinline__ void s2_cp16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s2_smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void s2_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ unsigned s2_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long s2_globaltimer() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both sides 16-byte aligned)
+__device__ __forceinline__ void s2_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void s2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s2_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s2_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void s2_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "S2_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra S2_DONE_%=;\n"
+      "bra S2_WAIT_%=;\n"
+      "S2_DONE_%=:\n"
+      "}\n" ::"r"(s2_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 template <int N>
 __device__ __forceinline__ void s2_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __host__ __device__ inline int s2_up4(int x) { return (x + 3) & ~3; }
+// item -> (item / w, item % w) with a shift when w is a power of two (the usual widths: 4, 8)
+__host__ __device__ inline int s2_log2_exact(int w) {
+  int sh = 0;
+  while ((1 << sh) < w) ++sh;
+  return (1 << sh) == w ? sh : -1;
+}
+struct S2Div {
+  int w, sh;
+  __device__ __forceinline__ explicit S2Div(int w_) : w(w_), sh(s2_log2_exact(w_)) {}
+  __device__ __forceinline__ void split(int item, int& q, int& r) const {
+    if (sh >= 0) { q = item >> sh; r = item & (w - 1); }
+    else { q = item / w; r = item - q * w; }
+  }
+};
 
 // Shared-memory plan (offsets in 4-byte words, every offset a multiple of 4 = 16 bytes).
 struct Step2Plan {
   // float regions
   int xs, ax, z1, dz1, w1t, w2t, w2, p1, ap, z2, p2, dz2, dap, dp1;
   int fc1w, fc2w, fc1b, fc2b, rrow, hrow, dhrow, drrow, prow, red;
-  // int regions
-  int arg0, arg1, rp0, col0, rp1, col1, cmp0, cmem0, cl0, cmp1, cmem1, cl1, cscp1, cscr1;
+  // int regions: arg-max ids, the graph's structure blob (every index slice, staged by one bulk copy), mbarriers
+  int arg0, arg1, blob, bars;
+  int blob_words;
   int ldx, ldz1, ldp, ldz2;   // row strides (words): F+4, h1+4, h1+4, h2+4
   int xs_words;               // capacity of the xs region (split-K scratch in the backward)
   int max_e1;
   int total;
+  int fused_reduce;           // set by the launcher: the gradient reduction (+ Adam) runs inside the launch
 };
 __host__ __device__ inline Step2Plan step2_plan(int F, int h1, int h2, int max_n, int max_k, int max_q, int max_e, int Hd,
                                                 int out) {
@@ -97,19 +148,11 @@ __host__ __device__ inline Step2Plan step2_plan(int F, int h1, int h2, int max_n
   p.red = take((S2_THREADS / 32) * h2);
   p.arg0 = take(k8 * h1);
   p.arg1 = take(q8 * h2);
-  p.rp0 = take(max_n + 1);
-  p.col0 = take(max_e);
-  p.rp1 = take(max_k + 1);
-  p.col1 = take(p.max_e1);
-  p.cmp0 = take(max_k + 1);
-  p.cmem0 = take(max_n);
-  p.cl0 = take(max_n);
-  p.cmp1 = take(max_q + 1);
-  p.cmem1 = take(max_k);
-  p.cl1 = take(max_k);
-  p.cscp1 = take(max_k + 1);
-  p.cscr1 = take(p.max_e1);
+  p.blob_words = DRGNN_BLOB_USED(max_n, max_e);
+  p.blob = take(p.blob_words);
+  p.bars = take(4);           // two 8-byte mbarriers
   p.total = o;
+  p.fused_reduce = 0;
   return p;
 }
 
@@ -162,9 +205,11 @@ __device__ __noinline__ void s2_gemm(const float* __restrict__ A, int lda, const
 __device__ __noinline__ void s2_gather(const int* __restrict__ rp, const int* __restrict__ col, int ebase, int nbase,
                                        const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int W4,
                                        int tid, int nth) {
+  const S2Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int i = item / W4, q4 = item - i * W4;
+    int i, q4;
+    dv.split(item, i, q4);
     const int sb = rp[i] - ebase, se = rp[i + 1] - ebase;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
@@ -181,9 +226,11 @@ __device__ __noinline__ void s2_gather(const int* __restrict__ rp, const int* __
 __device__ __noinline__ void s2_cluster_max(const int* __restrict__ cmp, const int* __restrict__ cmem, int mbase, int nbase,
                                             const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
                                             int* __restrict__ arg, int ldarg, int rows, int W4, int tid, int nth) {
+  const S2Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int k = item / W4, q4 = item - k * W4;
+    int k, q4;
+    dv.split(item, k, q4);
     const int sb = cmp[k] - mbase, se = cmp[k + 1] - mbase;
     float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
     int4 am = make_int4(-1, -1, -1, -1);
@@ -210,9 +257,11 @@ __device__ __noinline__ void s2_cluster_max(const int* __restrict__ cmp, const i
 __device__ __noinline__ void s2_route(const int* __restrict__ cl, int kbase, const int* __restrict__ arg, int ldarg,
                                       const float* __restrict__ z, int ldz, const float* __restrict__ d, int ldd, float scale,
                                       float* __restrict__ dst, int lddst, int rows, int W4, int self0, int tid, int nth) {
+  const S2Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int i = item / W4, q4 = item - i * W4;
+    int i, q4;
+    dv.split(item, i, q4);
     const int k = cl[i] - kbase;
     const int4 am = *reinterpret_cast<const int4*>(arg + k * ldarg + q4 * 4);
     const float4 zz = *reinterpret_cast<const float4*>(z + i * ldz + q4 * 4);
@@ -289,14 +338,24 @@ __device__ __noinline__ void s2_stage128(void* dst, const void* src, int count, 
   for (int i = tid; i < count; i += nth)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * i), "l"(g + 16 * (size_t)i) : "memory");
 }
-// rows x W4 float4 words of shared memory -> global memory (test mirror of the intermediates)
-__device__ __noinline__ void s2_mirror(const void* src, int lds, void* dst, int64_t ldd, int rows, int W4, int tid, int nth) {
-  const float* sp = reinterpret_cast<const float*>(src);
-  float* dp = reinterpret_cast<float*>(dst);
+// rows x W4 16-byte words of shared memory -> global memory (test mirror of the intermediates).
+// iadd1 > 0: the words are int32 local ids; non-negative ones are stored as id + (iadd1 - 1).
+__device__ __noinline__ void s2_mirror(const void* src, int lds, void* dst, int64_t ldd, int rows, int W4, int iadd1, int tid,
+                                       int nth) {
+  const int* sp = reinterpret_cast<const int*>(src);
+  int* dp = reinterpret_cast<int*>(dst);
+  const S2Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int i = item / W4, q4 = item - i * W4;
-    *reinterpret_cast<float4*>(dp + i * ldd + q4 * 4) = *reinterpret_cast<const float4*>(sp + i * lds + q4 * 4);
+    int i, q4;
+    dv.split(item, i, q4);
+    int4 v = *reinterpret_cast<const int4*>(sp + i * lds + q4 * 4);
+    if (iadd1 > 0) {
+      const int ad = iadd1 - 1;
+      v.x = v.x >= 0 ? v.x + ad : v.x; v.y = v.y >= 0 ? v.y + ad : v.y;
+      v.z = v.z >= 0 ? v.z + ad : v.z; v.w = v.w >= 0 ? v.w + ad : v.w;
+    }
+    *reinterpret_cast<int4*>(dp + i * ldd + q4 * 4) = v;
   }
 }
 
@@ -308,7 +367,7 @@ __host__ __device__ inline int s2_split(int cap_words, int mn) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
-    ginet_graph_step2_kernel(const drgnn_ginet_step_args s) {
+    ginet_graph_step2_kernel(const drgnn_ginet_step_args s, const Step2Plan P) {
   extern __shared__ __align__(16) float sm[];
   cgx::cluster_group cluster = cgx::this_cluster();
   const drgnn_ginet_fused_args& a = s.g;
@@ -319,7 +378,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const int F = a.F, H1 = a.h1, H2 = a.h2, C1 = 2 * H1, C2 = 2 * H2, Hd = s.Hd, out = s.out;
   const int co1 = r * H1, co2 = r * H2;
   const bool mirror = (s.flags & 1) != 0;   // also store the intermediates to global memory
-  const Step2Plan P = step2_plan(F, H1, H2, a.max_n, a.max_k, a.max_q, s.max_e, Hd, out);
   DRGNN_PHASE(0);
   float* xs = sm + P.xs;   float* ax = sm + P.ax;   float* z1 = sm + P.z1;   float* dz1 = sm + P.dz1;
   float* w1t = sm + P.w1t; float* w2t = sm + P.w2t; float* w2 = sm + P.w2;
@@ -330,19 +388,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   float* prow = sm + P.prow; float* red = sm + P.red;
   int* ism = reinterpret_cast<int*>(sm);
   int* arg0 = ism + P.arg0;  int* arg1 = ism + P.arg1;
-  int* rp0 = ism + P.rp0;    int* col0 = ism + P.col0;   int* rp1 = ism + P.rp1;   int* col1 = ism + P.col1;
-  int* cmp0 = ism + P.cmp0;  int* cmem0 = ism + P.cmem0; int* cl0 = ism + P.cl0;
-  int* cmp1 = ism + P.cmp1;  int* cmem1 = ism + P.cmem1; int* cl1 = ism + P.cl1;
-  int* cscp1 = ism + P.cscp1; int* cscr1 = ism + P.cscr1;
+  int* blb = ism + P.blob;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ism + P.bars);
   const int LDX = P.ldx, LDZ1 = P.ldz1, LDP = P.ldp, LDZ2 = P.ldz2;
 
-  // ---- graph extents (two dependent levels of tiny loads, the only global latency chain of the kernel)
+  // ---- graph extents: ONE level of tiny loads (host-built pointers), then three bulk copies
   const int n0 = __ldg(a.node_ptr + g), n = __ldg(a.node_ptr + g + 1) - n0;
-  const int k0 = __ldg(a.kptr0 + g), K = __ldg(a.kptr0 + g + 1) - k0;
-  const int q0 = __ldg(a.kptr1 + g), Q = __ldg(a.kptr1 + g + 1) - q0;
+  const int eg0 = __ldg(s.edge_ptr + g), m = __ldg(s.edge_ptr + g + 1) - eg0;
   const bool train = !(s.forward_only || s.task == 0);
   float* part = s.partial + (int64_t)g * s.partial_ld;
-  // loop-invariant global scalars of the head, fetched while the staging copies fly
+  // loop-invariant global scalars of the head and this branch's weights, fetched while the copies fly
   const uint32_t drop_ctr = (!s.keep && s.drop_p > 0.f) ? (uint32_t)__ldg(s.step_dev) : 0u;
   float y_first = 0.f;
   int y_cls = 0;
@@ -350,49 +405,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     if (s.task == 3) y_cls = (int)__ldg(s.y_class + g);
     else y_first = __ldg(s.y + (int64_t)g * out);
   }
-  bool ok = n >= 0 && K >= 0 && Q >= 0 && n <= a.max_n && K <= a.max_k && Q <= a.max_q;
-  int e00 = 0, E0 = 0, e10 = 0, E1 = 0, c10 = 0, m00 = 0, m10 = 0;
-  if (ok) {
-    // the feature tile first: it needs nothing but n0 / n
-    s2_stage128(xs, a.x + (int64_t)n0 * F, n * (F >> 2), t, T);
-    e00 = __ldg(a.rowptr0 + n0); E0 = __ldg(a.rowptr0 + n0 + n) - e00;
-    e10 = __ldg(a.rowptr1 + k0); E1 = __ldg(a.rowptr1 + k0 + K) - e10;
-    c10 = __ldg(a.cscptr1 + k0);
-    m00 = __ldg(a.cmptr0 + k0);  m10 = __ldg(a.cmptr1 + q0);
-    ok = E0 >= 0 && E1 >= 0 && E0 <= s.max_e && E1 <= P.max_e1;
-  }
-  if (!ok) {   // host bounds violated: flag and leave (checked by validate()); both CTAs take this branch
-    s2_wait<0>();
+  if (n < 0 || m < 0 || n > a.max_n || m > s.max_e) {   // host bounds violated: flag and leave (validate())
     if (t == 0) atomicOr(a.status, 64);
-    if (train && r == 0)
+    if (train && r == 0) {
 #pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
-    return;
+    }
+    return;   // both CTAs of the cluster take this branch
   }
-  // The peer CTA must be running before its shared memory is written (read-out exchange below):
-  // arrive now, wait just before the exchange, so the barrier costs nothing.
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  // ---- group 0 (forward): index slices of both levels
-  s2_stage32(rp0, a.rowptr0 + n0, n + 1, t, T);
-  s2_stage32(col0, a.col0 + e00, E0, t, T);
-  s2_stage32(rp1, a.rowptr1 + k0, K + 1, t, T);
-  s2_stage32(col1, a.col1 + e10, E1, t, T);
-  s2_stage32(cmp0, a.cmptr0 + k0, K + 1, t, T);
-  s2_stage32(cmem0, a.cmem0 + m00, n, t, T);
-  s2_stage32(cmp1, a.cmptr1 + q0, Q + 1, t, T);
-  s2_stage32(cmem1, a.cmem1 + m10, K, t, T);
-  s2_commit();
-  // ---- group 1 (head + backward): head weights, cluster ids, CSC of the coarsened graph
-  s2_stage128(fc1w, s.fc1_w, (Hd * C2) >> 2, t, T);
+  if (t == 0) {
+    s2_mbar_init(&bars[0], 1);
+    s2_mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bbytes = (uint32_t)DRGNN_BLOB_USED(n, m) * 4u, xbytes = (uint32_t)(n * F) * 4u;
+    s2_mbar_expect_tx(&bars[0], bbytes + xbytes);
+    s2_bulk_g2s(blb, s.blob + DRGNN_BLOB_OFFSET(g, n0, eg0), bbytes, &bars[0]);
+    if (xbytes) s2_bulk_g2s(xs, a.x + (int64_t)n0 * F, xbytes, &bars[0]);
+    const uint32_t wbytes = (uint32_t)(Hd * C2) * 4u;
+    s2_mbar_expect_tx(&bars[1], wbytes);
+    s2_bulk_g2s(fc1w, s.fc1_w, wbytes, &bars[1]);
+  }
+  // small head vectors (any alignment): cp.async
   s2_stage32(fc2w, s.fc2_w, out * Hd, t, T);
   if (s.fc1_b) s2_stage32(fc1b, s.fc1_b, Hd, t, T);
   if (s.fc2_b) s2_stage32(fc2b, s.fc2_b, out, t, T);
-  if (train) {
-    s2_stage32(cl0, a.cl0 + n0, n, t, T);
-    s2_stage32(cl1, a.cl1 + k0, K, t, T);
-    s2_stage32(cscp1, a.cscptr1 + k0, K + 1, t, T);
-    s2_stage32(cscr1, a.cscrow1 + c10, E1, t, T);
-  }
   s2_commit();
   // ---- this branch's weights, transposed through registers
 #pragma unroll 1
@@ -407,19 +443,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     w2[i] = v;
     w2t[j * H2 + o] = v;
   }
-  if (!s.fc1_b)
+  if (!s.fc1_b) {
 #pragma unroll 1
     for (int i = t; i < Hd; i += T) fc1b[i] = 0.f;
-  if (!s.fc2_b)
+  }
+  if (!s.fc2_b) {
 #pragma unroll 1
     for (int i = t; i < out; i += T) fc2b[i] = 0.f;
-  s2_wait<1>();
-  __syncthreads();
+  }
+  __syncthreads();               // barrier initialisation visible to every thread
+  s2_mbar_wait(&bars[0], 0);     // structure blob + feature tile have landed
+  const int K = blb[2], E1 = blb[3], Q = blb[4];
+  if (blb[5] != 1 || blb[0] != n || blb[1] != m || K > a.max_k || Q > a.max_q || K < 0 || Q < 0 || E1 < 0 || E1 > m) {
+    s2_mbar_wait(&bars[1], 0);   // no bulk copy may be in flight into a CTA that exits
+    s2_wait<0>();
+    if (t == 0) atomicOr(a.status, 64);
+    if (train && r == 0) {
+#pragma unroll 1
+      for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
+    }
+    return;
+  }
+  const BlobLayout BL = blob_layout(n, m);
+  const int* rp0 = blb + BL.rp0;     const int* col0 = blb + BL.col0;   const int* rp1 = blb + BL.rp1;  const int* col1 = blb + BL.col1;
+  const int* cmp0 = blb + BL.cmp0;   const int* cmem0 = blb + BL.cmem0; const int* cl0 = blb + BL.cl0;
+  const int* cmp1 = blb + BL.cmp1;   const int* cmem1 = blb + BL.cmem1; const int* cl1 = blb + BL.cl1;
+  const int* cscp1 = blb + BL.cscp1; const int* cscr1 = blb + BL.cscr1;
+  // The peer CTA must be running before its shared memory is written (read-out exchange below):
+  // arrive now, wait just before the exchange, so the barrier costs nothing.
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   DRGNN_PHASE(1);
 
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;
   // ---- AX = A x : the F/4 lanes of a row share its edge list and read whole 16-byte-aligned feature rows
-  s2_gather(rp0, col0, e00, n0, xs, F, ax, LDX, n, F4, t, T);
+  s2_gather(rp0, col0, 0, 0, xs, F, ax, LDX, n, F4, t, T);
   __syncthreads();
   DRGNN_PHASE(2);
   // ---- Z1 = relu(AX W1_r^T)
@@ -427,11 +484,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(3);
   // ---- P1 = cluster max of Z1 (community_pooling.py:201)
-  s2_cluster_max(cmp0, cmem0, m00, n0, z1, LDZ1, p1, LDP, arg0, H1, K, H14, t, T);
+  s2_cluster_max(cmp0, cmem0, 0, 0, z1, LDZ1, p1, LDP, arg0, H1, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(4);
   // ---- AP = A1 P1 on the coarsened graph
-  s2_gather(rp1, col1, e10, k0, p1, LDP, ap, LDP, K, H14, t, T);
+  s2_gather(rp1, col1, 0, 0, p1, LDP, ap, LDP, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(5);
   // ---- Z2 = relu(AP W2_r^T)
@@ -439,16 +496,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
-  s2_cluster_max(cmp1, cmem1, m10, k0, z2, LDZ2, p2, H2, arg1, H2, Q, H24, t, T);
+  s2_cluster_max(cmp1, cmem1, 0, 0, z2, LDZ2, p2, H2, arg1, H2, Q, H24, t, T);
   __syncthreads();
   DRGNN_PHASE(7);
-  if (mirror) {   // parity tests: the intermediates the single-CTA kernel leaves in global memory
-    if (r == 0) s2_mirror(ax, LDX, a.Zin1 + (int64_t)n0 * F, F, n, F4, t, T);
-    s2_mirror(z1, LDZ1, a.Z1 + (int64_t)n0 * C1 + co1, C1, n, H14, t, T);
-    s2_mirror(arg0, H1, a.arg0 + (int64_t)k0 * C1 + co1, C1, K, H14, t, T);
-    s2_mirror(ap, LDP, a.Zin2 + (int64_t)k0 * C1 + co1, C1, K, H14, t, T);
-    s2_mirror(z2, LDZ2, a.Z2 + (int64_t)k0 * C2 + co2, C2, K, H24, t, T);
-    s2_mirror(arg1, H2, a.arg1 + (int64_t)q0 * C2 + co2, C2, Q, H24, t, T);
+  if (mirror) {   // parity tests: the intermediates the single-CTA kernel leaves in global memory (global ids)
+    const int k0 = __ldg(a.kptr0 + g), q0 = __ldg(a.kptr1 + g);
+    if (r == 0) s2_mirror(ax, LDX, a.Zin1 + (int64_t)n0 * F, F, n, F4, 0, t, T);
+    s2_mirror(z1, LDZ1, a.Z1 + (int64_t)n0 * C1 + co1, C1, n, H14, 0, t, T);
+    s2_mirror(arg0, H1, a.arg0 + (int64_t)k0 * C1 + co1, C1, K, H14, n0 + 1, t, T);
+    s2_mirror(ap, LDP, a.Zin2 + (int64_t)k0 * C1 + co1, C1, K, H14, 0, t, T);
+    s2_mirror(z2, LDZ2, a.Z2 + (int64_t)k0 * C2 + co2, C2, K, H24, 0, t, T);
+    s2_mirror(arg1, H2, a.arg1 + (int64_t)q0 * C2 + co2, C2, Q, H24, k0 + 1, t, T);
   }
   // ---- R[g] half = mean over the graph's level-1 clusters; both halves land in both CTAs (DSMEM)
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -464,43 +522,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       peer_rrow[co2 + c] = acc;
     }
   }
-  s2_wait<0>();      // head weights / backward indices have landed (this thread's copies)
-  cluster.sync();    // ... everybody's, and the peer's half of the read-out row
+  s2_wait<0>();                // small head vectors (this thread's copies) ...
+  s2_mbar_wait(&bars[1], 0);   // ... and fc1.weight have landed
+  cluster.sync();              // everybody's copies, and the peer's half of the read-out row
   DRGNN_PHASE(8);
-  // ---- fc1 (both CTAs, identical results): a warp reduces 8 hidden units at once - 8 independent
-  // shuffle trees in flight instead of 8 dependent ones; per unit the arithmetic is the v1 chain
-  // (lanes over the read-out channels, xor butterfly), so predictions stay bit-identical.
+  // ---- fc1 (both CTAs, identical results): four lanes per hidden unit, each a quarter of the read-out
+  // channels as 16-byte loads, two shuffles to combine
+  {
+    const int sub = t & 3;
 #pragma unroll 1
-  for (int jb = warp * 8; jb < Hd; jb += NW * 8) {
-    float acc[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = jb + u;
+    for (int j = t >> 2; j < Hd; j += T >> 2) {
+      const float* wrow = fc1w + j * C2;
       float av = 0.f;
-      if (j < Hd) {
-#pragma unroll 1
-        for (int c = lane; c < C2; c += 32) av = fmaf(rrow[c], fc1w[j * C2 + c], av);
+#pragma unroll 2
+      for (int c = sub * 4; c < C2; c += 16) {
+        const float4 wv = *reinterpret_cast<const float4*>(wrow + c);
+        const float4 rv = *reinterpret_cast<const float4*>(rrow + c);
+        av = fmaf(rv.x, wv.x, av); av = fmaf(rv.y, wv.y, av); av = fmaf(rv.z, wv.z, av); av = fmaf(rv.w, wv.w, av);
       }
-      acc[u] = av;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) mine = (lane == u) ? acc[u] : mine;
-    const int j = jb + lane;
-    if (lane < 8 && j < Hd) {
-      float v = mine + fc1b[j];
-      v = v < 0.f ? 0.f : v;
-      if (s.keep) {
-        v = s.keep[(int64_t)g * Hd + j] > 0.f ? v * s.keep_scale : 0.f;
-      } else if (s.drop_p > 0.f) {
-        v = hash_uniform(s.seed, drop_ctr, (uint32_t)(g * Hd + j)) >= s.drop_p ? v * s.keep_scale : 0.f;
+      av += __shfl_xor_sync(0xffffffffu, av, 1);
+      av += __shfl_xor_sync(0xffffffffu, av, 2);
+      if (sub == 0) {
+        float v = av + fc1b[j];
+        v = v < 0.f ? 0.f : v;
+        if (s.keep) {
+          v = s.keep[(int64_t)g * Hd + j] > 0.f ? v * s.keep_scale : 0.f;
+        } else if (s.drop_p > 0.f) {
+          v = hash_uniform(s.seed, drop_ctr, (uint32_t)(g * Hd + j)) >= s.drop_p ? v * s.keep_scale : 0.f;
+        }
+        hrow[j] = v;
       }
-      hrow[j] = v;
     }
   }
   __syncthreads();
@@ -575,10 +626,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     for (int o = t; o < out; o += T) part[s.off_fc2b + o] = prow[o];
   }
   __syncthreads();
+  {   // fc1.weight gradient rows of this CTA's hidden units: dh[j] * R[g][:], 16-byte stores
+    const int C24 = C2 >> 2;
+    const S2Div dv(C24);
 #pragma unroll 1
-  for (int i = t; i < nj * C2; i += T) {
-    const int j = j0 + i / C2, c = i % C2;
-    part[s.off_fc1w + j * C2 + c] = dhrow[j] * rrow[c];
+    for (int i = t; i < nj * C24; i += T) {
+      int jj, c4;
+      dv.split(i, jj, c4);
+      const float dh = dhrow[j0 + jj];
+      float4 rv = *reinterpret_cast<const float4*>(rrow + c4 * 4);
+      rv.x *= dh; rv.y *= dh; rv.z *= dh; rv.w *= dh;
+      *reinterpret_cast<float4*>(part + s.off_fc1w + (j0 + jj) * C2 + c4 * 4) = rv;
+    }
   }
   // dR[c] of this branch's channels = sum_j dh[j] W1[j][co2 + c]: warps split the hidden units, fixed-order sum
 #pragma unroll 1
@@ -599,7 +658,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(11);
   // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU
-  s2_route(cl1, q0, arg1, H2, z2, LDZ2, drrow, 0, 1.f / (float)max(Q, 1), dz2, LDZ2, K, H24, k0, t, T);
+  s2_route(cl1, 0, arg1, H2, z2, LDZ2, drrow, 0, 1.f / (float)max(Q, 1), dz2, LDZ2, K, H24, 0, t, T);
   __syncthreads();
   DRGNN_PHASE(12);
   // ---- dW2_r = dZ2^T AP (split over the K0 rows, first half of the CTA)  ||  dAP = dZ2 W2_r (second half)
@@ -611,11 +670,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   DRGNN_PHASE(13);
   s2_splitk_reduce(scratch, H2 * H1, KS2, part + s.off_w2 + r * H2 * H1, t, T);
   // ---- dP1 = A1^T dAP  (CSC of the coarsened graph)
-  s2_gather(cscp1, cscr1, c10, k0, dap, LDP, dp1, LDP, K, H14, t, T);
+  s2_gather(cscp1, cscr1, 0, 0, dap, LDP, dp1, LDP, K, H14, t, T);
   __syncthreads();
   DRGNN_PHASE(14);
   // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU
-  s2_route(cl0, k0, arg0, H1, z1, LDZ1, dp1, LDP, 1.f, dz1, LDZ1, n, H14, n0, t, T);
+  s2_route(cl0, 0, arg0, H1, z1, LDZ1, dp1, LDP, 1.f, dz1, LDZ1, n, H14, 0, t, T);
   __syncthreads();
   DRGNN_PHASE(15);
   // ---- dW1_r [H1][F] = dZ1^T AX, split over the nodes
@@ -623,10 +682,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   s2_splitk_reduce(scratch, H1 * F, KS1, part + s.off_w1 + r * H1 * F, t, T);
   DRGNN_PHASE(16);
+  if (!P.fused_reduce) return;
+  // ---- gradient reduction (+ Adam) inside this launch: the grid is co-resident (2B <= SMs, one CTA
+  // per SM), so a grid barrier is safe; afterwards CTA c owns a slice of the flat gradient buffer and
+  // sums the per-graph rows in four contiguous quarters (ascending), combined in ascending order.
+  __syncthreads();
+  unsigned* sync_ctr = reinterpret_cast<unsigned*>(s.step_dev + 2);
+  if (t == 0) {
+    __threadfence();
+    atomicAdd(sync_ctr, 1u);
+    const unsigned G = gridDim.x;
+    const unsigned long long t0 = s2_globaltimer();
+    while (s2_ld_acquire(sync_ctr) < G) {
+      if (s2_globaltimer() - t0 > 200000000ull) {   // 0.2 s: something is badly wrong; flag and go on
+        atomicOr(a.status, 128);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int n = s.n_params, B = a.B;
+    const int per = (n + 1 + (int)gridDim.x - 1) / (int)gridDim.x;   // elements of this CTA, 128 per sweep
+    const int el = t & 127, q = t >> 7;
+    float* psum = xs;   // [4][128]
+    float* adamc = red; // [3]
+    if (s.fuse_adam && t == 0) {
+      const float st = s.step_dev[0] + 1.f;
+      adamc[0] = st;
+      adamc[1] = 1.f - (float)pow((double)s.beta1, (double)st);
+      adamc[2] = 1.f - (float)pow((double)s.beta2, (double)st);
+    }
+#pragma unroll 1
+    for (int sweep = 0; sweep < per; sweep += 128) {
+      const int e = (int)blockIdx.x * per + sweep + el;
+      const bool mine = sweep + el < per && e <= n;
+      float acc = 0.f;
+      if (mine) {
+        const int gs = (B + 3) >> 2;
+        const int g0 = q * gs, g1 = min(B, g0 + gs);
+        const float* src = s.partial + e;
+        int gg = g0;
+#pragma unroll 1
+        for (; gg + 8 <= g1; gg += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(gg + u) * s.partial_ld);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+#pragma unroll 1
+        for (; gg < g1; ++gg) acc += __ldcg(src + (int64_t)gg * s.partial_ld);
+      }
+      psum[q * 128 + el] = acc;
+      __syncthreads();
+      if (q == 0 && mine) {
+        acc = ((psum[el] + psum[128 + el]) + psum[256 + el]) + psum[384 + el];
+        if (e < n) {
+          s.grads[e] = acc;
+          if (s.fuse_adam) {
+            float mi = s.adam_m[e], vi = s.adam_v[e];
+            mi = mi + (acc - mi) * (1.f - s.beta1);
+            vi = vi * s.beta2 + (1.f - s.beta2) * acc * acc;
+            s.adam_m[e] = mi;
+            s.adam_v[e] = vi;
+            const float denom = sqrtf(vi) / sqrtf(adamc[2]) + s.eps;
+            s.adam_p[e] = s.adam_p[e] - (s.lr / adamc[1]) * (mi / denom);
+          }
+        } else if (s.loss) {
+          s.loss[0] = acc;
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (t == 0) {   // the last CTA to finish re-arms the barrier and bumps the optimiser step
+      unsigned* ticket = reinterpret_cast<unsigned*>(s.step_dev + 1);
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0u;
+        *sync_ctr = 0u;
+        if (s.fuse_adam) s.step_dev[0] = adamc[0];
+      }
+    }
+  }
 }
 
 static inline bool step2_shapes_ok(const drgnn_ginet_step_args& s) {
   const drgnn_ginet_fused_args& a = s.g;
-  return a.nb == 2 && a.F % 4 == 0 && a.h1 % 4 == 0 && a.h2 % 4 == 0 && s.max_e > 0 && a.max_n > 0 && a.max_k > 0 &&
-         a.max_q > 0 && s.Hd > 0 && s.out > 0 && ((2 * a.h2 * s.Hd) % 4 == 0);
+  return a.nb == 2 && s.blob != nullptr && s.edge_ptr != nullptr && a.F % 4 == 0 && a.h1 % 4 == 0 && a.h2 % 4 == 0 && s.max_e > 0 && a.max_n > 0 && a.max_k > 0 &&
+         a.max_q > 0 && s.Hd > 0 && s.out > 0 && ((2 * a.h2 * s.Hd) % 4 == 0) &&
+         // 16-byte stores of the fc1.weight gradient rows (training only)
+         (s.forward_only || s.task == 0 ||
+          (s.partial_ld % 4 == 0 && s.off_fc1w % 4 == 0 && ((uintptr_t)s.partial % 16) == 0));
 }

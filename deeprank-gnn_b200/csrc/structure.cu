@@ -85,10 +85,11 @@ __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) 
 // ---------------------------------------------------------------------------------------
 // Stable counting sort: slot[ptr[k] .. ptr[k+1]) = indices e (ascending) with key[e] == k.
 // The elements are cut into `nchunk` contiguous chunks, one per warp.  Pass 1 counts the keys of a
-// chunk into hist[key][chunk] (lanes holding the same key are found with match.any, the lowest one
-// adds the group's size: no atomics), an exclusive scan in (key major, chunk minor) order turns
-// the counts into the first slot of every (key, chunk), pass 2 places element e at that slot plus
-// its rank among the equal keys before it in the warp.  Deterministic and stable by construction.
+// chunk into hist[key][chunk] (shared-memory atomics, almost never colliding), a per-key prefix over
+// the chunks plus a scan over the keys give the first slot of every (key, chunk), pass 2 hands out
+// the slots of a group in arrival order and a checking sweep repairs the rare inversions (equal keys
+// inside one warp instruction).  match.any would give the rank directly but costs ~1000 cycles per
+// call on 32 distinct keys (tools/micro/lat.cu).  The result is the unique stable order.
 // ---------------------------------------------------------------------------------------
 // In-place exclusive scan of a[0..len) for len <= blockDim.x (one element per thread, two barriers);
 // longer arrays take the chunked block_exclusive_scan.  Returns the total.  All threads must call.
@@ -128,14 +129,7 @@ __device__ __noinline__ void csr_build(const uint16_t* key, int m, int n, int* p
   chunk = (chunk + 31) & ~31;
   const int beg = min(m, w * chunk), end = (w < nchunk) ? min(m, beg + chunk) : beg;
 #pragma unroll 1
-  for (int base = beg; base < end; base += 32) {
-    const int e = base + lane;
-    const bool valid = e < end;
-    const unsigned k = valid ? (unsigned)key[e] : 0xFFFFFFFFu;
-    const unsigned mask = __match_any_sync(0xffffffffu, k);
-    if (valid && lane == __ffs(mask) - 1) hist[k * hs + w] += __popc(mask);
-    __syncwarp();
-  }
+  for (int e = beg + lane; e < end; e += 32) atomicAdd(&hist[(int)key[e] * hs + w], 1);
   __syncthreads();
   // per key (one thread): exclusive prefix of its chunk counts in place, total into ptr[key]
 #pragma unroll 1
@@ -154,17 +148,31 @@ __device__ __noinline__ void csr_build(const uint16_t* key, int m, int n, int* p
   __syncthreads();
   block_scan_small(ptr, n + 1, wsum);    // ptr[k] = first slot of key k, ptr[n] = m
 #pragma unroll 1
-  for (int base = beg; base < end; base += 32) {
-    const int e = base + lane;
-    const bool valid = e < end;
-    const unsigned k = valid ? (unsigned)key[e] : 0xFFFFFFFFu;
-    const unsigned mask = __match_any_sync(0xffffffffu, k);
-    if (valid) slot[ptr[k] + hist[k * hs + w] + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)e;
-    __syncwarp();
-    if (valid && lane == __ffs(mask) - 1) hist[k * hs + w] += __popc(mask);
-    __syncwarp();
+  for (int e = beg + lane; e < end; e += 32) {
+    const int k = key[e];
+    slot[ptr[k] + atomicAdd(&hist[k * hs + w], 1)] = (uint16_t)e;
   }
   __syncthreads();
+  // Elements of one (key, chunk) group that met in the same warp instruction got their slots in the
+  // order the hardware resolved the colliding atomics: a segmented odd-even transposition restores
+  // ascending e (usually nothing to swap: one checking sweep).
+  for (;;) {
+    int swapped = 0;
+#pragma unroll 1
+    for (int parity = 0; parity < 2; ++parity) {
+#pragma unroll 1
+      for (int p = 2 * t + parity; p + 1 < m; p += 2 * T) {
+        const uint16_t a = slot[p], b = slot[p + 1];
+        if (a > b && key[a] == key[b]) {
+          slot[p] = b;
+          slot[p + 1] = a;
+          swapped = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(swapped)) break;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -321,6 +329,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   const int n0 = io.node_ptr[g], n = io.node_ptr[g + 1] - n0;
   const int e0 = io.edge_ptr[g], m = io.edge_ptr[g + 1] - e0;
   const int ne = io.ne;
+  // per-graph structure blob (graph-local indices, one contiguous block; see drgnn.h)
+  int32_t* bl = io.blob ? io.blob + DRGNN_BLOB_OFFSET(g, n0, e0) : nullptr;
+  const BlobLayout BL = blob_layout(n, m);
+  if (bl && t < DRGNN_BLOB_HEADER) bl[t] = 0;   // header[5] (complete) is set at the very end
 
   DRGNN_SPHASE(0);
   // ---- 1. local edge list ----
@@ -349,6 +361,11 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     io.col0[e0 + p] = n0 + ecol[e];
     io.eid0[e0 + p] = e0 + e;
     if (io.w0csr) io.w0csr[e0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
+    if (bl) bl[BL.col0 + p] = ecol[e];
+  }
+  if (bl) {
+#pragma unroll 1
+    for (int i = t; i <= n; i += T) bl[BL.rp0 + i] = ptrR[i];
   }
   DRGNN_SPHASE(2);
   // ---- 3. CSC (transposed graph) ----
@@ -378,6 +395,15 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   for (int k = t; k <= K; k += T) S.mptr0[n0 + g + k] = mptr[k];
 #pragma unroll 1
   for (int p = t; p < n; p += T) io.cmem0[n0 + p] = n0 + mem[p];
+  if (bl) {
+#pragma unroll 1
+    for (int k = t; k <= K; k += T) bl[BL.cmp0 + k] = mptr[k];
+#pragma unroll 1
+    for (int p = t; p < n; p += T) {
+      bl[BL.cmem0 + p] = mem[p];
+      bl[BL.cl0 + p] = dense0[p];
+    }
+  }
 
   DRGNN_SPHASE(5);
   // ---- 6. coarsened edges: per pooled row a column bitmap -> sorted unique columns ----
@@ -465,6 +491,11 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   for (int p = t; p < E1; p += T) {
     S.col1[e0 + p] = pcol[p];
     S.row1[e0 + p] = prow[p];
+    if (bl) bl[BL.col1 + p] = pcol[p];
+  }
+  if (bl) {
+#pragma unroll 1
+    for (int r = t; r <= K; r += T) bl[BL.rp1 + r] = rowptr1[r];
   }
   __syncthreads();
 
@@ -480,6 +511,11 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     int q = slotC1[p];
     S.cscrow1[e0 + p] = prow[q];
     S.csceid1[e0 + p] = q;
+    if (bl) bl[BL.cscr1 + p] = prow[q];
+  }
+  if (bl) {
+#pragma unroll 1
+    for (int r = t; r <= K; r += T) bl[BL.cscp1 + r] = ptrC1[r];
   }
   __syncthreads();
 
@@ -502,6 +538,15 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     for (int q = t; q <= K1; q += T) S.mptr1[c0 + g + q] = mptr1[q];
 #pragma unroll 1
     for (int p = t; p < c1len; p += T) S.mem1[c0 + p] = mem1[p];
+    if (bl) {
+#pragma unroll 1
+      for (int q = t; q <= K1; q += T) bl[BL.cmp1 + q] = mptr1[q];
+#pragma unroll 1
+      for (int p = t; p < min(c1len, n); p += T) {
+        bl[BL.cmem1 + p] = mem1[p];
+        bl[BL.cl1 + p] = dense1[p];
+      }
+    }
   }
 
   DRGNN_SPHASE(8);
@@ -515,6 +560,10 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     gs[5] = (int32_t)(cmax & 0xffffffffll);
     gs[6] = (int32_t)(cmax >> 32);
     gs[7] = n;
+    if (bl) {
+      bl[0] = n; bl[1] = m; bl[2] = K; bl[3] = E1; bl[4] = K1;
+      bl[5] = (io.cluster1 != nullptr && c1len == K) ? 1 : 0;
+    }
   }
 }
 

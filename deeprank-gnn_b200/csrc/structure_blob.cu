@@ -1,0 +1,439 @@
+// Structure pass of the per-graph fused kernels: ONE launch, one CTA per graph, output = the graph's
+// structure blob (include/drgnn.h, drgnn_structure_io.blob) and nothing else.
+//
+// Same results as graph_local_kernel (structure.cu), i.e. bit-exact replacements of
+//   get_preloaded_cluster / consecutive_cluster   community_pooling.py:25-30, 197; ginet.py:114,129
+//   pool_edge + coalesce (structure only)          community_pooling.py:204-205
+//   the dst-sorted CSR the aggregation reads instead of x[col] + scatter_add (ginet.py:57-71)
+// but built for the graphs the fused step kernel takes (a few hundred nodes, a few thousand edges):
+// every sorted list is read off a BITMAP instead of being produced by a counting sort -
+//   row i of the level-0 CSR        = set bits of rowbits[i][.]  over the edge ids      (ascending e)
+//   pooled row r / pooled column c  = set bits of bm[r][.] / bmT[c][.] over pooled ids   (sorted, unique)
+//   members of cluster k / q        = set bits of mem0[k][.] / mem1[q][.] over node ids  (ascending)
+// so the whole pass is: load -> two presence bitmaps + popcount prefixes (dense relabel of both
+// cluster levels) -> ONE scatter sweep of atomicOr -> ONE exclusive scan over all row counts ->
+// ONE emit sweep (a thread per item ranks itself by popcounts).  About a dozen CTA barriers in total; the
+// counting-sort pass needs ~60.  Nothing cross-graph is computed: the blob holds graph-local indices
+// and the fused kernels need no global offsets (no finalize launch).
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace drgnn {
+
+static constexpr int SB_THREADS = 512;
+static constexpr int SB_WARPS = SB_THREADS / 32;
+static constexpr int SB_CAP_WORDS = 1024;        // presence bitmap: cluster-id range of one graph <= 32768
+static constexpr int SB_ROWBITS_MAX = 20 * 1024; // words of the level-0 row bitmap (80 KB)
+
+__device__ unsigned long long g_bphase[16];
+#define DRGNN_BPHASE(i)                                                         \
+  do {                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_bphase[i] = (unsigned long long)clock64(); \
+  } while (0)
+
+struct BlobPlan {   // word offsets into dynamic shared memory
+  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, rowbits, bm, bmT, mem0, mem1, cnt, total;
+  int mw1;   // row stride of rowbits: ceil(max_e/32) + 1 (odd strides keep a thread-per-row walk conflict-free)
+  int kw1;   // row stride of the pooled / member bitmaps: ceil(max_n/32) + 1
+};
+__host__ __device__ inline int sb_up4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e) {
+  BlobPlan p;
+  int o = 0;
+  auto take = [&](int words) { const int at = o; o += sb_up4(words); return at; };
+  p.mw1 = ((max_e + 31) >> 5) | 1;
+  if (p.mw1 == ((max_e + 31) >> 5)) p.mw1 += 2;   // odd and strictly larger than the word count
+  p.kw1 = ((max_n + 31) >> 5) | 1;
+  if (p.kw1 == ((max_n + 31) >> 5)) p.kw1 += 2;
+  p.erow = take((max_e + 1) / 2);
+  p.ecol = take((max_e + 1) / 2);
+  p.id0 = take(max_n);
+  p.id1 = take(max_n);
+  p.dense0 = take((max_n + 1) / 2);
+  p.dense1 = take((max_n + 1) / 2);
+  p.cb0 = take(SB_CAP_WORDS);
+  p.cb1 = take(SB_CAP_WORDS);
+  p.cp0 = take(SB_CAP_WORDS);
+  p.cp1 = take(SB_CAP_WORDS);
+  p.rowbits = take(max_n * p.mw1);
+  p.bm = take(max_n * p.kw1);
+  p.bmT = take(max_n * p.kw1);
+  p.mem0 = take(max_n * p.kw1);
+  p.mem1 = take(max_n * p.kw1);
+  p.cnt = take(5 * max_n + 8);
+  p.total = o;
+  return p;
+}
+
+__device__ __forceinline__ long long sb_ld_id(const void* base, int64_t i, int idx32) {
+  return idx32 ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
+}
+
+// min / max over the CTA of two value pairs at once (level-0 and level-1 cluster ids); results in red[0..3]
+__device__ __noinline__ void sb_minmax2(long long mn0, long long mx0, long long mn1, long long mx1, long long* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, mn0, o), b = __shfl_xor_sync(0xffffffffu, mx0, o);
+    const long long c = __shfl_xor_sync(0xffffffffu, mn1, o), d = __shfl_xor_sync(0xffffffffu, mx1, o);
+    mn0 = a < mn0 ? a : mn0; mx0 = b > mx0 ? b : mx0;
+    mn1 = c < mn1 ? c : mn1; mx1 = d > mx1 ? d : mx1;
+  }
+  if (lane == 0) {
+    red[4 + 4 * w + 0] = mn0; red[4 + 4 * w + 1] = mx0; red[4 + 4 * w + 2] = mn1; red[4 + 4 * w + 3] = mx1;
+  }
+  __syncthreads();
+  if (w == 0) {
+    mn0 = lane < SB_WARPS ? red[4 + 4 * lane + 0] : LLONG_MAX;
+    mx0 = lane < SB_WARPS ? red[4 + 4 * lane + 1] : LLONG_MIN;
+    mn1 = lane < SB_WARPS ? red[4 + 4 * lane + 2] : LLONG_MAX;
+    mx1 = lane < SB_WARPS ? red[4 + 4 * lane + 3] : LLONG_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long a = __shfl_xor_sync(0xffffffffu, mn0, o), b = __shfl_xor_sync(0xffffffffu, mx0, o);
+      const long long c = __shfl_xor_sync(0xffffffffu, mn1, o), d = __shfl_xor_sync(0xffffffffu, mx1, o);
+      mn0 = a < mn0 ? a : mn0; mx0 = b > mx0 ? b : mx0;
+      mn1 = c < mn1 ? c : mn1; mx1 = d > mx1 ? d : mx1;
+    }
+    if (lane == 0) {
+      red[0] = mn0; red[1] = mx0; red[2] = mn1; red[3] = mx1;
+    }
+  }
+  __syncthreads();
+}
+
+// exclusive popcount prefix of `W` presence words (cpre) by one warp (W <= 32) or the CTA; total -> *K
+__device__ __forceinline__ void sb_prefix_warp(const uint32_t* cb, int* cp, int W, int* Kout) {
+  const int lane = threadIdx.x & 31;
+  const int c = lane < W ? __popc(cb[lane]) : 0;
+  const int incl = warp_scan_incl(c);
+  if (lane < W) cp[lane] = incl - c;
+  if (lane == 31) *Kout = incl;
+}
+
+__global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_structure_io io, const BlobPlan P) {
+  extern __shared__ __align__(16) uint32_t sb[];
+  __shared__ long long red[4 + 4 * SB_WARPS];
+  __shared__ int wsum[33];
+  __shared__ int sK[2];
+  const int T = SB_THREADS, t = threadIdx.x, w = t >> 5;
+  const int g = blockIdx.x;
+  uint16_t* erow = reinterpret_cast<uint16_t*>(sb + P.erow);
+  uint16_t* ecol = reinterpret_cast<uint16_t*>(sb + P.ecol);
+  int* id0 = reinterpret_cast<int*>(sb + P.id0);
+  int* id1 = reinterpret_cast<int*>(sb + P.id1);
+  uint16_t* dense0 = reinterpret_cast<uint16_t*>(sb + P.dense0);
+  uint16_t* dense1 = reinterpret_cast<uint16_t*>(sb + P.dense1);
+  uint32_t* cb0 = sb + P.cb0; uint32_t* cb1 = sb + P.cb1;
+  int* cp0 = reinterpret_cast<int*>(sb + P.cp0);
+  int* cp1 = reinterpret_cast<int*>(sb + P.cp1);
+  uint32_t* rowbits = sb + P.rowbits;
+  uint32_t* bm = sb + P.bm; uint32_t* bmT = sb + P.bmT; uint32_t* mem0 = sb + P.mem0; uint32_t* mem1 = sb + P.mem1;
+  int* cnt = reinterpret_cast<int*>(sb + P.cnt);
+  const int MW1 = P.mw1, KW1 = P.kw1;
+  DRGNN_BPHASE(0);
+
+  const int n0 = io.node_ptr[g], n = io.node_ptr[g + 1] - n0;
+  const int e0 = io.edge_ptr[g], m = io.edge_ptr[g + 1] - e0;
+  const int c0 = io.c1_ptr[g];
+  int c1len = io.c1_ptr[g + 1] - c0;
+  int32_t* bl = io.blob + DRGNN_BLOB_OFFSET(g, n0, e0);
+  const BlobLayout BL = blob_layout(n, m);
+  if (t < DRGNN_BLOB_HEADER) bl[t] = 0;
+  if (n < 0 || m < 0 || n > io.max_n || m > io.max_e) {   // host bounds violated: header stays incomplete
+    if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
+    return;
+  }
+  bool bad1 = c1len > io.max_n || c1len < 0;
+  if (bad1) c1len = 0;
+
+  // ---- 0. zero every bitmap (the presence words follow once the id ranges are known)
+  {
+    const int MW = (m + 31) >> 5, KWn = (n + 31) >> 5;
+#pragma unroll 1
+    for (int i = t; i < n * MW1; i += T) rowbits[i] = 0u;
+#pragma unroll 1
+    for (int i = t; i < n * KW1; i += T) {
+      bm[i] = 0u; bmT[i] = 0u; mem0[i] = 0u; mem1[i] = 0u;
+    }
+    (void)MW; (void)KWn;
+  }
+  // ---- 1. local edge list; cluster ids of both levels (read from global memory once), their extremes
+#pragma unroll 1
+  for (int e = t; e < m; e += T) {
+    long long r = sb_ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
+    long long c = sb_ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
+    if (r < 0 || r >= n || c < 0 || c >= n) {
+      atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
+      r = 0;
+      c = 0;
+    }
+    erow[e] = (uint16_t)r;
+    ecol[e] = (uint16_t)c;
+  }
+  long long mn0 = LLONG_MAX, mx0 = LLONG_MIN, mn1 = LLONG_MAX, mx1 = LLONG_MIN;
+  // raw ids are kept in registers for graphs of up to 2 * T nodes (else re-read)
+  long long r0a = 0, r0b = 0, r1a = 0, r1b = 0;
+  if (t < n) { r0a = sb_ld_id(io.cluster0, (int64_t)n0 + t, io.idx32); mn0 = r0a; mx0 = r0a; }
+  if (t + T < n) { r0b = sb_ld_id(io.cluster0, (int64_t)n0 + t + T, io.idx32); mn0 = r0b < mn0 ? r0b : mn0; mx0 = r0b > mx0 ? r0b : mx0; }
+#pragma unroll 1
+  for (int i = t + 2 * T; i < n; i += T) {
+    const long long v = sb_ld_id(io.cluster0, (int64_t)n0 + i, io.idx32);
+    mn0 = v < mn0 ? v : mn0; mx0 = v > mx0 ? v : mx0;
+  }
+  if (t < c1len) { r1a = sb_ld_id(io.cluster1, (int64_t)c0 + t, io.idx32); mn1 = r1a; mx1 = r1a; }
+  if (t + T < c1len) { r1b = sb_ld_id(io.cluster1, (int64_t)c0 + t + T, io.idx32); mn1 = r1b < mn1 ? r1b : mn1; mx1 = r1b > mx1 ? r1b : mx1; }
+#pragma unroll 1
+  for (int i = t + 2 * T; i < c1len; i += T) {
+    const long long v = sb_ld_id(io.cluster1, (int64_t)c0 + i, io.idx32);
+    mn1 = v < mn1 ? v : mn1; mx1 = v > mx1 ? v : mx1;
+  }
+  if (io.idx32) {   // int32 ids (packed feeder batches): hardware warp reductions, then 16 values per extreme
+    const int a0 = __reduce_min_sync(0xffffffffu, (int)(mn0 > INT_MAX ? INT_MAX : mn0));
+    const int b0 = __reduce_max_sync(0xffffffffu, (int)(mx0 < INT_MIN ? INT_MIN : mx0));
+    const int a1 = __reduce_min_sync(0xffffffffu, (int)(mn1 > INT_MAX ? INT_MAX : mn1));
+    const int b1 = __reduce_max_sync(0xffffffffu, (int)(mx1 < INT_MIN ? INT_MIN : mx1));
+    int* r32 = reinterpret_cast<int*>(red);
+    if ((t & 31) == 0) { r32[4 * w] = a0; r32[4 * w + 1] = b0; r32[4 * w + 2] = a1; r32[4 * w + 3] = b1; }
+    __syncthreads();
+    int v0 = INT_MAX, v1 = INT_MIN, v2 = INT_MAX, v3 = INT_MIN;
+#pragma unroll
+    for (int u = 0; u < SB_WARPS; ++u) {
+      v0 = min(v0, r32[4 * u]); v1 = max(v1, r32[4 * u + 1]); v2 = min(v2, r32[4 * u + 2]); v3 = max(v3, r32[4 * u + 3]);
+    }
+    mn0 = v0; mx0 = v1; mn1 = v2; mx1 = v3;
+  } else {
+    sb_minmax2(mn0, mx0, mn1, mx1, red);
+    mn0 = red[0]; mx0 = red[1]; mn1 = red[2]; mx1 = red[3];
+  }
+  DRGNN_BPHASE(1);
+  // ---- 2. presence bitmaps over the id ranges
+  const long long range0 = n > 0 ? mx0 - mn0 + 1 : 0, range1 = c1len > 0 ? mx1 - mn1 + 1 : 0;
+  bool bad_range = range0 > (long long)SB_CAP_WORDS * 32 || range1 > (long long)SB_CAP_WORDS * 32;
+  if ((n > 0 && mn0 < 0) || (c1len > 0 && mn1 < 0)) {
+    if (t == 0) atomicOr(io.status, DRGNN_ST_NEGATIVE_ID);
+  }
+  if (bad_range) {   // same flag as the full pass; the blob stays incomplete (the step kernel refuses it)
+    if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER_RANGE);
+    return;
+  }
+  const int W0 = (int)((range0 + 31) >> 5), W1c = (int)((range1 + 31) >> 5);
+#pragma unroll 1
+  for (int i = t; i < W0; i += T) cb0[i] = 0u;
+#pragma unroll 1
+  for (int i = t; i < W1c; i += T) cb1[i] = 0u;
+  __syncthreads();
+  if (t < n) { const int v = (int)(r0a - mn0); id0[t] = v; atomicOr(&cb0[v >> 5], 1u << (v & 31)); }
+  if (t + T < n) { const int v = (int)(r0b - mn0); id0[t + T] = v; atomicOr(&cb0[v >> 5], 1u << (v & 31)); }
+#pragma unroll 1
+  for (int i = t + 2 * T; i < n; i += T) {
+    const int v = (int)(sb_ld_id(io.cluster0, (int64_t)n0 + i, io.idx32) - mn0);
+    id0[i] = v;
+    atomicOr(&cb0[v >> 5], 1u << (v & 31));
+  }
+  if (t < c1len) { const int v = (int)(r1a - mn1); id1[t] = v; atomicOr(&cb1[v >> 5], 1u << (v & 31)); }
+  if (t + T < c1len) { const int v = (int)(r1b - mn1); id1[t + T] = v; atomicOr(&cb1[v >> 5], 1u << (v & 31)); }
+#pragma unroll 1
+  for (int i = t + 2 * T; i < c1len; i += T) {
+    const int v = (int)(sb_ld_id(io.cluster1, (int64_t)c0 + i, io.idx32) - mn1);
+    id1[i] = v;
+    atomicOr(&cb1[v >> 5], 1u << (v & 31));
+  }
+  __syncthreads();
+  // ---- 3. popcount prefixes -> number of clusters of both levels
+  if (W0 <= 32 && W1c <= 32) {
+    if (w == 0) sb_prefix_warp(cb0, cp0, W0, &sK[0]);
+    if (w == 1) sb_prefix_warp(cb1, cp1, W1c, &sK[1]);
+    __syncthreads();
+  } else {
+#pragma unroll 1
+    for (int i = t; i < W0; i += T) cp0[i] = __popc(cb0[i]);
+#pragma unroll 1
+    for (int i = t; i < W1c; i += T) cp1[i] = __popc(cb1[i]);
+    __syncthreads();
+    const int k0 = block_exclusive_scan(cp0, W0, wsum);
+    const int k1 = block_exclusive_scan(cp1, W1c, wsum);
+    if (t == 0) { sK[0] = k0; sK[1] = k1; }
+    __syncthreads();
+  }
+  const int K = sK[0], K1 = sK[1];
+  if (c1len != K || bad1) {
+    if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER1_LENGTH);
+    bad1 = true;
+  }
+  DRGNN_BPHASE(2);
+  // ---- 4. dense ids (consecutive_cluster restricted to the graph); into the blob as cl0 / cl1
+#pragma unroll 1
+  for (int i = t; i < n; i += T) {
+    const int v = id0[i];
+    const int d = cp0[v >> 5] + __popc(cb0[v >> 5] & ((1u << (v & 31)) - 1u));
+    dense0[i] = (uint16_t)d;
+    bl[BL.cl0 + i] = d;
+  }
+#pragma unroll 1
+  for (int i = t; i < c1len; i += T) {
+    const int v = id1[i];
+    const int d = cp1[v >> 5] + __popc(cb1[v >> 5] & ((1u << (v & 31)) - 1u));
+    dense1[i] = (uint16_t)d;
+    if (i < n) bl[BL.cl1 + i] = d;
+  }
+  __syncthreads();
+  // ---- 5. ONE scatter sweep: every sorted list of the blob becomes a bitmap row, and every row is
+  // counted on the way (a pooled edge counts when its bit was not set before: coalesce's unique)
+  //   cnt: [0, n) level-0 CSR rows | [n, n+K) pooled rows | [n+K, n+2K) pooled columns
+  //        [n+2K, n+3K) members of cluster k | [n+3K, n+3K+K1) members of level-1 cluster q
+  const int L = n + 3 * K + K1;
+#pragma unroll 1
+  for (int i = t; i <= L; i += T) cnt[i] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int e = t; e < m; e += T) {
+    const int r = erow[e], c = ecol[e];
+    atomicOr(&rowbits[r * MW1 + (e >> 5)], 1u << (e & 31));
+    atomicAdd(&cnt[r], 1);
+    const int pr = dense0[r], pc = dense0[c];
+    if (pr != pc) {   // remove_self_loops of pool_edge
+      const uint32_t bit = 1u << (pc & 31);
+      if (!(atomicOr(&bm[pr * KW1 + (pc >> 5)], bit) & bit)) {   // first edge of this pooled pair
+        atomicOr(&bmT[pc * KW1 + (pr >> 5)], 1u << (pr & 31));
+        atomicAdd(&cnt[n + pr], 1);
+        atomicAdd(&cnt[n + K + pc], 1);
+      }
+    }
+  }
+#pragma unroll 1
+  for (int i = t; i < n; i += T) {
+    const int k = dense0[i];
+    atomicOr(&mem0[k * KW1 + (i >> 5)], 1u << (i & 31));
+    atomicAdd(&cnt[n + 2 * K + k], 1);
+  }
+#pragma unroll 1
+  for (int i = t; i < c1len; i += T) {
+    const int q = dense1[i];
+    atomicOr(&mem1[q * KW1 + (i >> 5)], 1u << (i & 31));
+    atomicAdd(&cnt[n + 3 * K + q], 1);
+  }
+  __syncthreads();
+  DRGNN_BPHASE(3);
+  // ---- 6. ONE exclusive scan over all row counts
+  block_exclusive_scan(cnt, L + 1, wsum);
+  const int base1 = cnt[n], baseT = cnt[n + K], baseM0 = cnt[n + 2 * K], baseM1 = cnt[n + 3 * K];
+  const int E1 = baseT - base1;
+  const int KWk = (K + 31) >> 5;
+  DRGNN_BPHASE(4);
+  // ---- 7. ONE emit sweep, a thread per ITEM: its slot = start of its row + number of set bits of the
+  // row below its own bit (popcount of the words before + of the lower bits of its word)
+#pragma unroll 1
+  for (int e = t; e < m; e += T) {          // level-0 CSR: ascending edge id inside a row = the CPU scatter order
+    const int r = erow[e], wi = e >> 5;
+    const uint32_t* row = rowbits + r * MW1;
+    int pos = cnt[r] + __popc(row[wi] & ((1u << (e & 31)) - 1u));
+#pragma unroll 4
+    for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
+    bl[BL.col0 + pos] = ecol[e];
+  }
+#pragma unroll 1
+  for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
+    bl[BL.rp0 + i] = cnt[i];
+    const int k = dense0[i], wi = i >> 5;
+    const uint32_t* row = mem0 + k * KW1;
+    int pos = cnt[n + 2 * K + k] - baseM0 + __popc(row[wi] & ((1u << (i & 31)) - 1u));
+#pragma unroll 1
+    for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
+    bl[BL.cmem0 + pos] = i;
+  }
+#pragma unroll 1
+  for (int i = t; i < c1len; i += T) {      // members of the level-1 clusters, ascending pooled-node id
+    const int q = dense1[i], wi = i >> 5;
+    const uint32_t* row = mem1 + q * KW1;
+    int pos = cnt[n + 3 * K + q] - baseM1 + __popc(row[wi] & ((1u << (i & 31)) - 1u));
+#pragma unroll 1
+    for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
+    bl[BL.cmem1 + pos] = i;
+  }
+#pragma unroll 1
+  for (int k = t; k < K; k += T) {          // row pointers of the pooled lists
+    bl[BL.rp1 + k] = cnt[n + k] - base1;
+    bl[BL.cscp1 + k] = cnt[n + K + k] - baseT;
+    bl[BL.cmp0 + k] = cnt[n + 2 * K + k] - baseM0;
+  }
+#pragma unroll 1
+  for (int q = t; q < K1; q += T) bl[BL.cmp1 + q] = cnt[n + 3 * K + q] - baseM1;
+  // pooled rows / columns: a thread per (row, word) emits the set bits of its word (sorted, unique)
+#pragma unroll 1
+  for (int item = t; item < 2 * K * KWk; item += T) {
+    const int which = item >= K * KWk;
+    const int it = which ? item - K * KWk : item;
+    const int r = it / KWk, wi = it - r * KWk;
+    const uint32_t* row = (which ? bmT : bm) + r * KW1;
+    int q = which ? cnt[n + K + r] - baseT : cnt[n + r] - base1;
+#pragma unroll 1
+    for (int ww = 0; ww < wi; ++ww) q += __popc(row[ww]);
+    int32_t* dst = bl + (which ? BL.cscr1 : BL.col1);
+    uint32_t bits = row[wi];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      dst[q++] = wi * 32 + b;
+    }
+  }
+  if (t == 0) {   // closing pointers and the header
+    bl[BL.rp0 + n] = m;
+    bl[BL.rp1 + K] = E1;
+    bl[BL.cscp1 + K] = E1;
+    bl[BL.cmp0 + K] = n;
+    bl[BL.cmp1 + K1] = c1len;
+    bl[0] = n; bl[1] = m; bl[2] = K; bl[3] = E1; bl[4] = K1;
+    bl[5] = bad1 ? 0 : 1;
+    int32_t* gs = io.gstat + 8 * g;
+    gs[0] = K; gs[1] = E1; gs[2] = K1; gs[7] = n;
+  }
+  DRGNN_BPHASE(5);
+}
+
+}  // namespace drgnn
+
+using namespace drgnn;
+
+extern "C" int64_t drgnn_structure_blob_smem_bytes(int32_t max_n, int32_t max_e) {
+  if (max_n <= 0 || max_e < 0) return DRGNN_ERR_INVALID;
+  if (max_n > 16384 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;
+  const BlobPlan p = blob_plan(max_n, max_e);
+  if ((int64_t)max_n * p.mw1 > SB_ROWBITS_MAX) return DRGNN_ERR_UNSUPPORTED;
+  const int64_t bytes = 4 * (int64_t)p.total;
+  if (bytes > device_info().smem_optin - 4096) return DRGNN_ERR_UNSUPPORTED;
+  return bytes;
+}
+
+// Blob-only structure pass (the inputs of drgnn_structure_build; outputs: io->blob, io->status,
+// io->gstat).  The caller zeroes status.  DRGNN_ERR_UNSUPPORTED when a graph of max_n / max_e does
+// not fit the bitmap kernel: run drgnn_structure_build (which also writes the blob) instead.
+extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) {
+  DRGNN_REQUIRE(io != nullptr, "structure_blob: io is NULL");
+  DRGNN_REQUIRE(io->B >= 0 && io->N >= 0 && io->E >= 0, "structure_blob: negative size");
+  if (io->B == 0) return DRGNN_OK;
+  DRGNN_REQUIRE(io->node_ptr && io->edge_ptr && io->edge_index && io->cluster0 && io->c1_ptr && io->cluster1,
+                "structure_blob: NULL input (both cluster levels are required)");
+  DRGNN_REQUIRE(io->blob && io->status && io->gstat, "structure_blob: NULL output");
+  const int64_t smem = drgnn_structure_blob_smem_bytes(io->max_n, io->max_e);
+  if (smem < 0)
+    return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges does not fit the bitmap kernel",
+                io->max_n, io->max_e);
+  static thread_local int64_t configured = -1;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(graph_blob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)device_info().smem_optin - 4096));
+    configured = device_info().smem_optin - 4096;
+  }
+  const BlobPlan plan = blob_plan(io->max_n, io->max_e);
+  graph_blob_kernel<<<io->B, SB_THREADS, smem, (cudaStream_t)stream>>>(*io, plan);
+  DRGNN_CHECK_LAUNCH("graph_blob_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_debug_blob_cycles(uint64_t* out16) {
+  DRGNN_REQUIRE(out16 != nullptr, "debug_blob_cycles: NULL");
+  DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out16, g_bphase, sizeof(unsigned long long) * 16));
+  return DRGNN_OK;
+}

@@ -280,7 +280,9 @@ class Engine(object):
         self._adam_done = False
         self.fuse_adam = True
         self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
+        self.blob_structure = os.environ.get('DRGNN_BLOB_STRUCTURE', '1') != '0'   # one-launch bitmap structure pass
         self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
+        self.fuse_reduce = os.environ.get('DRGNN_FUSE_REDUCE', '1') != '0'   # gradient reduction + Adam behind a grid barrier
         self.seed = 0x5EED if seed is None else int(seed)
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
@@ -410,12 +412,36 @@ class Engine(object):
         if need_w and d.edge_attr.size(1) != 1:
             raise DrgnnError('sGAT supports one edge feature (the reference broadcast needs ne in {1, Fout})')
         slot = self.structs[d.sslot]
+        if self._blob_only(d):
+            # fused GINet path: ONE launch writes the per-graph structure blobs, nothing else
+            st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
+                                    d.cluster1, out=slot, L1=d.L1)
+            if slot is None:
+                self.structs[d.sslot] = st
+            self._last_struct = st
+            return st
         st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
                                  c1_ptr=d.c1_ptr, cluster1=d.cluster1, edge_attr=d.edge_attr if need_w else None,
                                  clusters_are_local=True, mirrors=False, out=slot, L1=d.L1)
         assert st is slot
         self._last_struct = st
         return st
+
+    def _blob_only(self, d):
+        """True when the step of batch ``d`` runs the cluster whole-step kernel, which stages the
+        per-graph structure blobs and needs none of the global structure arrays: the structure pass
+        is then the one-launch bitmap kernel (``ops.structure_blob``)."""
+        s = self.spec
+        if not (self.blob_structure and self.fused_head and self.step_variant != 1 and not self.keep_intermediates
+                and s.nb == 2 and d.cluster1 is not None and d.c1_ptr is not None and self._use_fused_graph(d)):
+            return False
+        key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'blob')
+        fit = self._fused_fit.get(key)
+        if fit is None:
+            fit = (ops.ginet_step2_smem_bytes(s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out) >= 0
+                   and ops.structure_blob_fits(d.max_n, d.max_e) and s.F % 4 == 0 and s.h1 % 4 == 0 and s.h2 % 4 == 0)
+            self._fused_fit[key] = fit
+        return fit
 
     def _use_fused_graph(self, d):
         s = self.spec
@@ -497,7 +523,9 @@ class Engine(object):
                                adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
                                          beta2=self.betas[1], eps=self.eps) if fuse_adam else None,
                                skip_reduce=use_comm, max_e=d.max_e, mirror=self.keep_intermediates,
-                               variant=self.step_variant)
+                               variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
+                               blob=st.blob,
+                               edge_ptr=d.edge_ptr)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._adam_done = fuse_adam
                 if use_comm:

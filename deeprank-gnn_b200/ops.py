@@ -40,7 +40,7 @@ def _i32(t, name):
 # ------------------------------------------------------------------------------------------
 _INT_FIELDS = ('rowptr0', 'col0', 'eid0', 'cscptr0', 'cscrow0', 'csceid0', 'cl0', 'cmptr0', 'cmem0', 'kptr0',
                'batch1', 'rowptr1', 'col1', 'cscptr1', 'cscrow1', 'csceid1', 'cl1', 'cmptr1', 'cmem1', 'kptr1',
-               'batch2', 'counts', 'status', 'gstat', 'scratch_n', 'scratch_e')
+               'batch2', 'counts', 'status', 'gstat', 'scratch_n', 'scratch_e', 'blob')
 _FLOAT_FIELDS = ('w0csr', 'w0csc', 'edge_attr1', 'w1csc', 'scratch_f')
 _I64_FIELDS = ('cl0_i64', 'batch1_i64', 'edge_index1', 'batch2_i64')
 
@@ -50,7 +50,8 @@ def _structure_sizes(B, N, E, L1, ne):
     ints = dict(rowptr0=n1, col0=E, eid0=E, cscptr0=n1, cscrow0=E, csceid0=E, cl0=N, cmptr0=n1, cmem0=N,
                 kptr0=B + 1, batch1=N, rowptr1=n1, col1=E, cscptr1=n1, cscrow1=E, csceid1=E, cl1=L1, cmptr1=l1,
                 cmem1=L1, kptr1=B + 1, batch2=L1, counts=4, status=1, gstat=8 * B,
-                scratch_n=5 * (N + B + 1) + 8, scratch_e=4 * E + 8)
+                scratch_n=5 * (N + B + 1) + 8, scratch_e=4 * E + 8,
+                blob=48 * B + 12 * N + 4 * E + 16)        # DRGNN_BLOB_WORDS: per-graph structure blobs
     floats = dict(w0csr=E if ne else 0, w0csc=E if ne else 0, edge_attr1=E * ne, w1csc=E if ne else 0,
                   scratch_f=E * max(ne, 1) if ne else 0)
     i64 = dict(cl0_i64=N, batch1_i64=N, edge_index1=2 * E, batch2_i64=L1)
@@ -78,7 +79,8 @@ class Structure(object):
         tot_i = sum(pad(v) for v in ints.values())
         tot_f = sum(pad(v) for v in floats.values())
         tot_l = sum(pad(v) for v in i64.values()) if mirrors else 0
-        self._iarena = torch.empty(max(tot_i, 4), dtype=I32, device=device)
+        self._iarena = torch.zeros(max(tot_i, 4), dtype=I32, device=device)   # status / counts start at zero
+        self.blob_only = False
         self._farena = torch.empty(max(tot_f, 4), dtype=F32, device=device)
         self._larena = torch.empty(max(tot_l, 4), dtype=I64, device=device) if mirrors else None
         o = 0
@@ -131,6 +133,10 @@ class Structure(object):
         if self._counts_host is None:
             host = torch.cat([self.counts, self.status]).cpu().tolist()
             st = host[4]
+            if self.blob_only:
+                host[:3] = [-1, -1, -1]      # the blob-only pass computes no batch totals
+                if st:
+                    self.status.zero_()      # sticky status: reported once, then re-armed
             if st:
                 msgs = [t for bit, t in _lib.STATUS_TEXT.items() if st & bit]
                 raise DrgnnError('invalid batch structure: ' + '; '.join(msgs))
@@ -188,6 +194,7 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     s.B, s.N, s.E, s.L1 = B, N, E, L1
     s._shape_views()
     s._counts_host = None
+    s.blob_only = False
     s._keep = (node_ptr, edge_ptr, c1_ptr, edge_index, edge_attr, cluster0, cluster1)
     s.node_ptr, s.edge_ptr, s.c1_ptr = node_ptr, edge_ptr, c1_ptr
     s.max_n, s.max_e = int(max_n), int(max_e)
@@ -206,6 +213,55 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     st = stream_ptr()
     call('drgnn_fill_i32', ptr(s.status), 0, 1, st)
     call('drgnn_structure_build', C.byref(io), st)
+    return s
+
+
+def structure_blob_fits(max_n, max_e):
+    """True when graphs of up to ``max_n`` nodes / ``max_e`` directed edges fit the bitmap kernel of
+    the blob-only structure pass (``drgnn_structure_blob``)."""
+    return int(_lib.load().drgnn_structure_blob_smem_bytes(int(max_n), int(max_e))) >= 0
+
+
+def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None):
+    """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
+    structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
+    global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
+    sticky: zeroed at allocation and by ``Structure.sync_counts``).  Same argument checks as
+    ``structure_build``; both cluster levels are required."""
+    require_cuda(node_ptr, edge_ptr, edge_index, cluster0, c1_ptr, cluster1)
+    _i32(node_ptr, 'node_ptr'), _i32(edge_ptr, 'edge_ptr'), _i32(c1_ptr, 'c1_ptr')
+    if cluster1 is None or c1_ptr is None:
+        raise DrgnnError('the blob-only structure pass needs cluster1 and c1_ptr')
+    B = node_ptr.numel() - 1
+    N = cluster0.numel()
+    E = edge_index.size(1) if edge_index.dim() == 2 else 0
+    L1 = cluster1.numel() if L1 is None else int(L1)
+    if edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or cluster1.dtype != edge_index.dtype:
+        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32)')
+    if not edge_index.is_contiguous() or not cluster0.is_contiguous() or not cluster1.is_contiguous():
+        raise DrgnnError('edge_index / cluster tensors must be contiguous')
+    if L1 > N:
+        raise DrgnnError('len(cluster1)=%d exceeds the number of nodes %d' % (L1, N))
+    s = out
+    if s is None or not s.fits(B, N, E, L1, s.ne if s is not None else 0, s.mirrors if s is not None else False):
+        s = Structure(B, N, E, L1, 0, cluster0.device, False)
+    s.B, s.N, s.E, s.L1 = B, N, E, L1
+    s._shape_views()
+    s._counts_host = None
+    s.blob_only = True
+    s._keep = (node_ptr, edge_ptr, c1_ptr, edge_index, None, cluster0, cluster1)
+    s.node_ptr, s.edge_ptr, s.c1_ptr = node_ptr, edge_ptr, c1_ptr
+    s.max_n, s.max_e = int(max_n), int(max_e)
+    io = s.io
+    io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, 0
+    io.max_n, io.max_e = int(max_n), int(max_e)
+    io.clusters_are_local = 1
+    io.idx32 = 1 if edge_index.dtype == I32 else 0
+    io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
+    io.edge_index, io.edge_attr = ptr(edge_index), None
+    io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
+    if B:
+        call('drgnn_structure_blob', C.byref(io), stream_ptr())
     return s
 
 
@@ -437,7 +493,8 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
-               drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0):
+               drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
+               fuse_reduce=True, blob=None, edge_ptr=None):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -465,10 +522,13 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
         s.adam_p, s.adam_m, s.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
         s.lr, s.beta1, s.beta2, s.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
     s.skip_reduce = 1 if skip_reduce else 0
-    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0), int(variant)
+    require_cuda(blob, edge_ptr)
+    s.blob, s.edge_ptr = ptr(blob), ptr(edge_ptr)
+    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2), int(variant)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
-    if skip_reduce or forward_only:
-        _lib.kernel_count -= 1          # only the per-graph kernel was launched
+    # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the
+    # in-kernel reduction (grid barrier) launch only the per-graph kernel
+    _lib.kernel_count += int(_lib.load().drgnn_ginet_step_last_launches()) - 2
 
 
 def ginet_step_last_variant():

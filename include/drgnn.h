@@ -60,6 +60,11 @@ int drgnn_device_smem_optin(void);
  *    One CTA per graph; graphs are contiguous node / edge ranges given by node_ptr /
  *    edge_ptr (as produced by Batch.from_data_list).
  * ---------------------------------------------------------------------------------- */
+#define DRGNN_BLOB_HEADER 32
+#define DRGNN_BLOB_OFFSET(g, n0, e0) (48 * (int64_t)(g) + 12 * (int64_t)(n0) + 4 * (int64_t)(e0))
+#define DRGNN_BLOB_WORDS(B, N, E) (48 * (int64_t)(B) + 12 * (int64_t)(N) + 4 * (int64_t)(E) + 16)
+/* words of graph g's block that carry data: header + 9n + 5 + 3m, rounded up to 4 */
+#define DRGNN_BLOB_USED(n, m) ((DRGNN_BLOB_HEADER + 9 * (n) + 5 + 3 * (m) + 3) & ~3)
 typedef struct drgnn_structure_io {
   /* ---- sizes ---- */
   int32_t B;            /* graphs                                                        */
@@ -125,6 +130,16 @@ typedef struct drgnn_structure_io {
   int32_t* scratch_n;/* [6*(N+B)+L1+8] node-indexed scratch                               */
   int32_t* scratch_e;/* [4*E+8] edge-indexed scratch                                      */
   float* scratch_f;  /* [E*max(ne,1)] pooled attr scratch                                 */
+  /* ---- per-graph structure blob (optional, NULL to skip) ----
+   * Everything integer the per-graph fused kernels need of graph g, with graph-LOCAL indices, in
+   * one contiguous 16-byte aligned block so that a CTA stages it with ONE bulk copy and depends on
+   * nothing the cross-graph finalize kernel computes.  Block g starts at word
+   * DRGNN_BLOB_OFFSET(g, node_ptr[g], edge_ptr[g]); layout (n nodes, m directed edges):
+   *   header[32]: [0] n, [1] m, [2] K0, [3] E1, [4] K1, [5] 1 when complete, rest 0
+   *   rowptr0[n+1] col0[m] | rowptr1[n+1] col1[m] | cmptr0[n+1] cmem0[n] cl0[n] |
+   *   cmptr1[n+1] cmem1[n] cl1[n] | cscptr1[n+1] cscrow1[m]      (capacity by n / m; K0+1, E1, ...
+   *   entries are valid).  Size of the buffer: DRGNN_BLOB_WORDS(B, N, E) int32. */
+  int32_t* blob;
 } drgnn_structure_io;
 
 /* Dynamic shared memory the per-graph kernel needs for (max_n, max_e); <0 if a graph is
@@ -360,12 +375,17 @@ typedef struct drgnn_ginet_step_args {
    * them itself, e.g. with drgnn_peer_reduce_adam on several GPUs */
   int32_t skip_reduce;
   /* flags bit 0: the cluster kernel also mirrors the intermediates (Zin1, Z1, arg0, Zin2, Z2, arg1)
-   * to global memory (it keeps them in shared memory; the single-CTA kernel always stores them) */
+   * to global memory (it keeps them in shared memory; the single-CTA kernel always stores them);
+   * bit 1: never fuse the gradient reduction into the cluster kernel (step_dev must be [4] floats,
+   * zero-initialised: [2] is the grid-barrier counter of the fused reduction) */
   int32_t flags;
   /* max_e: host bound of the directed edges of one graph (> 0 enables the cluster kernel: a pair of
    * CTAs per graph, one GINet branch each, nb == 2).  variant: 0 = pick (cluster kernel when it
    * fits shared memory, else single CTA), 1 = single-CTA kernel, 2 = cluster kernel or error. */
   int32_t max_e; int32_t variant;
+  /* cluster kernel inputs: the per-graph structure blobs of the structure pass
+   * (drgnn_structure_io.blob) and the edge pointers [B+1] of the batch; NULL -> single-CTA kernel */
+  const int32_t* blob; const int32_t* edge_ptr;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
@@ -375,11 +395,28 @@ int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream);
 int64_t drgnn_ginet_step2_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
                                      int32_t max_e, int32_t Hd, int32_t out);
 int drgnn_ginet_step_last_variant(void);
+/* kernels the last drgnn_ginet_step call of this thread launched: 1 when the cluster kernel also
+ * reduced the gradients (+ Adam) behind a grid barrier (the whole grid co-resident: B <= clusters the
+ * device can hold; flags bit 1 disables it), else 2 (per-graph kernel + reduction), 1 for scoring */
+int drgnn_ginet_step_last_launches(void);
+/* 2-CTA clusters of the cluster kernel the device holds at once with `smem_bytes` per CTA (<0: error) */
+int drgnn_ginet_step2_max_clusters(int64_t smem_bytes);
 /* diagnostic: SM clock (clock64) at the phase boundaries of the CTA that ran graph 0 in the last
  * per-graph launch: [0] start, [1] staged, [2] AX, [3] Z1, [4] P1, [5] AP, [6] Z2, [7] P2, [8] R+fc1,
  * [9] fc2, [10] loss, [11] head backward, [12] dZ2 staged, [13] dW2/dAP, [14] dP1, [15] dZ1 staged,
  * [16] dW1 (end).  Synchronises the device. */
 int drgnn_debug_phase_cycles(uint64_t* out32);
+/* Blob-only structure pass: ONE launch (bitmap kernel, one CTA per graph) that writes io->blob,
+ * io->status and io->gstat[8g + {0,1,2,7}] and nothing else - what the cluster step kernel of
+ * drgnn_ginet_step needs.  Replaces get_preloaded_cluster / consecutive_cluster / pool_edge +
+ * coalesce / the CSR build for graphs whose bitmaps fit shared memory
+ * (drgnn_structure_blob_smem_bytes >= 0); larger graphs: drgnn_structure_build (which writes the
+ * blob too).  Both cluster levels are required.  status is NOT zeroed by the call. */
+int64_t drgnn_structure_blob_smem_bytes(int32_t max_n, int32_t max_e);
+int drgnn_structure_blob(const drgnn_structure_io* io, void* stream);
+/* diagnostic: clock64 at the section boundaries of graph_blob_kernel, CTA of graph 0:
+ * [0] start, [1] loaded + id extremes, [2] relabelled, [3] scattered, [4] counted + scanned, [5] end */
+int drgnn_debug_blob_cycles(uint64_t* out16);
 /* same for the structure pass (graph_local_kernel): [0] start, [1] edge list, [2] CSR, [3] CSC,
  * [4] relabel, [5] members, [6] coarsened edges, [7] coarsened CSC, [8] level-1 clustering (end) */
 int drgnn_debug_structure_cycles(uint64_t* out32);

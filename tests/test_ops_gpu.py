@@ -101,6 +101,99 @@ def test_structure_matches_reference_pooling(lib, name, idx):
                                                          torch.bincount(ref['batch2'], minlength=st.B).cumsum(0)]))
 
 
+def _blob_views(blob, g, n0, e0, n, m):
+    """The arrays of graph g inside a structure blob buffer (host tensor), cut to their valid lengths."""
+    off = 48 * g + 12 * n0 + 4 * e0
+    h = blob[off:off + 32].tolist()
+    K, E1, K1 = h[2], h[3], h[4]
+    o = off + 32
+    out = {'header': h[:6]}
+    for name, cap, valid in (('rp0', n + 1, n + 1), ('col0', m, m), ('rp1', n + 1, K + 1), ('col1', m, E1),
+                             ('cmp0', n + 1, K + 1), ('cmem0', n, n), ('cl0', n, n), ('cmp1', n + 1, K1 + 1),
+                             ('cmem1', n, K), ('cl1', n, K), ('cscp1', n + 1, K + 1), ('cscr1', m, E1)):
+        out[name] = blob[o:o + valid]
+        o += cap
+    return out
+
+
+@pytest.mark.parametrize('name', ['fixture10', 'fixture1', 'cfg2x8', 'small_mixed'])
+@pytest.mark.parametrize('idx', [torch.int64, torch.int32])
+def test_blob_structure_pass_equals_full_pass(lib, name, idx):
+    """The one-launch bitmap kernel (``drgnn_structure_blob``) against the full structure pass: the
+    per-graph blobs are identical word for word, and (graph-local + offsets) equal to the global
+    arrays that are themselves checked against the reference pooling above.  Bit-exact."""
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.data import Batch
+    sets = _graph_sets()
+    sets['small_mixed'] = synthetic.make_graphs(dict(nodes=(5, 260), edges_per_node=6, feat=8), count=9, seed=17)
+    graphs = sets[name]
+    dev = _dev()
+    b, st = _build(graphs, idx, mirrors=False, with_attr=False)
+    K0, E1tot, K1tot = st.sync_counts()
+    assert ops.structure_blob_fits(b._max_n, b._max_e)
+    sb = ops.structure_blob(b._node_ptr.to(dev), b._edge_ptr.to(dev), b.edge_index.to(idx).to(dev),
+                            b.cluster0.to(idx).to(dev), b._max_n, b._max_e, b._c1_ptr.to(dev),
+                            b.cluster1.to(idx).to(dev))
+    sb.sync_counts()
+    full, lean = st.blob.cpu(), sb.blob.cpu()
+    nptr, eptr = b._node_ptr.tolist(), b._edge_ptr.tolist()
+    kptr0, kptr1 = st.kptr0.cpu().tolist(), st.kptr1.cpu().tolist()
+    rowptr1, cscptr1 = st.rowptr1.cpu(), st.cscptr1.cpu()
+    k_seen = e1_seen = 0
+    for g in range(len(graphs)):
+        n0, e0 = nptr[g], eptr[g]
+        n, m = nptr[g + 1] - n0, eptr[g + 1] - e0
+        vf, vl = _blob_views(full, g, n0, e0, n, m), _blob_views(lean, g, n0, e0, n, m)
+        assert vl['header'] == vf['header'] and vl['header'][5] == 1 and vl['header'][:2] == [n, m]
+        for key in vf:
+            if key != 'header':
+                assert torch.equal(vl[key], vf[key]), (g, key)
+        K, E1, K1 = vl['header'][2:5]
+        k0, q0 = kptr0[g], kptr1[g]
+        assert (K, K1) == (kptr0[g + 1] - k0, kptr1[g + 1] - q0)
+        e10 = int(rowptr1[k0])
+        assert E1 == int(rowptr1[k0 + K]) - e10
+        # graph-local blob == global arrays of the full pass
+        assert torch.equal(vl['rp0'] + e0, st.rowptr0[n0:n0 + n + 1].cpu())
+        assert torch.equal(vl['col0'] + n0, st.col0[e0:e0 + m].cpu())
+        assert torch.equal(vl['cl0'] + k0, st.cl0[n0:n0 + n].cpu())
+        assert torch.equal(vl['cmem0'] + n0, st.cmem0[n0:n0 + n].cpu())
+        assert torch.equal(vl['cmp0'] + n0, st.cmptr0[k0:k0 + K + 1].cpu())
+        assert torch.equal(vl['rp1'] + e10, rowptr1[k0:k0 + K + 1])
+        assert torch.equal(vl['col1'] + k0, st.col1[e10:e10 + E1].cpu())
+        assert torch.equal(vl['cscp1'] + e10, cscptr1[k0:k0 + K + 1])
+        assert torch.equal(vl['cscr1'] + k0, st.cscrow1[e10:e10 + E1].cpu())
+        assert torch.equal(vl['cl1'] + q0, st.cl1[k0:k0 + K].cpu())
+        assert torch.equal(vl['cmem1'] + k0, st.cmem1[k0:k0 + K].cpu())
+        assert torch.equal(vl['cmp1'] + k0, st.cmptr1[q0:q0 + K1 + 1].cpu())
+        k_seen += K
+        e1_seen += E1
+    assert (k_seen, e1_seen) == (K0, E1tot)
+
+
+def test_blob_structure_pass_flags_invalid_input(lib):
+    from deeprank_gnn_b200 import ops
+    from deeprank_gnn_b200._lib import DrgnnError
+    dev = _dev()
+    node_ptr = torch.tensor([0, 3, 6], dtype=torch.int32, device=dev)
+    edge_ptr = torch.tensor([0, 2, 4], dtype=torch.int32, device=dev)
+    c1_ptr = torch.tensor([0, 2, 4], dtype=torch.int32, device=dev)
+    cluster = torch.tensor([0, 0, 1, 0, 1, 1], device=dev)
+    cluster1 = torch.tensor([0, 0, 0, 1], device=dev)
+    bad_edge = torch.tensor([[0, 1, 3, 5], [1, 0, 4, 1]], device=dev)        # last edge leaves graph 1
+    st = ops.structure_blob(node_ptr, edge_ptr, bad_edge, cluster, 3, 2, c1_ptr, cluster1)
+    with pytest.raises(DrgnnError):
+        st.sync_counts()
+    ok_edge = torch.tensor([[0, 1, 3, 5], [1, 0, 4, 4]], device=dev)
+    st = ops.structure_blob(node_ptr, edge_ptr, ok_edge, cluster, 3, 2, c1_ptr, cluster1, out=st)
+    st.sync_counts()                                                          # sticky status was re-armed
+    short_c1 = torch.tensor([0, 2, 3], dtype=torch.int32, device=dev)        # graph 1 has 2 clusters, 1 id given
+    st = ops.structure_blob(node_ptr, edge_ptr, ok_edge, cluster, 3, 2, short_c1, cluster1[:3].contiguous(), out=st)
+    with pytest.raises(DrgnnError):
+        st.sync_counts()
+    assert int(st.blob[48 * 1 + 12 * 3 + 4 * 2 + 5]) == 0                    # blob of graph 1 is marked incomplete
+
+
 def test_structure_toy_graph_of_reference_test(lib):
     """tests/test_community_pooling.py:10-18,52-58: two copies of the 6-node toy graph with
     clusters [0,0,0,1,1,1 | 2,2,2,3,3,3]: every edge becomes a self loop -> no pooled edge."""

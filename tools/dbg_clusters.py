@@ -1,0 +1,6 @@
+import sys; sys.path.insert(0,'.')
+import torch
+from deeprank_gnn_b200 import _lib, ops
+lib=_lib.load()
+sm=ops.ginet_step2_smem_bytes(32,16,32,200,64,32,1000,128,1)
+print('smem',sm,'max clusters',lib.drgnn_ginet_step2_max_clusters(sm), lib.drgnn_last_error())

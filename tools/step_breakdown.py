@@ -60,6 +60,10 @@ def main():
             tot = ph[16] - ph[0]
             print('graph-step kernel, CTA of graph 0: %d cycles total' % tot)
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
+            _lib.check(_lib.load().drgnn_debug_blob_cycles(ph), 'bphase')
+            bnames = ['load+minmax', 'relabel', 'scatter', 'count+scan', 'emit']
+            print('blob structure kernel, CTA of graph 0: %d cycles total' % (ph[5] - ph[0]))
+            print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(bnames)))
             _lib.check(_lib.load().drgnn_debug_structure_cycles(ph), 'sphase')
             snames = ['edges', 'CSR', 'CSC', 'relabel', 'members', 'coarsen', 'CSC1', 'level1']
             print('structure kernel, CTA of graph 0: %d cycles total' % (ph[8] - ph[0]))
