@@ -368,6 +368,7 @@ def run_b200(args):
     eng.use_graph = not args.no_graph
     for d in resident:                                   # capture / first-touch everything (untimed)
         eng.step(d, B_global=B_global)
+    eng.train_resident(resident, steps=len(resident), B_global=B_global)   # captures the chunk graphs of one rotation (untimed)
     eng.train_resident(resident, steps=max(args.warmup, 3), B_global=B_global)
     torch.cuda.synchronize()
     if world > 1:

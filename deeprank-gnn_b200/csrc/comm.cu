@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(PR_THREADS) peer_reduce_adam_kernel(const drgn
     s_epoch = *reinterpret_cast<volatile uint32_t*>(c.ctr) + 1u;
     const float st = a.step_dev ? a.step_dev[0] + 1.f : 1.f;
     sh[0] = st;
-    sh[1] = 1.f - (float)pow((double)a.beta1, (double)st);
-    sh[2] = 1.f - (float)pow((double)a.beta2, (double)st);
+    sh[1] = adam_bias_correction(a.beta1, st);
+    sh[2] = adam_bias_correction(a.beta2, st);
   }
   __syncthreads();
   const uint32_t epoch = s_epoch;

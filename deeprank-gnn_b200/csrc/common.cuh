@@ -103,6 +103,13 @@ __device__ inline int block_exclusive_scan(int* a, int len, int* wsum) {
   return total;
 }
 
+// Adam bias correction 1 - beta^step, the same expression in every optimiser kernel (single GPU, peer
+// exchange, in-kernel reduction) so that they stay bit-identical: -expm1(step * log1p(beta - 1)) is
+// accurate for beta near 1 and needs no double-precision pow on the critical path.
+__device__ __forceinline__ float adam_bias_correction(float beta, float step) {
+  return -expm1f(step * log1pf(beta - 1.f));
+}
+
 // Word offsets of the arrays inside one graph's structure blob (include/drgnn.h, drgnn_structure_io.blob)
 struct BlobLayout {
   int rp0, col0, rp1, col1, cmp0, cmem0, cl0, cmp1, cmem1, cl1, cscp1, cscr1, end;

@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(32 * RED_SPLITS) ginet_step_reduce_kernel(cons
   if (s.fuse_adam && threadIdx.x == 0) {
     const float st = s.step_dev[0] + 1.f;
     sh[0] = st;
-    sh[1] = 1.f - (float)pow((double)s.beta1, (double)st);
-    sh[2] = 1.f - (float)pow((double)s.beta2, (double)st);
+    sh[1] = adam_bias_correction(s.beta1, st);
+    sh[2] = adam_bias_correction(s.beta2, st);
   }
   {
     const int gs = (B + RED_SPLITS - 1) / RED_SPLITS;

@@ -701,6 +701,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     }
   }
   __syncthreads();
+  DRGNN_PHASE(17);
   {
     const int n = s.n_params, B = a.B;
     const int per = (n + 1 + (int)gridDim.x - 1) / (int)gridDim.x;   // elements of this CTA, 128 per sweep
@@ -710,8 +711,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     if (s.fuse_adam && t == 0) {
       const float st = s.step_dev[0] + 1.f;
       adamc[0] = st;
-      adamc[1] = 1.f - (float)pow((double)s.beta1, (double)st);
-      adamc[2] = 1.f - (float)pow((double)s.beta2, (double)st);
+      // bias corrections 1 - beta^t without the double-precision pow (FP64 is slow here and thread 0 sits
+      // on the critical path of the whole CTA): -expm1(t * log1p(beta - 1)) is accurate for beta near 1
+      adamc[1] = adam_bias_correction(s.beta1, st);
+      adamc[2] = adam_bias_correction(s.beta2, st);
     }
 #pragma unroll 1
     for (int sweep = 0; sweep < per; sweep += 128) {
@@ -766,6 +769,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       }
     }
   }
+  DRGNN_PHASE(18);
 }
 
 static inline bool step2_shapes_ok(const drgnn_ginet_step_args& s) {

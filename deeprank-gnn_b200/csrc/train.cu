@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   if (threadIdx.x == 0) {  // one thread does the double-precision powers (FP64 is slow on this part)
     const float st = step_dev[0] + 1.f;
     sh[0] = st;
-    sh[1] = 1.f - (float)pow((double)beta1, (double)st);
-    sh[2] = 1.f - (float)pow((double)beta2, (double)st);
+    sh[1] = adam_bias_correction(beta1, st);
+    sh[2] = adam_bias_correction(beta2, st);
   }
   __syncthreads();
   const float step = sh[0];
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(1024) adam_flat_small_kernel(float* __restrict
   if (threadIdx.x == 0) {  // one thread does the double-precision powers (FP64 is slow on this part)
     const float st = step_dev[0] + 1.f;
     sh[0] = st;
-    sh[1] = 1.f - (float)pow((double)beta1, (double)st);
-    sh[2] = 1.f - (float)pow((double)beta2, (double)st);
+    sh[1] = adam_bias_correction(beta1, st);
+    sh[2] = adam_bias_correction(beta2, st);
   }
   __syncthreads();
   const float step = sh[0];

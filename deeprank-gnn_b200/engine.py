@@ -280,6 +280,7 @@ class Engine(object):
         self._adam_done = False
         self.fuse_adam = True
         self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
+        self.rotation_graph = os.environ.get('DRGNN_ROTATION_GRAPH', '1') != '0'   # train_resident: one CUDA graph per rotation
         self.blob_structure = os.environ.get('DRGNN_BLOB_STRUCTURE', '1') != '0'   # one-launch bitmap structure pass
         self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
         self.fuse_reduce = os.environ.get('DRGNN_FUSE_REDUCE', '1') != '0'   # gradient reduction + Adam behind a grid barrier
@@ -931,11 +932,28 @@ class Engine(object):
         n = len(dbatches) if steps is None else steps
         main = torch.cuda.current_stream(self.device)
         self._pipeline_state()
+        out = None
+        first = 0
+        R = len(dbatches)
+        C = self._rotation_chunk(dbatches) if (self.use_graph and self.rotation_graph and n >= 4 and
+                                               (self.world == 1 or self.comm is not None)) else 0
+        if C and n >= C:
+            # CUDA graphs of C consecutive steps each (structure passes of the batches two steps ahead on side
+            # streams + the steps, with their dependencies): the host issues one launch per C steps instead of
+            # ~4 calls per step - the per-step issue cost had become the bound of the resident loop
+            LA = self.ROTATION_LOOKAHEAD
+            for j in range(LA):                      # structure passes the first chunk expects to find done
+                self._prepare_any(dbatches[j % R])
+            for c in range(n // C):
+                self._chunk_graph(dbatches, (c * C) % R, C, B_global).replay()
+            first = (n // C) * C
+            out = (self.ws.loss, self.ws.pred[:dbatches[(first - 1) % R].B])
+            if first == n:
+                return out
         for ps in self._prep_streams:
             ps.wait_stream(main)
         used = set()
-        out = None
-        for i in range(n):
+        for i in range(first, n):
             d = dbatches[i % len(dbatches)]
             slot = d.sslot
             ps = self._prep_streams[i & 1]
@@ -949,6 +967,78 @@ class Engine(object):
             self._slot_free[slot].record(main)
             used.add(slot)
         return out
+
+    ROTATION_LOOKAHEAD = 2      # structure passes run this many steps ahead inside a chunk graph (< STRUCT_SLOTS)
+
+    def _rotation_chunk(self, dbatches):
+        """Steps per chunk graph for ``train_resident`` (0: not applicable).  Needs keyed (packed) batches,
+        a chunk length that divides the rotation, and structure slots such that a batch, the two batches
+        before it and the batch STRUCT_SLOTS before it never collide (so a pass two steps ahead only waits
+        for the step that read its slot last)."""
+        R, ns, la = len(dbatches), self.STRUCT_SLOTS, self.ROTATION_LOOKAHEAD
+        if R < ns or any(d.key is None for d in dbatches):
+            return 0
+        for i in range(R):
+            s_i = dbatches[i].sslot
+            if any(dbatches[(i - k) % R].sslot == s_i for k in range(1, ns)) or dbatches[(i - ns) % R].sslot != s_i:
+                return 0
+        for C in (16, 12, 8, 6, 5, 4):
+            if R % C == 0 and C > la:
+                return C
+        return 0
+
+    def _chunk_graph(self, dbatches, start, C, B_global):
+        """One CUDA graph: steps ``start .. start+C-1`` of the rotation on the capturing stream and the
+        structure passes of batches ``start+LA .. start+C-1+LA`` on two side streams.  Pass j waits for step
+        j - STRUCT_SLOTS (the last reader of its slot) when that step is in this chunk; step i waits for pass
+        i when that pass is in this chunk - everything older finished with the previous replay."""
+        key = ('chunk', tuple(d.key for d in dbatches), start, C, B_global, self.training)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        R, ns, la = len(dbatches), self.STRUCT_SLOTS, self.ROTATION_LOOKAHEAD
+        for d in dbatches:
+            self._ensure(d.B, d.N, d.E)
+        # eager warm-up of one step (first-use setup inside the C-ABI), optimiser state restored afterwards
+        snap = [t.clone() for t in (self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev)]
+        use_graph, self.use_graph = self.use_graph, False
+        try:
+            self._no_exchange = True
+            try:
+                self.step(dbatches[start % R], B_global=B_global)
+                for j in range(la):              # the warm-up rewrote a structure slot: restore what the chunk expects
+                    self.prepare(dbatches[(start + j) % R])
+            finally:
+                self._no_exchange = False
+            torch.cuda.current_stream(self.device).synchronize()
+            for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
+                t.copy_(c)
+            done, ready = {}, {}
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream(self.device)
+                for ps in self._prep_streams:
+                    ps.wait_stream(main)
+                for i in range(start, start + C):
+                    j = i + la
+                    ps = self._prep_streams[j & 1]
+                    with torch.cuda.stream(ps):
+                        if j - ns in done:
+                            ps.wait_event(done[j - ns])
+                        self.prepare(dbatches[j % R])
+                        ready[j] = torch.cuda.Event()
+                        ready[j].record(ps)
+                    if i in ready:
+                        main.wait_event(ready[i])
+                    self.step(dbatches[i % R], B_global=B_global, prepared=True)
+                    done[i] = torch.cuda.Event()
+                    done[i].record(main)
+                for ps in self._prep_streams:
+                    main.wait_stream(ps)
+        finally:
+            self.use_graph = use_graph
+        self._graphs[key] = g
+        return g
 
     def validate(self):
         """Raise if the last structure pass flagged invalid input (ONE host sync)."""

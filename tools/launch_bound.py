@@ -23,7 +23,7 @@ def main():
         ds = [eng.upload(pb, slot=i) for i, pb in enumerate(packed)]
         for d in ds:
             eng.step(d)
-        eng.train_resident(ds, steps=32)
+        eng.train_resident(ds, steps=max(32, pool))      # captures every chunk graph of the rotation
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()

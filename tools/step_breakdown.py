@@ -60,6 +60,8 @@ def main():
             tot = ph[16] - ph[0]
             print('graph-step kernel, CTA of graph 0: %d cycles total' % tot)
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
+            if ph[18] > ph[16]:
+                print('  in-kernel reduction: grid barrier %d | reduce + Adam %d' % (ph[17] - ph[16], ph[18] - ph[17]))
             _lib.check(_lib.load().drgnn_debug_blob_cycles(ph), 'bphase')
             bnames = ['load+minmax', 'relabel', 'scatter', 'count+scan', 'emit']
             print('blob structure kernel, CTA of graph 0: %d cycles total' % (ph[5] - ph[0]))
