@@ -132,7 +132,7 @@ class GinetStepArgs(C.Structure):
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
         ('skip_reduce', C.c_int32), ('flags', C.c_int32), ('max_e', C.c_int32), ('variant', C.c_int32),
-        ('blob', VP), ('edge_ptr', VP),
+        ('blob', VP), ('edge_ptr', VP), ('comm', VP),
     ]
 
 
@@ -146,6 +146,7 @@ class PeerComm(C.Structure):
         ('xbuf', VP * MAX_PEERS), ('xflag', VP * MAX_PEERS),
         ('ctr', VP), ('stride', C.c_int64), ('max_blocks', C.c_int32), ('reserved', C.c_int32),
         ('timeout_ns', C.c_uint64),
+        ('xll', VP * MAX_PEERS),
     ]
 
 

@@ -20,6 +20,7 @@
 // (L2 resident, just written).  GINet has no bias, no self term, unit edge weights (alpha == 1).
 #include <cooperative_groups.h>
 #include <float.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -788,7 +789,25 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
     const int G = 2 * a->B;
     const int occ_clusters = step2_max_clusters(smem2);   // co-resident 2-CTA clusters at this shared-memory size
     plan.fused_reduce = (train && !s->skip_reduce && s->step_dev != nullptr && !(s->flags & 2) && a->B <= occ_clusters) ? 1 : 0;
-    ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(*s, plan);
+    drgnn_peer_comm comm;
+    memset(&comm, 0, sizeof(comm));
+    if (s->comm != nullptr && train && !s->skip_reduce) {
+      // the exchange over peer memory runs inside the launch: every rank must take this very path
+      const drgnn_peer_comm* c = s->comm;
+      DRGNN_REQUIRE(c->world >= 1 && c->world <= DRGNN_MAX_PEERS && c->rank >= 0 && c->rank < c->world,
+                    "ginet_step: bad world / rank %d / %d", c->world, c->rank);
+      if (c->world > 1) {
+        if (!plan.fused_reduce)
+          return fail(DRGNN_ERR_UNSUPPORTED, "ginet_step: the in-kernel exchange needs the co-resident grid (B %d, clusters %d)",
+                      a->B, occ_clusters);
+        DRGNN_REQUIRE(s->fuse_adam, "ginet_step: the in-kernel exchange applies Adam (fuse_adam)");
+        DRGNN_REQUIRE(c->ctr && c->max_blocks >= G && c->stride >= s->n_params + 1, "ginet_step: exchange layout too small");
+        for (int r = 0; r < c->world; ++r)
+          DRGNN_REQUIRE(c->xll[r], "ginet_step: rank %d has no low-latency exchange buffer", r);
+        comm = *c;
+      }
+    }
+    ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(*s, plan, comm);
     DRGNN_CHECK_LAUNCH("ginet_graph_step2_kernel");
     g_step_variant = 2;
     g_step_launches = plan.fused_reduce ? 1 : ((train && !s->skip_reduce) ? 2 : 1);

@@ -42,6 +42,21 @@ __device__ __forceinline__ unsigned s2_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void s2_st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t s2_ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// low-latency exchange word: value bits and epoch in ONE 8-byte store / load (never torn)
+__device__ __forceinline__ void s2_st_ll(uint64_t* p, unsigned bits, unsigned epoch) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void s2_ld_ll(const uint64_t* p, unsigned& bits, unsigned& epoch) {
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(epoch) : "l"(p) : "memory");
+}
 __device__ __forceinline__ unsigned long long s2_globaltimer() {
   unsigned long long v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
@@ -367,7 +382,7 @@ __host__ __device__ inline int s2_split(int cap_words, int mn) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
-    ginet_graph_step2_kernel(const drgnn_ginet_step_args s, const Step2Plan P) {
+    ginet_graph_step2_kernel(const drgnn_ginet_step_args s, const Step2Plan P, const drgnn_peer_comm C) {
   extern __shared__ __align__(16) float sm[];
   cgx::cluster_group cluster = cgx::this_cluster();
   const drgnn_ginet_fused_args& a = s.g;
@@ -707,15 +722,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     const int per = (n + 1 + (int)gridDim.x - 1) / (int)gridDim.x;   // elements of this CTA, 128 per sweep
     const int el = t & 127, q = t >> 7;
     float* psum = xs;   // [4][128]
-    float* adamc = red; // [3]
-    if (s.fuse_adam && t == 0) {
-      const float st = s.step_dev[0] + 1.f;
-      adamc[0] = st;
-      // bias corrections 1 - beta^t without the double-precision pow (FP64 is slow here and thread 0 sits
-      // on the critical path of the whole CTA): -expm1(t * log1p(beta - 1)) is accurate for beta near 1
-      adamc[1] = adam_bias_correction(s.beta1, st);
-      adamc[2] = adam_bias_correction(s.beta2, st);
+    float* adamc = red; // [3] + exchange epoch
+    unsigned* epoch_s = reinterpret_cast<unsigned*>(red + 4);
+    const int world = C.world, rank = C.rank;
+    const bool peers = world > 1;
+    if (t == 0) {
+      if (s.fuse_adam) {
+        const float st = s.step_dev[0] + 1.f;
+        adamc[0] = st;
+        adamc[1] = adam_bias_correction(s.beta1, st);
+        adamc[2] = adam_bias_correction(s.beta2, st);
+      }
+      if (peers) *epoch_s = *reinterpret_cast<volatile uint32_t*>(C.ctr) + 1u;
     }
+    // ---- local sums of this CTA's slice; one GPU: Adam right away, several: delivered to every rank
 #pragma unroll 1
     for (int sweep = 0; sweep < per; sweep += 128) {
       const int e = (int)blockIdx.x * per + sweep + el;
@@ -741,7 +761,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       __syncthreads();
       if (q == 0 && mine) {
         acc = ((psum[el] + psum[128 + el]) + psum[256 + el]) + psum[384 + el];
-        if (e < n) {
+        if (peers) {
+          // ONE 8-byte store {value, epoch} per rank over NVLink peer memory into slot `rank` of every
+          // rank's low-latency buffer (own included): validity travels with the value, no flag, no fence
+          const unsigned ep = *epoch_s;
+          const int64_t slot = ((int64_t)(ep & 1u) * world + rank) * C.stride + e;
+#pragma unroll 1
+          for (int p = 0; p < world; ++p) s2_st_ll(C.xll[(rank + p) % world] + slot, __float_as_uint(acc), ep);
+        } else if (e < n) {
           s.grads[e] = acc;
           if (s.fuse_adam) {
             float mi = s.adam_m[e], vi = s.adam_v[e];
@@ -758,13 +785,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       }
       __syncthreads();
     }
+    if (peers) {
+      // ---- every thread waits for ITS element from every rank (element e only depends on element e of
+      // the peers: no flag, no cross-GPU barrier), sums the slots in rank order and applies Adam
+      const unsigned epoch = *epoch_s;
+      const int par = (int)(epoch & 1u);
+      const unsigned long long t0 = s2_globaltimer(), limit = C.timeout_ns ? C.timeout_ns : 20000000000ull;
+#pragma unroll 1
+      for (int sweep = 0; sweep < per; sweep += T) {
+        const int e = (int)blockIdx.x * per + sweep + t;
+        if (sweep + t < per && e <= n) {
+          float tot = 0.f;
+          const uint64_t* mine = C.xll[rank] + (int64_t)par * world * C.stride + e;
+#pragma unroll 1
+          for (int rr = 0; rr < world; ++rr) {
+            unsigned bits, ep;
+            s2_ld_ll(mine + (int64_t)rr * C.stride, bits, ep);
+            while (ep != epoch) {
+              if (s2_globaltimer() - t0 > limit) {
+                atomicOr(C.ctr + 2, 1u);
+                break;
+              }
+              __nanosleep(20);
+              s2_ld_ll(mine + (int64_t)rr * C.stride, bits, ep);
+            }
+            tot += __uint_as_float(bits);
+          }
+          if (e < n) {
+            s.grads[e] = tot;
+            if (s.fuse_adam) {
+              float mi = s.adam_m[e], vi = s.adam_v[e];
+              mi = mi + (tot - mi) * (1.f - s.beta1);
+              vi = vi * s.beta2 + (1.f - s.beta2) * tot * tot;
+              s.adam_m[e] = mi;
+              s.adam_v[e] = vi;
+              const float denom = sqrtf(vi) / sqrtf(adamc[2]) + s.eps;
+              s.adam_p[e] = s.adam_p[e] - (s.lr / adamc[1]) * (mi / denom);
+            }
+          } else if (s.loss) {
+            s.loss[0] = tot;
+          }
+        }
+      }
+    }
     __syncthreads();
-    if (t == 0) {   // the last CTA to finish re-arms the barrier and bumps the optimiser step
+    if (t == 0) {   // the last CTA to finish re-arms the barrier, publishes the epoch, bumps the optimiser step
       unsigned* ticket = reinterpret_cast<unsigned*>(s.step_dev + 1);
       __threadfence();
       if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
         *ticket = 0u;
         *sync_ctr = 0u;
+        if (peers) *reinterpret_cast<volatile uint32_t*>(C.ctr) = *epoch_s;
         if (s.fuse_adam) s.step_dev[0] = adamc[0];
       }
     }

@@ -280,6 +280,9 @@ class Engine(object):
         self._adam_done = False
         self.fuse_adam = True
         self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
+        self.fuse_comm = os.environ.get('DRGNN_FUSE_COMM', '1') != '0'   # peer exchange inside the step kernel
+        self._cur_B_global = None
+        self._last_exchange = None
         self.rotation_graph = os.environ.get('DRGNN_ROTATION_GRAPH', '1') != '0'   # train_resident: one CUDA graph per rotation
         self.blob_structure = os.environ.get('DRGNN_BLOB_STRUCTURE', '1') != '0'   # one-launch bitmap structure pass
         self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
@@ -305,7 +308,11 @@ class Engine(object):
         """Name of the gradient exchange this engine uses (reported by bench.py)."""
         if self.world == 1:
             return 'none'
-        return 'peer-memory exchange fused with reduce+Adam (1 launch)' if self.comm is not None else 'nccl all_reduce'
+        if self.comm is None:
+            return 'nccl all_reduce'
+        if self._last_exchange == 'in-kernel':
+            return 'peer-memory exchange + rank-ordered sum + Adam inside the step kernel (no extra launch)'
+        return 'peer-memory exchange fused with reduce+Adam (1 launch)'
 
     # ---------------------------------------------------------------- parameters
     def reset_parameters(self, seed=None):
@@ -428,6 +435,22 @@ class Engine(object):
         self._last_struct = st
         return st
 
+    def _comm_in_kernel(self, d, st):
+        """Can the peer-memory exchange run inside the cluster step kernel for batch ``d``?  Decided from
+        values that are identical on every rank (equal shards, same device type, same shapes), because
+        all ranks must take the same path."""
+        s = self.spec
+        if not (self.fuse_comm and self.fuse_reduce and st.blob_only and self._cur_B_global is not None
+                and d.B * self.world == self._cur_B_global and 2 * d.B <= int(self.comm.struct.max_blocks)):
+            return False
+        key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'clusters')
+        mc = self._fused_fit.get(key)
+        if mc is None:
+            smem = ops.ginet_step2_smem_bytes(s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+            mc = ops.ginet_step2_max_clusters(smem) if smem >= 0 else 0
+            self._fused_fit[key] = mc
+        return d.B <= mc
+
     def _blob_only(self, d):
         """True when the step of batch ``d`` runs the cluster whole-step kernel, which stages the
         per-graph structure blobs and needs none of the global structure arrays: the structure pass
@@ -503,6 +526,9 @@ class Engine(object):
                 train_step = loss_inv is not None
                 fuse_adam = train_step and self.world == 1 and self.fuse_adam
                 use_comm = train_step and self.comm is not None and self._want_adam
+                # several GPUs: the exchange over peer memory runs INSIDE the step kernel when every rank
+                # launches the same co-resident grid (equal shards); else in its own launch behind it
+                in_kernel = use_comm and not self._no_exchange and self._comm_in_kernel(d, st)
                 task = ops.TASK_NONE
                 if train_step:
                     task = ops.TASK_CE if self.task == 'class' else \
@@ -522,14 +548,19 @@ class Engine(object):
                                forward_only=not train_step, drop_p=s.dropout if hashed else 0.0, seed=self.seed,
                                step_dev=self.step_dev,
                                adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
-                                         beta2=self.betas[1], eps=self.eps) if fuse_adam else None,
-                               skip_reduce=use_comm, max_e=d.max_e, mirror=self.keep_intermediates,
+                                         beta2=self.betas[1], eps=self.eps) if (fuse_adam or in_kernel) else None,
+                               skip_reduce=use_comm and not in_kernel, comm=self.comm if in_kernel else None,
+                               max_e=d.max_e, mirror=self.keep_intermediates,
                                variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
                                blob=st.blob,
                                edge_ptr=d.edge_ptr)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._adam_done = fuse_adam
-                if use_comm:
+                if use_comm and not self._no_exchange:
+                    self._last_exchange = 'in-kernel' if in_kernel else 'launch'
+                if in_kernel:
+                    self._reduced = self._adam_done = True
+                elif use_comm:
                     # per-graph rows -> rank-local sum -> peers -> rank-ordered sum -> Adam: ONE launch
                     self._peer_exchange(partial=ws.partial_full, B=B)
                 return ws.pred[:B]
@@ -738,6 +769,7 @@ class Engine(object):
         is sum/B_global so the all-reduced (summed) gradient is the gradient of the global mean
         (SURVEY 8e)."""
         inv = self._inv_norm(d, B_global, inv_norm)
+        self._cur_B_global = B_global
         if self.use_graph and d.key is not None and keep_mask is None:
             if not prepared:
                 self.prepare_graph(d)

@@ -494,7 +494,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
                drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
-               fuse_reduce=True, blob=None, edge_ptr=None):
+               fuse_reduce=True, blob=None, edge_ptr=None, comm=None):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -524,6 +524,8 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     s.skip_reduce = 1 if skip_reduce else 0
     require_cuda(blob, edge_ptr)
     s.blob, s.edge_ptr = ptr(blob), ptr(edge_ptr)
+    # comm (parallel.PeerComm): the gradient exchange over peer memory runs inside the cluster kernel
+    s.comm = C.addressof(comm.struct) if comm is not None else None
     s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2), int(variant)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the
@@ -534,6 +536,11 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
 def ginet_step_last_variant():
     """1 = single-CTA kernel, 2 = cluster kernel: what the last ``ginet_step`` of this thread launched."""
     return int(_lib.load().drgnn_ginet_step_last_variant())
+
+
+def ginet_step2_max_clusters(smem_bytes):
+    """Co-resident 2-CTA clusters of the cluster step kernel at ``smem_bytes`` per CTA (needs a device)."""
+    return int(_lib.load().drgnn_ginet_step2_max_clusters(int(smem_bytes)))
 
 
 def ginet_step2_smem_bytes(F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):

@@ -84,17 +84,21 @@ class PeerComm(object):
     after which ``ops.peer_reduce_adam`` moves gradients with plain stores over NVLink - no NCCL
     call on the step.  ``regions`` (same-process pointers) builds a communicator without IPC: used
     by the single-GPU protocol test, where two "ranks" run on two streams of one device.
-    Region layout: ctr[16] u32 | flags [2][world][max_blocks] u32 | buffers [2][world][stride] f32."""
+    Region layout: ctr[16] u32 | flags [2][world][max_blocks] u32 | buffers [2][world][stride] f32 |
+    low-latency slots [2][world][stride] x 8 bytes (value + epoch in one store; in-kernel exchange)."""
 
     THREADS = 256
 
     @staticmethod
     def layout(world, n_sum):
         stride = (int(n_sum) + 3) // 4 * 4
-        max_blocks = (int(n_sum) + PeerComm.THREADS - 1) // PeerComm.THREADS
+        # one flag per block of the stand-alone kernel (256 elements each) or per CTA of the cluster step
+        # kernel when the exchange runs inside it (at most 2 CTAs per SM pair, 320 covers every B200)
+        max_blocks = max((int(n_sum) + PeerComm.THREADS - 1) // PeerComm.THREADS, 320)
         flags_off = 64
         buf_off = (flags_off + 4 * 2 * world * max_blocks + 255) // 256 * 256
-        return stride, max_blocks, flags_off, buf_off, buf_off + 4 * 2 * world * stride
+        ll_off = (buf_off + 4 * 2 * world * stride + 255) // 256 * 256     # 8-byte {value, epoch} slots
+        return stride, max_blocks, flags_off, buf_off, ll_off, ll_off + 8 * 2 * world * stride
 
     def __init__(self, n_sum, rank=None, world=None, group=None, regions=None, timeout_s=None):
         import ctypes as C
@@ -107,7 +111,7 @@ class PeerComm(object):
         if world > _lib.MAX_PEERS:
             raise _lib.DrgnnError('PeerComm supports up to %d ranks (one NVSwitch domain)' % _lib.MAX_PEERS)
         self.world, self.rank, self.n_sum = int(world), int(rank), int(n_sum)
-        stride, max_blocks, flags_off, buf_off, nbytes = self.layout(world, n_sum)
+        stride, max_blocks, flags_off, buf_off, ll_off, nbytes = self.layout(world, n_sum)
         self.nbytes = nbytes
         self._own = None
         self._opened = []
@@ -148,6 +152,7 @@ class PeerComm(object):
         for r in range(self.world):
             st.xflag[r] = self.regions[r] + flags_off
             st.xbuf[r] = self.regions[r] + buf_off
+            st.xll[r] = self.regions[r] + ll_off
         st.ctr = self.regions[self.rank]
         st.stride, st.max_blocks = stride, max_blocks
         if timeout_s is None:

@@ -351,6 +351,7 @@ int drgnn_ginet_fused_bwd(const drgnn_ginet_fused_args* a, void* stream);
  * gradient buffer `grads` [n_params] (offsets off_*; slot n_params of a row holds the graph's loss
  * term); rows must be ZERO in the slots no live parameter owns.  The reduction sums the rows in
  * graph order (deterministic) into grads and loss.  forward_only != 0: predictions only. */
+struct drgnn_peer_comm;
 typedef struct drgnn_ginet_step_args {
   drgnn_ginet_fused_args g;            /* dR / partial / dW1 / dW2 of the embedded block are unused */
   const float* fc1_w; const float* fc1_b; const float* fc2_w; const float* fc2_b;
@@ -386,6 +387,13 @@ typedef struct drgnn_ginet_step_args {
   /* cluster kernel inputs: the per-graph structure blobs of the structure pass
    * (drgnn_structure_io.blob) and the edge pointers [B+1] of the batch; NULL -> single-CTA kernel */
   const int32_t* blob; const int32_t* edge_ptr;
+  /* comm != NULL (host pointer to a drgnn_peer_comm, world > 1): the cluster kernel also runs the
+   * gradient exchange of drgnn_peer_reduce_adam itself - after its grid barrier every CTA sums its
+   * slice of the per-graph rows, stores it into every rank's exchange buffer over NVLink peer
+   * memory, releases its flag, waits for the same CTA of every peer, sums the slots in rank order
+   * and applies Adam.  Every rank must launch the same grid (equal graphs per rank); needs
+   * comm->max_blocks >= 2B, the grid co-resident (drgnn_ginet_step2_max_clusters) and fuse_adam. */
+  const struct drgnn_peer_comm* comm;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
@@ -433,7 +441,7 @@ int drgnn_debug_structure_cycles(uint64_t* out32);
  * exchanges handles (torch.distributed.all_gather_object) and opens the peers' regions.
  * Region layout (the host computes the pointers): ctr[16] u32 (local: [0] epoch, [1] ticket,
  * [2] error status, 1 = a peer did not deliver within timeout_ns) | flags [2][world][max_blocks] u32
- * | buffers [2][world][stride] f32. */
+ * | buffers [2][world][stride] f32 | low-latency slots [2][world][stride] of 8 bytes. */
 #define DRGNN_MAX_PEERS 8
 #define DRGNN_IPC_HANDLE_BYTES 64
 typedef struct drgnn_peer_comm {
@@ -444,6 +452,10 @@ typedef struct drgnn_peer_comm {
   int64_t stride;                      /* floats per slot (>= n_sum)                                  */
   int32_t max_blocks; int32_t reserved;
   uint64_t timeout_ns;                 /* watchdog of the wait (0 = 20 s)                             */
+  /* low-latency slots [2][world][stride] of 8-byte words {value bits, epoch} of rank r as mapped in
+   * THIS process: the in-kernel exchange of drgnn_ginet_step stores value and validity in ONE 8-byte
+   * store, so it needs neither a flag nor a system-scope fence (one NVLink hop per step) */
+  uint64_t* xll[DRGNN_MAX_PEERS];
 } drgnn_peer_comm;
 typedef struct drgnn_peer_adam_args {
   const float* partial; int32_t B; int32_t reserved0; int64_t partial_ld;  /* optional per-graph rows, summed in
