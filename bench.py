@@ -220,7 +220,7 @@ def describe(cfg, args, note=None):
                      'batch %d per GPU' % (args.workload, nodes, cfg.get('edges', '8 per node'), cfg['feat'], cfg['net'],
                                            tuple(cfg['hidden']), cfg['batch']),
          'net': cfg['net'], 'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * args.gpus,
-         'step': 'structure pass + forward + loss + backward + all-reduce + Adam',
+         'step': 'structure pass + forward + loss + backward + gradient reduction / exchange + Adam',
          'l2': 'inputs larger than L2: %d distinct batches rotated' % args.pool,
          'parallelism': 'dp%d' % args.gpus}
     if note:
@@ -353,7 +353,8 @@ def run_b200(args):
     cfg = workload_config(args.workload, args.batch)
     B = cfg['batch']
     graphs, batches = make_pool(cfg, args.pool, seed=1000 * rank)
-    packed = [PackedBatch.from_batch(b) for b in batches]
+    # compact feeder records (what NeuralNet builds): uint16 graph-local edge ids, edge attributes only for sGAT
+    packed = [PackedBatch.from_batch(b, idx16=True, edge_attr=cfg['net'] == 'sGAT') for b in batches]
     eng = Engine(cfg['net'], cfg['feat'], 1, 1, hidden=cfg['hidden'], device=dev, lr=0.001, graph=not args.no_graph,
                  seed=0)
     B_global = B * world
@@ -437,6 +438,20 @@ def run_b200(args):
     }
     if world == 1 and not args.no_roofline:
         line['roofline'] = aggregation_roofline(cfg, graphs, args.stream_nodes, hbm, peak_src, batches[0])
+        if cfg['net'] == 'GINet':
+            # the kernel that dominates the step itself: whole-step cluster kernel, one launch per step on the main
+            # stream (its duration is bounded by the step time measured above); algorithmic bytes = feature tiles +
+            # structure blobs read once, per-graph gradient rows written and re-read by the in-kernel reduction
+            pb0 = packed[0]
+            n_par = int(eng.params.numel)
+            blob_bytes = 4 * (32 * B + 9 * pb0.N + 5 * B + 3 * pb0.E)
+            alg = 4 * pb0.N * cfg['feat'] + blob_bytes + 2 * 4 * B * (n_par + 4) + 3 * 4 * n_par
+            us = 1e3 * t_dev / args.steps
+            line['roofline']['in_step'] = {
+                'kernel': 'ginet_graph_step2_kernel', 'algorithmic_bytes_per_launch': alg, 'launch_us_upper_bound': us,
+                'achieved': alg / (us * 1e-6) / 1e9, 'frac': alg / (us * 1e-6) / 1e9 / hbm,
+                'note': 'latency / issue bound at batch 64 (SURVEY fact 10): ncu shows 34 % issue-slot use and 3 MB of '
+                        'DRAM traffic per launch (profiles/r1_cluster_step_kernels_ncu_raw.csv)'}
     if world == 1 and not args.no_cpu:
         gps, ms, n = cpu_steps(cfg, batches[:8], seconds=args.cpu_seconds, warmup=2)
         cores = torch.get_num_threads()

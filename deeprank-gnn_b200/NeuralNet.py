@@ -260,7 +260,9 @@ class NeuralNet(object):
         packed, inv, tg = [], [], []
         for b in batches:
             has_y = getattr(b, 'y', None) is not None
-            packed.append(PackedBatch.from_batch(b, classes=classes if has_y else None))
+            # compact feeder records: uint16 graph-local edge ids; edge attributes only for the net that reads them
+            packed.append(PackedBatch.from_batch(b, classes=classes if has_y else None, idx16=True,
+                                                 edge_attr=eng.spec.kind == 'sgat'))
             if not has_y:
                 tg.append(None)
                 inv.append(1.0)

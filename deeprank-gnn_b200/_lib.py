@@ -37,7 +37,7 @@ class StructureIO(C.Structure):
     _fields_ = [
         ('B', C.c_int32), ('N', C.c_int32), ('E', C.c_int32), ('L1', C.c_int32), ('ne', C.c_int32),
         ('max_n', C.c_int32), ('max_e', C.c_int32), ('clusters_are_local', C.c_int32),
-        ('idx32', C.c_int32), ('reserved0', C.c_int32),
+        ('idx32', C.c_int32), ('edge16', C.c_int32),
         ('node_ptr', VP), ('edge_ptr', VP), ('c1_ptr', VP), ('edge_index', VP), ('edge_attr', VP),
         ('cluster0', VP), ('cluster1', VP),
         ('rowptr0', VP), ('col0', VP), ('eid0', VP), ('cscptr0', VP), ('cscrow0', VP), ('csceid0', VP),
@@ -136,6 +136,15 @@ class GinetStepArgs(C.Structure):
     ]
 
 
+class FeedStep(C.Structure):
+    _fields_ = [
+        ('h_src', VP), ('d_dst', VP), ('nbytes', C.c_int64),
+        ('prep_graph', VP), ('step_graph', VP),
+        ('d_out', VP), ('h_out', VP), ('out_bytes', C.c_int64),
+        ('slot', C.c_int32), ('reserved', C.c_int32),
+    ]
+
+
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
 
@@ -210,6 +219,7 @@ _SIGNATURES = {
     'drgnn_debug_blob_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_structure_blob_smem_bytes': (_i64, [_i32, _i32]),
     'drgnn_structure_blob': (C.c_int, [C.POINTER(StructureIO), VP]),
+    'drgnn_feed_run': (C.c_int, [C.POINTER(FeedStep), _i32, _i32, VP, VP, VP, VP, VP, VP, _i64, _i32]),
     'drgnn_debug_structure_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),
     'drgnn_head': (C.c_int, [C.POINTER(HeadArgs), VP]),

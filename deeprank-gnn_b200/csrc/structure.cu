@@ -338,8 +338,14 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   // ---- 1. local edge list ----
 #pragma unroll 1
   for (int e = t; e < m; e += T) {
-    long long r = ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
-    long long c = ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
+    long long r, c;
+    if (io.edge16) {   // compact feeder batches: uint16 graph-local ids
+      r = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)e0 + e];
+      c = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)io.E + e0 + e];
+    } else {
+      r = ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
+      c = ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
+    }
     if (r < 0 || r >= n || c < 0 || c >= n) {
       atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
       r = 0;

@@ -176,15 +176,17 @@ class PackedBatch(object):
     FLOAT_SECTIONS = ('x', 'edge_attr', 'y')
     INT_SECTIONS = ('edge_index', 'cluster0', 'node_ptr', 'edge_ptr', 'c1_ptr')
 
-    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False, max_k0=None, max_k1=None):
+    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False, max_k0=None, max_k1=None, idx16=False):
         self.B, self.N, self.E, self.L1, self.F, self.ne = B, N, E, L1, F, ne
+        # idx16: edge_index travels as uint16 graph-LOCAL node ids (2E half-words = E words instead of 2E)
+        self.idx16 = bool(idx16)
         self.max_n, self.max_e = max_n, max_e
         # per-graph cluster-count bounds, rounded up so that batches of one shape share a layout key
         # (and therefore one captured CUDA graph) although their exact counts differ
         self.max_k0 = None if not max_k0 else min(max_n, (max_k0 + 31) // 32 * 32)
         self.max_k1 = None if not max_k1 else min(max_n, (max_k1 + 15) // 16 * 16)
         self.with_class = with_class
-        sizes = dict(x=N * F, edge_attr=E * ne, y=B, edge_index=2 * E, cluster0=N, cluster1=L1, node_ptr=B + 1,
+        sizes = dict(x=N * F, edge_attr=E * ne, y=B, edge_index=(E if self.idx16 else 2 * E), cluster0=N, cluster1=L1, node_ptr=B + 1,
                      edge_ptr=B + 1, c1_ptr=B + 1)
         self.offsets = {}
         o = 0
@@ -202,7 +204,8 @@ class PackedBatch(object):
         self.has_y = False
 
     def layout_key(self):
-        return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class, self.max_k0, self.max_k1)
+        return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class, self.max_k0, self.max_k1,
+                self.idx16)
 
     @property
     def nbytes(self):
@@ -224,7 +227,11 @@ class PackedBatch(object):
             v['cluster1'] = ibuf[o:o + self.N]
         v['x'] = v['x'].view(self.N, self.F)
         v['edge_attr'] = v['edge_attr'].view(self.E, self.ne) if self.ne else None
-        v['edge_index'] = v['edge_index'].view(2, self.E)
+        if self.idx16:
+            o, _n = self.offsets['edge_index']
+            v['edge_index'] = buf.view(torch.int16)[2 * o:2 * o + 2 * self.E].view(2, self.E)
+        else:
+            v['edge_index'] = v['edge_index'].view(2, self.E)
         if self.with_class:
             o, n = self.offsets['y_class']
             v['y_class'] = ibuf[o:o + n].view(torch.int64)
@@ -233,9 +240,12 @@ class PackedBatch(object):
         return v
 
     @staticmethod
-    def from_batch(batch, pin=None, classes=None):
+    def from_batch(batch, pin=None, classes=None, edge_attr=True, idx16=False):
         """Pack a collated ``Batch``.  ``classes``: for classification, the class list used to
-        map targets to class indices (``format_output``, NeuralNet.py:616-631)."""
+        map targets to class indices (``format_output``, NeuralNet.py:616-631).  Compact options that
+        cut the bytes a step moves over PCIe: ``edge_attr=False`` leaves the edge attributes out
+        (GINet's attention is the identity - alpha == 1, SURVEY a1 - and FoutNet ignores them; only sGAT
+        reads them), ``idx16=True`` stores ``edge_index`` as uint16 graph-local node ids."""
         if batch._node_ptr is None or batch._c1_ptr is None:
             raise ValueError('PackedBatch needs a Batch collated by Batch.from_data_list with cluster0/cluster1')
         x = batch.x
@@ -244,9 +254,12 @@ class PackedBatch(object):
             ea = ea.unsqueeze(-1)
         N, F = x.size(0), (x.size(1) if x.dim() == 2 else 1)
         E = batch.edge_index.size(1)
+        if not edge_attr:
+            ea = None
         ne = 0 if ea is None else ea.size(1)
+        idx16 = bool(idx16) and batch._max_n <= 32767
         pb = PackedBatch(batch.num_graphs, N, E, batch.cluster1.numel(), F, ne, batch._max_n, batch._max_e,
-                         with_class=classes is not None, max_k0=batch._max_k0, max_k1=batch._max_k1)
+                         with_class=classes is not None, max_k0=batch._max_k0, max_k1=batch._max_k1, idx16=idx16)
         pin = torch.cuda.is_available() if pin is None else pin
         pb.buf = torch.zeros(pb.numel, dtype=torch.float32, pin_memory=bool(pin))
         v = pb.views(pb.buf)
@@ -260,7 +273,12 @@ class PackedBatch(object):
             if classes is not None:
                 c2i = {int(c): i for i, c in enumerate(classes)}
                 v['y_class'].copy_(torch.tensor([c2i[int(t)] for t in y.reshape(-1).tolist()], dtype=torch.int64))
-        v['edge_index'].copy_(batch.edge_index)
+        if idx16:
+            counts = (batch._edge_ptr[1:] - batch._edge_ptr[:-1]).long()
+            first = torch.repeat_interleave(batch._node_ptr[:-1].long(), counts)     # first node of every edge's graph
+            v['edge_index'].copy_(batch.edge_index - first.unsqueeze(0))
+        else:
+            v['edge_index'].copy_(batch.edge_index)
         v['cluster0'].copy_(batch.cluster0)
         v['cluster1'].copy_(batch.cluster1)
         v['node_ptr'].copy_(batch._node_ptr)

@@ -280,6 +280,10 @@ class Engine(object):
         self._adam_done = False
         self.fuse_adam = True
         self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
+        self.native_feed = os.environ.get('DRGNN_NATIVE_FEED', '1') != '0'   # train_batches loop issued from C
+        self._feed_keep = None
+        self._read_stream = None
+        self._read_ring = None
         self.fuse_comm = os.environ.get('DRGNN_FUSE_COMM', '1') != '0'   # peer exchange inside the step kernel
         self._cur_B_global = None
         self._last_exchange = None
@@ -828,10 +832,30 @@ class Engine(object):
             return
         g.replay()
 
+    def _prep_graph_handle(self, d):
+        """The captured structure-pass graph of batch ``d``'s slot (captured now if needed; the pass runs
+        once eagerly on the way, which is idempotent)."""
+        key = ('prep', d.key)
+        if self._graphs.get(key) is None:
+            self.prepare_graph(d)
+            if self._graphs.get(key) is None:   # buffer growth dropped it: second try captures
+                self.prepare_graph(d)
+        return self._graphs[key]
+
     def _step_graph(self, d, inv):
         """Replay (capture on first use) everything after the structure pass as one CUDA graph.
         The graph is tied to the staging buffer / structure slot of the batch; with several ranks
         the gradient all-reduce sits between the two captured halves."""
+        g1, g2 = self._step_graph_entry(d, inv)
+        g1.replay()
+        if g2 is not None:
+            self._all_reduce()
+            g2.replay()
+        return self.ws.loss, self.ws.pred[:d.B]
+
+    def _step_graph_entry(self, d, inv):
+        """The captured step graph(s) of batch ``d``'s slot: ``(g1, g2)``, captured on first use (warm-up on
+        the slot's current contents with the optimiser state restored afterwards); nothing is replayed."""
         key = ('step', d.key, round(inv, 12), self.training)
         ent = self._graphs.get(key)
         if ent is None:
@@ -868,12 +892,7 @@ class Engine(object):
             g2 = self._capture(self._adam) if split else None
             ent = (g1, g2)
             self._graphs[key] = ent
-        g1, g2 = ent
-        g1.replay()
-        if g2 is not None:
-            self._all_reduce()
-            g2.replay()
-        return self.ws.loss, self.ws.pred[:d.B]
+        return ent
 
     def _pipeline_state(self):
         if self._copy_stream is None:
@@ -917,6 +936,13 @@ class Engine(object):
         # one pinned read-back block for the whole pass (a pinned allocation per step would cost more than the step)
         width = 4 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
         host_all = torch.empty(max(len(packed_batches), 1), width, dtype=F32, pin_memory=True)
+        if self._feed_native(packed_batches, B_global, inv_norms, train, host_all, main, cs):
+            main.synchronize()
+            self.train(was_training)
+            n0, B0, out = self.params.numel, packed_batches[0].B, self.spec.out
+            losses = host_all[:, 0].clone()
+            preds = [host_all[i, 4:4 + B0 * out].view(B0, out) for i in range(len(packed_batches))]
+            return losses, preds
         for i, pb in enumerate(packed_batches):
             # pipeline: H2D copies and structure passes of the next batches (up to STRUCT_SLOTS - 1 ahead, on the
             # copy stream and two alternating structure streams) | step of batch i
@@ -953,6 +979,66 @@ class Engine(object):
         losses = torch.stack([h[0] for h, _ in outs]) if outs else torch.zeros(0)
         preds = [h[4:].view(shape) for h, shape in outs]
         return losses, preds
+
+    def _feed_native(self, packed_batches, B_global, inv_norms, train, host_all, main, cs):
+        """The loop of ``train_batches`` issued from C (``drgnn_feed_run``, csrc/feed.cu) when every batch
+        shares one layout (fixed-shape mini-batches), trains through the cluster step kernel and uses one
+        loss normaliser: per step the host then pays a handful of runtime calls instead of ~20 calls into
+        torch (55 us, more than the step and the PCIe copy need).  Returns False when not applicable."""
+        import ctypes as C
+        from . import _lib
+        ns = self.STRUCT_SLOTS
+        n = len(packed_batches)
+        if not (self.native_feed and self.use_graph and train and n > ns and (self.world == 1 or self.comm is not None)):
+            return False
+        key0 = packed_batches[0].layout_key()
+        if any(pb.layout_key() != key0 or not pb.has_y for pb in packed_batches):
+            return False
+        if inv_norms is not None and any(abs(v - inv_norms[0]) > 0 for v in inv_norms):
+            return False
+        if not hasattr(torch.cuda.CUDAGraph, 'raw_cuda_graph_exec'):
+            return False
+        inv0 = None if inv_norms is None else inv_norms[0]
+        # one staging slot, structure slot and pair of captured graphs per pipeline slot
+        slots = []
+        for j in range(ns):
+            d = self.upload(packed_batches[j], j, j)
+            if not self._blob_only(d):
+                return False
+            inv = self._inv_norm(d, B_global, inv0)
+            self._cur_B_global = B_global
+            pg = self._prep_graph_handle(d)
+            g1, g2 = self._step_graph_entry(d, inv)
+            if g2 is not None:
+                return False
+            slots.append((d, self._staging[(key0, j)], pg, g1))
+        torch.cuda.current_stream(self.device).synchronize()
+        steps = (_lib.FeedStep * n)()
+        n0 = self.params.numel
+        out_bytes = 4 * (4 + packed_batches[0].B * self.spec.out)
+        d_out = self._grads_full.data_ptr() + 4 * n0
+        for i, pb in enumerate(packed_batches):
+            d, stage, pg, g1 = slots[i % ns]
+            st = steps[i]
+            st.h_src, st.d_dst, st.nbytes = pb.buf.data_ptr(), stage.data_ptr(), 4 * pb.numel
+            st.prep_graph, st.step_graph = pg.raw_cuda_graph_exec(), g1.raw_cuda_graph_exec()
+            st.d_out, st.h_out, st.out_bytes = d_out, host_all[i].data_ptr(), out_bytes
+            st.slot = i % ns
+        if self._read_stream is None:
+            self._read_stream = torch.cuda.Stream(self.device)
+        ring_slots, ring_stride = 8, (out_bytes + 255) // 256 * 256
+        if self._read_ring is None or self._read_ring.numel() < ring_slots * ring_stride:
+            self._read_ring = torch.zeros(ring_slots * ring_stride, dtype=torch.uint8, device=self.device)
+        self._feed_keep = (steps, packed_batches, host_all)       # alive until the streams have drained
+        _lib.check(_lib.load().drgnn_feed_run(steps, n, ns, main.cuda_stream, cs.cuda_stream,
+                                              self._prep_streams[0].cuda_stream, self._prep_streams[1].cuda_stream,
+                                              self._read_stream.cuda_stream, self._read_ring.data_ptr(), ring_stride,
+                                              ring_slots),
+                   'drgnn_feed_run')
+        last = slots[(n - 1) % ns][0]
+        last.L1, last.mol = packed_batches[-1].L1, packed_batches[-1].mol
+        self._last_struct = self.structs[last.sslot]
+        return True
 
     def train_resident(self, dbatches, steps=None, B_global=None):
         """Training steps over batches already resident in HBM (``upload``-ed DeviceBatches, e.g. a

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, GinetStepArgs, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
                    require_cuda, stream_ptr)
 
-I32, I64, F32 = torch.int32, torch.int64, torch.float32
+I16, I32, I64, F32 = torch.int16, torch.int32, torch.int64, torch.float32
 
 
 def _ld(t):
@@ -168,9 +168,12 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     E = edge_index.size(1) if edge_index.dim() == 2 else 0
     # L1: live length of cluster1 when the tensor is a capacity-sized view (packed staging buffers)
     L1 = (0 if cluster1 is None else cluster1.numel()) if L1 is None else int(L1)
-    if edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or \
-            (cluster1 is not None and cluster1.dtype != edge_index.dtype):
-        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32)')
+    edge16 = edge_index.dtype == I16     # compact feeder batches: uint16 graph-local node ids, int32 cluster ids
+    if (edge16 and (cluster0.dtype != I32 or (cluster1 is not None and cluster1.dtype != I32))) or \
+            (not edge16 and (edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or
+                             (cluster1 is not None and cluster1.dtype != edge_index.dtype))):
+        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32), or be '
+                         'int16 graph-local edge ids with int32 cluster ids')
     if not edge_index.is_contiguous() or not cluster0.is_contiguous() or \
             (cluster1 is not None and not cluster1.is_contiguous()):
         raise DrgnnError('edge_index / cluster tensors must be contiguous')
@@ -202,7 +205,8 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, ne
     io.max_n, io.max_e = int(max_n), int(max_e)
     io.clusters_are_local = 1 if clusters_are_local else 0
-    io.idx32 = 1 if edge_index.dtype == I32 else 0
+    io.idx32 = 1 if cluster0.dtype == I32 else 0
+    io.edge16 = 1 if edge16 else 0
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
     io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
@@ -236,8 +240,12 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     N = cluster0.numel()
     E = edge_index.size(1) if edge_index.dim() == 2 else 0
     L1 = cluster1.numel() if L1 is None else int(L1)
-    if edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or cluster1.dtype != edge_index.dtype:
-        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32)')
+    edge16 = edge_index.dtype == I16
+    if (edge16 and (cluster0.dtype != I32 or cluster1.dtype != I32)) or \
+            (not edge16 and (edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or
+                             cluster1.dtype != edge_index.dtype)):
+        raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32), or be '
+                         'int16 graph-local edge ids with int32 cluster ids')
     if not edge_index.is_contiguous() or not cluster0.is_contiguous() or not cluster1.is_contiguous():
         raise DrgnnError('edge_index / cluster tensors must be contiguous')
     if L1 > N:
@@ -256,7 +264,8 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, 0
     io.max_n, io.max_e = int(max_n), int(max_e)
     io.clusters_are_local = 1
-    io.idx32 = 1 if edge_index.dtype == I32 else 0
+    io.idx32 = 1 if cluster0.dtype == I32 else 0
+    io.edge16 = 1 if edge16 else 0
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
     io.edge_index, io.edge_attr = ptr(edge_index), None
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)

@@ -78,7 +78,8 @@ typedef struct drgnn_structure_io {
                                  0: ids are already global (must increase with graph id)  */
   int32_t idx32;        /* 0: edge_index / cluster0 / cluster1 are int64 (reference tensors);
                            1: they are int32 (packed feeder batches)                       */
-  int32_t reserved0;
+  int32_t edge16;       /* 1: edge_index is uint16 [2,E] holding graph-LOCAL node ids (compact feeder
+                           batches: half the bytes over PCIe); cluster ids stay int32 (idx32 = 1)   */
   /* ---- inputs ---- */
   const int32_t* node_ptr;   /* [B+1] */
   const int32_t* edge_ptr;   /* [B+1] */
@@ -470,6 +471,26 @@ int drgnn_comm_close(void* peer_ptr);
 int drgnn_comm_free(void* dev_ptr);
 int drgnn_comm_status(const void* region, uint32_t* ctr4);   /* host copy of ctr[0..3] (synchronises the device) */
 int drgnn_peer_reduce_adam(const drgnn_peer_comm* c, const drgnn_peer_adam_args* a, void* stream);
+
+/* ---- end-to-end feeder: the pipelined epoch loop issued from C ----
+ * Replaces the per-step Python of Engine.train_batches (NeuralNet.py:490-523 over a DataLoader): for
+ * step i, on the copy stream ONE host->device copy of the packed batch into staging slot `slot`, on a
+ * structure stream the launch of the slot's structure-pass graph, on the main stream the launch of the
+ * slot's step graph, and ONE device->host copy of [loss | predictions] (staged through a small device
+ * ring on a read-back stream); a slot is rewritten only after the step that read it.  Handles: cudaStream_t / cudaGraphExec_t of the caller (PyTorch's are
+ * driver handles and valid here).  No host synchronisation. */
+typedef struct drgnn_feed_step {
+  const void* h_src; void* d_dst; int64_t nbytes;      /* pinned packed batch -> device staging slot        */
+  void* prep_graph; void* step_graph;                  /* cudaGraphExec_t of the slot's two captured graphs */
+  const void* d_out; void* h_out; int64_t out_bytes;   /* [loss | pad | predictions] read-back (may be 0)   */
+  int32_t slot; int32_t reserved;
+} drgnn_feed_step;
+/* ring (device, ring_slots x ring_stride bytes, ring_slots <= 8; 0 = read back on the main stream): the
+ * step's output block is copied device-to-device into ring slot i % ring_slots on the main stream and
+ * read back from there on read_stream, so the D2H latency stays off the step chain */
+int drgnn_feed_run(const drgnn_feed_step* steps, int32_t n, int32_t n_slots, void* main_stream, void* copy_stream,
+                   void* prep_stream0, void* prep_stream1, void* read_stream, void* ring, int64_t ring_stride,
+                   int32_t ring_slots);
 
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,

@@ -367,3 +367,50 @@ def test_cluster_step_kernel_in_kernel_reduction_equals_reduction_launch(lib):
     ea.step(big)
     assert ops.ginet_step_last_variant() == 2 and _lib.load().drgnn_ginet_step_last_launches() == 2
     ea.validate()
+
+
+def test_compact_packed_batches_train_like_reference_dtype_batches(lib):
+    """PackedBatch(idx16=True, edge_attr=False) - uint16 graph-local edge ids, no edge attributes (GINet's
+    attention is the identity) - trains exactly like the int64 reference-dtype batch."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs(dict(nodes=(20, 200), edges_per_node=5, feat=32), count=12, seed=31)
+    batch = Batch.from_data_list(graphs)
+    ea = Engine('GINet', 32, 1, 1, device='cuda:0', seed=2, dropout=0.0)
+    eb = Engine('GINet', 32, 1, 1, device='cuda:0', seed=2, dropout=0.0)
+    da = _device_batch(graphs)
+    pb = PackedBatch.from_batch(batch, idx16=True, edge_attr=False)
+    assert pb.nbytes < PackedBatch.from_batch(batch).nbytes
+    db = eb.upload(pb)
+    for _ in range(3):
+        la, pa = ea.step(da)
+        lb, pred_b = eb.step(db)
+        ea.validate(), eb.validate()
+        assert torch.equal(pa, pred_b) and torch.equal(la, lb)
+    assert torch.equal(ea.params.data, eb.params.data)
+
+
+def test_native_feed_loop_equals_python_pipeline(lib):
+    """Engine.train_batches with the loop issued from C (drgnn_feed_run: H2D copy, structure-pass graph,
+    step graph, D2H read-back per step) against the same pass issued from Python: identical losses,
+    predictions and weights."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch
+    from deeprank_gnn_b200.engine import Engine
+    packed = []
+    for i in range(11):
+        graphs = synthetic.make_graphs('cfg2', count=6, seed=100 + i)
+        packed.append(PackedBatch.from_batch(Batch.from_data_list(graphs), idx16=True, edge_attr=False))
+    ea = Engine('GINet', 32, 1, 1, device='cuda:0', seed=4, lr=1e-3, graph=True)
+    eb = Engine('GINet', 32, 1, 1, device='cuda:0', seed=4, lr=1e-3, graph=True)
+    eb.native_feed = False
+    la, pa = ea.train_batches(packed)
+    lb, pb_ = eb.train_batches(packed)
+    ea.validate(), eb.validate()
+    assert ea._feed_keep is not None and eb._feed_keep is None
+    assert torch.equal(la, lb)
+    for x, y in zip(pa, pb_):
+        assert torch.equal(x, y)
+    assert torch.equal(ea.params.data, eb.params.data)
+    assert float(ea.step_dev[0]) == 11.0

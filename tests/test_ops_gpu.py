@@ -135,6 +135,20 @@ def test_blob_structure_pass_equals_full_pass(lib, name, idx):
                             b.cluster0.to(idx).to(dev), b._max_n, b._max_e, b._c1_ptr.to(dev),
                             b.cluster1.to(idx).to(dev))
     sb.sync_counts()
+    if idx == torch.int32:
+        # compact feeder form: uint16 graph-LOCAL edge ids (what PackedBatch(idx16=True) ships), int32 cluster ids
+        cnt = (b._edge_ptr[1:] - b._edge_ptr[:-1]).long()
+        first = torch.repeat_interleave(b._node_ptr[:-1].long(), cnt)
+        ei16 = (b.edge_index - first.unsqueeze(0)).to(torch.int16).to(dev)
+        s16 = ops.structure_blob(b._node_ptr.to(dev), b._edge_ptr.to(dev), ei16, b.cluster0.to(idx).to(dev),
+                                 b._max_n, b._max_e, b._c1_ptr.to(dev), b.cluster1.to(idx).to(dev))
+        s16.sync_counts()
+        nw = 48 * len(graphs) + 12 * b.x.size(0) + 4 * b.edge_index.size(1)
+        assert torch.equal(s16.blob[:nw].cpu(), sb.blob[:nw].cpu())
+        f16 = ops.structure_build(b._node_ptr.to(dev), b._edge_ptr.to(dev), ei16, b.cluster0.to(idx).to(dev), b._max_n,
+                                  b._max_e, c1_ptr=b._c1_ptr.to(dev), cluster1=b.cluster1.to(idx).to(dev))
+        assert f16.sync_counts() == (K0, E1tot, K1tot)
+        assert torch.equal(f16.col0.cpu(), st.col0.cpu()) and torch.equal(f16.col1[:E1tot].cpu(), st.col1[:E1tot].cpu())
     full, lean = st.blob.cpu(), sb.blob.cpu()
     nptr, eptr = b._node_ptr.tolist(), b._edge_ptr.tolist()
     kptr0, kptr1 = st.kptr0.cpu().tolist(), st.kptr1.cpu().tolist()
