@@ -338,8 +338,11 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # keep stdout to the one JSON line: NCCL prints its version banner (and anything else) to stdout
+        # unless told otherwise
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
     if rank == 0:
