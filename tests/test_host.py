@@ -53,6 +53,9 @@ def test_ctypes_structs_match_header_layout(lib):
     assert fields('drgnn_ginet_step_args') == [f[0] for f in _lib.GinetStepArgs._fields_]
     assert fields('drgnn_peer_comm') == [f[0] for f in _lib.PeerComm._fields_]
     assert fields('drgnn_peer_adam_args') == [f[0] for f in _lib.PeerAdamArgs._fields_]
+    assert fields('drgnn_feed_step') == [f[0] for f in _lib.FeedStep._fields_]
+    import ctypes
+    assert ctypes.sizeof(_lib.FeedStep) == 72          # Engine._feed_native fills the records as 9 x int64
 
 
 def test_product_refuses_cpu_tensors(lib):
@@ -119,6 +122,18 @@ def test_batch_collation_and_packed_roundtrip():
         assert other.offsets[k][0] == pb.offsets[k][0]                          # one CUDA graph serves both
     pc = PackedBatch.from_batch(b, pin=False, classes=[0, 1])
     assert pc.views(pc.buf)['y_class'].dtype == torch.int64
+    # compact feeder record: uint16 graph-local edge ids, no edge attributes
+    cp = PackedBatch.from_batch(b, pin=False, idx16=True, edge_attr=False)
+    cv = cp.views(cp.buf)
+    assert cp.nbytes < pb.nbytes - 4 * b.edge_index.size(1) and cv['edge_attr'] is None
+    assert cv['edge_index'].dtype == torch.int16 and int(cv['edge_index'].max()) < 200
+    first = torch.repeat_interleave(b._node_ptr[:-1].long(), (b._edge_ptr[1:] - b._edge_ptr[:-1]).long())
+    assert torch.equal(cv['edge_index'].long() + first, b.edge_index)
+    assert torch.equal(cv['x'], b.x) and torch.equal(cv['cluster0'].long(), b.cluster0) and torch.equal(cv['y'], b.y)
+    assert cp.layout_key() != pb.layout_key()
+    dev_like = torch.zeros(cp.capacity_numel)          # staging-buffer sized views keep the same offsets
+    dev_like[:cp.numel] = cp.buf
+    assert torch.equal(cp.views(dev_like)['edge_index'], cv['edge_index'])
 
     class DS(object):
         def len(self):
@@ -216,3 +231,18 @@ def test_two_rank_gloo_gradient_allreduce_equals_full_batch(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count('ok') == 2
+
+
+def test_structure_blob_layout_macros_match_the_kernels():
+    """The blob addressing used by tests / host code (48 g + 12 n0 + 4 e0 words, 9 n + 5 + 3 m payload) is what the
+    header declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'drgnn.h')).read()
+    assert '#define DRGNN_BLOB_HEADER 32' in hdr
+    assert '(48 * (int64_t)(g) + 12 * (int64_t)(n0) + 4 * (int64_t)(e0))' in hdr
+    assert '(48 * (int64_t)(B) + 12 * (int64_t)(N) + 4 * (int64_t)(E) + 16)' in hdr
+    from deeprank_gnn_b200 import ops
+    ints, _f, _l = ops._structure_sizes(3, 100, 400, 100, 0)
+    assert ints['blob'] == 48 * 3 + 12 * 100 + 4 * 400 + 16
+    # every graph's payload fits its slot: 32 + 9 n + 5 + 3 m <= 48 + 12 n + 4 m
+    for n, m in ((0, 0), (1, 0), (5, 40), (200, 1000)):
+        assert ((32 + 9 * n + 5 + 3 * m + 3) & ~3) <= 48 + 12 * n + 4 * m

@@ -17,7 +17,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
     cfg = bench.workload_config('cfg2', None)
     _g, batches = bench.make_pool(cfg, 64, seed=0)
-    packed = [PackedBatch.from_batch(b) for b in batches]
+    packed = [PackedBatch.from_batch(b, idx16=True, edge_attr=False) for b in batches]
     eng = Engine(cfg['net'], cfg['feat'], 1, 1, hidden=cfg['hidden'], device='cuda:0', lr=1e-3, graph=True, seed=0)
     seq = [packed[i % 64] for i in range(n)]
     eng.train_batches(seq[:8])
@@ -31,6 +31,7 @@ def main():
     torch.cuda.synchronize()
     dev = 1e3 * s.elapsed_time(e) / n
     nbytes = packed[0].nbytes
+    print('host issue per step (C loop): %s us' % ('%.1f' % eng.feed_issue_us if eng.feed_issue_us else 'n/a (Python loop)'))
     print('train_batches: wall (incl. final sync) %.1f us/step | device %.1f us/step | H2D %.2f MB/step = %.1f GB/s at that rate'
           % (1e6 * (t1 - t0) / n, dev, nbytes / 1e6, nbytes / dev / 1e3))
     # raw H2D rate of the same buffers, nothing else
