@@ -219,7 +219,7 @@ def describe(cfg, args, note=None):
     d = {'workload': '%s: synthetic residue graphs, %s nodes / %s directed edges, %d node features, %s hidden %s, '
                      'batch %d per GPU' % (args.workload, nodes, cfg.get('edges', '8 per node'), cfg['feat'], cfg['net'],
                                            tuple(cfg['hidden']), cfg['batch']),
-         'net': cfg['net'], 'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * args.gpus,
+         'path': cfg['net'] + ' train step', 'batch_per_gpu': cfg['batch'], 'global_batch': cfg['batch'] * args.gpus,
          'step': 'structure pass + forward + loss + backward + gradient reduction / exchange + Adam',
          'l2': 'inputs larger than L2: %d distinct batches rotated' % args.pool,
          'parallelism': 'dp%d' % args.gpus}

@@ -741,11 +741,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       const int e = (int)blockIdx.x * per + sweep + el;
       const bool mine = sweep + el < per && e <= n;
       float acc = 0.f;
+      // optimiser state of this element, fetched alongside the gradient rows (one L2 round trip, not two)
+      float adam_mi = 0.f, adam_vi = 0.f, adam_pi = 0.f;
+      if (q == 0 && mine && !peers && s.fuse_adam && e < n) {
+        adam_mi = __ldcg(s.adam_m + e); adam_vi = __ldcg(s.adam_v + e); adam_pi = __ldcg(s.adam_p + e);
+      }
       if (mine) {
         const int gs = (B + 3) >> 2;
         const int g0 = q * gs, g1 = min(B, g0 + gs);
         const float* src = s.partial + e;
         int gg = g0;
+#pragma unroll 1
+        for (; gg + 16 <= g1; gg += 16) {     // 16 independent loads in flight (the whole quarter at batch 64)
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)(gg + u) * s.partial_ld);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc += v[u];
+        }
 #pragma unroll 1
         for (; gg + 8 <= g1; gg += 8) {
           float v[8];
@@ -771,13 +784,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
         } else if (e < n) {
           s.grads[e] = acc;
           if (s.fuse_adam) {
-            float mi = s.adam_m[e], vi = s.adam_v[e];
+            float mi = adam_mi, vi = adam_vi;
             mi = mi + (acc - mi) * (1.f - s.beta1);
             vi = vi * s.beta2 + (1.f - s.beta2) * acc * acc;
             s.adam_m[e] = mi;
             s.adam_v[e] = vi;
             const float denom = sqrtf(vi) / sqrtf(adamc[2]) + s.eps;
-            s.adam_p[e] = s.adam_p[e] - (s.lr / adamc[1]) * (mi / denom);
+            s.adam_p[e] = adam_pi - (s.lr / adamc[1]) * (mi / denom);
           }
         } else if (s.loss) {
           s.loss[0] = acc;
