@@ -414,3 +414,39 @@ def test_native_feed_loop_equals_python_pipeline(lib):
         assert torch.equal(x, y)
     assert torch.equal(ea.params.data, eb.params.data)
     assert float(ea.step_dev[0]) == 11.0
+
+
+def test_cluster_step_kernel_edge_cases_match_oracle(lib):
+    """SURVEY 8a-ter through the cluster kernel + bitmap structure pass, against the CPU oracle: a single
+    graph (B = 1: get_preloaded_cluster's loop never runs; the in-kernel reduction sweeps 5 k elements per
+    CTA), a graph whose clusters swallow every edge (pooled edge_index empty: conv2 aggregates nothing),
+    singleton clusters with gaps in the ids (consecutive_cluster closes them), an isolated node (deg 0 ->
+    zero row) and duplicate edges (aggregated twice at level 0, coalesced at level 1)."""
+    from deeprank_gnn_b200 import ops, synthetic
+    graphs = synthetic.make_graphs(dict(nodes=(40, 120), edges_per_node=5, feat=32), count=4, seed=41)
+    g = graphs[1]
+    n = g.x.size(0)
+    # all edges intra-cluster: two clusters = the two connected halves would still have cross edges, so use ONE cluster
+    g.cluster0 = torch.zeros(n, dtype=torch.long)
+    g.cluster1 = torch.zeros(1, dtype=torch.long)
+    h = graphs[2]
+    nh = h.x.size(0)
+    h.cluster0 = torch.arange(nh, dtype=torch.long) * 3 + 7          # singletons, ids with gaps
+    h.cluster1 = (torch.arange(nh, dtype=torch.long) // 2) * 5       # pairs, ids with gaps
+    k = graphs[3]
+    victim = 5
+    keep = (k.edge_index[0] != victim) & (k.edge_index[1] != victim)
+    k.edge_index = torch.cat([k.edge_index[:, keep], k.edge_index[:, keep][:, :7]], dim=1).contiguous()   # + duplicates
+    k.edge_attr = torch.cat([k.edge_attr[keep], k.edge_attr[keep][:7]]).contiguous()
+    for subset in (graphs, graphs[1:2], graphs[:1]):
+        sd0, loss, pred, grads, sd1 = _oracle_run('GINet', subset, (16, 32), 1, train=False)
+        eng = _engine('GINet', subset, (16, 32), 1, sd0).eval()
+        eng.step_variant = 2
+        d = _device_batch(subset)
+        eloss, epred = eng.step(d)
+        eng.validate()
+        assert ops.ginet_step_last_variant() == 2 and eng.structs[d.sslot].blob_only
+        _close(epred.view(-1), pred, 'pred')
+        _close(eloss.view(-1), loss.view(-1), 'loss')
+        for name, gr in eng.named_grads().items():
+            _close(gr, grads[name], 'grad ' + name)
