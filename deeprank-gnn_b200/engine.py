@@ -896,6 +896,24 @@ class Engine(object):
             self._graphs[key] = ent
         return ent
 
+    def _eval_graph_entry(self, d, inv):
+        """The captured scoring graph of batch ``d``'s slot: forward (+ loss without gradient), captured on
+        first use; nothing is replayed.  The inner call of ``NeuralNet.eval`` / ``test`` (NeuralNet.py:432-460)."""
+        key = ('eval', d.key, round(inv, 12), self.training)
+        g = self._graphs.get(key)
+        if g is None:
+            def body():
+                self._forward(d)
+                self._loss(d, inv, with_grad=False)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                body()                                   # eager warm-up: first-use setup inside the C-ABI
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = self._capture(body)
+            self._graphs[key] = g
+        return g
+
     def _pipeline_state(self):
         if self._copy_stream is None:
             ns = self.STRUCT_SLOTS
@@ -991,7 +1009,7 @@ class Engine(object):
         from . import _lib
         ns = self.STRUCT_SLOTS
         n = len(packed_batches)
-        if not (self.native_feed and self.use_graph and train and n > ns and (self.world == 1 or self.comm is not None)):
+        if not (self.native_feed and self.use_graph and n > ns and (self.world == 1 or self.comm is not None or not train)):
             return False
         key0 = packed_batches[0].layout_key()
         if any(pb.layout_key() != key0 or not pb.has_y for pb in packed_batches):
@@ -1002,7 +1020,7 @@ class Engine(object):
             return False
         inv0 = None if inv_norms is None else inv_norms[0]
         # one staging slot, structure slot and pair of captured graphs per pipeline slot (cached per layout)
-        ck = ('feed', key0, B_global, inv0, self.training)
+        ck = ('feed', key0, B_global, inv0, self.training, bool(train))
         slots = self._graphs.get(ck)
         if slots is None:
             slots = []
@@ -1013,7 +1031,7 @@ class Engine(object):
                 inv = self._inv_norm(d, B_global, inv0)
                 self._cur_B_global = B_global
                 pg = self._prep_graph_handle(d)
-                g1, g2 = self._step_graph_entry(d, inv)
+                g1, g2 = self._step_graph_entry(d, inv) if train else (self._eval_graph_entry(d, inv), None)
                 if g2 is not None:
                     return False
                 slots.append((d, self._staging[(key0, j)], pg, g1, pg.raw_cuda_graph_exec(), g1.raw_cuda_graph_exec()))

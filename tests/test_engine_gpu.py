@@ -450,3 +450,26 @@ def test_cluster_step_kernel_edge_cases_match_oracle(lib):
         _close(eloss.view(-1), loss.view(-1), 'loss')
         for name, gr in eng.named_grads().items():
             _close(gr, grads[name], 'grad ' + name)
+
+
+def test_native_feed_scoring_equals_python_pipeline(lib):
+    """Forward-only pass (NeuralNet.eval / test) through the C feeder loop: same losses and predictions as
+    the Python loop, weights untouched."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch
+    from deeprank_gnn_b200.engine import Engine
+    packed = []
+    for i in range(9):
+        graphs = synthetic.make_graphs('cfg2', count=5, seed=300 + i)
+        packed.append(PackedBatch.from_batch(Batch.from_data_list(graphs), idx16=True, edge_attr=False))
+    ea = Engine('GINet', 32, 1, 1, device='cuda:0', seed=8, graph=True)
+    eb = Engine('GINet', 32, 1, 1, device='cuda:0', seed=8, graph=True)
+    eb.native_feed = False
+    w0 = ea.params.data.clone()
+    la, pa = ea.train_batches(packed, train=False)
+    lb, pb_ = eb.train_batches(packed, train=False)
+    assert ea._feed_keep is not None and eb._feed_keep is None
+    torch.testing.assert_close(la, lb, rtol=1e-6, atol=1e-7)
+    for x, y in zip(pa, pb_):
+        assert torch.equal(x, y)
+    assert torch.equal(ea.params.data, w0) and float(ea.step_dev[0]) == 0.0

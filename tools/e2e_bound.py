@@ -34,6 +34,15 @@ def main():
     print('host issue per step (C loop): %s us' % ('%.1f' % eng.feed_issue_us if eng.feed_issue_us else 'n/a (Python loop)'))
     print('train_batches: wall (incl. final sync) %.1f us/step | device %.1f us/step | H2D %.2f MB/step = %.1f GB/s at that rate'
           % (1e6 * (t1 - t0) / n, dev, nbytes / 1e6, nbytes / dev / 1e3))
+    eng.train_batches(seq[:8], train=False)
+    torch.cuda.synchronize()
+    s.record()
+    eng.train_batches(seq, train=False)
+    e.record()
+    torch.cuda.synchronize()
+    sc = 1e3 * s.elapsed_time(e) / n
+    print('scoring (forward + loss, no gradient): %.1f us/step = %.2f M graphs/s end to end'
+          % (sc, cfg['batch'] / sc))
     # raw H2D rate of the same buffers, nothing else
     stage = torch.empty(packed[0].capacity_numel, dtype=torch.float32, device='cuda:0')
     torch.cuda.synchronize()
