@@ -709,7 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     const unsigned G = gridDim.x;
     const unsigned long long t0 = s2_globaltimer();
     while (s2_ld_acquire(sync_ctr) < G) {
-      if (s2_globaltimer() - t0 > 200000000ull) {   // 0.2 s: something is badly wrong; flag and go on
+      if (s2_globaltimer() - t0 > 2000000000ull) {   // 2 s (a time-sliced or instrumented GPU is slow, not wrong): flag and go on
         atomicOr(a.status, 128);
         break;
       }
