@@ -132,7 +132,7 @@ class GinetStepArgs(C.Structure):
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
         ('skip_reduce', C.c_int32), ('flags', C.c_int32), ('max_e', C.c_int32), ('variant', C.c_int32),
-        ('blob', VP), ('edge_ptr', VP), ('comm', VP),
+        ('blob', VP), ('edge_ptr', VP), ('comm', VP), ('gdesc', VP),
     ]
 
 

@@ -408,8 +408,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const int LDX = P.ldx, LDZ1 = P.ldz1, LDP = P.ldp, LDZ2 = P.ldz2;
 
   // ---- graph extents: ONE level of tiny loads (host-built pointers), then three bulk copies
-  const int n0 = __ldg(a.node_ptr + g), n = __ldg(a.node_ptr + g + 1) - n0;
-  const int eg0 = __ldg(s.edge_ptr + g), m = __ldg(s.edge_ptr + g + 1) - eg0;
+  int n0, n, eg0, m;
+  if (s.gdesc) {   // the record the structure pass left in L2 a moment ago: [K0, E1, K1, n0 | e0, m, 0, n]
+    const int4 lo = __ldg(reinterpret_cast<const int4*>(s.gdesc + 8 * (int64_t)g));
+    const int4 hi = __ldg(reinterpret_cast<const int4*>(s.gdesc + 8 * (int64_t)g + 4));
+    n0 = lo.w; eg0 = hi.x; m = hi.y; n = hi.w;
+  } else {
+    n0 = __ldg(a.node_ptr + g); n = __ldg(a.node_ptr + g + 1) - n0;
+    eg0 = __ldg(s.edge_ptr + g); m = __ldg(s.edge_ptr + g + 1) - eg0;
+  }
   const bool train = !(s.forward_only || s.task == 0);
   float* part = s.partial + (int64_t)g * s.partial_ld;
   // loop-invariant global scalars of the head and this branch's weights, fetched while the copies fly

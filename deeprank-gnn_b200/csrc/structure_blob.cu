@@ -141,6 +141,10 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   int32_t* bl = io.blob + DRGNN_BLOB_OFFSET(g, n0, e0);
   const BlobLayout BL = blob_layout(n, m);
   if (t < DRGNN_BLOB_HEADER) bl[t] = 0;
+  if (t == 0) {   // the graph's extents for the step kernel (io.gstat doubles as its descriptor table)
+    int32_t* gs = io.gstat + 8 * g;
+    gs[3] = n0; gs[4] = e0; gs[5] = m; gs[6] = 0; gs[7] = n;
+  }
   if (n < 0 || m < 0 || n > io.max_n || m > io.max_e) {   // host bounds violated: header stays incomplete
     if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
     return;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     bl[0] = n; bl[1] = m; bl[2] = K; bl[3] = E1; bl[4] = K1;
     bl[5] = bad1 ? 0 : 1;
     int32_t* gs = io.gstat + 8 * g;
-    gs[0] = K; gs[1] = E1; gs[2] = K1; gs[7] = n;
+    gs[0] = K; gs[1] = E1; gs[2] = K1;
   }
   DRGNN_BPHASE(5);
 }

@@ -558,7 +558,7 @@ class Engine(object):
                                skip_reduce=use_comm and not in_kernel, comm=self.comm if in_kernel else None,
                                max_e=d.max_e, mirror=self.keep_intermediates,
                                variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
-                               blob=st.blob,
+                               blob=st.blob, gdesc=st.gstat if st.blob_only else None,
                                edge_ptr=d.edge_ptr)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._adam_done = fuse_adam

@@ -503,7 +503,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
                drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
-               fuse_reduce=True, blob=None, edge_ptr=None, comm=None):
+               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -535,6 +535,8 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     s.blob, s.edge_ptr = ptr(blob), ptr(edge_ptr)
     # comm (parallel.PeerComm): the gradient exchange over peer memory runs inside the cluster kernel
     s.comm = C.addressof(comm.struct) if comm is not None else None
+    require_cuda(gdesc)
+    s.gdesc = ptr(gdesc)          # per-graph extents of a blob-only structure pass (Structure.gstat)
     s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2), int(variant)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the

@@ -395,6 +395,10 @@ typedef struct drgnn_ginet_step_args {
    * and applies Adam.  Every rank must launch the same grid (equal graphs per rank); needs
    * comm->max_blocks >= 2B, the grid co-resident (drgnn_ginet_step2_max_clusters) and fuse_adam. */
   const struct drgnn_peer_comm* comm;
+  /* gdesc (optional): io->gstat of a blob-only structure pass (drgnn_structure_blob) - 8 ints per graph
+   * [K0, E1, K1, node_ptr[g], edge_ptr[g], m, 0, n]: the cluster kernel reads a graph's extents from this
+   * L2-resident record (written a few microseconds earlier) instead of the cold node_ptr / edge_ptr */
+  const int32_t* gdesc;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
@@ -416,7 +420,7 @@ int drgnn_ginet_step2_max_clusters(int64_t smem_bytes);
  * [16] dW1 (end).  Synchronises the device. */
 int drgnn_debug_phase_cycles(uint64_t* out32);
 /* Blob-only structure pass: ONE launch (bitmap kernel, one CTA per graph) that writes io->blob,
- * io->status and io->gstat[8g + {0,1,2,7}] and nothing else - what the cluster step kernel of
+ * io->status and io->gstat[8g + 0..7] = [K0, E1, K1, node_ptr[g], edge_ptr[g], m, 0, n] and nothing else - what the cluster step kernel of
  * drgnn_ginet_step needs.  Replaces get_preloaded_cluster / consecutive_cluster / pool_edge +
  * coalesce / the CSR build for graphs whose bitmaps fit shared memory
  * (drgnn_structure_blob_smem_bytes >= 0); larger graphs: drgnn_structure_build (which writes the
