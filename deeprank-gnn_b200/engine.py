@@ -34,6 +34,24 @@ from ._lib import DrgnnError
 F32, I32, I64 = torch.float32, torch.int32, torch.int64
 
 
+def rotation_chunk(sslots, n_slots, lookahead):
+    """Steps per chunk CUDA graph for a rotation over batches whose structure slots are ``sslots`` (0: chunk
+    graphs do not apply).  Needs a chunk length that divides the rotation, and slots such that a batch, the
+    ``n_slots - 1`` batches before it never collide while the batch ``n_slots`` before it uses the same slot -
+    then a structure pass ``lookahead`` steps ahead only has to wait for the step that read its slot last."""
+    R = len(sslots)
+    if R < n_slots:
+        return 0
+    for i in range(R):
+        s_i = sslots[i]
+        if any(sslots[(i - k) % R] == s_i for k in range(1, n_slots)) or sslots[(i - n_slots) % R] != s_i:
+            return 0
+    for C in (16, 12, 8, 6, 5, 4):
+        if R % C == 0 and C > lookahead:
+            return C
+    return 0
+
+
 class NetSpec(object):
     """Architecture description of one of the reference networks."""
 
@@ -1124,21 +1142,10 @@ class Engine(object):
     ROTATION_LOOKAHEAD = 2      # structure passes run this many steps ahead inside a chunk graph (< STRUCT_SLOTS)
 
     def _rotation_chunk(self, dbatches):
-        """Steps per chunk graph for ``train_resident`` (0: not applicable).  Needs keyed (packed) batches,
-        a chunk length that divides the rotation, and structure slots such that a batch, the two batches
-        before it and the batch STRUCT_SLOTS before it never collide (so a pass two steps ahead only waits
-        for the step that read its slot last)."""
-        R, ns, la = len(dbatches), self.STRUCT_SLOTS, self.ROTATION_LOOKAHEAD
-        if R < ns or any(d.key is None for d in dbatches):
+        """Steps per chunk graph for ``train_resident`` (0: not applicable); see ``rotation_chunk``."""
+        if any(d.key is None for d in dbatches):
             return 0
-        for i in range(R):
-            s_i = dbatches[i].sslot
-            if any(dbatches[(i - k) % R].sslot == s_i for k in range(1, ns)) or dbatches[(i - ns) % R].sslot != s_i:
-                return 0
-        for C in (16, 12, 8, 6, 5, 4):
-            if R % C == 0 and C > la:
-                return C
-        return 0
+        return rotation_chunk([d.sslot for d in dbatches], self.STRUCT_SLOTS, self.ROTATION_LOOKAHEAD)
 
     def _chunk_graph(self, dbatches, start, C, B_global):
         """One CUDA graph: steps ``start .. start+C-1`` of the rotation on the capturing stream and the

@@ -246,3 +246,16 @@ def test_structure_blob_layout_macros_match_the_kernels():
     # every graph's payload fits its slot: 32 + 9 n + 5 + 3 m <= 48 + 12 n + 4 m
     for n, m in ((0, 0), (1, 0), (5, 40), (200, 1000)):
         assert ((32 + 9 * n + 5 + 3 * m + 3) & ~3) <= 48 + 12 * n + 4 * m
+
+
+def test_rotation_chunk_selection():
+    """Chunk CUDA graphs of Engine.train_resident: only for rotations whose structure slots cycle cleanly."""
+    from deeprank_gnn_b200.engine import rotation_chunk
+    assert rotation_chunk([i % 4 for i in range(64)], 4, 2) == 16
+    assert rotation_chunk([i % 4 for i in range(8)], 4, 2) == 8
+    assert rotation_chunk([i % 4 for i in range(20)], 4, 2) == 5
+    assert rotation_chunk([i % 4 for i in range(4)], 4, 2) == 4
+    assert rotation_chunk([i % 4 for i in range(6)], 4, 2) == 0        # slots collide across the wrap-around
+    assert rotation_chunk([0, 1], 4, 2) == 0                            # fewer batches than slots
+    assert rotation_chunk([0, 0, 1, 1, 2, 2, 3, 3], 4, 2) == 0          # neighbours share a slot
+    assert rotation_chunk([i % 4 for i in range(28)], 4, 2) == 4        # 28 = 4 * 7
