@@ -721,6 +721,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
         break;
       }
     }
+  } else if (t == 32) {
+    // optimiser step / exchange epoch of this launch (by another warp, while thread 0 waits at the barrier),
+    // read BEFORE the CTA's ticket is taken (below): the last ticket holder changes them
+    if (s.fuse_adam) {
+      const float st = *reinterpret_cast<volatile float*>(s.step_dev) + 1.f;
+      red[0] = st;
+      red[1] = adam_bias_correction(s.beta1, st);
+      red[2] = adam_bias_correction(s.beta2, st);
+    }
+    if (C.world > 1) *reinterpret_cast<unsigned*>(red + 4) = *reinterpret_cast<volatile uint32_t*>(C.ctr) + 1u;
+    __threadfence();
   }
   __syncthreads();
   DRGNN_PHASE(17);
@@ -733,14 +744,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     unsigned* epoch_s = reinterpret_cast<unsigned*>(red + 4);
     const int world = C.world, rank = C.rank;
     const bool peers = world > 1;
-    if (t == 0) {
-      if (s.fuse_adam) {
-        const float st = s.step_dev[0] + 1.f;
-        adamc[0] = st;
-        adamc[1] = adam_bias_correction(s.beta1, st);
-        adamc[2] = adam_bias_correction(s.beta2, st);
+    if (t == T - 1) {
+      // Bookkeeping of the launch by a thread that has no element to reduce (per < 128), so its global round
+      // trips overlap the loads of the others: the last CTA to take a ticket re-arms the grid barrier,
+      // publishes the exchange epoch and bumps the optimiser step.  A CTA takes its ticket AFTER it passed the
+      // barrier and after thread 0 read the step / epoch (fence + CTA barrier above), so nothing of this
+      // launch can still need the old values when they change.
+      unsigned* ticket = reinterpret_cast<unsigned*>(s.step_dev + 1);
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        *ticket = 0u;
+        *sync_ctr = 0u;
+        if (peers) *reinterpret_cast<volatile uint32_t*>(C.ctr) = *epoch_s;
+        if (s.fuse_adam) s.step_dev[0] = adamc[0];
       }
-      if (peers) *epoch_s = *reinterpret_cast<volatile uint32_t*>(C.ctr) + 1u;
     }
     // ---- local sums of this CTA's slice; one GPU: Adam right away, several: delivered to every rank
 #pragma unroll 1
@@ -846,17 +863,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
             s.loss[0] = tot;
           }
         }
-      }
-    }
-    __syncthreads();
-    if (t == 0) {   // the last CTA to finish re-arms the barrier, publishes the epoch, bumps the optimiser step
-      unsigned* ticket = reinterpret_cast<unsigned*>(s.step_dev + 1);
-      __threadfence();
-      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-        *ticket = 0u;
-        *sync_ctr = 0u;
-        if (peers) *reinterpret_cast<volatile uint32_t*>(C.ctr) = *epoch_s;
-        if (s.fuse_adam) s.step_dev[0] = adamc[0];
       }
     }
   }
