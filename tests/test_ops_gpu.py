@@ -185,6 +185,57 @@ def test_blob_structure_pass_equals_full_pass(lib, name, idx):
     assert (k_seen, e1_seen) == (K0, E1tot)
 
 
+def _numpy_blob(n, row, col, c0, c1):
+    """The blob arrays of ONE graph from first principles (graph-local ids): consecutive_cluster = rank among
+    the sorted unique ids; CSR = stable sort by destination; pool_edge + coalesce = sorted unique (row, col)
+    pairs of the relabelled edges without self loops; member lists = stable sort by cluster."""
+    def rank(ids):
+        u = np.unique(ids)
+        return np.searchsorted(u, ids), len(u)
+
+    def ptr(keys, k):
+        return np.concatenate([[0], np.cumsum(np.bincount(keys, minlength=k))])
+    d0, K = rank(c0)
+    d1, K1 = rank(c1)
+    order = np.argsort(row, kind='stable')
+    out = {'rp0': ptr(row, n), 'col0': col[order], 'cl0': d0, 'cmp0': ptr(d0, K), 'cmem0': np.argsort(d0, kind='stable'),
+           'cl1': d1, 'cmp1': ptr(d1, K1), 'cmem1': np.argsort(d1, kind='stable')}
+    pr, pc = d0[row], d0[col]
+    keep = pr != pc
+    pairs = np.unique(np.stack([pr[keep], pc[keep]], axis=1), axis=0) if keep.any() else np.zeros((0, 2), dtype=np.int64)
+    out['rp1'], out['col1'] = ptr(pairs[:, 0], K), pairs[:, 1]
+    byc = pairs[np.lexsort((pairs[:, 0], pairs[:, 1]))] if len(pairs) else pairs
+    out['cscp1'], out['cscr1'] = ptr(byc[:, 1], K), byc[:, 0]
+    return out, K, len(pairs), K1
+
+
+@pytest.mark.parametrize('name', ['fixture10', 'cfg2x8', 'small_mixed'])
+def test_blob_structure_pass_matches_first_principles(lib, name):
+    """``drgnn_structure_blob`` against an independent numpy construction of every list (not against another
+    kernel): bit-exact, on the shipped fixture (real MCL clusters with id gaps) and on synthetic graphs."""
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.data import Batch
+    sets = _graph_sets()
+    sets['small_mixed'] = synthetic.make_graphs(dict(nodes=(5, 260), edges_per_node=6, feat=8), count=9, seed=17)
+    graphs = sets[name]
+    dev = _dev()
+    b = Batch.from_data_list(graphs)
+    sb = ops.structure_blob(b._node_ptr.to(dev), b._edge_ptr.to(dev), b.edge_index.to(dev), b.cluster0.to(dev),
+                            b._max_n, b._max_e, b._c1_ptr.to(dev), b.cluster1.to(dev))
+    sb.sync_counts()
+    blob = sb.blob.cpu()
+    nptr, eptr, cptr = b._node_ptr.tolist(), b._edge_ptr.tolist(), b._c1_ptr.tolist()
+    for g in range(len(graphs)):
+        n0, e0 = nptr[g], eptr[g]
+        n, m = nptr[g + 1] - n0, eptr[g + 1] - e0
+        ei = b.edge_index[:, e0:e0 + m].numpy() - n0
+        ref, K, E1, K1 = _numpy_blob(n, ei[0], ei[1], b.cluster0[n0:n0 + n].numpy(), b.cluster1[cptr[g]:cptr[g + 1]].numpy())
+        v = _blob_views(blob, g, n0, e0, n, m)
+        assert v['header'] == [n, m, K, E1, K1, 1], (g, v['header'])
+        for key, arr in ref.items():
+            assert np.array_equal(v[key].numpy(), arr), (g, key)
+
+
 def test_blob_structure_pass_flags_invalid_input(lib):
     from deeprank_gnn_b200 import ops
     from deeprank_gnn_b200._lib import DrgnnError
