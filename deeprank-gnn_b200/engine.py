@@ -448,8 +448,7 @@ class Engine(object):
             # fused GINet path: ONE launch writes the per-graph structure blobs, nothing else
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
                                     d.cluster1, out=slot, L1=d.L1)
-            if slot is None:
-                self.structs[d.sslot] = st
+            assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
         st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
