@@ -288,6 +288,79 @@ class PackedBatch(object):
         return pb
 
 
+class PackedCache(object):
+    """Packed, memory-mapped on-disk cache of feeder records: every mini-batch of a pass is
+    stored as its ``PackedBatch`` block (compact: uint16 graph-local edge ids, int32 cluster ids, fp32 features)
+    in ONE binary file, 64-byte aligned, behind a small JSON index.  An epoch then never touches HDF5 or Python
+    collation (``DataSet.py:241-366`` opens the file and rebuilds ~10 tensors per graph): ``cache[i]`` is a
+    ``PackedBatch`` whose buffer is a view of the memory map (``pin=True``: a pinned copy, ready for the
+    asynchronous host->device copy of ``Engine.train_batches``).
+
+    File: ``b'DRGNNPC1'`` | uint64 index length | JSON index | padding to 64 | records."""
+
+    MAGIC = b'DRGNNPC1'
+    FIELDS = ('B', 'N', 'E', 'L1', 'F', 'ne', 'max_n', 'max_e')
+
+    @staticmethod
+    def build(path, packed_batches):
+        """Write ``packed_batches`` (an iterable of ``PackedBatch``) to ``path``.  Returns the number of records."""
+        import json
+        metas, blobs, off = [], [], 0
+        for pb in packed_batches:
+            m = {k: int(getattr(pb, k)) for k in PackedCache.FIELDS}
+            m.update(with_class=bool(pb.with_class), idx16=bool(pb.idx16), has_y=bool(pb.has_y),
+                     max_k0=pb.max_k0, max_k1=pb.max_k1, numel=int(pb.numel), offset=off,
+                     mol=list(pb.mol) if pb.mol is not None else None)
+            metas.append(m)
+            blobs.append(pb.buf.detach().cpu().numpy().view(np.uint8))
+            off += (4 * pb.numel + 63) // 64 * 64
+        index = json.dumps({'version': 1, 'records': metas}).encode()
+        head = PackedCache.MAGIC + np.uint64(len(index)).tobytes() + index
+        head += b'\0' * ((-len(head)) % 64)
+        with open(path, 'wb') as f:
+            f.write(head)
+            for m, raw in zip(metas, blobs):
+                f.write(raw.tobytes())
+                f.write(b'\0' * ((-raw.nbytes) % 64))
+        return len(metas)
+
+    def __init__(self, path, pin=False):
+        import json
+        self.path, self.pin = path, bool(pin)
+        with open(path, 'rb') as f:
+            if f.read(8) != self.MAGIC:
+                raise ValueError('%s is not a packed cache' % path)
+            n = int(np.frombuffer(f.read(8), dtype=np.uint64)[0])
+            index = json.loads(f.read(n).decode())
+        if index.get('version') != 1:
+            raise ValueError('unsupported packed-cache version %r' % index.get('version'))
+        self.records = index['records']
+        self._base = (16 + n + 63) // 64 * 64
+        self._map = np.memmap(path, dtype=np.float32, mode='r', offset=self._base) if self.records else None
+
+    def __len__(self):
+        return len(self.records)
+
+    def __getitem__(self, i):
+        m = self.records[i]
+        pb = PackedBatch(m['B'], m['N'], m['E'], m['L1'], m['F'], m['ne'], m['max_n'], m['max_e'],
+                         with_class=m['with_class'], idx16=m['idx16'])
+        pb.max_k0, pb.max_k1 = m['max_k0'], m['max_k1']          # stored already rounded
+        assert pb.numel == m['numel'], 'packed-cache record %d does not match the record layout' % i
+        start = m['offset'] // 4
+        view = torch.from_numpy(np.asarray(self._map[start:start + pb.numel]))
+        if self.pin:
+            buf = torch.empty(pb.numel, dtype=torch.float32, pin_memory=True)
+            buf.copy_(view)
+        else:
+            buf = view                                            # read-only view of the memory map
+        pb.buf, pb.has_y, pb.mol = buf, m['has_y'], m['mol']
+        return pb
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class DataLoader(object):
     """Worker-less loader with the call signature the reference uses
     (``DataLoader(dataset, batch_size=..., shuffle=...)``, ``NeuralNet.py:105,153,158``).

@@ -259,3 +259,39 @@ def test_rotation_chunk_selection():
     assert rotation_chunk([0, 1], 4, 2) == 0                            # fewer batches than slots
     assert rotation_chunk([0, 0, 1, 1, 2, 2, 3, 3], 4, 2) == 0          # neighbours share a slot
     assert rotation_chunk([i % 4 for i in range(28)], 4, 2) == 4        # 28 = 4 * 7
+
+
+def test_packed_cache_roundtrip(tmp_path):
+    """Packed on-disk cache of feeder records: what comes back from the memory map is the
+    record that went in - sections, layout key, bounds, molecule names - for compact and plain records."""
+    import warnings
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch, PackedCache
+    from deeprank_gnn_b200.DataSet import HDF5DataSet
+    from conftest import FIXTURE
+    ds = HDF5DataSet(database=FIXTURE, node_feature=['type', 'polarity', 'bsa'], target='irmsd')
+    fix = [ds.get(i) for i in range(ds.len())]
+    packed = [PackedBatch.from_batch(Batch.from_data_list(fix[:4]), pin=False, idx16=True, edge_attr=False),
+              PackedBatch.from_batch(Batch.from_data_list(fix[4:]), pin=False),
+              PackedBatch.from_batch(Batch.from_data_list(synthetic.make_graphs('cfg2', count=3, seed=1)), pin=False,
+                                     idx16=True, classes=[0, 1])]
+    path = str(tmp_path / 'epoch.drgnnpc')
+    assert PackedCache.build(path, packed) == 3
+    assert os.path.getsize(path) % 64 == 0
+    cache = PackedCache(path)
+    assert len(cache) == 3
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')          # torch warns about the read-only memory map
+        for src, got in zip(packed, cache):
+            assert got.layout_key() == src.layout_key() and got.numel == src.numel and got.has_y == src.has_y
+            assert got.mol == (list(src.mol) if src.mol is not None else None)
+            assert torch.equal(got.buf, src.buf)
+            va, vb = src.views(src.buf), got.views(got.buf)
+            for k in ('x', 'y', 'edge_index', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr'):
+                assert torch.equal(va[k], vb[k]), k
+        again = PackedCache(path)[1]
+        assert torch.equal(again.views(again.buf)['edge_attr'], packed[1].views(packed[1].buf)['edge_attr'])
+    with open(str(tmp_path / 'junk'), 'wb') as f:
+        f.write(b'not a cache, definitely')
+    with pytest.raises(ValueError):
+        PackedCache(str(tmp_path / 'junk'))
