@@ -8,19 +8,25 @@
 //
 //   * the cluster's CTA r owns branch r (conv1_r -> pool -> conv2_r -> pool -> mean), so a batch of
 //     64 graphs occupies 128 SMs and every dense product is half as wide;
-//   * ONE asynchronous staging pass (cp.async, two commit groups) brings the graph's feature tile,
-//     EVERY index slice of both graph levels (CSR, CSC, cluster members, cluster ids) and the head
-//     weights into shared memory; after it no phase touches global memory except to store results;
+//   * ONE asynchronous staging pass - three TMA bulk copies (cp.async.bulk + mbarrier): the graph's
+//     structure blob (EVERY index slice of both graph levels with graph-local ids, written by the
+//     structure pass, structure_blob.cu), its feature tile and fc1.weight - brings everything into
+//     shared memory; after it no phase touches global memory except to store results;
 //   * every intermediate the backward needs (AX, Z1, argmax0, AP, Z2, argmax1) stays in shared
 //     memory (optionally mirrored to global memory for the parity tests, flag bit 0);
 //   * the two halves of the read-out row are exchanged through distributed shared memory
 //     (one cluster barrier); the tiny head (fc1 / ReLU / dropout / fc2 / loss) is evaluated by both
 //     CTAs, its gradient rows are written half by each;
 //   * the weight-gradient products (dW1 = dZ1^T AX, dW2 = dZ2^T AP: M, N tiny, K = nodes) are
-//     split over K across the whole CTA and reduced in a fixed order (deterministic).
+//     split over K across the whole CTA and reduced in a fixed order (deterministic);
+//   * when the grid is co-resident (B <= clusters the device holds) the per-graph gradient rows are
+//     reduced behind a grid barrier inside the same launch, Adam is applied there, and on several
+//     GPUs the slices travel to the peers over NVLink as 8-byte {value, epoch} words first
+//     (rank-ordered sum: bit-identical weights on every rank, no flag, no fence, no extra launch).
 //
-// Arithmetic per output element is the same fmaf chain, in the same order, as v1 / the op-level
-// kernels for everything but the split-K weight gradients.
+// Arithmetic per output element of the graph part is the same fmaf chain, in the same order, as v1 /
+// the op-level kernels; the split-K weight gradients, the 4-lane fc1 and the 4-quarter gradient
+// reduction use their own fixed orders.
 #pragma once
 // (fused.cu includes <cooperative_groups.h> at global scope before entering the namespace)
 
