@@ -31,8 +31,17 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = 'protein-interface graphs/sec (GINet fwd+bwd, batch=64)'
+METRIC = 'protein-interface graphs/sec (GINet fwd+bwd, batch=64)'      # BASELINE.json (cfg2)
 UNIT = 'graphs/s'
+ALIGN_STEPS = 16      # untimed steps enqueued right before the start event (device-side rank alignment)
+
+
+def metric_name(cfg):
+    """BASELINE.json's metric for the headline workload; the same wording with the network / batch of the
+    other workloads."""
+    if cfg['net'] == 'GINet' and cfg['batch'] == 64:
+        return METRIC
+    return 'protein-interface graphs/sec (%s fwd+bwd, batch=%d)' % (cfg['net'], cfg['batch'])
 
 
 def parse():
@@ -40,6 +49,8 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--repeats', type=int, default=25,
+                    help='the K-step timed region is measured this many times; the median is reported')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--batch', type=int, default=None, help='graphs per GPU per step (default: the config batch)')
@@ -200,21 +211,21 @@ def run_reference(args):
         if args.steps * 0.2 < 240 else cpu_steps(cfg, batches, seconds=120.0, warmup=3)
     cores = torch.get_num_threads()
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': gps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n,
+        'impl': 'reference', 'metric': metric_name(cfg), 'value': gps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': describe(cfg, args, note='CPU oracle: pure-torch restatement of the reference step '
-                                           '(the reference itself needs torch_geometric/torch_scatter, absent here)'),
+        'config': describe(cfg, args),
         'cpu_baseline': {'value': gps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d training steps (fwd+bwd+Adam) of batch %d on %d host threads'
-                                   % (n, cfg['batch'], cores)},
+                         'sample': '%d training steps (fwd+bwd+Adam) of batch %d on %d host threads; CPU oracle = '
+                                   'pure-torch restatement of the reference step (the reference itself needs '
+                                   'torch_geometric / torch_scatter, absent here)' % (n, cfg['batch'], cores)},
         'e2e': {'value': gps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def describe(cfg, args, note=None):
+def describe(cfg, args):
     nodes = cfg['nodes']
     d = {'workload': '%s: synthetic residue graphs, %s nodes / %s directed edges, %d node features, %s hidden %s, '
                      'batch %d per GPU' % (args.workload, nodes, cfg.get('edges', '8 per node'), cfg['feat'], cfg['net'],
@@ -223,8 +234,6 @@ def describe(cfg, args, note=None):
          'step': 'structure pass + forward + loss + backward + gradient reduction / exchange + Adam',
          'l2': 'inputs larger than L2: %d distinct batches rotated' % args.pool,
          'parallelism': 'dp%d' % args.gpus}
-    if note:
-        d['note'] = note
     return d
 
 
@@ -311,9 +320,12 @@ def aggregation_roofline(cfg, graphs, n_nodes_target, hbm_gbs, peak_src, in_situ
     return {
         'bound': 'hbm', 'kernel': best, 'achieved': achieved, 'peak': hbm_gbs, 'unit': 'GB/s',
         'frac': achieved / hbm_gbs,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this stream, from the
-        # ncu --set full capture committed as profiles/r1_agg_tiled_final_ncu_raw.csv (996.4 MB + 791.0 MB)
-        'traffic': 1787434496.0 if (N == 6553600 and C == 32 and best == 'aggregate_tiled_kernel') else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this stream: NOT measured
+        # in this run - read from the committed ncu --set full capture (996.4 MB + 791.0 MB)
+        'traffic': _profile_csv_metric(os.path.join(ROOT, 'profiles', 'r1_agg_tiled_final_ncu_raw.csv'),
+                                       'aggregate_tiled_kernel', ['dram__bytes_read.sum', 'dram__bytes_write.sum'])
+        if (N == 6553600 and C == 32 and best == 'aggregate_tiled_kernel') else None,
+        'traffic_source': 'profiles/r1_agg_tiled_final_ncu_raw.csv (ncu --set full of the same launch; not measured in this run)',
         'peak_source': peak_src,
         'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': t_best,
         'stream': {'nodes': N, 'directed_edges': E, 'channels': C, 'rows_kernel_ms': t_rows, 'tiled_kernel_ms': t_tiled,
@@ -325,6 +337,59 @@ def aggregation_roofline(cfg, graphs, n_nodes_target, hbm_gbs, peak_src, in_situ
                     'note': 'step-sized launch replayed from a CUDA graph (L2 resident, launch-latency bound)'},
     }
 
+
+
+def _profile_csv_metric(path, kernel_substr, metrics):
+    """Sum of `metrics` (ncu --page raw --csv columns) over the launches of the kernels matching
+    `kernel_substr` in a committed profile, divided by the number of launches; None when absent."""
+    import csv
+    if not os.path.exists(path):
+        return None
+    with open(path, newline='') as f:
+        rows = list(csv.reader(f))
+    if len(rows) < 3:
+        return None
+    head = rows[0]
+    try:
+        kcol = head.index('Kernel Name')
+        cols = [head.index(m) for m in metrics]
+    except ValueError:
+        return None
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        if len(r) <= max(cols + [kcol]) or kernel_substr not in r[kcol]:
+            continue
+        try:
+            vals = [float(r[c].replace(',', '')) for c in cols]
+        except ValueError:
+            continue
+        units = [rows[1][c] for c in cols]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        tot += sum(v * scale.get(u, 1.0) for v, u in zip(vals, units))
+        n += 1
+    return tot / n if n else None
+
+
+def step_kernel_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
+    `ncu --set full` capture of this workload (profiles/); (None, reason) when there is none."""
+    for name in ('r2_step_%s_ncu_raw.csv' % workload, 'r1_cluster_step_kernels_ncu_raw.csv' if workload == 'cfg2' else ''):
+        if not name:
+            continue
+        path = os.path.join(ROOT, 'profiles', name)
+        v = _profile_csv_metric(path, kernel, ['dram__bytes_read.sum', 'dram__bytes_write.sum'])
+        if v is not None:
+            return v, 'profiles/' + name + ' (ncu --set full, per launch; not measured in this run)'
+    return None, 'no ncu capture of this kernel committed'
+
+
+def dense_roofline():
+    """The dense per-node transform on the tensor pipe (cfg4 shape), from the committed ncu capture."""
+    path = os.path.join(ROOT, 'profiles', 'r2_dense_summary.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
 
 # ------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
@@ -372,49 +437,78 @@ def run_b200(args):
     eng.use_graph = not args.no_graph
     for d in resident:                                   # capture / first-touch everything (untimed)
         eng.step(d, B_global=B_global)
-    eng.train_resident(resident, steps=len(resident), B_global=B_global)   # captures the chunk graphs of one rotation (untimed)
-    eng.train_resident(resident, steps=max(args.warmup, 3), B_global=B_global)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    K, W, REP = args.steps, max(args.warmup, 3), max(1, args.repeats)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    # structure pass of step i+1 on a side stream while step i computes (Engine.train_resident)
-    eng.train_resident(resident, steps=args.steps, B_global=B_global)
-    ev1.record()
-    torch.cuda.synchronize()
-    t_dev = ev0.elapsed_time(ev1)          # ms
-    if world > 1:
-        dist.barrier()
-        t = torch.tensor([t_dev], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev = float(t.item())
+        sampler.start()                                  # nvidia-smi forks here, far away from any timed region
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def resident_region():
+        """barrier + synchronize | ALIGN_STEPS untimed steps | start event | EXACTLY K steps | stop event |
+        synchronize + barrier.  The untimed steps are enqueued without a host sync in front of the start event:
+        with several ranks every step ends in the peer exchange, so all ranks' start events sit within one
+        NVLink hop of each other whatever the skew of the hosts leaving the barrier (the host is far ahead of
+        the device: one graph launch per 16 steps).  No step of the region is issued eagerly (chunk graphs of
+        16 steps + one of K % 16)."""
+        sync_all()
+        eng.train_resident(resident, steps=ALIGN_STEPS, B_global=B_global, start=0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        eng.train_resident(resident, steps=K, B_global=B_global, start=ALIGN_STEPS)
+        ev1.record()
+        sync_all()
+        return ev0.elapsed_time(ev1)          # ms
+
+    resident_region()                                    # captures the chunk graphs (untimed)
+    eng.train_resident(resident, steps=W, B_global=B_global)     # the W warm-up steps
+    t_res = [resident_region() for _ in range(REP)]
     final_loss = float(eng.ws.loss.item())
     eng.validate()
 
     # ---- end to end: pinned host batches -> train_batches (H2D + step + D2H per step)
-    seq = [packed[i % len(packed)] for i in range(args.steps)]
-    eng.train_batches(seq[:max(4, args.warmup)], B_global=B_global)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    losses, preds = eng.train_batches(seq, B_global=B_global)
-    e1.record()
-    torch.cuda.synchronize()
-    t_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        dist.barrier()
-        t = torch.tensor([t_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    seq = [packed[i % len(packed)] for i in range(K)]
+    eng.train_batches(seq[:max(8, W)], B_global=B_global)
+
+    def e2e_region():
+        sync_all()
+        eng.train_resident(resident, steps=ALIGN_STEPS, B_global=B_global, start=0)   # untimed: aligns the ranks
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses, _preds = eng.train_batches(seq, B_global=B_global)     # returns after its own host sync
+        e1.record()
+        sync_all()
+        assert bool(torch.isfinite(losses).all()), 'non-finite loss in the end-to-end run'
+        return e0.elapsed_time(e1)
+
+    e2e_region()
+    t_e2e = [e2e_region() for _ in range(max(1, min(REP, 15)))]
     clocks = sampler.stop() if rank == 0 else None
-    assert bool(torch.isfinite(losses).all()), 'non-finite loss in the end-to-end run'
+    eng.validate()
+
+    def over_ranks(ts):
+        """per-repeat MAX over ranks, then the median over the repeats"""
+        t = torch.tensor(ts, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = sorted(t.tolist())
+        return v[len(v) // 2], v[0], v[-1]
+    t_dev, t_dev_min, t_dev_max = over_ranks(t_res)
+    t_e2e_med, t_e2e_min, t_e2e_max = over_ranks(t_e2e)
+    # data-parallel invariant: every rank holds bit-identical weights after the same steps
+    weights_equal = True
+    if world > 1:
+        chk = eng.params.data.view(torch.int32).to(torch.int64)
+        mine = torch.stack([chk.sum(), (chk * torch.arange(1, chk.numel() + 1, device=dev)).sum()])
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        weights_equal = all(bool(torch.equal(c, allc[0])) for c in allc)
+        assert weights_equal, 'the weights differ between ranks after the same training steps'
+    t_e2e = t_e2e_med
 
     if rank != 0:
         if world > 1:
@@ -423,13 +517,14 @@ def run_b200(args):
         return
     hbm, peak_src = peaks()
     line = {
-        'metric': METRIC, 'value': B_global * args.steps / (t_dev * 1e-3), 'unit': UNIT, 'n_gpus': world,
+        'metric': metric_name(cfg), 'value': B_global * args.steps / (t_dev * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': describe(cfg, args),
         'e2e': {'value': B_global * args.steps / (t_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(pool_bytes / len(packed)), 'd2h_bytes_per_step': 4 * (4 + B),
-                'ms_per_step': t_e2e / args.steps,
+                'ms_per_step': t_e2e / args.steps, 'repeats': len(range(max(1, min(REP, 15)))),
+                'ms_per_step_min_max': [t_e2e_min / K, t_e2e_max / K],
                 'api': 'Engine.train_batches(PackedBatch[...]) - pinned host batch, one H2D copy, fused step, '
                        'D2H of loss + predictions'},
         'gpu_launches': kernels_per_step * args.steps,
@@ -438,23 +533,40 @@ def run_b200(args):
         'collective': eng.collective() + ('' if eng.comm_error is None else ' (peer memory unavailable: %s)' % eng.comm_error),
         'final_loss': final_loss,
         'clocks': clocks,
+        'timing': {'repeats': REP, 'statistic': 'median over repeats of (max over ranks) of the K-step region',
+                   'ms_per_step_min_max': [t_dev_min / K, t_dev_max / K],
+                   'region': 'barrier + synchronize | %d untimed steps (device-side rank alignment, no host sync) | '
+                             'CUDA event | exactly K steps (chunk CUDA graphs, none eager) | CUDA event | synchronize + '
+                             'barrier' % ALIGN_STEPS},
+        'weights_equal_across_ranks': weights_equal if world > 1 else None,
     }
     if world == 1 and not args.no_roofline:
-        line['roofline'] = aggregation_roofline(cfg, graphs, args.stream_nodes, hbm, peak_src, batches[0])
-        if cfg['net'] == 'GINet':
-            # the kernel that dominates the step itself: whole-step cluster kernel, one launch per step on the main
-            # stream (its duration is bounded by the step time measured above); algorithmic bytes = feature tiles +
-            # structure blobs read once, per-graph gradient rows written and re-read by the in-kernel reduction
-            pb0 = packed[0]
-            n_par = int(eng.params.numel)
-            blob_bytes = 4 * (32 * B + 9 * pb0.N + 5 * B + 3 * pb0.E)
-            alg = 4 * pb0.N * cfg['feat'] + blob_bytes + 2 * 4 * B * (n_par + 4) + 3 * 4 * n_par
-            us = 1e3 * t_dev / args.steps
-            line['roofline']['in_step'] = {
-                'kernel': 'ginet_graph_step2_kernel', 'algorithmic_bytes_per_launch': alg, 'launch_us_upper_bound': us,
-                'achieved': alg / (us * 1e-6) / 1e9, 'frac': alg / (us * 1e-6) / 1e9 / hbm,
-                'note': 'latency / issue bound at batch 64 (SURVEY fact 10): ncu shows 34 % issue-slot use and 3 MB of '
-                        'DRAM traffic per launch (profiles/r1_cluster_step_kernels_ncu_raw.csv)'}
+        agg = aggregation_roofline(cfg, graphs, args.stream_nodes, hbm, peak_src, batches[0])
+        # PRIMARY entry = the kernel that dominates the timed step: the whole-step kernel, one launch per step,
+        # back to back on the main stream inside the chunk graphs (the structure pass of later batches runs
+        # beside it on side streams), so its average launch duration over the timed region is ms_per_step.
+        # Algorithmic bytes per launch = feature tiles + structure blobs read once
+        # + per-graph gradient rows written and re-read by the in-kernel reduction + parameters / Adam state.
+        pb0 = packed[0]
+        n_par = int(eng.params.numel)
+        blob_bytes = 4 * (32 * B + 9 * pb0.N + 5 * B + 3 * pb0.E)
+        alg = 4 * pb0.N * cfg['feat'] + blob_bytes + 2 * 4 * B * (n_par + 4) + 3 * 4 * n_par
+        us = 1e3 * t_dev / K
+        step_kernel = eng.step_kernel_name()
+        traffic, traffic_src = step_kernel_traffic(step_kernel, args.workload)
+        line['roofline'] = {
+            'bound': 'hbm', 'kernel': step_kernel, 'achieved': alg / (us * 1e-6) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+            'frac': alg / (us * 1e-6) / 1e9 / hbm, 'traffic': traffic, 'traffic_source': traffic_src,
+            'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg, 'launch_us': us,
+            'launches_per_step': kernels_per_step,
+            'note': 'whole-step kernel at batch %d: latency / issue bound by construction (SURVEY fact 10, %d KB per '
+                    'graph); the HBM-bound stream-scale kernel of the path is reported under aggregation_stream'
+                    % (B, alg // B // 1024),
+            'aggregation_stream': agg,
+        }
+        dense = dense_roofline()
+        if dense is not None:
+            line['roofline']['dense'] = dense
     if world == 1 and not args.no_cpu:
         gps, ms, n = cpu_steps(cfg, batches[:8], seconds=args.cpu_seconds, warmup=2)
         cores = torch.get_num_threads()

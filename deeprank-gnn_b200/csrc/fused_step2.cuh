@@ -433,13 +433,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     if (s.task == 3) y_cls = (int)__ldg(s.y_class + g);
     else y_first = __ldg(s.y + (int64_t)g * out);
   }
-  if (n < 0 || m < 0 || n > a.max_n || m > s.max_e) {   // host bounds violated: flag and leave (validate())
+  // The per-graph work sits in a do { } while (0): an invalid graph (host bounds violated, incomplete blob)
+  // zeroes its gradient row, flags the status word and BREAKS to the grid barrier below instead of leaving the
+  // kernel - every CTA must reach the barrier and take its ticket, or the counters would not be re-armed
+  // for the next launch.  Both CTAs of a cluster see the same extents and take the same path.
+  do {
+  if (n < 0 || m < 0 || n > a.max_n || m > s.max_e) {   // host bounds violated: flag, contribute nothing (validate())
     if (t == 0) atomicOr(a.status, 64);
     if (train && r == 0) {
 #pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
     }
-    return;   // both CTAs of the cluster take this branch
+    break;
   }
   if (t == 0) {
     s2_mbar_init(&bars[0], 1);
@@ -490,7 +495,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 #pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
     }
-    return;
+    break;
   }
   const BlobLayout BL = blob_layout(n, m);
   const int* rp0 = blb + BL.rp0;     const int* col0 = blb + BL.col0;   const int* rp1 = blb + BL.rp1;  const int* col1 = blb + BL.col1;
@@ -710,7 +715,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   s2_splitk_reduce(scratch, H1 * F, KS1, part + s.off_w1 + r * H1 * F, t, T);
   DRGNN_PHASE(16);
-  if (!P.fused_reduce) return;
+  } while (0);
+  if (!P.fused_reduce || !train) return;
   // ---- gradient reduction (+ Adam) inside this launch: the grid is co-resident (2B <= SMs, one CTA
   // per SM), so a grid barrier is safe; afterwards CTA c owns a slice of the flat gradient buffer and
   // sums the per-graph rows in four contiguous quarters (ascending), combined in ascending order.

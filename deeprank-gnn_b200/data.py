@@ -211,9 +211,10 @@ class PackedBatch(object):
     def nbytes(self):
         return 4 * self.numel
 
-    def views(self, buf):
+    def views(self, buf, capacity=False):
         """Typed views of the sections inside ``buf`` (a float32 tensor of ``numel`` elements,
-        host or device)."""
+        host or device).  ``capacity=True`` (device staging buffers of ``capacity_numel`` elements
+        only): ``cluster1`` is a view of N entries whose live length is ``L1``."""
         v = {}
         for k in self.FLOAT_SECTIONS:
             o, n = self.offsets[k]
@@ -222,7 +223,9 @@ class PackedBatch(object):
         for k in self.INT_SECTIONS + ('cluster1',):
             o, n = self.offsets[k]
             v[k] = ibuf[o:o + n]
-        if buf.numel() >= self.capacity_numel:      # staging buffers: capacity-sized view, live length = L1
+        if capacity:                                # staging buffers: capacity-sized view, live length = L1
+            if buf.numel() < self.capacity_numel:
+                raise ValueError('a capacity view needs a buffer of capacity_numel = %d elements' % self.capacity_numel)
             o, _n = self.offsets['cluster1']
             v['cluster1'] = ibuf[o:o + self.N]
         v['x'] = v['x'].view(self.N, self.F)

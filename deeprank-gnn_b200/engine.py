@@ -232,7 +232,7 @@ class DeviceBatch(object):
     def from_packed(pb, dev_buf):
         """Views into ``dev_buf`` (device float32 buffer holding a copy of ``pb.buf``)."""
         d = DeviceBatch()
-        v = pb.views(dev_buf)
+        v = pb.views(dev_buf, capacity=True)
         d.x, d.edge_attr, d.y, d.y_class = v['x'], v['edge_attr'], (v['y'] if pb.has_y else None), v['y_class']
         d.edge_index, d.cluster0, d.cluster1 = v['edge_index'], v['cluster0'], v['cluster1']
         d.node_ptr, d.edge_ptr, d.c1_ptr = v['node_ptr'], v['edge_ptr'], v['c1_ptr']
@@ -296,6 +296,7 @@ class Engine(object):
         self._fused_fit = {}
         self._graph_done = False
         self._all_done = False
+        self._all_done_kernel = False    # the last training step ran a whole-step kernel
         self._adam_done = False
         self.fuse_adam = True
         self.step_variant = int(os.environ.get('DRGNN_STEP_VARIANT', '0'))   # 0 pick, 1 single-CTA kernel, 2 cluster kernel
@@ -304,6 +305,8 @@ class Engine(object):
         self.feed_issue_us = None
         self._read_stream = None
         self._read_ring = None
+        self._host_out = None
+        self._primed = None              # (rotation, index): structure passes train_resident left done
         self.fuse_comm = os.environ.get('DRGNN_FUSE_COMM', '1') != '0'   # peer exchange inside the step kernel
         self._cur_B_global = None
         self._last_exchange = None
@@ -312,6 +315,11 @@ class Engine(object):
         self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
         self.fuse_reduce = os.environ.get('DRGNN_FUSE_REDUCE', '1') != '0'   # gradient reduction + Adam behind a grid barrier
         self.seed = 0x5EED if seed is None else int(seed)
+        if self.world > 1:
+            # per-rank dropout stream: the in-kernel mask hashes (seed, step, LOCAL graph, unit), so
+            # ranks sharing a seed would draw identical masks for their shards
+            rank = dist.get_rank(process_group)
+            self.seed = (self.seed ^ (0x9E3779B1 * (rank + 1))) & 0xffffffff
         self._head_fits = ops.head_fits(self.spec.C2, self.spec.Hd, self.spec.out)
         self._head_done = False
         self.launches_per_step = 0
@@ -337,6 +345,13 @@ class Engine(object):
         if self._last_exchange == 'in-kernel':
             return 'peer-memory exchange + rank-ordered sum + Adam inside the step kernel (no extra launch)'
         return 'peer-memory exchange fused with reduce+Adam (1 launch)'
+
+    def step_kernel_name(self):
+        """Name of the kernel that carries the step of the last batch (bench.py's roofline entry)."""
+        if self.spec.kind == 'ginet' and self._all_done_kernel:
+            return {1: 'ginet_graph_step_kernel', 2: 'ginet_graph_step2_kernel'}.get(ops.ginet_step_last_variant(),
+                                                                                      'ginet_graph_step_kernel')
+        return 'op-level sequence (aggregate_rows_kernel / linear_fma_kernel / ...)'
 
     # ---------------------------------------------------------------- parameters
     def reset_parameters(self, seed=None):
@@ -429,6 +444,8 @@ class Engine(object):
             self.ws.pred = self._grads_full[n + 4:].view(nb, self.spec.out)
             ne_attr = 1 if self.spec.kind == 'sgat' else 0
             self.structs = [ops.Structure(nb, nn_, ne_, nn_, ne_attr, self.device) for _ in range(self.STRUCT_SLOTS)]
+            for st in self.structs:
+                st.sticky_status = True      # status words are OR-ed over the passes of an epoch, see validate()
             self._graphs.clear()
         return self.ws
 
@@ -438,6 +455,7 @@ class Engine(object):
         stream.  It depends on the batch only (not on the weights), so callers may run it on a
         side stream while the previous step computes (``train_batches`` / ``train_resident`` do)."""
         self._ensure(d.B, d.N, d.E)
+        self._primed = None              # a structure slot changes: train_resident primes its lookahead again
         need_w = self.spec.kind == 'sgat'
         if need_w and d.edge_attr is None:
             raise DrgnnError('sGAT needs edge_attr')
@@ -578,6 +596,7 @@ class Engine(object):
                                blob=st.blob, gdesc=st.gstat if st.blob_only else None,
                                edge_ptr=d.edge_ptr)
                 self._graph_done = self._head_done = self._all_done = train_step
+                self._all_done_kernel = True
                 self._adam_done = fuse_adam
                 if use_comm and not self._no_exchange:
                     self._last_exchange = 'in-kernel' if in_kernel else 'launch'
@@ -841,6 +860,7 @@ class Engine(object):
         """``prepare`` replayed from a CUDA graph (captured on first use for the batch's layout)."""
         key = ('prep', d.key)
         g = self._graphs.get(key)
+        self._primed = None
         if g is None:
             self.prepare(d)                     # eager warm-up (first-use attribute setup, buffer growth)
             if self._graphs.get(key) is None:   # growth clears the cache; the warm-up result stays valid
@@ -963,6 +983,7 @@ class Engine(object):
         main = torch.cuda.current_stream(self.device)
         cs = self._pipeline_state()
         ns = self.STRUCT_SLOTS
+        self._primed = None
         cs.wait_stream(main)
         for ps in self._prep_streams:
             ps.wait_stream(main)
@@ -972,13 +993,19 @@ class Engine(object):
         packed_batches = list(packed_batches)
         # one pinned read-back block for the whole pass (a pinned allocation per step would cost more than the step)
         width = 4 + max([pb.B for pb in packed_batches] + [1]) * self.spec.out
-        host_all = torch.empty(max(len(packed_batches), 1), width, dtype=F32, pin_memory=True)
+        rows = max(len(packed_batches), 1)
+        # the pinned block is cached (grow-only): cudaHostAlloc costs 0.1-1 ms and serialises between the
+        # processes of a multi-GPU job - inside a short pass it was the N = 4 / 8 end-to-end outlier
+        if self._host_out is None or self._host_out.numel() < rows * width:
+            self._host_out = torch.empty(max(rows * width, 4096), dtype=F32, pin_memory=True)
+        host_all = self._host_out[:rows * width].view(rows, width)
         if self._feed_native(packed_batches, B_global, inv_norms, train, host_all, main, cs):
             main.synchronize()
             self.train(was_training)
             n0, B0, out = self.params.numel, packed_batches[0].B, self.spec.out
             losses = host_all[:, 0].clone()
-            preds = [host_all[i, 4:4 + B0 * out].view(B0, out) for i in range(len(packed_batches))]
+            pall = host_all[:, 4:4 + B0 * out].clone()          # the pinned block is reused by the next pass
+            preds = [pall[i].view(B0, out) for i in range(len(packed_batches))]
             return losses, preds
         for i, pb in enumerate(packed_batches):
             # pipeline: H2D copies and structure passes of the next batches (up to STRUCT_SLOTS - 1 ahead, on the
@@ -1014,7 +1041,7 @@ class Engine(object):
         main.synchronize()
         self.train(was_training)
         losses = torch.stack([h[0] for h, _ in outs]) if outs else torch.zeros(0)
-        preds = [h[4:].view(shape) for h, shape in outs]
+        preds = [h[4:].clone().view(shape) for h, shape in outs]
         return losses, preds
 
     def _feed_native(self, packed_batches, B_global, inv_norms, train, host_all, main, cs):
@@ -1092,39 +1119,47 @@ class Engine(object):
         self._last_struct = self.structs[last.sslot]
         return True
 
-    def train_resident(self, dbatches, steps=None, B_global=None):
+    def train_resident(self, dbatches, steps=None, B_global=None, start=0):
         """Training steps over batches already resident in HBM (``upload``-ed DeviceBatches, e.g. a
         data set cached on the device across epochs), cycling through ``dbatches`` for ``steps``
         steps.  The structure passes of the next batches run on two side streams while step i
         computes (``upload(pb, slot)`` spreads the batches over ``STRUCT_SLOTS`` structure slots;
         a slot is rewritten only after the step that read it).  No host synchronisation.  Returns
-        (loss, pred) of the last step."""
+        (loss, pred) of the last step.  ``start``: index of the first batch of this call in the rotation;
+        a call that continues where the previous one stopped finds its first structure passes done."""
         n = len(dbatches) if steps is None else steps
+        start = int(start) % max(len(dbatches), 1)
         main = torch.cuda.current_stream(self.device)
         self._pipeline_state()
         out = None
         first = 0
         R = len(dbatches)
-        C = self._rotation_chunk(dbatches) if (self.use_graph and self.rotation_graph and n >= 4 and
+        C = self._rotation_chunk(dbatches) if (self.use_graph and self.rotation_graph and n >= 1 and
                                                (self.world == 1 or self.comm is not None)) else 0
-        if C and n >= C:
+        if C:
             # CUDA graphs of C consecutive steps each (structure passes of the batches two steps ahead on side
             # streams + the steps, with their dependencies): the host issues one launch per C steps instead of
-            # ~4 calls per step - the per-step issue cost had become the bound of the resident loop
+            # ~4 calls per step - the per-step issue cost had become the bound of the resident loop.  The
+            # remainder n % C is one more (shorter) chunk graph, so NO step is issued eagerly.
             LA = self.ROTATION_LOOKAHEAD
-            for j in range(LA):                      # structure passes the first chunk expects to find done
-                self._prepare_any(dbatches[j % R])
-            for c in range(n // C):
-                self._chunk_graph(dbatches, (c * C) % R, C, B_global).replay()
+            rot = tuple(d.key for d in dbatches)
+            # (a first-use capture runs an eager warm-up step that rewrites structure slots: capture first, prime after)
+            graphs = [self._chunk_graph(dbatches, (start + c * C) % R, C, B_global) for c in range(n // C)]
             first = (n // C) * C
-            out = (self.ws.loss, self.ws.pred[:dbatches[(first - 1) % R].B])
-            if first == n:
-                return out
+            if n > first:
+                graphs.append(self._chunk_graph(dbatches, (start + first) % R, n - first, B_global))
+            if self._primed != (rot, start):
+                for j in range(LA):                  # structure passes the first chunk expects to find done
+                    self._prepare_any(dbatches[(start + j) % R])
+            for g in graphs:
+                g.replay()
+            self._primed = (rot, (start + n) % R)    # every chunk leaves the passes of the next LA batches done
+            return (self.ws.loss, self.ws.pred[:dbatches[(start + n - 1) % R].B])
         for ps in self._prep_streams:
             ps.wait_stream(main)
         used = set()
         for i in range(first, n):
-            d = dbatches[i % len(dbatches)]
+            d = dbatches[(start + i) % len(dbatches)]
             slot = d.sslot
             ps = self._prep_streams[i & 1]
             with torch.cuda.stream(ps):
@@ -1200,10 +1235,24 @@ class Engine(object):
         return g
 
     def validate(self):
-        """Raise if the last structure pass flagged invalid input (ONE host sync)."""
-        if self._last_struct is not None:
-            self._last_struct._counts_host = None
-            self._last_struct.sync_counts()
+        """Raise if ANY structure pass / step since the last call flagged invalid input (ONE host sync).
+        Every structure slot keeps a sticky status word (never cleared by a launch), so a malformed batch in
+        the middle of an epoch is reported by the check at its end.  After an error the grid-barrier counters
+        of the fused step are re-armed, so training may go on with the next batch."""
+        live = [st for st in self.structs if st is not None]
+        if live:
+            bits = 0
+            for v in torch.cat([st.status for st in live]).cpu().tolist():
+                bits |= int(v)
+            for st in live:
+                st._counts_host = None
+            if bits:
+                for st in live:
+                    st.status.zero_()
+                self.step_dev[1:3].zero_()       # ticket / barrier counter of the in-kernel reduction
+                from . import _lib
+                msgs = [t for bit, t in _lib.STATUS_TEXT.items() if bits & bit]
+                raise DrgnnError('invalid batch structure: ' + '; '.join(msgs or ['status %d' % bits]))
         if self.comm is not None and self.comm.status() != 0:
             raise DrgnnError('gradient exchange: a peer rank did not deliver its gradients within the watchdog '
                              '(DRGNN_PEER_TIMEOUT_S); the weights of this rank are no longer valid')

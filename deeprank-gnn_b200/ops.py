@@ -101,6 +101,7 @@ class Structure(object):
             setattr(self.io, k, ptr(getattr(self, k)))
         self._counts_host = None
         self._keep = None
+        self.sticky_status = False       # True: structure_build does not zero `status` (Engine: one check per epoch)
         self._shape_views()
 
     def fits(self, B, N, E, L1, ne, mirrors):
@@ -135,8 +136,8 @@ class Structure(object):
             st = host[4]
             if self.blob_only:
                 host[:3] = [-1, -1, -1]      # the blob-only pass computes no batch totals
-                if st:
-                    self.status.zero_()      # sticky status: reported once, then re-armed
+            if st and (self.blob_only or self.sticky_status):
+                self.status.zero_()          # sticky status: reported once, then re-armed
             if st:
                 msgs = [t for bit, t in _lib.STATUS_TEXT.items() if st & bit]
                 raise DrgnnError('invalid batch structure: ' + '; '.join(msgs))
@@ -215,7 +216,8 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
         s.status.zero_()
         return s
     st = stream_ptr()
-    call('drgnn_fill_i32', ptr(s.status), 0, 1, st)
+    if not s.sticky_status:
+        call('drgnn_fill_i32', ptr(s.status), 0, 1, st)
     call('drgnn_structure_build', C.byref(io), st)
     return s
 

@@ -295,3 +295,22 @@ def test_packed_cache_roundtrip(tmp_path):
         f.write(b'not a cache, definitely')
     with pytest.raises(ValueError):
         PackedCache(str(tmp_path / 'junk'))
+
+
+def test_packed_batch_with_almost_as_many_clusters_as_nodes():
+    """a batch whose number of level-0 clusters falls into the same 4-word bucket as its node
+    count (pad4(L1) == pad4(N), L1 < N) must pack: only device staging buffers get the capacity-sized
+    ``cluster1`` view (``views(buf, capacity=True)``)."""
+    from deeprank_gnn_b200.data import Batch, Data, PackedBatch
+    g = Data(x=torch.randn(4, 3), edge_index=torch.tensor([[0, 1, 2, 3], [1, 0, 3, 2]]),
+             edge_attr=torch.rand(4, 1), y=torch.tensor([0.5]), pos=torch.randn(4, 3),
+             cluster0=torch.tensor([0, 1, 2, 2]), cluster1=torch.tensor([0, 0, 1]))
+    b = Batch.from_data_list([g])
+    pb = PackedBatch.from_batch(b, pin=False)
+    assert pb.L1 == 3 and pb.N == 4 and pb.numel == pb.capacity_numel
+    v = pb.views(pb.buf)
+    assert v['cluster1'].numel() == 3 and v['cluster1'].tolist() == [0, 0, 1]
+    cap = pb.views(torch.zeros(pb.capacity_numel), capacity=True)
+    assert cap['cluster1'].numel() == 4
+    with pytest.raises(ValueError):
+        pb.views(torch.zeros(pb.capacity_numel - 4), capacity=True)
