@@ -401,6 +401,8 @@ def run_b200(args):
         raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from deeprank_gnn_b200.parallel import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else 'single process: not bound'
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # keep stdout to the one JSON line: NCCL prints its version banner (and anything else) to stdout
@@ -539,6 +541,7 @@ def run_b200(args):
                              'CUDA event | exactly K steps (chunk CUDA graphs, none eager) | CUDA event | synchronize + '
                              'barrier' % ALIGN_STEPS},
         'weights_equal_across_ranks': weights_equal if world > 1 else None,
+        'host_numa': numa,
     }
     if world == 1 and not args.no_roofline:
         agg = aggregation_roofline(cfg, graphs, args.stream_nodes, hbm, peak_src, batches[0])

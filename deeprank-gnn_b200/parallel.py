@@ -11,6 +11,54 @@ import os
 import torch
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        a, _, b = part.partition('-')
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is
+    allocated (first-touch: the feeder's pinned blocks then live in the memory next to the GPU's PCIe root
+    instead of crossing the socket interconnect - with 8 feeders that link is the end-to-end bound).
+    Reads /sys (numa_node of the GPU's PCI function, cpulist of the node); returns a short description of
+    what was done, never raises."""
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id \
+            if hasattr(torch.cuda.get_device_properties(device_index), 'pci_bus_id') else None
+        if bdf is None:
+            import ctypes
+            rt = ctypes.CDLL('libcudart.so')
+            buf = ctypes.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device_index)) != 0:
+                return 'unbound (no PCI bus id)'
+            bdf = buf.value.decode()
+        if isinstance(bdf, int):
+            return 'unbound (PCI bus id unavailable)'
+        bdf = bdf.lower()
+        if len(bdf.split(':')[0]) == 8:           # cudart prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        node_path = '/sys/bus/pci/devices/%s/numa_node' % bdf
+        if not os.path.exists(node_path):
+            return 'unbound (%s missing)' % node_path
+        with open(node_path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return 'unbound (single NUMA node)'
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return 'GPU %s on NUMA node %d: bound to %d CPUs' % (bdf, node, len(cpus))
+    except Exception as e:                         # pragma: no cover - best effort
+        return 'unbound (%s)' % e
+
+
 def graph_cost(d):
     """Work estimate of one graph: nodes + directed edges."""
     return int(d.num_nodes) + int(d.num_edges)
