@@ -49,7 +49,7 @@ class StructureIO(C.Structure):
         ('cl1', VP), ('cmptr1', VP), ('cmem1', VP), ('kptr1', VP), ('batch2', VP), ('batch2_i64', VP),
         ('counts', VP), ('status', VP),
         ('gstat', VP), ('scratch_n', VP), ('scratch_e', VP), ('scratch_f', VP),
-        ('blob', VP),
+        ('blob', VP), ('wblob', VP),
     ]
 
 
@@ -136,6 +136,34 @@ class GinetStepArgs(C.Structure):
     ]
 
 
+class NetStepArgs(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32), ('B', C.c_int32), ('F', C.c_int32), ('h1', C.c_int32), ('h2', C.c_int32), ('Hd', C.c_int32),
+        ('out', C.c_int32),
+        ('max_n', C.c_int32), ('max_e', C.c_int32), ('max_k', C.c_int32), ('max_q', C.c_int32),
+        ('tiles', C.c_int32),
+        ('x', VP),
+        ('blob', VP), ('wblob', VP), ('gdesc', VP),
+        ('node_ptr', VP), ('edge_ptr', VP),
+        ('params', VP),
+        ('off_w1', C.c_int32), ('off_b1', C.c_int32), ('off_w2', C.c_int32), ('off_b2', C.c_int32),
+        ('off_fc1w', C.c_int32), ('off_fc1b', C.c_int32), ('off_fc2w', C.c_int32), ('off_fc2b', C.c_int32),
+        ('keep', VP), ('keep_scale', C.c_float), ('drop_p', C.c_float), ('seed', C.c_uint32),
+        ('y', VP), ('y_class', VP), ('class_w', VP),
+        ('task', C.c_int32), ('inv_norm', C.c_float), ('forward_only', C.c_int32), ('skip_reduce', C.c_int32),
+        ('pred', VP), ('loss', VP), ('R', VP),
+        ('partial', VP), ('partial_ld', C.c_int64),
+        ('grads', VP), ('n_params', C.c_int32),
+        ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+        ('flags', C.c_int32),
+        ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
+        ('status', VP),
+        ('comm', VP),
+        ('kptr0', VP), ('kptr1', VP),
+        ('Zin1', VP), ('Z1', VP), ('arg0', VP), ('Zin2', VP), ('Z2', VP), ('arg1', VP),
+    ]
+
+
 class FeedStep(C.Structure):
     _fields_ = [
         ('h_src', VP), ('d_dst', VP), ('nbytes', C.c_int64),
@@ -219,6 +247,13 @@ _SIGNATURES = {
     'drgnn_debug_blob_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_structure_blob_smem_bytes': (_i64, [_i32, _i32]),
     'drgnn_structure_blob': (C.c_int, [C.POINTER(StructureIO), VP]),
+    'drgnn_net_step_smem_bytes': (_i64, [_i32] * 11),
+    'drgnn_net_step_pick_tiles': (C.c_int, [_i32] * 10),
+    'drgnn_net_step_max_clusters': (C.c_int, [_i32, _i32, _i64]),
+    'drgnn_net_step': (C.c_int, [C.POINTER(NetStepArgs), VP]),
+    'drgnn_net_step_last_launches': (C.c_int, []),
+    'drgnn_net_step_last_tiles': (C.c_int, []),
+    'drgnn_debug_phase3_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_feed_run': (C.c_int, [C.POINTER(FeedStep), _i32, _i32, VP, VP, VP, VP, VP, VP, _i64, _i32]),
     'drgnn_debug_structure_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_head_smem_bytes': (_i64, [_i32, _i32, _i32]),

@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
   const int ne = io.ne;
   // per-graph structure blob (graph-local indices, one contiguous block; see drgnn.h)
   int32_t* bl = io.blob ? io.blob + DRGNN_BLOB_OFFSET(g, n0, e0) : nullptr;
+  // edge weights of the blob's lists (sGAT): a float array parallel to the blob
+  float* wb = (io.blob && io.wblob && io.edge_attr) ? io.wblob + DRGNN_BLOB_OFFSET(g, n0, e0) : nullptr;
   const BlobLayout BL = blob_layout(n, m);
   if (bl && t < DRGNN_BLOB_HEADER) bl[t] = 0;   // header[5] (complete) is set at the very end
 
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     io.eid0[e0 + p] = e0 + e;
     if (io.w0csr) io.w0csr[e0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
     if (bl) bl[BL.col0 + p] = ecol[e];
+    if (wb) wb[BL.col0 + p] = io.edge_attr[(int64_t)(e0 + e) * ne];
   }
   if (bl) {
 #pragma unroll 1
@@ -486,6 +489,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
             }
           }
           io.scratch_f[(int64_t)(e0 + base + sidx) * ne + f] = acc;
+          if (wb && f == 0) wb[BL.col1 + base + sidx] = acc;
         }
       }
     }
@@ -518,6 +522,7 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
     S.cscrow1[e0 + p] = prow[q];
     S.csceid1[e0 + p] = q;
     if (bl) bl[BL.cscr1 + p] = prow[q];
+    if (wb) wb[BL.cscr1 + p] = io.scratch_f[(int64_t)(e0 + q) * ne];   // written by this CTA before the barrier above
   }
   if (bl) {
 #pragma unroll 1
@@ -773,6 +778,9 @@ extern "C" int drgnn_structure_build(const drgnn_structure_io* io, void* stream)
     DRGNN_REQUIRE(io->scratch_f != nullptr, "structure_build: scratch_f is NULL");
   }
   if (io->w1csc) DRGNN_REQUIRE(io->edge_attr1 != nullptr, "structure_build: w1csc needs edge_attr1");
+  if (io->wblob && io->edge_attr)
+    DRGNN_REQUIRE(io->blob != nullptr && io->edge_attr1 != nullptr && io->scratch_f != nullptr,
+                  "structure_build: wblob needs blob, edge_attr1 and scratch_f");
   const int max_c1 = io->L1 > 0 ? io->max_n : 0;
   int64_t smem = drgnn_structure_smem_bytes(io->max_n, io->max_e, max_c1);
   if (smem < 0)

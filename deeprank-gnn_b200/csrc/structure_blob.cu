@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   const int c0 = io.c1_ptr[g];
   int c1len = io.c1_ptr[g + 1] - c0;
   int32_t* bl = io.blob + DRGNN_BLOB_OFFSET(g, n0, e0);
+  // edge weights of the lists (sGAT, sGAT.py:76): a float array parallel to the blob
+  float* wb = (io.wblob && io.edge_attr) ? io.wblob + DRGNN_BLOB_OFFSET(g, n0, e0) : nullptr;
   const BlobLayout BL = blob_layout(n, m);
   if (t < DRGNN_BLOB_HEADER) bl[t] = 0;
   if (t == 0) {   // the graph's extents for the step kernel (io.gstat doubles as its descriptor table)
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 4
     for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
     bl[BL.col0 + pos] = ecol[e];
+    if (wb) wb[BL.col0 + pos] = io.edge_attr[(int64_t)(e0 + e) * io.ne];
   }
 #pragma unroll 1
   for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
@@ -388,6 +391,69 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
       dst[q++] = wi * 32 + b;
     }
   }
+  if (wb) {
+    // ---- 8. summed attributes of the merged (coalesced) edges, community_pooling.py:204-205: a thread per
+    // (pooled row, bitmap word) walks its pooled edges; each sum runs over the members of the row's cluster
+    // (ascending) and their level-0 edges (ascending edge id) - the fixed order of graph_local_kernel, so both
+    // structure passes give bit-identical weights.  Everything but edge_attr itself is read from shared memory.
+    const int MWm = (m + 31) >> 5, KWn = (n + 31) >> 5;
+#pragma unroll 1
+    for (int item = t; item < K * KWk; item += T) {
+      const int r = item / KWk, wi = item - r * KWk;
+      const uint32_t* row = bm + r * KW1;
+      int q = cnt[n + r] - base1;
+#pragma unroll 1
+      for (int ww = 0; ww < wi; ++ww) q += __popc(row[ww]);
+      uint32_t bits = row[wi];
+      while (bits) {
+        const int tc = wi * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        float acc = 0.f;
+        const uint32_t* mrow = mem0 + r * KW1;
+#pragma unroll 1
+        for (int mw = 0; mw < KWn; ++mw) {
+          uint32_t mb = mrow[mw];
+          while (mb) {
+            const int i = mw * 32 + __ffs(mb) - 1;
+            mb &= mb - 1;
+            const uint32_t* erw = rowbits + i * MW1;
+#pragma unroll 1
+            for (int ew_ = 0; ew_ < MWm; ++ew_) {
+              uint32_t eb = erw[ew_];
+              while (eb) {
+                const int e = ew_ * 32 + __ffs(eb) - 1;
+                eb &= eb - 1;
+                if (dense0[ecol[e]] == tc) acc += io.edge_attr[(int64_t)(e0 + e) * io.ne];
+              }
+            }
+          }
+        }
+        wb[BL.col1 + q] = acc;
+        ++q;
+      }
+    }
+    __syncthreads();   // the pooled-CSR weights (global memory, this CTA's own writes) are visible to the CTA
+    // ---- 9. the same weights in pooled-CSC order: CSC slot (column c, row r) <- CSR slot of (r, c)
+#pragma unroll 1
+    for (int item = t; item < K * KWk; item += T) {
+      const int c = item / KWk, wi = item - c * KWk;
+      const uint32_t* rowT = bmT + c * KW1;
+      int qT = cnt[n + K + c] - baseT;
+#pragma unroll 1
+      for (int ww = 0; ww < wi; ++ww) qT += __popc(rowT[ww]);
+      uint32_t bits = rowT[wi];
+      while (bits) {
+        const int r = wi * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t* row = bm + r * KW1;
+        int slot = cnt[n + r] - base1 + __popc(row[c >> 5] & ((1u << (c & 31)) - 1u));
+#pragma unroll 1
+        for (int ww = 0; ww < (c >> 5); ++ww) slot += __popc(row[ww]);
+        wb[BL.cscr1 + qT] = wb[BL.col1 + slot];
+        ++qT;
+      }
+    }
+  }
   if (t == 0) {   // closing pointers and the header
     bl[BL.rp0 + n] = m;
     bl[BL.rp1 + K] = E1;
@@ -426,6 +492,7 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
   DRGNN_REQUIRE(io->node_ptr && io->edge_ptr && io->edge_index && io->cluster0 && io->c1_ptr && io->cluster1,
                 "structure_blob: NULL input (both cluster levels are required)");
   DRGNN_REQUIRE(io->blob && io->status && io->gstat, "structure_blob: NULL output");
+  DRGNN_REQUIRE(!io->wblob || !io->edge_attr || io->ne >= 1, "structure_blob: edge weights requested but ne == 0");
   const int64_t smem = drgnn_structure_blob_smem_bytes(io->max_n, io->max_e);
   if (smem < 0)
     return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges does not fit the bitmap kernel",

@@ -183,7 +183,7 @@ class Workspace(object):
         # per-graph weight-gradient partials of the fused per-graph backward (GINet)
         self.partial = z(B, s.C1 * s.F + s.nb * s.h2 * s.h1) if s.kind == 'ginet' else None
         # per-graph rows shaped like the flat gradient buffer (+ the loss slot) for the whole-step kernel
-        self.partial_full = z(B, n_params + 4) if s.kind == 'ginet' else None
+        self.partial_full = z(B, n_params + 4)
 
 
 class DeviceBatch(object):
@@ -314,6 +314,11 @@ class Engine(object):
         self.blob_structure = os.environ.get('DRGNN_BLOB_STRUCTURE', '1') != '0'   # one-launch bitmap structure pass
         self.keep_intermediates = False   # cluster kernel: also mirror AX / Z1 / argmax ... to global memory (tests)
         self.fuse_reduce = os.environ.get('DRGNN_FUSE_REDUCE', '1') != '0'   # gradient reduction + Adam behind a grid barrier
+        # general cluster whole-step kernel (csrc/fused_step3.cuh): sGAT / FoutNet, and GINet graphs too large for
+        # the CTA-pair kernel (node dimension tiled over the cluster, neighbours through distributed shared memory)
+        self.step3 = os.environ.get('DRGNN_STEP3', '1') != '0'
+        self.step3_tiles = int(os.environ.get('DRGNN_STEP3_TILES', '0'))      # 0: smallest tile count that fits
+        self._last_path = None
         self.seed = 0x5EED if seed is None else int(seed)
         if self.world > 1:
             # per-rank dropout stream: the in-kernel mask hashes (seed, step, LOCAL graph, unit), so
@@ -348,6 +353,8 @@ class Engine(object):
 
     def step_kernel_name(self):
         """Name of the kernel that carries the step of the last batch (bench.py's roofline entry)."""
+        if self._last_path == 'step3':
+            return 'net_graph_step3_kernel'
         if self.spec.kind == 'ginet' and self._all_done_kernel:
             return {1: 'ginet_graph_step_kernel', 2: 'ginet_graph_step2_kernel'}.get(ops.ginet_step_last_variant(),
                                                                                       'ginet_graph_step_kernel')
@@ -463,9 +470,9 @@ class Engine(object):
             raise DrgnnError('sGAT supports one edge feature (the reference broadcast needs ne in {1, Fout})')
         slot = self.structs[d.sslot]
         if self._blob_only(d):
-            # fused GINet path: ONE launch writes the per-graph structure blobs, nothing else
+            # fused whole-step paths: ONE launch writes the per-graph structure blobs (+ edge weights for sGAT)
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
-                                    d.cluster1, out=slot, L1=d.L1)
+                                    d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None)
             assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
@@ -492,11 +499,42 @@ class Engine(object):
             self._fused_fit[key] = mc
         return d.B <= mc
 
+    def _step3_tiles(self, d):
+        """Node tiles of the general cluster step kernel for batch ``d`` (0: that kernel does not apply).
+        GINet prefers the tuned CTA-pair kernel whenever a graph fits it."""
+        s = self.spec
+        if not (self.step3 and self.fused_head and self.fused_graph and d.max_k0 and d.max_k1 and d.cluster1 is not None
+                and d.c1_ptr is not None and d.x.size(1) == s.F and s.F % 4 == 0 and self.step_variant == 0):
+            return 0
+        if s.kind == 'sgat' and (d.edge_attr is None or d.edge_attr.size(1) != 1):
+            return 0
+        key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'step3', self.step3_tiles)
+        tiles = self._fused_fit.get(key)
+        if tiles is None:
+            if s.kind == 'ginet' and ops.ginet_step2_smem_bytes(s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e,
+                                                                 s.Hd, s.out) >= 0 and not self.step3_tiles:
+                tiles = 0
+            elif self.step3_tiles:
+                ok = ops.net_step_smem_bytes(s.kind, self.step3_tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1,
+                                             d.max_e, s.Hd, s.out) >= 0
+                tiles = self.step3_tiles if ok else 0
+            else:
+                tiles = ops.net_step_pick_tiles(s.kind, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+            self._fused_fit[key] = tiles
+        return tiles
+
     def _blob_only(self, d):
-        """True when the step of batch ``d`` runs the cluster whole-step kernel, which stages the
+        """True when the step of batch ``d`` runs a cluster whole-step kernel, which stages the
         per-graph structure blobs and needs none of the global structure arrays: the structure pass
         is then the one-launch bitmap kernel (``ops.structure_blob``)."""
         s = self.spec
+        if self._step3_tiles(d):
+            key = (d.max_n, d.max_e, 'blobfit')
+            fit = self._fused_fit.get(key)
+            if fit is None:
+                fit = ops.structure_blob_fits(d.max_n, d.max_e)
+                self._fused_fit[key] = fit
+            return bool(fit and self.blob_structure and not self.keep_intermediates)
         if not (self.blob_structure and self.fused_head and self.step_variant != 1 and not self.keep_intermediates
                 and s.nb == 2 and d.cluster1 is not None and d.c1_ptr is not None and self._use_fused_graph(d)):
             return False
@@ -544,6 +582,10 @@ class Engine(object):
         pv = lambda name: P.view(P.data, name)
         flat = lambda name, n: P.data[P.offset(name):P.offset(name) + n]
         self._graph_done = self._all_done = self._adam_done = False
+        tiles3 = self._step3_tiles(d)
+        if tiles3:
+            return self._forward_step3(d, st, tiles3, keep_mask, loss_inv)
+        self._last_path = 'ops'
         if self._use_fused_graph(d):
             # ONE launch: conv1 -> pool -> conv2 -> pool -> read-out, one CTA per graph (csrc/fused.cu)
             self._fa = ops.ginet_fused_args(st, d.x, flat('conv1.fc.weight', s.C1 * s.F),
@@ -639,6 +681,69 @@ class Engine(object):
         ops.maxpool_fwd(ws.Z2[:L1], st.cmptr1, st.cmem1, ws.P2[:L1], ws.arg1[:L1], n_clusters_dev=K1d)
         ops.segment_mean_fwd(ws.P2[:L1], st.kptr1[:B + 1], ws.R[:B])
         return self._heads(d, keep_mask, loss_inv)
+
+    def _forward_step3(self, d, st, tiles, keep_mask, loss_inv):
+        """The whole step of every graph in ONE launch of the general cluster kernel (``ops.net_step``)."""
+        s, ws, P, B = self.spec, self.ws, self.params, d.B
+        drop = self.training and s.dropout > 0
+        if drop and keep_mask is not None:
+            ws.keep[:B].copy_(keep_mask.to(self.device, F32))
+        hashed = drop and keep_mask is None
+        train_step = loss_inv is not None
+        fuse_adam = train_step and self.world == 1 and self.fuse_adam and self._want_adam
+        use_comm = train_step and self.comm is not None and self._want_adam
+        task = ops.TASK_NONE
+        if train_step:
+            task = ops.TASK_CE if self.task == 'class' else (ops.TASK_MSE_SIGMOID if self.transform_sigmoid else ops.TASK_MSE)
+            if self.task == 'class' and d.y_class is None:
+                raise DrgnnError('classification needs class-index targets (pass `classes` when building the batch)')
+            if self.task == 'reg' and d.y is None:
+                raise DrgnnError('the batch has no target')
+        if s.kind == 'ginet':
+            offs = dict(w1=P.offset('conv1.fc.weight'), w2=P.offset('conv2.fc.weight'))
+        elif s.kind == 'sgat':
+            offs = dict(w1=P.offset('conv1.weight'), b1=P.offset('conv1.bias'), w2=P.offset('conv2.weight'),
+                        b2=P.offset('conv2.bias'))
+        else:
+            offs = dict(w1=P.offset('conv1.Wc'), b1=P.offset('conv1.bias'), w2=P.offset('conv2.Wc'), b2=P.offset('conv2.bias'))
+        offs.update(fc1w=P.offset('fc1.weight'), fc1b=P.offset('fc1.bias'), fc2w=P.offset('fc2.weight'),
+                    fc2b=P.offset('fc2.bias'))
+        in_kernel = False
+        if use_comm and not self._no_exchange and self.fuse_comm and self.fuse_reduce and self._cur_B_global is not None \
+                and d.B * self.world == self._cur_B_global:
+            key = (d.max_n, d.max_e, d.max_k0, d.max_k1, tiles, 'clusters3')
+            mc = self._fused_fit.get(key)
+            if mc is None:
+                smem = ops.net_step_smem_bytes(s.kind, tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+                mc = ops.net_step_max_clusters(s.kind, tiles, smem) if smem >= 0 else 0
+                self._fused_fit[key] = mc
+            in_kernel = d.B <= mc and tiles * s.nb * d.B <= int(self.comm.struct.max_blocks)
+        mirror = None
+        if self.keep_intermediates:
+            mirror = dict(Zin1=ws.Zin1, Z1=ws.Z1, arg0=ws.arg0, Zin2=ws.Zin2, Z2=ws.Z2, arg1=ws.arg1)
+        ops.net_step(s.kind, st, d.x, P.data, offs, B, s.F, s.h1, s.h2, s.Hd, s.out, d.max_n, d.max_e, d.max_k0, d.max_k1,
+                     ws.pred[:B], d.node_ptr, d.edge_ptr, tiles=tiles, task=task,
+                     inv_norm=loss_inv if train_step else 1.0, y=d.y if self.task == 'reg' else None,
+                     y_class=d.y_class if self.task == 'class' else None, class_w=self.class_weights,
+                     keep=ws.keep[:B] if (drop and not hashed) else None,
+                     keep_scale=1.0 / (1.0 - s.dropout) if drop else 1.0, drop_p=s.dropout if hashed else 0.0,
+                     seed=self.seed, loss=ws.loss, R=ws.R[:B], partial=ws.partial_full, grads=self.grads,
+                     n_params=P.numel, forward_only=not train_step, step_dev=self.step_dev,
+                     adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
+                               beta2=self.betas[1], eps=self.eps) if (fuse_adam or in_kernel) else None,
+                     skip_reduce=use_comm and not in_kernel, fuse_reduce=self.fuse_reduce,
+                     comm=self.comm if in_kernel else None, mirror=mirror)
+        self._last_path = 'step3'
+        self._graph_done = self._head_done = self._all_done = train_step
+        self._all_done_kernel = True
+        self._adam_done = fuse_adam
+        if use_comm and not self._no_exchange:
+            self._last_exchange = 'in-kernel' if in_kernel else 'launch'
+        if in_kernel:
+            self._reduced = self._adam_done = True
+        elif use_comm:
+            self._peer_exchange(partial=ws.partial_full, B=B)
+        return ws.pred[:B]
 
     def _heads(self, d, keep_mask, loss_inv):
         s, ws, P, B = self.spec, self.ws, self.params, d.B

@@ -8,8 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, GinetStepArgs, HeadArgs, LinearArgs, LinearWgradArgs, StructureIO, call, ptr,
-                   require_cuda, stream_ptr)
+from ._lib import (AggregateArgs, DrgnnError, GinetFusedArgs, GinetStepArgs, HeadArgs, LinearArgs, LinearWgradArgs, NetStepArgs,
+                   StructureIO, call, ptr, require_cuda, stream_ptr)
 
 I16, I32, I64, F32 = torch.int16, torch.int32, torch.int64, torch.float32
 
@@ -41,7 +41,7 @@ def _i32(t, name):
 _INT_FIELDS = ('rowptr0', 'col0', 'eid0', 'cscptr0', 'cscrow0', 'csceid0', 'cl0', 'cmptr0', 'cmem0', 'kptr0',
                'batch1', 'rowptr1', 'col1', 'cscptr1', 'cscrow1', 'csceid1', 'cl1', 'cmptr1', 'cmem1', 'kptr1',
                'batch2', 'counts', 'status', 'gstat', 'scratch_n', 'scratch_e', 'blob')
-_FLOAT_FIELDS = ('w0csr', 'w0csc', 'edge_attr1', 'w1csc', 'scratch_f')
+_FLOAT_FIELDS = ('w0csr', 'w0csc', 'edge_attr1', 'w1csc', 'scratch_f', 'wblob')
 _I64_FIELDS = ('cl0_i64', 'batch1_i64', 'edge_index1', 'batch2_i64')
 
 
@@ -53,7 +53,8 @@ def _structure_sizes(B, N, E, L1, ne):
                 scratch_n=5 * (N + B + 1) + 8, scratch_e=4 * E + 8,
                 blob=48 * B + 12 * N + 4 * E + 16)        # DRGNN_BLOB_WORDS: per-graph structure blobs
     floats = dict(w0csr=E if ne else 0, w0csc=E if ne else 0, edge_attr1=E * ne, w1csc=E if ne else 0,
-                  scratch_f=E * max(ne, 1) if ne else 0)
+                  scratch_f=E * max(ne, 1) if ne else 0,
+                  wblob=(48 * B + 12 * N + 4 * E + 16) if ne else 0)   # edge weights parallel to the blob (sGAT)
     i64 = dict(cl0_i64=N, batch1_i64=N, edge_index1=2 * E, batch2_i64=L1)
     return ints, floats, i64
 
@@ -228,7 +229,8 @@ def structure_blob_fits(max_n, max_e):
     return int(_lib.load().drgnn_structure_blob_smem_bytes(int(max_n), int(max_e))) >= 0
 
 
-def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None):
+def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None,
+                   edge_attr=None):
     """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
     structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
     global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
@@ -252,24 +254,35 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
         raise DrgnnError('edge_index / cluster tensors must be contiguous')
     if L1 > N:
         raise DrgnnError('len(cluster1)=%d exceeds the number of nodes %d' % (L1, N))
+    ne = 0
+    if edge_attr is not None:       # sGAT: the pass also writes the edge weights of the blob's lists (Structure.wblob)
+        require_cuda(edge_attr)
+        _f32(edge_attr, 'edge_attr')
+        if edge_attr.dim() == 1:
+            edge_attr = edge_attr.unsqueeze(-1)
+        if not edge_attr.is_contiguous():
+            edge_attr = edge_attr.contiguous()
+        ne = edge_attr.size(1)
+        if edge_attr.size(0) != E:
+            raise DrgnnError('edge_attr has %d rows for %d edges' % (edge_attr.size(0), E))
     s = out
-    if s is None or not s.fits(B, N, E, L1, s.ne if s is not None else 0, s.mirrors if s is not None else False):
-        s = Structure(B, N, E, L1, 0, cluster0.device, False)
+    if s is None or not s.fits(B, N, E, L1, ne if ne else s.ne, s.mirrors):
+        s = Structure(B, N, E, L1, ne, cluster0.device, False)
     s.B, s.N, s.E, s.L1 = B, N, E, L1
     s._shape_views()
     s._counts_host = None
     s.blob_only = True
-    s._keep = (node_ptr, edge_ptr, c1_ptr, edge_index, None, cluster0, cluster1)
+    s._keep = (node_ptr, edge_ptr, c1_ptr, edge_index, edge_attr, cluster0, cluster1)
     s.node_ptr, s.edge_ptr, s.c1_ptr = node_ptr, edge_ptr, c1_ptr
     s.max_n, s.max_e = int(max_n), int(max_e)
     io = s.io
-    io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, 0
+    io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, ne
     io.max_n, io.max_e = int(max_n), int(max_e)
     io.clusters_are_local = 1
     io.idx32 = 1 if cluster0.dtype == I32 else 0
     io.edge16 = 1 if edge16 else 0
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
-    io.edge_index, io.edge_attr = ptr(edge_index), None
+    io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
     if B:
         call('drgnn_structure_blob', C.byref(io), stream_ptr())
@@ -558,6 +571,86 @@ def ginet_step2_max_clusters(smem_bytes):
 
 def ginet_step2_smem_bytes(F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
     return int(_lib.load().drgnn_ginet_step2_smem_bytes(*[int(v) for v in (F, h1, h2, max_n, max_k, max_q, max_e, Hd, out)]))
+
+
+NET_KINDS = {'ginet': 0, 'sgat': 1, 'fout': 2}
+
+
+def net_step_pick_tiles(kind, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
+    """Smallest number of node tiles (CTAs sharing one graph) for which the general cluster step kernel fits
+    shared memory; 0 when the graph fits no cluster of 8 CTAs."""
+    v = int(_lib.load().drgnn_net_step_pick_tiles(*[int(x) for x in (NET_KINDS[kind], F, h1, h2, max_n, max_k, max_q, max_e,
+                                                                       Hd, out)]))
+    return v if v > 0 else 0
+
+
+def net_step_smem_bytes(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
+    return int(_lib.load().drgnn_net_step_smem_bytes(*[int(x) for x in (NET_KINDS[kind], tiles, F, h1, h2, max_n, max_k,
+                                                                         max_q, max_e, Hd, out)]))
+
+
+def net_step_max_clusters(kind, tiles, smem_bytes):
+    """Clusters of the general step kernel the device holds at once (needs a device)."""
+    return int(_lib.load().drgnn_net_step_max_clusters(NET_KINDS[kind], int(tiles), int(smem_bytes)))
+
+
+def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, max_k, max_q, pred, node_ptr, edge_ptr,
+             tiles=0, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None, keep_scale=1.0, drop_p=0.0,
+             seed=0, loss=None, R=None, partial=None, grads=None, n_params=0, forward_only=False, step_dev=None, adam=None,
+             skip_reduce=False, fuse_reduce=True, comm=None, mirror=None):
+    """Whole step of every graph in one launch for GINet / sGAT / FoutNet (``drgnn_net_step``, the general
+    cluster kernel).  ``st``: the ``Structure`` of the batch (blob, + wblob for sGAT); ``offsets``: dict of the
+    tensor offsets inside the flat parameter buffer (w1, b1, w2, b2, fc1w, fc1b, fc2w, fc2b; b1 / b2 None for
+    GINet); ``mirror``: dict(Zin1, Z1, arg0, Zin2, Z2, arg1) of global buffers that receive the intermediates
+    (tests; needs a full structure pass for kptr0 / kptr1)."""
+    require_cuda(x, params, pred, y, y_class, class_w, keep, loss, R, partial, grads, step_dev, node_ptr, edge_ptr)
+    s = NetStepArgs()
+    s.kind = NET_KINDS[kind]
+    s.B, s.F, s.h1, s.h2, s.Hd, s.out = int(B), int(F), int(h1), int(h2), int(Hd), int(out)
+    s.max_n, s.max_e, s.max_k, s.max_q = int(max_n), int(max_e), int(max_k), int(max_q)
+    s.tiles = int(tiles)
+    s.x = ptr(_f32(x, 'x'))
+    s.blob = ptr(st.blob)
+    s.wblob = ptr(st.wblob) if kind == 'sgat' else None
+    s.gdesc = ptr(st.gstat) if st.blob_only else None
+    s.node_ptr, s.edge_ptr = ptr(_i32(node_ptr, 'node_ptr')), ptr(_i32(edge_ptr, 'edge_ptr'))
+    s.params = ptr(_f32(params, 'params'))
+    o = offsets
+    s.off_w1, s.off_w2 = int(o['w1']), int(o['w2'])
+    s.off_b1 = -1 if o.get('b1') is None else int(o['b1'])
+    s.off_b2 = -1 if o.get('b2') is None else int(o['b2'])
+    s.off_fc1w, s.off_fc1b, s.off_fc2w, s.off_fc2b = int(o['fc1w']), int(o['fc1b']), int(o['fc2w']), int(o['fc2b'])
+    s.keep, s.keep_scale = ptr(_f32(keep, 'keep')), float(keep_scale)
+    s.drop_p, s.seed = float(drop_p), int(seed) & 0xffffffff
+    s.y, s.y_class, s.class_w = ptr(y), ptr(y_class), ptr(class_w)
+    s.task, s.inv_norm = int(task), float(inv_norm)
+    s.forward_only, s.skip_reduce = 1 if forward_only else 0, 1 if skip_reduce else 0
+    s.pred, s.loss, s.R = ptr(pred), ptr(loss), ptr(R)
+    s.partial, s.partial_ld = ptr(partial), (partial.stride(0) if partial is not None else 0)
+    s.grads, s.n_params = ptr(grads), int(n_params)
+    if adam is not None:
+        require_cuda(adam['p'], adam['m'], adam['v'])
+        s.fuse_adam = 1
+        s.adam_p, s.adam_m, s.adam_v = ptr(adam['p']), ptr(adam['m']), ptr(adam['v'])
+        s.lr, s.beta1, s.beta2, s.eps = float(adam['lr']), float(adam['beta1']), float(adam['beta2']), float(adam['eps'])
+    s.step_dev = ptr(step_dev)
+    s.status = ptr(st.status)
+    s.comm = C.addressof(comm.struct) if comm is not None else None
+    s.flags = (0 if fuse_reduce else 2)
+    if mirror is not None:
+        require_cuda(*mirror.values())
+        s.flags |= 1
+        s.kptr0, s.kptr1 = ptr(st.kptr0), ptr(st.kptr1)
+        s.Zin1, s.Z1, s.arg0 = ptr(mirror['Zin1']), ptr(mirror['Z1']), ptr(mirror['arg0'])
+        s.Zin2, s.Z2, s.arg1 = ptr(mirror['Zin2']), ptr(mirror['Z2']), ptr(mirror['arg1'])
+    call('drgnn_net_step', C.byref(s), stream_ptr())
+    _lib.kernel_count += int(_lib.load().drgnn_net_step_last_launches()) - 1
+
+
+def net_step_last():
+    """(kernels launched, node tiles) of the last ``net_step`` of this thread."""
+    lib = _lib.load()
+    return int(lib.drgnn_net_step_last_launches()), int(lib.drgnn_net_step_last_tiles())
 
 
 def peer_reduce_adam(comm, grads, n_params, n_sum, partial=None, B=0, adam=None, step_dev=None):

@@ -141,6 +141,12 @@ typedef struct drgnn_structure_io {
    *   cmptr1[n+1] cmem1[n] cl1[n] | cscptr1[n+1] cscrow1[m]      (capacity by n / m; K0+1, E1, ...
    *   entries are valid).  Size of the buffer: DRGNN_BLOB_WORDS(B, N, E) int32. */
   int32_t* blob;
+  /* Edge weights of the blob's neighbour lists (optional, NULL to skip; needs edge_attr, uses column 0):
+   * a float array PARALLEL to blob (same size, same per-graph offsets) that holds, at the word offsets of
+   * col0 / col1 / cscrow1 inside graph g's block, edge_attr of the level-0 CSR slot, the summed attribute of
+   * the pooled edge (coalesce, community_pooling.py:204-205) in pooled-CSR order and in pooled-CSC order.
+   * What the fused sGAT step (drgnn_net_step, kind 1) stages next to the index lists (sGAT.py:76). */
+  float* wblob;
 } drgnn_structure_io;
 
 /* Dynamic shared memory the per-graph kernel needs for (max_n, max_e); <0 if a graph is
@@ -433,6 +439,74 @@ int drgnn_debug_blob_cycles(uint64_t* out16);
 /* same for the structure pass (graph_local_kernel): [0] start, [1] edge list, [2] CSR, [3] CSC,
  * [4] relabel, [5] members, [6] coarsened edges, [7] coarsened CSC, [8] level-1 clustering (end) */
 int drgnn_debug_structure_cycles(uint64_t* out32);
+
+/* ------------------------------------------------------------------------------------
+ * 8b. Whole training / scoring step of every graph of a mini-batch in ONE launch, for the three reference
+ *     networks and for graphs of any size a thread-block cluster holds (csrc/fused_step3.cuh):
+ *       kind 0  GINet    ginet.py:99-141     two branches on two CTA groups of the cluster
+ *       kind 1  sGAT     sGAT.py:62-93, 114-138
+ *       kind 2  FoutNet  foutnet.py:56-82, 103-125  (a node without neighbour gives a NaN row, foutnet.py:73)
+ *     conv1 -> ReLU -> cluster max (community_pooling) -> conv2 on the coarsened graph -> ReLU -> level-1
+ *     cluster max (max_pool_x) -> per-graph mean -> fc1 / ReLU / [dropout] / fc2 -> loss -> the autograd
+ *     backward of all of it -> per-graph gradient rows -> (grid co-resident) ordered sum + Adam (+ the peer
+ *     exchange of drgnn_peer_reduce_adam) behind a grid barrier, else a second launch.
+ *     `tiles` CTAs share the nodes of one graph (rows of every level split evenly, neighbours / cluster members
+ *     of other tiles read through distributed shared memory); cluster size = tiles * (kind == 0 ? 2 : 1) <= 8.
+ *     Inputs: the per-graph structure blobs of the structure pass (drgnn_structure_io.blob, + wblob for kind 1),
+ *     node_ptr / edge_ptr [B+1] (or gdesc = io->gstat of drgnn_structure_blob), x [N,F], the FLAT parameter
+ *     buffer `params` with the offsets (in floats) of the tensors inside it:
+ *       kind 0: off_w1 -> conv1.fc.weight | conv1_ext.fc.weight ([2][h1][F]), off_w2 -> [2][h2][h1], no biases
+ *       kind 1: off_w1 -> conv1.weight [2F][h1], off_b1, off_w2 -> conv2.weight [2h1][h2], off_b2
+ *       kind 2: off_w1 -> conv1.Wc | conv1.Wn ([2F][h1]), off_b1, off_w2 -> conv2.Wc | conv2.Wn, off_b2
+ *       all  : off_fc1w [Hd][nbr*h2], off_fc1b, off_fc2w [out][Hd], off_fc2b
+ *     partial [B, partial_ld] rows and grads [n_params] use the same offsets; slot n_params of a row holds the
+ *     graph's loss term; rows must be ZERO in slots no live parameter owns.  task / inv_norm / keep / drop_p /
+ *     fuse_adam / skip_reduce / comm / step_dev as in drgnn_ginet_step_args.  flags bit 0: mirror the
+ *     intermediates to Zin1 [N,Kin1] Z1 [N,nbr*h1] arg0 Zin2 Z2 arg1 (needs kptr0 / kptr1 of
+ *     drgnn_structure_build); bit 1: never fuse the gradient reduction.  R (optional): read-out rows [B, nbr*h2].
+ * ---------------------------------------------------------------------------------- */
+typedef struct drgnn_net_step_args {
+  int32_t kind; int32_t B; int32_t F; int32_t h1; int32_t h2; int32_t Hd; int32_t out;
+  int32_t max_n; int32_t max_e; int32_t max_k; int32_t max_q;
+  int32_t tiles;                       /* 0: the smallest count whose shared memory fits */
+  const float* x;
+  const int32_t* blob; const float* wblob; const int32_t* gdesc;
+  const int32_t* node_ptr; const int32_t* edge_ptr;
+  const float* params;
+  int32_t off_w1; int32_t off_b1; int32_t off_w2; int32_t off_b2;
+  int32_t off_fc1w; int32_t off_fc1b; int32_t off_fc2w; int32_t off_fc2b;
+  const float* keep; float keep_scale; float drop_p; uint32_t seed;
+  const float* y; const int64_t* y_class; const float* class_w;
+  int32_t task; float inv_norm; int32_t forward_only; int32_t skip_reduce;
+  float* pred; float* loss; float* R;
+  float* partial; int64_t partial_ld;
+  float* grads; int32_t n_params;
+  int32_t fuse_adam; float lr; float beta1; float beta2; float eps; int32_t flags;
+  float* adam_p; float* adam_m; float* adam_v; float* step_dev;
+  int32_t* status;
+  const struct drgnn_peer_comm* comm;
+  /* test mirrors (flags bit 0) */
+  const int32_t* kptr0; const int32_t* kptr1;
+  float* Zin1; float* Z1; int32_t* arg0; float* Zin2; float* Z2; int32_t* arg1;
+} drgnn_net_step_args;
+/* shared memory of one CTA (<0: unsupported shape / does not fit) */
+int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
+                                  int32_t max_q, int32_t max_e, int32_t Hd, int32_t out);
+/* smallest tile count (1, 2, 4, 8; cluster <= 8 CTAs) whose plan fits shared memory; <0: none */
+int drgnn_net_step_pick_tiles(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
+                              int32_t max_e, int32_t Hd, int32_t out);
+/* clusters of the step kernel the device holds at once for this plan (<0: error); the gradient reduction
+ * (+ Adam, + peer exchange) runs inside the launch when B <= this */
+int drgnn_net_step_max_clusters(int32_t kind, int32_t tiles, int64_t smem_bytes);
+int drgnn_net_step(const drgnn_net_step_args* s, void* stream);
+/* kernels the last drgnn_net_step of this thread launched (1: reduction fused / scoring, 2: + reduction launch)
+ * and the tile count it used */
+int drgnn_net_step_last_launches(void);
+int drgnn_net_step_last_tiles(void);
+/* diagnostic: clock64 at the phase boundaries of the CTA that ran block 0 of the last launch: [0] start, [1] staged,
+ * [2] zin1, [3] Z1, [4] P1, [5] zin2, [6] Z2, [7] P2, [8] read-out, [9] head, [10] head backward, [11] dZ2,
+ * [12] dW2 / dzin2, [13] dP1, [14] dZ1, [15] dW1, [16] reduction.  Synchronises the device. */
+int drgnn_debug_phase3_cycles(uint64_t* out32);
 
 /* ---- multi-GPU: gradient exchange over NVLink peer memory fused with the optimiser ----
  * Replaces, on every rank, the sequence  [reduce per-graph rows] -> torch.distributed.all_reduce(flat

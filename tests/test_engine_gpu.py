@@ -330,11 +330,19 @@ def test_cluster_step_kernel_falls_back_when_a_graph_does_not_fit(lib):
     d = _device_batch(graphs)
     assert ops.ginet_step2_smem_bytes(32, 16, 32, d.max_n, d.max_k0, d.max_k1, d.max_e, 128, 1) < 0
     e = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1)
+    e.step3 = False                       # without the general cluster kernel: the single-CTA whole-step kernel
     e.step(d)
-    assert ops.ginet_step_last_variant() == 1
+    assert ops.ginet_step_last_variant() == 1 and e._last_path == 'ops'
     e.step_variant = 2
     with pytest.raises(DrgnnError):
         e.step(d)
+    e2 = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1)
+    e2.load_state_dict(e.state_dict())
+    e.step_variant = 1
+    l1, p1 = e.step(d)
+    l2, p2 = e2.step(d)                   # default: node-tiled cluster kernel (2 tiles x 2 branches per graph)
+    assert e2._last_path == 'step3' and ops.net_step_last()[1] >= 2
+    torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-5)
 
 
 def test_cluster_step_kernel_in_kernel_reduction_equals_reduction_launch(lib):
