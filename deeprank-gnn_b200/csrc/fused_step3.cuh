@@ -106,8 +106,8 @@ struct Step3Plan {
   int fused_reduce;
 };
 
-__host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int F, int h1, int h2, int max_n, int max_k, int max_q,
-                                                int max_e, int Hd, int out) {
+__host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, int F, int h1, int h2, int max_n, int max_k,
+                                                int max_q, int max_e, int Hd, int out) {
   Step3Plan p;
   p.tiles = tiles;
   p.nbr = kind == 0 ? 2 : 1;
@@ -126,10 +126,10 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int F, int 
   const int mn1 = kind == 0 ? h1 * F : (p.Kin1 + 4) * h1;
   const int mn2 = kind == 0 ? h2 * h1 : (p.Kin2 + 4) * h2;
   p.wg_words = s3_up4(mn1 > mn2 ? mn1 : mn2);
-  p.xs_words = tiles == 1 ? s3_up4(max_n * F) : 0;
+  p.xs_words = stage ? s3_up4(max_n * F) : 0;
   int scr = 4 * p.wg_words;                       // at least four K splits
   if (scr < 4 * 128) scr = 4 * 128;               // partial sums of the in-kernel gradient reduction
-  if (scr < p.xs_words) scr = p.xs_words;         // NT = 1: the feature tile is dead after the first aggregation
+  if (scr < p.xs_words) scr = p.xs_words;         // staged: the feature tile is dead after the first aggregation
   p.scr_words = scr;
   p.scr = take(scr);
   p.xs = p.scr;
@@ -159,7 +159,7 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int F, int 
   p.post1 = take(p.kt);
   p.arg0 = take(p.kt * h1);
   p.arg1 = take(p.qt * h2);
-  p.blob_words = tiles == 1 ? DRGNN_BLOB_USED(max_n, max_e) : 0;
+  p.blob_words = stage ? DRGNN_BLOB_USED(max_n, max_e) : 0;
   p.blob = take(p.blob_words);
   p.wblob = take(kind == 1 ? p.blob_words : 0);
   p.bases = take(2 * 7 * S3_MAX_TILES);           // seven distributed arrays x 8 tiles of 8-byte generic pointers
@@ -173,16 +173,47 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int F, int 
 // A row-distributed array: tile t holds rows [t*rpt, (t+1)*rpt) at base[t] (a generic pointer into that CTA's
 // shared memory, own or remote).  Level-0 features with NT > 1 are one global array: rpt = INT_MAX, base[0].
 struct S3Rows {
-  const void* const* base;   // in shared memory
+  const void* const* base;   // [tiles] in shared memory (used when magic != 0)
+  const void* b0;            // the only tile when the array is not distributed (magic == 0): no lookup, no division
+  unsigned magic;            // ceil(2^32 / rpt): owner(i) = umulhi(i, magic), exact for i, rpt < 2^16
   int rpt;
   int ld;
-  __device__ __forceinline__ const float* frow(int i) const {
-    const int o = i / rpt;
-    return reinterpret_cast<const float*>(base[o]) + (i - o * rpt) * ld;
+  __device__ __forceinline__ const void* row(int i) const {
+    if (magic == 0u) return reinterpret_cast<const char*>(b0) + (size_t)(i * ld) * 4u;
+    const int o = (int)__umulhi((unsigned)i, magic);
+    return reinterpret_cast<const char*>(base[o]) + (size_t)((i - o * rpt) * ld) * 4u;
   }
-  __device__ __forceinline__ const int* irow(int i) const {
-    const int o = i / rpt;
-    return reinterpret_cast<const int*>(base[o]) + (i - o * rpt) * ld;
+  __device__ __forceinline__ const float* frow(int i) const { return reinterpret_cast<const float*>(row(i)); }
+  __device__ __forceinline__ const int* irow(int i) const { return reinterpret_cast<const int*>(row(i)); }
+};
+// rows of a cluster-distributed array (tile t at base[t], rpt rows each); one tile: direct addressing
+__device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, int rpt, int ld) {
+  S3Rows r;
+  r.base = base;
+  r.b0 = base[0];
+  r.rpt = rpt;
+  r.ld = ld;
+  r.magic = tiles > 1 ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
+  return r;
+}
+__device__ __forceinline__ S3Rows s3_rows_flat(const void* b0, int ld) {
+  S3Rows r;
+  r.base = nullptr;
+  r.b0 = b0;
+  r.rpt = 0;
+  r.ld = ld;
+  r.magic = 0u;
+  return r;
+}
+// item -> (item / w, item % w) with a shift when w is a power of two (the usual widths: 4, 8, 16)
+struct S3Div {
+  int w, sh;
+  __device__ __forceinline__ explicit S3Div(int w_) : w(w_), sh(-1) {
+    if ((w_ & (w_ - 1)) == 0) sh = __ffs(w_) - 1;
+  }
+  __device__ __forceinline__ void split(int item, int& q, int& r) const {
+    if (sh >= 0) { q = item >> sh; r = item & (w - 1); }
+    else { q = item / w; r = item - q * w; }
   }
 };
 
@@ -195,9 +226,11 @@ __device__ __noinline__ void s3_aggregate(int kind, const int* __restrict__ rp, 
                                           float* __restrict__ post_out, int tid, int nth) {
   const int W4 = C >> 2;
   const int rows = hi - lo;
+  const S3Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int il = item / W4, q4 = item - il * W4;
+    int il, q4;
+    dv.split(item, il, q4);
     const int i = lo + il;
     const int sb = rp[i], se = rp[i + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -293,9 +326,11 @@ __device__ __noinline__ void s3_cluster_max(const int* __restrict__ cmp, const i
                                             float* __restrict__ dst, int ldd, int* __restrict__ arg, int ldarg, int W4,
                                             int tid, int nth) {
   const int rows = hi - lo;
+  const S3Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int kl = item / W4, q4 = item - kl * W4;
+    int kl, q4;
+    dv.split(item, kl, q4);
     const int k = lo + kl;
     const int sb = cmp[k], se = cmp[k + 1];
     float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
@@ -324,9 +359,11 @@ __device__ __noinline__ void s3_cluster_max(const int* __restrict__ cmp, const i
 __device__ __noinline__ void s3_route(const int* __restrict__ cl, S3Rows arg, S3Rows d, const float* __restrict__ drow, float scale,
                                       float* __restrict__ z, int ldz, int lo, int hi, int W4, int tid, int nth) {
   const int rows = hi - lo;
+  const S3Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int il = item / W4, q4 = item - il * W4;
+    int il, q4;
+    dv.split(item, il, q4);
     const int i = lo + il;
     const int k = cl[i];
     const int4 am = *reinterpret_cast<const int4*>(arg.irow(k) + q4 * 4);
@@ -351,9 +388,11 @@ __device__ __noinline__ void s3_gather_t(int kind, const int* __restrict__ cp, c
                                          int ldd, int tid, int nth) {
   const int W4 = C >> 2;
   const int rows = hi - lo;
+  const S3Div dv(W4);
 #pragma unroll 1
   for (int item = tid; item < rows * W4; item += nth) {
-    const int jl = item / W4, q4 = item - jl * W4;
+    int jl, q4;
+    dv.split(item, jl, q4);
     const int j = lo + jl;
     const int sb = cp[j], se = cp[j + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -431,14 +470,14 @@ __device__ __noinline__ void s3_cross_tile_store(const void* const* wgbase, int 
   const int MN = M * N;
   const int per = (MN + tiles - 1) / tiles;
   const int e0 = ti * per, e1 = min(MN, e0 + per);
+  const int wend = Mw * N, bend = wend + N;     // [0, wend): weight rows, [wend, bend): the bias row
 #pragma unroll 1
   for (int e = e0 + tid; e < e1; e += nth) {
     float acc = 0.f;
 #pragma unroll 1
     for (int tt = 0; tt < tiles; ++tt) acc += reinterpret_cast<const float*>(wgbase[tt])[e];
-    const int m = e / N;
-    if (m < Mw) dw[e] = acc;
-    else if (m == Mw && db) db[e - Mw * N] = acc;
+    if (e < wend) dw[e] = acc;
+    else if (e < bend && db) db[e - wend] = acc;
   }
 }
 
@@ -625,7 +664,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int Kin1 = P.Kin1, Kin2 = P.Kin2;
   const int co1 = br * H1, co2 = br * H2;
   const bool mirror = (s.flags & 1) != 0;
-  const bool multi = NT > 1;
+  const bool multi = NT > 1;             // rows distributed over the cluster: cluster barriers between phases
+  const bool staged = P.blob_words > 0;  // the graph's blob and feature tile are staged in shared memory
   DRGNN_PHASE3(0);
   float* xs = sm + P.xs;     float* scr = sm + P.scr;   float* zin1 = sm + P.zin1; float* z1 = sm + P.z1;
   float* p1 = sm + P.p1;     float* zin2 = sm + P.zin2; float* z2 = sm + P.z2;     float* p2 = sm + P.p2;
@@ -667,7 +707,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int64_t boff = DRGNN_BLOB_OFFSET(g, n0, eg0);
   const int* blb = s.blob + boff;                 // NT > 1: the index lists are read from global memory / L2
   const float* wbl = s.wblob ? s.wblob + boff : nullptr;
-  if (!multi) {
+  if (staged) {
     if (t == 0) {
       s3_mbar_init(&bars[0], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -727,7 +767,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     bases[which * S3_MAX_TILES + tt] = (tt == ti) ? local : cluster.map_shared_rank(local, (unsigned)(br * NT + tt));
   }
   __syncthreads();
-  if (!multi) s3_mbar_wait(&bars[0], 0);
+  if (staged) s3_mbar_wait(&bars[0], 0);
   const int K = blb[2], E1 = blb[3], Q = blb[4];
   if (blb[5] != 1 || blb[0] != n || blb[1] != m || K > s.max_k || Q > s.max_q || K < 0 || Q < 0 || E1 < 0 || E1 > m) {
     if (t == 0) atomicOr(s.status, 64);
@@ -752,33 +792,32 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const void* const* barg0 = bases + 2 * S3_MAX_TILES; const void* const* bz2 = bases + 3 * S3_MAX_TILES;
   const void* const* barg1 = bases + 4 * S3_MAX_TILES; const void* const* bdzin2 = bases + 5 * S3_MAX_TILES;
   const void* const* bwg = bases + 6 * S3_MAX_TILES;
-  // level-0 features: the staged tile (NT = 1) or the global rows of the graph
-  __shared__ const void* xbase[1];
-  if (t == 0) xbase[0] = multi ? (const void*)(s.x + (int64_t)n0 * F) : (const void*)xs;
-  if (multi) cluster.sync(); else __syncthreads();   // every CTA of the cluster runs (its shared memory may be read from now on)
+  // level-0 features: the staged tile or the global rows of the graph
+  const void* xsrc = staged ? (const void*)xs : (const void*)(s.x + (int64_t)n0 * F);
+  if (multi) cluster.sync();   // every CTA of the cluster runs (its shared memory may be read from now on)
   DRGNN_PHASE3(1);
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;
 
   // ---- conv1: aggregate, transform
-  s3_aggregate(kind, rp0, col0, ew0, S3Rows{xbase, INT_MAX, F}, F, lo0, hi0, zin1, LDZIN1, nullptr, nullptr, t, T);
+  s3_aggregate(kind, rp0, col0, ew0, s3_rows_flat(xsrc, F), F, lo0, hi0, zin1, LDZIN1, nullptr, nullptr, t, T);
   __syncthreads();
   DRGNN_PHASE3(2);
   s3_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(3);
   // ---- P1 = cluster max of Z1 (community_pooling.py:201): members may live in any tile
-  s3_cluster_max(cmp0, cmem0, S3Rows{bz1, nta, LDZ1}, lo1, hi1, p1, LDP, arg0, H1, H14, t, T);
+  s3_cluster_max(cmp0, cmem0, s3_rows(bz1, NT, nta, LDZ1), lo1, hi1, p1, LDP, arg0, H1, H14, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(4);
   // ---- conv2 on the coarsened graph
-  s3_aggregate(kind, rp1, col1, ew1, S3Rows{bp1, kta, LDP}, H1, lo1, hi1, zin2, LDZIN2, s1, post1, t, T);
+  s3_aggregate(kind, rp1, col1, ew1, s3_rows(bp1, NT, kta, LDP), H1, lo1, hi1, zin2, LDZIN2, s1, post1, t, T);
   __syncthreads();
   DRGNN_PHASE3(5);
   s3_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
-  s3_cluster_max(cmp1, cmem1, S3Rows{bz2, kta, LDZ2}, lo2, hi2, p2, H2, arg1, H2, H24, t, T);
+  s3_cluster_max(cmp1, cmem1, s3_rows(bz2, NT, kta, LDZ2), lo2, hi2, p2, H2, arg1, H2, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(7);
   if (mirror) {   // parity tests: the intermediates the op-level path leaves in global memory (global ids)
@@ -964,7 +1003,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     }
   }
   // ---- dZ2 (in place): read-out mean backward, routed to the arg-max member, gated by ReLU
-  s3_route(cl1, S3Rows{barg1, qta, H2}, S3Rows{barg1, qta, H2}, drrow, 1.f / (float)max(Q, 1), z2, LDZ2, lo1, hi1, H24, t, T);
+  s3_route(cl1, s3_rows(barg1, NT, qta, H2), s3_rows(barg1, NT, qta, H2), drrow, 1.f / (float)max(Q, 1), z2, LDZ2, lo1, hi1, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(11);
   // ---- conv2 weight (+ bias) gradient over this tile's rows: split-K partials, local sum, sum over the tiles
@@ -982,11 +1021,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   if (kind == 0) s3_cross_tile_store(bwg, NT, ti, M2, N2, M2, part + s.off_w2 + br * H2 * H1, nullptr, t, T);
   else s3_cross_tile_store(bwg, NT, ti, M2, N2, Kin2, part + s.off_w2, part + s.off_b2, t, T);
   // ---- dP1 = transposed aggregation of dzin2 (CSC of the coarsened graph) (+ self term)
-  s3_gather_t(kind, cscp1, cscr1, ew1t, S3Rows{bdzin2, kta, LDZIN2}, kind ? H1 : 0, dzin2, LDZIN2, s1, H1, lo1, hi1, dp1, LDP, t, T);
+  s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin2, NT, kta, LDZIN2), kind ? H1 : 0, dzin2, LDZIN2, s1, H1, lo1, hi1, dp1, LDP, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(13);
   // ---- dZ1 (in place): routed to the arg-max node of its cluster, gated by ReLU
-  s3_route(cl0, S3Rows{barg0, kta, H1}, S3Rows{bp1, kta, LDP}, nullptr, 1.f, z1, LDZ1, lo0, hi0, H14, t, T);
+  s3_route(cl0, s3_rows(barg0, NT, kta, H1), s3_rows(bp1, NT, kta, LDP), nullptr, 1.f, z1, LDZ1, lo0, hi0, H14, t, T);
   __syncthreads();
   DRGNN_PHASE3(14);
   // ---- conv1 weight (+ bias) gradient

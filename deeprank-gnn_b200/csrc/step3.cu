@@ -25,9 +25,17 @@ extern "C" int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_
   if (tiles != 1 && tiles != 2 && tiles != 4 && tiles != 8) return DRGNN_ERR_INVALID;
   if (tiles * (kind == 0 ? 2 : 1) > 8) return DRGNN_ERR_UNSUPPORTED;          // portable cluster size
   if ((int64_t)max_n * (2 * F + h1 + 8) > (1 << 24) || max_e > (1 << 24) || (int64_t)Hd * h2 > (1 << 22)) return DRGNN_ERR_UNSUPPORTED;
-  const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
-  if (bytes > device_info().smem_optin - 1024) return DRGNN_ERR_UNSUPPORTED;
-  return bytes;
+  // staged (the graph's blob + feature tile in every CTA's shared memory) when that fits, else streamed from L2
+  for (int stage = 1; stage >= 0; --stage) {
+    const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, stage, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
+    if (bytes <= device_info().smem_optin - 1024) return bytes;
+  }
+  return DRGNN_ERR_UNSUPPORTED;
+}
+
+static int step3_stage(int kind, int tiles, int F, int h1, int h2, int max_n, int max_k, int max_q, int max_e, int Hd, int out) {
+  const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, 1, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
+  return bytes <= device_info().smem_optin - 1024 ? 1 : 0;
 }
 
 extern "C" int drgnn_net_step_pick_tiles(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
@@ -126,7 +134,8 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
     return fail(DRGNN_ERR_UNSUPPORTED, "net_step: kind %d with %d tiles does not fit (max_n %d, max_e %d)", s->kind, tiles, s->max_n, s->max_e);
   int rc = step3_configure(smem);
   if (rc) return rc;
-  Step3Plan plan = step3_plan(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
+  const int stage = step3_stage(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
+  Step3Plan plan = step3_plan(s->kind, tiles, stage, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
   const int cs = plan.cs;
   const int occ = step3_max_clusters(cs, smem);
   plan.fused_reduce = (train && !s->skip_reduce && s->step_dev != nullptr && !(s->flags & 2) && s->B <= occ) ? 1 : 0;

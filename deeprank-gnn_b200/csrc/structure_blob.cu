@@ -33,7 +33,7 @@ __device__ unsigned long long g_bphase[16];
   } while (0)
 
 struct BlobPlan {   // word offsets into dynamic shared memory
-  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, rowbits, bm, bmT, mem0, mem1, cnt, total;
+  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, rowbits, bm, bmT, mem0, mem1, cnt, ea, eord, total;
   int mw1;   // row stride of rowbits: ceil(max_e/32) + 1 (odd strides keep a thread-per-row walk conflict-free)
   int kw1;   // row stride of the pooled / member bitmaps: ceil(max_n/32) + 1
 };
@@ -62,6 +62,8 @@ __host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e) {
   p.mem0 = take(max_n * p.kw1);
   p.mem1 = take(max_n * p.kw1);
   p.cnt = take(5 * max_n + 8);
+  p.ea = take(max_e);   // edge attributes of the graph (sGAT weights; 4 KB at 1000 edges)
+  p.eord = take((max_e + 1) / 2);
   p.total = o;
   return p;
 }
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   uint32_t* rowbits = sb + P.rowbits;
   uint32_t* bm = sb + P.bm; uint32_t* bmT = sb + P.bmT; uint32_t* mem0 = sb + P.mem0; uint32_t* mem1 = sb + P.mem1;
   int* cnt = reinterpret_cast<int*>(sb + P.cnt);
+  float* eas = reinterpret_cast<float*>(sb + P.ea);
+  uint16_t* eord = reinterpret_cast<uint16_t*>(sb + P.eord);
   const int MW1 = P.mw1, KW1 = P.kw1;
   DRGNN_BPHASE(0);
 
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     }
     erow[e] = (uint16_t)r;
     ecol[e] = (uint16_t)c;
+    if (wb) eas[e] = io.edge_attr[(int64_t)(e0 + e) * io.ne];   // staged once: the weight sums read shared memory
   }
   long long mn0 = LLONG_MAX, mx0 = LLONG_MIN, mn1 = LLONG_MAX, mx1 = LLONG_MIN;
   // raw ids are kept in registers for graphs of up to 2 * T nodes (else re-read)
@@ -344,7 +349,10 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 4
     for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
     bl[BL.col0 + pos] = ecol[e];
-    if (wb) wb[BL.col0 + pos] = io.edge_attr[(int64_t)(e0 + e) * io.ne];
+    if (wb) {
+      wb[BL.col0 + pos] = eas[e];
+      eord[pos] = (uint16_t)e;       // edge id of the CSR slot: the weight sums walk a node's edges in slot order
+    }
   }
 #pragma unroll 1
   for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
@@ -392,44 +400,67 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     }
   }
   if (wb) {
-    // ---- 8. summed attributes of the merged (coalesced) edges, community_pooling.py:204-205: a thread per
-    // (pooled row, bitmap word) walks its pooled edges; each sum runs over the members of the row's cluster
-    // (ascending) and their level-0 edges (ascending edge id) - the fixed order of graph_local_kernel, so both
-    // structure passes give bit-identical weights.  Everything but edge_attr itself is read from shared memory.
-    const int MWm = (m + 31) >> 5, KWn = (n + 31) >> 5;
+    // ---- 8. summed attributes of the merged (coalesced) edges, community_pooling.py:204-205.  A WARP per
+    // pooled row, a LANE per pooled edge of the row: all lanes walk the same sequence - the members of the
+    // row's cluster (ascending), their level-0 edges (ascending edge id: the fixed order of
+    // graph_local_kernel, so both structure passes give bit-identical weights) - with warp-uniform control
+    // flow, and each lane adds the attribute when the edge lands in ITS pooled column.  Everything is read
+    // from shared memory (the attributes were staged in step 1).
+    const int KWn = (n + 31) >> 5;
+    const int lane = t & 31;
+    __syncthreads();   // eord (the emit sweep above) is complete
 #pragma unroll 1
-    for (int item = t; item < K * KWk; item += T) {
-      const int r = item / KWk, wi = item - r * KWk;
+    for (int r = w; r < K; r += SB_WARPS) {
       const uint32_t* row = bm + r * KW1;
-      int q = cnt[n + r] - base1;
+      const uint32_t* mrow = mem0 + r * KW1;
+      const int rbase = cnt[n + r] - base1;
+      const int rcnt = cnt[n + r + 1] - base1 - rbase;     // cnt[n + K] = baseT = base1 + E1 closes the last row
 #pragma unroll 1
-      for (int ww = 0; ww < wi; ++ww) q += __popc(row[ww]);
-      uint32_t bits = row[wi];
-      while (bits) {
-        const int tc = wi * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
+      for (int s0 = 0; s0 < rcnt; s0 += 32) {
+        int tc = -1;                                        // this lane's pooled column: the (s0 + lane)-th set bit
+        {
+          int want = s0 + lane;
+          if (want < rcnt) {
+#pragma unroll 1
+            for (int ww = 0; ww < KWk; ++ww) {
+              const uint32_t bw = row[ww];
+              const int c = __popc(bw);
+              if (want < c) {
+                tc = ww * 32 + (int)__fns(bw, 0, want + 1);
+                break;
+              }
+              want -= c;
+            }
+          }
+        }
         float acc = 0.f;
-        const uint32_t* mrow = mem0 + r * KW1;
 #pragma unroll 1
         for (int mw = 0; mw < KWn; ++mw) {
-          uint32_t mb = mrow[mw];
+          uint32_t mb = mrow[mw];                           // warp-uniform
           while (mb) {
             const int i = mw * 32 + __ffs(mb) - 1;
             mb &= mb - 1;
-            const uint32_t* erw = rowbits + i * MW1;
+            const int a = cnt[i], b = cnt[i + 1];           // CSR slots of node i (cnt[n] = m closes the last row)
 #pragma unroll 1
-            for (int ew_ = 0; ew_ < MWm; ++ew_) {
-              uint32_t eb = erw[ew_];
-              while (eb) {
-                const int e = ew_ * 32 + __ffs(eb) - 1;
-                eb &= eb - 1;
-                if (dense0[ecol[e]] == tc) acc += io.edge_attr[(int64_t)(e0 + e) * io.ne];
+            for (int c0 = a; c0 < b; c0 += 32) {            // the lanes fetch up to 32 edges of the node at once ...
+              const int nb_ = min(32, b - c0);
+              int pc = -2;
+              float val = 0.f;
+              if (lane < nb_) {
+                const int e = eord[c0 + lane];
+                pc = (int)dense0[ecol[e]];
+                val = eas[e];
+              }
+#pragma unroll 1
+              for (int j = 0; j < nb_; ++j) {               // ... and add them in ascending edge order
+                const int pcj = __shfl_sync(0xffffffffu, pc, j);
+                const float vj = __shfl_sync(0xffffffffu, val, j);
+                if (pcj == tc) acc += vj;
               }
             }
           }
         }
-        wb[BL.col1 + q] = acc;
-        ++q;
+        if (s0 + lane < rcnt) wb[BL.col1 + rbase + s0 + lane] = acc;
       }
     }
     __syncthreads();   // the pooled-CSR weights (global memory, this CTA's own writes) are visible to the CTA

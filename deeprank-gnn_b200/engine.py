@@ -508,7 +508,7 @@ class Engine(object):
             return 0
         if s.kind == 'sgat' and (d.edge_attr is None or d.edge_attr.size(1) != 1):
             return 0
-        key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'step3', self.step3_tiles)
+        key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'step3', self.step3_tiles, d.B)
         tiles = self._fused_fit.get(key)
         if tiles is None:
             if s.kind == 'ginet' and ops.ginet_step2_smem_bytes(s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e,
@@ -520,6 +520,12 @@ class Engine(object):
                 tiles = self.step3_tiles if ok else 0
             else:
                 tiles = ops.net_step_pick_tiles(s.kind, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+                # more tiles than shared memory demands while the grid still fits the machine in one wave: a batch
+                # of 64 single-branch graphs then works on 128 SMs instead of 64
+                while tiles and tiles < 4 and 2 * tiles * s.nb <= 8 and d.B * s.nb * tiles * 2 <= self._sms and \
+                        ops.net_step_smem_bytes(s.kind, 2 * tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e,
+                                                s.Hd, s.out) >= 0:
+                    tiles *= 2
             self._fused_fit[key] = tiles
         return tiles
 

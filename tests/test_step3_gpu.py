@@ -160,9 +160,11 @@ def test_step3_in_kernel_reduction_equals_reduction_launch_and_graph_replay(lib,
     rc = [ec.upload(pb, slot=i) for i, pb in enumerate(packed)]
     for i in range(10):
         la, pa = ea.step(ra[i % 8])
-        assert ops.net_step_last()[0] == 1
+        if i < 8:                                   # first use of a slot captures its graph (later steps replay it)
+            assert ops.net_step_last()[0] == 1
         lb, pb_ = eb.step(rb[i % 8])
-        assert ops.net_step_last()[0] == 2
+        if i < 8:
+            assert ops.net_step_last()[0] == 2
         torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(pa, pb_, rtol=1e-4, atol=1e-5)
     ea.validate(), eb.validate()

@@ -31,7 +31,7 @@ def main():
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     cfg = bench.workload_config(name, None)
     _graphs, batches = bench.make_pool(cfg, 8, seed=0)
-    packed = [PackedBatch.from_batch(b) for b in batches]
+    packed = [PackedBatch.from_batch(b, idx16=True, edge_attr=cfg['net'] == 'sGAT') for b in batches]
     for graph in (True, False):
         eng = Engine(cfg['net'], cfg['feat'], 1, 1, hidden=cfg['hidden'], device='cuda:0', lr=1e-3, graph=graph, seed=0)
         ds = [eng.upload(pb, slot=i) for i, pb in enumerate(packed)]
@@ -62,6 +62,15 @@ def main():
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
             if ph[18] > ph[16]:
                 print('  in-kernel reduction: grid barrier %d | reduce + Adam %d' % (ph[17] - ph[16], ph[18] - ph[17]))
+            if eng._last_path == 'step3':
+                _lib.check(_lib.load().drgnn_debug_phase3_cycles(ph), 'phase3')
+                n3 = ['stage', 'zin1', 'Z1', 'P1', 'zin2', 'Z2', 'P2', 'readout', 'head', 'headbwd', 'dZ2', 'dW2/dzin2',
+                      'dP1', 'dZ1', 'dW1', 'reduce']
+                from deeprank_gnn_b200 import ops
+                print('general cluster step kernel (tiles %d), block 0: %d cycles total'
+                      % (ops.net_step_last()[1], max(ph[15], ph[16]) - ph[0]))
+                print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(n3)
+                                        if ph[i + 1] >= ph[i]))
             _lib.check(_lib.load().drgnn_debug_blob_cycles(ph), 'bphase')
             bnames = ['load+minmax', 'relabel', 'scatter', 'count+scan', 'emit']
             print('blob structure kernel, CTA of graph 0: %d cycles total' % (ph[5] - ph[0]))
