@@ -82,12 +82,21 @@ def PreCluster(dataset, method):
             missing.append((fname, mol))
     if not missing:
         return
-    from .community_pooling import community_detection, community_pooling_host
-    for fname, mol in missing:
-        data = dataset.load_one_graph(fname, mol)
-        c0 = community_detection(data.internal_edge_index, data.num_nodes, method=method)
-        pooled = community_pooling_host(c0, data)
-        c1 = community_detection(pooled.internal_edge_index, pooled.num_nodes, method=method)
+    from .community_pooling import community_detection, community_pooling_host, mcl_detection_batch
+    graphs = [dataset.load_one_graph(fname, mol) for fname, mol in missing]
+    if method == 'mcl' and torch.cuda.is_available():
+        # GPU pre-clustering (csrc/mcl.cu): both levels of ALL missing graphs in two launches, one CTA per graph
+        c0s = mcl_detection_batch([g.internal_edge_index for g in graphs], [g.num_nodes for g in graphs])
+        pooled = [community_pooling_host(c0, g) for c0, g in zip(c0s, graphs)]
+        c1s = mcl_detection_batch([p.internal_edge_index for p in pooled], [p.num_nodes for p in pooled])
+    else:
+        c0s, c1s = [], []
+        for data in graphs:
+            c0 = community_detection(data.internal_edge_index, data.num_nodes, method=method)
+            p = community_pooling_host(c0, data)
+            c0s.append(c0)
+            c1s.append(community_detection(p.internal_edge_index, p.num_nodes, method=method))
+    for (fname, mol), data, c0, c1 in zip(missing, graphs, c0s, c1s):
         data.cluster0, data.cluster1 = c0, c1
         dataset._cache[(fname, mol)] = data
 

@@ -156,9 +156,36 @@ def community_pooling(cluster, data):
 # ------------------------------------------------------------------------------------------
 # offline community detection (not on the hot path; same optional dependencies as the reference)
 # ------------------------------------------------------------------------------------------
+def mcl_detection_batch(edge_indices, num_nodes, device=None):
+    """Markov clustering of MANY graphs in one launch of the GPU kernel (``drgnn_mcl_cluster``, csrc/mcl.cu: the
+    algorithm of ``markov_clustering.run_mcl`` with default parameters + ``get_clusters`` + the labelling of
+    community_pooling.py:148-153, float64).  ``edge_indices``: list of ``[2, e_g]`` integer tensors with graph-LOCAL
+    node ids (unit weights, undirected), ``num_nodes``: list of node counts.  Returns a list of int64 CPU tensors."""
+    from . import ops
+    device = torch.device('cuda' if device is None else device)
+    node_ptr, edge_ptr, parts = [0], [0], []
+    for ei, n in zip(edge_indices, num_nodes):
+        ei = torch.as_tensor(ei).long().reshape(2, -1)
+        parts.append(ei + node_ptr[-1])
+        node_ptr.append(node_ptr[-1] + int(n))
+        edge_ptr.append(edge_ptr[-1] + ei.size(1))
+    if not parts:
+        return []
+    ei = torch.cat(parts, dim=1).contiguous().to(device)
+    nptr = torch.tensor(node_ptr, dtype=torch.int32, device=device)
+    eptr = torch.tensor(edge_ptr, dtype=torch.int32, device=device)
+    out = ops.mcl_cluster(ei, nptr, eptr, max(int(n) for n in num_nodes)).cpu()
+    return [out[a:b].clone() for a, b in zip(node_ptr[:-1], node_ptr[1:])]
+
+
 def community_detection(edge_index, num_nodes, edge_attr=None, method='mcl'):
-    """Cluster one graph with Markov clustering or Louvain (community_pooling.py:95-158).
-    Needs networkx plus ``markov_clustering`` (mcl) or ``community`` (python-louvain)."""
+    """Cluster one graph with Markov clustering or Louvain (community_pooling.py:95-158).  ``method='mcl'``
+    without edge weights (what ``PreCluster`` asks for, DataSet.py:76,84) runs on the GPU (``mcl_detection_batch``)
+    and returns the labels on ``edge_index``'s device; weighted MCL and Louvain keep the reference's optional
+    dependencies (networkx plus ``markov_clustering`` / ``python-louvain``)."""
+    if method == 'mcl' and edge_attr is None and torch.cuda.is_available():
+        dev = edge_index.device if edge_index.is_cuda else None
+        return mcl_detection_batch([edge_index], [num_nodes], device=dev)[0].to(edge_index.device)
     import networkx as nx
     g = nx.Graph()
     g.add_nodes_from(range(num_nodes))

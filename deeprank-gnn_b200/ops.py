@@ -573,6 +573,32 @@ def ginet_step2_smem_bytes(F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
     return int(_lib.load().drgnn_ginet_step2_smem_bytes(*[int(v) for v in (F, h1, h2, max_n, max_k, max_q, max_e, Hd, out)]))
 
 
+def mcl_cluster(edge_index, node_ptr, edge_ptr, max_n, return_iters=False):
+    """Markov clustering of every graph of a block-diagonal batch on the GPU (``drgnn_mcl_cluster``): int64
+    ``[N]`` per-graph local labels as ``community_detection(..., method='mcl')`` returns them
+    (community_pooling.py:142-155).  ``edge_index [2,E]`` int64 / int32 with global node ids.  ONE host sync
+    (status check)."""
+    require_cuda(edge_index, node_ptr, edge_ptr)
+    _i32(node_ptr, 'node_ptr'), _i32(edge_ptr, 'edge_ptr')
+    if edge_index.dtype not in (I32, I64) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise DrgnnError('edge_index must be an int64 / int32 [2, E] tensor')
+    edge_index = edge_index.contiguous()
+    B = node_ptr.numel() - 1
+    dev = edge_index.device
+    N = int(node_ptr[-1].item()) if B > 0 else 0
+    cluster = torch.zeros(N, dtype=I64, device=dev)
+    iters = torch.zeros(max(B, 1), dtype=I32, device=dev)
+    status = torch.zeros(1, dtype=I32, device=dev)
+    need = int(_lib.load().drgnn_mcl_work_doubles(B, int(max_n)))
+    work = torch.empty(max(need, 1), dtype=torch.float64, device=dev)
+    call('drgnn_mcl_cluster', ptr(node_ptr), ptr(edge_ptr), ptr(edge_index), B, edge_index.size(1),
+         1 if edge_index.dtype == I32 else 0, int(max_n), ptr(work), ptr(cluster), ptr(iters), ptr(status), stream_ptr())
+    st = int(status.item())
+    if st:
+        raise DrgnnError('mcl_cluster: ' + '; '.join(t for bit, t in _lib.STATUS_TEXT.items() if st & bit))
+    return (cluster, iters[:B]) if return_iters else cluster
+
+
 NET_KINDS = {'ginet': 0, 'sgat': 1, 'fout': 2}
 
 

@@ -570,6 +570,20 @@ int drgnn_feed_run(const drgnn_feed_step* steps, int32_t n, int32_t n_slots, voi
                    void* prep_stream0, void* prep_stream1, void* read_stream, void* ring, int64_t ring_stride,
                    int32_t ring_slots);
 
+/* ---- GPU pre-clustering: Markov clustering of every graph of a batch, one CTA per graph ----
+ * Replaces community_detection(edge_index, num_nodes, method='mcl') (community_pooling.py:95-158: networkx ->
+ * scipy -> markov_clustering.run_mcl with default parameters + get_clusters), which PreCluster runs twice per
+ * graph on the CPU (DataSet.py:45-88).  edge_index [2,E] int64 (idx32 = 0) or int32 with GLOBAL node ids of a
+ * block-diagonal batch (graph g owns nodes node_ptr[g]..node_ptr[g+1] and edges edge_ptr[g]..edge_ptr[g+1]);
+ * unit weights, undirected.  cluster [N] int64 receives per-graph LOCAL labels exactly as the reference returns
+ * them (clusters sorted as member tuples, a node of several clusters keeps the last; ids may have gaps).
+ * work: drgnn_mcl_work_doubles(B, max_n) doubles (two dense n x n float64 matrices per graph);
+ * iters [B] (optional) receives the iterations run; status as in the structure pass. */
+int64_t drgnn_mcl_work_doubles(int32_t B, int32_t max_n);
+int drgnn_mcl_cluster(const int32_t* node_ptr, const int32_t* edge_ptr, const void* edge_index, int32_t B, int64_t E,
+                      int32_t idx32, int32_t max_n, double* work, int64_t* cluster, int32_t* iters, int32_t* status,
+                      void* stream);
+
 /* small utilities used by the host layer */
 int drgnn_relu_mask(const float* g, int32_t ldg, const float* out, int32_t ldo, int32_t rows,
                     const int32_t* rows_dev, int32_t C, float* gz, int32_t ldgz, void* stream);
