@@ -87,8 +87,15 @@ class NeuralNet(object):
     def __init__(self, database, Net, node_feature=['type', 'polarity', 'bsa'], edge_feature=['dist'], target='irmsd',
                  lr=0.01, batch_size=32, percent=[1.0, 0.0], database_eval=None, index=None, class_weights=None,
                  task=None, classes=[0, 1], threshold=None, pretrained_model=None, shuffle=True, outdir='./',
-                 cluster_nodes='mcl', transform_sigmoid=False, fused=True, device=None, verbose=True):
+                 cluster_nodes='mcl', transform_sigmoid=False, fused=True, device=None, verbose=True, cache=None):
+        """``cache`` (fused path only): a directory; the packed feeder records of every loader are written there
+        once (``data.PackedCache``: one memory-mapped file per loader, page-locked with ``cudaHostRegister``) and
+        every later epoch feeds the GPU straight from the mapping - no HDF5 access, no Python collation
+        (``DataSet.py:231-366`` does both per graph per epoch).  The mini-batches are then FROZEN as composed in
+        the first epoch; ``shuffle=True`` reshuffles their order, not their members."""
         self.fused = fused
+        self.cache = cache
+        self._records = {}
         self.verbose = verbose
         self._device_arg = device
         if pretrained_model is None:
@@ -253,8 +260,79 @@ class NeuralNet(object):
         data['raw_outputs'] += raw
         return data
 
+    def _cached_records(self, loader):
+        """(packed records, targets, loss normalisers, mol names) of ``loader`` from the packed cache, built on
+        first use."""
+        import hashlib
+        import json
+        from .data import PackedCache
+        key = id(loader)
+        if key in self._records:
+            return self._records[key]
+        os.makedirs(self.cache, exist_ok=True)
+        ds = loader.dataset
+        ident = json.dumps([[str(f), str(m)] for f, m in getattr(ds, 'index_complexes', [])] +
+                           [self.batch_size, list(self.node_feature), list(self.edge_feature), str(self.target),
+                            self.task, self.engine.spec.kind])
+        stem = os.path.join(self.cache, 'records_' + hashlib.sha1(ident.encode()).hexdigest()[:16])
+        if not (os.path.exists(stem + '.pack') and os.path.exists(stem + '.json')):
+            shuffle, loader.shuffle = loader.shuffle, False        # composition frozen in data-set order
+            try:
+                packed, inv, tg, mols = self._pack(list(loader))
+            finally:
+                loader.shuffle = shuffle
+            PackedCache.build(stem + '.pack', packed)
+            with open(stem + '.json', 'w') as f:
+                json.dump({'inv': inv, 'targets': tg, 'mol': mols}, f)
+        cache = PackedCache(stem + '.pack', register=True)
+        with open(stem + '.json') as f:
+            meta = json.load(f)
+        rec = (cache, [cache[i] for i in range(len(cache))], meta['targets'], meta['inv'], meta['mol'])
+        self._records[key] = rec
+        return rec
+
+    def _pack(self, batches):
+        eng = self.engine
+        classes = self.classes if self.task == 'class' else None
+        packed, inv, tg, mols = [], [], [], []
+        for b in batches:
+            has_y = getattr(b, 'y', None) is not None
+            # compact feeder records: uint16 graph-local edge ids; edge attributes only for the net that reads them
+            packed.append(PackedBatch.from_batch(b, classes=classes if has_y else None, idx16=True,
+                                                 edge_attr=eng.spec.kind == 'sgat'))
+            mols.append(list(b.mol) if isinstance(b.mol, list) else [b.mol])
+            if not has_y:
+                tg.append(None)
+                inv.append(1.0)
+            elif self.task == 'class':
+                idx = [self.classes_to_idx[int(t)] for t in b.y.reshape(-1).tolist()]
+                tg.append(idx)
+                w = self.weights
+                inv.append(1.0 / (float(w[idx].sum()) if w is not None else len(idx)))
+            else:
+                tg.append(b.y.reshape(-1).tolist())
+                inv.append(1.0 / b.num_graphs)
+        return packed, inv, tg, mols
+
     def _fused_pass(self, loader, train):
         eng = self.engine
+        if self.cache:
+            _cache, packed, tg, inv, mols = self._cached_records(loader)
+            order = torch.randperm(len(packed)).tolist() if (loader.shuffle and train) else list(range(len(packed)))
+            packed, tg, inv, mols = ([packed[i] for i in order], [tg[i] for i in order], [inv[i] for i in order],
+                                     [mols[i] for i in order])
+            losses, preds = eng.train_batches(packed, inv_norms=inv, train=train)
+            eng.validate()
+            out, raw, y = [], [], []
+            data = {'outputs': [], 'raw_outputs': [], 'targets': [], 'mol': []}
+            loss_val = 0.0
+            for mol, l, p, t in zip(mols, losses.tolist(), preds, tg):
+                if t is not None:
+                    loss_val += l
+                self._collect(data, out, raw, y, p, t, mol)
+            if train:
+                self.model.load_state_dict(eng.state_dict())
+            return out, y, loss_val, self._finish(data, out, raw, y)
         batches = list(loader)
         classes = self.classes if self.task == 'class' else None
         packed, inv, tg = [], [], []

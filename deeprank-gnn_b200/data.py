@@ -327,9 +327,14 @@ class PackedCache(object):
                 f.write(b'\0' * ((-raw.nbytes) % 64))
         return len(metas)
 
-    def __init__(self, path, pin=False):
+    def __init__(self, path, pin=False, register=False):
+        """``pin=True``: every record is copied into its own pinned block when read.  ``register=True``: the
+        memory map itself is page-locked once (``cudaHostRegister``), so records are handed to the asynchronous
+        host->device copy of ``Engine.train_batches`` / ``drgnn_feed_run`` straight from the mapping - no copy, no
+        per-record pinned allocation (falls back to ``pin=True`` when the driver refuses the mapping)."""
         import json
         self.path, self.pin = path, bool(pin)
+        self.registered = False
         with open(path, 'rb') as f:
             if f.read(8) != self.MAGIC:
                 raise ValueError('%s is not a packed cache' % path)
@@ -339,7 +344,33 @@ class PackedCache(object):
             raise ValueError('unsupported packed-cache version %r' % index.get('version'))
         self.records = index['records']
         self._base = (16 + n + 63) // 64 * 64
-        self._map = np.memmap(path, dtype=np.float32, mode='r', offset=self._base) if self.records else None
+        # 'c' (private copy-on-write): page-lockable without the read-only registration flag; nothing is written
+        self._map = np.memmap(path, dtype=np.float32, mode='c' if register else 'r', offset=self._base) \
+            if self.records else None
+        self._tmap = None
+        if register and self._map is not None:
+            self._register()
+
+    def _register(self):
+        try:
+            t = torch.from_numpy(self._map)
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
+            if int(rc) != 0:
+                raise RuntimeError('cudaHostRegister returned %s' % rc)
+            self._tmap, self.registered = t, True
+        except Exception:
+            self.pin = True               # per-record pinned copies instead
+
+    def close(self):
+        if self.registered and self._tmap is not None:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self._tmap.data_ptr())
+            except Exception:
+                pass
+            self.registered, self._tmap = False, None
+
+    def __del__(self):
+        self.close()
 
     def __len__(self):
         return len(self.records)
@@ -351,8 +382,11 @@ class PackedCache(object):
         pb.max_k0, pb.max_k1 = m['max_k0'], m['max_k1']          # stored already rounded
         assert pb.numel == m['numel'], 'packed-cache record %d does not match the record layout' % i
         start = m['offset'] // 4
-        view = torch.from_numpy(np.asarray(self._map[start:start + pb.numel]))
-        if self.pin:
+        if self.registered:
+            view = self._tmap[start:start + pb.numel]            # page-locked mapping: DMA source as it is
+        else:
+            view = torch.from_numpy(np.asarray(self._map[start:start + pb.numel]))
+        if self.pin and not self.registered:
             buf = torch.empty(pb.numel, dtype=torch.float32, pin_memory=True)
             buf.copy_(view)
         else:

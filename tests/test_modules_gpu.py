@@ -201,3 +201,42 @@ def test_neuralnet_fused_epoch_equals_autograd_epoch(lib, tmp_path):
         assert abs(a - b) <= 1e-3 * max(1.0, abs(b))
     for k in res[0][1]:
         _close(res[0][1][k], res[1][1][k], k, 2e-3)
+
+
+@pytest.mark.parametrize('net', ['GINet', 'sGAT'])
+def test_neuralnet_epochs_from_the_packed_cache_equal_epochs_from_hdf5(lib, tmp_path, net):
+    """SURVEY 8f rank 1 wired into the plugin API: ``NeuralNet(..., cache=dir)`` writes the packed feeder records
+    once (data.PackedCache: one memory-mapped file, page-locked with cudaHostRegister) and feeds every later epoch
+    from the mapping; training from the cache must equal training from ``HDF5DataSet`` batch for batch
+    (DataSet.py:231-366 replaced), and a second NeuralNet must reuse the files without touching HDF5 collation."""
+    import os
+    from deeprank_gnn_b200 import ginet, sGAT
+    from deeprank_gnn_b200.NeuralNet import NeuralNet
+    Net = {'GINet': ginet.GINet, 'sGAT': sGAT.sGAT}[net]
+    kw = dict(node_feature=['type', 'polarity', 'bsa'], edge_feature=['dist'], target='irmsd', lr=0.01, batch_size=3,
+              percent=[1.0, 0.0], shuffle=False, outdir=str(tmp_path), verbose=False)
+    torch.manual_seed(3)
+    a = NeuralNet(FIXTURE, Net, **kw)
+    sd0 = {k: v.clone() for k, v in a.model.state_dict().items()}
+    b = NeuralNet(FIXTURE, Net, cache=str(tmp_path / 'cache'), **kw)
+    for m in (a, b):
+        m.model.load_state_dict(sd0)
+        m.engine.load_state_dict(sd0)
+        m.engine.spec.dropout = 0.0
+    a.train(nepoch=3, validate=False, save_model='none')
+    b.train(nepoch=3, validate=False, save_model='none')
+    assert a.train_loss == b.train_loss
+    for k, v in a.model.state_dict().items():
+        assert torch.equal(v, b.model.state_dict()[k]), k
+    files = sorted(os.listdir(str(tmp_path / 'cache')))
+    assert len(files) == 2 and files[0].endswith('.json') and files[1].endswith('.pack')
+    cache = b._records[id(b.train_loader)][0]
+    assert cache.registered or cache.pin           # page-locked mapping (or the pinned-copy fallback)
+    stamp = os.path.getmtime(os.path.join(str(tmp_path / 'cache'), files[1]))
+    c = NeuralNet(FIXTURE, Net, cache=str(tmp_path / 'cache'), **kw)
+    c.model.load_state_dict(sd0)
+    c.engine.load_state_dict(sd0)
+    c.engine.spec.dropout = 0.0
+    c.train(nepoch=3, validate=False, save_model='none')
+    assert c.train_loss == a.train_loss
+    assert os.path.getmtime(os.path.join(str(tmp_path / 'cache'), files[1])) == stamp      # reused, not rebuilt
