@@ -55,24 +55,46 @@ class Metrics(object):
         self.FNR = _ratio(fn, tp + fn)
         self.FDR = _ratio(fp, tp + fp)
         self.accuracy = _ratio(tp + tn, tp + fp + fn + tn)
-        p, t = np.asarray(prediction, dtype=np.float64), np.asarray(y, dtype=np.float64)
-        if p.size and p.shape == t.shape:
-            err = p - t
+        # regression metrics: only for the continuous targets, None otherwise (Metrics.py:176-215); the attribute
+        # names (including the reference's ``mean_abolute_error`` / ``median_squared_log_error``) are kept
+        self.explained_variance = self.max_error = self.mean_abolute_error = self.mean_squared_error = None
+        self.root_mean_squared_error = self.mean_squared_log_error = self.median_squared_log_error = None
+        self.r2_score = self.mean_absolute_error = None
+        if target in ('fnat', 'irmsd', 'lrmsd'):
+            p, t = np.asarray(prediction, dtype=np.float64), np.asarray(y, dtype=np.float64)
+            if p.size == 0 or p.shape != t.shape:
+                raise ValueError('Metrics: predictions and targets must be non-empty lists of the same length')
+            err = t - p
             self.max_error = float(np.abs(err).max())
             self.mean_absolute_error = float(np.abs(err).mean())
             self.mean_squared_error = float((err ** 2).mean())
             self.root_mean_squared_error = float(np.sqrt((err ** 2).mean()))
             var = float(t.var())
-            self.explained_variance = float(1 - err.var() / var) if var > 0 else None
-            self.r2_score = float(1 - (err ** 2).sum() / ((t - t.mean()) ** 2).sum()) if var > 0 else None
+            # sklearn conventions for a constant target: 1.0 for a perfect fit, 0.0 otherwise
+            self.explained_variance = float(1 - err.var() / var) if var > 0 else (1.0 if float(err.var()) == 0 else 0.0)
+            ss_res, ss_tot = float((err ** 2).sum()), float(((t - t.mean()) ** 2).sum())
+            self.r2_score = float(1 - ss_res / ss_tot) if ss_tot > 0 else (1.0 if ss_res == 0 else 0.0)
+            if (p < 0).any() or (t < 0).any():
+                print('WARNING: Mean Squared Logarithmic Error cannot be used when targets contain negative values.')
+            else:
+                self.mean_squared_log_error = float(((np.log1p(t) - np.log1p(p)) ** 2).mean())
+            self.median_squared_log_error = float(np.median(np.abs(err)))      # (median ABSOLUTE error, Metrics.py:210)
 
-    def hitrate(self):
+    def format_score(self):
+        """Ranks of the predictions (best first: descending for fnat / bin_class, ascending otherwise) and the binary
+        ground truth (Metrics.py:218-239)."""
         idx = np.argsort(self.prediction)
         if self.target in ('fnat', 'bin_class'):
             idx = idx[::-1]
-        gt = np.asarray(get_binary(self.y, self.threshold, self.target))[idx]
-        return np.cumsum(gt)
+        return idx, np.array(get_binary(self.y, self.threshold, self.target))
+
+    def hitrate(self):
+        idx, gt = self.format_score()
+        return np.cumsum(gt[idx])
 
     def auc(self):
+        """``roc_auc_score(ground_truth, idx)`` exactly as the reference computes it (Metrics.py:251-260: the score it
+        passes is the rank INDEX array, not the predictions - kept for attribute-level parity)."""
         from sklearn.metrics import roc_auc_score
-        return roc_auc_score(get_binary(self.y, self.threshold, self.target), self.prediction)
+        idx, gt = self.format_score()
+        return roc_auc_score(gt, idx)

@@ -173,14 +173,14 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, 
 // A row-distributed array: tile t holds rows [t*rpt, (t+1)*rpt) at base[t] (a generic pointer into that CTA's
 // shared memory, own or remote).  Level-0 features with NT > 1 are one global array: rpt = INT_MAX, base[0].
 struct S3Rows {
-  const void* const* base;   // [tiles] in shared memory (used when magic != 0)
-  const void* b0;            // the only tile when the array is not distributed (magic == 0): no lookup, no division
+  const void* const* base;   // [tiles] in shared memory; NULL: the array is not distributed
+  const void* b0;            // the only tile when the array is not distributed: no lookup, no division
   unsigned magic;            // ceil(2^32 / rpt): owner(i) = umulhi(i, magic), exact for i, rpt < 2^16
   int rpt;
   int ld;
   __device__ __forceinline__ const void* row(int i) const {
-    if (magic == 0u) return reinterpret_cast<const char*>(b0) + (size_t)(i * ld) * 4u;
-    const int o = (int)__umulhi((unsigned)i, magic);
+    if (base == nullptr) return reinterpret_cast<const char*>(b0) + (size_t)(i * ld) * 4u;
+    const int o = rpt == 1 ? i : (int)__umulhi((unsigned)i, magic);    // (2^32 / 1 does not fit the magic word)
     return reinterpret_cast<const char*>(base[o]) + (size_t)((i - o * rpt) * ld) * 4u;
   }
   __device__ __forceinline__ const float* frow(int i) const { return reinterpret_cast<const float*>(row(i)); }
@@ -189,11 +189,11 @@ struct S3Rows {
 // rows of a cluster-distributed array (tile t at base[t], rpt rows each); one tile: direct addressing
 __device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, int rpt, int ld) {
   S3Rows r;
-  r.base = base;
+  r.base = tiles > 1 ? base : nullptr;
   r.b0 = base[0];
   r.rpt = rpt;
   r.ld = ld;
-  r.magic = tiles > 1 ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
+  r.magic = (tiles > 1 && rpt > 1) ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
   return r;
 }
 __device__ __forceinline__ S3Rows s3_rows_flat(const void* b0, int ld) {

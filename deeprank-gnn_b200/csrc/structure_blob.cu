@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     const int KWn = (n + 31) >> 5;
     const int lane = t & 31;
     __syncthreads();   // eord (the emit sweep above) is complete
+    DRGNN_BPHASE(6);
 #pragma unroll 1
     for (int r = w; r < K; r += SB_WARPS) {
       const uint32_t* row = bm + r * KW1;
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
       }
     }
     __syncthreads();   // the pooled-CSR weights (global memory, this CTA's own writes) are visible to the CTA
+    DRGNN_BPHASE(7);
     // ---- 9. the same weights in pooled-CSC order: CSC slot (column c, row r) <- CSR slot of (r, c)
 #pragma unroll 1
     for (int item = t; item < K * KWk; item += T) {

@@ -520,12 +520,8 @@ class Engine(object):
                 tiles = self.step3_tiles if ok else 0
             else:
                 tiles = ops.net_step_pick_tiles(s.kind, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
-                # more tiles than shared memory demands while the grid still fits the machine in one wave: a batch
-                # of 64 single-branch graphs then works on 128 SMs instead of 64
-                while tiles and tiles < 4 and 2 * tiles * s.nb <= 8 and d.B * s.nb * tiles * 2 <= self._sms and \
-                        ops.net_step_smem_bytes(s.kind, 2 * tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e,
-                                                s.Hd, s.out) >= 0:
-                    tiles *= 2
+                # (more tiles than shared memory demands do not pay: measured on cfg3, B = 64, 1 / 2 / 4 tiles =
+                # 41 / 46 / 82 us per step - the cluster barriers and DSMEM latency outweigh the halved rows)
             self._fused_fit[key] = tiles
         return tiles
 

@@ -48,7 +48,12 @@ class GINetConvLayer(nn.Module):
         x = x.to(torch.float32)
         if graph is None:
             graph = Fn.GraphOp.from_edge_index(edge_index, x.size(0))
-        z = Fn.linear(Fn.aggregate_sum(x, graph), self.fc.weight, self.fc.bias)
+        z = Fn.linear(Fn.aggregate_sum(x, graph), self.fc.weight, None)
+        if self.fc.bias is not None:
+            # the reference applies fc (with its bias) to x[col] per EDGE before the sum (ginet.py:57,71): a node
+            # receives its bias once per incoming edge
+            deg = (graph.rowptr[1:] - graph.rowptr[:-1]).to(z.dtype).unsqueeze(1)
+            z = z + deg * self.fc.bias
         return z + self._dead()
 
     def __repr__(self):
@@ -83,6 +88,52 @@ class GINet(nn.Module):
         W2 = torch.cat([self.conv2.fc.weight, self.conv2_ext.fc.weight], dim=0)          # [2 h2, h1]
         z2 = Fn.linear(Fn.aggregate_sum(p1, lv.g1), W2, None, Fin=h1, Fout=h2, groups=2, relu=True)   # [K0, 2 h2]
         r = lv.readout(lv.pool1(z2))                                                       # [B, 2 h2] = cat(x, x_ext)
+        keep = None
+        if self.training and self.dropout > 0:
+            keep = torch.empty(r.size(0), self.fc1.out_features, device=r.device).bernoulli_(1.0 - self.dropout)
+        h = Fn.linear(r, self.fc1.weight, self.fc1.bias, relu=True, keep_mask=keep,
+                      keep_scale=1.0 / (1.0 - self.dropout) if keep is not None else 1.0)
+        out = Fn.linear(h, self.fc2.weight, self.fc2.bias)
+        dead = self.conv1._dead() + self.conv2._dead() + self.conv1_ext._dead() + self.conv2_ext._dead()
+        return out + dead
+
+
+class GINetInternal(nn.Module):
+    """The two-graph GINet of the reference documentation (``docs/tutorial.advanced.rst:126-137``, README "Custom
+    GNN"): ``conv1`` / ``conv2`` convolve over the INTERFACE edges (``edge_index``, ``edge_attr``) and
+    ``conv1_ext`` / ``conv2_ext`` over the INTERNAL edges (``internal_edge_index``, ``internal_edge_attr``) of the
+    same nodes, both pooled with the same clusters; read-outs concatenated -> fc1 -> ReLU -> dropout -> fc2.  (The
+    shipped ``ginet.GINet`` feeds ``edge_index`` to both branches, ginet.py:104-126; this is the variant its
+    documentation describes.)  Same constructor contract ``(input_shape, output_shape, input_shape_edge)`` and
+    ``state_dict`` names as ``GINet``; runs on the generic autograd ops (two structure passes, one per edge set)."""
+
+    def __init__(self, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32)):
+        super().__init__()
+        h1, h2 = hidden
+        self.hidden = (h1, h2)
+        self.conv1 = GINetConvLayer(input_shape, h1, input_shape_edge)
+        self.conv2 = GINetConvLayer(h1, h2, input_shape_edge)
+        self.conv1_ext = GINetConvLayer(input_shape, h1, input_shape_edge)
+        self.conv2_ext = GINetConvLayer(h1, h2, input_shape_edge)
+        self.fc1 = nn.Linear(2 * h2, 4 * h2)
+        self.fc2 = nn.Linear(4 * h2, output_shape)
+        self.clustering = 'mcl'
+        self.dropout = 0.4
+
+    def _branch(self, x, lv, conv1, conv2):
+        z1 = Fn.linear(Fn.aggregate_sum(x, lv.g0), conv1.fc.weight, None, relu=True)
+        z2 = Fn.linear(Fn.aggregate_sum(lv.pool0(z1), lv.g1), conv2.fc.weight, None, relu=True)
+        return lv.readout(lv.pool1(z2))
+
+    def forward(self, data):
+        if getattr(data, 'internal_edge_index', None) is None:
+            from ._lib import DrgnnError
+            raise DrgnnError('GINetInternal needs internal_edge_index (DataSet.py:289-306)')
+        x = node_features(data)
+        r_int = self._branch(x, Levels(data), self.conv1, self.conv2)
+        lv_ext = Levels(data, edge_index=data.internal_edge_index, edge_attr=getattr(data, 'internal_edge_attr', None))
+        r_ext = self._branch(x, lv_ext, self.conv1_ext, self.conv2_ext)
+        r = torch.cat([r_int, r_ext], dim=1)
         keep = None
         if self.training and self.dropout > 0:
             keep = torch.empty(r.size(0), self.fc1.out_features, device=r.device).bernoulli_(1.0 - self.dropout)

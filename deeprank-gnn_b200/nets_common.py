@@ -11,8 +11,11 @@ class Levels(object):
     """The two graphs a forward pass convolves over and the two pooling maps, as views of one
     ``Structure`` (ONE host sync for the live sizes K0, E1, K1)."""
 
-    def __init__(self, data):
-        st = batch_structure(data, mirrors=False if getattr(data, '_no_mirrors', False) else True)
+    def __init__(self, data, edge_index=None, edge_attr='__own__'):
+        """``edge_index`` / ``edge_attr``: another edge set over the same nodes and clusters (the internal edges
+        of the two-graph GINet of docs/tutorial.advanced.rst:126-137)."""
+        st = batch_structure(data, mirrors=False if getattr(data, '_no_mirrors', False) else True,
+                             edge_index=edge_index, edge_attr=edge_attr)
         self.st = st
         K0, E1, K1 = st.sync_counts()
         self.K0, self.E1, self.K1 = K0, E1, K1

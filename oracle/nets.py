@@ -101,6 +101,36 @@ class GINet(nn.Module):
         return self.fc2(x)
 
 
+class GINetInternal(GINet):
+    """The two-graph variant of the reference documentation (docs/tutorial.advanced.rst:126-137): identical to
+    ``GINet`` except that the ``_ext`` branch convolves over ``internal_edge_index`` / ``internal_edge_attr``."""
+
+    def forward(self, data):
+        act = F.relu
+        data_ext = data.clone()
+
+        data.x = act(self.conv1(data.x, data.edge_index, data.edge_attr))
+        cluster = _offset(data.cluster0, data.batch)
+        data = pooling.community_pooling(cluster, data)
+        data.x = act(self.conv2(data.x, data.edge_index, data.edge_attr))
+        cluster = _offset(data.cluster1, data.batch)
+        x, batch = max_pool_x(cluster, data.x, data.batch)
+
+        data_ext.x = act(self.conv1_ext(data_ext.x, data_ext.internal_edge_index, data_ext.internal_edge_attr))
+        cluster = _offset(data_ext.cluster0, data_ext.batch)
+        data_ext = pooling.community_pooling(cluster, data_ext)
+        data_ext.x = act(self.conv2_ext(data_ext.x, data_ext.internal_edge_index, data_ext.internal_edge_attr))
+        cluster = _offset(data_ext.cluster1, data_ext.batch)
+        x_ext, batch_ext = max_pool_x(cluster, data_ext.x, data_ext.batch)
+
+        x = scatter_mean(x, batch, dim=0)
+        x_ext = scatter_mean(x_ext, batch_ext, dim=0)
+        x = torch.cat([x, x_ext], dim=1)
+        x = act(self.fc1(x))
+        x = F.dropout(x, self.dropout, training=self.training)
+        return self.fc2(x)
+
+
 # ------------------------------------------------------------------- sGAT ---
 class sGraphAttentionLayer(nn.Module):
     def __init__(self, in_channels, out_channels, bias=True, undirected=True):           # sGAT.py:35-56

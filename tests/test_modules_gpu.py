@@ -240,3 +240,42 @@ def test_neuralnet_epochs_from_the_packed_cache_equal_epochs_from_hdf5(lib, tmp_
     c.train(nepoch=3, validate=False, save_model='none')
     assert c.train_loss == a.train_loss
     assert os.path.getmtime(os.path.join(str(tmp_path / 'cache'), files[1])) == stamp      # reused, not rebuilt
+
+
+def test_two_graph_ginet_of_the_documentation_matches_oracle(lib):
+    """docs/tutorial.advanced.rst:126-137: interface edges for conv1 / conv2, INTERNAL edges for the ``_ext``
+    branch; forward and every parameter gradient against the oracle restatement, on the fixture."""
+    from deeprank_gnn_b200 import ginet
+    from deeprank_gnn_b200.data import Batch
+    graphs = _graphs('fixture')[:6]
+    torch.manual_seed(2)
+    ref = onets.GINetInternal(graphs[0].x.size(1), 1, 1).eval()
+    sd = copy.deepcopy(ref.state_dict())
+    pred = ref(to_oracle_batch(graphs))
+    pred.pow(2).mean().backward()
+    mod = ginet.GINetInternal(graphs[0].x.size(1), 1, 1).to(DEV).eval()
+    mod.load_state_dict(sd)
+    out = mod(Batch.from_data_list(graphs).to(DEV))
+    out.pow(2).mean().backward()
+    _close(out, pred, 'pred')
+    ref_g = dict(ref.named_parameters())
+    for n, p in mod.named_parameters():
+        _close(p.grad, ref_g[n].grad, 'grad ' + n)
+    # the branches really see different graphs: the shipped single-graph GINet gives another answer
+    single = ginet.GINet(graphs[0].x.size(1), 1, 1).to(DEV).eval()
+    single.load_state_dict(sd)
+    assert float((single(Batch.from_data_list(graphs).to(DEV)) - out).abs().max()) > 1e-4
+
+
+def test_ginet_conv_layer_with_bias_adds_it_once_per_incoming_edge(lib):
+    """GINetConvLayer(bias=True): the reference applies fc (with bias) to x[col] per edge before scatter_sum
+    (ginet.py:57,71), so node i receives deg_i * b."""
+    from deeprank_gnn_b200 import ginet
+    g = _graphs('cfg2')[0]
+    torch.manual_seed(4)
+    ref = onets.GINetConvLayer(32, 16, 1, bias=True)
+    mod = ginet.GINetConvLayer(32, 16, 1, bias=True).to(DEV)
+    mod.load_state_dict(ref.state_dict())
+    out_ref = ref(g.x, g.edge_index, g.edge_attr)
+    out = mod(g.x.to(DEV), g.edge_index.to(DEV), g.edge_attr.to(DEV))
+    _close(out, out_ref, 'conv with bias')

@@ -75,6 +75,9 @@ def main():
             bnames = ['load+minmax', 'relabel', 'scatter', 'count+scan', 'emit']
             print('blob structure kernel, CTA of graph 0: %d cycles total' % (ph[5] - ph[0]))
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(bnames)))
+            if ph[6] and ph[7]:
+                print('  emit split (sGAT weights): lists %d | pooled sums %d | CSC order + header %d'
+                      % (ph[6] - ph[4], ph[7] - ph[6], ph[5] - ph[7]))
             _lib.check(_lib.load().drgnn_debug_structure_cycles(ph), 'sphase')
             snames = ['edges', 'CSR', 'CSC', 'relabel', 'members', 'coarsen', 'CSC1', 'level1']
             print('structure kernel, CTA of graph 0: %d cycles total' % (ph[8] - ph[0]))
