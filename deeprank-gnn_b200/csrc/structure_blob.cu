@@ -461,31 +461,18 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
             }
           }
         }
-        if (s0 + lane < rcnt) wb[BL.col1 + rbase + s0 + lane] = acc;
+        if (s0 + lane < rcnt) {
+          wb[BL.col1 + rbase + s0 + lane] = acc;
+          // the same weight at the edge's pooled-CSC slot: column tc, rank of row r among the rows of bmT[tc]
+          const uint32_t* rowT = bmT + tc * KW1;
+          int posT = cnt[n + K + tc] - baseT + __popc(rowT[r >> 5] & ((1u << (r & 31)) - 1u));
+#pragma unroll 1
+          for (int ww = 0; ww < (r >> 5); ++ww) posT += __popc(rowT[ww]);
+          wb[BL.cscr1 + posT] = acc;
+        }
       }
     }
-    __syncthreads();   // the pooled-CSR weights (global memory, this CTA's own writes) are visible to the CTA
     DRGNN_BPHASE(7);
-    // ---- 9. the same weights in pooled-CSC order: CSC slot (column c, row r) <- CSR slot of (r, c)
-#pragma unroll 1
-    for (int item = t; item < K * KWk; item += T) {
-      const int c = item / KWk, wi = item - c * KWk;
-      const uint32_t* rowT = bmT + c * KW1;
-      int qT = cnt[n + K + c] - baseT;
-#pragma unroll 1
-      for (int ww = 0; ww < wi; ++ww) qT += __popc(rowT[ww]);
-      uint32_t bits = rowT[wi];
-      while (bits) {
-        const int r = wi * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t* row = bm + r * KW1;
-        int slot = cnt[n + r] - base1 + __popc(row[c >> 5] & ((1u << (c & 31)) - 1u));
-#pragma unroll 1
-        for (int ww = 0; ww < (c >> 5); ++ww) slot += __popc(row[ww]);
-        wb[BL.cscr1 + qT] = wb[BL.col1 + slot];
-        ++qT;
-      }
-    }
   }
   if (t == 0) {   // closing pointers and the header
     bl[BL.rp0 + n] = m;

@@ -329,14 +329,14 @@ def test_cluster_step_kernel_falls_back_when_a_graph_does_not_fit(lib):
     graphs = synthetic.make_graphs(dict(nodes=(250, 300), edges_per_node=5, feat=32), count=4, seed=3)
     d = _device_batch(graphs)
     assert ops.ginet_step2_smem_bytes(32, 16, 32, d.max_n, d.max_k0, d.max_k1, d.max_e, 128, 1) < 0
-    e = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1)
+    e = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1, dropout=0.0)
     e.step3 = False                       # without the general cluster kernel: the single-CTA whole-step kernel
     e.step(d)
     assert ops.ginet_step_last_variant() == 1 and e._last_path == 'ops'
     e.step_variant = 2
     with pytest.raises(DrgnnError):
         e.step(d)
-    e2 = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1)
+    e2 = Engine('GINet', 32, 1, 1, device='cuda:0', seed=1, dropout=0.0)
     e2.load_state_dict(e.state_dict())
     e.step_variant = 1
     l1, p1 = e.step(d)
