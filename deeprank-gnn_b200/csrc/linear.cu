@@ -449,14 +449,15 @@ extern "C" int drgnn_linear(const drgnn_linear_args* a, void* stream) {
                 a->rows, a->Fin, a->Fout, a->groups);
   DRGNN_REQUIRE(a->X && a->W && a->Y, "linear: NULL pointer");
   DRGNN_REQUIRE(a->w_layout == 0 || a->w_layout == 1, "linear: bad w_layout %d", a->w_layout);
-  DRGNN_REQUIRE(a->math == 0 || a->math == 1, "linear: bad math mode %d", a->math);
+  DRGNN_REQUIRE(a->math >= 0 && a->math <= 2, "linear: bad math mode %d", a->math);
   DRGNN_REQUIRE(a->ldx >= a->groups * a->Fin && a->ldy >= a->groups * a->Fout, "linear: leading dimension too small");
   DRGNN_REQUIRE(!a->out_mask || a->ld_mask >= a->groups * a->Fout, "linear: ld_mask too small");
   if (a->rows == 0) return DRGNN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int col_tiles = (a->Fout + LT_C - 1) / LT_C;
   dim3 grid((a->rows + LT_R - 1) / LT_R, a->groups * col_tiles);
-  if (a->math == 1) {
+  if (a->math == 2 && drgnn_linear_tcgen05_supported(a)) return drgnn_linear_tcgen05(a, stream);
+  if (a->math >= 1) {
     linear_tf32x3_kernel<<<grid, 128, 0, st>>>(*a, col_tiles);
     DRGNN_CHECK_LAUNCH("linear_tf32x3_kernel");
   } else {

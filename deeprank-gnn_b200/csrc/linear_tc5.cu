@@ -1,0 +1,237 @@
+// Dense per-node transform on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   Y[r, 0:Fout] = act( X[r, 0:Fin] W + bias ) (* mask)         (include/drgnn.h section 3, math = 2)
+//
+// the nn.Linear / torch.mm of the reference layers (ginet.py:57-58, sGAT.py:73, foutnet.py:62-65) applied to
+// node rows - the only GEMM-shaped work of the path (north_star: "tensor cores used only for the dense per-node
+// feature x weight contraction").  fp32 parity is kept with the 3xTF32 split: x = x_hi + x_lo with both halves
+// exactly representable in TF32, and D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in TMEM
+// (the dropped A_lo B_lo term is ~2^-22 relative).
+//
+// One CTA = 128 threads = one 128-row tile per iteration (persistent over tiles):
+//   1. the tile's rows are split into A_hi / A_lo and written to shared memory in the canonical K-major
+//      no-swizzle UMMA layout (core matrices of 8 rows x 16 bytes; LBO = stride between the two 16-byte
+//      K chunks of an MMA, SBO = stride between 8-row groups); W is split once per CTA the same way;
+//   2. ONE thread issues 3 x Fin/8 tcgen05.mma.kind::tf32 (M = 128, N = Fout, K = 8) into a TMEM
+//      accumulator and commits them to an mbarrier;
+//   3. every warp reads its 32 TMEM lanes (= 32 rows) with tcgen05.ld, applies bias / ReLU / mask and stores
+//      whole output rows.
+// Two CTAs per SM interleave (64-96 KB of shared memory, 64 of the 512 TMEM columns each), so one tile's
+// loads and stores overlap the other's MMAs.  The kernel is HBM-bound by design (about 10 FLOP per byte at
+// Fin = 32, Fout = 64); the tensor pipe only has to stay out of the way, which the fp32 FMA version cannot
+// (75 TFLOP/s of FMA peak vs 6.5 TB/s x 10 FLOP/B).
+#include "common.cuh"
+
+namespace drgnn {
+
+static constexpr int TC_THREADS = 128;
+static constexpr int TC_BM = 128;
+static constexpr int TC_TMEM_COLS = 64;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t tc_f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// x = hi + lo, hi = tf32(x), lo = tf32(x - hi)  (both with the 13 low mantissa bits zero)
+__device__ __forceinline__ void tc_split(float x, float& hi, float& lo) {
+  const uint32_t h = tc_f2tf32(x);
+  hi = __uint_as_float(h);
+  lo = __uint_as_float(tc_f2tf32(x - hi));
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits [4,6) = 1), A = B = TF32 (bits [7,10) and
+// [10,13) = 2), both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
+__host__ __device__ inline uint32_t tc_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE_%=;\n"
+      "bra TC_WAIT_%=;\n"
+      "TC_DONE_%=:\n"
+      "}\n" ::"r"(tc_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// element (row, k) of a [rows x K] K-major operand tile in the canonical layout: core matrix (row / 8, k / 4)
+// at ((k / 4) * (rows / 8) + row / 8) * 128 bytes, inside it row % 8 at 16-byte steps
+__device__ __forceinline__ int tc_chunk_word(int row, int kchunk, int rows8) {
+  return ((kchunk * rows8 + (row >> 3)) << 5) + ((row & 7) << 2);      // in 4-byte words
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) linear_tcgen05_kernel(const drgnn_linear_args a, int n_tiles) {
+  extern __shared__ __align__(128) float tsm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int Fin = a.Fin, Fout = a.Fout;
+  const int KC = Fin >> 2;                       // 16-byte K chunks per row
+  const int rows = a.rows_dev ? min(*a.rows_dev, a.rows) : a.rows;
+  float* Ahi = tsm;                              // [128 x Fin]
+  float* Alo = Ahi + TC_BM * Fin;
+  float* Bhi = Alo + TC_BM * Fin;                // [Fout x Fin]
+  float* Blo = Bhi + Fout * Fin;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "n"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // W -> B_hi / B_lo as an [N = Fout][K = Fin] K-major operand (w_layout 0: W[o][k], 1: W[k][o])
+  for (int idx = t; idx < Fout * KC; idx += TC_THREADS) {
+    const int o = idx / KC, kc = idx - o * KC;
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * 4 + j;
+      const float w = a.w_layout == 0 ? __ldg(a.W + (int64_t)o * Fin + k) : __ldg(a.W + (int64_t)k * Fout + o);
+      tc_split(w, hi[j], lo[j]);
+    }
+    const int wd = tc_chunk_word(o, kc, Fout >> 3);
+    *reinterpret_cast<float4*>(Bhi + wd) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(Blo + wd) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = tc_idesc(TC_BM, Fout);
+  const uint32_t a_lbo = (TC_BM >> 3) * 128, b_lbo = (uint32_t)(Fout >> 3) * 128;   // between the 16-byte K chunks
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int r0 = tile * TC_BM;
+    // ---- 1. this thread's row -> A_hi / A_lo (rows past the end are zero)
+    {
+      const int r = r0 + t;
+      const float* xr = a.X + (int64_t)r * a.ldx;
+      for (int kc = 0; kc < KC; ++kc) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) v = __ldg(reinterpret_cast<const float4*>(xr + kc * 4));
+        float4 h, l;
+        tc_split(v.x, h.x, l.x); tc_split(v.y, h.y, l.y); tc_split(v.z, h.z, l.z); tc_split(v.w, h.w, l.w);
+        const int wd = tc_chunk_word(t, kc, TC_BM >> 3);
+        *reinterpret_cast<float4*>(Ahi + wd) = h;
+        *reinterpret_cast<float4*>(Alo + wd) = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // ---- 2. one thread issues the MMAs
+    if (t == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ahi = tc_smem_u32(Ahi), alo = tc_smem_u32(Alo), bhi = tc_smem_u32(Bhi), blo = tc_smem_u32(Blo);
+      uint32_t acc = 0;
+      for (int ks = 0; ks < (Fin >> 3); ++ks) {                       // K = 8 per instruction = two 16-byte chunks
+        const uint32_t ao = (uint32_t)(2 * ks) * a_lbo, bo = (uint32_t)(2 * ks) * b_lbo;
+        tc_mma(tmem_d, tc_desc(alo + ao, a_lbo, 128), tc_desc(bhi + bo, b_lbo, 128), idesc, acc);
+        acc = 1;
+        tc_mma(tmem_d, tc_desc(ahi + ao, a_lbo, 128), tc_desc(blo + bo, b_lbo, 128), idesc, acc);
+        tc_mma(tmem_d, tc_desc(ahi + ao, a_lbo, 128), tc_desc(bhi + bo, b_lbo, 128), idesc, acc);
+      }
+      tc_commit(&bar);                                                // implies tcgen05.fence::before_thread_sync
+    }
+    // ---- 3. epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows r0 + 32w + lane
+    tc_mbar_wait(&bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = r0 + t;
+    for (int c0 = 0; c0 < Fout; c0 += 16) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (r < rows) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (a.bias) x += __ldg(a.bias + c0 + j);
+          if (a.relu) x = x < 0.f ? 0.f : x;                          // keeps NaN like torch.relu
+          if (a.out_mask) x = (a.out_mask[(int64_t)r * a.ld_mask + c0 + j] > 0.f) ? x * a.mask_scale : 0.f;
+          o[j] = x;
+        }
+        float* yr = a.Y + (int64_t)r * a.ldy + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+    }
+    // the next tile overwrites the operand tiles and the accumulator: everybody is done reading them
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_TMEM_COLS) : "memory");
+}
+
+}  // namespace drgnn
+
+using namespace drgnn;
+
+// 0 when the tcgen05 kernel takes this shape (else the caller uses the mma.sync / FMA kernels)
+extern "C" int drgnn_linear_tcgen05_supported(const drgnn_linear_args* a) {
+  if (a == nullptr) return 0;
+  const bool ok = a->groups == 1 && a->Fin % 8 == 0 && a->Fin >= 8 && a->Fin <= 64 && a->Fout % 16 == 0 && a->Fout >= 16 &&
+                  a->Fout <= TC_TMEM_COLS && a->ldx % 4 == 0 && a->ldy % 4 == 0 && ((uintptr_t)a->X % 16) == 0 &&
+                  ((uintptr_t)a->Y % 16) == 0;
+  return ok ? 1 : 0;
+}
+
+extern "C" int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream) {
+  DRGNN_REQUIRE(a != nullptr && a->X && a->W && a->Y, "linear_tcgen05: NULL pointer");
+  DRGNN_REQUIRE(drgnn_linear_tcgen05_supported(a), "linear_tcgen05: unsupported shape (groups 1, Fin %% 8, Fin <= 64, Fout %% 16, Fout <= 64, "
+                                                   "16-byte aligned rows)");
+  if (a->rows == 0) return DRGNN_OK;
+  const int n_tiles = (a->rows + TC_BM - 1) / TC_BM;
+  const size_t smem = (size_t)4 * (2 * TC_BM * a->Fin + 2 * a->Fout * a->Fin);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    DRGNN_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));
+    configured = 96 * 1024;
+  }
+  int grid = 2 * device_info().sms;
+  if (grid > n_tiles) grid = n_tiles;
+  linear_tcgen05_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*a, n_tiles);
+  DRGNN_CHECK_LAUNCH("linear_tcgen05_kernel");
+  return DRGNN_OK;
+}

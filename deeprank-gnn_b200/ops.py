@@ -352,7 +352,7 @@ def aggregate(src, rowptr, col, out, C_=None, ew=None, sscale=None, self_src=Non
 # ------------------------------------------------------------------------------------------
 # Dense transform
 # ------------------------------------------------------------------------------------------
-MATH_FMA, MATH_TF32X3 = 0, 1
+MATH_FMA, MATH_TF32X3, MATH_TCGEN05 = 0, 1, 2     # 2: tcgen05.mma kind::tf32 (3xTF32, TMEM accumulator), falls back to 1
 default_math = MATH_FMA
 
 

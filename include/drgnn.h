@@ -217,7 +217,11 @@ int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr
  *    activation (out_mask has Y's shape, leading dimension ld_mask).  One mechanism, two uses:
  *    train-mode dropout (ginet.py:138; out_mask = 0/1 keep mask, mask_scale = 1/(1-p)) and
  *    the fused ReLU / dropout backward (out_mask = the forward activation).
- *    math: 0 = fp32 FMA, 1 = 3xTF32 tensor cores (error-compensated, ~fp32 accuracy)
+ *    math: 0 = fp32 FMA, 1 = 3xTF32 on mma.sync tensor-core tiles (error-compensated, ~fp32 accuracy),
+ *          2 = 3xTF32 on the 5th-generation tensor cores: tcgen05.mma.kind::tf32, M = 128 row tiles, fp32
+ *              accumulator in TMEM, operands in the canonical K-major shared-memory layout (csrc/linear_tc5.cu);
+ *              shapes it does not take (drgnn_linear_tcgen05_supported == 0: groups > 1, Fin % 8, Fin > 64,
+ *              Fout % 16, Fout > 64, unaligned rows) fall back to mode 1
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_linear_args {
   const float* X; int32_t ldx;
@@ -229,6 +233,8 @@ typedef struct drgnn_linear_args {
   int32_t w_layout; int32_t relu; int32_t math;
 } drgnn_linear_args;
 int drgnn_linear(const drgnn_linear_args* a, void* stream);
+int drgnn_linear_tcgen05_supported(const drgnn_linear_args* a);
+int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream);
 
 /* Weight / bias gradient of the transform: dW[g][o][k] (w_layout 0) or dW[g][k][o]
  * (w_layout 1) (+)= sum_r G[r, g*Fout+o] * X[r, g*Fin+k], dbias[g*Fout+o] (+)= sum_r G[r,..].

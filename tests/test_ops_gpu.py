@@ -436,6 +436,40 @@ def test_linear_matches_torch(lib, math, rows, Fin, Fout, groups, layout):
     assert (out[rows:] == -1).all() and (out[:, groups * Fout:] == -1).all()
 
 
+@pytest.mark.parametrize('rows,Fin,Fout,layout', [(1000, 32, 32, 0), (128, 32, 16, 1), (129, 64, 64, 0), (70001, 32, 64, 1),
+                                                  (5, 8, 16, 0), (40000, 16, 32, 1), (4097, 48, 16, 0)])
+def test_linear_tcgen05_matches_torch(lib, rows, Fin, Fout, layout):
+    """math = 2: tcgen05.mma kind::tf32 with the 3xTF32 split, fp32 accumulator in TMEM (csrc/linear_tc5.cu) - same
+    contract and the same 2e-5 bound as the FMA kernel (bias, ReLU, mask, padded leading dimensions, live rows)."""
+    from deeprank_gnn_b200 import _lib, ops
+    import ctypes as C
+    dev = _dev()
+    g = torch.Generator().manual_seed(rows + Fin)
+    X = torch.randn(rows, Fin, generator=g)
+    W = torch.randn(Fout, Fin, generator=g) / (Fin ** 0.5)
+    bias = torch.randn(Fout, generator=g)
+    mask = (torch.rand(rows, Fout, generator=g) > 0.4).float()
+    ref = torch.relu(X.double() @ W.double().t() + bias.double()) * mask.double() * 1.5
+    Wst = W if layout == 0 else W.t()
+    out = torch.full((rows + 3, Fout + 4), -1.0, device=dev)              # padded buffer: checks ld handling
+    Xd = torch.zeros(rows + 2, Fin + 4, device=dev)
+    Xd[:rows, :Fin] = X.to(dev)
+    a = _lib.LinearArgs()
+    a.X, a.ldx, a.Y, a.ldy, a.groups, a.Fin, a.Fout = Xd.data_ptr(), Fin + 4, out.data_ptr(), Fout + 4, 1, Fin, Fout
+    assert _lib.load().drgnn_linear_tcgen05_supported(C.byref(a)) == 1
+    ops.linear(Xd[:rows, :Fin], Wst.contiguous().to(dev), Fin, Fout, out[:rows, :Fout], bias=bias.to(dev), w_layout=layout,
+               relu=True, out_mask=mask.to(dev), mask_scale=1.5, math=ops.MATH_TCGEN05)
+    torch.testing.assert_close(out[:rows, :Fout].cpu().double(), ref, rtol=2e-5, atol=2e-5)
+    assert (out[rows:] == -1).all() and (out[:, Fout:] == -1).all()
+    # live row count on the device, no bias / activation
+    live = torch.tensor([rows // 2 + 1], dtype=torch.int32, device=dev)
+    out2 = torch.zeros(rows, Fout, device=dev)
+    ops.linear(Xd[:rows, :Fin], Wst.contiguous().to(dev), Fin, Fout, out2, w_layout=layout, rows_dev=live, math=ops.MATH_TCGEN05)
+    n = rows // 2 + 1
+    torch.testing.assert_close(out2[:n].cpu().double(), (X.double() @ W.double().t())[:n], rtol=2e-5, atol=2e-5)
+    assert (out2[n:] == 0).all()
+
+
 def test_linear_rows_dev_limits_work(lib):
     from deeprank_gnn_b200 import ops
     dev = _dev()
