@@ -41,7 +41,7 @@ def metric_name(cfg):
     other workloads."""
     if cfg['net'] == 'GINet' and cfg['batch'] == 64:
         return METRIC
-    return 'protein-interface graphs/sec (%s fwd+bwd, batch=%d)' % (cfg['net'], cfg['batch'])
+    return 'protein-interface graphs/sec (%s%s fwd+bwd, batch=%d)' % (cfg['net'], cfg.get('layers_tag', ''), cfg['batch'])
 
 
 def parse():
@@ -54,6 +54,8 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--batch', type=int, default=None, help='graphs per GPU per step (default: the config batch)')
+    ap.add_argument('--layers', type=int, default=2, choices=[2, 3],
+                    help='3: the three-layer sGAT / FoutNet throughput variant (BASELINE config 3 "sGAT 3-layer")')
     ap.add_argument('--pool', type=int, default=64, help='distinct batches rotated through (must exceed L2)')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of CUDA-graph replay')
     ap.add_argument('--no-roofline', action='store_true')
@@ -165,6 +167,10 @@ def cpu_steps(cfg, batches, seconds, steps=None, warmup=1):
     from oracle import step as ostep
     torch.set_num_threads(os.cpu_count() or 1)
     net = {'GINet': onets.GINet, 'sGAT': onets.sGAT, 'FoutNet': onets.FoutNet}[cfg['net']]
+    if cfg.get('layers_tag'):
+        if cfg['net'] != 'sGAT':
+            raise SystemExit('--layers 3 has a CPU oracle for sGAT only')
+        net = onets.sGAT3
     onets.LITERAL = cfg['net'] != 'FoutNet'       # the literal per-node Fout loop takes seconds per batch
     torch.manual_seed(0)
     model = net(cfg['feat'], 1, 1, hidden=cfg['hidden']).train()
@@ -205,6 +211,8 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload_config(args.workload, args.batch)
+    if args.layers == 3:
+        cfg['layers_tag'] = ' 3-layer'
     _graphs, batches = make_pool(cfg, min(args.pool, 8), seed=0)
     # a "step" is one batch; bound the run to a few minutes whatever K is
     gps, ms, n = cpu_steps(cfg, batches, seconds=None, steps=args.steps, warmup=max(1, min(args.warmup, 5))) \
@@ -421,12 +429,14 @@ def run_b200(args):
     from deeprank_gnn_b200.engine import Engine
 
     cfg = workload_config(args.workload, args.batch)
+    if args.layers == 3:
+        cfg['layers_tag'] = ' 3-layer'
     B = cfg['batch']
     graphs, batches = make_pool(cfg, args.pool, seed=1000 * rank)
     # compact feeder records (what NeuralNet builds): uint16 graph-local edge ids, edge attributes only for sGAT
     packed = [PackedBatch.from_batch(b, idx16=True, edge_attr=cfg['net'] == 'sGAT') for b in batches]
     eng = Engine(cfg['net'], cfg['feat'], 1, 1, hidden=cfg['hidden'], device=dev, lr=0.001, graph=not args.no_graph,
-                 seed=0)
+                 seed=0, layers=args.layers)
     B_global = B * world
     pool_bytes = sum(p.nbytes for p in packed)
 

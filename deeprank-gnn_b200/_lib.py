@@ -161,6 +161,7 @@ class NetStepArgs(C.Structure):
         ('comm', VP),
         ('kptr0', VP), ('kptr1', VP),
         ('Zin1', VP), ('Z1', VP), ('arg0', VP), ('Zin2', VP), ('Z2', VP), ('arg1', VP),
+        ('layers3', C.c_int32), ('off_w3', C.c_int32), ('off_b3', C.c_int32), ('reserved3', C.c_int32),
     ]
 
 
@@ -252,6 +253,8 @@ _SIGNATURES = {
     'drgnn_net_step_smem_bytes': (_i64, [_i32] * 11),
     'drgnn_net_step_pick_tiles': (C.c_int, [_i32] * 10),
     'drgnn_net_step_max_clusters': (C.c_int, [_i32, _i32, _i64]),
+    'drgnn_net_step_smem_bytes_l': (_i64, [_i32] * 12),
+    'drgnn_net_step_pick_tiles_l': (C.c_int, [_i32] * 11),
     'drgnn_net_step': (C.c_int, [C.POINTER(NetStepArgs), VP]),
     'drgnn_net_step_last_launches': (C.c_int, []),
     'drgnn_net_step_last_tiles': (C.c_int, []),

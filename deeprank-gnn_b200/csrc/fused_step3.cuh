@@ -99,6 +99,7 @@ struct Step3Plan {
   int Kin1, Kin2;                 // widths of the transform inputs: F | 2F, h1 | 2h1
   int ldzin1, ldz1, ldp, ldzin2, ldz2;
   int xs, zin1, z1, p1, zin2, z2, p2, wg, scr, w1, w2, w2t, b1, b2, fc2w, fc1b, fc2b;
+  int zin3, z3, t3, w3, w3t, b3, ldzin3, layers3;     // optional third conv layer on the coarsened graph
   int rrow, hrow, dhrow, drrow, prow, red, rpart, s1, post1;
   int arg0, arg1, blob, wblob, bases, bars;
   int xs_words, scr_words, wg_words, blob_words;
@@ -107,8 +108,9 @@ struct Step3Plan {
 };
 
 __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, int F, int h1, int h2, int max_n, int max_k,
-                                                int max_q, int max_e, int Hd, int out) {
+                                                int max_q, int max_e, int Hd, int out, int layers3 = 0) {
   Step3Plan p;
+  p.layers3 = (layers3 && kind != 0) ? 1 : 0;
   p.tiles = tiles;
   p.nbr = kind == 0 ? 2 : 1;
   p.cs = tiles * p.nbr;
@@ -125,7 +127,8 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, 
   // ones column of zin giving the bias gradient)
   const int mn1 = kind == 0 ? h1 * F : (p.Kin1 + 4) * h1;
   const int mn2 = kind == 0 ? h2 * h1 : (p.Kin2 + 4) * h2;
-  p.wg_words = s3_up4(mn1 > mn2 ? mn1 : mn2);
+  const int mn3 = p.layers3 ? (2 * h2 + 4) * h2 : 0;
+  p.wg_words = s3_up4(mn1 > mn2 ? (mn1 > mn3 ? mn1 : mn3) : (mn2 > mn3 ? mn2 : mn3));
   p.xs_words = stage ? s3_up4(max_n * F) : 0;
   int scr = 4 * p.wg_words;                       // at least four K splits
   if (scr < 4 * 128) scr = 4 * 128;               // partial sums of the in-kernel gradient reduction
@@ -139,6 +142,13 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, 
   p.zin2 = take(p.kt * p.ldzin2);
   p.z2 = take(p.kt * p.ldz2);
   p.p2 = take(p.qt * h2);
+  p.ldzin3 = 2 * h2 + 4;
+  p.zin3 = take(p.layers3 ? p.kt * p.ldzin3 : 0);
+  p.z3 = take(p.layers3 ? p.kt * p.ldz2 : 0);
+  p.t3 = take(p.layers3 ? p.kt * p.ldz2 : 0);
+  p.w3 = take(p.layers3 ? 2 * h2 * h2 : 0);
+  p.w3t = take(p.layers3 ? 2 * h2 * h2 : 0);
+  p.b3 = take(p.layers3 ? h2 : 0);
   p.wg = take(p.wg_words);
   p.w1 = take(p.Kin1 * h1);
   p.w2 = take(p.Kin2 * h2);
@@ -162,7 +172,7 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, 
   p.blob_words = stage ? DRGNN_BLOB_USED(max_n, max_e) : 0;
   p.blob = take(p.blob_words);
   p.wblob = take(kind == 1 ? p.blob_words : 0);
-  p.bases = take(2 * 7 * S3_MAX_TILES);           // seven distributed arrays x 8 tiles of 8-byte generic pointers
+  p.bases = take(2 * 9 * S3_MAX_TILES);           // nine distributed arrays x 8 tiles of 8-byte generic pointers
   p.bars = take(4);
   p.total = o;
   p.fused_reduce = 0;
@@ -680,6 +690,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const void** bases = reinterpret_cast<const void**>(ism + P.bases);   // [7][S3_MAX_TILES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ism + P.bars);
   const int LDZIN1 = P.ldzin1, LDZ1 = P.ldz1, LDP = P.ldp, LDZIN2 = P.ldzin2, LDZ2 = P.ldz2;
+  const bool L3 = P.layers3 != 0;
+  float* zin3 = sm + P.zin3; float* z3 = sm + P.z3; float* t3 = sm + P.t3; float* w3 = sm + P.w3; float* w3t = sm + P.w3t;
+  float* b3 = sm + P.b3;
+  const int LDZIN3 = P.ldzin3;
   float* dp1 = p1;          // the pooled features are dead once conv2 has aggregated them
   float* dzin2 = zin2;      // overwritten after the conv2 weight-gradient products
 
@@ -747,6 +761,18 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
         w2[i] = v;
         w2t[o * Kin2 + k] = v;
       }
+      if (L3) {
+        const float* W3g = s.params + s.off_w3;
+#pragma unroll 1
+        for (int i = t; i < 2 * H2 * H2; i += T) {   // [2H2][H2] as stored -> w3, transposed -> w3t [H2][2H2]
+          const int k = i / H2, o = i - k * H2;
+          const float v = __ldg(W3g + i);
+          w3[i] = v;
+          w3t[o * 2 * H2 + k] = v;
+        }
+#pragma unroll 1
+        for (int i = t; i < H2; i += T) b3[i] = __ldg(s.params + s.off_b3 + i);
+      }
 #pragma unroll 1
       for (int i = t; i < H1; i += T) b1[i] = __ldg(s.params + s.off_b1 + i);
 #pragma unroll 1
@@ -760,10 +786,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     for (int i = t; i < out; i += T) fc2b[i] = __ldg(s.params + s.off_fc2b + i);
   }
   // ---- DSMEM base pointers of the row-distributed arrays of this branch: z1, p1, arg0, z2, arg1, dzin2/zin2, wg
-  if (t < 7 * NT) {
+  if (t < 9 * NT) {
     const int which = t / NT, tt = t - which * NT;
     float* local = which == 0 ? z1 : which == 1 ? p1 : which == 2 ? reinterpret_cast<float*>(arg0)
-                 : which == 3 ? z2 : which == 4 ? reinterpret_cast<float*>(arg1) : which == 5 ? zin2 : wg;
+                 : which == 3 ? z2 : which == 4 ? reinterpret_cast<float*>(arg1) : which == 5 ? zin2
+                 : which == 6 ? wg : which == 7 ? z3 : zin3;
     bases[which * S3_MAX_TILES + tt] = (tt == ti) ? local : cluster.map_shared_rank(local, (unsigned)(br * NT + tt));
   }
   __syncthreads();
@@ -792,6 +819,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const void* const* barg0 = bases + 2 * S3_MAX_TILES; const void* const* bz2 = bases + 3 * S3_MAX_TILES;
   const void* const* barg1 = bases + 4 * S3_MAX_TILES; const void* const* bdzin2 = bases + 5 * S3_MAX_TILES;
   const void* const* bwg = bases + 6 * S3_MAX_TILES;
+  const void* const* bz3 = bases + 7 * S3_MAX_TILES; const void* const* bdzin3 = bases + 8 * S3_MAX_TILES;
   // level-0 features: the staged tile or the global rows of the graph
   const void* xsrc = staged ? (const void*)xs : (const void*)(s.x + (int64_t)n0 * F);
   if (multi) cluster.sync();   // every CTA of the cluster runs (its shared memory may be read from now on)
@@ -816,8 +844,15 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   s3_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(6);
+  if (L3) {   // third conv layer on the coarsened graph (BASELINE config 3: "sGAT 3-layer"), h2 -> h2
+    s3_aggregate(kind, rp1, col1, ew1, s3_rows(bz2, NT, kta, LDZ2), H2, lo1, hi1, zin3, LDZIN3, nullptr, nullptr, t, T);
+    __syncthreads();
+    s3_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
+    if (multi) cluster.sync(); else __syncthreads();
+  }
+  float* zl = L3 ? z3 : z2;                                  // the last conv output: pooled, read out
   // ---- P2 = level-1 cluster max (max_pool_x)
-  s3_cluster_max(cmp1, cmem1, s3_rows(bz2, NT, kta, LDZ2), lo2, hi2, p2, H2, arg1, H2, H24, t, T);
+  s3_cluster_max(cmp1, cmem1, s3_rows(L3 ? bz3 : bz2, NT, kta, LDZ2), lo2, hi2, p2, H2, arg1, H2, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(7);
   if (mirror) {   // parity tests: the intermediates the op-level path leaves in global memory (global ids)
@@ -1001,11 +1036,41 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
       const int il = item / H14, q4 = item - il * H14;
       if (rp1[lo1 + il + 1] == rp1[lo1 + il]) *reinterpret_cast<float4*>(zin2 + il * LDZIN2 + H1 + q4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (L3) {
+#pragma unroll 1
+      for (int item = t; item < r1n * H24; item += T) {
+        const int il = item / H24, q4 = item - il * H24;
+        if (rp1[lo1 + il + 1] == rp1[lo1 + il]) *reinterpret_cast<float4*>(zin3 + il * LDZIN3 + H2 + q4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
   }
   // ---- dZ2 (in place): read-out mean backward, routed to the arg-max member, gated by ReLU
-  s3_route(cl1, s3_rows(barg1, NT, qta, H2), s3_rows(barg1, NT, qta, H2), drrow, 1.f / (float)max(Q, 1), z2, LDZ2, lo1, hi1, H24, t, T);
+  s3_route(cl1, s3_rows(barg1, NT, qta, H2), s3_rows(barg1, NT, qta, H2), drrow, 1.f / (float)max(Q, 1), zl, LDZ2, lo1, hi1, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(11);
+  if (L3) {
+    // ---- third layer backward: dW3 / db3, dzin3 = dZ3 W3^T (aggregated half times post[row]) over zin3, then
+    // dZ2 = relu'(Z2) * (s1 dzin3[:, :H2] + A1^T-weighted dzin3[:, H2:])  (in place on z2)
+    const int M3 = 2 * H2 + 4, N3 = H2;
+    const int KS3 = s3_split(P.scr_words, M3 * N3);
+    s3_splitk_partial(zin3, LDZIN3, z3, LDZ2, M3, N3, r1n, KS3, scr, t, T);
+    __syncthreads();
+    s3_splitk_reduce(scr, M3 * N3, KS3, wg, t, T);
+    s3_gemm(z3, LDZ2, w3t, 2 * H2, r1n, 2 * H2, H2, zin3, LDZIN3, nullptr, 0, post1, H2, t, T);
+    if (multi) cluster.sync(); else __syncthreads();
+    s3_cross_tile_store(bwg, NT, ti, M3, N3, 2 * H2, part + s.off_w3, part + s.off_b3, t, T);
+    s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin3, NT, kta, LDZIN3), H2, zin3, LDZIN3, s1, H2, lo1, hi1, t3, LDZ2, t, T);
+    __syncthreads();
+#pragma unroll 1
+    for (int item = t; item < r1n * H24; item += T) {
+      const int il = item / H24, q4 = item - il * H24;
+      float4* zp = reinterpret_cast<float4*>(z2 + il * LDZ2 + q4 * 4);
+      const float4 zz = *zp;
+      const float4 dd = *reinterpret_cast<const float4*>(t3 + il * LDZ2 + q4 * 4);
+      *zp = make_float4(zz.x > 0.f ? dd.x : 0.f, zz.y > 0.f ? dd.y : 0.f, zz.z > 0.f ? dd.z : 0.f, zz.w > 0.f ? dd.w : 0.f);
+    }
+    if (multi) cluster.sync(); else __syncthreads();   // nobody reads this tile's wg / dzin3 any more
+  }
   // ---- conv2 weight (+ bias) gradient over this tile's rows: split-K partials, local sum, sum over the tiles
   const int M2 = kind == 0 ? H2 : Kin2 + 4, N2 = kind == 0 ? H1 : H2;
   const int M1 = kind == 0 ? H1 : Kin1 + 4, N1 = kind == 0 ? F : H1;

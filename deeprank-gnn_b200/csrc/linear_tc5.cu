@@ -27,6 +27,7 @@ namespace drgnn {
 static constexpr int TC_THREADS = 128;
 static constexpr int TC_BM = 128;
 static constexpr int TC_TMEM_COLS = 64;
+static constexpr int TC_MAX_KC = 16;          // Fin <= 64: at most 16 16-byte chunks per row
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t tc_f2tf32(float x) {
@@ -88,7 +89,7 @@ __device__ __forceinline__ int tc_chunk_word(int row, int kchunk, int rows8) {
   return ((kchunk * rows8 + (row >> 3)) << 5) + ((row & 7) << 2);      // in 4-byte words
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) linear_tcgen05_kernel(const drgnn_linear_args a, int n_tiles) {
+__global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drgnn_linear_args a, int n_tiles) {
   extern __shared__ __align__(128) float tsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -132,15 +133,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_tcgen05_kernel(const drg
   const uint32_t a_lbo = (TC_BM >> 3) * 128, b_lbo = (uint32_t)(Fout >> 3) * 128;   // between the 16-byte K chunks
   uint32_t phase = 0;
 
+  // software pipeline: the rows of the NEXT tile are fetched into registers before the epilogue of the current
+  // one, so their global-memory latency hides behind the TMEM read-back and the output stores
+  float4 xv[TC_MAX_KC];
+  auto fetch = [&](int tile_) {
+    const int r = tile_ * TC_BM + t;
+    const float* xr = a.X + (int64_t)r * a.ldx;
+#pragma unroll
+    for (int kc = 0; kc < TC_MAX_KC; ++kc) {
+      xv[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc < KC && tile_ < n_tiles && r < rows) xv[kc] = __ldg(reinterpret_cast<const float4*>(xr + kc * 4));
+    }
+  };
+  fetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int r0 = tile * TC_BM;
     // ---- 1. this thread's row -> A_hi / A_lo (rows past the end are zero)
-    {
-      const int r = r0 + t;
-      const float* xr = a.X + (int64_t)r * a.ldx;
-      for (int kc = 0; kc < KC; ++kc) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows) v = __ldg(reinterpret_cast<const float4*>(xr + kc * 4));
+#pragma unroll
+    for (int kc = 0; kc < TC_MAX_KC; ++kc) {
+      if (kc < KC) {
+        const float4 v = xv[kc];
         float4 h, l;
         tc_split(v.x, h.x, l.x); tc_split(v.y, h.y, l.y); tc_split(v.z, h.z, l.z); tc_split(v.w, h.w, l.w);
         const int wd = tc_chunk_word(t, kc, TC_BM >> 3);
@@ -165,6 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_tcgen05_kernel(const drg
       }
       tc_commit(&bar);                                                // implies tcgen05.fence::before_thread_sync
     }
+    fetch(tile + (int)gridDim.x);                                     // next tile's rows: in flight during the epilogue
     // ---- 3. epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows r0 + 32w + lane
     tc_mbar_wait(&bar, phase);
     phase ^= 1u;
@@ -229,7 +242,10 @@ extern "C" int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));
     configured = 96 * 1024;
   }
-  int grid = 2 * device_info().sms;
+  int per_sm = (int)((device_info().smem_optin + 1024) / (smem + 1024));     // CTAs one SM holds (shared memory; TMEM: 8)
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * device_info().sms;
   if (grid > n_tiles) grid = n_tiles;
   linear_tcgen05_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*a, n_tiles);
   DRGNN_CHECK_LAUNCH("linear_tcgen05_kernel");

@@ -18,34 +18,44 @@ static bool step3_dims_ok(int kind, int F, int h1, int h2, int Hd, int out) {
          ((kind == 0 ? 2 : 1) * h2) % 4 == 0;
 }
 
-extern "C" int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n,
-                                             int32_t max_k, int32_t max_q, int32_t max_e, int32_t Hd, int32_t out) {
+extern "C" int64_t drgnn_net_step_smem_bytes_l(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n,
+                                               int32_t max_k, int32_t max_q, int32_t max_e, int32_t Hd, int32_t out, int32_t layers3) {
   if (max_n <= 0 || max_k <= 0 || max_q <= 0 || max_e <= 0) return DRGNN_ERR_INVALID;
   if (!step3_dims_ok(kind, F, h1, h2, Hd, out)) return DRGNN_ERR_UNSUPPORTED;
   if (tiles != 1 && tiles != 2 && tiles != 4 && tiles != 8) return DRGNN_ERR_INVALID;
   if (tiles * (kind == 0 ? 2 : 1) > 8) return DRGNN_ERR_UNSUPPORTED;          // portable cluster size
   if ((int64_t)max_n * (2 * F + h1 + 8) > (1 << 24) || max_e > (1 << 24) || (int64_t)Hd * h2 > (1 << 22)) return DRGNN_ERR_UNSUPPORTED;
   // staged (the graph's blob + feature tile in every CTA's shared memory) when that fits, else streamed from L2
+  if (layers3 && kind == 0) return DRGNN_ERR_UNSUPPORTED;
   for (int stage = 1; stage >= 0; --stage) {
-    const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, stage, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
+    const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, stage, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, layers3).total;
     if (bytes <= device_info().smem_optin - 1024) return bytes;
   }
   return DRGNN_ERR_UNSUPPORTED;
 }
+extern "C" int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n,
+                                             int32_t max_k, int32_t max_q, int32_t max_e, int32_t Hd, int32_t out) {
+  return drgnn_net_step_smem_bytes_l(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, 0);
+}
 
-static int step3_stage(int kind, int tiles, int F, int h1, int h2, int max_n, int max_k, int max_q, int max_e, int Hd, int out) {
-  const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, 1, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out).total;
+static int step3_stage(int kind, int tiles, int F, int h1, int h2, int max_n, int max_k, int max_q, int max_e, int Hd, int out,
+                       int layers3) {
+  const int64_t bytes = 4 * (int64_t)step3_plan(kind, tiles, 1, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, layers3).total;
   return bytes <= device_info().smem_optin - 1024 ? 1 : 0;
 }
 
-extern "C" int drgnn_net_step_pick_tiles(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
-                                         int32_t max_q, int32_t max_e, int32_t Hd, int32_t out) {
+extern "C" int drgnn_net_step_pick_tiles_l(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
+                                           int32_t max_q, int32_t max_e, int32_t Hd, int32_t out, int32_t layers3) {
   for (int tiles = 1; tiles <= 8; tiles *= 2) {
-    const int64_t b = drgnn_net_step_smem_bytes(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out);
+    const int64_t b = drgnn_net_step_smem_bytes_l(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, layers3);
     if (b >= 0) return tiles;
     if (b == DRGNN_ERR_INVALID) return DRGNN_ERR_INVALID;
   }
   return DRGNN_ERR_UNSUPPORTED;
+}
+extern "C" int drgnn_net_step_pick_tiles(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
+                                         int32_t max_q, int32_t max_e, int32_t Hd, int32_t out) {
+  return drgnn_net_step_pick_tiles_l(kind, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, 0);
 }
 
 static int step3_configure(int64_t smem) {
@@ -108,6 +118,8 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   DRGNN_REQUIRE(s->kind != 1 || s->wblob, "net_step: sGAT needs the edge weights of the structure pass (wblob)");
   DRGNN_REQUIRE(s->kind == 0 || (s->off_b1 >= 0 && s->off_b2 >= 0), "net_step: conv biases missing");
   DRGNN_REQUIRE(s->task >= 0 && s->task <= 3, "net_step: bad task %d", s->task);
+  DRGNN_REQUIRE(!s->layers3 || (s->kind != 0 && s->off_w3 >= 0 && s->off_b3 >= 0 && !(s->flags & 1)),
+                "net_step: the three-layer variant needs kind 1 / 2, conv3 offsets and no mirror flag");
   DRGNN_REQUIRE(((uintptr_t)s->x % 16) == 0 && ((uintptr_t)s->blob % 16) == 0 && ((uintptr_t)s->params % 16) == 0 &&
                     s->off_fc1w % 4 == 0 && (s->wblob == nullptr || ((uintptr_t)s->wblob % 16) == 0),
                 "net_step: x / blob / params must be 16-byte aligned");
@@ -125,17 +137,19 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   if (s->B == 0) return DRGNN_OK;
   int tiles = s->tiles;
   if (tiles == 0) {
-    tiles = drgnn_net_step_pick_tiles(s->kind, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
+    tiles = drgnn_net_step_pick_tiles_l(s->kind, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out, s->layers3);
     if (tiles < 0)
       return fail(DRGNN_ERR_UNSUPPORTED, "net_step: a graph of %d nodes / %d edges does not fit a cluster of 8 CTAs", s->max_n, s->max_e);
   }
-  const int64_t smem = drgnn_net_step_smem_bytes(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
+  const int64_t smem = drgnn_net_step_smem_bytes_l(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd,
+                                                   s->out, s->layers3);
   if (smem < 0)
     return fail(DRGNN_ERR_UNSUPPORTED, "net_step: kind %d with %d tiles does not fit (max_n %d, max_e %d)", s->kind, tiles, s->max_n, s->max_e);
   int rc = step3_configure(smem);
   if (rc) return rc;
-  const int stage = step3_stage(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
-  Step3Plan plan = step3_plan(s->kind, tiles, stage, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out);
+  const int stage = step3_stage(s->kind, tiles, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out, s->layers3);
+  Step3Plan plan = step3_plan(s->kind, tiles, stage, s->F, s->h1, s->h2, s->max_n, s->max_k, s->max_q, s->max_e, s->Hd, s->out,
+                              s->layers3);
   const int cs = plan.cs;
   const int occ = step3_max_clusters(cs, smem);
   plan.fused_reduce = (train && !s->skip_reduce && s->step_dev != nullptr && !(s->flags & 2) && s->B <= occ) ? 1 : 0;

@@ -55,8 +55,13 @@ def rotation_chunk(sslots, n_slots, lookahead):
 class NetSpec(object):
     """Architecture description of one of the reference networks."""
 
-    def __init__(self, kind, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), dropout=None):
+    def __init__(self, kind, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), dropout=None, layers=2):
         kind = {'GINet': 'ginet', 'sGAT': 'sgat', 'FoutNet': 'fout'}.get(kind, kind).lower()
+        # layers = 3 (sGAT / FoutNet): a third conv layer h2 -> h2 on the coarsened graph before the level-1 max-pool -
+        # the "sGAT 3-layer" throughput variant of BASELINE config 3 (the reference nets have two layers)
+        self.layers = int(layers)
+        if self.layers not in (2, 3) or (self.layers == 3 and kind == 'ginet'):
+            raise ValueError('layers must be 2, or 3 for sGAT / FoutNet')
         if kind not in ('ginet', 'sgat', 'fout'):
             raise ValueError('unknown network %r (GINet, sGAT or FoutNet)' % kind)
         self.kind = kind
@@ -88,14 +93,18 @@ class NetSpec(object):
                 p.append((name + '.fc_attention.weight', (1, 2 * cout + ne), False))
         elif self.kind == 'sgat':
             p = [('conv1.weight', (2 * F, h1), True), ('conv1.bias', (h1,), True),
-                 ('conv2.weight', (2 * h1, h2), True), ('conv2.bias', (h2,), True),
-                 ('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
-                 ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
+                 ('conv2.weight', (2 * h1, h2), True), ('conv2.bias', (h2,), True)]
+            if self.layers == 3:
+                p += [('conv3.weight', (2 * h2, h2), True), ('conv3.bias', (h2,), True)]
+            p += [('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
+                  ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
         else:
             p = [('conv1.Wc', (F, h1), True), ('conv1.Wn', (F, h1), True), ('conv1.bias', (h1,), True),
-                 ('conv2.Wc', (h1, h2), True), ('conv2.Wn', (h1, h2), True), ('conv2.bias', (h2,), True),
-                 ('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
-                 ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
+                 ('conv2.Wc', (h1, h2), True), ('conv2.Wn', (h1, h2), True), ('conv2.bias', (h2,), True)]
+            if self.layers == 3:
+                p += [('conv3.Wc', (h2, h2), True), ('conv3.Wn', (h2, h2), True), ('conv3.bias', (h2,), True)]
+            p += [('fc1.weight', (Hd, h2), True), ('fc1.bias', (Hd,), True),
+                  ('fc2.weight', (out, Hd), True), ('fc2.bias', (out,), True)]
         return p
 
     # names in the order the reference's nn.Module registers them (state_dict order)
@@ -105,11 +114,7 @@ class NetSpec(object):
             for c in ('conv1', 'conv2', 'conv1_ext', 'conv2_ext'):
                 names += [c + '.fc.weight', c + '.fc_edge_attr.weight', c + '.fc_attention.weight']
             return names + ['fc1.weight', 'fc1.bias', 'fc2.weight', 'fc2.bias']
-        if self.kind == 'sgat':
-            return ['conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'fc1.weight', 'fc1.bias',
-                    'fc2.weight', 'fc2.bias']
-        return ['conv1.Wc', 'conv1.Wn', 'conv1.bias', 'conv2.Wc', 'conv2.Wn', 'conv2.bias', 'fc1.weight', 'fc1.bias',
-                'fc2.weight', 'fc2.bias']
+        return [name for name, _shape, _live in self.param_shapes()]
 
 
 def _pad4(n):
@@ -251,8 +256,8 @@ class Engine(object):
     def __init__(self, net, input_shape, output_shape=1, input_shape_edge=1, hidden=(16, 32), device='cuda',
                  task='reg', class_weights=None, transform_sigmoid=False, lr=0.01, betas=(0.9, 0.999), eps=1e-8,
                  dropout=None, graph=False, tiled=True, fused_head=True, fused_graph=True, process_group=None, seed=None,
-                 peer_comm=True):
-        self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout)
+                 peer_comm=True, layers=2):
+        self.spec = NetSpec(net, input_shape, output_shape, input_shape_edge, hidden, dropout, layers)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise DrgnnError('the engine runs on a CUDA device only (no CPU fallback)')
@@ -370,7 +375,7 @@ class Engine(object):
         for name, shape, _live in s.param_shapes():
             layer = name.split('.')[0]
             if layer.startswith('conv'):
-                cin = s.F if layer.startswith('conv1') else s.h1
+                cin = s.F if layer.startswith('conv1') else (s.h1 if layer.startswith('conv2') else s.h2)
                 size = 2 * cin if s.kind == 'sgat' else cin
                 bound = 1.0 / (size ** 0.5)
             else:   # nn.Linear default: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)), same for bias
@@ -516,10 +521,11 @@ class Engine(object):
                 tiles = 0
             elif self.step3_tiles:
                 ok = ops.net_step_smem_bytes(s.kind, self.step3_tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1,
-                                             d.max_e, s.Hd, s.out) >= 0
+                                             d.max_e, s.Hd, s.out, layers3=s.layers == 3) >= 0
                 tiles = self.step3_tiles if ok else 0
             else:
-                tiles = ops.net_step_pick_tiles(s.kind, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+                tiles = ops.net_step_pick_tiles(s.kind, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out,
+                                                layers3=s.layers == 3)
                 # (more tiles than shared memory demands do not pay: measured on cfg3, B = 64, 1 / 2 / 4 tiles =
                 # 41 / 46 / 82 us per step - the cluster barriers and DSMEM latency outweigh the halved rows)
             self._fused_fit[key] = tiles
@@ -588,6 +594,9 @@ class Engine(object):
         if tiles3:
             return self._forward_step3(d, st, tiles3, keep_mask, loss_inv)
         self._last_path = 'ops'
+        if s.layers == 3:
+            raise DrgnnError('the three-layer variant runs through the fused cluster kernel only; this batch does not fit it '
+                             '(graphs of up to %d nodes / %d edges)' % (d.max_n, d.max_e))
         if self._use_fused_graph(d):
             # ONE launch: conv1 -> pool -> conv2 -> pool -> read-out, one CTA per graph (csrc/fused.cu)
             self._fa = ops.ginet_fused_args(st, d.x, flat('conv1.fc.weight', s.C1 * s.F),
@@ -710,13 +719,16 @@ class Engine(object):
             offs = dict(w1=P.offset('conv1.Wc'), b1=P.offset('conv1.bias'), w2=P.offset('conv2.Wc'), b2=P.offset('conv2.bias'))
         offs.update(fc1w=P.offset('fc1.weight'), fc1b=P.offset('fc1.bias'), fc2w=P.offset('fc2.weight'),
                     fc2b=P.offset('fc2.bias'))
+        if s.layers == 3:
+            offs.update(w3=P.offset('conv3.weight' if s.kind == 'sgat' else 'conv3.Wc'), b3=P.offset('conv3.bias'))
         in_kernel = False
         if use_comm and not self._no_exchange and self.fuse_comm and self.fuse_reduce and self._cur_B_global is not None \
                 and d.B * self.world == self._cur_B_global:
             key = (d.max_n, d.max_e, d.max_k0, d.max_k1, tiles, 'clusters3')
             mc = self._fused_fit.get(key)
             if mc is None:
-                smem = ops.net_step_smem_bytes(s.kind, tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out)
+                smem = ops.net_step_smem_bytes(s.kind, tiles, s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out,
+                                               layers3=s.layers == 3)
                 mc = ops.net_step_max_clusters(s.kind, tiles, smem) if smem >= 0 else 0
                 self._fused_fit[key] = mc
             in_kernel = d.B <= mc and tiles * s.nb * d.B <= int(self.comm.struct.max_blocks)

@@ -602,17 +602,17 @@ def mcl_cluster(edge_index, node_ptr, edge_ptr, max_n, return_iters=False):
 NET_KINDS = {'ginet': 0, 'sgat': 1, 'fout': 2}
 
 
-def net_step_pick_tiles(kind, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
+def net_step_pick_tiles(kind, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, layers3=False):
     """Smallest number of node tiles (CTAs sharing one graph) for which the general cluster step kernel fits
     shared memory; 0 when the graph fits no cluster of 8 CTAs."""
-    v = int(_lib.load().drgnn_net_step_pick_tiles(*[int(x) for x in (NET_KINDS[kind], F, h1, h2, max_n, max_k, max_q, max_e,
-                                                                       Hd, out)]))
+    v = int(_lib.load().drgnn_net_step_pick_tiles_l(*[int(x) for x in (NET_KINDS[kind], F, h1, h2, max_n, max_k, max_q, max_e,
+                                                                         Hd, out, 1 if layers3 else 0)]))
     return v if v > 0 else 0
 
 
-def net_step_smem_bytes(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out):
-    return int(_lib.load().drgnn_net_step_smem_bytes(*[int(x) for x in (NET_KINDS[kind], tiles, F, h1, h2, max_n, max_k,
-                                                                         max_q, max_e, Hd, out)]))
+def net_step_smem_bytes(kind, tiles, F, h1, h2, max_n, max_k, max_q, max_e, Hd, out, layers3=False):
+    return int(_lib.load().drgnn_net_step_smem_bytes_l(*[int(x) for x in (NET_KINDS[kind], tiles, F, h1, h2, max_n, max_k,
+                                                                           max_q, max_e, Hd, out, 1 if layers3 else 0)]))
 
 
 def net_step_max_clusters(kind, tiles, smem_bytes):
@@ -646,6 +646,8 @@ def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, 
     s.off_b1 = -1 if o.get('b1') is None else int(o['b1'])
     s.off_b2 = -1 if o.get('b2') is None else int(o['b2'])
     s.off_fc1w, s.off_fc1b, s.off_fc2w, s.off_fc2b = int(o['fc1w']), int(o['fc1b']), int(o['fc2w']), int(o['fc2b'])
+    if o.get('w3') is not None:          # three-layer variant (conv3 on the coarsened graph)
+        s.layers3, s.off_w3, s.off_b3 = 1, int(o['w3']), int(o['b3'])
     s.keep, s.keep_scale = ptr(_f32(keep, 'keep')), float(keep_scale)
     s.drop_p, s.seed = float(drop_p), int(seed) & 0xffffffff
     s.y, s.y_class, s.class_w = ptr(y), ptr(y_class), ptr(class_w)

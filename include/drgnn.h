@@ -494,6 +494,10 @@ typedef struct drgnn_net_step_args {
   /* test mirrors (flags bit 0) */
   const int32_t* kptr0; const int32_t* kptr1;
   float* Zin1; float* Z1; int32_t* arg0; float* Zin2; float* Z2; int32_t* arg1;
+  /* layers3 != 0 (kinds 1, 2): a THIRD conv layer h2 -> h2 on the coarsened graph between conv2 and the level-1
+   * max-pool - the "sGAT 3-layer" throughput variant of BASELINE config 3 (the reference nets have two);
+   * off_w3 -> conv3.weight [2h2][h2] (kind 2: conv3.Wc | conv3.Wn), off_b3 -> conv3.bias [h2] */
+  int32_t layers3; int32_t off_w3; int32_t off_b3; int32_t reserved3;
 } drgnn_net_step_args;
 /* shared memory of one CTA (<0: unsupported shape / does not fit) */
 int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
@@ -504,6 +508,11 @@ int drgnn_net_step_pick_tiles(int32_t kind, int32_t F, int32_t h1, int32_t h2, i
 /* clusters of the step kernel the device holds at once for this plan (<0: error); the gradient reduction
  * (+ Adam, + peer exchange) runs inside the launch when B <= this */
 int drgnn_net_step_max_clusters(int32_t kind, int32_t tiles, int64_t smem_bytes);
+/* the same two queries for the three-layer variant (layers3 != 0) */
+int64_t drgnn_net_step_smem_bytes_l(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,
+                                    int32_t max_q, int32_t max_e, int32_t Hd, int32_t out, int32_t layers3);
+int drgnn_net_step_pick_tiles_l(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
+                                int32_t max_e, int32_t Hd, int32_t out, int32_t layers3);
 int drgnn_net_step(const drgnn_net_step_args* s, void* stream);
 /* kernels the last drgnn_net_step of this thread launched (1: reduction fused / scoring, 2: + reduction launch)
  * and the tile count it used */

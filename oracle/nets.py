@@ -189,6 +189,29 @@ class sGAT(nn.Module):
         return self.fc2(x)
 
 
+class sGAT3(sGAT):
+    """The "sGAT 3-layer + community_pooling" throughput variant of BASELINE config 3: the reference
+    sGAT (two conv layers) with a third ``sGraphAttentionLayer(h2, h2)`` on the coarsened graph before
+    ``max_pool_x``.  Not a reference network - it exists so the fused three-layer path has an oracle."""
+
+    def __init__(self, input_shape, output_shape=1, input_shape_edge=None, hidden=(16, 32)):
+        super().__init__(input_shape, output_shape, input_shape_edge, hidden)
+        self.conv3 = sGraphAttentionLayer(hidden[1], hidden[1])
+
+    def forward(self, data):
+        act = F.relu
+        data.x = act(self.conv1(data.x, data.edge_index, data.edge_attr))
+        cluster = _offset(data.cluster0, data.batch)
+        data = pooling.community_pooling(cluster, data)
+        data.x = act(self.conv2(data.x, data.edge_index, data.edge_attr))
+        data.x = act(self.conv3(data.x, data.edge_index, data.edge_attr))
+        cluster = _offset(data.cluster1, data.batch)
+        x, batch = max_pool_x(cluster, data.x, data.batch)
+        x = scatter_mean(x, batch, dim=0)
+        x = act(self.fc1(x))
+        return self.fc2(x)
+
+
 # ---------------------------------------------------------------- FoutNet ---
 class FoutLayer(nn.Module):
     def __init__(self, in_channels, out_channels, bias=True):                            # foutnet.py:29-48

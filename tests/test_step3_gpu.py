@@ -191,3 +191,33 @@ def test_step3_end_to_end_feeder_for_sgat(lib):
     assert torch.equal(la, lb) and torch.equal(ea.params.data, eb.params.data)
     for x, y in zip(pa, pb_):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('tiles', [0, 2])
+def test_step3_three_layer_sgat_matches_oracle(lib, tiles):
+    """BASELINE config 3 names "sGAT 3-layer": the throughput variant with a third sGraphAttentionLayer(32, 32) on
+    the coarsened graph, fused in the same launch; against the oracle's three-layer restatement."""
+    import copy
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.engine import Engine
+    from helpers import to_oracle_batch
+    from oracle import nets as onets
+    from oracle import step as ostep
+    graphs = synthetic.make_graphs('cfg3', count=12, seed=6, internal=False)
+    torch.manual_seed(3)
+    model = onets.sGAT3(32, 1, 1).eval()
+    sd0 = copy.deepcopy(model.state_dict())
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    loss, pred = ostep.train_step(model, opt, ostep.make_loss('reg'), to_oracle_batch(graphs))
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    eng = Engine('sGAT', 32, 1, 1, device='cuda:0', layers=3).eval()
+    eng.step3_tiles = tiles
+    assert list(eng.state_dict().keys()) == list(sd0.keys())
+    eng.load_state_dict(sd0)
+    eloss, epred = eng.step(_device_batch(graphs))
+    eng.validate()
+    assert eng._last_path == 'step3'
+    _close_abs(epred.view(-1), pred, 'pred')
+    _close_abs(eloss.view(-1), loss.view(-1), 'loss')
+    for name, g in eng.named_grads().items():
+        _close(g, grads[name], 'grad ' + name)
