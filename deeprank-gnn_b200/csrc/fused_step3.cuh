@@ -246,7 +246,7 @@ __device__ __noinline__ void s3_aggregate(int kind, const int* __restrict__ rp, 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float wsum = 0.f;
     if (kind == 1) {
-#pragma unroll 2
+#pragma unroll 4
       for (int p = sb; p < se; ++p) {
         const float w = ew[p];
         const float4 v = *reinterpret_cast<const float4*>(src.frow(col[p]) + q4 * 4);
@@ -254,7 +254,7 @@ __device__ __noinline__ void s3_aggregate(int kind, const int* __restrict__ rp, 
         wsum += w;
       }
     } else {
-#pragma unroll 2
+#pragma unroll 4
       for (int p = sb; p < se; ++p) {
         const float4 v = *reinterpret_cast<const float4*>(src.frow(col[p]) + q4 * 4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -407,14 +407,14 @@ __device__ __noinline__ void s3_gather_t(int kind, const int* __restrict__ cp, c
     const int sb = cp[j], se = cp[j + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kind == 1) {
-#pragma unroll 2
+#pragma unroll 4
       for (int p = sb; p < se; ++p) {
         const float w = ew[p];
         const float4 v = *reinterpret_cast<const float4*>(src.frow(crow[p]) + goff + q4 * 4);
         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
     } else {
-#pragma unroll 2
+#pragma unroll 4
       for (int p = sb; p < se; ++p) {
         const float4 v = *reinterpret_cast<const float4*>(src.frow(crow[p]) + goff + q4 * 4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;

@@ -212,7 +212,7 @@ def test_step3_three_layer_sgat_matches_oracle(lib, tiles):
     grads = {n: p.grad.clone() for n, p in model.named_parameters()}
     eng = Engine('sGAT', 32, 1, 1, device='cuda:0', layers=3).eval()
     eng.step3_tiles = tiles
-    assert list(eng.state_dict().keys()) == list(sd0.keys())
+    assert sorted(eng.state_dict().keys()) == sorted(sd0.keys())
     eng.load_state_dict(sd0)
     eloss, epred = eng.step(_device_batch(graphs))
     eng.validate()
