@@ -28,8 +28,10 @@ def bind_to_gpu_numa_node(device_index):
     Reads /sys (numa_node of the GPU's PCI function, cpulist of the node); returns a short description of
     what was done, never raises."""
     try:
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id \
-            if hasattr(torch.cuda.get_device_properties(device_index), 'pci_bus_id') else None
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = None
+        if all(hasattr(props, k) for k in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bdf = '%04x:%02x:%02x.0' % (int(props.pci_domain_id), int(props.pci_bus_id), int(props.pci_device_id))
         if bdf is None:
             import ctypes
             rt = ctypes.CDLL('libcudart.so')
