@@ -228,6 +228,7 @@ _SIGNATURES = {
     'drgnn_linear': (C.c_int, [C.POINTER(LinearArgs), VP]),
     'drgnn_linear_tcgen05_supported': (C.c_int, [C.POINTER(LinearArgs)]),
     'drgnn_linear_tcgen05': (C.c_int, [C.POINTER(LinearArgs), VP]),
+    'drgnn_debug_tc5_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_linear_wgrad_work_floats': (_i64, [_i32, _i32, _i32, _i32]),
     'drgnn_linear_wgrad': (C.c_int, [C.POINTER(LinearWgradArgs), VP]),
     'drgnn_maxpool_fwd': (C.c_int, [VP, _i32, VP, VP, _i32, VP, _i32, VP, _i32, VP, VP]),

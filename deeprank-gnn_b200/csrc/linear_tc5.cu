@@ -83,11 +83,29 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__host__ __device__ inline int tc_a_region_words(int Fin, int Fout) {
+  const int a = 2 * TC_BM * Fin, y = TC_BM * Fout;
+  return a > y ? a : y;
+}
+
 // element (row, k) of a [rows x K] K-major operand tile in the canonical layout: core matrix (row / 8, k / 4)
 // at ((k / 4) * (rows / 8) + row / 8) * 128 bytes, inside it row % 8 at 16-byte steps
 __device__ __forceinline__ int tc_chunk_word(int row, int kchunk, int rows8) {
   return ((kchunk * rows8 + (row >> 3)) << 5) + ((row & 7) << 2);      // in 4-byte words
 }
+
+// diagnostic: cycles CTA 0 / thread 0 spent per phase, summed over its tiles (drgnn_debug_tc5_cycles):
+// [0] split + store A, [1] fence + barrier + MMA issue, [2] prefetch issue, [3] wait for the MMAs, [4] TMEM read + output stores,
+// [5] closing barrier, [6] tiles
+__device__ unsigned long long g_tc5_phase[8];
+#define TC5_T(i)                                                           \
+  do {                                                                     \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                             \
+      const unsigned long long now_ = clock64();                           \
+      g_tc5_phase[i] += now_ - tprev;                                      \
+      tprev = now_;                                                        \
+    }                                                                      \
+  } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drgnn_linear_args a, int n_tiles) {
   extern __shared__ __align__(128) float tsm[];
@@ -97,9 +115,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
   const int Fin = a.Fin, Fout = a.Fout;
   const int KC = Fin >> 2;                       // 16-byte K chunks per row
   const int rows = a.rows_dev ? min(*a.rows_dev, a.rows) : a.rows;
-  float* Ahi = tsm;                              // [128 x Fin]
+  float* Ahi = tsm;                              // [128 x Fin]; the region also stages the [128 x Fout] output tile
   float* Alo = Ahi + TC_BM * Fin;
-  float* Bhi = Alo + TC_BM * Fin;                // [Fout x Fin]
+  float* Bhi = tsm + tc_a_region_words(Fin, Fout);   // [Fout x Fin]
   float* Blo = Bhi + Fout * Fin;
 
   if (warp == 0) {
@@ -132,6 +150,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
   const uint32_t idesc = tc_idesc(TC_BM, Fout);
   const uint32_t a_lbo = (TC_BM >> 3) * 128, b_lbo = (uint32_t)(Fout >> 3) * 128;   // between the 16-byte K chunks
   uint32_t phase = 0;
+  const uint64_t desc_ahi = tc_desc(tc_smem_u32(Ahi), a_lbo, 128), desc_alo = tc_desc(tc_smem_u32(Alo), a_lbo, 128);
+  const uint64_t desc_bhi = tc_desc(tc_smem_u32(Bhi), b_lbo, 128), desc_blo = tc_desc(tc_smem_u32(Blo), b_lbo, 128);
 
   // software pipeline: the rows of the NEXT tile are fetched into registers before the epilogue of the current
   // one, so their global-memory latency hides behind the TMEM read-back and the output stores
@@ -146,8 +166,13 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
     }
   };
   fetch(blockIdx.x);
+  unsigned long long tprev = clock64();
+  if (blockIdx.x == 0 && t == 0) {
+    for (int i = 0; i < 8; ++i) g_tc5_phase[i] = 0ull;
+  }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int r0 = tile * TC_BM;
+    if (blockIdx.x == 0 && t == 0) { g_tc5_phase[6] += 1ull; tprev = clock64(); }
     // ---- 1. this thread's row -> A_hi / A_lo (rows past the end are zero)
 #pragma unroll
     for (int kc = 0; kc < TC_MAX_KC; ++kc) {
@@ -160,29 +185,40 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
         *reinterpret_cast<float4*>(Alo + wd) = l;
       }
     }
+    TC5_T(0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---- 2. one thread issues the MMAs
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ahi = tc_smem_u32(Ahi), alo = tc_smem_u32(Alo), bhi = tc_smem_u32(Bhi), blo = tc_smem_u32(Blo);
       uint32_t acc = 0;
-      for (int ks = 0; ks < (Fin >> 3); ++ks) {                       // K = 8 per instruction = two 16-byte chunks
-        const uint32_t ao = (uint32_t)(2 * ks) * a_lbo, bo = (uint32_t)(2 * ks) * b_lbo;
-        tc_mma(tmem_d, tc_desc(alo + ao, a_lbo, 128), tc_desc(bhi + bo, b_lbo, 128), idesc, acc);
+      // K = 8 per instruction = two 16-byte chunks: the descriptors of step ks are the base descriptors with the
+      // start-address field (bits [0,14), units of 16 bytes) advanced by 2 ks LBO
+      const uint64_t da = (uint64_t)((2 * a_lbo) >> 4), db = (uint64_t)((2 * b_lbo) >> 4);
+      uint64_t d_alo = desc_alo, d_ahi = desc_ahi, d_blo = desc_blo, d_bhi = desc_bhi;
+      for (int ks = 0; ks < (Fin >> 3); ++ks) {
+        tc_mma(tmem_d, d_alo, d_bhi, idesc, acc);
         acc = 1;
-        tc_mma(tmem_d, tc_desc(ahi + ao, a_lbo, 128), tc_desc(blo + bo, b_lbo, 128), idesc, acc);
-        tc_mma(tmem_d, tc_desc(ahi + ao, a_lbo, 128), tc_desc(bhi + bo, b_lbo, 128), idesc, acc);
+        tc_mma(tmem_d, d_ahi, d_blo, idesc, acc);
+        tc_mma(tmem_d, d_ahi, d_bhi, idesc, acc);
+        d_alo += da; d_ahi += da; d_blo += db; d_bhi += db;
       }
       tc_commit(&bar);                                                // implies tcgen05.fence::before_thread_sync
     }
+    TC5_T(1);
     fetch(tile + (int)gridDim.x);                                     // next tile's rows: in flight during the epilogue
+    TC5_T(2);
     // ---- 3. epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows r0 + 32w + lane
     tc_mbar_wait(&bar, phase);
     phase ^= 1u;
+    TC5_T(3);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int r = r0 + t;
+    // (a) TMEM -> registers -> shared memory.  The output tile [128 x Fout] is staged row-major in the (now idle)
+    // operand region with the 16-byte chunks of a row XOR-swizzled by the row number: a warp's 32 rows hit all
+    // banks evenly (4 wavefronts per 512-byte store, the minimum), and step (b) reads rows back conflict-free.
+    float* Ys = Ahi;
+    const int FC = Fout >> 2;                                         // 16-byte chunks per output row (4, 8 or 16)
     for (int c0 = 0; c0 < Fout; c0 += 16) {
       uint32_t v[16];
       const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
@@ -193,25 +229,42 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (r < rows) {
-        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (a.bias) x += __ldg(a.bias + c0 + j);
-          if (a.relu) x = x < 0.f ? 0.f : x;                          // keeps NaN like torch.relu
-          if (a.out_mask) x = (a.out_mask[(int64_t)r * a.ld_mask + c0 + j] > 0.f) ? x * a.mask_scale : 0.f;
-          o[j] = x;
-        }
-        float* yr = a.Y + (int64_t)r * a.ldy + c0;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      for (int j = 0; j < 16; j += 4) {
+        const int ch = ((c0 + j) >> 2) ^ (t & (FC - 1));
+        *reinterpret_cast<float4*>(Ys + t * Fout + ch * 4) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
     }
+    __syncthreads();
+    // (b) shared memory -> global memory, coalesced: consecutive threads store consecutive 16-byte chunks of a row
+    // (a warp writes whole 128-byte lines), bias / ReLU / mask applied on the way
+    for (int c = t; c < TC_BM * FC; c += TC_THREADS) {
+      const int rr = c / FC, ch = c - rr * FC;
+      const int r = r0 + rr;
+      if (r >= rows) continue;
+      float4 x = *reinterpret_cast<const float4*>(Ys + rr * Fout + ((ch ^ (rr & (FC - 1))) << 2));
+      const int o = ch << 2;
+      if (a.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + o));
+        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+      }
+      if (a.relu) {                                                   // v < 0 ? 0 : v keeps NaN like torch.relu
+        x.x = x.x < 0.f ? 0.f : x.x; x.y = x.y < 0.f ? 0.f : x.y; x.z = x.z < 0.f ? 0.f : x.z; x.w = x.w < 0.f ? 0.f : x.w;
+      }
+      if (a.out_mask) {
+        const float* mk = a.out_mask + (int64_t)r * a.ld_mask + o;
+        x.x = mk[0] > 0.f ? x.x * a.mask_scale : 0.f; x.y = mk[1] > 0.f ? x.y * a.mask_scale : 0.f;
+        x.z = mk[2] > 0.f ? x.z * a.mask_scale : 0.f; x.w = mk[3] > 0.f ? x.w * a.mask_scale : 0.f;
+      }
+      *reinterpret_cast<float4*>(a.Y + (int64_t)r * a.ldy + o) = x;
+    }
+    TC5_T(4);
     // the next tile overwrites the operand tiles and the accumulator: everybody is done reading them
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TC5_T(5);
   }
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_TMEM_COLS) : "memory");
@@ -224,9 +277,10 @@ using namespace drgnn;
 // 0 when the tcgen05 kernel takes this shape (else the caller uses the mma.sync / FMA kernels)
 extern "C" int drgnn_linear_tcgen05_supported(const drgnn_linear_args* a) {
   if (a == nullptr) return 0;
-  const bool ok = a->groups == 1 && a->Fin % 8 == 0 && a->Fin >= 8 && a->Fin <= 64 && a->Fout % 16 == 0 && a->Fout >= 16 &&
+  const bool ok = a->groups == 1 && a->Fin % 8 == 0 && a->Fin >= 8 && a->Fin <= 64 &&
+                  (a->Fout == 16 || a->Fout == 32 || a->Fout == 64) &&      // N % 16, power of two (swizzled output staging)
                   a->Fout <= TC_TMEM_COLS && a->ldx % 4 == 0 && a->ldy % 4 == 0 && ((uintptr_t)a->X % 16) == 0 &&
-                  ((uintptr_t)a->Y % 16) == 0;
+                  ((uintptr_t)a->Y % 16) == 0 && (a->bias == nullptr || ((uintptr_t)a->bias % 16) == 0);
   return ok ? 1 : 0;
 }
 
@@ -236,7 +290,7 @@ extern "C" int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream) {
                                                    "16-byte aligned rows)");
   if (a->rows == 0) return DRGNN_OK;
   const int n_tiles = (a->rows + TC_BM - 1) / TC_BM;
-  const size_t smem = (size_t)4 * (2 * TC_BM * a->Fin + 2 * a->Fout * a->Fin);
+  const size_t smem = (size_t)4 * (tc_a_region_words(a->Fin, a->Fout) + 2 * a->Fout * a->Fin);
   static thread_local size_t configured = 0;
   if (smem > configured) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));
@@ -249,5 +303,11 @@ extern "C" int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream) {
   if (grid > n_tiles) grid = n_tiles;
   linear_tcgen05_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*a, n_tiles);
   DRGNN_CHECK_LAUNCH("linear_tcgen05_kernel");
+  return DRGNN_OK;
+}
+
+extern "C" int drgnn_debug_tc5_cycles(uint64_t* out8) {
+  DRGNN_REQUIRE(out8 != nullptr, "debug_tc5_cycles: NULL");
+  DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_tc5_phase, sizeof(unsigned long long) * 8));
   return DRGNN_OK;
 }

@@ -221,7 +221,7 @@ int drgnn_aggregate_tiled(const drgnn_aggregate_args* a, const int32_t* tile_ptr
  *          2 = 3xTF32 on the 5th-generation tensor cores: tcgen05.mma.kind::tf32, M = 128 row tiles, fp32
  *              accumulator in TMEM, operands in the canonical K-major shared-memory layout (csrc/linear_tc5.cu);
  *              shapes it does not take (drgnn_linear_tcgen05_supported == 0: groups > 1, Fin % 8, Fin > 64,
- *              Fout % 16, Fout > 64, unaligned rows) fall back to mode 1
+ *              Fout other than 16 / 32 / 64, unaligned rows) fall back to mode 1
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_linear_args {
   const float* X; int32_t ldx;
@@ -235,6 +235,10 @@ typedef struct drgnn_linear_args {
 int drgnn_linear(const drgnn_linear_args* a, void* stream);
 int drgnn_linear_tcgen05_supported(const drgnn_linear_args* a);
 int drgnn_linear_tcgen05(const drgnn_linear_args* a, void* stream);
+/* diagnostic: cycles CTA 0 of the last tcgen05 launch spent per phase, summed over its tiles: [0] TF32 split + operand
+ * stores, [1] fence + barrier + MMA issue, [2] prefetch issue, [3] wait for the MMAs, [4] TMEM read-back + output
+ * stores, [5] closing barrier, [6] tiles.  Synchronises the device. */
+int drgnn_debug_tc5_cycles(uint64_t* out8);
 
 /* Weight / bias gradient of the transform: dW[g][o][k] (w_layout 0) or dW[g][k][o]
  * (w_layout 1) (+)= sum_r G[r, g*Fout+o] * X[r, g*Fin+k], dbias[g*Fout+o] (+)= sum_r G[r,..].

@@ -44,6 +44,15 @@ def main():
             ref = torch.relu(X[:: max(1, rows // 4096)].double() @ W.double().t() + b.double())
         out['modes'][str(m)] = {'kernel': names[m], 'ms': ms, 'gbs': out['algorithmic_bytes'] / ms / 1e6,
                                 'tflops': out['logical_flop'] / ms / 1e9, 'max_abs_err': float((chk - ref).abs().max())}
+    if 2 in modes:
+        import ctypes
+        from deeprank_gnn_b200 import _lib
+        ph = (ctypes.c_uint64 * 8)()
+        torch.cuda.synchronize()
+        _lib.check(_lib.load().drgnn_debug_tc5_cycles(ph), 'tc5 cycles')
+        tiles = max(int(ph[6]), 1)
+        out['tc5_cycles_per_tile_cta0'] = {k: round(ph[i] / tiles) for i, k in enumerate(
+            ['split_store', 'fence_bar_issue', 'prefetch_issue', 'mma_wait', 'tmem_ld_store', 'closing_barrier'])}
     print(json.dumps(out))
 
 
