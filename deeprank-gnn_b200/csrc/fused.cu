@@ -593,6 +593,7 @@ __global__ void __launch_bounds__(256) ginet_wgrad_reduce_kernel(const float* __
   else dW2[e - E1] = s;
 }
 
+#include "tc_tiles.cuh"
 #include "fused_step2.cuh"
 
 static inline bool fused_shapes_ok(const drgnn_ginet_fused_args& a) {
@@ -807,7 +808,9 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
         comm = *c;
       }
     }
-    ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(*s, plan, comm);
+    drgnn_ginet_step_args k2 = *s;
+    if (a->F % 8 || a->h1 % 8 || a->h2 % 8) k2.flags &= ~4;   // the tensor-core tiles need widths that are multiples of 8
+    ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(k2, plan, comm);
     DRGNN_CHECK_LAUNCH("ginet_graph_step2_kernel");
     g_step_variant = 2;
     g_step_launches = plan.fused_reduce ? 1 : ((train && !s->skip_reduce) ? 2 : 1);

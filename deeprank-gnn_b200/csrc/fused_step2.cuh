@@ -399,6 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const int F = a.F, H1 = a.h1, H2 = a.h2, C1 = 2 * H1, C2 = 2 * H2, Hd = s.Hd, out = s.out;
   const int co1 = r * H1, co2 = r * H2;
   const bool mirror = (s.flags & 1) != 0;   // also store the intermediates to global memory
+  const bool tc = (s.flags & 4) != 0;       // dense products on tensor-core tiles (mma.sync 3xTF32, tc_tiles.cuh)
   DRGNN_PHASE(0);
   float* xs = sm + P.xs;   float* ax = sm + P.ax;   float* z1 = sm + P.z1;   float* dz1 = sm + P.dz1;
   float* w1t = sm + P.w1t; float* w2t = sm + P.w2t; float* w2 = sm + P.w2;
@@ -423,6 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     n0 = __ldg(a.node_ptr + g); n = __ldg(a.node_ptr + g + 1) - n0;
     eg0 = __ldg(s.edge_ptr + g); m = __ldg(s.edge_ptr + g + 1) - eg0;
   }
+  DRGNN_PHASE(20);   // staging sub-phases 20..25 (diagnostic): extents known
   const bool train = !(s.forward_only || s.task == 0);
   float* part = s.partial + (int64_t)g * s.partial_ld;
   // loop-invariant global scalars of the head and this branch's weights, fetched while the copies fly
@@ -458,11 +460,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     s2_mbar_expect_tx(&bars[1], wbytes);
     s2_bulk_g2s(fc1w, s.fc1_w, wbytes, &bars[1]);
   }
+  DRGNN_PHASE(21);   // bulk copies issued
   // small head vectors (any alignment): cp.async
   s2_stage32(fc2w, s.fc2_w, out * Hd, t, T);
   if (s.fc1_b) s2_stage32(fc1b, s.fc1_b, Hd, t, T);
   if (s.fc2_b) s2_stage32(fc2b, s.fc2_b, out, t, T);
   s2_commit();
+  DRGNN_PHASE(22);   // head-vector copies issued
   // ---- this branch's weights, transposed through registers
 #pragma unroll 1
   for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. -> w1t [F][H1]
@@ -484,8 +488,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 #pragma unroll 1
     for (int i = t; i < out; i += T) fc2b[i] = 0.f;
   }
+  DRGNN_PHASE(23);               // weights transposed (this thread's share)
   __syncthreads();               // barrier initialisation visible to every thread
+  DRGNN_PHASE(24);
   s2_mbar_wait(&bars[0], 0);     // structure blob + feature tile have landed
+  DRGNN_PHASE(25);
   const int K = blb[2], E1 = blb[3], Q = blb[4];
   if (blb[5] != 1 || blb[0] != n || blb[1] != m || K > a.max_k || Q > a.max_q || K < 0 || Q < 0 || E1 < 0 || E1 > m) {
     s2_mbar_wait(&bars[1], 0);   // no bulk copy may be in flight into a CTA that exits
@@ -513,7 +520,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(2);
   // ---- Z1 = relu(AX W1_r^T)
-  s2_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, 1, t, T);
+  if (tc) tc_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, nullptr, 1, nullptr, 0, t, T);
+  else s2_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, 1, t, T);
   __syncthreads();
   DRGNN_PHASE(3);
   // ---- P1 = cluster max of Z1 (community_pooling.py:201)
@@ -525,7 +533,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(5);
   // ---- Z2 = relu(AP W2_r^T)
-  s2_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, 1, t, T);
+  if (tc) tc_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, nullptr, 1, nullptr, 0, t, T);
+  else s2_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, 1, t, T);
   __syncthreads();
   DRGNN_PHASE(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
@@ -697,8 +706,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   // ---- dW2_r = dZ2^T AP (split over the K0 rows, first half of the CTA)  ||  dAP = dZ2 W2_r (second half)
   const int KS2 = s2_split(P.xs_words, H2 * H1), KS1 = s2_split(P.xs_words, H1 * F);
   float* scratch = xs;   // the feature tile is dead since AX
-  if (t < (T >> 1)) s2_splitk_partial(dz2, LDZ2, ap, LDP, H2, H1, K, KS2, scratch, t, T >> 1);
-  else s2_gemm(dz2, LDZ2, w2, H1, K, H1, H2, dap, LDP, 0, t - (T >> 1), T >> 1);
+  if (tc) {
+    if (t < (T >> 1)) tc_splitk_partial(dz2, LDZ2, ap, LDP, H2, H1, K, KS2, scratch, t, T >> 1);
+    else tc_gemm(dz2, LDZ2, w2, H1, K, H1, H2, dap, LDP, nullptr, 0, nullptr, 0, t - (T >> 1), T >> 1);
+  } else {
+    if (t < (T >> 1)) s2_splitk_partial(dz2, LDZ2, ap, LDP, H2, H1, K, KS2, scratch, t, T >> 1);
+    else s2_gemm(dz2, LDZ2, w2, H1, K, H1, H2, dap, LDP, 0, t - (T >> 1), T >> 1);
+  }
   __syncthreads();
   DRGNN_PHASE(13);
   s2_splitk_reduce(scratch, H2 * H1, KS2, part + s.off_w2 + r * H2 * H1, t, T);
@@ -711,7 +725,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE(15);
   // ---- dW1_r [H1][F] = dZ1^T AX, split over the nodes
-  s2_splitk_partial(dz1, LDZ1, ax, LDX, H1, F, n, KS1, scratch, t, T);
+  if (tc) tc_splitk_partial(dz1, LDZ1, ax, LDX, H1, F, n, KS1, scratch, t, T);
+  else s2_splitk_partial(dz1, LDZ1, ax, LDX, H1, F, n, KS1, scratch, t, T);
   __syncthreads();
   s2_splitk_reduce(scratch, H1 * F, KS1, part + s.off_w1 + r * H1 * F, t, T);
   DRGNN_PHASE(16);

@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int co1 = br * H1, co2 = br * H2;
   const bool mirror = (s.flags & 1) != 0;
   const bool multi = NT > 1;             // rows distributed over the cluster: cluster barriers between phases
+  const bool tc = (s.flags & 4) != 0;    // dense products on the tensor cores (mma.sync 3xTF32) instead of FFMA tiles
   const bool staged = P.blob_words > 0;  // the graph's blob and feature tile are staged in shared memory
   DRGNN_PHASE3(0);
   float* xs = sm + P.xs;     float* scr = sm + P.scr;   float* zin1 = sm + P.zin1; float* z1 = sm + P.z1;
@@ -830,7 +831,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   s3_aggregate(kind, rp0, col0, ew0, s3_rows_flat(xsrc, F), F, lo0, hi0, zin1, LDZIN1, nullptr, nullptr, t, T);
   __syncthreads();
   DRGNN_PHASE3(2);
-  s3_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);
+  if (tc) tc_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);
+  else s3_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(3);
   // ---- P1 = cluster max of Z1 (community_pooling.py:201): members may live in any tile
@@ -841,13 +843,15 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   s3_aggregate(kind, rp1, col1, ew1, s3_rows(bp1, NT, kta, LDP), H1, lo1, hi1, zin2, LDZIN2, s1, post1, t, T);
   __syncthreads();
   DRGNN_PHASE3(5);
-  s3_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
+  if (tc) tc_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
+  else s3_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(6);
   if (L3) {   // third conv layer on the coarsened graph (BASELINE config 3: "sGAT 3-layer"), h2 -> h2
     s3_aggregate(kind, rp1, col1, ew1, s3_rows(bz2, NT, kta, LDZ2), H2, lo1, hi1, zin3, LDZIN3, nullptr, nullptr, t, T);
     __syncthreads();
-    s3_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
+    if (tc) tc_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
+    else s3_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
     if (multi) cluster.sync(); else __syncthreads();
   }
   float* zl = L3 ? z3 : z2;                                  // the last conv output: pooled, read out
@@ -1053,10 +1057,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     // dZ2 = relu'(Z2) * (s1 dzin3[:, :H2] + A1^T-weighted dzin3[:, H2:])  (in place on z2)
     const int M3 = 2 * H2 + 4, N3 = H2;
     const int KS3 = s3_split(P.scr_words, M3 * N3);
-    s3_splitk_partial(zin3, LDZIN3, z3, LDZ2, M3, N3, r1n, KS3, scr, t, T);
+    if (tc) tc_splitk_partial(zin3, LDZIN3, z3, LDZ2, M3, N3, r1n, KS3, scr, t, T);
+    else s3_splitk_partial(zin3, LDZIN3, z3, LDZ2, M3, N3, r1n, KS3, scr, t, T);
     __syncthreads();
     s3_splitk_reduce(scr, M3 * N3, KS3, wg, t, T);
-    s3_gemm(z3, LDZ2, w3t, 2 * H2, r1n, 2 * H2, H2, zin3, LDZIN3, nullptr, 0, post1, H2, t, T);
+    if (tc) tc_gemm(z3, LDZ2, w3t, 2 * H2, r1n, 2 * H2, H2, zin3, LDZIN3, nullptr, 0, post1, H2, t, T);
+    else s3_gemm(z3, LDZ2, w3t, 2 * H2, r1n, 2 * H2, H2, zin3, LDZIN3, nullptr, 0, post1, H2, t, T);
     if (multi) cluster.sync(); else __syncthreads();
     s3_cross_tile_store(bwg, NT, ti, M3, N3, 2 * H2, part + s.off_w3, part + s.off_b3, t, T);
     s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin3, NT, kta, LDZIN3), H2, zin3, LDZIN3, s1, H2, lo1, hi1, t3, LDZ2, t, T);
@@ -1075,12 +1081,18 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int M2 = kind == 0 ? H2 : Kin2 + 4, N2 = kind == 0 ? H1 : H2;
   const int M1 = kind == 0 ? H1 : Kin1 + 4, N1 = kind == 0 ? F : H1;
   const int KS2 = s3_split(P.scr_words, M2 * N2), KS1 = s3_split(P.scr_words, M1 * N1);
-  if (kind == 0) s3_splitk_partial(z2, LDZ2, zin2, LDZIN2, M2, N2, r1n, KS2, scr, t, T);
-  else s3_splitk_partial(zin2, LDZIN2, z2, LDZ2, M2, N2, r1n, KS2, scr, t, T);
+  if (tc) {
+    if (kind == 0) tc_splitk_partial(z2, LDZ2, zin2, LDZIN2, M2, N2, r1n, KS2, scr, t, T);
+    else tc_splitk_partial(zin2, LDZIN2, z2, LDZ2, M2, N2, r1n, KS2, scr, t, T);
+  } else {
+    if (kind == 0) s3_splitk_partial(z2, LDZ2, zin2, LDZIN2, M2, N2, r1n, KS2, scr, t, T);
+    else s3_splitk_partial(zin2, LDZIN2, z2, LDZ2, M2, N2, r1n, KS2, scr, t, T);
+  }
   __syncthreads();
   s3_splitk_reduce(scr, M2 * N2, KS2, wg, t, T);
   // ---- dzin2 = dZ2 W2 (GINet: [K][H1]) | dZ2 W^T ([K][2H1], aggregated half times post[row]) - over zin2
-  s3_gemm(z2, LDZ2, w2t, Kin2, r1n, Kin2, H2, dzin2, LDZIN2, nullptr, 0, kind ? post1 : nullptr, H1, t, T);
+  if (tc) tc_gemm(z2, LDZ2, w2t, Kin2, r1n, Kin2, H2, dzin2, LDZIN2, nullptr, 0, kind ? post1 : nullptr, H1, t, T);
+  else s3_gemm(z2, LDZ2, w2t, Kin2, r1n, Kin2, H2, dzin2, LDZIN2, nullptr, 0, kind ? post1 : nullptr, H1, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(12);
   if (kind == 0) s3_cross_tile_store(bwg, NT, ti, M2, N2, M2, part + s.off_w2 + br * H2 * H1, nullptr, t, T);
@@ -1094,8 +1106,13 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   __syncthreads();
   DRGNN_PHASE3(14);
   // ---- conv1 weight (+ bias) gradient
-  if (kind == 0) s3_splitk_partial(z1, LDZ1, zin1, LDZIN1, M1, N1, r0n, KS1, scr, t, T);
-  else s3_splitk_partial(zin1, LDZIN1, z1, LDZ1, M1, N1, r0n, KS1, scr, t, T);
+  if (tc) {
+    if (kind == 0) tc_splitk_partial(z1, LDZ1, zin1, LDZIN1, M1, N1, r0n, KS1, scr, t, T);
+    else tc_splitk_partial(zin1, LDZIN1, z1, LDZ1, M1, N1, r0n, KS1, scr, t, T);
+  } else {
+    if (kind == 0) s3_splitk_partial(z1, LDZ1, zin1, LDZIN1, M1, N1, r0n, KS1, scr, t, T);
+    else s3_splitk_partial(zin1, LDZIN1, z1, LDZ1, M1, N1, r0n, KS1, scr, t, T);
+  }
   __syncthreads();
   s3_splitk_reduce(scr, M1 * N1, KS1, wg, t, T);
   if (multi) cluster.sync(); else __syncthreads();

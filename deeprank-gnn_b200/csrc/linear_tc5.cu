@@ -83,6 +83,27 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// TMEM -> registers: this warp's 32 lanes x 16 / 32 consecutive columns (one row of the accumulator per thread)
+__device__ __forceinline__ void tc_ld16(uint32_t (&v)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t (&v)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 __host__ __device__ inline int tc_a_region_words(int Fin, int Fout) {
   const int a = 2 * TC_BM * Fin, y = TC_BM * Fout;
   return a > y ? a : y;
@@ -95,7 +116,7 @@ __device__ __forceinline__ int tc_chunk_word(int row, int kchunk, int rows8) {
 }
 
 // diagnostic: cycles CTA 0 / thread 0 spent per phase, summed over its tiles (drgnn_debug_tc5_cycles):
-// [0] split + store A, [1] fence + barrier + MMA issue, [2] prefetch issue, [3] wait for the MMAs, [4] TMEM read + output stores,
+// [0] split + store A, [1] fence + barrier + MMA issue, [2] prefetch issue, [3] wait for the MMAs, [7] TMEM read-back + staging, [4] output stores,
 // [5] closing barrier, [6] tiles
 __device__ unsigned long long g_tc5_phase[8];
 #define TC5_T(i)                                                           \
@@ -219,24 +240,33 @@ __global__ void __launch_bounds__(TC_THREADS, 3) linear_tcgen05_kernel(const drg
     // banks evenly (4 wavefronts per 512-byte store, the minimum), and step (b) reads rows back conflict-free.
     float* Ys = Ahi;
     const int FC = Fout >> 2;                                         // 16-byte chunks per output row (4, 8 or 16)
-    for (int c0 = 0; c0 < Fout; c0 += 16) {
-      uint32_t v[16];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr)
-          : "memory");
+    {
+      // every TMEM load of the tile is issued before the single wait (their latencies overlap)
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+      if (Fout >= 32) tc_ld32(v0, taddr); else tc_ld16(v0, taddr);
+      if (Fout == 64) tc_ld32(v1, taddr + 32u);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n0 = Fout >= 32 ? 32 : 16;
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const int ch = ((c0 + j) >> 2) ^ (t & (FC - 1));
-        *reinterpret_cast<float4*>(Ys + t * Fout + ch * 4) =
-            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      for (int j = 0; j < 32; j += 4) {
+        if (j < n0) {
+          const int ch = (j >> 2) ^ (t & (FC - 1));
+          *reinterpret_cast<float4*>(Ys + t * Fout + ch * 4) =
+              make_float4(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]), __uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3]));
+        }
+      }
+      if (Fout == 64) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int ch = ((32 + j) >> 2) ^ (t & (FC - 1));
+          *reinterpret_cast<float4*>(Ys + t * Fout + ch * 4) =
+              make_float4(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1]), __uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3]));
+        }
       }
     }
     __syncthreads();
+    TC5_T(7);
     // (b) shared memory -> global memory, coalesced: consecutive threads store consecutive 16-byte chunks of a row
     // (a warp writes whole 128-byte lines), bias / ReLU / mask applied on the way
     for (int c = t; c < TC_BM * FC; c += TC_THREADS) {

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 namespace drgnn {
+#include "tc_tiles.cuh"
 #include "fused_step3.cuh"
 }  // namespace drgnn
 
@@ -182,6 +183,7 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   cfg.numAttrs = 1;
   drgnn_net_step_args k = *s;
   k.tiles = tiles;
+  if (s->F % 8 || s->h1 % 8 || s->h2 % 8) k.flags &= ~4;      // the tensor-core tiles need widths that are multiples of 8
   DRGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, net_graph_step3_kernel, k, plan, comm));
   g_step3_tiles = tiles;
   g_step3_launches = 1;

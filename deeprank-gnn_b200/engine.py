@@ -323,6 +323,9 @@ class Engine(object):
         # the CTA-pair kernel (node dimension tiled over the cluster, neighbours through distributed shared memory)
         self.step3 = os.environ.get('DRGNN_STEP3', '1') != '0'
         self.step3_tiles = int(os.environ.get('DRGNN_STEP3_TILES', '0'))      # 0: smallest tile count that fits
+        # dense products of the fused step on the tensor cores (mma.sync 3xTF32, error ~1e-6) instead of FFMA tiles;
+        # opt-in: measured slower than the FFMA register tiles at every BASELINE config (profiles/README.md, round 2)
+        self.fused_tc = os.environ.get('DRGNN_FUSED_TC', '0') != '0'
         self._last_path = None
         self.seed = 0x5EED if seed is None else int(seed)
         if self.world > 1:
@@ -647,7 +650,7 @@ class Engine(object):
                                max_e=d.max_e, mirror=self.keep_intermediates,
                                variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
                                blob=st.blob, gdesc=st.gstat if st.blob_only else None,
-                               edge_ptr=d.edge_ptr)
+                               edge_ptr=d.edge_ptr, tc=self.fused_tc)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._all_done_kernel = True
                 self._adam_done = fuse_adam
@@ -746,7 +749,7 @@ class Engine(object):
                      adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
                                beta2=self.betas[1], eps=self.eps) if (fuse_adam or in_kernel) else None,
                      skip_reduce=use_comm and not in_kernel, fuse_reduce=self.fuse_reduce,
-                     comm=self.comm if in_kernel else None, mirror=mirror)
+                     comm=self.comm if in_kernel else None, mirror=mirror, tc=self.fused_tc)
         self._last_path = 'step3'
         self._graph_done = self._head_done = self._all_done = train_step
         self._all_done_kernel = True

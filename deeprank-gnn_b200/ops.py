@@ -518,7 +518,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
                drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
-               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None):
+               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None, tc=False):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -552,7 +552,8 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     s.comm = C.addressof(comm.struct) if comm is not None else None
     require_cuda(gdesc)
     s.gdesc = ptr(gdesc)          # per-graph extents of a blob-only structure pass (Structure.gstat)
-    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2), int(variant)
+    # flags: bit 0 mirror the intermediates, bit 1 no in-kernel reduction, bit 2 dense products on mma.sync 3xTF32 tiles
+    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2) | (4 if tc else 0), int(variant)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the
     # in-kernel reduction (grid barrier) launch only the per-graph kernel
@@ -623,7 +624,7 @@ def net_step_max_clusters(kind, tiles, smem_bytes):
 def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, max_k, max_q, pred, node_ptr, edge_ptr,
              tiles=0, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None, keep_scale=1.0, drop_p=0.0,
              seed=0, loss=None, R=None, partial=None, grads=None, n_params=0, forward_only=False, step_dev=None, adam=None,
-             skip_reduce=False, fuse_reduce=True, comm=None, mirror=None):
+             skip_reduce=False, fuse_reduce=True, comm=None, mirror=None, tc=False):
     """Whole step of every graph in one launch for GINet / sGAT / FoutNet (``drgnn_net_step``, the general
     cluster kernel).  ``st``: the ``Structure`` of the batch (blob, + wblob for sGAT); ``offsets``: dict of the
     tensor offsets inside the flat parameter buffer (w1, b1, w2, b2, fc1w, fc1b, fc2w, fc2b; b1 / b2 None for
@@ -664,7 +665,7 @@ def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, 
     s.step_dev = ptr(step_dev)
     s.status = ptr(st.status)
     s.comm = C.addressof(comm.struct) if comm is not None else None
-    s.flags = (0 if fuse_reduce else 2)
+    s.flags = (0 if fuse_reduce else 2) | (4 if tc else 0)      # bit 2: dense products on mma.sync 3xTF32 tiles
     if mirror is not None:
         require_cuda(*mirror.values())
         s.flags |= 1

@@ -395,7 +395,9 @@ typedef struct drgnn_ginet_step_args {
   /* flags bit 0: the cluster kernel also mirrors the intermediates (Zin1, Z1, arg0, Zin2, Z2, arg1)
    * to global memory (it keeps them in shared memory; the single-CTA kernel always stores them);
    * bit 1: never fuse the gradient reduction into the cluster kernel (step_dev must be [4] floats,
-   * zero-initialised: [2] is the grid-barrier counter of the fused reduction) */
+   * zero-initialised: [2] is the grid-barrier counter of the fused reduction);
+   * bit 2 (cluster kernel): the dense products run on tensor-core tiles (mma.sync.m16n8k8 TF32 with the 3-product
+   * error compensation, ~1e-6; widths must be multiples of 8, else the fp32 FMA tiles are used) */
   int32_t flags;
   /* max_e: host bound of the directed edges of one graph (> 0 enables the cluster kernel: a pair of
    * CTAs per graph, one GINet branch each, nb == 2).  variant: 0 = pick (cluster kernel when it
@@ -473,7 +475,9 @@ int drgnn_debug_structure_cycles(uint64_t* out32);
  *     graph's loss term; rows must be ZERO in slots no live parameter owns.  task / inv_norm / keep / drop_p /
  *     fuse_adam / skip_reduce / comm / step_dev as in drgnn_ginet_step_args.  flags bit 0: mirror the
  *     intermediates to Zin1 [N,Kin1] Z1 [N,nbr*h1] arg0 Zin2 Z2 arg1 (needs kptr0 / kptr1 of
- *     drgnn_structure_build); bit 1: never fuse the gradient reduction.  R (optional): read-out rows [B, nbr*h2].
+ *     drgnn_structure_build); bit 1: never fuse the gradient reduction; bit 2: the dense products (conv transforms,
+ *     their input and weight gradients) run on tensor-core tiles (mma.sync.m16n8k8 TF32, 3-product error compensation,
+ *     ~1e-6) instead of fp32 FMA register tiles.  R (optional): read-out rows [B, nbr*h2].
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_net_step_args {
   int32_t kind; int32_t B; int32_t F; int32_t h1; int32_t h2; int32_t Hd; int32_t out;

@@ -230,6 +230,7 @@ def test_fused_per_graph_kernels_equal_op_by_op_path(lib, fused_head, variant):
     e_o = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_graph=False, fused_head=False)
     e_f = Engine('GINet', 32, 1, 1, device='cuda:0', seed=5, dropout=0.0, fused_head=fused_head)
     e_f.step_variant, e_f.keep_intermediates = variant, True
+    e_f.fused_tc = False                  # fp32 FMA tiles: the intermediates are then bit-identical to the op-level kernels
     assert e_f._use_fused_graph(d) and not e_o._use_fused_graph(d)
     for step in range(3):
         lo, po = e_o.step(d)
@@ -481,3 +482,27 @@ def test_native_feed_scoring_equals_python_pipeline(lib):
     for x, y in zip(pa, pb_):
         assert torch.equal(x, y)
     assert torch.equal(ea.params.data, w0) and float(ea.step_dev[0]) == 0.0
+
+
+def test_cluster_step_kernel_tensor_core_tiles_match_fma_tiles(lib):
+    """The dense products of the cluster kernel on mma.sync 3xTF32 tiles (opt-in) against the fp32 FMA register tiles:
+    same predictions, loss and gradients to 1e-5, several optimiser steps stay together."""
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs(dict(nodes=(20, 200), edges_per_node=5, feat=32), count=24, seed=9)
+    d = _device_batch(graphs)
+    ea = Engine('GINet', 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=0.0)
+    eb = Engine('GINet', 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=0.0)
+    ea.step_variant = eb.step_variant = 2
+    ea.fused_tc, eb.fused_tc = True, False
+    for step in range(4):
+        la, pa = ea.step(d)
+        lb, pb = eb.step(d)
+        assert ops.ginet_step_last_variant() == 2
+        ea.validate(), eb.validate()
+        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
+        if step == 0:
+            for name, g in ea.named_grads().items():
+                torch.testing.assert_close(g, eb.named_grads()[name], rtol=1e-4, atol=1e-5, msg=name)
+    torch.testing.assert_close(ea.params.data, eb.params.data, rtol=1e-3, atol=1e-5)

@@ -39,6 +39,8 @@ def test_step3_intermediates_and_gradients_equal_op_level_path(lib, net, tiles):
     d = _device_batch(graphs)
     e_o, e_f = _pair(net, tiles=tiles)
     e_f.keep_intermediates = True
+    e_f.fused_tc = tiles != 1             # 1 tile: fp32 FMA tiles (bit-identical to the op-level kernels for GINet);
+                                          # 2 / 4 tiles: the tensor-core (3xTF32) products
     for step in range(3):
         lo, po = e_o.step(d)
         lf, pf = e_f.step(d)
@@ -53,11 +55,12 @@ def test_step3_intermediates_and_gradients_equal_op_level_path(lib, net, tiles):
                 if exact:
                     assert torch.equal(a, b), name
                 else:
-                    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, equal_nan=True, msg=name)
+                    tol = dict(rtol=3e-5, atol=1e-5) if e_f.fused_tc else dict(rtol=1e-5, atol=1e-6)
+                    torch.testing.assert_close(a, b, equal_nan=True, msg=name, **tol)
             for name, rows in (('arg0', K0), ('arg1', K1)):
                 a, b = getattr(e_f.ws, name)[:rows], getattr(e_o.ws, name)[:rows]
                 same = float((a == b).float().mean())
-                assert same == 1.0 if exact else same > 0.999, '%s: %.5f equal' % (name, same)
+                assert same == 1.0 if exact else same > 0.995, '%s: %.5f equal' % (name, same)
             torch.testing.assert_close(e_f.ws.R[:d.B], e_o.ws.R[:d.B], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(pf, po, rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(lf, lo, rtol=1e-4, atol=1e-6)

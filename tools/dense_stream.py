@@ -52,7 +52,8 @@ def main():
         _lib.check(_lib.load().drgnn_debug_tc5_cycles(ph), 'tc5 cycles')
         tiles = max(int(ph[6]), 1)
         out['tc5_cycles_per_tile_cta0'] = {k: round(ph[i] / tiles) for i, k in enumerate(
-            ['split_store', 'fence_bar_issue', 'prefetch_issue', 'mma_wait', 'tmem_ld_store', 'closing_barrier'])}
+            ['split_store', 'fence_bar_issue', 'prefetch_issue', 'mma_wait', 'global_stores', 'closing_barrier'])}
+        out['tc5_cycles_per_tile_cta0']['tmem_ld_stage'] = round(ph[7] / tiles)
     print(json.dumps(out))
 
 

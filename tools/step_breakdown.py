@@ -60,6 +60,11 @@ def main():
             tot = ph[16] - ph[0]
             print('graph-step kernel, CTA of graph 0: %d cycles total' % tot)
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(names)))
+            if ph[25] > ph[0]:
+                print('  staging split: extents %d | bulk issue %d | head vectors %d | weight transposes %d | CTA barrier %d | '
+                      'wait for blob + features %d | header check + cluster arrive %d'
+                      % (ph[20] - ph[0], ph[21] - ph[20], ph[22] - ph[21], ph[23] - ph[22], ph[24] - ph[23],
+                         ph[25] - ph[24], ph[1] - ph[25]))
             if ph[18] > ph[16]:
                 print('  in-kernel reduction: grid barrier %d | reduce + Adam %d' % (ph[17] - ph[16], ph[18] - ph[17]))
             if eng._last_path == 'step3':
