@@ -50,6 +50,8 @@ class StructureIO(C.Structure):
         ('counts', VP), ('status', VP),
         ('gstat', VP), ('scratch_n', VP), ('scratch_e', VP), ('scratch_f', VP),
         ('blob', VP), ('wblob', VP),
+        ('x', VP), ('zin1', VP), ('F', C.c_int32), ('ld_zin1', C.c_int32), ('zin_kind', C.c_int32),
+        ('launch_flags', C.c_int32),
     ]
 
 
@@ -132,7 +134,7 @@ class GinetStepArgs(C.Structure):
         ('fuse_adam', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
         ('adam_p', VP), ('adam_m', VP), ('adam_v', VP), ('step_dev', VP),
         ('skip_reduce', C.c_int32), ('flags', C.c_int32), ('max_e', C.c_int32), ('variant', C.c_int32),
-        ('blob', VP), ('edge_ptr', VP), ('comm', VP), ('gdesc', VP),
+        ('blob', VP), ('edge_ptr', VP), ('comm', VP), ('gdesc', VP), ('zin1', VP),
     ]
 
 
@@ -162,6 +164,7 @@ class NetStepArgs(C.Structure):
         ('kptr0', VP), ('kptr1', VP),
         ('Zin1', VP), ('Z1', VP), ('arg0', VP), ('Zin2', VP), ('Z2', VP), ('arg1', VP),
         ('layers3', C.c_int32), ('off_w3', C.c_int32), ('off_b3', C.c_int32), ('reserved3', C.c_int32),
+        ('zin1', VP),
     ]
 
 

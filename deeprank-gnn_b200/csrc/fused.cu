@@ -808,6 +808,7 @@ extern "C" int drgnn_ginet_step(const drgnn_ginet_step_args* s, void* stream) {
         comm = *c;
       }
     }
+    DRGNN_REQUIRE(((uintptr_t)s->zin1 % 16) == 0, "ginet_step: zin1 must be 16-byte aligned");
     drgnn_ginet_step_args k2 = *s;
     if (a->F % 8 || a->h1 % 8 || a->h2 % 8) k2.flags &= ~4;   // the tensor-core tiles need widths that are multiples of 8
     ginet_graph_step2_kernel<<<G, S2_THREADS, smem2, st>>>(k2, plan, comm);

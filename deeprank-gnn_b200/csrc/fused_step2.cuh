@@ -390,17 +390,28 @@ __host__ __device__ inline int s2_split(int cap_words, int mn) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     ginet_graph_step2_kernel(const drgnn_ginet_step_args s, const Step2Plan P, const drgnn_peer_comm C) {
   extern __shared__ __align__(16) float sm[];
+  // A structure pass launched behind this kernel as its programmatic dependent (drgnn_structure_io.launch_flags bit 0)
+  // may start now: every CTA of this grid is resident by the time all of them have passed this point, so the
+  // dependent's CTAs fill the SMs this grid leaves free instead of racing it for SMs (no-op without a dependent).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   cgx::cluster_group cluster = cgx::this_cluster();
   const drgnn_ginet_fused_args& a = s.g;
   const int r = (int)cluster.block_rank();   // branch of this CTA
   const int g = blockIdx.x >> 1;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // phase clocks of block 0 (diagnostic, flag bit 3): their global stores delay the release fences of block 0, and
+  // the whole grid waits for block 0 at the grid barrier, so they are off unless asked for
+  const bool timers = (s.flags & 8) != 0 && blockIdx.x == 0 && t == 0;
+#define S2_PHASE(i)                                                  \
+  do {                                                               \
+    if (timers) g_phase[i] = (unsigned long long)clock64();          \
+  } while (0)
   constexpr int T = S2_THREADS, NW = S2_THREADS / 32;
   const int F = a.F, H1 = a.h1, H2 = a.h2, C1 = 2 * H1, C2 = 2 * H2, Hd = s.Hd, out = s.out;
   const int co1 = r * H1, co2 = r * H2;
   const bool mirror = (s.flags & 1) != 0;   // also store the intermediates to global memory
   const bool tc = (s.flags & 4) != 0;       // dense products on tensor-core tiles (mma.sync 3xTF32, tc_tiles.cuh)
-  DRGNN_PHASE(0);
+  S2_PHASE(0);
   float* xs = sm + P.xs;   float* ax = sm + P.ax;   float* z1 = sm + P.z1;   float* dz1 = sm + P.dz1;
   float* w1t = sm + P.w1t; float* w2t = sm + P.w2t; float* w2 = sm + P.w2;
   float* p1 = sm + P.p1;   float* ap = sm + P.ap;   float* z2 = sm + P.z2;   float* p2 = sm + P.p2;
@@ -414,6 +425,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ism + P.bars);
   const int LDX = P.ldx, LDZ1 = P.ldz1, LDP = P.ldp, LDZ2 = P.ldz2;
 
+  // ---- this branch's conv weights, requested before anything else (they do not depend on the graph): 4-byte
+  // asynchronous copies whose DESTINATION address does the transposition, so no register, no dependent store and
+  // ONE L2 round trip that overlaps the extent loads and the bulk-copy issue below (first commit group)
+#pragma unroll 1
+  for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. (contiguous) -> w1t [F][H1]
+    const int c = i / F, f = i - c * F;
+    s2_cp4(w1t + f * H1 + c, a.W1 + (int64_t)co1 * F + i);
+  }
+#pragma unroll 1
+  for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] group r -> w2 [H2][H1], w2t [H1][H2]
+    const int o = i / H1, j = i - o * H1;
+    const float* src = a.W2 + (int64_t)r * H2 * H1 + i;
+    s2_cp4(w2 + i, src);
+    s2_cp4(w2t + j * H2 + o, src);
+  }
+  s2_commit();
   // ---- graph extents: ONE level of tiny loads (host-built pointers), then three bulk copies
   int n0, n, eg0, m;
   if (s.gdesc) {   // the record the structure pass left in L2 a moment ago: [K0, E1, K1, n0 | e0, m, 0, n]
@@ -424,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     n0 = __ldg(a.node_ptr + g); n = __ldg(a.node_ptr + g + 1) - n0;
     eg0 = __ldg(s.edge_ptr + g); m = __ldg(s.edge_ptr + g + 1) - eg0;
   }
-  DRGNN_PHASE(20);   // staging sub-phases 20..25 (diagnostic): extents known
+  S2_PHASE(20);   // staging sub-phases 20..25 (diagnostic): extents known
   const bool train = !(s.forward_only || s.task == 0);
   float* part = s.partial + (int64_t)g * s.partial_ld;
   // loop-invariant global scalars of the head and this branch's weights, fetched while the copies fly
@@ -441,6 +468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   // for the next launch.  Both CTAs of a cluster see the same extents and take the same path.
   do {
   if (n < 0 || m < 0 || n > a.max_n || m > s.max_e) {   // host bounds violated: flag, contribute nothing (validate())
+    s2_wait<0>();                                         // the weight copies issued above
     if (t == 0) atomicOr(a.status, 64);
     if (train && r == 0) {
 #pragma unroll 1
@@ -451,35 +479,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   if (t == 0) {
     s2_mbar_init(&bars[0], 1);
     s2_mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bbytes = (uint32_t)DRGNN_BLOB_USED(n, m) * 4u, xbytes = (uint32_t)(n * F) * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the initialised barriers, seen by the async proxy
+    // the feature tile - or, when the structure pass left AX = A x ready (s.zin1, row stride LDX), those rows
+    const uint32_t bbytes = (uint32_t)DRGNN_BLOB_USED(n, m) * 4u, xbytes = (uint32_t)(n * (s.zin1 ? LDX : F)) * 4u;
     s2_mbar_expect_tx(&bars[0], bbytes + xbytes);
     s2_bulk_g2s(blb, s.blob + DRGNN_BLOB_OFFSET(g, n0, eg0), bbytes, &bars[0]);
-    if (xbytes) s2_bulk_g2s(xs, a.x + (int64_t)n0 * F, xbytes, &bars[0]);
+    if (xbytes) {
+      if (s.zin1) s2_bulk_g2s(ax, s.zin1 + (int64_t)n0 * LDX, xbytes, &bars[0]);
+      else s2_bulk_g2s(xs, a.x + (int64_t)n0 * F, xbytes, &bars[0]);
+    }
     const uint32_t wbytes = (uint32_t)(Hd * C2) * 4u;
     s2_mbar_expect_tx(&bars[1], wbytes);
     s2_bulk_g2s(fc1w, s.fc1_w, wbytes, &bars[1]);
   }
-  DRGNN_PHASE(21);   // bulk copies issued
+  S2_PHASE(21);   // bulk copies issued
   // small head vectors (any alignment): cp.async
   s2_stage32(fc2w, s.fc2_w, out * Hd, t, T);
   if (s.fc1_b) s2_stage32(fc1b, s.fc1_b, Hd, t, T);
   if (s.fc2_b) s2_stage32(fc2b, s.fc2_b, out, t, T);
   s2_commit();
-  DRGNN_PHASE(22);   // head-vector copies issued
-  // ---- this branch's weights, transposed through registers
-#pragma unroll 1
-  for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. -> w1t [F][H1]
-    const int c = i / F, f = i - c * F;
-    w1t[f * H1 + c] = __ldg(a.W1 + (int64_t)(co1 + c) * F + f);
-  }
-#pragma unroll 1
-  for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] group r -> w2 [H2][H1], w2t [H1][H2]
-    const int o = i / H1, j = i - o * H1;
-    const float v = __ldg(a.W2 + (int64_t)r * H2 * H1 + i);
-    w2[i] = v;
-    w2t[j * H2 + o] = v;
-  }
+  S2_PHASE(22);   // head-vector copies issued
   if (!s.fc1_b) {
 #pragma unroll 1
     for (int i = t; i < Hd; i += T) fc1b[i] = 0.f;
@@ -488,11 +507,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 #pragma unroll 1
     for (int i = t; i < out; i += T) fc2b[i] = 0.f;
   }
-  DRGNN_PHASE(23);               // weights transposed (this thread's share)
-  __syncthreads();               // barrier initialisation visible to every thread
-  DRGNN_PHASE(24);
+  s2_wait<1>();                  // this thread's conv-weight copies (the head vectors may still be in flight)
+  S2_PHASE(23);
+  __syncthreads();               // everybody's conv weights; barrier initialisation visible to every thread
+  S2_PHASE(24);
   s2_mbar_wait(&bars[0], 0);     // structure blob + feature tile have landed
-  DRGNN_PHASE(25);
+  S2_PHASE(25);
   const int K = blb[2], E1 = blb[3], Q = blb[4];
   if (blb[5] != 1 || blb[0] != n || blb[1] != m || K > a.max_k || Q > a.max_q || K < 0 || Q < 0 || E1 < 0 || E1 > m) {
     s2_mbar_wait(&bars[1], 0);   // no bulk copy may be in flight into a CTA that exits
@@ -512,35 +532,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   // The peer CTA must be running before its shared memory is written (read-out exchange below):
   // arrive now, wait just before the exchange, so the barrier costs nothing.
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  DRGNN_PHASE(1);
+  S2_PHASE(1);
 
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;
   // ---- AX = A x : the F/4 lanes of a row share its edge list and read whole 16-byte-aligned feature rows
-  s2_gather(rp0, col0, 0, 0, xs, F, ax, LDX, n, F4, t, T);
-  __syncthreads();
-  DRGNN_PHASE(2);
+  if (!s.zin1) {
+    s2_gather(rp0, col0, 0, 0, xs, F, ax, LDX, n, F4, t, T);
+    __syncthreads();
+  }
+  S2_PHASE(2);
   // ---- Z1 = relu(AX W1_r^T)
   if (tc) tc_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, nullptr, 1, nullptr, 0, t, T);
   else s2_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, 1, t, T);
   __syncthreads();
-  DRGNN_PHASE(3);
+  S2_PHASE(3);
+  if (s.flags & 16) {   // diagnostic: the same product once more (warm instruction cache, same data) - clocks 26 / 27
+    S2_PHASE(26);
+    if (tc) tc_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, nullptr, 1, nullptr, 0, t, T);
+    else s2_gemm(ax, LDX, w1t, H1, n, H1, F, z1, LDZ1, 1, t, T);
+    __syncthreads();
+    S2_PHASE(27);
+    if (!s.zin1) s2_gather(rp0, col0, 0, 0, xs, F, ax, LDX, n, F4, t, T);
+    __syncthreads();
+    S2_PHASE(28);
+  }
   // ---- P1 = cluster max of Z1 (community_pooling.py:201)
   s2_cluster_max(cmp0, cmem0, 0, 0, z1, LDZ1, p1, LDP, arg0, H1, K, H14, t, T);
   __syncthreads();
-  DRGNN_PHASE(4);
+  S2_PHASE(4);
   // ---- AP = A1 P1 on the coarsened graph
   s2_gather(rp1, col1, 0, 0, p1, LDP, ap, LDP, K, H14, t, T);
   __syncthreads();
-  DRGNN_PHASE(5);
+  S2_PHASE(5);
   // ---- Z2 = relu(AP W2_r^T)
   if (tc) tc_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, nullptr, 1, nullptr, 0, t, T);
   else s2_gemm(ap, LDP, w2t, H2, K, H2, H1, z2, LDZ2, 1, t, T);
   __syncthreads();
-  DRGNN_PHASE(6);
+  S2_PHASE(6);
   // ---- P2 = level-1 cluster max (max_pool_x)
   s2_cluster_max(cmp1, cmem1, 0, 0, z2, LDZ2, p2, H2, arg1, H2, Q, H24, t, T);
   __syncthreads();
-  DRGNN_PHASE(7);
+  S2_PHASE(7);
   if (mirror) {   // parity tests: the intermediates the single-CTA kernel leaves in global memory (global ids)
     const int k0 = __ldg(a.kptr0 + g), q0 = __ldg(a.kptr1 + g);
     if (r == 0) s2_mirror(ax, LDX, a.Zin1 + (int64_t)n0 * F, F, n, F4, 0, t, T);
@@ -567,7 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   s2_wait<0>();                // small head vectors (this thread's copies) ...
   s2_mbar_wait(&bars[1], 0);   // ... and fc1.weight have landed
   cluster.sync();              // everybody's copies, and the peer's half of the read-out row
-  DRGNN_PHASE(8);
+  S2_PHASE(8);
   // ---- fc1 (both CTAs, identical results): four lanes per hidden unit, each a quarter of the read-out
   // channels as 16-byte loads, two shuffles to combine
   {
@@ -597,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     }
   }
   __syncthreads();
-  DRGNN_PHASE(9);
+  S2_PHASE(9);
   // ---- fc2: warp per output
 #pragma unroll 1
   for (int o = warp; o < out; o += NW) {
@@ -612,7 +644,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     }
   }
   __syncthreads();
-  DRGNN_PHASE(10);
+  S2_PHASE(10);
   if (!train) return;
   // ---- loss term of this graph and dLoss/dpred (one thread per CTA, identical results)
   if (t == 0) {
@@ -698,11 +730,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     drrow[c] = acc;
   }
   __syncthreads();
-  DRGNN_PHASE(11);
+  S2_PHASE(11);
   // ---- dZ2: read-out mean backward, routed to the arg-max member, gated by ReLU
   s2_route(cl1, 0, arg1, H2, z2, LDZ2, drrow, 0, 1.f / (float)max(Q, 1), dz2, LDZ2, K, H24, 0, t, T);
   __syncthreads();
-  DRGNN_PHASE(12);
+  S2_PHASE(12);
   // ---- dW2_r = dZ2^T AP (split over the K0 rows, first half of the CTA)  ||  dAP = dZ2 W2_r (second half)
   const int KS2 = s2_split(P.xs_words, H2 * H1), KS1 = s2_split(P.xs_words, H1 * F);
   float* scratch = xs;   // the feature tile is dead since AX
@@ -714,22 +746,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     else s2_gemm(dz2, LDZ2, w2, H1, K, H1, H2, dap, LDP, 0, t - (T >> 1), T >> 1);
   }
   __syncthreads();
-  DRGNN_PHASE(13);
+  S2_PHASE(13);
   s2_splitk_reduce(scratch, H2 * H1, KS2, part + s.off_w2 + r * H2 * H1, t, T);
   // ---- dP1 = A1^T dAP  (CSC of the coarsened graph)
   s2_gather(cscp1, cscr1, 0, 0, dap, LDP, dp1, LDP, K, H14, t, T);
   __syncthreads();
-  DRGNN_PHASE(14);
+  S2_PHASE(14);
   // ---- dZ1: routed to the arg-max node of its cluster, gated by ReLU
   s2_route(cl0, 0, arg0, H1, z1, LDZ1, dp1, LDP, 1.f, dz1, LDZ1, n, H14, 0, t, T);
   __syncthreads();
-  DRGNN_PHASE(15);
+  S2_PHASE(15);
   // ---- dW1_r [H1][F] = dZ1^T AX, split over the nodes
   if (tc) tc_splitk_partial(dz1, LDZ1, ax, LDX, H1, F, n, KS1, scratch, t, T);
   else s2_splitk_partial(dz1, LDZ1, ax, LDX, H1, F, n, KS1, scratch, t, T);
   __syncthreads();
   s2_splitk_reduce(scratch, H1 * F, KS1, part + s.off_w1 + r * H1 * F, t, T);
-  DRGNN_PHASE(16);
+  S2_PHASE(16);
   } while (0);
   if (!P.fused_reduce || !train) return;
   // ---- gradient reduction (+ Adam) inside this launch: the grid is co-resident (2B <= SMs, one CTA
@@ -761,7 +793,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     __threadfence();
   }
   __syncthreads();
-  DRGNN_PHASE(17);
+  S2_PHASE(17);
   {
     const int n = s.n_params, B = a.B;
     const int per = (n + 1 + (int)gridDim.x - 1) / (int)gridDim.x;   // elements of this CTA, 128 per sweep
@@ -893,7 +925,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       }
     }
   }
-  DRGNN_PHASE(18);
+  S2_PHASE(18);
 }
 
 static inline bool step2_shapes_ok(const drgnn_ginet_step_args& s) {

@@ -34,12 +34,17 @@ static constexpr int S3_MAX_TILES = 8;
 static constexpr int S3_MAX_KS = 16;
 
 __device__ unsigned long long g_phase3[32];
+// (flag bit 3 of the launch enables the clocks: their global stores delay the release fences of block 0, and the
+// whole grid waits for block 0 at the grid barrier)
 #define DRGNN_PHASE3(i)                                                                       \
   do {                                                                                        \
-    if (blockIdx.x == 0 && threadIdx.x == 0) g_phase3[i] = (unsigned long long)clock64();     \
+    if (timers) g_phase3[i] = (unsigned long long)clock64();                                  \
   } while (0)
 
 __device__ __forceinline__ uint32_t s3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s3_cp4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s3_smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void s3_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_smem_u32(bar)), "r"(count));
 }
@@ -661,13 +666,42 @@ __host__ __device__ inline int s3_split(int cap_words, int mn) {
 __global__ void __launch_bounds__(S3_THREADS, 1)
     net_graph_step3_kernel(const drgnn_net_step_args s, const Step3Plan P, const drgnn_peer_comm C) {
   extern __shared__ __align__(16) float sm[];
+  // a structure pass launched as the programmatic dependent of this grid may start once every CTA is resident
+  // (see ginet_graph_step2_kernel)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   cgx::cluster_group cluster = cgx::this_cluster();
   const int kind = s.kind;
   const int NT = P.tiles, CS = P.cs;
   const int r = (int)cluster.block_rank();
   const int br = r / NT, ti = r - br * NT;      // branch (GINet), node tile
-  const int g = blockIdx.x / CS;
+  int g = blockIdx.x / CS;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if ((s.flags & 32) && s.B + 4 <= P.scr_words) {
+    // Largest graph first (flag bit 5; grids larger than the device): cluster c takes the graph of size rank c, so
+    // the clusters scheduled last - when SMs free up - run the smallest graphs and the tail of the launch is short
+    // (longest-processing-time order; mixed sizes, BASELINE config 5).  Every CTA ranks the B node counts itself
+    // (one coalesced load of node_ptr, B^2 / T shared-memory compares): no extra launch, no host-side permutation.
+    int* sz = reinterpret_cast<int*>(sm + P.scr);
+    const int B = s.B, cid = g;
+#pragma unroll 1
+    for (int i = t; i < B; i += S3_THREADS) sz[i] = __ldg(s.node_ptr + i + 1) - __ldg(s.node_ptr + i);
+    __syncthreads();
+#pragma unroll 1
+    for (int i = t; i < B; i += S3_THREADS) {
+      const int ni = sz[i];
+      int rank = 0;
+#pragma unroll 4
+      for (int h = 0; h < B; ++h) {
+        const int nh = sz[h];
+        rank += (nh > ni || (nh == ni && h < i)) ? 1 : 0;
+      }
+      if (rank == cid) sz[B] = i;
+    }
+    __syncthreads();
+    g = sz[B];
+    __syncthreads();
+  }
+  const bool timers = (s.flags & 8) != 0 && blockIdx.x == 0 && t == 0;   // phase clocks of block 0 (diagnostic)
   constexpr int T = S3_THREADS, NW = S3_THREADS / 32;
   const int F = s.F, H1 = s.h1, H2 = s.h2, Hd = s.Hd, out = s.out;
   const int NBR = P.nbr, C1 = NBR * H1, C2 = NBR * H2;
@@ -698,6 +732,57 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   float* dp1 = p1;          // the pooled features are dead once conv2 has aggregated them
   float* dzin2 = zin2;      // overwritten after the conv2 weight-gradient products
 
+  // ---- this CTA's weights in the layouts the products read (B operand: [k][n]): 4-byte asynchronous copies whose
+  // DESTINATION address does the transposition - no register, no dependent store, so every copy of the phase is in
+  // flight at once (ONE L2 round trip instead of one per loop), waited for together with the bulk copies
+  {
+    const float* W1g = s.params + s.off_w1;
+    const float* W2g = s.params + s.off_w2;
+    if (kind == 0) {
+#pragma unroll 1
+      for (int i = t; i < H1 * F; i += T) {        // W1 [2][H1][F] branch br (contiguous) -> w1 [F][H1]
+        const int c = i / F, f = i - c * F;
+        s3_cp4(w1 + f * H1 + c, W1g + (int64_t)co1 * F + i);
+      }
+#pragma unroll 1
+      for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] branch br -> w2t [H2][H1] (as stored), w2 [H1][H2]
+        const int o = i / H1, j = i - o * H1;
+        const float* src = W2g + (int64_t)br * H2 * H1 + i;
+        s3_cp4(w2t + i, src);
+        s3_cp4(w2 + j * H2 + o, src);
+      }
+    } else {
+#pragma unroll 1
+      for (int i = t; i < Kin1 * H1; i += T) s3_cp4(w1 + i, W1g + i);     // [2F][H1] as stored
+#pragma unroll 1
+      for (int i = t; i < Kin2 * H2; i += T) {     // [2H1][H2] as stored -> w2, transposed -> w2t [H2][2H1]
+        const int k = i / H2, o = i - k * H2;
+        s3_cp4(w2 + i, W2g + i);
+        s3_cp4(w2t + o * Kin2 + k, W2g + i);
+      }
+      if (L3) {
+        const float* W3g = s.params + s.off_w3;
+#pragma unroll 1
+        for (int i = t; i < 2 * H2 * H2; i += T) {   // [2H2][H2] as stored -> w3, transposed -> w3t [H2][2H2]
+          const int k = i / H2, o = i - k * H2;
+          s3_cp4(w3 + i, W3g + i);
+          s3_cp4(w3t + o * 2 * H2 + k, W3g + i);
+        }
+#pragma unroll 1
+        for (int i = t; i < H2; i += T) s3_cp4(b3 + i, s.params + s.off_b3 + i);
+      }
+#pragma unroll 1
+      for (int i = t; i < H1; i += T) s3_cp4(b1 + i, s.params + s.off_b1 + i);
+#pragma unroll 1
+      for (int i = t; i < H2; i += T) s3_cp4(b2 + i, s.params + s.off_b2 + i);
+    }
+#pragma unroll 1
+    for (int i = t; i < out * Hd; i += T) s3_cp4(fc2w + i, s.params + s.off_fc2w + i);
+#pragma unroll 1
+    for (int i = t; i < Hd; i += T) s3_cp4(fc1b + i, s.params + s.off_fc1b + i);
+#pragma unroll 1
+    for (int i = t; i < out; i += T) s3_cp4(fc2b + i, s.params + s.off_fc2b + i);
+  }
   // ---- graph extents
   int n0, n, eg0, m;
   if (s.gdesc) {
@@ -715,6 +800,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
 
   do {
   if (n < 0 || m < 0 || n > s.max_n || m > s.max_e) {   // host bounds violated: flag, contribute nothing
+    asm volatile("cp.async.wait_all;" ::: "memory");      // the weight copies issued above
     if (t == 0) atomicOr(s.status, 64);
     valid = false;
     break;
@@ -722,69 +808,29 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int64_t boff = DRGNN_BLOB_OFFSET(g, n0, eg0);
   const int* blb = s.blob + boff;                 // NT > 1: the index lists are read from global memory / L2
   const float* wbl = s.wblob ? s.wblob + boff : nullptr;
-  if (staged) {
-    if (t == 0) {
-      s3_mbar_init(&bars[0], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const uint32_t bbytes = (uint32_t)DRGNN_BLOB_USED(n, m) * 4u, xbytes = (uint32_t)(n * F) * 4u;
+  const bool pre = s.zin1 != nullptr;             // conv1's input rows were computed by the structure pass
+  if (t == 0 && (staged || pre)) {
+    if (staged) s3_mbar_init(&bars[0], 1);
+    if (pre) s3_mbar_init(&bars[1], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the initialised barriers, seen by the async proxy
+    if (staged) {
+      const uint32_t bbytes = (uint32_t)DRGNN_BLOB_USED(n, m) * 4u, xbytes = pre ? 0u : (uint32_t)(n * F) * 4u;
       s3_mbar_expect_tx(&bars[0], bbytes + xbytes + (kind == 1 ? bbytes : 0u));
       s3_bulk_g2s(blbs, blb, bbytes, &bars[0]);
       if (kind == 1) s3_bulk_g2s(wbls, wbl, bbytes, &bars[0]);
       if (xbytes) s3_bulk_g2s(xs, s.x + (int64_t)n0 * F, xbytes, &bars[0]);
     }
+    if (pre) {   // this tile's rows of zin1 (row stride LDZIN1), ONE bulk copy
+      const int nta_ = s3_cdiv(max(n, 1), NT);
+      const int lo_ = min(n, ti * nta_), hi_ = min(n, lo_ + nta_);
+      const uint32_t zbytes = (uint32_t)((hi_ - lo_) * LDZIN1) * 4u;
+      s3_mbar_expect_tx(&bars[1], zbytes);
+      if (zbytes) s3_bulk_g2s(zin1, s.zin1 + ((int64_t)n0 + lo_) * LDZIN1, zbytes, &bars[1]);
+    }
+  }
+  if (staged) {
     blb = blbs;
     wbl = wbls;
-  }
-  // ---- this CTA's weights in the layouts the products read (B operand: [k][n])
-  {
-    const float* W1g = s.params + s.off_w1;
-    const float* W2g = s.params + s.off_w2;
-    if (kind == 0) {
-#pragma unroll 1
-      for (int i = t; i < H1 * F; i += T) {        // W1 [2][H1][F] branch br -> w1 [F][H1]
-        const int c = i / F, f = i - c * F;
-        w1[f * H1 + c] = __ldg(W1g + (int64_t)(co1 + c) * F + f);
-      }
-#pragma unroll 1
-      for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] branch br -> w2t [H2][H1] (as stored), w2 [H1][H2]
-        const int o = i / H1, j = i - o * H1;
-        const float v = __ldg(W2g + (int64_t)br * H2 * H1 + i);
-        w2t[i] = v;
-        w2[j * H2 + o] = v;
-      }
-    } else {
-#pragma unroll 1
-      for (int i = t; i < Kin1 * H1; i += T) w1[i] = __ldg(W1g + i);     // [2F][H1] as stored
-#pragma unroll 1
-      for (int i = t; i < Kin2 * H2; i += T) {     // [2H1][H2] as stored -> w2, transposed -> w2t [H2][2H1]
-        const int k = i / H2, o = i - k * H2;
-        const float v = __ldg(W2g + i);
-        w2[i] = v;
-        w2t[o * Kin2 + k] = v;
-      }
-      if (L3) {
-        const float* W3g = s.params + s.off_w3;
-#pragma unroll 1
-        for (int i = t; i < 2 * H2 * H2; i += T) {   // [2H2][H2] as stored -> w3, transposed -> w3t [H2][2H2]
-          const int k = i / H2, o = i - k * H2;
-          const float v = __ldg(W3g + i);
-          w3[i] = v;
-          w3t[o * 2 * H2 + k] = v;
-        }
-#pragma unroll 1
-        for (int i = t; i < H2; i += T) b3[i] = __ldg(s.params + s.off_b3 + i);
-      }
-#pragma unroll 1
-      for (int i = t; i < H1; i += T) b1[i] = __ldg(s.params + s.off_b1 + i);
-#pragma unroll 1
-      for (int i = t; i < H2; i += T) b2[i] = __ldg(s.params + s.off_b2 + i);
-    }
-#pragma unroll 1
-    for (int i = t; i < out * Hd; i += T) fc2w[i] = __ldg(s.params + s.off_fc2w + i);
-#pragma unroll 1
-    for (int i = t; i < Hd; i += T) fc1b[i] = __ldg(s.params + s.off_fc1b + i);
-#pragma unroll 1
-    for (int i = t; i < out; i += T) fc2b[i] = __ldg(s.params + s.off_fc2b + i);
   }
   // ---- DSMEM base pointers of the row-distributed arrays of this branch: z1, p1, arg0, z2, arg1, dzin2/zin2, wg
   if (t < 9 * NT) {
@@ -794,8 +840,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
                  : which == 6 ? wg : which == 7 ? z3 : zin3;
     bases[which * S3_MAX_TILES + tt] = (tt == ti) ? local : cluster.map_shared_rank(local, (unsigned)(br * NT + tt));
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's weight copies
   __syncthreads();
   if (staged) s3_mbar_wait(&bars[0], 0);
+  if (pre) s3_mbar_wait(&bars[1], 0);
   const int K = blb[2], E1 = blb[3], Q = blb[4];
   if (blb[5] != 1 || blb[0] != n || blb[1] != m || K > s.max_k || Q > s.max_q || K < 0 || Q < 0 || E1 < 0 || E1 > m) {
     if (t == 0) atomicOr(s.status, 64);
@@ -828,8 +876,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;
 
   // ---- conv1: aggregate, transform
-  s3_aggregate(kind, rp0, col0, ew0, s3_rows_flat(xsrc, F), F, lo0, hi0, zin1, LDZIN1, nullptr, nullptr, t, T);
-  __syncthreads();
+  if (!pre) {
+    s3_aggregate(kind, rp0, col0, ew0, s3_rows_flat(xsrc, F), F, lo0, hi0, zin1, LDZIN1, nullptr, nullptr, t, T);
+    __syncthreads();
+  }
   DRGNN_PHASE3(2);
   if (tc) tc_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);
   else s3_gemm(zin1, LDZIN1, w1, H1, r0n, H1, Kin1, z1, LDZ1, kind ? b1 : nullptr, 1, nullptr, 0, t, T);

@@ -119,6 +119,7 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   DRGNN_REQUIRE(s->kind != 1 || s->wblob, "net_step: sGAT needs the edge weights of the structure pass (wblob)");
   DRGNN_REQUIRE(s->kind == 0 || (s->off_b1 >= 0 && s->off_b2 >= 0), "net_step: conv biases missing");
   DRGNN_REQUIRE(s->task >= 0 && s->task <= 3, "net_step: bad task %d", s->task);
+  DRGNN_REQUIRE(((uintptr_t)s->zin1 % 16) == 0, "net_step: zin1 must be 16-byte aligned");
   DRGNN_REQUIRE(!s->layers3 || (s->kind != 0 && s->off_w3 >= 0 && s->off_b3 >= 0 && !(s->flags & 1)),
                 "net_step: the three-layer variant needs kind 1 / 2, conv3 offsets and no mirror flag");
   DRGNN_REQUIRE(((uintptr_t)s->x % 16) == 0 && ((uintptr_t)s->blob % 16) == 0 && ((uintptr_t)s->params % 16) == 0 &&

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   if (n < 0 || m < 0 || n > io.max_n || m > io.max_e) {   // host bounds violated: header stays incomplete
     if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   bool bad1 = c1len > io.max_n || c1len < 0;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   if (bad_range) {   // same flag as the full pass; the blob stays incomplete (the step kernel refuses it)
     if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER_RANGE);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   const int W0 = (int)((range0 + 31) >> 5), W1c = (int)((range1 + 31) >> 5);
@@ -349,10 +351,8 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 4
     for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
     bl[BL.col0 + pos] = ecol[e];
-    if (wb) {
-      wb[BL.col0 + pos] = eas[e];
-      eord[pos] = (uint16_t)e;       // edge id of the CSR slot: the weight sums walk a node's edges in slot order
-    }
+    if (wb) wb[BL.col0 + pos] = eas[e];
+    if (wb || io.zin1) eord[pos] = (uint16_t)e;   // edge id of the CSR slot: the weight sums / the first aggregation walk a node's edges in slot order
   }
 #pragma unroll 1
   for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
@@ -474,6 +474,58 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     }
     DRGNN_BPHASE(7);
   }
+  if (io.zin1) {
+    // ---- 9. the first aggregation of the network (optional): the input rows of conv1's dense transform depend on
+    // the batch only, not on the weights, so they are computed HERE - on the side stream, while the previous step
+    // still computes - and the step kernel stages them ready-made instead of the feature tile:
+    //   kind 0 (GINet, ginet.py:57-71)    zin1_i = sum_e x_col
+    //   kind 1 (sGAT, sGAT.py:70-92)      zin1_i = [ s_i x_i | (1/max(deg,1)) sum_e a_e x_col | 1 0 0 0 ],  s_i = mean_e a_e
+    //   kind 2 (FoutNet, foutnet.py:62-80) zin1_i = [ x_i | (1/deg) sum_e x_col | 1 0 0 0 ]   (deg = 0 -> NaN)
+    // Same arithmetic, in the same order (ascending CSR slot = the CPU scatter order), as the aggregation phase of the
+    // step kernels (s2_gather / s3_aggregate), so the rows are bit-identical.  The feature rows come from global
+    // memory (each is read deg times: L1 / L2 hits after the first).
+    __syncthreads();   // eord (the emit sweep above) is complete; cnt holds the CSR row pointers
+    const int F = io.F, F4 = F >> 2, ld = io.ld_zin1, kind = io.zin_kind;
+    const float* xg = io.x + (int64_t)n0 * F;
+    float* zg = io.zin1 + (int64_t)n0 * ld;
+#pragma unroll 1
+    for (int item = t; item < n * F4; item += T) {
+      const int i = item / F4, q4 = item - i * F4;
+      const int sb_ = cnt[i], se_ = cnt[i + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float wsum = 0.f;
+      if (kind == 1) {
+#pragma unroll 4
+        for (int p = sb_; p < se_; ++p) {
+          const int e = eord[p];
+          const float wv = eas[e];
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xg + (int)ecol[e] * F) + q4);
+          acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
+          wsum += wv;
+        }
+      } else {
+#pragma unroll 4
+        for (int p = sb_; p < se_; ++p) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xg + (int)ecol[eord[p]] * F) + q4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      float* zr = zg + (int64_t)i * ld;
+      if (kind == 0) {
+        *reinterpret_cast<float4*>(zr + q4 * 4) = acc;
+      } else {
+        const int deg = se_ - sb_;
+        const float post = kind == 1 ? 1.f / (float)max(deg, 1) : 1.f / (float)deg;
+        const float selfc = kind == 1 ? post * wsum : 1.f;
+        acc.x *= post; acc.y *= post; acc.z *= post; acc.w *= post;
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(xg + i * F) + q4);
+        *reinterpret_cast<float4*>(zr + q4 * 4) = make_float4(selfc * sv.x, selfc * sv.y, selfc * sv.z, selfc * sv.w);
+        *reinterpret_cast<float4*>(zr + F + q4 * 4) = acc;
+        if (q4 == 0) *reinterpret_cast<float4*>(zr + 2 * F) = make_float4(1.f, 0.f, 0.f, 0.f);   // ones column: bias gradient
+      }
+    }
+    DRGNN_BPHASE(8);
+  }
   if (t == 0) {   // closing pointers and the header
     bl[BL.rp0 + n] = m;
     bl[BL.rp1 + K] = E1;
@@ -486,6 +538,10 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     gs[0] = K; gs[1] = E1; gs[2] = K1;
   }
   DRGNN_BPHASE(5);
+  // Launched as the programmatic dependent of the step kernel in front of it (launch_flags bit 0), this grid started
+  // while that kernel was still running; it must not COMPLETE before it, because the next step in the stream is
+  // ordered after this grid only (no-op for a normal launch).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace drgnn
@@ -513,6 +569,10 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
                 "structure_blob: NULL input (both cluster levels are required)");
   DRGNN_REQUIRE(io->blob && io->status && io->gstat, "structure_blob: NULL output");
   DRGNN_REQUIRE(!io->wblob || !io->edge_attr || io->ne >= 1, "structure_blob: edge weights requested but ne == 0");
+  DRGNN_REQUIRE(!io->zin1 || (io->x && io->F > 0 && io->F % 4 == 0 && io->zin_kind >= 0 && io->zin_kind <= 2 &&
+                               io->ld_zin1 % 4 == 0 && io->ld_zin1 >= (io->zin_kind ? 2 * io->F + 4 : io->F)),
+                "structure_blob: first aggregation requested with an invalid x / F / ld_zin1 / zin_kind");
+  DRGNN_REQUIRE(!io->zin1 || io->zin_kind != 1 || (io->wblob && io->edge_attr), "structure_blob: the sGAT aggregation needs edge_attr and wblob");
   const int64_t smem = drgnn_structure_blob_smem_bytes(io->max_n, io->max_e);
   if (smem < 0)
     return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges does not fit the bitmap kernel",
@@ -524,7 +584,24 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
     configured = device_info().smem_optin - 4096;
   }
   const BlobPlan plan = blob_plan(io->max_n, io->max_e);
-  graph_blob_kernel<<<io->B, SB_THREADS, smem, (cudaStream_t)stream>>>(*io, plan);
+  if (io->launch_flags & 1) {
+    // programmatic dependent launch: the grid may start as soon as every CTA of the kernel in front of it in the
+    // stream has executed griddepcontrol.launch_dependents (the step kernels do so first thing) - its CTAs then go
+    // to the SMs that kernel leaves free; it waits for that kernel's completion itself, at its end
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)io->B);
+    cfg.blockDim = dim3(SB_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DRGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, graph_blob_kernel, *io, plan));
+  } else {
+    graph_blob_kernel<<<io->B, SB_THREADS, smem, (cudaStream_t)stream>>>(*io, plan);
+  }
   DRGNN_CHECK_LAUNCH("graph_blob_kernel");
   return DRGNN_OK;
 }

@@ -326,6 +326,21 @@ class Engine(object):
         # dense products of the fused step on the tensor cores (mma.sync 3xTF32, error ~1e-6) instead of FFMA tiles;
         # opt-in: measured slower than the FFMA register tiles at every BASELINE config (profiles/README.md, round 2)
         self.fused_tc = os.environ.get('DRGNN_FUSED_TC', '0') != '0'
+        # general cluster kernel on a grid larger than the device: clusters take the graphs largest first
+        self.step3_lpt = os.environ.get('DRGNN_STEP3_LPT', '1') != '0'
+        self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # The blob structure pass also computes conv1's input rows (the first aggregation depends on the batch only)
+        # and the step kernels stage them: '1' always, '0' never, 'auto' when the step grid leaves SMs for the
+        # longer pass (it runs beside the step on the SMs the step does not occupy: sGAT / FoutNet at batch 64 use
+        # 64 of 148 SMs - cfg3 44.1 -> 40.0 us per step; the CTA-pair GINet kernel uses 128 and the pass
+        # becomes the bottleneck - cfg2 26.6 -> 28.8 us)
+        self.pre_agg = os.environ.get('DRGNN_PRE_AGG', 'auto')
+        # train_resident chunk graphs: structure passes as programmatic dependents of the steps, on one stream.
+        # Opt-in: on this driver a dependent grid does not start before its primary ends even when every CTA of
+        # the primary has triggered and SMs are free (tools/micro/pdl_test.cu: 28.9 vs 29.4 us per pair), so the
+        # single-stream order only serialises pass and step (cfg2: 33.5 vs 26.6 us per step).
+        self.pdl_prep = os.environ.get('DRGNN_PDL_PREP', '0') != '0'
+        self.phase_timers = False     # diagnostic: block 0 of the fused step kernels records its phase clocks
         self._last_path = None
         self.seed = 0x5EED if seed is None else int(seed)
         if self.world > 1:
@@ -465,10 +480,12 @@ class Engine(object):
         return self.ws
 
     # ---------------------------------------------------------------- structure pass
-    def prepare(self, d):
+    def prepare(self, d, dependent=False):
         """Run the structure pass of batch ``d`` into structure slot ``d.sslot`` on the current
         stream.  It depends on the batch only (not on the weights), so callers may run it on a
-        side stream while the previous step computes (``train_batches`` / ``train_resident`` do)."""
+        side stream while the previous step computes (``train_batches`` / ``train_resident`` do).
+        ``dependent``: launch it as the programmatic dependent of the step kernel in front of it in the stream
+        (blob pass only; ``_chunk_graph``)."""
         self._ensure(d.B, d.N, d.E)
         self._primed = None              # a structure slot changes: train_resident primes its lookahead again
         need_w = self.spec.kind == 'sgat'
@@ -479,8 +496,12 @@ class Engine(object):
         slot = self.structs[d.sslot]
         if self._blob_only(d):
             # fused whole-step paths: ONE launch writes the per-graph structure blobs (+ edge weights for sGAT)
+            # (+ the input rows of conv1's transform: the first aggregation does not depend on the weights)
+            pre = self._pre_agg_on(d)
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
-                                    d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None)
+                                    d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None,
+                                    x=d.x if pre else None, zin_kind=self.spec.kind if pre else None,
+                                    dependent=dependent)
             assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
@@ -490,6 +511,19 @@ class Engine(object):
         assert st is slot
         self._last_struct = st
         return st
+
+    def _pre_agg_on(self, d):
+        """Does the blob structure pass of batch ``d`` also compute conv1's input rows?  (``self.pre_agg``)"""
+        mode = self.pre_agg
+        if isinstance(mode, bool):
+            mode = '1' if mode else '0'
+        if mode == '0' or self.spec.F % 4:
+            return False
+        if mode != 'auto':
+            return True
+        tiles = self._step3_tiles(d)
+        ctas = (tiles if tiles else 1) * self.spec.nb * d.B        # grid of the step kernel
+        return ctas + (d.B + 1) // 2 <= self._sm_count             # + the pass at two CTAs per SM
 
     def _comm_in_kernel(self, d, st):
         """Can the peer-memory exchange run inside the cluster step kernel for batch ``d``?  Decided from
@@ -650,7 +684,8 @@ class Engine(object):
                                max_e=d.max_e, mirror=self.keep_intermediates,
                                variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
                                blob=st.blob, gdesc=st.gstat if st.blob_only else None,
-                               edge_ptr=d.edge_ptr, tc=self.fused_tc)
+                               edge_ptr=d.edge_ptr, tc=self.fused_tc, timers=self.phase_timers,
+                               zin1=getattr(st, 'zin1', None) if st.blob_only else None)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._all_done_kernel = True
                 self._adam_done = fuse_adam
@@ -749,7 +784,9 @@ class Engine(object):
                      adam=dict(p=P.data, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
                                beta2=self.betas[1], eps=self.eps) if (fuse_adam or in_kernel) else None,
                      skip_reduce=use_comm and not in_kernel, fuse_reduce=self.fuse_reduce,
-                     comm=self.comm if in_kernel else None, mirror=mirror, tc=self.fused_tc)
+                     comm=self.comm if in_kernel else None, mirror=mirror, tc=self.fused_tc,
+                     timers=self.phase_timers, lpt=self.step3_lpt and tiles * s.nb * B > self._sm_count,
+                     zin1=getattr(st, 'zin1', None) if st.blob_only else None)
         self._last_path = 'step3'
         self._graph_done = self._head_done = self._all_done = train_step
         self._all_done_kernel = True
@@ -1322,6 +1359,14 @@ class Engine(object):
             self._no_exchange = True
             try:
                 self.step(dbatches[start % R], B_global=B_global)
+                # is a step ONE kernel launch?  (then a structure pass can be its programmatic dependent)
+                from . import _lib
+                c0 = _lib.launch_count
+                self.step(dbatches[start % R], B_global=B_global, prepared=True)
+                one_call = _lib.launch_count - c0 == 1
+                lib = _lib.load()
+                last = lib.drgnn_net_step_last_launches() if self._last_path == 'step3' else lib.drgnn_ginet_step_last_launches()
+                single_launch = one_call and int(last) == 1 and self._all_done_kernel
                 for j in range(la):              # the warm-up rewrote a structure slot: restore what the chunk expects
                     self.prepare(dbatches[(start + j) % R])
             finally:
@@ -1329,28 +1374,49 @@ class Engine(object):
             torch.cuda.current_stream(self.device).synchronize()
             for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
                 t.copy_(c)
-            done, ready = {}, {}
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                main = torch.cuda.current_stream(self.device)
-                for ps in self._prep_streams:
-                    ps.wait_stream(main)
-                for i in range(start, start + C):
-                    j = i + la
-                    ps = self._prep_streams[j & 1]
-                    with torch.cuda.stream(ps):
-                        if j - ns in done:
-                            ps.wait_event(done[j - ns])
-                        self.prepare(dbatches[j % R])
-                        ready[j] = torch.cuda.Event()
-                        ready[j].record(ps)
-                    if i in ready:
-                        main.wait_event(ready[i])
-                    self.step(dbatches[i % R], B_global=B_global, prepared=True)
-                    done[i] = torch.cuda.Event()
-                    done[i].record(main)
-                for ps in self._prep_streams:
-                    main.wait_stream(ps)
+            def capture(pdl):
+                g = torch.cuda.CUDAGraph()
+                if pdl:
+                    # ONE stream: step i | structure pass i + LA as the PROGRAMMATIC DEPENDENT of step i | step i + 1 ...
+                    # The pass starts when every CTA of step i is resident (so its CTAs take the SMs the step leaves
+                    # free instead of racing it for SMs - on side streams it started at the same instant as a step
+                    # and its CTAs, spread one per SM, kept step CTAs from becoming resident) and completes after
+                    # step i; step i + 1 is ordered after the pass.  Slot (i + LA) % STRUCT_SLOTS was last read by
+                    # step i + LA - STRUCT_SLOTS < i.
+                    with torch.cuda.graph(g):
+                        for i in range(start, start + C):
+                            self.step(dbatches[i % R], B_global=B_global, prepared=True)
+                            self.prepare(dbatches[(i + la) % R], dependent=True)
+                    return g
+                done, ready = {}, {}
+                with torch.cuda.graph(g):
+                    main = torch.cuda.current_stream(self.device)
+                    for ps in self._prep_streams:
+                        ps.wait_stream(main)
+                    for i in range(start, start + C):
+                        j = i + la
+                        ps = self._prep_streams[j & 1]
+                        with torch.cuda.stream(ps):
+                            if j - ns in done:
+                                ps.wait_event(done[j - ns])
+                            self.prepare(dbatches[j % R])
+                            ready[j] = torch.cuda.Event()
+                            ready[j].record(ps)
+                        if i in ready:
+                            main.wait_event(ready[i])
+                        self.step(dbatches[i % R], B_global=B_global, prepared=True)
+                        done[i] = torch.cuda.Event()
+                        done[i].record(main)
+                    for ps in self._prep_streams:
+                        main.wait_stream(ps)
+                return g
+
+            pdl = self.pdl_prep and single_launch and all(self._blob_only(d) for d in dbatches)
+            g = capture(pdl)
+            if pdl and self.world > 1 and getattr(self, '_last_exchange', None) != 'in-kernel':
+                pdl = False                      # the exchange is its own launch behind the step: side streams
+                g = capture(False)
+            self._last_chunk_pdl = pdl
         finally:
             self.use_graph = use_graph
         self._graphs[key] = g

@@ -229,13 +229,24 @@ def structure_blob_fits(max_n, max_e):
     return int(_lib.load().drgnn_structure_blob_smem_bytes(int(max_n), int(max_e))) >= 0
 
 
+ZIN_KIND = {'ginet': 0, 'sgat': 1, 'fout': 2}
+
+
+def zin1_ld(kind, F):
+    """Row stride of the precomputed conv1 input rows (``Structure.zin1``): the stride the step kernels keep them
+    at in shared memory (F + 4 for GINet, 2F + 4 columns + 4 for the others)."""
+    return (F if ZIN_KIND[kind] == 0 else 2 * F) + 4
+
+
 def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None,
-                   edge_attr=None):
+                   edge_attr=None, x=None, zin_kind=None, dependent=False):
     """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
     structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
     global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
     sticky: zeroed at allocation and by ``Structure.sync_counts``).  Same argument checks as
-    ``structure_build``; both cluster levels are required."""
+    ``structure_build``; both cluster levels are required.  ``x`` [N, F] + ``zin_kind`` ('ginet' | 'sgat' | 'fout'):
+    the pass also computes the input rows of conv1's transform (the first aggregation depends on the batch only) into
+    ``Structure.zin1`` for the step kernels (``drgnn_structure_io.zin1``)."""
     require_cuda(node_ptr, edge_ptr, edge_index, cluster0, c1_ptr, cluster1)
     _i32(node_ptr, 'node_ptr'), _i32(edge_ptr, 'edge_ptr'), _i32(c1_ptr, 'c1_ptr')
     if cluster1 is None or c1_ptr is None:
@@ -284,6 +295,21 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
     io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
+    if x is not None and zin_kind is not None:
+        require_cuda(x)
+        _f32(x, 'x')
+        F = x.size(1)
+        ld = zin1_ld(zin_kind, F)
+        need = s.cap[1] * ld
+        if getattr(s, '_zin1', None) is None or s._zin1.numel() < need:
+            s._zin1 = torch.empty(need, dtype=F32, device=cluster0.device)     # capacity-sized: fixed address
+        s.zin1, s.zin1_ld = s._zin1, ld
+        s._keep = s._keep + (x,)
+        io.x, io.zin1, io.F, io.ld_zin1, io.zin_kind = ptr(x), ptr(s._zin1), F, ld, ZIN_KIND[zin_kind]
+    else:
+        s.zin1, s.zin1_ld = None, 0
+        io.x, io.zin1 = None, None
+    io.launch_flags = 1 if dependent else 0     # programmatic dependent of the kernel in front of it in the stream
     if B:
         call('drgnn_structure_blob', C.byref(io), stream_ptr())
     return s
@@ -518,7 +544,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
                drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
-               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None, tc=False):
+               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None, tc=False, timers=False, zin1=None):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -552,8 +578,12 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     s.comm = C.addressof(comm.struct) if comm is not None else None
     require_cuda(gdesc)
     s.gdesc = ptr(gdesc)          # per-graph extents of a blob-only structure pass (Structure.gstat)
-    # flags: bit 0 mirror the intermediates, bit 1 no in-kernel reduction, bit 2 dense products on mma.sync 3xTF32 tiles
-    s.max_e, s.flags, s.variant = int(max_e or 0), (1 if mirror else 0) | (0 if fuse_reduce else 2) | (4 if tc else 0), int(variant)
+    require_cuda(zin1)
+    s.zin1 = ptr(zin1)            # AX of the structure pass (Structure.zin1, row stride F + 4)
+    # flags: bit 0 mirror the intermediates, bit 1 no in-kernel reduction, bit 2 dense products on mma.sync 3xTF32 tiles,
+    # bit 3 phase clocks of block 0 (drgnn_debug_phase_cycles)
+    s.max_e, s.variant = int(max_e or 0), int(variant)
+    s.flags = (1 if mirror else 0) | (0 if fuse_reduce else 2) | (4 if tc else 0) | (8 if timers else 0) | (16 if int(timers) > 1 else 0)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the
     # in-kernel reduction (grid barrier) launch only the per-graph kernel
@@ -624,7 +654,7 @@ def net_step_max_clusters(kind, tiles, smem_bytes):
 def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, max_k, max_q, pred, node_ptr, edge_ptr,
              tiles=0, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None, keep_scale=1.0, drop_p=0.0,
              seed=0, loss=None, R=None, partial=None, grads=None, n_params=0, forward_only=False, step_dev=None, adam=None,
-             skip_reduce=False, fuse_reduce=True, comm=None, mirror=None, tc=False):
+             skip_reduce=False, fuse_reduce=True, comm=None, mirror=None, tc=False, timers=False, lpt=False, zin1=None):
     """Whole step of every graph in one launch for GINet / sGAT / FoutNet (``drgnn_net_step``, the general
     cluster kernel).  ``st``: the ``Structure`` of the batch (blob, + wblob for sGAT); ``offsets``: dict of the
     tensor offsets inside the flat parameter buffer (w1, b1, w2, b2, fc1w, fc1b, fc2w, fc2b; b1 / b2 None for
@@ -665,7 +695,11 @@ def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, 
     s.step_dev = ptr(step_dev)
     s.status = ptr(st.status)
     s.comm = C.addressof(comm.struct) if comm is not None else None
-    s.flags = (0 if fuse_reduce else 2) | (4 if tc else 0)      # bit 2: dense products on mma.sync 3xTF32 tiles
+    require_cuda(zin1)
+    s.zin1 = ptr(zin1)            # conv1 input rows of the structure pass (Structure.zin1, row stride Kin1 + 4)
+    # bit 2: dense products on mma.sync 3xTF32 tiles; bit 3: phase clocks of block 0 (drgnn_debug_phase3_cycles)
+    # bit 5: clusters take the graphs in descending size order (grids larger than the device, mixed sizes)
+    s.flags = (0 if fuse_reduce else 2) | (4 if tc else 0) | (8 if timers else 0) | (32 if lpt else 0)
     if mirror is not None:
         require_cuda(*mirror.values())
         s.flags |= 1

@@ -147,6 +147,24 @@ typedef struct drgnn_structure_io {
    * the pooled edge (coalesce, community_pooling.py:204-205) in pooled-CSR order and in pooled-CSC order.
    * What the fused sGAT step (drgnn_net_step, kind 1) stages next to the index lists (sGAT.py:76). */
   float* wblob;
+  /* First aggregation of the network, computed next to the structure (optional, zin1 == NULL to skip; honoured by
+   * drgnn_structure_blob only).  The input rows of conv1's dense transform depend on the batch alone, so the
+   * structure pass - which runs on a side stream while the previous step computes - can leave them ready for the
+   * step kernels (drgnn_ginet_step_args.zin1 / drgnn_net_step_args.zin1), which then stage them instead of the feature tile:
+   *   zin_kind 0 (GINet, ginet.py:57-71):    zin1[i] = sum_e x[col]                                     (ld_zin1 >= F)
+   *   zin_kind 1 (sGAT, sGAT.py:70-92):      zin1[i] = [ s_i x_i | mean_e a_e x_col | 1 0 0 0 ]         (ld_zin1 >= 2F + 4)
+   *   zin_kind 2 (FoutNet, foutnet.py:62-80): zin1[i] = [ x_i | (1/deg) sum_e x_col | 1 0 0 0 ], deg 0 -> NaN
+   * rows of node i at zin1 + i * ld_zin1, summed in CSR-slot order (bit-identical to the step kernels' own phase).
+   * x [N, F] fp32 row-major, F % 4 == 0, ld_zin1 % 4 == 0. */
+  const float* x;
+  float* zin1;
+  int32_t F; int32_t ld_zin1; int32_t zin_kind;
+  /* launch_flags bit 0 (drgnn_structure_blob): launch the pass as the PROGRAMMATIC DEPENDENT of the kernel in front
+   * of it in the stream (cudaLaunchAttributeProgrammaticStreamSerialization).  Behind a step kernel
+   * (drgnn_ginet_step / drgnn_net_step, which trigger their dependents first thing) the pass starts once every
+   * CTA of the step is resident and runs beside it on the SMs it leaves free; it completes after that step.  The
+   * pass must not depend on anything that step writes (it never does: it reads the NEXT batches' inputs). */
+  int32_t launch_flags;
 } drgnn_structure_io;
 
 /* Dynamic shared memory the per-graph kernel needs for (max_n, max_e); <0 if a graph is
@@ -397,7 +415,8 @@ typedef struct drgnn_ginet_step_args {
    * bit 1: never fuse the gradient reduction into the cluster kernel (step_dev must be [4] floats,
    * zero-initialised: [2] is the grid-barrier counter of the fused reduction);
    * bit 2 (cluster kernel): the dense products run on tensor-core tiles (mma.sync.m16n8k8 TF32 with the 3-product
-   * error compensation, ~1e-6; widths must be multiples of 8, else the fp32 FMA tiles are used) */
+   * error compensation, ~1e-6; widths must be multiples of 8, else the fp32 FMA tiles are used);
+   * bit 3: block 0 records its phase clocks (drgnn_debug_phase_cycles; diagnostic, slows the launch slightly) */
   int32_t flags;
   /* max_e: host bound of the directed edges of one graph (> 0 enables the cluster kernel: a pair of
    * CTAs per graph, one GINet branch each, nb == 2).  variant: 0 = pick (cluster kernel when it
@@ -417,6 +436,10 @@ typedef struct drgnn_ginet_step_args {
    * [K0, E1, K1, node_ptr[g], edge_ptr[g], m, 0, n]: the cluster kernel reads a graph's extents from this
    * L2-resident record (written a few microseconds earlier) instead of the cold node_ptr / edge_ptr */
   const int32_t* gdesc;
+  /* zin1 (optional, cluster kernel): AX = A x of every node, precomputed by the structure pass
+   * (drgnn_structure_io.zin1 with zin_kind 0 and ld_zin1 = F + 4): the kernel stages the graph's rows with ONE bulk
+   * copy instead of the feature tile and skips its own aggregation phase (bit-identical rows) */
+  const float* zin1;
 } drgnn_ginet_step_args;
 int64_t drgnn_ginet_step_smem_bytes(int32_t F, int32_t h1, int32_t h2, int32_t nb, int32_t max_n, int32_t max_k,
                                     int32_t max_q, int32_t Hd, int32_t out);
@@ -477,7 +500,9 @@ int drgnn_debug_structure_cycles(uint64_t* out32);
  *     intermediates to Zin1 [N,Kin1] Z1 [N,nbr*h1] arg0 Zin2 Z2 arg1 (needs kptr0 / kptr1 of
  *     drgnn_structure_build); bit 1: never fuse the gradient reduction; bit 2: the dense products (conv transforms,
  *     their input and weight gradients) run on tensor-core tiles (mma.sync.m16n8k8 TF32, 3-product error compensation,
- *     ~1e-6) instead of fp32 FMA register tiles.  R (optional): read-out rows [B, nbr*h2].
+ *     ~1e-6) instead of fp32 FMA register tiles; bit 3: block 0 records its phase clocks (drgnn_debug_phase3_cycles);
+ *     bit 5: cluster c runs the graph of size rank c (largest first: shortens the tail of a grid larger than the device).
+ *     R (optional): read-out rows [B, nbr*h2].
  * ---------------------------------------------------------------------------------- */
 typedef struct drgnn_net_step_args {
   int32_t kind; int32_t B; int32_t F; int32_t h1; int32_t h2; int32_t Hd; int32_t out;
@@ -506,6 +531,10 @@ typedef struct drgnn_net_step_args {
    * max-pool - the "sGAT 3-layer" throughput variant of BASELINE config 3 (the reference nets have two);
    * off_w3 -> conv3.weight [2h2][h2] (kind 2: conv3.Wc | conv3.Wn), off_b3 -> conv3.bias [h2] */
   int32_t layers3; int32_t off_w3; int32_t off_b3; int32_t reserved3;
+  /* zin1 (optional): the input rows of conv1's transform, precomputed by the structure pass
+   * (drgnn_structure_io.zin1 with zin_kind = kind and ld_zin1 = Kin1 + 4, Kin1 = F | 2F): every CTA stages its rows
+   * with ONE bulk copy and skips the level-0 aggregation phase and the feature tile (bit-identical rows) */
+  const float* zin1;
 } drgnn_net_step_args;
 /* shared memory of one CTA (<0: unsupported shape / does not fit) */
 int64_t drgnn_net_step_smem_bytes(int32_t kind, int32_t tiles, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k,

@@ -224,3 +224,42 @@ def test_step3_three_layer_sgat_matches_oracle(lib, tiles):
     _close_abs(eloss.view(-1), loss.view(-1), 'loss')
     for name, g in eng.named_grads().items():
         _close(g, grads[name], 'grad ' + name)
+
+
+@pytest.mark.parametrize('tiles', [0, 1, 2])
+@pytest.mark.parametrize('net', ['GINet', 'sGAT', 'FoutNet'])
+def test_first_aggregation_of_the_structure_pass_is_bit_identical_to_the_step_kernels_phase(lib, net, tiles):
+    """conv1's input rows computed by the blob structure pass (``drgnn_structure_io.zin1``, default) against the
+    step kernels' own aggregation phase (``pre_agg = False``): same bits in every intermediate the kernels mirror,
+    same predictions, loss, gradients and weights over several optimiser steps.  Isolated nodes included (Fout NaN
+    rows).  tiles 0 = the kernel the engine picks (the CTA-pair kernel for GINet)."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs(dict(nodes=(5, 200), edges_per_node=5, feat=32), count=19, seed=23)
+    g = graphs[3]
+    keep = (g.edge_index[0] != 0) & (g.edge_index[1] != 0)        # node 0 of one graph loses every edge
+    g.edge_index = g.edge_index[:, keep].contiguous()
+    g.edge_attr = g.edge_attr[keep].contiguous()
+    d = _device_batch(graphs)
+    ea = Engine(net, 32, 1, 1, hidden=HIDDEN, device='cuda:0', seed=7, dropout=0.0, lr=1e-3)
+    eb = Engine(net, 32, 1, 1, hidden=HIDDEN, device='cuda:0', seed=7, dropout=0.0, lr=1e-3)
+    ea.pre_agg, eb.pre_agg = '1', '0'
+    for e in (ea, eb):
+        e.keep_intermediates = True
+        e.step3_tiles = tiles             # != 0: the general cluster kernel with that tile count, GINet included
+    for step in range(3):
+        la, pa = ea.step(d)
+        lb, pb = eb.step(d)
+        ea.validate(), eb.validate()
+        assert ea._last_path == eb._last_path
+        st = ea._last_struct
+        if st.blob_only:      # (the CTA-pair kernel mirrors its intermediates from the full structure pass: nothing precomputed)
+            assert st.zin1 is not None and eb._last_struct.zin1 is None
+        for name in ('Zin1', 'Z1', 'Zin2', 'Z2'):
+            a, b = getattr(ea.ws, name), getattr(eb.ws, name)
+            assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)), name
+        assert torch.equal(torch.nan_to_num(pa, nan=-7.0), torch.nan_to_num(pb, nan=-7.0))
+        assert torch.equal(torch.nan_to_num(la, nan=-7.0), torch.nan_to_num(lb, nan=-7.0))
+        for name, gr in ea.named_grads().items():
+            assert torch.equal(torch.nan_to_num(gr, nan=-7.0), torch.nan_to_num(eb.named_grads()[name], nan=-7.0)), name
+    assert torch.equal(torch.nan_to_num(ea.params.data, nan=-7.0), torch.nan_to_num(eb.params.data, nan=-7.0))

@@ -52,7 +52,9 @@ def main():
         if graph:
             import ctypes
             from deeprank_gnn_b200 import _lib
+            eng.phase_timers, eng.use_graph = 2, False      # one eager launch with the phase clocks on
             eng.step(ds[0], prepared=True)
+            eng.phase_timers, eng.use_graph = False, True
             ph = (ctypes.c_uint64 * 32)()
             _lib.check(_lib.load().drgnn_debug_phase_cycles(ph), 'phase')
             names = ['stage', 'AX', 'Z1', 'P1', 'AP', 'Z2', 'P2', 'R', 'fc1', 'fc2', 'loss+headbwd+dR', 'dZ2stage',
@@ -65,6 +67,8 @@ def main():
                       'wait for blob + features %d | header check + cluster arrive %d'
                       % (ph[20] - ph[0], ph[21] - ph[20], ph[22] - ph[21], ph[23] - ph[22], ph[24] - ph[23],
                          ph[25] - ph[24], ph[1] - ph[25]))
+            if ph[28] > ph[26] > 0:
+                print('  repeated inside the launch (warm code, same data): Z1 %d | AX %d' % (ph[27] - ph[26], ph[28] - ph[27]))
             if ph[18] > ph[16]:
                 print('  in-kernel reduction: grid barrier %d | reduce + Adam %d' % (ph[17] - ph[16], ph[18] - ph[17]))
             if eng._last_path == 'step3':
