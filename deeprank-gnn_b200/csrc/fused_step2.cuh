@@ -428,19 +428,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   // ---- this branch's conv weights, requested before anything else (they do not depend on the graph): 4-byte
   // asynchronous copies whose DESTINATION address does the transposition, so no register, no dependent store and
   // ONE L2 round trip that overlaps the extent loads and the bulk-copy issue below (first commit group)
+  {
 #pragma unroll 1
-  for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. (contiguous) -> w1t [F][H1]
-    const int c = i / F, f = i - c * F;
-    s2_cp4(w1t + f * H1 + c, a.W1 + (int64_t)co1 * F + i);
-  }
+    for (int i = t; i < H1 * F; i += T) {        // W1 [C1][F] rows co1.. (contiguous) -> w1t [F][H1]
+      const int c = i / F, f = i - c * F;
+      s2_cp4(w1t + f * H1 + c, a.W1 + (int64_t)co1 * F + i);
+    }
 #pragma unroll 1
-  for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] group r -> w2 [H2][H1], w2t [H1][H2]
-    const int o = i / H1, j = i - o * H1;
-    const float* src = a.W2 + (int64_t)r * H2 * H1 + i;
-    s2_cp4(w2 + i, src);
-    s2_cp4(w2t + j * H2 + o, src);
+    for (int i = t; i < H2 * H1; i += T) {       // W2 [2][H2][H1] group r -> w2 [H2][H1], w2t [H1][H2]
+      const int o = i / H1, j = i - o * H1;
+      const float* src = a.W2 + (int64_t)r * H2 * H1 + i;
+      s2_cp4(w2 + i, src);
+      s2_cp4(w2t + j * H2 + o, src);
+    }
+    s2_commit();
   }
-  s2_commit();
   // ---- graph extents: ONE level of tiny loads (host-built pointers), then three bulk copies
   int n0, n, eg0, m;
   if (s.gdesc) {   // the record the structure pass left in L2 a moment ago: [K0, E1, K1, n0 | e0, m, 0, n]
@@ -531,7 +533,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const int* cscp1 = blb + BL.cscp1; const int* cscr1 = blb + BL.cscr1;
   // The peer CTA must be running before its shared memory is written (read-out exchange below):
   // arrive now, wait just before the exchange, so the barrier costs nothing.
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  // (relaxed: the barrier only tells the peer that this CTA runs - a releasing arrive would first wait for the
+  // asynchronous copies of the head vectors, which are not needed before the read-out)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   S2_PHASE(1);
 
   const int F4 = F >> 2, H14 = H1 >> 2, H24 = H2 >> 2;

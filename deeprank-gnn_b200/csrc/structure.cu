@@ -44,8 +44,10 @@ struct SmemPlan {
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // edge_index / cluster ids arrive as int64 (reference tensors) or int32 (packed feeder batches)
+// idx32: 0 = int64 ids (reference tensors), 1 = int32, 2 = uint16 (compact feeder records)
 __device__ __forceinline__ long long ld_id(const void* base, int64_t i, int idx32) {
-  return idx32 ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
+  return idx32 == 2 ? (long long)reinterpret_cast<const uint16_t*>(base)[i]
+         : idx32  ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
 }
 
 __host__ __device__ inline SmemPlan make_plan(int max_n, int max_e, int max_c1) {
@@ -341,7 +343,15 @@ __global__ void __launch_bounds__(kThreads) graph_local_kernel(const drgnn_struc
 #pragma unroll 1
   for (int e = t; e < m; e += T) {
     long long r, c;
-    if (io.edge16) {   // compact feeder batches: uint16 graph-local ids
+    if (io.edge16 == 2) {   // compact feeder batches: m / 2 undirected pairs of uint16 graph-local ids (the second half
+      // of the graph's directed edges mirrors the first, DataSet.py:266-269); pairs of the graph start at e0 / 2
+      const uint16_t* ei = reinterpret_cast<const uint16_t*>(io.edge_index);
+      const int mh = m >> 1, eh = e < mh ? e : e - mh;
+      const int64_t at = (int64_t)(e0 >> 1) + eh;
+      const long long a = ei[at], b = ei[((int64_t)io.E >> 1) + at];
+      r = ((m | e0) & 1) ? -1 : (e < mh ? a : b);   // an odd edge count cannot be two mirrored halves: flagged below
+      c = e < mh ? b : a;
+    } else if (io.edge16) {   // uint16 graph-local ids, both directions stored
       r = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)e0 + e];
       c = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)io.E + e0 + e];
     } else {

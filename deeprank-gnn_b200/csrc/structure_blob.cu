@@ -68,8 +68,20 @@ __host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e) {
   return p;
 }
 
+// idx32: 0 = int64 ids (reference tensors), 1 = int32, 2 = uint16 (compact feeder records)
 __device__ __forceinline__ long long sb_ld_id(const void* base, int64_t i, int idx32) {
-  return idx32 ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
+  return idx32 == 2 ? (long long)reinterpret_cast<const uint16_t*>(base)[i]
+         : idx32  ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
+}
+// Edge e of a graph whose m directed edges travel as m / 2 undirected pairs (edge16 == 2: the loader stores every
+// edge in both directions, first half i -> j, second half j -> i, DataSet.py:266-269, so the second half is implied):
+// ei = [2, E / 2] uint16 graph-local ids, the graph's pairs start at e0 / 2.
+__device__ __forceinline__ void sb_ld_half_edge(const uint16_t* ei, int64_t E, int e0, int m, int e, long long& r, long long& c) {
+  const int mh = m >> 1, eh = e < mh ? e : e - mh;
+  const int64_t at = (int64_t)(e0 >> 1) + eh;
+  const long long a = ei[at], b = ei[(E >> 1) + at];
+  r = e < mh ? a : b;
+  c = e < mh ? b : a;
 }
 
 // min / max over the CTA of two value pairs at once (level-0 and level-1 cluster ids); results in red[0..3]
@@ -174,7 +186,10 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 1
   for (int e = t; e < m; e += T) {
     long long r, c;
-    if (io.edge16) {   // compact feeder batches: uint16 graph-local ids
+    if (io.edge16 == 2) {   // compact feeder batches: undirected pairs of uint16 graph-local ids
+      sb_ld_half_edge(reinterpret_cast<const uint16_t*>(io.edge_index), io.E, e0, m, e, r, c);
+      if ((m | e0) & 1) r = -1;   // an odd edge count cannot be two mirrored halves: flagged below
+    } else if (io.edge16) {   // uint16 graph-local ids, both directions stored
       r = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)e0 + e];
       c = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)io.E + e0 + e];
     } else {

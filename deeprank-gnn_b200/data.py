@@ -176,18 +176,29 @@ class PackedBatch(object):
     FLOAT_SECTIONS = ('x', 'edge_attr', 'y')
     INT_SECTIONS = ('edge_index', 'cluster0', 'node_ptr', 'edge_ptr', 'c1_ptr')
 
-    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False, max_k0=None, max_k1=None, idx16=False):
+    def __init__(self, B, N, E, L1, F, ne, max_n, max_e, with_class=False, max_k0=None, max_k1=None, idx16=False,
+                 compact=False):
         self.B, self.N, self.E, self.L1, self.F, self.ne = B, N, E, L1, F, ne
         # idx16: edge_index travels as uint16 graph-LOCAL node ids (2E half-words = E words instead of 2E)
         self.idx16 = bool(idx16)
+        # compact (needs idx16): only the FIRST half of every graph's directed edges travels ([2, E/2] uint16 - the
+        # loader stores each edge in both directions, first half i -> j, second half j -> i, DataSet.py:266-269,
+        # so the structure pass mirrors it back) and the cluster ids are uint16: E/2 + N/2 + L1/2 words instead of
+        # E + N + L1 (cfg2: 1.96 -> 1.80 MB per step over PCIe)
+        self.compact = bool(compact) and self.idx16
+        if self.compact and E % 2:
+            raise ValueError('compact records need an even number of directed edges')
         self.max_n, self.max_e = max_n, max_e
         # per-graph cluster-count bounds, rounded up so that batches of one shape share a layout key
         # (and therefore one captured CUDA graph) although their exact counts differ
         self.max_k0 = None if not max_k0 else min(max_n, (max_k0 + 31) // 32 * 32)
         self.max_k1 = None if not max_k1 else min(max_n, (max_k1 + 15) // 16 * 16)
         self.with_class = with_class
-        sizes = dict(x=N * F, edge_attr=E * ne, y=B, edge_index=(E if self.idx16 else 2 * E), cluster0=N, cluster1=L1, node_ptr=B + 1,
-                     edge_ptr=B + 1, c1_ptr=B + 1)
+        half = lambda n: (n + 1) // 2
+        sizes = dict(x=N * F, edge_attr=E * ne, y=B,
+                     edge_index=(E // 2 if self.compact else E if self.idx16 else 2 * E),
+                     cluster0=half(N) if self.compact else N, cluster1=half(L1) if self.compact else L1,
+                     node_ptr=B + 1, edge_ptr=B + 1, c1_ptr=B + 1)
         self.offsets = {}
         o = 0
         for k in self.FLOAT_SECTIONS + self.INT_SECTIONS:
@@ -196,16 +207,16 @@ class PackedBatch(object):
         if with_class:
             self.offsets['y_class'] = (o, 2 * B)
             o += _pad4(2 * B)
-        self.offsets['cluster1'] = (o, L1)
-        self.numel = o + _pad4(L1)
-        self.capacity_numel = o + _pad4(N)          # len(cluster1) <= N
+        self.offsets['cluster1'] = (o, sizes['cluster1'])
+        self.numel = o + _pad4(sizes['cluster1'])
+        self.capacity_numel = o + _pad4(sizes['cluster0'])          # len(cluster1) <= N
         self.buf = None
         self.mol = None
         self.has_y = False
 
     def layout_key(self):
         return (self.B, self.N, self.E, self.F, self.ne, self.max_n, self.max_e, self.with_class, self.max_k0, self.max_k1,
-                self.idx16)
+                self.idx16, self.compact)
 
     @property
     def nbytes(self):
@@ -230,7 +241,15 @@ class PackedBatch(object):
             v['cluster1'] = ibuf[o:o + self.N]
         v['x'] = v['x'].view(self.N, self.F)
         v['edge_attr'] = v['edge_attr'].view(self.E, self.ne) if self.ne else None
-        if self.idx16:
+        if self.compact:                            # uint16 sections (torch has no uint16: int16 views, ids <= 32767)
+            hbuf = buf.view(torch.int16)
+            o, _n = self.offsets['edge_index']
+            v['edge_index'] = hbuf[2 * o:2 * o + self.E].view(2, self.E // 2)
+            o, _n = self.offsets['cluster0']
+            v['cluster0'] = hbuf[2 * o:2 * o + self.N]
+            o, _n = self.offsets['cluster1']
+            v['cluster1'] = hbuf[2 * o:2 * o + (self.N if capacity else self.L1)]
+        elif self.idx16:
             o, _n = self.offsets['edge_index']
             v['edge_index'] = buf.view(torch.int16)[2 * o:2 * o + 2 * self.E].view(2, self.E)
         else:
@@ -243,12 +262,35 @@ class PackedBatch(object):
         return v
 
     @staticmethod
-    def from_batch(batch, pin=None, classes=None, edge_attr=True, idx16=False):
+    def _mirrored_halves(batch):
+        """Boolean mask of the edges in the FIRST half of their graph's edge list when every graph stores its
+        edges as [i -> j pairs | the same pairs j -> i] (the loader's layout, DataSet.py:266-269); None otherwise."""
+        ep = batch._edge_ptr.long()
+        counts = ep[1:] - ep[:-1]
+        if int((counts % 2).sum()) != 0:
+            return None
+        E = batch.edge_index.size(1)
+        if E == 0:
+            return torch.zeros(0, dtype=torch.bool)
+        start = torch.repeat_interleave(ep[:-1], counts)
+        half = torch.repeat_interleave(counts // 2, counts)
+        pos = torch.arange(E) - start
+        first = pos < half
+        ei = batch.edge_index
+        a, b = ei[:, first], ei[:, ~first]         # per graph, both keep their order: pair k of a graph <-> pair k
+        if not (torch.equal(a[0], b[1]) and torch.equal(a[1], b[0])):
+            return None
+        return first
+
+    @staticmethod
+    def from_batch(batch, pin=None, classes=None, edge_attr=True, idx16=False, compact=None):
         """Pack a collated ``Batch``.  ``classes``: for classification, the class list used to
         map targets to class indices (``format_output``, NeuralNet.py:616-631).  Compact options that
         cut the bytes a step moves over PCIe: ``edge_attr=False`` leaves the edge attributes out
         (GINet's attention is the identity - alpha == 1, SURVEY a1 - and FoutNet ignores them; only sGAT
-        reads them), ``idx16=True`` stores ``edge_index`` as uint16 graph-local node ids."""
+        reads them), ``idx16=True`` stores ``edge_index`` as uint16 graph-local node ids; ``compact`` (default: with
+        ``idx16``, whenever the batch allows it) additionally sends only the first half of every graph's mirrored
+        edge list and the cluster ids as uint16."""
         if batch._node_ptr is None or batch._c1_ptr is None:
             raise ValueError('PackedBatch needs a Batch collated by Batch.from_data_list with cluster0/cluster1')
         x = batch.x
@@ -261,8 +303,15 @@ class PackedBatch(object):
             ea = None
         ne = 0 if ea is None else ea.size(1)
         idx16 = bool(idx16) and batch._max_n <= 32767
+        half_mask = None
+        if idx16 and (compact is None or compact):
+            c0, c1 = batch.cluster0, batch.cluster1
+            ids_ok = (c0.numel() == 0 or (int(c0.min()) >= 0 and int(c0.max()) <= 32767)) and \
+                (c1.numel() == 0 or (int(c1.min()) >= 0 and int(c1.max()) <= 32767))
+            half_mask = PackedBatch._mirrored_halves(batch) if ids_ok else None
         pb = PackedBatch(batch.num_graphs, N, E, batch.cluster1.numel(), F, ne, batch._max_n, batch._max_e,
-                         with_class=classes is not None, max_k0=batch._max_k0, max_k1=batch._max_k1, idx16=idx16)
+                         with_class=classes is not None, max_k0=batch._max_k0, max_k1=batch._max_k1, idx16=idx16,
+                         compact=half_mask is not None)
         pin = torch.cuda.is_available() if pin is None else pin
         pb.buf = torch.zeros(pb.numel, dtype=torch.float32, pin_memory=bool(pin))
         v = pb.views(pb.buf)
@@ -279,7 +328,8 @@ class PackedBatch(object):
         if idx16:
             counts = (batch._edge_ptr[1:] - batch._edge_ptr[:-1]).long()
             first = torch.repeat_interleave(batch._node_ptr[:-1].long(), counts)     # first node of every edge's graph
-            v['edge_index'].copy_(batch.edge_index - first.unsqueeze(0))
+            local = batch.edge_index - first.unsqueeze(0)
+            v['edge_index'].copy_(local[:, half_mask] if pb.compact else local)
         else:
             v['edge_index'].copy_(batch.edge_index)
         v['cluster0'].copy_(batch.cluster0)
@@ -311,7 +361,7 @@ class PackedCache(object):
         metas, blobs, off = [], [], 0
         for pb in packed_batches:
             m = {k: int(getattr(pb, k)) for k in PackedCache.FIELDS}
-            m.update(with_class=bool(pb.with_class), idx16=bool(pb.idx16), has_y=bool(pb.has_y),
+            m.update(with_class=bool(pb.with_class), idx16=bool(pb.idx16), compact=bool(pb.compact), has_y=bool(pb.has_y),
                      max_k0=pb.max_k0, max_k1=pb.max_k1, numel=int(pb.numel), offset=off,
                      mol=list(pb.mol) if pb.mol is not None else None)
             metas.append(m)
@@ -378,7 +428,7 @@ class PackedCache(object):
     def __getitem__(self, i):
         m = self.records[i]
         pb = PackedBatch(m['B'], m['N'], m['E'], m['L1'], m['F'], m['ne'], m['max_n'], m['max_e'],
-                         with_class=m['with_class'], idx16=m['idx16'])
+                         with_class=m['with_class'], idx16=m['idx16'], compact=m.get('compact', False))
         pb.max_k0, pb.max_k1 = m['max_k0'], m['max_k1']          # stored already rounded
         assert pb.numel == m['numel'], 'packed-cache record %d does not match the record layout' % i
         start = m['offset'] // 4

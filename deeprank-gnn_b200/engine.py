@@ -194,7 +194,8 @@ class Workspace(object):
 class DeviceBatch(object):
     """The tensors of one mini-batch the engine consumes, resident on the device."""
     __slots__ = ('x', 'edge_index', 'edge_attr', 'cluster0', 'cluster1', 'node_ptr', 'edge_ptr', 'c1_ptr', 'y',
-                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'max_k0', 'max_k1', 'mol', 'key', 'sslot')
+                 'y_class', 'B', 'N', 'E', 'L1', 'L1b', 'max_n', 'max_e', 'max_k0', 'max_k1', 'mol', 'key', 'sslot',
+                 'edge_half')
 
     @staticmethod
     def from_batch(batch, device, classes=None):
@@ -230,6 +231,7 @@ class DeviceBatch(object):
         d.mol = getattr(batch, 'mol', None)
         d.key = None
         d.sslot = 0
+        d.edge_half = False
         d.L1b = d.L1                     # upper bound of level-1 rows used for launch sizes
         return d
 
@@ -246,6 +248,7 @@ class DeviceBatch(object):
         d.mol = pb.mol
         d.key = pb.layout_key()
         d.sslot = 0
+        d.edge_half = bool(pb.compact)   # edge_index is [2, E/2]: the first half of every graph's mirrored edge list
         d.L1b = pb.N                     # fixed bound: batches of one layout replay the same CUDA graph
         return d
 
@@ -501,13 +504,13 @@ class Engine(object):
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
                                     d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None,
                                     x=d.x if pre else None, zin_kind=self.spec.kind if pre else None,
-                                    dependent=dependent)
+                                    dependent=dependent, edge_half=d.edge_half)
             assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
         st = ops.structure_build(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e,
                                  c1_ptr=d.c1_ptr, cluster1=d.cluster1, edge_attr=d.edge_attr if need_w else None,
-                                 clusters_are_local=True, mirrors=False, out=slot, L1=d.L1)
+                                 clusters_are_local=True, mirrors=False, out=slot, L1=d.L1, edge_half=d.edge_half)
         assert st is slot
         self._last_struct = st
         return st

@@ -159,7 +159,7 @@ class Structure(object):
 
 
 def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr=None, cluster1=None,
-                    edge_attr=None, clusters_are_local=True, mirrors=False, out=None, L1=None):
+                    edge_attr=None, clusters_are_local=True, mirrors=False, out=None, L1=None, edge_half=False):
     """Run the structure pass for one mini-batch.  ``node_ptr/edge_ptr/c1_ptr`` are int32
     ``[B+1]`` device tensors; ``edge_index`` ``[2,E]`` and ``cluster0/1`` are int64 (reference
     layout) or int32.  Returns a ``Structure`` (``out`` is reused if given)."""
@@ -170,8 +170,12 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     E = edge_index.size(1) if edge_index.dim() == 2 else 0
     # L1: live length of cluster1 when the tensor is a capacity-sized view (packed staging buffers)
     L1 = (0 if cluster1 is None else cluster1.numel()) if L1 is None else int(L1)
-    edge16 = edge_index.dtype == I16     # compact feeder batches: uint16 graph-local node ids, int32 cluster ids
-    if (edge16 and (cluster0.dtype != I32 or (cluster1 is not None and cluster1.dtype != I32))) or \
+    edge16 = edge_index.dtype == I16     # compact feeder batches: uint16 graph-local node ids, int32 / uint16 cluster ids
+    if edge_half:                        # ... of which only the first (undirected) half of every graph travels
+        if not edge16:
+            raise DrgnnError('edge_half needs int16 graph-local edge ids')
+        E *= 2
+    if (edge16 and (cluster0.dtype not in (I32, I16) or (cluster1 is not None and cluster1.dtype != cluster0.dtype))) or \
             (not edge16 and (edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or
                              (cluster1 is not None and cluster1.dtype != edge_index.dtype))):
         raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32), or be '
@@ -207,8 +211,8 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, ne
     io.max_n, io.max_e = int(max_n), int(max_e)
     io.clusters_are_local = 1 if clusters_are_local else 0
-    io.idx32 = 1 if cluster0.dtype == I32 else 0
-    io.edge16 = 1 if edge16 else 0
+    io.idx32 = 2 if cluster0.dtype == I16 else (1 if cluster0.dtype == I32 else 0)
+    io.edge16 = (2 if edge_half else 1) if edge16 else 0
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
     io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)
@@ -239,7 +243,7 @@ def zin1_ld(kind, F):
 
 
 def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None,
-                   edge_attr=None, x=None, zin_kind=None, dependent=False):
+                   edge_attr=None, x=None, zin_kind=None, dependent=False, edge_half=False):
     """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
     structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
     global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
@@ -256,7 +260,11 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     E = edge_index.size(1) if edge_index.dim() == 2 else 0
     L1 = cluster1.numel() if L1 is None else int(L1)
     edge16 = edge_index.dtype == I16
-    if (edge16 and (cluster0.dtype != I32 or cluster1.dtype != I32)) or \
+    if edge_half:                        # compact records: only the first (undirected) half of every graph's edges
+        if not edge16:
+            raise DrgnnError('edge_half needs int16 graph-local edge ids')
+        E *= 2
+    if (edge16 and (cluster0.dtype not in (I32, I16) or cluster1.dtype != cluster0.dtype)) or \
             (not edge16 and (edge_index.dtype not in (I32, I64) or cluster0.dtype != edge_index.dtype or
                              cluster1.dtype != edge_index.dtype)):
         raise DrgnnError('edge_index / cluster0 / cluster1 must share one integer dtype (int64 or int32), or be '
@@ -290,8 +298,8 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     io.B, io.N, io.E, io.L1, io.ne = B, N, E, L1, ne
     io.max_n, io.max_e = int(max_n), int(max_e)
     io.clusters_are_local = 1
-    io.idx32 = 1 if cluster0.dtype == I32 else 0
-    io.edge16 = 1 if edge16 else 0
+    io.idx32 = 2 if cluster0.dtype == I16 else (1 if cluster0.dtype == I32 else 0)
+    io.edge16 = (2 if edge_half else 1) if edge16 else 0
     io.node_ptr, io.edge_ptr, io.c1_ptr = ptr(node_ptr), ptr(edge_ptr), ptr(c1_ptr)
     io.edge_index, io.edge_attr = ptr(edge_index), ptr(edge_attr)
     io.cluster0, io.cluster1 = ptr(cluster0), ptr(cluster1)

@@ -77,9 +77,14 @@ typedef struct drgnn_structure_io {
   int32_t clusters_are_local; /* 1: ids are per-graph local (un-offset, DataSet.py:348-357);
                                  0: ids are already global (must increase with graph id)  */
   int32_t idx32;        /* 0: edge_index / cluster0 / cluster1 are int64 (reference tensors);
-                           1: they are int32 (packed feeder batches)                       */
+                           1: they are int32 (packed feeder batches); 2: cluster0 / cluster1 are uint16
+                           (compact feeder records; needs edge16 != 0)                     */
   int32_t edge16;       /* 1: edge_index is uint16 [2,E] holding graph-LOCAL node ids (compact feeder
-                           batches: half the bytes over PCIe); cluster ids stay int32 (idx32 = 1)   */
+                           batches: half the bytes over PCIe); cluster ids are int32 or uint16 (idx32 = 1 | 2);
+                           2: edge_index is uint16 [2,E/2]: only the FIRST half of every graph's directed edges
+                           travels - the loader stores each edge in both directions, first half i -> j, second
+                           half j -> i (DataSet.py:266-269), so edge m/2 + e of a graph is edge e mirrored; E and
+                           edge_ptr still count directed edges (all even), the graph's pairs start at edge_ptr[g]/2 */
   /* ---- inputs ---- */
   const int32_t* node_ptr;   /* [B+1] */
   const int32_t* edge_ptr;   /* [B+1] */

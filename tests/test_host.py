@@ -123,7 +123,7 @@ def test_batch_collation_and_packed_roundtrip():
     pc = PackedBatch.from_batch(b, pin=False, classes=[0, 1])
     assert pc.views(pc.buf)['y_class'].dtype == torch.int64
     # compact feeder record: uint16 graph-local edge ids, no edge attributes
-    cp = PackedBatch.from_batch(b, pin=False, idx16=True, edge_attr=False)
+    cp = PackedBatch.from_batch(b, pin=False, idx16=True, edge_attr=False, compact=False)
     cv = cp.views(cp.buf)
     assert cp.nbytes < pb.nbytes - 4 * b.edge_index.size(1) and cv['edge_attr'] is None
     assert cv['edge_index'].dtype == torch.int16 and int(cv['edge_index'].max()) < 200
@@ -134,6 +134,29 @@ def test_batch_collation_and_packed_roundtrip():
     dev_like = torch.zeros(cp.capacity_numel)          # staging-buffer sized views keep the same offsets
     dev_like[:cp.numel] = cp.buf
     assert torch.equal(cp.views(dev_like)['edge_index'], cv['edge_index'])
+    # ... and the default compact form: the loader stores every edge in both directions (first half i -> j, second
+    # half j -> i, DataSet.py:266-269), so only the first half of every graph's list travels; cluster ids as uint16
+    hp = PackedBatch.from_batch(b, pin=False, idx16=True, edge_attr=False)
+    assert hp.compact and not cp.compact and hp.layout_key() != cp.layout_key()
+    E, N, L1 = b.edge_index.size(1), b.x.size(0), b.cluster1.numel()
+    assert cp.nbytes - hp.nbytes >= 4 * (E // 2 + N // 2 + L1 // 2) - 48
+    hv = hp.views(hp.buf)
+    assert hv['edge_index'].shape == (2, E // 2) and hv['cluster0'].dtype == torch.int16
+    local = b.edge_index - first
+    for g in range(5):                                                          # graph g: pairs [500 g, 500 g + 500)
+        half = hv['edge_index'][:, 500 * g:500 * (g + 1)].long()
+        assert torch.equal(half, local[:, 1000 * g:1000 * g + 500])
+        assert torch.equal(half.flip(0), local[:, 1000 * g + 500:1000 * (g + 1)])
+    assert torch.equal(hv['cluster0'].long(), b.cluster0) and torch.equal(hv['cluster1'].long(), b.cluster1)
+    assert torch.equal(hv['x'], b.x) and torch.equal(hv['node_ptr'], b._node_ptr) and torch.equal(hv['edge_ptr'], b._edge_ptr)
+    dev_like = torch.zeros(hp.capacity_numel)
+    dev_like[:hp.numel] = hp.buf
+    assert hp.views(dev_like, capacity=True)['cluster1'].numel() == N
+    assert torch.equal(hp.views(dev_like, capacity=True)['cluster1'][:L1], hv['cluster1'])
+    # a batch whose edge list is not two mirrored halves keeps the full list
+    gs = synthetic.make_graphs('cfg2', count=2, seed=4)
+    gs[1].edge_index = gs[1].edge_index[:, torch.randperm(gs[1].edge_index.size(1), generator=torch.Generator().manual_seed(1))]
+    assert not PackedBatch.from_batch(Batch.from_data_list(gs), pin=False, idx16=True, edge_attr=False).compact
 
     class DS(object):
         def len(self):

@@ -27,7 +27,7 @@ def _close_abs(a, b, name, tol=1e-4):
     assert err <= tol, '%s: max|diff| = %.3e (absolute bound %.1e)' % (name, err, tol)
 
 
-def _pool(cfg, n_batches, B, seed, edge_attr=False):
+def _pool(cfg, n_batches, B, seed, edge_attr=False, compact=None):
     from deeprank_gnn_b200 import synthetic
     from deeprank_gnn_b200.data import Batch, PackedBatch
     graphs = synthetic.make_graphs(cfg, count=2 * B, seed=seed, internal=False)
@@ -36,7 +36,7 @@ def _pool(cfg, n_batches, B, seed, edge_attr=False):
     for _ in range(n_batches):
         idx = torch.randperm(len(graphs), generator=g)[:B].tolist()
         packed.append(PackedBatch.from_batch(Batch.from_data_list([graphs[i] for i in idx]), idx16=True,
-                                             edge_attr=edge_attr))
+                                             edge_attr=edge_attr, compact=compact))
     return packed
 
 
@@ -141,7 +141,8 @@ def test_malformed_batch_in_the_middle_of_a_pass_is_reported_and_contained(lib, 
     armed wrong and every later step reduces garbage): after the error a clean step equals a fresh engine's."""
     from deeprank_gnn_b200._lib import DrgnnError
     from deeprank_gnn_b200.engine import Engine
-    packed = _pool('cfg2', 9, 12, seed=23)
+    # (uint16 cluster ids of the compact records cannot leave the bitmap range: that fault needs int32 ids)
+    packed = _pool('cfg2', 9, 12, seed=23, compact=None if fault == 'edge_outside' else False)
     bad = packed[4]
     v = bad.views(bad.buf)
     if fault == 'edge_outside':
@@ -221,3 +222,34 @@ def test_batch_without_clusters_is_refused_like_the_reference(lib):
         del g.cluster0, g.cluster1
     with pytest.raises(DrgnnError, match='cluster0'):
         DeviceBatch.from_batch(Batch.from_data_list(graphs), 'cuda:0')
+
+
+@pytest.mark.parametrize('case', ['GINet-blob', 'sGAT-blob', 'FoutNet-large'])
+def test_compact_records_give_the_same_structure_and_steps(lib, case):
+    """Compact feeder records (first half of every graph's mirrored edge list, uint16 cluster ids) against the
+    full uint16 records: the structure pass rebuilds bit-identical blobs (bitmap pass and counting-sort pass) and
+    training steps leave bit-identical predictions, loss and weights."""
+    from deeprank_gnn_b200 import synthetic
+    from deeprank_gnn_b200.data import Batch, PackedBatch
+    from deeprank_gnn_b200.engine import Engine
+    net = case.split('-')[0]
+    cfg = dict(nodes=(300, 600), edges_per_node=8, feat=32) if case.endswith('large') else dict(nodes=(20, 200), edges_per_node=5, feat=32)
+    graphs = synthetic.make_graphs(cfg, count=12, seed=17, internal=False)
+    b = Batch.from_data_list(graphs)
+    full = PackedBatch.from_batch(b, idx16=True, edge_attr=net == 'sGAT', compact=False)
+    half = PackedBatch.from_batch(b, idx16=True, edge_attr=net == 'sGAT')
+    assert half.compact and not full.compact and half.nbytes < full.nbytes
+    ea = Engine(net, 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=0.0)
+    eb = Engine(net, 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=0.0)
+    da, db = ea.upload(full), eb.upload(half)
+    assert db.edge_half and not da.edge_half and db.cluster0.dtype == torch.int16
+    for step in range(3):
+        la, pa = ea.step(da)
+        lb, pb_ = eb.step(db)
+        ea.validate(), eb.validate()
+        sa, sb = ea.structs[da.sslot], eb.structs[db.sslot]
+        assert sa.blob_only == sb.blob_only == case.endswith('blob')
+        assert torch.equal(sa.blob, sb.blob)
+        assert torch.equal(torch.nan_to_num(pa, nan=-7.0), torch.nan_to_num(pb_, nan=-7.0))
+        assert torch.equal(torch.nan_to_num(la, nan=-7.0), torch.nan_to_num(lb, nan=-7.0))
+    assert torch.equal(torch.nan_to_num(ea.params.data, nan=-7.0), torch.nan_to_num(eb.params.data, nan=-7.0))
