@@ -409,8 +409,14 @@ def run_b200(args):
         raise RuntimeError('bench.py needs a CUDA device: the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    from deeprank_gnn_b200.parallel import bind_to_gpu_numa_node
-    numa = bind_to_gpu_numa_node(local) if world > 1 else 'single process: not bound'
+    from deeprank_gnn_b200.parallel import bind_to_gpu_numa_node, prefer_gpu_numa_memory
+    # the pinned host batches must live in the memory next to the GPU's PCIe root (H2D copies out of the other
+    # socket's memory are 15-40 % slower): several ranks bind their CPUs, a single process only sets its memory
+    # policy (it keeps every core for the CPU baseline and resets the policy before that leg)
+    if os.environ.get('DRGNN_BENCH_NUMA', '1') == '0':
+        numa = 'not bound (DRGNN_BENCH_NUMA=0)'
+    else:
+        numa = bind_to_gpu_numa_node(local) if world > 1 else prefer_gpu_numa_memory(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # keep stdout to the one JSON line: NCCL prints its version banner (and anything else) to stdout
@@ -581,6 +587,7 @@ def run_b200(args):
         if dense is not None:
             line['roofline']['dense'] = dense
     if world == 1 and not args.no_cpu:
+        prefer_gpu_numa_memory(local, enable=False)        # the CPU leg allocates under the default policy
         gps, ms, n = cpu_steps(cfg, batches[:8], seconds=args.cpu_seconds, warmup=2)
         cores = torch.get_num_threads()
         line['cpu_baseline'] = {'value': gps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'ms_per_step': ms,

@@ -61,6 +61,49 @@ def bind_to_gpu_numa_node(device_index):
         return 'unbound (%s)' % e
 
 
+def _gpu_numa_node(device_index):
+    """NUMA node of the GPU's PCI function (from /sys), or None."""
+    props = torch.cuda.get_device_properties(device_index)
+    if not all(hasattr(props, k) for k in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+        return None
+    bdf = '%04x:%02x:%02x.0' % (int(props.pci_domain_id), int(props.pci_bus_id), int(props.pci_device_id))
+    node_path = '/sys/bus/pci/devices/%s/numa_node' % bdf
+    if not os.path.exists(node_path):
+        return None
+    with open(node_path) as f:
+        node = int(f.read().strip())
+    return node if node >= 0 else None
+
+
+def prefer_gpu_numa_memory(device_index, enable=True):
+    """Memory policy of the calling thread: prefer the NUMA node the GPU hangs off (``enable=False``: back to the
+    default policy).  Pinned host blocks allocated afterwards (``PackedBatch``) then live next to the GPU's PCIe
+    root - the same H2D copy is 15-40 % slower out of the other socket's memory - WITHOUT touching the CPU affinity
+    (a single-process run keeps every core, e.g. for the CPU baseline timed in the same process).  Linux
+    ``set_mempolicy`` through ctypes; returns a short description, never raises."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        SYS_set_mempolicy, MPOL_DEFAULT, MPOL_PREFERRED = 238, 0, 1          # x86-64
+        import platform
+        if platform.machine() not in ('x86_64', 'AMD64'):
+            return 'memory policy unchanged (not x86-64)'
+        if not enable:
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_DEFAULT, None, 0)
+            return 'default memory policy' if rc == 0 else 'memory policy unchanged (errno %d)' % ctypes.get_errno()
+        node = _gpu_numa_node(device_index)
+        if node is None:
+            return 'memory policy unchanged (single NUMA node)'
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, 16 * 64 + 1)
+        if rc != 0:
+            return 'memory policy unchanged (errno %d)' % ctypes.get_errno()
+        return 'single process: host memory preferred on NUMA node %d (the GPU\'s), CPU affinity unchanged' % node
+    except Exception as e:                         # pragma: no cover - best effort
+        return 'memory policy unchanged (%s)' % e
+
+
 def graph_cost(d):
     """Work estimate of one graph: nodes + directed edges."""
     return int(d.num_nodes) + int(d.num_edges)
