@@ -51,7 +51,7 @@ class StructureIO(C.Structure):
         ('gstat', VP), ('scratch_n', VP), ('scratch_e', VP), ('scratch_f', VP),
         ('blob', VP), ('wblob', VP),
         ('x', VP), ('zin1', VP), ('F', C.c_int32), ('ld_zin1', C.c_int32), ('zin_kind', C.c_int32),
-        ('launch_flags', C.c_int32),
+        ('launch_flags', C.c_int32), ('max_k', C.c_int32), ('max_q', C.c_int32),
     ]
 
 
@@ -253,6 +253,7 @@ _SIGNATURES = {
     'drgnn_debug_phase_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_debug_blob_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_structure_blob_smem_bytes': (_i64, [_i32, _i32]),
+    'drgnn_structure_blob_smem_bytes_ex': (_i64, [_i32, _i32, _i32, _i32, _i32]),
     'drgnn_structure_blob': (C.c_int, [C.POINTER(StructureIO), VP]),
     'drgnn_net_step_smem_bytes': (_i64, [_i32] * 11),
     'drgnn_net_step_pick_tiles': (C.c_int, [_i32] * 10),

@@ -5,16 +5,18 @@
 //   get_preloaded_cluster / consecutive_cluster   community_pooling.py:25-30, 197; ginet.py:114,129
 //   pool_edge + coalesce (structure only)          community_pooling.py:204-205
 //   the dst-sorted CSR the aggregation reads instead of x[col] + scatter_add (ginet.py:57-71)
-// but built for the graphs the fused step kernel takes (a few hundred nodes, a few thousand edges):
-// every sorted list is read off a BITMAP instead of being produced by a counting sort -
-//   row i of the level-0 CSR        = set bits of rowbits[i][.]  over the edge ids      (ascending e)
+// but built for one CTA per graph with everything in shared memory: the sorted lists of the COARSENED graph are
+// read off bitmaps instead of being produced by counting sorts -
 //   pooled row r / pooled column c  = set bits of bm[r][.] / bmT[c][.] over pooled ids   (sorted, unique)
 //   members of cluster k / q        = set bits of mem0[k][.] / mem1[q][.] over node ids  (ascending)
-// so the whole pass is: load -> two presence bitmaps + popcount prefixes (dense relabel of both
-// cluster levels) -> ONE scatter sweep of atomicOr -> ONE exclusive scan over all row counts ->
-// ONE emit sweep (a thread per item ranks itself by popcounts).  About a dozen CTA barriers in total; the
-// counting-sort pass needs ~60.  Nothing cross-graph is computed: the blob holds graph-local indices
-// and the fused kernels need no global offsets (no finalize launch).
+// (bitmaps sized by the host's per-graph cluster bounds max_k / max_q, checked in the kernel), and the level-0 CSR
+// (rows by destination, ascending edge id inside a row = the CPU scatter order) comes from an atomic slot
+// assignment followed by a rank sweep inside every row (an edge's place = the number of smaller edge ids in its
+// row: deterministic, no per-row bitmap over the edges - that bitmap was n x m / 32 words and kept graphs beyond
+// ~250 nodes out of this pass).  The whole pass is: load -> two presence bitmaps + popcount prefixes (dense relabel of
+// both cluster levels) -> ONE scatter sweep -> ONE exclusive scan over all row counts -> emit sweeps.  About a dozen
+// CTA barriers in total; the counting-sort pass needs ~60.  Nothing cross-graph is computed: the blob holds
+// graph-local indices and the fused kernels need no global offsets (no finalize launch).
 #include <limits.h>
 
 #include "common.cuh"
@@ -24,7 +26,6 @@ namespace drgnn {
 static constexpr int SB_THREADS = 512;
 static constexpr int SB_WARPS = SB_THREADS / 32;
 static constexpr int SB_CAP_WORDS = 1024;        // presence bitmap: cluster-id range of one graph <= 32768
-static constexpr int SB_ROWBITS_MAX = 20 * 1024; // words of the level-0 row bitmap (80 KB)
 
 __device__ unsigned long long g_bphase[16];
 #define DRGNN_BPHASE(i)                                                         \
@@ -33,22 +34,30 @@ __device__ unsigned long long g_bphase[16];
   } while (0)
 
 struct BlobPlan {   // word offsets into dynamic shared memory
-  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, rowbits, bm, bmT, mem0, mem1, cnt, ea, eord, total;
-  int mw1;   // row stride of rowbits: ceil(max_e/32) + 1 (odd strides keep a thread-per-row walk conflict-free)
-  int kw1;   // row stride of the pooled / member bitmaps: ceil(max_n/32) + 1
+  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, bm, bmT, mem0, mem1, cnt, ea, eord, eun, total;
+  int max_k, max_q;   // per-graph bounds of the level-0 / level-1 cluster counts the bitmaps are sized for
+  int kwk;   // row stride of bm / bmT / mem1 (bitmaps over pooled-node ids): ceil(max_k/32), made odd
+  int kwn;   // row stride of mem0 (bitmap over node ids): ceil(max_n/32), made odd
 };
 __host__ __device__ inline int sb_up4(int x) { return (x + 3) & ~3; }
-__host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e) {
+__host__ __device__ inline int sb_odd_words(int bits) {   // words for `bits` bits, odd and strictly larger (conflict-free row walks)
+  int w = ((bits + 31) >> 5) | 1;
+  if (w == ((bits + 31) >> 5)) w += 2;
+  return w;
+}
+__host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e, int max_k, int max_q, int weights) {
   BlobPlan p;
   int o = 0;
   auto take = [&](int words) { const int at = o; o += sb_up4(words); return at; };
-  p.mw1 = ((max_e + 31) >> 5) | 1;
-  if (p.mw1 == ((max_e + 31) >> 5)) p.mw1 += 2;   // odd and strictly larger than the word count
-  p.kw1 = ((max_n + 31) >> 5) | 1;
-  if (p.kw1 == ((max_n + 31) >> 5)) p.kw1 += 2;
+  if (max_k <= 0 || max_k > max_n) max_k = max_n;
+  if (max_q <= 0 || max_q > max_k) max_q = max_k;
+  p.max_k = max_k;
+  p.max_q = max_q;
+  p.kwk = sb_odd_words(max_k);
+  p.kwn = sb_odd_words(max_n);
   p.erow = take((max_e + 1) / 2);
   p.ecol = take((max_e + 1) / 2);
-  p.id0 = take(max_n);
+  p.id0 = take(max_n);            // raw ids minus their minimum; later the fill counters of the level-0 rows
   p.id1 = take(max_n);
   p.dense0 = take((max_n + 1) / 2);
   p.dense1 = take((max_n + 1) / 2);
@@ -56,14 +65,14 @@ __host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e) {
   p.cb1 = take(SB_CAP_WORDS);
   p.cp0 = take(SB_CAP_WORDS);
   p.cp1 = take(SB_CAP_WORDS);
-  p.rowbits = take(max_n * p.mw1);
-  p.bm = take(max_n * p.kw1);
-  p.bmT = take(max_n * p.kw1);
-  p.mem0 = take(max_n * p.kw1);
-  p.mem1 = take(max_n * p.kw1);
-  p.cnt = take(5 * max_n + 8);
-  p.ea = take(max_e);   // edge attributes of the graph (sGAT weights; 4 KB at 1000 edges)
-  p.eord = take((max_e + 1) / 2);
+  p.bm = take(max_k * p.kwk);
+  p.bmT = take(max_k * p.kwk);
+  p.mem0 = take(max_k * p.kwn);
+  p.mem1 = take(max_q * p.kwk);
+  p.cnt = take(max_n + 3 * max_k + max_q + 8);
+  p.ea = take(weights ? max_e : 0);   // edge attributes of the graph (sGAT weights; 4 KB at 1000 edges)
+  p.eord = take((max_e + 1) / 2);     // edge id of every level-0 CSR slot
+  p.eun = take((max_e + 1) / 2);      // ... before the rank sweep (atomic slot order)
   p.total = o;
   return p;
 }
@@ -142,12 +151,13 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   uint32_t* cb0 = sb + P.cb0; uint32_t* cb1 = sb + P.cb1;
   int* cp0 = reinterpret_cast<int*>(sb + P.cp0);
   int* cp1 = reinterpret_cast<int*>(sb + P.cp1);
-  uint32_t* rowbits = sb + P.rowbits;
   uint32_t* bm = sb + P.bm; uint32_t* bmT = sb + P.bmT; uint32_t* mem0 = sb + P.mem0; uint32_t* mem1 = sb + P.mem1;
   int* cnt = reinterpret_cast<int*>(sb + P.cnt);
+  int* fill = id0;                      // fill counters of the level-0 rows (the raw ids are dead by then)
   float* eas = reinterpret_cast<float*>(sb + P.ea);
   uint16_t* eord = reinterpret_cast<uint16_t*>(sb + P.eord);
-  const int MW1 = P.mw1, KW1 = P.kw1;
+  uint16_t* eun = reinterpret_cast<uint16_t*>(sb + P.eun);
+  const int KWK = P.kwk, KWN = P.kwn;
   DRGNN_BPHASE(0);
 
   const int n0 = io.node_ptr[g], n = io.node_ptr[g + 1] - n0;
@@ -172,16 +182,14 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   if (bad1) c1len = 0;
 
   // ---- 0. zero every bitmap (the presence words follow once the id ranges are known)
-  {
-    const int MW = (m + 31) >> 5, KWn = (n + 31) >> 5;
 #pragma unroll 1
-    for (int i = t; i < n * MW1; i += T) rowbits[i] = 0u;
-#pragma unroll 1
-    for (int i = t; i < n * KW1; i += T) {
-      bm[i] = 0u; bmT[i] = 0u; mem0[i] = 0u; mem1[i] = 0u;
-    }
-    (void)MW; (void)KWn;
+  for (int i = t; i < P.max_k * KWK; i += T) {
+    bm[i] = 0u; bmT[i] = 0u;
   }
+#pragma unroll 1
+  for (int i = t; i < P.max_k * KWN; i += T) mem0[i] = 0u;
+#pragma unroll 1
+  for (int i = t; i < P.max_q * KWK; i += T) mem1[i] = 0u;
   // ---- 1. local edge list; cluster ids of both levels (read from global memory once), their extremes
 #pragma unroll 1
   for (int e = t; e < m; e += T) {
@@ -296,6 +304,11 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER1_LENGTH);
     bad1 = true;
   }
+  if (K > P.max_k || K1 > P.max_q) {   // the host's per-graph cluster bounds (bitmap sizes) are violated: blob stays incomplete
+    if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    return;
+  }
   DRGNN_BPHASE(2);
   // ---- 4. dense ids (consecutive_cluster restricted to the graph); into the blob as cl0 / cl1
 #pragma unroll 1
@@ -324,13 +337,12 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 1
   for (int e = t; e < m; e += T) {
     const int r = erow[e], c = ecol[e];
-    atomicOr(&rowbits[r * MW1 + (e >> 5)], 1u << (e & 31));
     atomicAdd(&cnt[r], 1);
     const int pr = dense0[r], pc = dense0[c];
     if (pr != pc) {   // remove_self_loops of pool_edge
       const uint32_t bit = 1u << (pc & 31);
-      if (!(atomicOr(&bm[pr * KW1 + (pc >> 5)], bit) & bit)) {   // first edge of this pooled pair
-        atomicOr(&bmT[pc * KW1 + (pr >> 5)], 1u << (pr & 31));
+      if (!(atomicOr(&bm[pr * KWK + (pc >> 5)], bit) & bit)) {   // first edge of this pooled pair
+        atomicOr(&bmT[pc * KWK + (pr >> 5)], 1u << (pr & 31));
         atomicAdd(&cnt[n + pr], 1);
         atomicAdd(&cnt[n + K + pc], 1);
       }
@@ -339,13 +351,14 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 1
   for (int i = t; i < n; i += T) {
     const int k = dense0[i];
-    atomicOr(&mem0[k * KW1 + (i >> 5)], 1u << (i & 31));
+    atomicOr(&mem0[k * KWN + (i >> 5)], 1u << (i & 31));
     atomicAdd(&cnt[n + 2 * K + k], 1);
+    fill[i] = 0;
   }
 #pragma unroll 1
   for (int i = t; i < c1len; i += T) {
     const int q = dense1[i];
-    atomicOr(&mem1[q * KW1 + (i >> 5)], 1u << (i & 31));
+    atomicOr(&mem1[q * KWK + (i >> 5)], 1u << (i & 31));
     atomicAdd(&cnt[n + 3 * K + q], 1);
   }
   __syncthreads();
@@ -356,24 +369,31 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   const int E1 = baseT - base1;
   const int KWk = (K + 31) >> 5;
   DRGNN_BPHASE(4);
-  // ---- 7. ONE emit sweep, a thread per ITEM: its slot = start of its row + number of set bits of the
-  // row below its own bit (popcount of the words before + of the lower bits of its word)
+  // ---- 7. emit.  Level-0 CSR: every edge takes a slot of its row (atomic: any order), then every slot ranks its
+  // edge id among the ids of its row - ascending edge id inside a row = the CPU scatter order, deterministic.
 #pragma unroll 1
-  for (int e = t; e < m; e += T) {          // level-0 CSR: ascending edge id inside a row = the CPU scatter order
-    const int r = erow[e], wi = e >> 5;
-    const uint32_t* row = rowbits + r * MW1;
-    int pos = cnt[r] + __popc(row[wi] & ((1u << (e & 31)) - 1u));
+  for (int e = t; e < m; e += T) {
+    const int r = erow[e];
+    eun[cnt[r] + atomicAdd(&fill[r], 1)] = (uint16_t)e;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int p = t; p < m; p += T) {
+    const int e = eun[p], r = erow[e];
+    const int a = cnt[r], b = cnt[r + 1];           // cnt[n] = m closes the last row
+    int rank = 0;
 #pragma unroll 4
-    for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
+    for (int q = a; q < b; ++q) rank += (int)eun[q] < e ? 1 : 0;
+    const int pos = a + rank;
+    eord[pos] = (uint16_t)e;       // edge id of the CSR slot: the weight sums / the first aggregation walk a node's edges in slot order
     bl[BL.col0 + pos] = ecol[e];
     if (wb) wb[BL.col0 + pos] = eas[e];
-    if (wb || io.zin1) eord[pos] = (uint16_t)e;   // edge id of the CSR slot: the weight sums / the first aggregation walk a node's edges in slot order
   }
 #pragma unroll 1
   for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
     bl[BL.rp0 + i] = cnt[i];
     const int k = dense0[i], wi = i >> 5;
-    const uint32_t* row = mem0 + k * KW1;
+    const uint32_t* row = mem0 + k * KWN;
     int pos = cnt[n + 2 * K + k] - baseM0 + __popc(row[wi] & ((1u << (i & 31)) - 1u));
 #pragma unroll 1
     for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 1
   for (int i = t; i < c1len; i += T) {      // members of the level-1 clusters, ascending pooled-node id
     const int q = dense1[i], wi = i >> 5;
-    const uint32_t* row = mem1 + q * KW1;
+    const uint32_t* row = mem1 + q * KWK;
     int pos = cnt[n + 3 * K + q] - baseM1 + __popc(row[wi] & ((1u << (i & 31)) - 1u));
 #pragma unroll 1
     for (int ww = 0; ww < wi; ++ww) pos += __popc(row[ww]);
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     const int which = item >= K * KWk;
     const int it = which ? item - K * KWk : item;
     const int r = it / KWk, wi = it - r * KWk;
-    const uint32_t* row = (which ? bmT : bm) + r * KW1;
+    const uint32_t* row = (which ? bmT : bm) + r * KWK;
     int q = which ? cnt[n + K + r] - baseT : cnt[n + r] - base1;
 #pragma unroll 1
     for (int ww = 0; ww < wi; ++ww) q += __popc(row[ww]);
@@ -427,8 +447,8 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     DRGNN_BPHASE(6);
 #pragma unroll 1
     for (int r = w; r < K; r += SB_WARPS) {
-      const uint32_t* row = bm + r * KW1;
-      const uint32_t* mrow = mem0 + r * KW1;
+      const uint32_t* row = bm + r * KWK;
+      const uint32_t* mrow = mem0 + r * KWN;
       const int rbase = cnt[n + r] - base1;
       const int rcnt = cnt[n + r + 1] - base1 - rbase;     // cnt[n + K] = baseT = base1 + E1 closes the last row
 #pragma unroll 1
@@ -479,7 +499,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
         if (s0 + lane < rcnt) {
           wb[BL.col1 + rbase + s0 + lane] = acc;
           // the same weight at the edge's pooled-CSC slot: column tc, rank of row r among the rows of bmT[tc]
-          const uint32_t* rowT = bmT + tc * KW1;
+          const uint32_t* rowT = bmT + tc * KWK;
           int posT = cnt[n + K + tc] - baseT + __popc(rowT[r >> 5] & ((1u << (r & 31)) - 1u));
 #pragma unroll 1
           for (int ww = 0; ww < (r >> 5); ++ww) posT += __popc(rowT[ww]);
@@ -563,14 +583,17 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 
 using namespace drgnn;
 
-extern "C" int64_t drgnn_structure_blob_smem_bytes(int32_t max_n, int32_t max_e) {
+extern "C" int64_t drgnn_structure_blob_smem_bytes_ex(int32_t max_n, int32_t max_e, int32_t max_k, int32_t max_q,
+                                                      int32_t weights) {
   if (max_n <= 0 || max_e < 0) return DRGNN_ERR_INVALID;
-  if (max_n > 16384 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;
-  const BlobPlan p = blob_plan(max_n, max_e);
-  if ((int64_t)max_n * p.mw1 > SB_ROWBITS_MAX) return DRGNN_ERR_UNSUPPORTED;
+  if (max_n > 16384 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;   // uint16 ids inside the kernel
+  const BlobPlan p = blob_plan(max_n, max_e, max_k, max_q, weights);
   const int64_t bytes = 4 * (int64_t)p.total;
   if (bytes > device_info().smem_optin - 4096) return DRGNN_ERR_UNSUPPORTED;
   return bytes;
+}
+extern "C" int64_t drgnn_structure_blob_smem_bytes(int32_t max_n, int32_t max_e) {
+  return drgnn_structure_blob_smem_bytes_ex(max_n, max_e, 0, 0, 1);
 }
 
 // Blob-only structure pass (the inputs of drgnn_structure_build; outputs: io->blob, io->status,
@@ -588,17 +611,18 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
                                io->ld_zin1 % 4 == 0 && io->ld_zin1 >= (io->zin_kind ? 2 * io->F + 4 : io->F)),
                 "structure_blob: first aggregation requested with an invalid x / F / ld_zin1 / zin_kind");
   DRGNN_REQUIRE(!io->zin1 || io->zin_kind != 1 || (io->wblob && io->edge_attr), "structure_blob: the sGAT aggregation needs edge_attr and wblob");
-  const int64_t smem = drgnn_structure_blob_smem_bytes(io->max_n, io->max_e);
+  const int weights = (io->wblob && io->edge_attr) ? 1 : 0;
+  const int64_t smem = drgnn_structure_blob_smem_bytes_ex(io->max_n, io->max_e, io->max_k, io->max_q, weights);
   if (smem < 0)
-    return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges does not fit the bitmap kernel",
-                io->max_n, io->max_e);
+    return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges / %d clusters does not fit the bitmap kernel",
+                io->max_n, io->max_e, io->max_k);
   static thread_local int64_t configured = -1;
   if (smem > configured) {
     DRGNN_CHECK_CUDA(cudaFuncSetAttribute(graph_blob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)device_info().smem_optin - 4096));
     configured = device_info().smem_optin - 4096;
   }
-  const BlobPlan plan = blob_plan(io->max_n, io->max_e);
+  const BlobPlan plan = blob_plan(io->max_n, io->max_e, io->max_k, io->max_q, weights);
   if (io->launch_flags & 1) {
     // programmatic dependent launch: the grid may start as soon as every CTA of the kernel in front of it in the
     // stream has executed griddepcontrol.launch_dependents (the step kernels do so first thing) - its CTAs then go

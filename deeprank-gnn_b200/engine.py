@@ -504,7 +504,7 @@ class Engine(object):
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
                                     d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None,
                                     x=d.x if pre else None, zin_kind=self.spec.kind if pre else None,
-                                    dependent=dependent, edge_half=d.edge_half)
+                                    dependent=dependent, edge_half=d.edge_half, max_k=d.max_k0, max_q=d.max_k1)
             assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
@@ -526,7 +526,11 @@ class Engine(object):
             return True
         tiles = self._step3_tiles(d)
         ctas = (tiles if tiles else 1) * self.spec.nb * d.B        # grid of the step kernel
-        return ctas + (d.B + 1) // 2 <= self._sm_count             # + the pass at two CTAs per SM
+        smem = ops.structure_blob_smem(d.max_n, d.max_e, d.max_k0, d.max_k1, weights=self.spec.kind == 'sgat')
+        # CTAs of the pass that share an SM: at most two are counted - with more, the longer pass was still the
+        # bottleneck beside a 128-CTA step (cfg2: 27.2 vs 26.0 us per step), with two it pays (cfg4: 95.1 vs 100.6 us)
+        per_sm = max(1, min(2, (227 * 1024) // max(smem + 1024, 1)))
+        return ctas + (d.B + per_sm - 1) // per_sm <= self._sm_count
 
     def _comm_in_kernel(self, d, st):
         """Can the peer-memory exchange run inside the cluster step kernel for batch ``d``?  Decided from
@@ -577,10 +581,10 @@ class Engine(object):
         is then the one-launch bitmap kernel (``ops.structure_blob``)."""
         s = self.spec
         if self._step3_tiles(d):
-            key = (d.max_n, d.max_e, 'blobfit')
+            key = (d.max_n, d.max_e, d.max_k0, d.max_k1, 'blobfit')
             fit = self._fused_fit.get(key)
             if fit is None:
-                fit = ops.structure_blob_fits(d.max_n, d.max_e)
+                fit = ops.structure_blob_fits(d.max_n, d.max_e, d.max_k0, d.max_k1, weights=s.kind == 'sgat')
                 self._fused_fit[key] = fit
             return bool(fit and self.blob_structure and not self.keep_intermediates)
         if not (self.blob_structure and self.fused_head and self.step_variant != 1 and not self.keep_intermediates
@@ -590,7 +594,8 @@ class Engine(object):
         fit = self._fused_fit.get(key)
         if fit is None:
             fit = (ops.ginet_step2_smem_bytes(s.F, s.h1, s.h2, d.max_n, d.max_k0, d.max_k1, d.max_e, s.Hd, s.out) >= 0
-                   and ops.structure_blob_fits(d.max_n, d.max_e) and s.F % 4 == 0 and s.h1 % 4 == 0 and s.h2 % 4 == 0)
+                   and ops.structure_blob_fits(d.max_n, d.max_e, d.max_k0, d.max_k1, weights=False)
+                   and s.F % 4 == 0 and s.h1 % 4 == 0 and s.h2 % 4 == 0)
             self._fused_fit[key] = fit
         return fit
 

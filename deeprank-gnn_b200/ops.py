@@ -227,10 +227,16 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     return s
 
 
-def structure_blob_fits(max_n, max_e):
-    """True when graphs of up to ``max_n`` nodes / ``max_e`` directed edges fit the bitmap kernel of
-    the blob-only structure pass (``drgnn_structure_blob``)."""
-    return int(_lib.load().drgnn_structure_blob_smem_bytes(int(max_n), int(max_e))) >= 0
+def structure_blob_smem(max_n, max_e, max_k=0, max_q=0, weights=True):
+    """Shared memory (bytes) of one CTA of the blob-only structure pass for graphs of up to ``max_n`` nodes / ``max_e``
+    directed edges / ``max_k``, ``max_q`` clusters of the two levels (0: ``max_n``); negative when it does not fit."""
+    return int(_lib.load().drgnn_structure_blob_smem_bytes_ex(int(max_n), int(max_e), int(max_k or 0), int(max_q or 0),
+                                                              1 if weights else 0))
+
+
+def structure_blob_fits(max_n, max_e, max_k=0, max_q=0, weights=True):
+    """True when such graphs fit the blob-only structure pass (``drgnn_structure_blob``)."""
+    return structure_blob_smem(max_n, max_e, max_k, max_q, weights) >= 0
 
 
 ZIN_KIND = {'ginet': 0, 'sgat': 1, 'fout': 2}
@@ -243,7 +249,7 @@ def zin1_ld(kind, F):
 
 
 def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None,
-                   edge_attr=None, x=None, zin_kind=None, dependent=False, edge_half=False):
+                   edge_attr=None, x=None, zin_kind=None, dependent=False, edge_half=False, max_k=0, max_q=0):
     """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
     structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
     global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
@@ -318,6 +324,7 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
         s.zin1, s.zin1_ld = None, 0
         io.x, io.zin1 = None, None
     io.launch_flags = 1 if dependent else 0     # programmatic dependent of the kernel in front of it in the stream
+    io.max_k, io.max_q = int(max_k or 0), int(max_q or 0)   # per-graph cluster bounds: sizes of the pooled-graph bitmaps
     if B:
         call('drgnn_structure_blob', C.byref(io), stream_ptr())
     return s

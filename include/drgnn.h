@@ -170,11 +170,19 @@ typedef struct drgnn_structure_io {
    * CTA of the step is resident and runs beside it on the SMs it leaves free; it completes after that step.  The
    * pass must not depend on anything that step writes (it never does: it reads the NEXT batches' inputs). */
   int32_t launch_flags;
+  /* max_k / max_q (drgnn_structure_blob; 0 = unknown -> max_n): host bounds of the level-0 / level-1 cluster counts
+   * of ONE graph.  The pass sizes its pooled-graph bitmaps by them (shared memory: K x K/32 words instead of
+   * n x n/32), which lets several CTAs share an SM and lets graphs of a thousand nodes take this pass; a graph that
+   * exceeds them is flagged (DRGNN_ST_FUSED_BOUNDS) and its blob left incomplete. */
+  int32_t max_k; int32_t max_q;
 } drgnn_structure_io;
 
 /* Dynamic shared memory the per-graph kernel needs for (max_n, max_e); <0 if a graph is
  * too large for one CTA (DRGNN_ERR_UNSUPPORTED). */
 int64_t drgnn_structure_smem_bytes(int32_t max_n, int32_t max_e, int32_t max_c1);
+/* ... of drgnn_structure_blob for graphs of up to max_n nodes / max_e directed edges / max_k and max_q clusters of the
+ * two levels (0: max_n), with (weights != 0) or without the sGAT edge weights; <0 when it does not fit */
+int64_t drgnn_structure_blob_smem_bytes_ex(int32_t max_n, int32_t max_e, int32_t max_k, int32_t max_q, int32_t weights);
 int drgnn_structure_build(const drgnn_structure_io* io, void* stream);
 
 /* get_preloaded_cluster as a stand-alone op (community_pooling.py:25-30):
