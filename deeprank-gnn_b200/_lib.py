@@ -253,7 +253,7 @@ _SIGNATURES = {
     'drgnn_debug_phase_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_debug_blob_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
     'drgnn_structure_blob_smem_bytes': (_i64, [_i32, _i32]),
-    'drgnn_structure_blob_smem_bytes_ex': (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    'drgnn_structure_blob_smem_bytes_ex': (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     'drgnn_structure_blob': (C.c_int, [C.POINTER(StructureIO), VP]),
     'drgnn_net_step_smem_bytes': (_i64, [_i32] * 11),
     'drgnn_net_step_pick_tiles': (C.c_int, [_i32] * 10),

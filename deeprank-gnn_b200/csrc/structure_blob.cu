@@ -34,7 +34,8 @@ __device__ unsigned long long g_bphase[16];
   } while (0)
 
 struct BlobPlan {   // word offsets into dynamic shared memory
-  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, bm, bmT, mem0, mem1, cnt, ea, eord, eun, total;
+  int erow, ecol, id0, id1, dense0, dense1, cb0, cb1, cp0, cp1, bm, bmT, mem0, mem1, cnt, ea, eord, eun, xs, bar, total;
+  int xs_words;       // > 0: the graph's feature tile is staged for the first aggregation (one bulk copy)
   int max_k, max_q;   // per-graph bounds of the level-0 / level-1 cluster counts the bitmaps are sized for
   int kwk;   // row stride of bm / bmT / mem1 (bitmaps over pooled-node ids): ceil(max_k/32), made odd
   int kwn;   // row stride of mem0 (bitmap over node ids): ceil(max_n/32), made odd
@@ -45,7 +46,7 @@ __host__ __device__ inline int sb_odd_words(int bits) {   // words for `bits` bi
   if (w == ((bits + 31) >> 5)) w += 2;
   return w;
 }
-__host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e, int max_k, int max_q, int weights) {
+__host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e, int max_k, int max_q, int weights, int x_words = 0) {
   BlobPlan p;
   int o = 0;
   auto take = [&](int words) { const int at = o; o += sb_up4(words); return at; };
@@ -73,6 +74,9 @@ __host__ __device__ inline BlobPlan blob_plan(int max_n, int max_e, int max_k, i
   p.ea = take(weights ? max_e : 0);   // edge attributes of the graph (sGAT weights; 4 KB at 1000 edges)
   p.eord = take((max_e + 1) / 2);     // edge id of every level-0 CSR slot
   p.eun = take((max_e + 1) / 2);      // ... before the rank sweep (atomic slot order)
+  p.xs_words = x_words > 0 ? sb_up4(x_words) : 0;
+  p.xs = take(p.xs_words);            // feature tile of the graph (first aggregation)
+  p.bar = take(p.xs_words ? 4 : 0);   // its mbarrier
   p.total = o;
   return p;
 }
@@ -82,15 +86,28 @@ __device__ __forceinline__ long long sb_ld_id(const void* base, int64_t i, int i
   return idx32 == 2 ? (long long)reinterpret_cast<const uint16_t*>(base)[i]
          : idx32  ? (long long)reinterpret_cast<const int32_t*>(base)[i] : reinterpret_cast<const int64_t*>(base)[i];
 }
-// Edge e of a graph whose m directed edges travel as m / 2 undirected pairs (edge16 == 2: the loader stores every
-// edge in both directions, first half i -> j, second half j -> i, DataSet.py:266-269, so the second half is implied):
-// ei = [2, E / 2] uint16 graph-local ids, the graph's pairs start at e0 / 2.
-__device__ __forceinline__ void sb_ld_half_edge(const uint16_t* ei, int64_t E, int e0, int m, int e, long long& r, long long& c) {
-  const int mh = m >> 1, eh = e < mh ? e : e - mh;
-  const int64_t at = (int64_t)(e0 >> 1) + eh;
-  const long long a = ei[at], b = ei[(E >> 1) + at];
-  r = e < mh ? a : b;
-  c = e < mh ? b : a;
+__device__ __forceinline__ uint32_t sb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// bulk copy of the graph's feature tile into shared memory (issue by one thread) / wait for it (every thread)
+__device__ __forceinline__ void sb_stage_x(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_u32(bar)));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(bytes) : "memory");
+  if (bytes)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sb_wait_x(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra SB_DONE_%=;\n"
+      "bra SB_WAIT_%=;\n"
+      "SB_DONE_%=:\n"
+      "}\n" ::"r"(sb_smem_u32(bar))
+      : "memory");
 }
 
 // min / max over the CTA of two value pairs at once (level-0 and level-1 cluster ids); results in red[0..3]
@@ -180,6 +197,12 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   bool bad1 = c1len > io.max_n || c1len < 0;
   if (bad1) c1len = 0;
+  // the feature tile of the first aggregation (step 9) starts its way into shared memory now
+  const bool stage_x = io.zin1 != nullptr && P.xs_words > 0;
+  float* xs = reinterpret_cast<float*>(sb + P.xs);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(sb + P.bar);
+  if (stage_x && t == 0) sb_stage_x(xs, io.x + (int64_t)n0 * io.F, (uint32_t)(n * io.F) * 4u, xbar);
+  if (stage_x) __syncthreads();          // the barrier is initialised before anybody may wait on it
 
   // ---- 0. zero every bitmap (the presence words follow once the id ranges are known)
 #pragma unroll 1
@@ -191,27 +214,77 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 #pragma unroll 1
   for (int i = t; i < P.max_q * KWK; i += T) mem1[i] = 0u;
   // ---- 1. local edge list; cluster ids of both levels (read from global memory once), their extremes
+  // (four edges per thread and sweep: the global loads of a sweep are issued together, then checked and stored -
+  // one dependent load per loop iteration made this phase 18 k cycles for a graph of 8000 edges)
+  if (io.edge16 == 2) {
+    // compact feeder batches: m / 2 undirected pairs of uint16 graph-local ids; pair k gives edge k and its mirror
+    // m / 2 + k.  An odd edge count cannot be two mirrored halves: every edge is flagged below.
+    const uint16_t* ei = reinterpret_cast<const uint16_t*>(io.edge_index);
+    const int mh = m >> 1;
+    const int64_t h0 = e0 >> 1, Eh = (int64_t)io.E >> 1;
+    const bool odd = ((m | e0) & 1) != 0;
 #pragma unroll 1
-  for (int e = t; e < m; e += T) {
-    long long r, c;
-    if (io.edge16 == 2) {   // compact feeder batches: undirected pairs of uint16 graph-local ids
-      sb_ld_half_edge(reinterpret_cast<const uint16_t*>(io.edge_index), io.E, e0, m, e, r, c);
-      if ((m | e0) & 1) r = -1;   // an odd edge count cannot be two mirrored halves: flagged below
-    } else if (io.edge16) {   // uint16 graph-local ids, both directions stored
-      r = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)e0 + e];
-      c = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)io.E + e0 + e];
-    } else {
-      r = sb_ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
-      c = sb_ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
+    for (int k0 = t; k0 < mh; k0 += 4 * T) {
+      int a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * T;
+        a[u] = k < mh ? (int)ei[h0 + k] : 0;
+        b[u] = k < mh ? (int)ei[Eh + h0 + k] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * T;
+        if (k < mh) {
+          int r = a[u], c = b[u];
+          if (odd || r >= n || c >= n) {
+            atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
+            r = 0;
+            c = 0;
+          }
+          erow[k] = (uint16_t)r;      ecol[k] = (uint16_t)c;
+          erow[mh + k] = (uint16_t)c; ecol[mh + k] = (uint16_t)r;
+        }
+      }
     }
-    if (r < 0 || r >= n || c < 0 || c >= n) {
-      atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
-      r = 0;
-      c = 0;
+    if (odd && t == 0) { erow[m - 1] = 0; ecol[m - 1] = 0; atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH); }
+  } else {
+#pragma unroll 1
+    for (int e00 = t; e00 < m; e00 += 4 * T) {
+      long long rr[4], cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e00 + u * T;
+        rr[u] = cc[u] = 0;
+        if (e < m) {
+          if (io.edge16) {   // uint16 graph-local ids, both directions stored
+            rr[u] = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)e0 + e];
+            cc[u] = reinterpret_cast<const uint16_t*>(io.edge_index)[(int64_t)io.E + e0 + e];
+          } else {
+            rr[u] = sb_ld_id(io.edge_index, (int64_t)e0 + e, io.idx32) - n0;
+            cc[u] = sb_ld_id(io.edge_index, (int64_t)io.E + e0 + e, io.idx32) - n0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e00 + u * T;
+        if (e < m) {
+          long long r = rr[u], c = cc[u];
+          if (r < 0 || r >= n || c < 0 || c >= n) {
+            atomicOr(io.status, DRGNN_ST_EDGE_OUTSIDE_GRAPH);
+            r = 0;
+            c = 0;
+          }
+          erow[e] = (uint16_t)r;
+          ecol[e] = (uint16_t)c;
+        }
+      }
     }
-    erow[e] = (uint16_t)r;
-    ecol[e] = (uint16_t)c;
-    if (wb) eas[e] = io.edge_attr[(int64_t)(e0 + e) * io.ne];   // staged once: the weight sums read shared memory
+  }
+  if (wb) {   // staged once: the weight sums read shared memory
+#pragma unroll 4
+    for (int e = t; e < m; e += T) eas[e] = io.edge_attr[(int64_t)(e0 + e) * io.ne];
   }
   long long mn0 = LLONG_MAX, mx0 = LLONG_MIN, mn1 = LLONG_MAX, mx1 = LLONG_MIN;
   // raw ids are kept in registers for graphs of up to 2 * T nodes (else re-read)
@@ -257,6 +330,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   if (bad_range) {   // same flag as the full pass; the blob stays incomplete (the step kernel refuses it)
     if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER_RANGE);
+    if (stage_x) sb_wait_x(xbar);        // no bulk copy may be in flight into a CTA that exits
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
@@ -306,6 +380,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   if (K > P.max_k || K1 > P.max_q) {   // the host's per-graph cluster bounds (bitmap sizes) are violated: blob stays incomplete
     if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
+    if (stage_x) sb_wait_x(xbar);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
@@ -389,6 +464,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     bl[BL.col0 + pos] = ecol[e];
     if (wb) wb[BL.col0 + pos] = eas[e];
   }
+  DRGNN_BPHASE(9);
 #pragma unroll 1
   for (int i = t; i < n; i += T) {          // members of the level-0 clusters, ascending node id
     bl[BL.rp0 + i] = cnt[i];
@@ -416,6 +492,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
 #pragma unroll 1
   for (int q = t; q < K1; q += T) bl[BL.cmp1 + q] = cnt[n + 3 * K + q] - baseM1;
+  DRGNN_BPHASE(10);
   // pooled rows / columns: a thread per (row, word) emits the set bits of its word (sorted, unique)
 #pragma unroll 1
   for (int item = t; item < 2 * K * KWk; item += T) {
@@ -509,6 +586,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     }
     DRGNN_BPHASE(7);
   }
+  DRGNN_BPHASE(11);
   if (io.zin1) {
     // ---- 9. the first aggregation of the network (optional): the input rows of conv1's dense transform depend on
     // the batch only, not on the weights, so they are computed HERE - on the side stream, while the previous step
@@ -517,11 +595,13 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     //   kind 1 (sGAT, sGAT.py:70-92)      zin1_i = [ s_i x_i | (1/max(deg,1)) sum_e a_e x_col | 1 0 0 0 ],  s_i = mean_e a_e
     //   kind 2 (FoutNet, foutnet.py:62-80) zin1_i = [ x_i | (1/deg) sum_e x_col | 1 0 0 0 ]   (deg = 0 -> NaN)
     // Same arithmetic, in the same order (ascending CSR slot = the CPU scatter order), as the aggregation phase of the
-    // step kernels (s2_gather / s3_aggregate), so the rows are bit-identical.  The feature rows come from global
-    // memory (each is read deg times: L1 / L2 hits after the first).
+    // step kernels (s2_gather / s3_aggregate), so the rows are bit-identical.  The feature rows come from the tile
+    // staged in shared memory at the start of the kernel (one bulk copy, in flight during steps 1-8) - from global
+    // memory only when the tile does not fit (each row is read deg times: 29 k of 64 k cycles at cfg4).
     __syncthreads();   // eord (the emit sweep above) is complete; cnt holds the CSR row pointers
     const int F = io.F, F4 = F >> 2, ld = io.ld_zin1, kind = io.zin_kind;
-    const float* xg = io.x + (int64_t)n0 * F;
+    if (stage_x) sb_wait_x(xbar);
+    const float* xg = stage_x ? xs : io.x + (int64_t)n0 * F;   // staged tile (shared memory) or the global rows
     float* zg = io.zin1 + (int64_t)n0 * ld;
 #pragma unroll 1
     for (int item = t; item < n * F4; item += T) {
@@ -534,14 +614,14 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
         for (int p = sb_; p < se_; ++p) {
           const int e = eord[p];
           const float wv = eas[e];
-          const float4 v = __ldg(reinterpret_cast<const float4*>(xg + (int)ecol[e] * F) + q4);
+          const float4 v = *(reinterpret_cast<const float4*>(xg + (int)ecol[e] * F) + q4);
           acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
           wsum += wv;
         }
       } else {
 #pragma unroll 4
         for (int p = sb_; p < se_; ++p) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(xg + (int)ecol[eord[p]] * F) + q4);
+          const float4 v = *(reinterpret_cast<const float4*>(xg + (int)ecol[eord[p]] * F) + q4);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
       }
@@ -553,7 +633,7 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
         const float post = kind == 1 ? 1.f / (float)max(deg, 1) : 1.f / (float)deg;
         const float selfc = kind == 1 ? post * wsum : 1.f;
         acc.x *= post; acc.y *= post; acc.z *= post; acc.w *= post;
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(xg + i * F) + q4);
+        const float4 sv = *(reinterpret_cast<const float4*>(xg + i * F) + q4);
         *reinterpret_cast<float4*>(zr + q4 * 4) = make_float4(selfc * sv.x, selfc * sv.y, selfc * sv.z, selfc * sv.w);
         *reinterpret_cast<float4*>(zr + F + q4 * 4) = acc;
         if (q4 == 0) *reinterpret_cast<float4*>(zr + 2 * F) = make_float4(1.f, 0.f, 0.f, 0.f);   // ones column: bias gradient
@@ -584,16 +664,16 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
 using namespace drgnn;
 
 extern "C" int64_t drgnn_structure_blob_smem_bytes_ex(int32_t max_n, int32_t max_e, int32_t max_k, int32_t max_q,
-                                                      int32_t weights) {
-  if (max_n <= 0 || max_e < 0) return DRGNN_ERR_INVALID;
+                                                      int32_t weights, int32_t x_words) {
+  if (max_n <= 0 || max_e < 0 || x_words < 0) return DRGNN_ERR_INVALID;
   if (max_n > 16384 || max_e > 65535) return DRGNN_ERR_UNSUPPORTED;   // uint16 ids inside the kernel
-  const BlobPlan p = blob_plan(max_n, max_e, max_k, max_q, weights);
+  const BlobPlan p = blob_plan(max_n, max_e, max_k, max_q, weights, x_words);
   const int64_t bytes = 4 * (int64_t)p.total;
   if (bytes > device_info().smem_optin - 4096) return DRGNN_ERR_UNSUPPORTED;
   return bytes;
 }
 extern "C" int64_t drgnn_structure_blob_smem_bytes(int32_t max_n, int32_t max_e) {
-  return drgnn_structure_blob_smem_bytes_ex(max_n, max_e, 0, 0, 1);
+  return drgnn_structure_blob_smem_bytes_ex(max_n, max_e, 0, 0, 1, 0);
 }
 
 // Blob-only structure pass (the inputs of drgnn_structure_build; outputs: io->blob, io->status,
@@ -612,7 +692,14 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
                 "structure_blob: first aggregation requested with an invalid x / F / ld_zin1 / zin_kind");
   DRGNN_REQUIRE(!io->zin1 || io->zin_kind != 1 || (io->wblob && io->edge_attr), "structure_blob: the sGAT aggregation needs edge_attr and wblob");
   const int weights = (io->wblob && io->edge_attr) ? 1 : 0;
-  const int64_t smem = drgnn_structure_blob_smem_bytes_ex(io->max_n, io->max_e, io->max_k, io->max_q, weights);
+  // the feature tile of the first aggregation is staged in shared memory when it fits next to the rest
+  int x_words = io->zin1 ? io->max_n * io->F : 0;
+  int64_t smem = drgnn_structure_blob_smem_bytes_ex(io->max_n, io->max_e, io->max_k, io->max_q, weights, x_words);
+  if (smem < 0 && x_words) {
+    x_words = 0;
+    smem = drgnn_structure_blob_smem_bytes_ex(io->max_n, io->max_e, io->max_k, io->max_q, weights, 0);
+  }
+  DRGNN_REQUIRE(!io->zin1 || ((uintptr_t)io->x % 16) == 0, "structure_blob: x must be 16-byte aligned");
   if (smem < 0)
     return fail(DRGNN_ERR_UNSUPPORTED, "structure_blob: a graph with %d nodes / %d edges / %d clusters does not fit the bitmap kernel",
                 io->max_n, io->max_e, io->max_k);
@@ -622,7 +709,7 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
                                           (int)device_info().smem_optin - 4096));
     configured = device_info().smem_optin - 4096;
   }
-  const BlobPlan plan = blob_plan(io->max_n, io->max_e, io->max_k, io->max_q, weights);
+  const BlobPlan plan = blob_plan(io->max_n, io->max_e, io->max_k, io->max_q, weights, x_words);
   if (io->launch_flags & 1) {
     // programmatic dependent launch: the grid may start as soon as every CTA of the kernel in front of it in the
     // stream has executed griddepcontrol.launch_dependents (the step kernels do so first thing) - its CTAs then go

@@ -333,10 +333,8 @@ class Engine(object):
         self.step3_lpt = os.environ.get('DRGNN_STEP3_LPT', '1') != '0'
         self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         # The blob structure pass also computes conv1's input rows (the first aggregation depends on the batch only)
-        # and the step kernels stage them: '1' always, '0' never, 'auto' when the step grid leaves SMs for the
-        # longer pass (it runs beside the step on the SMs the step does not occupy: sGAT / FoutNet at batch 64 use
-        # 64 of 148 SMs - cfg3 44.1 -> 40.0 us per step; the CTA-pair GINet kernel uses 128 and the pass
-        # becomes the bottleneck - cfg2 26.6 -> 28.8 us)
+        # and the step kernels stage them: '1' always, '0' never, 'auto' when the step grid fits the device (the pass
+        # runs beside the step; see _pre_agg_on for the measurements)
         self.pre_agg = os.environ.get('DRGNN_PRE_AGG', 'auto')
         # train_resident chunk graphs: structure passes as programmatic dependents of the steps, on one stream.
         # Opt-in: on this driver a dependent grid does not start before its primary ends even when every CTA of
@@ -526,11 +524,9 @@ class Engine(object):
             return True
         tiles = self._step3_tiles(d)
         ctas = (tiles if tiles else 1) * self.spec.nb * d.B        # grid of the step kernel
-        smem = ops.structure_blob_smem(d.max_n, d.max_e, d.max_k0, d.max_k1, weights=self.spec.kind == 'sgat')
-        # CTAs of the pass that share an SM: at most two are counted - with more, the longer pass was still the
-        # bottleneck beside a 128-CTA step (cfg2: 27.2 vs 26.0 us per step), with two it pays (cfg4: 95.1 vs 100.6 us)
-        per_sm = max(1, min(2, (227 * 1024) // max(smem + 1024, 1)))
-        return ctas + (d.B + per_sm - 1) // per_sm <= self._sm_count
+        # measured (driver's command, us per step with / without): cfg2 25.9 / 26.1, cfg3 40.0 / 44.1, cfg4 91.3 / 100.0 -
+        # but cfg5 131.2 / 122.2: a step grid larger than the device leaves the longer pass no SM of its own
+        return ctas <= self._sm_count
 
     def _comm_in_kernel(self, d, st):
         """Can the peer-memory exchange run inside the cluster step kernel for batch ``d``?  Decided from

@@ -227,11 +227,15 @@ def structure_build(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_p
     return s
 
 
-def structure_blob_smem(max_n, max_e, max_k=0, max_q=0, weights=True):
+def structure_blob_smem(max_n, max_e, max_k=0, max_q=0, weights=True, x_words=0):
     """Shared memory (bytes) of one CTA of the blob-only structure pass for graphs of up to ``max_n`` nodes / ``max_e``
     directed edges / ``max_k``, ``max_q`` clusters of the two levels (0: ``max_n``); negative when it does not fit."""
-    return int(_lib.load().drgnn_structure_blob_smem_bytes_ex(int(max_n), int(max_e), int(max_k or 0), int(max_q or 0),
-                                                              1 if weights else 0))
+    v = int(_lib.load().drgnn_structure_blob_smem_bytes_ex(int(max_n), int(max_e), int(max_k or 0), int(max_q or 0),
+                                                           1 if weights else 0, int(x_words)))
+    if v < 0 and x_words:      # the feature tile of the first aggregation is staged only when it fits
+        v = int(_lib.load().drgnn_structure_blob_smem_bytes_ex(int(max_n), int(max_e), int(max_k or 0), int(max_q or 0),
+                                                               1 if weights else 0, 0))
+    return v
 
 
 def structure_blob_fits(max_n, max_e, max_k=0, max_q=0, weights=True):

@@ -181,8 +181,10 @@ typedef struct drgnn_structure_io {
  * too large for one CTA (DRGNN_ERR_UNSUPPORTED). */
 int64_t drgnn_structure_smem_bytes(int32_t max_n, int32_t max_e, int32_t max_c1);
 /* ... of drgnn_structure_blob for graphs of up to max_n nodes / max_e directed edges / max_k and max_q clusters of the
- * two levels (0: max_n), with (weights != 0) or without the sGAT edge weights; <0 when it does not fit */
-int64_t drgnn_structure_blob_smem_bytes_ex(int32_t max_n, int32_t max_e, int32_t max_k, int32_t max_q, int32_t weights);
+ * two levels (0: max_n), with (weights != 0) or without the sGAT edge weights, with a feature tile of x_words floats
+ * staged for the first aggregation (0: none); <0 when it does not fit */
+int64_t drgnn_structure_blob_smem_bytes_ex(int32_t max_n, int32_t max_e, int32_t max_k, int32_t max_q, int32_t weights,
+                                           int32_t x_words);
 int drgnn_structure_build(const drgnn_structure_io* io, void* stream);
 
 /* get_preloaded_cluster as a stand-alone op (community_pooling.py:25-30):

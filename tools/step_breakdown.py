@@ -84,6 +84,9 @@ def main():
             bnames = ['load+minmax', 'relabel', 'scatter', 'count+scan', 'emit']
             print('blob structure kernel, CTA of graph 0: %d cycles total' % (ph[5] - ph[0]))
             print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(bnames)))
+            if ph[9] and ph[11] and ph[5] > ph[0]:
+                print('  emit split: level-0 CSR (slots + rank sweep) %d | member lists + pointers %d | pooled rows / columns %d | '
+                      'rest (weights, first aggregation, header) %d' % (ph[9] - ph[4], ph[10] - ph[9], ph[11] - ph[10], ph[5] - ph[11]))
             if ph[6] and ph[7]:
                 print('  emit split (sGAT weights): lists %d | pooled sums %d | CSC order + header %d'
                       % (ph[6] - ph[4], ph[7] - ph[6], ph[5] - ph[7]))
