@@ -390,10 +390,6 @@ __host__ __device__ inline int s2_split(int cap_words, int mn) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     ginet_graph_step2_kernel(const drgnn_ginet_step_args s, const Step2Plan P, const drgnn_peer_comm C) {
   extern __shared__ __align__(16) float sm[];
-  // A structure pass launched behind this kernel as its programmatic dependent (drgnn_structure_io.launch_flags bit 0)
-  // may start now: every CTA of this grid is resident by the time all of them have passed this point, so the
-  // dependent's CTAs fill the SMs this grid leaves free instead of racing it for SMs (no-op without a dependent).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   cgx::cluster_group cluster = cgx::this_cluster();
   const drgnn_ginet_fused_args& a = s.g;
   const int r = (int)cluster.block_rank();   // branch of this CTA

@@ -202,13 +202,18 @@ struct S3Rows {
   __device__ __forceinline__ const int* irow(int i) const { return reinterpret_cast<const int*>(row(i)); }
 };
 // rows of a cluster-distributed array (tile t at base[t], rpt rows each); one tile: direct addressing
-__device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, int rpt, int ld) {
+// magic word of a rows-per-tile count (one 64-bit division: computed ONCE per kernel for the three levels, not per
+// call - the division was 5 % of the kernel's stall samples at cfg4)
+__device__ __forceinline__ unsigned s3_magic(int tiles, int rpt) {
+  return (tiles > 1 && rpt > 1) ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
+}
+__device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, int rpt, int ld, unsigned magic) {
   S3Rows r;
   r.base = tiles > 1 ? base : nullptr;
   r.b0 = base[0];
   r.rpt = rpt;
   r.ld = ld;
-  r.magic = (tiles > 1 && rpt > 1) ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
+  r.magic = magic;
   return r;
 }
 __device__ __forceinline__ S3Rows s3_rows_flat(const void* b0, int ld) {
@@ -666,9 +671,6 @@ __host__ __device__ inline int s3_split(int cap_words, int mn) {
 __global__ void __launch_bounds__(S3_THREADS, 1)
     net_graph_step3_kernel(const drgnn_net_step_args s, const Step3Plan P, const drgnn_peer_comm C) {
   extern __shared__ __align__(16) float sm[];
-  // a structure pass launched as the programmatic dependent of this grid may start once every CTA is resident
-  // (see ginet_graph_step2_kernel)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   cgx::cluster_group cluster = cgx::this_cluster();
   const int kind = s.kind;
   const int NT = P.tiles, CS = P.cs;
@@ -864,6 +866,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   const int lo1 = min(K, ti * kta), hi1 = min(K, lo1 + kta);
   const int lo2 = min(Q, ti * qta), hi2 = min(Q, lo2 + qta);
   const int r0n = hi0 - lo0, r1n = hi1 - lo1, r2n = hi2 - lo2;
+  const unsigned mg0 = s3_magic(NT, nta), mg1 = s3_magic(NT, kta), mg2 = s3_magic(NT, qta);
   const void* const* bz1 = bases;                    const void* const* bp1 = bases + S3_MAX_TILES;
   const void* const* barg0 = bases + 2 * S3_MAX_TILES; const void* const* bz2 = bases + 3 * S3_MAX_TILES;
   const void* const* barg1 = bases + 4 * S3_MAX_TILES; const void* const* bdzin2 = bases + 5 * S3_MAX_TILES;
@@ -886,11 +889,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(3);
   // ---- P1 = cluster max of Z1 (community_pooling.py:201): members may live in any tile
-  s3_cluster_max(cmp0, cmem0, s3_rows(bz1, NT, nta, LDZ1), lo1, hi1, p1, LDP, arg0, H1, H14, t, T);
+  s3_cluster_max(cmp0, cmem0, s3_rows(bz1, NT, nta, LDZ1, mg0), lo1, hi1, p1, LDP, arg0, H1, H14, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(4);
   // ---- conv2 on the coarsened graph
-  s3_aggregate(kind, rp1, col1, ew1, s3_rows(bp1, NT, kta, LDP), H1, lo1, hi1, zin2, LDZIN2, s1, post1, t, T);
+  s3_aggregate(kind, rp1, col1, ew1, s3_rows(bp1, NT, kta, LDP, mg1), H1, lo1, hi1, zin2, LDZIN2, s1, post1, t, T);
   __syncthreads();
   DRGNN_PHASE3(5);
   if (tc) tc_gemm(zin2, LDZIN2, w2, H2, r1n, H2, Kin2, z2, LDZ2, kind ? b2 : nullptr, 1, nullptr, 0, t, T);
@@ -898,7 +901,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(6);
   if (L3) {   // third conv layer on the coarsened graph (BASELINE config 3: "sGAT 3-layer"), h2 -> h2
-    s3_aggregate(kind, rp1, col1, ew1, s3_rows(bz2, NT, kta, LDZ2), H2, lo1, hi1, zin3, LDZIN3, nullptr, nullptr, t, T);
+    s3_aggregate(kind, rp1, col1, ew1, s3_rows(bz2, NT, kta, LDZ2, mg1), H2, lo1, hi1, zin3, LDZIN3, nullptr, nullptr, t, T);
     __syncthreads();
     if (tc) tc_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
     else s3_gemm(zin3, LDZIN3, w3, H2, r1n, H2, 2 * H2, z3, LDZ2, b3, 1, nullptr, 0, t, T);
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   }
   float* zl = L3 ? z3 : z2;                                  // the last conv output: pooled, read out
   // ---- P2 = level-1 cluster max (max_pool_x)
-  s3_cluster_max(cmp1, cmem1, s3_rows(L3 ? bz3 : bz2, NT, kta, LDZ2), lo2, hi2, p2, H2, arg1, H2, H24, t, T);
+  s3_cluster_max(cmp1, cmem1, s3_rows(L3 ? bz3 : bz2, NT, kta, LDZ2, mg1), lo2, hi2, p2, H2, arg1, H2, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(7);
   if (mirror) {   // parity tests: the intermediates the op-level path leaves in global memory (global ids)
@@ -1099,7 +1102,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     }
   }
   // ---- dZ2 (in place): read-out mean backward, routed to the arg-max member, gated by ReLU
-  s3_route(cl1, s3_rows(barg1, NT, qta, H2), s3_rows(barg1, NT, qta, H2), drrow, 1.f / (float)max(Q, 1), zl, LDZ2, lo1, hi1, H24, t, T);
+  s3_route(cl1, s3_rows(barg1, NT, qta, H2, mg2), s3_rows(barg1, NT, qta, H2, mg2), drrow, 1.f / (float)max(Q, 1), zl, LDZ2, lo1, hi1, H24, t, T);
   __syncthreads();
   DRGNN_PHASE3(11);
   if (L3) {
@@ -1115,7 +1118,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     else s3_gemm(z3, LDZ2, w3t, 2 * H2, r1n, 2 * H2, H2, zin3, LDZIN3, nullptr, 0, post1, H2, t, T);
     if (multi) cluster.sync(); else __syncthreads();
     s3_cross_tile_store(bwg, NT, ti, M3, N3, 2 * H2, part + s.off_w3, part + s.off_b3, t, T);
-    s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin3, NT, kta, LDZIN3), H2, zin3, LDZIN3, s1, H2, lo1, hi1, t3, LDZ2, t, T);
+    s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin3, NT, kta, LDZIN3, mg1), H2, zin3, LDZIN3, s1, H2, lo1, hi1, t3, LDZ2, t, T);
     __syncthreads();
 #pragma unroll 1
     for (int item = t; item < r1n * H24; item += T) {
@@ -1148,11 +1151,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   if (kind == 0) s3_cross_tile_store(bwg, NT, ti, M2, N2, M2, part + s.off_w2 + br * H2 * H1, nullptr, t, T);
   else s3_cross_tile_store(bwg, NT, ti, M2, N2, Kin2, part + s.off_w2, part + s.off_b2, t, T);
   // ---- dP1 = transposed aggregation of dzin2 (CSC of the coarsened graph) (+ self term)
-  s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin2, NT, kta, LDZIN2), kind ? H1 : 0, dzin2, LDZIN2, s1, H1, lo1, hi1, dp1, LDP, t, T);
+  s3_gather_t(kind, cscp1, cscr1, ew1t, s3_rows(bdzin2, NT, kta, LDZIN2, mg1), kind ? H1 : 0, dzin2, LDZIN2, s1, H1, lo1, hi1, dp1, LDP, t, T);
   if (multi) cluster.sync(); else __syncthreads();
   DRGNN_PHASE3(13);
   // ---- dZ1 (in place): routed to the arg-max node of its cluster, gated by ReLU
-  s3_route(cl0, s3_rows(barg0, NT, kta, H1), s3_rows(bp1, NT, kta, LDP), nullptr, 1.f, z1, LDZ1, lo0, hi0, H14, t, T);
+  s3_route(cl0, s3_rows(barg0, NT, kta, H1, mg1), s3_rows(bp1, NT, kta, LDP, mg1), nullptr, 1.f, z1, LDZ1, lo0, hi0, H14, t, T);
   __syncthreads();
   DRGNN_PHASE3(14);
   // ---- conv1 weight (+ bias) gradient

@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   }
   if (n < 0 || m < 0 || n > io.max_n || m > io.max_e) {   // host bounds violated: header stays incomplete
     if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   bool bad1 = c1len > io.max_n || c1len < 0;
@@ -331,7 +330,6 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   if (bad_range) {   // same flag as the full pass; the blob stays incomplete (the step kernel refuses it)
     if (t == 0) atomicOr(io.status, DRGNN_ST_CLUSTER_RANGE);
     if (stage_x) sb_wait_x(xbar);        // no bulk copy may be in flight into a CTA that exits
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   const int W0 = (int)((range0 + 31) >> 5), W1c = (int)((range1 + 31) >> 5);
@@ -381,7 +379,6 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
   if (K > P.max_k || K1 > P.max_q) {   // the host's per-graph cluster bounds (bitmap sizes) are violated: blob stays incomplete
     if (t == 0) atomicOr(io.status, DRGNN_ST_FUSED_BOUNDS);
     if (stage_x) sb_wait_x(xbar);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   DRGNN_BPHASE(2);
@@ -653,10 +650,6 @@ __global__ void __launch_bounds__(SB_THREADS) graph_blob_kernel(const drgnn_stru
     gs[0] = K; gs[1] = E1; gs[2] = K1;
   }
   DRGNN_BPHASE(5);
-  // Launched as the programmatic dependent of the step kernel in front of it (launch_flags bit 0), this grid started
-  // while that kernel was still running; it must not COMPLETE before it, because the next step in the stream is
-  // ordered after this grid only (no-op for a normal launch).
-  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace drgnn
@@ -710,24 +703,7 @@ extern "C" int drgnn_structure_blob(const drgnn_structure_io* io, void* stream) 
     configured = device_info().smem_optin - 4096;
   }
   const BlobPlan plan = blob_plan(io->max_n, io->max_e, io->max_k, io->max_q, weights, x_words);
-  if (io->launch_flags & 1) {
-    // programmatic dependent launch: the grid may start as soon as every CTA of the kernel in front of it in the
-    // stream has executed griddepcontrol.launch_dependents (the step kernels do so first thing) - its CTAs then go
-    // to the SMs that kernel leaves free; it waits for that kernel's completion itself, at its end
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)io->B);
-    cfg.blockDim = dim3(SB_THREADS);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DRGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, graph_blob_kernel, *io, plan));
-  } else {
-    graph_blob_kernel<<<io->B, SB_THREADS, smem, (cudaStream_t)stream>>>(*io, plan);
-  }
+  graph_blob_kernel<<<io->B, SB_THREADS, smem, (cudaStream_t)stream>>>(*io, plan);
   DRGNN_CHECK_LAUNCH("graph_blob_kernel");
   return DRGNN_OK;
 }

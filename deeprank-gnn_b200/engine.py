@@ -336,11 +336,6 @@ class Engine(object):
         # and the step kernels stage them: '1' always, '0' never, 'auto' when the step grid fits the device (the pass
         # runs beside the step; see _pre_agg_on for the measurements)
         self.pre_agg = os.environ.get('DRGNN_PRE_AGG', 'auto')
-        # train_resident chunk graphs: structure passes as programmatic dependents of the steps, on one stream.
-        # Opt-in: on this driver a dependent grid does not start before its primary ends even when every CTA of
-        # the primary has triggered and SMs are free (tools/micro/pdl_test.cu: 28.9 vs 29.4 us per pair), so the
-        # single-stream order only serialises pass and step (cfg2: 33.5 vs 26.6 us per step).
-        self.pdl_prep = os.environ.get('DRGNN_PDL_PREP', '0') != '0'
         self.phase_timers = False     # diagnostic: block 0 of the fused step kernels records its phase clocks
         self._last_path = None
         self.seed = 0x5EED if seed is None else int(seed)
@@ -481,12 +476,10 @@ class Engine(object):
         return self.ws
 
     # ---------------------------------------------------------------- structure pass
-    def prepare(self, d, dependent=False):
+    def prepare(self, d):
         """Run the structure pass of batch ``d`` into structure slot ``d.sslot`` on the current
         stream.  It depends on the batch only (not on the weights), so callers may run it on a
-        side stream while the previous step computes (``train_batches`` / ``train_resident`` do).
-        ``dependent``: launch it as the programmatic dependent of the step kernel in front of it in the stream
-        (blob pass only; ``_chunk_graph``)."""
+        side stream while the previous step computes (``train_batches`` / ``train_resident`` do)."""
         self._ensure(d.B, d.N, d.E)
         self._primed = None              # a structure slot changes: train_resident primes its lookahead again
         need_w = self.spec.kind == 'sgat'
@@ -502,7 +495,7 @@ class Engine(object):
             st = ops.structure_blob(d.node_ptr, d.edge_ptr, d.edge_index, d.cluster0, d.max_n, d.max_e, d.c1_ptr,
                                     d.cluster1, out=slot, L1=d.L1, edge_attr=d.edge_attr if need_w else None,
                                     x=d.x if pre else None, zin_kind=self.spec.kind if pre else None,
-                                    dependent=dependent, edge_half=d.edge_half, max_k=d.max_k0, max_q=d.max_k1)
+                                    edge_half=d.edge_half, max_k=d.max_k0, max_q=d.max_k1)
             assert st is slot               # _ensure sized the slot for this batch
             self._last_struct = st
             return st
@@ -1363,14 +1356,6 @@ class Engine(object):
             self._no_exchange = True
             try:
                 self.step(dbatches[start % R], B_global=B_global)
-                # is a step ONE kernel launch?  (then a structure pass can be its programmatic dependent)
-                from . import _lib
-                c0 = _lib.launch_count
-                self.step(dbatches[start % R], B_global=B_global, prepared=True)
-                one_call = _lib.launch_count - c0 == 1
-                lib = _lib.load()
-                last = lib.drgnn_net_step_last_launches() if self._last_path == 'step3' else lib.drgnn_ginet_step_last_launches()
-                single_launch = one_call and int(last) == 1 and self._all_done_kernel
                 for j in range(la):              # the warm-up rewrote a structure slot: restore what the chunk expects
                     self.prepare(dbatches[(start + j) % R])
             finally:
@@ -1378,49 +1363,28 @@ class Engine(object):
             torch.cuda.current_stream(self.device).synchronize()
             for t, c in zip((self.params.data, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
                 t.copy_(c)
-            def capture(pdl):
-                g = torch.cuda.CUDAGraph()
-                if pdl:
-                    # ONE stream: step i | structure pass i + LA as the PROGRAMMATIC DEPENDENT of step i | step i + 1 ...
-                    # The pass starts when every CTA of step i is resident (so its CTAs take the SMs the step leaves
-                    # free instead of racing it for SMs - on side streams it started at the same instant as a step
-                    # and its CTAs, spread one per SM, kept step CTAs from becoming resident) and completes after
-                    # step i; step i + 1 is ordered after the pass.  Slot (i + LA) % STRUCT_SLOTS was last read by
-                    # step i + LA - STRUCT_SLOTS < i.
-                    with torch.cuda.graph(g):
-                        for i in range(start, start + C):
-                            self.step(dbatches[i % R], B_global=B_global, prepared=True)
-                            self.prepare(dbatches[(i + la) % R], dependent=True)
-                    return g
-                done, ready = {}, {}
-                with torch.cuda.graph(g):
-                    main = torch.cuda.current_stream(self.device)
-                    for ps in self._prep_streams:
-                        ps.wait_stream(main)
-                    for i in range(start, start + C):
-                        j = i + la
-                        ps = self._prep_streams[j & 1]
-                        with torch.cuda.stream(ps):
-                            if j - ns in done:
-                                ps.wait_event(done[j - ns])
-                            self.prepare(dbatches[j % R])
-                            ready[j] = torch.cuda.Event()
-                            ready[j].record(ps)
-                        if i in ready:
-                            main.wait_event(ready[i])
-                        self.step(dbatches[i % R], B_global=B_global, prepared=True)
-                        done[i] = torch.cuda.Event()
-                        done[i].record(main)
-                    for ps in self._prep_streams:
-                        main.wait_stream(ps)
-                return g
-
-            pdl = self.pdl_prep and single_launch and all(self._blob_only(d) for d in dbatches)
-            g = capture(pdl)
-            if pdl and self.world > 1 and getattr(self, '_last_exchange', None) != 'in-kernel':
-                pdl = False                      # the exchange is its own launch behind the step: side streams
-                g = capture(False)
-            self._last_chunk_pdl = pdl
+            done, ready = {}, {}
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream(self.device)
+                for ps in self._prep_streams:
+                    ps.wait_stream(main)
+                for i in range(start, start + C):
+                    j = i + la
+                    ps = self._prep_streams[j & 1]
+                    with torch.cuda.stream(ps):
+                        if j - ns in done:
+                            ps.wait_event(done[j - ns])
+                        self.prepare(dbatches[j % R])
+                        ready[j] = torch.cuda.Event()
+                        ready[j].record(ps)
+                    if i in ready:
+                        main.wait_event(ready[i])
+                    self.step(dbatches[i % R], B_global=B_global, prepared=True)
+                    done[i] = torch.cuda.Event()
+                    done[i].record(main)
+                for ps in self._prep_streams:
+                    main.wait_stream(ps)
         finally:
             self.use_graph = use_graph
         self._graphs[key] = g

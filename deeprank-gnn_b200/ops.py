@@ -253,7 +253,7 @@ def zin1_ld(kind, F):
 
 
 def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_ptr, cluster1, out=None, L1=None,
-                   edge_attr=None, x=None, zin_kind=None, dependent=False, edge_half=False, max_k=0, max_q=0):
+                   edge_attr=None, x=None, zin_kind=None, edge_half=False, max_k=0, max_q=0):
     """Blob-only structure pass (``drgnn_structure_blob``): ONE launch that writes the per-graph
     structure blobs the cluster step kernel stages (graph-local indices) and nothing else - no
     global CSR arrays, no cross-graph finalize launch, no status-zeroing launch (``status`` is
@@ -327,7 +327,6 @@ def structure_blob(node_ptr, edge_ptr, edge_index, cluster0, max_n, max_e, c1_pt
     else:
         s.zin1, s.zin1_ld = None, 0
         io.x, io.zin1 = None, None
-    io.launch_flags = 1 if dependent else 0     # programmatic dependent of the kernel in front of it in the stream
     io.max_k, io.max_q = int(max_k or 0), int(max_q or 0)   # per-graph cluster bounds: sizes of the pooled-graph bitmaps
     if B:
         call('drgnn_structure_blob', C.byref(io), stream_ptr())

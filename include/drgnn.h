@@ -164,11 +164,7 @@ typedef struct drgnn_structure_io {
   const float* x;
   float* zin1;
   int32_t F; int32_t ld_zin1; int32_t zin_kind;
-  /* launch_flags bit 0 (drgnn_structure_blob): launch the pass as the PROGRAMMATIC DEPENDENT of the kernel in front
-   * of it in the stream (cudaLaunchAttributeProgrammaticStreamSerialization).  Behind a step kernel
-   * (drgnn_ginet_step / drgnn_net_step, which trigger their dependents first thing) the pass starts once every
-   * CTA of the step is resident and runs beside it on the SMs it leaves free; it completes after that step.  The
-   * pass must not depend on anything that step writes (it never does: it reads the NEXT batches' inputs). */
+  /* reserved (0) */
   int32_t launch_flags;
   /* max_k / max_q (drgnn_structure_blob; 0 = unknown -> max_n): host bounds of the level-0 / level-1 cluster counts
    * of ONE graph.  The pass sizes its pooled-graph bitmaps by them (shared memory: K x K/32 words instead of

@@ -41,27 +41,25 @@ def _pool(cfg, n_batches, B, seed, edge_attr=False, compact=None):
 
 
 @pytest.mark.parametrize('net', ['GINet', 'sGAT'])
-def test_train_resident_with_dependent_structure_passes_and_first_aggregation(lib, net):
-    """The two optional forms of the resident loop - structure passes launched as programmatic dependents of the
-    steps on ONE stream (``pdl_prep``) and the first aggregation computed by the structure pass (``pre_agg``) -
-    leave exactly the weights, optimiser state and loss of the default chunk graphs."""
+def test_train_resident_with_the_first_aggregation_in_the_structure_pass(lib, net):
+    """The resident loop with the first aggregation computed by the structure pass (``pre_agg``) leaves exactly the
+    weights, optimiser state and loss of the loop whose step kernels aggregate themselves."""
     from deeprank_gnn_b200.engine import Engine
     packed = _pool('cfg2' if net == 'GINet' else 'cfg3', 16, 64, seed=5, edge_attr=net == 'sGAT')
     ref = None
-    for pdl, pre in ((False, '0'), (True, '0'), (False, '1'), (True, '1')):
+    for pre in ('0', '1'):
         e = Engine(net, 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, graph=True)
-        e.pdl_prep, e.pre_agg = pdl, pre
+        e.pre_agg = pre
         r = [e.upload(pb, slot=i) for i, pb in enumerate(packed)]
         loss, pred = e.train_resident(r, steps=37)
         e.validate()
-        assert e._last_chunk_pdl == pdl
         assert (e.structs[r[0].sslot].zin1 is not None) == (pre == '1')
         got = (loss.clone(), pred.clone(), e.params.data.clone(), e.exp_avg.clone(), e.exp_avg_sq.clone())
         if ref is None:
             ref = got
         else:
-            for a, b in zip(got, ref):
-                assert torch.equal(a, b), (pdl, pre)
+            for a_, b_ in zip(got, ref):
+                assert torch.equal(a_, b_), pre
 
 
 @pytest.mark.parametrize('steps', [40, 43, 5])
