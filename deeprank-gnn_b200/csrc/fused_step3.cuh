@@ -188,29 +188,31 @@ __host__ __device__ inline Step3Plan step3_plan(int kind, int tiles, int stage, 
 // A row-distributed array: tile t holds rows [t*rpt, (t+1)*rpt) at base[t] (a generic pointer into that CTA's
 // shared memory, own or remote).  Level-0 features with NT > 1 are one global array: rpt = INT_MAX, base[0].
 struct S3Rows {
-  const void* const* base;   // [tiles] in shared memory; NULL: the array is not distributed
-  const void* b0;            // the only tile when the array is not distributed: no lookup, no division
+  const void* b0;            // base of tile 0 (distributed: its address in the cluster's shared-memory window)
+  long long stride;          // bytes from one tile's base to the next (the window is linear in the CTA rank); 0: one array
   unsigned magic;            // ceil(2^32 / rpt): owner(i) = umulhi(i, magic), exact for i, rpt < 2^16
   int rpt;
   int ld;
   __device__ __forceinline__ const void* row(int i) const {
-    if (base == nullptr) return reinterpret_cast<const char*>(b0) + (size_t)(i * ld) * 4u;
+    if (stride == 0) return reinterpret_cast<const char*>(b0) + (size_t)(i * ld) * 4u;
     const int o = rpt == 1 ? i : (int)__umulhi((unsigned)i, magic);    // (2^32 / 1 does not fit the magic word)
-    return reinterpret_cast<const char*>(base[o]) + (size_t)((i - o * rpt) * ld) * 4u;
+    return reinterpret_cast<const char*>(b0) + o * stride + (size_t)((i - o * rpt) * ld) * 4u;
   }
   __device__ __forceinline__ const float* frow(int i) const { return reinterpret_cast<const float*>(row(i)); }
   __device__ __forceinline__ const int* irow(int i) const { return reinterpret_cast<const int*>(row(i)); }
 };
-// rows of a cluster-distributed array (tile t at base[t], rpt rows each); one tile: direct addressing
 // magic word of a rows-per-tile count (one 64-bit division: computed ONCE per kernel for the three levels, not per
 // call - the division was 5 % of the kernel's stall samples at cfg4)
 __device__ __forceinline__ unsigned s3_magic(int tiles, int rpt) {
   return (tiles > 1 && rpt > 1) ? (unsigned)((0x100000000ull + (unsigned)rpt - 1ull) / (unsigned)rpt) : 0u;
 }
+// rows of a cluster-distributed array (tile t at base[t] = base[0] + t * stride, rpt rows each): the owner's base is
+// ONE multiply-add (a pointer table in shared memory cost a dependent load per row access: 8 % of the stall samples
+// at cfg4); one tile: direct addressing
 __device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, int rpt, int ld, unsigned magic) {
   S3Rows r;
-  r.base = tiles > 1 ? base : nullptr;
   r.b0 = base[0];
+  r.stride = tiles > 1 ? (reinterpret_cast<const char*>(base[1]) - reinterpret_cast<const char*>(base[0])) : 0;
   r.rpt = rpt;
   r.ld = ld;
   r.magic = magic;
@@ -218,8 +220,8 @@ __device__ __forceinline__ S3Rows s3_rows(const void* const* base, int tiles, in
 }
 __device__ __forceinline__ S3Rows s3_rows_flat(const void* b0, int ld) {
   S3Rows r;
-  r.base = nullptr;
   r.b0 = b0;
+  r.stride = 0;
   r.rpt = 0;
   r.ld = ld;
   r.magic = 0u;
@@ -840,10 +842,17 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     float* local = which == 0 ? z1 : which == 1 ? p1 : which == 2 ? reinterpret_cast<float*>(arg0)
                  : which == 3 ? z2 : which == 4 ? reinterpret_cast<float*>(arg1) : which == 5 ? zin2
                  : which == 6 ? wg : which == 7 ? z3 : zin3;
-    bases[which * S3_MAX_TILES + tt] = (tt == ti) ? local : cluster.map_shared_rank(local, (unsigned)(br * NT + tt));
+    // (every tile through the cluster window, the own one included: base[t] = base[0] + t * stride, see S3Rows)
+    bases[which * S3_MAX_TILES + tt] = NT == 1 ? local : cluster.map_shared_rank(local, (unsigned)(br * NT + tt));
   }
   asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's weight copies
   __syncthreads();
+  if (NT > 2 && t < 9 * NT) {   // the window must be linear in the CTA rank (it is: rank in the upper address bits)
+    const int which = t / NT, tt = t - which * NT;
+    const char* b0_ = reinterpret_cast<const char*>(bases[which * S3_MAX_TILES]);
+    const char* b1_ = reinterpret_cast<const char*>(bases[which * S3_MAX_TILES + 1]);
+    if (reinterpret_cast<const char*>(bases[which * S3_MAX_TILES + tt]) != b0_ + tt * (b1_ - b0_)) atomicOr(s.status, 64);
+  }
   if (staged) s3_mbar_wait(&bars[0], 0);
   if (pre) s3_mbar_wait(&bars[1], 0);
   const int K = blb[2], E1 = blb[3], Q = blb[4];
