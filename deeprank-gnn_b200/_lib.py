@@ -264,6 +264,7 @@ _SIGNATURES = {
     'drgnn_net_step_last_launches': (C.c_int, []),
     'drgnn_net_step_last_tiles': (C.c_int, []),
     'drgnn_debug_phase3_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
+    'drgnn_debug_cta_times': (C.c_int, [C.POINTER(C.c_uint64), C.c_int32]),
     'drgnn_mcl_work_doubles': (_i64, [_i32, _i32]),
     'drgnn_mcl_cluster': (C.c_int, [VP, VP, VP, _i32, _i64, _i32, _i32, VP, VP, VP, VP, VP]),
     'drgnn_feed_run': (C.c_int, [C.POINTER(FeedStep), _i32, _i32, VP, VP, VP, VP, VP, VP, _i64, _i32]),

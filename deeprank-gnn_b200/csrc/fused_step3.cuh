@@ -34,6 +34,9 @@ static constexpr int S3_MAX_TILES = 8;
 static constexpr int S3_MAX_KS = 16;
 
 __device__ unsigned long long g_phase3[32];
+// diagnostic (flag bit 3): %globaltimer of every CTA at kernel entry and at the end of its per-graph work
+// (drgnn_debug_cta_times: start skew and load imbalance across the grid - what the grid barrier waits for)
+__device__ unsigned long long g_cta_times[2048][2];
 // (flag bit 3 of the launch enables the clocks: their global stores delay the release fences of block 0, and the
 // whole grid waits for block 0 at the grid barrier)
 #define DRGNN_PHASE3(i)                                                                       \
@@ -706,6 +709,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
     __syncthreads();
   }
   const bool timers = (s.flags & 8) != 0 && blockIdx.x == 0 && t == 0;   // phase clocks of block 0 (diagnostic)
+  const bool cta_times = (s.flags & 8) != 0 && t == 0 && blockIdx.x < 2048;
+  if (cta_times) g_cta_times[blockIdx.x][0] = s3_globaltimer();
   constexpr int T = S3_THREADS, NW = S3_THREADS / 32;
   const int F = s.F, H1 = s.h1, H2 = s.h2, Hd = s.Hd, out = s.out;
   const int NBR = P.nbr, C1 = NBR * H1, C2 = NBR * H2;
@@ -1188,6 +1193,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1)
   }
   // nobody leaves (or reuses its shared memory) while a peer may still read it
   if (CS > 1) cluster.sync();
+  if (cta_times) g_cta_times[blockIdx.x][1] = s3_globaltimer();
   if (!P.fused_reduce || !train) return;
   s3_grid_reduce(s, C, scr, red);
   DRGNN_PHASE3(16);

@@ -570,6 +570,9 @@ int drgnn_net_step_last_tiles(void);
  * [2] zin1, [3] Z1, [4] P1, [5] zin2, [6] Z2, [7] P2, [8] read-out, [9] head, [10] head backward, [11] dZ2,
  * [12] dW2 / dzin2, [13] dP1, [14] dZ1, [15] dW1, [16] reduction.  Synchronises the device. */
 int drgnn_debug_phase3_cycles(uint64_t* out32);
+/* flag bit 3 of the last drgnn_net_step: %globaltimer (ns) of CTA c at kernel entry (out[2c]) and at the end of its
+ * per-graph work (out[2c+1]); ctas <= 2048 */
+int drgnn_debug_cta_times(uint64_t* out, int32_t ctas);
 
 /* ---- multi-GPU: gradient exchange over NVLink peer memory fused with the optimiser ----
  * Replaces, on every rank, the sequence  [reduce per-graph rows] -> torch.distributed.all_reduce(flat

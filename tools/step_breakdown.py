@@ -52,8 +52,16 @@ def main():
         if graph:
             import ctypes
             from deeprank_gnn_b200 import _lib
-            eng.phase_timers, eng.use_graph = 2, False      # one eager launch with the phase clocks on
+            eng.phase_timers, eng.use_graph = 2, False      # eager launches with the phase clocks on
+            for _ in range(3):
+                eng.step(ds[0], prepared=True)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             eng.step(ds[0], prepared=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            print('  the clocked launch, CUDA events around it: %.1f us' % (1e3 * ev0.elapsed_time(ev1)))
             eng.phase_timers, eng.use_graph = False, True
             ph = (ctypes.c_uint64 * 32)()
             _lib.check(_lib.load().drgnn_debug_phase_cycles(ph), 'phase')
@@ -76,6 +84,15 @@ def main():
                 n3 = ['stage', 'zin1', 'Z1', 'P1', 'zin2', 'Z2', 'P2', 'readout', 'head', 'headbwd', 'dZ2', 'dW2/dzin2',
                       'dP1', 'dZ1', 'dW1', 'reduce']
                 from deeprank_gnn_b200 import ops
+                nct = min(2048, cfg['batch'] * ops.net_step_last()[1] * (2 if cfg['net'] == 'GINet' else 1))
+                ct = (ctypes.c_uint64 * (2 * nct))()
+                _lib.check(_lib.load().drgnn_debug_cta_times(ct, nct), 'cta times')
+                st0 = [ct[2 * i] for i in range(nct)]
+                en0 = [ct[2 * i + 1] for i in range(nct)]
+                t00 = min(st0)
+                dur = sorted(e - s_ for s_, e in zip(st0, en0))
+                print('  CTAs (%d): start skew max %.1f us | per-graph work min / median / max %.1f / %.1f / %.1f us | last CTA done at %.1f us'
+                      % (nct, (max(st0) - t00) / 1e3, dur[0] / 1e3, dur[len(dur) // 2] / 1e3, dur[-1] / 1e3, (max(en0) - t00) / 1e3))
                 print('general cluster step kernel (tiles %d), block 0: %d cycles total'
                       % (ops.net_step_last()[1], max(ph[15], ph[16]) - ph[0]))
                 print('  ' + ' | '.join('%s %d' % (nm, ph[i + 1] - ph[i]) for i, nm in enumerate(n3)
