@@ -196,6 +196,12 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   return DRGNN_OK;
 }
 
+extern "C" int drgnn_debug_cta_times(uint64_t* out, int32_t ctas) {
+  DRGNN_REQUIRE(out != nullptr && ctas >= 0 && ctas <= 2048, "debug_cta_times: bad arguments");
+  DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_cta_times, sizeof(unsigned long long) * 2 * (size_t)ctas));
+  return DRGNN_OK;
+}
+
 extern "C" int drgnn_debug_phase3_cycles(uint64_t* out32) {
   DRGNN_REQUIRE(out32 != nullptr, "debug_phase3_cycles: NULL");
   DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_phase3, sizeof(unsigned long long) * 32));
