@@ -179,6 +179,7 @@ class FeedStep(C.Structure):
 
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
+NCCL_ID_BYTES = 128
 
 
 class PeerComm(C.Structure):
@@ -261,6 +262,8 @@ _SIGNATURES = {
     'drgnn_net_step_smem_bytes_l': (_i64, [_i32] * 12),
     'drgnn_net_step_pick_tiles_l': (C.c_int, [_i32] * 11),
     'drgnn_net_step': (C.c_int, [C.POINTER(NetStepArgs), VP]),
+    'drgnn_sgat_step': (C.c_int, [C.POINTER(NetStepArgs), VP]),
+    'drgnn_fout_step': (C.c_int, [C.POINTER(NetStepArgs), VP]),
     'drgnn_net_step_last_launches': (C.c_int, []),
     'drgnn_net_step_last_tiles': (C.c_int, []),
     'drgnn_debug_phase3_cycles': (C.c_int, [C.POINTER(C.c_uint64)]),
@@ -280,6 +283,11 @@ _SIGNATURES = {
     'drgnn_comm_free': (C.c_int, [VP]),
     'drgnn_comm_status': (C.c_int, [VP, C.POINTER(C.c_uint32)]),
     'drgnn_peer_reduce_adam': (C.c_int, [C.POINTER(PeerComm), C.POINTER(PeerAdamArgs), VP]),
+    'drgnn_nccl_available': (C.c_int, []),
+    'drgnn_nccl_unique_id': (C.c_int, [VP]),
+    'drgnn_nccl_init': (C.c_int, [C.POINTER(VP), _i32, _i32, VP]),
+    'drgnn_nccl_allreduce': (C.c_int, [VP, VP, _i64, VP]),
+    'drgnn_nccl_destroy': (C.c_int, [VP]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -196,6 +196,15 @@ extern "C" int drgnn_net_step(const drgnn_net_step_args* s, void* stream) {
   return DRGNN_OK;
 }
 
+extern "C" int drgnn_sgat_step(const drgnn_net_step_args* s, void* stream) {
+  DRGNN_REQUIRE(s != nullptr && s->kind == 1, "sgat_step: args must carry kind 1 (sGAT)");
+  return drgnn_net_step(s, stream);
+}
+extern "C" int drgnn_fout_step(const drgnn_net_step_args* s, void* stream) {
+  DRGNN_REQUIRE(s != nullptr && s->kind == 2, "fout_step: args must carry kind 2 (FoutNet)");
+  return drgnn_net_step(s, stream);
+}
+
 extern "C" int drgnn_debug_cta_times(uint64_t* out, int32_t ctas) {
   DRGNN_REQUIRE(out != nullptr && ctas >= 0 && ctas <= 2048, "debug_cta_times: bad arguments");
   DRGNN_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_cta_times, sizeof(unsigned long long) * 2 * (size_t)ctas));

@@ -350,6 +350,13 @@ class Engine(object):
         self.reset_parameters(seed)
         if self.world > 1 and peer_comm and os.environ.get('DRGNN_PEER_COMM', '1') != '0':
             self._open_comm()
+        # no peer memory (or DRGNN_PEER_COMM=0): ONE NCCL all-reduce of [gradients | loss] per step - through
+        # torch.distributed, or with DRGNN_NCCL_NATIVE=1 through the C-ABI (drgnn_nccl_allreduce on a communicator
+        # owned by libdrgnn: the binding a host without PyTorch's process group would use)
+        self.nccl = None
+        if self.world > 1 and self.comm is None and os.environ.get('DRGNN_NCCL_NATIVE', '0') != '0':
+            from .parallel import NcclComm
+            self.nccl = NcclComm(group=self.pg)
 
     def _open_comm(self):
         """Map the peers' exchange regions (CUDA IPC).  Symmetric on all ranks: either every rank
@@ -365,7 +372,7 @@ class Engine(object):
         if self.world == 1:
             return 'none'
         if self.comm is None:
-            return 'nccl all_reduce'
+            return 'nccl all_reduce' + (' (drgnn_nccl_allreduce)' if self.nccl is not None else '')
         if self._last_exchange == 'in-kernel':
             return 'peer-memory exchange + rank-ordered sum + Adam inside the step kernel (no extra launch)'
         return 'peer-memory exchange fused with reduce+Adam (1 launch)'
@@ -936,7 +943,10 @@ class Engine(object):
         if self.world > 1:
             # the path's only collective: one sum over ranks of [flat gradients | loss] (NCCL over NVLink)
             # (ws.loss IS the slot behind the gradients, see _ensure)
-            torch.distributed.all_reduce(self._grads_full[:self.params.numel + 4], group=self.pg)
+            if self.nccl is not None:
+                self.nccl.all_reduce_(self._grads_full[:self.params.numel + 4])
+            else:
+                torch.distributed.all_reduce(self._grads_full[:self.params.numel + 4], group=self.pg)
 
     def forward(self, d, keep_mask=None, prepared=False):
         """Forward only (``model(batch)``): returns the ``[B, out]`` prediction (a view of an

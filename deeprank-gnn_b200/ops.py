@@ -724,7 +724,8 @@ def net_step(kind, st, x, params, offsets, B, F, h1, h2, Hd, out, max_n, max_e, 
         s.kptr0, s.kptr1 = ptr(st.kptr0), ptr(st.kptr1)
         s.Zin1, s.Z1, s.arg0 = ptr(mirror['Zin1']), ptr(mirror['Z1']), ptr(mirror['arg0'])
         s.Zin2, s.Z2, s.arg1 = ptr(mirror['Zin2']), ptr(mirror['Z2']), ptr(mirror['arg1'])
-    call('drgnn_net_step', C.byref(s), stream_ptr())
+    # the per-network names of SURVEY 8b (same launch; the entry point checks the kind it is bound for)
+    call(('drgnn_net_step', 'drgnn_sgat_step', 'drgnn_fout_step')[int(s.kind)], C.byref(s), stream_ptr())
     _lib.kernel_count += int(_lib.load().drgnn_net_step_last_launches()) - 1
 
 

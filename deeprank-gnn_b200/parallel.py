@@ -270,3 +270,65 @@ class PeerComm(object):
         if self._own is not None:
             lib.drgnn_comm_free(self._own)
             self._own = None
+
+
+class NcclComm(object):
+    """The path's one collective through the C-ABI (``drgnn_nccl_*``, ``csrc/nccl_bridge.cu``): an NCCL
+    communicator owned by libdrgnn - the fallback of the gradient exchange where peer memory cannot be
+    mapped, and the form a non-PyTorch host would bind.
+
+    The 128-byte unique id of rank 0 reaches the other ranks through ``torch.distributed``
+    (``broadcast_object_list`` over ``group``; any backend) or, without a process group, through
+    ``id_bytes`` handed in by the launcher.  ``all_reduce_(t)`` sums a contiguous fp32 CUDA tensor
+    over the ranks in place on the current stream."""
+
+    def __init__(self, rank=None, world=None, group=None, id_bytes=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        if not lib.drgnn_nccl_available():
+            raise _lib.DrgnnError('no NCCL library could be bound (DRGNN_NCCL_LIB, libnccl.so.2)')
+        dist = torch.distributed
+        if id_bytes is None:
+            if world == 1:
+                rank = 0
+                id_bytes = self.unique_id()
+            else:
+                if not (dist.is_available() and dist.is_initialized()):
+                    raise _lib.DrgnnError('NcclComm needs the unique id of rank 0 (id_bytes) or a process group')
+                world, rank = dist.get_world_size(group), dist.get_rank(group)
+                box = [self.unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                           group=group)
+                id_bytes = box[0]
+        if len(id_bytes) != _lib.NCCL_ID_BYTES:
+            raise _lib.DrgnnError('an NCCL unique id has %d bytes' % _lib.NCCL_ID_BYTES)
+        self.world, self.rank = int(world), int(rank)
+        comm = _lib.VP()
+        buf = C.create_string_buffer(bytes(id_bytes), _lib.NCCL_ID_BYTES)
+        _lib.check(lib.drgnn_nccl_init(C.byref(comm), self.world, self.rank, C.cast(buf, _lib.VP)), 'drgnn_nccl_init')
+        self._comm = comm.value
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+        _lib.check(_lib.load().drgnn_nccl_unique_id(C.cast(buf, _lib.VP)), 'drgnn_nccl_unique_id')
+        return buf.raw
+
+    def all_reduce_(self, t):
+        from . import _lib
+        _lib.require_cuda(t)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.DrgnnError('drgnn_nccl_allreduce sums contiguous float32 buffers')
+        if self._comm is None:
+            raise _lib.DrgnnError('the communicator is closed')
+        _lib.call('drgnn_nccl_allreduce', self._comm, t.data_ptr(), t.numel(), _lib.stream_ptr(t.device))
+        return t
+
+    def close(self):
+        from . import _lib
+        if self._comm is not None:
+            _lib.load().drgnn_nccl_destroy(self._comm)
+            self._comm = None

@@ -562,6 +562,12 @@ int64_t drgnn_net_step_smem_bytes_l(int32_t kind, int32_t tiles, int32_t F, int3
 int drgnn_net_step_pick_tiles_l(int32_t kind, int32_t F, int32_t h1, int32_t h2, int32_t max_n, int32_t max_k, int32_t max_q,
                                 int32_t max_e, int32_t Hd, int32_t out, int32_t layers3);
 int drgnn_net_step(const drgnn_net_step_args* s, void* stream);
+/* The same launch under the names SURVEY 8b lists for the fused per-network entry points: drgnn_sgat_step
+ * requires kind == 1 (sGAT.py:62-93, 114-138), drgnn_fout_step kind == 2 (foutnet.py:56-82, 103-125) - a caller
+ * that binds one network cannot launch another by a wrong `kind`.  (GINet: drgnn_ginet_step, which takes the
+ * CTA-pair kernel when the graphs fit it, or drgnn_net_step with kind 0.) */
+int drgnn_sgat_step(const drgnn_net_step_args* s, void* stream);
+int drgnn_fout_step(const drgnn_net_step_args* s, void* stream);
 /* kernels the last drgnn_net_step of this thread launched (1: reduction fused / scoring, 2: + reduction launch)
  * and the tile count it used */
 int drgnn_net_step_last_launches(void);
@@ -615,6 +621,22 @@ int drgnn_comm_close(void* peer_ptr);
 int drgnn_comm_free(void* dev_ptr);
 int drgnn_comm_status(const void* region, uint32_t* ctr4);   /* host copy of ctr[0..3] (synchronises the device) */
 int drgnn_peer_reduce_adam(const drgnn_peer_comm* c, const drgnn_peer_adam_args* a, void* stream);
+
+/* ---- multi-GPU fallback: the path's ONE collective as NCCL (SURVEY 8b "drgnn_nccl_{init,allreduce,destroy}", 8e) ----
+ * For GPUs that cannot map each other's memory (no CUDA IPC / P2P: the exchange above is unavailable) the
+ * data-parallel step is  [step kernel with skip_reduce = 0, fuse_adam = 0] -> drgnn_nccl_allreduce(grads | loss)
+ * -> drgnn_adam_flat, the literal form of SURVEY 8e (replaces torch.distributed.all_reduce over the flat
+ * gradient buffer; the reference itself is single-device, NeuralNet.py:502-503).  libdrgnn.so does not link NCCL:
+ * the library is bound at run time (dlopen of $DRGNN_NCCL_LIB, "libnccl.so.2", "libnccl.so"; inside a PyTorch
+ * process that is the copy torch loaded).  The 128-byte unique id of rank 0 travels to the other ranks by any
+ * host channel (the Python launcher uses torch.distributed / a file); `comm` is an opaque ncclComm_t owned by
+ * the caller between init and destroy; the all-reduce is in place, fp32, sum, stream-ordered. */
+#define DRGNN_NCCL_ID_BYTES 128
+int drgnn_nccl_available(void);                                         /* 1: an NCCL library could be bound */
+int drgnn_nccl_unique_id(void* id128);                                  /* ncclGetUniqueId (rank 0)            */
+int drgnn_nccl_init(void** comm, int32_t world, int32_t rank, const void* id128);   /* ncclCommInitRank (collective) */
+int drgnn_nccl_allreduce(void* comm, float* buf, int64_t count, void* stream);      /* ncclAllReduce(sum, fp32), in place */
+int drgnn_nccl_destroy(void* comm);                                     /* ncclCommDestroy                     */
 
 /* ---- end-to-end feeder: the pipelined epoch loop issued from C ----
  * Replaces the per-step Python of Engine.train_batches (NeuralNet.py:490-523 over a DataLoader): for

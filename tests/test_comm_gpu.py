@@ -148,3 +148,85 @@ def test_two_processes_share_gradients_through_ipc_peer_memory(lib, tmp_path, gr
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count('peer-memory exchange') == 2, r.stdout
+
+
+def test_nccl_bridge_single_rank_communicator(lib):
+    """drgnn_nccl_* on a world of ONE (what a 1-GPU box can run): the library binds NCCL at run time, creates
+    a communicator from its own unique id, and the in-place fp32 sum over one rank is the identity - eagerly
+    and replayed from a CUDA graph (the step graphs capture the call)."""
+    from deeprank_gnn_b200.parallel import NcclComm
+    assert lib.drgnn_nccl_available() == 1
+    comm = NcclComm(world=1)
+    t = torch.arange(10701, device='cuda', dtype=torch.float32) * 0.25
+    ref = t.clone()
+    comm.all_reduce_(t)
+    torch.cuda.synchronize()
+    assert torch.equal(t, ref)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            comm.all_reduce_(t)
+            t.mul_(2.0)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(t, ref * 2)
+    with pytest.raises(Exception):
+        comm.all_reduce_(t.double())
+    comm.close()
+    with pytest.raises(Exception):
+        comm.all_reduce_(t)
+
+
+NCCL_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+os.environ['DRGNN_PEER_COMM'] = '0'          # no peer memory: the step falls back to the one NCCL all-reduce
+os.environ['DRGNN_NCCL_NATIVE'] = '1'        # ... through the C-ABI (drgnn_nccl_allreduce)
+import torch, torch.distributed as dist
+from deeprank_gnn_b200 import synthetic, parallel
+from deeprank_gnn_b200.data import Batch
+from deeprank_gnn_b200.engine import DeviceBatch, Engine
+rank, world, local = parallel.init_distributed('gloo')    # gloo carries the unique id; NCCL belongs to libdrgnn
+torch.cuda.set_device(local)
+dev = 'cuda:%%d' %% local
+graphs = synthetic.make_graphs('cfg2', count=8, seed=11)
+full = Engine('GINet', 32, 1, 1, device=dev, seed=5, peer_comm=False)
+full.world = 1
+full.eval()
+dense = DeviceBatch.from_batch(Batch.from_data_list(graphs), dev)
+eng = Engine('GINet', 32, 1, 1, device=dev, seed=5, graph=False).eval()
+assert eng.comm is None and eng.nccl is not None
+mine = parallel.shard_graphs(graphs, world, rank, balance=False)
+d = DeviceBatch.from_batch(Batch.from_data_list(mine), dev)
+for it in range(3):
+    full.step(dense)
+    loss, pred = eng.step(d, B_global=len(graphs))
+    eng.validate()
+    torch.cuda.synchronize()
+    assert abs(float(loss[0]) - float(full.ws.loss[0])) < 1e-5 * max(1.0, abs(float(full.ws.loss[0])))
+    for (n, a), (_, b) in zip(eng.state_dict().items(), full.state_dict().items()):
+        err = float((a - b).abs().max())
+        assert err < 5e-5, (it, n, err)
+flat = eng.params.data.cpu()
+both = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(both, flat)
+assert torch.equal(both[0], both[1]), 'weights differ between ranks'
+sys.stdout.write('rank ' + str(rank) + ' ok ' + eng.collective() + chr(10)); sys.stdout.flush()
+eng.nccl.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='NCCL needs one device per rank')
+def test_two_ranks_all_reduce_through_the_nccl_bridge(lib, tmp_path):
+    """world_size 2 on TWO GPUs without peer memory: Engine.step with drgnn_nccl_allreduce equals the
+    single-process step on the full batch; weights bit-identical across the ranks."""
+    script = tmp_path / 'nccl_worker.py'
+    script.write_text(NCCL_WORKER % {'root': ROOT})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29642', str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('drgnn_nccl_allreduce') == 2, r.stdout

@@ -337,3 +337,40 @@ def test_packed_batch_with_almost_as_many_clusters_as_nodes():
     assert cap['cluster1'].numel() == 4
     with pytest.raises(ValueError):
         pb.views(torch.zeros(pb.capacity_numel - 4), capacity=True)
+
+
+def test_nccl_bridge_binds_at_run_time_and_validates_arguments(lib):
+    """drgnn_nccl_* (csrc/nccl_bridge.cu): libdrgnn.so carries no link-time NCCL dependency, binds the library
+    with dlopen and refuses malformed calls with an error code + message (no compute, no GPU)."""
+    import ctypes as C
+    out = subprocess.run(['readelf', '-d', lib._name], capture_output=True, text=True).stdout
+    assert 'libnccl' not in out                                  # bound with dlopen, not linked
+    assert lib.drgnn_nccl_allreduce(None, None, 4, None) != 0
+    assert b'no communicator' in lib.drgnn_last_error()
+    assert lib.drgnn_nccl_destroy(None) == 0                     # closing nothing is fine
+    if not lib.drgnn_nccl_available():
+        pytest.skip('no NCCL library on this host')
+    from deeprank_gnn_b200.parallel import NcclComm
+    a, b = NcclComm.unique_id(), NcclComm.unique_id()
+    assert len(a) == len(b) == 128 and a != b
+    comm = C.c_void_p()
+    buf = C.create_string_buffer(a, 128)
+    assert lib.drgnn_nccl_init(C.byref(comm), 2, 5, C.cast(buf, C.c_void_p)) != 0
+    assert b'outside a world of 2' in lib.drgnn_last_error()
+    assert lib.drgnn_nccl_init(None, 1, 0, C.cast(buf, C.c_void_p)) != 0
+
+
+def test_named_network_entry_points_check_their_kind(lib):
+    """drgnn_sgat_step / drgnn_fout_step (SURVEY 8b names) are the general cluster launch bound to ONE network:
+    a record of another kind is refused before anything is launched."""
+    import ctypes as C
+    from deeprank_gnn_b200 import _lib
+    s = _lib.NetStepArgs()
+    for name, kind in (('drgnn_sgat_step', 1), ('drgnn_fout_step', 2)):
+        for k in (0, 1, 2):
+            if k == kind:
+                continue
+            s.kind = k
+            assert getattr(lib, name)(C.byref(s), None) == -1
+            assert b'must carry kind %d' % kind in lib.drgnn_last_error()
+        assert getattr(lib, name)(None, None) == -1
