@@ -54,6 +54,9 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--batch', type=int, default=None, help='graphs per GPU per step (default: the config batch)')
+    ap.add_argument('--global-batch', type=int, default=None,
+                    help='STRONG scaling (SURVEY 8e): graphs per step over ALL GPUs (cfg4: 256, cfg5: 512); each rank '
+                         'takes global / gpus of them.  Default: weak scaling, --batch graphs per GPU')
     ap.add_argument('--layers', type=int, default=2, choices=[2, 3],
                     help='3: the three-layer sGAT / FoutNet throughput variant (BASELINE config 3 "sGAT 3-layer")')
     ap.add_argument('--pool', type=int, default=64, help='distinct batches rotated through (must exceed L2)')
@@ -62,7 +65,17 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--stream-nodes', type=int, default=6553600, help='nodes of the roofline stream (>> L2)')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.global_batch is not None:
+        if args.batch is not None:
+            ap.error('--batch (per GPU, weak scaling) and --global-batch (strong scaling) exclude each other')
+        if args.global_batch % max(1, args.gpus) or args.global_batch < args.gpus:
+            ap.error('--global-batch must be a positive multiple of --gpus')
+        args.batch = args.global_batch // args.gpus
+        args.scaling = 'strong'
+    else:
+        args.scaling = 'weak'
+    return args
 
 
 def peaks():
@@ -220,7 +233,7 @@ def run_reference(args):
     cores = torch.get_num_threads()
     line = {
         'impl': 'reference', 'metric': metric_name(cfg), 'value': gps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n,
-        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': describe(cfg, args),
         'cpu_baseline': {'value': gps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
@@ -537,7 +550,7 @@ def run_b200(args):
     line = {
         'metric': metric_name(cfg), 'value': B_global * args.steps / (t_dev * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_dev / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': describe(cfg, args),
         'e2e': {'value': B_global * args.steps / (t_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(pool_bytes / len(packed)), 'd2h_bytes_per_step': 4 * (4 + B),
