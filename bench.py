@@ -439,8 +439,11 @@ def run_b200(args):
             os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
+    native = None
     if rank == 0:
         __graft_entry__.build()
+        from deeprank_gnn_b200 import build as _build
+        native = _build.build_record()
     if world > 1:
         dist.barrier()
     from deeprank_gnn_b200 import _lib
@@ -571,6 +574,7 @@ def run_b200(args):
                              'barrier' % ALIGN_STEPS},
         'weights_equal_across_ranks': weights_equal if world > 1 else None,
         'host_numa': numa,
+        'native': native,
     }
     if world == 1 and not args.no_roofline:
         agg = aggregation_roofline(cfg, graphs, args.stream_nodes, hbm, peak_src, batches[0])

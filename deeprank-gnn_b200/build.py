@@ -44,8 +44,28 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LAST = None      # record of the last build() of this process (see build_record)
+
+
+def build_record():
+    """What the last ``build()`` of this process did and which library is in place: sources compiled here (empty =
+    the objects that travelled with the working tree were newer than every source and header), whether the
+    library was re-linked, nvcc's release line, size / sha256 prefix / mtime of ``libdrgnn.so``.  bench.py prints it
+    as ``native`` so a reader can tell a box that recompiled from one that reused the shipped binary."""
+    import hashlib
+    rec = dict(LAST or {'compiled': None, 'linked': None, 'nvcc': None})
+    if os.path.exists(LIB):
+        with open(LIB, 'rb') as f:
+            blob = f.read()
+        rec.update(so=os.path.relpath(LIB, ROOT), so_bytes=len(blob), so_sha256_16=hashlib.sha256(blob).hexdigest()[:16],
+                   so_mtime=int(os.path.getmtime(LIB)))
+    rec['flags'] = ' '.join(NVCC_FLAGS[:5])
+    return rec
+
+
 def build(force=False, verbose=False):
     """Compile every ``csrc/*.cu`` for sm_100a and link ``libdrgnn.so``.  Returns the path."""
+    global LAST
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     hdrs = _deps()
@@ -68,7 +88,14 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + '.o') for s in sources()]
+    try:
+        ver = [ln for ln in subprocess.run([nvcc, '--version'], capture_output=True, text=True).stdout.splitlines()
+               if 'release' in ln]
+    except OSError:
+        ver = []
+    LAST = {'compiled': [os.path.basename(j[0]) for j in jobs], 'linked': False, 'nvcc': ver[0].strip() if ver else None}
     if force or jobs or _stale(LIB, objs):
+        LAST['linked'] = True
         cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
         if verbose:
             print(' '.join(cmd), flush=True)
