@@ -407,6 +407,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const int co1 = r * H1, co2 = r * H2;
   const bool mirror = (s.flags & 1) != 0;   // also store the intermediates to global memory
   const bool tc = (s.flags & 4) != 0;       // dense products on tensor-core tiles (mma.sync 3xTF32, tc_tiles.cuh)
+  // flag bit 6, "head v2" (same arithmetic, same bits; fewer barriers and less gradient-row traffic):
+  //   * the read-out row goes to global memory AFTER the cluster barrier of the exchange (its releasing arrive would
+  //     otherwise wait for those stores);
+  //   * regression with one output: every warp evaluates fc2, so prediction, loss term and dLoss/dpred live in every
+  //     thread's registers - no barrier between fc2, the loss and the head backward, no single-thread section;
+  //   * in-kernel reduction only: the fc1.weight gradient rows (Hd x C2 = 77 % of a gradient row) are NOT stored - the
+  //     reducing CTA forms dh_g[j] * R_g[c] from the fc1.bias gradient row and the read-out row of graph g
+  //     (rounded product, then the same four ordered quarter sums: bit-identical to summing stored rows)
+  const bool head2 = (s.flags & 64) != 0;
   S2_PHASE(0);
   float* xs = sm + P.xs;   float* ax = sm + P.ax;   float* z1 = sm + P.z1;   float* dz1 = sm + P.dz1;
   float* w1t = sm + P.w1t; float* w2t = sm + P.w2t; float* w2 = sm + P.w2;
@@ -456,10 +465,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   const uint32_t drop_ctr = (!s.keep && s.drop_p > 0.f) ? (uint32_t)__ldg(s.step_dev) : 0u;
   float y_first = 0.f;
   int y_cls = 0;
-  if (train && t == 0) {
+  if (train && (t == 0 || head2)) {
     if (s.task == 3) y_cls = (int)__ldg(s.y_class + g);
     else y_first = __ldg(s.y + (int64_t)g * out);
   }
+  const bool compact_fc1 = head2 && train && P.fused_reduce != 0;
   // The per-graph work sits in a do { } while (0): an invalid graph (host bounds violated, incomplete blob)
   // zeroes its gradient row, flags the status word and BREAKS to the grid barrier below instead of leaving the
   // kernel - every CTA must reach the barrier and take its ticket, or the counters would not be re-armed
@@ -471,6 +481,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     if (train && r == 0) {
 #pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
+#pragma unroll 1
+      for (int i = t; i < C2; i += T) a.R[(int64_t)g * C2 + i] = 0.f;   // (head v2 multiplies it with the zero dh row)
     }
     break;
   }
@@ -519,6 +531,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     if (train && r == 0) {
 #pragma unroll 1
       for (int i = t; i < s.n_params + 1; i += T) part[i] = 0.f;
+#pragma unroll 1
+      for (int i = t; i < C2; i += T) a.R[(int64_t)g * C2 + i] = 0.f;   // (head v2 multiplies it with the zero dh row)
     }
     break;
   }
@@ -591,7 +605,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       float acc = 0.f;
       for (int q = 0; q < Q; ++q) acc += p2[q * H2 + c];
       acc *= 1.f / (float)max(Q, 1);
-      a.R[(int64_t)g * C2 + co2 + c] = acc;
+      if (!head2) a.R[(int64_t)g * C2 + co2 + c] = acc;
       rrow[co2 + c] = acc;
       peer_rrow[co2 + c] = acc;
     }
@@ -599,6 +613,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   s2_wait<0>();                // small head vectors (this thread's copies) ...
   s2_mbar_wait(&bars[1], 0);   // ... and fc1.weight have landed
   cluster.sync();              // everybody's copies, and the peer's half of the read-out row
+  if (head2) {
+#pragma unroll 1
+    for (int c = t; c < H2; c += T) a.R[(int64_t)g * C2 + co2 + c] = rrow[co2 + c];
+  }
   S2_PHASE(8);
   // ---- fc1 (both CTAs, identical results): four lanes per hidden unit, each a quarter of the read-out
   // channels as 16-byte loads, two shuffles to combine
@@ -630,6 +648,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   }
   __syncthreads();
   S2_PHASE(9);
+  const int j0 = r ? (Hd >> 1) : 0, j1 = r ? Hd : (Hd >> 1), nj = j1 - j0;   // hidden units whose gradient rows CTA r writes
+  if (head2 && train && out == 1 && s.task == 1) {
+    // ---- fc2, loss term, dLoss/dpred in EVERY warp (same lanes, same order: the same bits in every thread)
+    float pv = 0.f;
+#pragma unroll 1
+    for (int j = lane; j < Hd; j += 32) pv = fmaf(hrow[j], fc2w[j], pv);
+    pv = warp_sum(pv);
+    pv += fc2b[0];
+    const float dd = pv - y_first;
+    const float dpred = 2.f * dd * s.inv_norm;
+    if (t == 0) {
+      prow[0] = dpred;
+      if (r == 0) {
+        s.pred[(int64_t)g * out] = pv;
+        part[s.n_params] = (dd * dd) * s.inv_norm;   // summed into the loss by the reduction
+        part[s.off_fc2b] = dpred;
+      }
+    }
+    S2_PHASE(10);
+    // ---- head backward: dh (all units, both CTAs); gradient slots of the hidden units [j0, j1) by CTA r
+#pragma unroll 1
+    for (int j = t; j < Hd; j += T) {
+      const float hv = hrow[j];
+      float acc = fmaf(dpred, fc2w[j], 0.f);
+      acc = hv > 0.f ? acc * s.keep_scale : 0.f;
+      dhrow[j] = acc;
+      if (j >= j0 && j < j1) {
+        part[s.off_fc1b + j] = acc;
+        part[s.off_fc2w + j] = dpred * hv;
+      }
+    }
+    __syncthreads();
+  } else {
   // ---- fc2: warp per output
 #pragma unroll 1
   for (int o = warp; o < out; o += NW) {
@@ -679,7 +730,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
   }
   __syncthreads();
   // ---- head backward: dh (all units, both CTAs); gradient rows of the hidden units [j0, j1) by CTA r
-  const int j0 = r ? (Hd >> 1) : 0, j1 = r ? Hd : (Hd >> 1), nj = j1 - j0;
 #pragma unroll 1
   for (int j = t; j < Hd; j += T) {
     float acc = 0.f;
@@ -700,7 +750,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
     for (int o = t; o < out; o += T) part[s.off_fc2b + o] = prow[o];
   }
   __syncthreads();
-  {   // fc1.weight gradient rows of this CTA's hidden units: dh[j] * R[g][:], 16-byte stores
+  }
+  if (!compact_fc1) {   // fc1.weight gradient rows of this CTA's hidden units: dh[j] * R[g][:], 16-byte stores
     const int C24 = C2 >> 2;
     const S2Div dv(C24);
 #pragma unroll 1
@@ -829,7 +880,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
       if (q == 0 && mine && !peers && s.fuse_adam && e < n) {
         adam_mi = __ldcg(s.adam_m + e); adam_vi = __ldcg(s.adam_v + e); adam_pi = __ldcg(s.adam_p + e);
       }
-      if (mine) {
+      const int fe = e - s.off_fc1w;
+      if (mine && compact_fc1 && fe >= 0 && fe < Hd * C2) {
+        // fc1.weight element (j, c): sum over the graphs of dh_g[j] * R_g[c], the product rounded like the stored row
+        // element would have been, the sums in the same order as below
+        const int gs = (B + 3) >> 2;
+        const int g0 = q * gs, g1 = min(B, g0 + gs);
+        const int j = fe / C2, c = fe - j * C2;
+        const float* dhp = s.partial + s.off_fc1b + j;
+        const float* rp = a.R + c;
+        int gg = g0;
+#pragma unroll 1
+        for (; gg + 16 <= g1; gg += 16) {
+          float v[16], w[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            v[u] = __ldcg(dhp + (int64_t)(gg + u) * s.partial_ld);
+            w[u] = __ldcg(rp + (int64_t)(gg + u) * C2);
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc += __fmul_rn(w[u], v[u]);
+        }
+#pragma unroll 1
+        for (; gg < g1; ++gg) acc += __fmul_rn(__ldcg(rp + (int64_t)gg * C2), __ldcg(dhp + (int64_t)gg * s.partial_ld));
+      } else if (mine) {
         const int gs = (B + 3) >> 2;
         const int g0 = q * gs, g1 = min(B, g0 + gs);
         const float* src = s.partial + e;

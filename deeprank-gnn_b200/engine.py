@@ -329,6 +329,9 @@ class Engine(object):
         # dense products of the fused step on the tensor cores (mma.sync 3xTF32, error ~1e-6) instead of FFMA tiles;
         # opt-in: measured slower than the FFMA register tiles at every BASELINE config (profiles/README.md, round 2)
         self.fused_tc = os.environ.get('DRGNN_FUSED_TC', '0') != '0'
+        # head v2 of the CTA-pair kernel (flag bit 6 of drgnn_ginet_step: fc2 / loss / dLoss/dpred in every warp, fc1.weight
+        # gradient rows formed inside the in-kernel reduction instead of stored and re-read; bit-identical results)
+        self.head_v2 = os.environ.get('DRGNN_HEAD_V2', '1') != '0'
         # general cluster kernel on a grid larger than the device: clusters take the graphs largest first
         self.step3_lpt = os.environ.get('DRGNN_STEP3_LPT', '1') != '0'
         self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
@@ -689,7 +692,7 @@ class Engine(object):
                                variant=2 if st.blob_only else self.step_variant, fuse_reduce=self.fuse_reduce,
                                blob=st.blob, gdesc=st.gstat if st.blob_only else None,
                                edge_ptr=d.edge_ptr, tc=self.fused_tc, timers=self.phase_timers,
-                               zin1=getattr(st, 'zin1', None) if st.blob_only else None)
+                               zin1=getattr(st, 'zin1', None) if st.blob_only else None, head2=self.head_v2)
                 self._graph_done = self._head_done = self._all_done = train_step
                 self._all_done_kernel = True
                 self._adam_done = fuse_adam

@@ -562,7 +562,7 @@ def ginet_step_fits(F, h1, h2, nb, max_n, max_k, max_q, Hd, out):
 def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=None, y_class=None, class_w=None, keep=None,
                keep_scale=1.0, loss=None, partial=None, grads=None, n_params=0, offsets=None, forward_only=False,
                drop_p=0.0, seed=0, step_dev=None, adam=None, skip_reduce=False, max_e=0, mirror=False, variant=0,
-               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None, tc=False, timers=False, zin1=None):
+               fuse_reduce=True, blob=None, edge_ptr=None, comm=None, gdesc=None, tc=False, timers=False, zin1=None, head2=False):
     """Whole GINet step of every graph in one launch (``drgnn_ginet_step``); ``fa`` from
     ``ginet_fused_args``.  ``max_e`` (directed edges of the largest graph) enables the cluster
     kernel (a pair of CTAs per graph, everything in shared memory); ``mirror`` makes it store the
@@ -601,7 +601,10 @@ def ginet_step(fa, fc1_w, fc1_b, fc2_w, fc2_b, pred, task=0, inv_norm=1.0, y=Non
     # flags: bit 0 mirror the intermediates, bit 1 no in-kernel reduction, bit 2 dense products on mma.sync 3xTF32 tiles,
     # bit 3 phase clocks of block 0 (drgnn_debug_phase_cycles)
     s.max_e, s.variant = int(max_e or 0), int(variant)
-    s.flags = (1 if mirror else 0) | (0 if fuse_reduce else 2) | (4 if tc else 0) | (8 if timers else 0) | (16 if int(timers) > 1 else 0)
+    # bit 6: head v2 of the cluster kernel (fc2 / loss / dLoss in every warp; fc1.weight gradient rows formed by the
+    # in-kernel reduction from the fc1.bias gradient and read-out rows instead of being stored; same bits)
+    s.flags = (1 if mirror else 0) | (0 if fuse_reduce else 2) | (4 if tc else 0) | (8 if timers else 0) | (16 if int(timers) > 1 else 0) \
+        | (64 if head2 else 0)
     call('drgnn_ginet_step', C.byref(s), stream_ptr())
     # KERNELS_PER_CALL counts 2 (per-graph kernel + reduction); scoring, the peer exchange and the
     # in-kernel reduction (grid barrier) launch only the per-graph kernel

@@ -427,7 +427,13 @@ typedef struct drgnn_ginet_step_args {
    * zero-initialised: [2] is the grid-barrier counter of the fused reduction);
    * bit 2 (cluster kernel): the dense products run on tensor-core tiles (mma.sync.m16n8k8 TF32 with the 3-product
    * error compensation, ~1e-6; widths must be multiples of 8, else the fp32 FMA tiles are used);
-   * bit 3: block 0 records its phase clocks (drgnn_debug_phase_cycles; diagnostic, slows the launch slightly) */
+   * bit 3: block 0 records its phase clocks (drgnn_debug_phase_cycles; diagnostic, slows the launch slightly);
+   * bit 6: head v2 of the cluster kernel - fc2 / loss term / dLoss/dpred evaluated by every warp (regression, out = 1:
+   * no barrier and no single-thread section between fc2 and the head backward), the read-out row stored after the
+   * cluster barrier of its exchange, and - with the in-kernel reduction - the fc1.weight gradient rows (77 % of a
+   * per-graph gradient row) NOT stored: the reducing CTA forms dh_g[j] * R_g[c] from the fc1.bias gradient slots of
+   * `partial` and the read-out rows R (rounded product, same ordered sums: bit-identical gradients); the fc1.weight
+   * slots of `partial` are then unspecified after the call */
   int32_t flags;
   /* max_e: host bound of the directed edges of one graph (> 0 enables the cluster kernel: a pair of
    * CTAs per graph, one GINet branch each, nb == 2).  variant: 0 = pick (cluster kernel when it

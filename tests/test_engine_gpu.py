@@ -506,3 +506,34 @@ def test_cluster_step_kernel_tensor_core_tiles_match_fma_tiles(lib):
             for name, g in ea.named_grads().items():
                 torch.testing.assert_close(g, eb.named_grads()[name], rtol=1e-4, atol=1e-5, msg=name)
     torch.testing.assert_close(ea.params.data, eb.params.data, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('dropout', [0.0, 0.4])
+@pytest.mark.parametrize('fuse_reduce', [True, False])
+def test_cluster_step_kernel_head_v2_is_bit_identical(lib, dropout, fuse_reduce):
+    """Head v2 of the CTA-pair kernel (flag bit 6: fc2 / loss / dLoss/dpred in every warp, fc1.weight gradient formed
+    inside the in-kernel reduction from the fc1.bias gradient rows and the read-out rows instead of stored rows)
+    against the first version: predictions, loss, every gradient, the weights and both Adam moments after several
+    steps are the SAME BITS (rounded products, same summation order), with and without the in-kernel reduction."""
+    from deeprank_gnn_b200 import ops, synthetic
+    from deeprank_gnn_b200.engine import Engine
+    graphs = synthetic.make_graphs(dict(nodes=(20, 200), edges_per_node=5, feat=32), count=40, seed=21)
+    d = _device_batch(graphs)
+    ea = Engine('GINet', 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=dropout)
+    eb = Engine('GINet', 32, 1, 1, device='cuda:0', seed=3, lr=1e-3, dropout=dropout)
+    ea.step_variant = eb.step_variant = 2
+    ea.fuse_reduce = eb.fuse_reduce = fuse_reduce
+    ea.head_v2, eb.head_v2 = True, False
+    la, pa = ea.loss_and_grads(d)
+    lb, pb = eb.loss_and_grads(d)
+    assert ops.ginet_step_last_variant() == 2
+    assert torch.equal(pa, pb) and torch.equal(la, lb)
+    for name, g in ea.named_grads().items():
+        assert torch.equal(g, eb.named_grads()[name]), name
+    for _ in range(4):
+        la, pa = ea.step(d)
+        lb, pb = eb.step(d)
+        ea.validate(), eb.validate()
+        assert torch.equal(pa, pb) and torch.equal(la, lb)
+    assert torch.equal(ea.params.data, eb.params.data)
+    assert torch.equal(ea.exp_avg, eb.exp_avg) and torch.equal(ea.exp_avg_sq, eb.exp_avg_sq)
