@@ -404,6 +404,24 @@ def step_kernel_traffic(kernel, workload):
     return None, 'no ncu capture of this kernel committed'
 
 
+def step_bytes(batch, n_nodes, n_edges, feat, B, n_par, row_floats_not_moved=0):
+    """(algorithmic, implementation) bytes of one whole-step launch.
+
+    ALGORITHMIC = SURVEY 8d's per-graph figure of the ideally fused step, from the batch's own sizes: forward 4nF (x)
+    + 16e (int64 edge_index as the reference delivers it) + 4e.ne (edge_attr) + 8n (cluster0) + 8 K0 (cluster1) + 8n
+    (batch) + 4.out, forward + backward = 2x  (49.2 KB per cfg2 graph -> 98.4 KB per graph and step).
+    IMPLEMENTATION = what the step kernel moves through L2 per launch: feature tiles + structure blobs read once + the
+    per-graph gradient rows it writes and re-reads in its reduction (head v2: without the fc1.weight part, which the
+    reduction forms from the fc1.bias gradient and read-out rows) + parameters / Adam state."""
+    ne = int(batch.edge_attr.size(1)) if batch.edge_attr.dim() > 1 else 1
+    n_b, e_b, k0_b = int(batch.x.size(0)), int(batch.edge_index.size(1)), int(batch.cluster1.numel())
+    alg = 2 * (4 * n_b * feat + 16 * e_b + 4 * e_b * ne + 8 * n_b + 8 * k0_b + 8 * n_b + 4 * B)
+    blob_bytes = 4 * (32 * B + 9 * n_nodes + 5 * B + 3 * n_edges)
+    row = n_par + 4 - int(row_floats_not_moved)
+    impl = 4 * n_nodes * feat + blob_bytes + 2 * 4 * B * row + 3 * 4 * n_par
+    return alg, impl
+
+
 def dense_roofline():
     """The dense per-node transform on the tensor pipe (cfg4 shape), from the committed ncu capture."""
     path = os.path.join(ROOT, 'profiles', 'r2_dense_summary.json')
@@ -581,23 +599,25 @@ def run_b200(args):
         # PRIMARY entry = the kernel that dominates the timed step: the whole-step kernel, one launch per step,
         # back to back on the main stream inside the chunk graphs (the structure pass of later batches runs
         # beside it on side streams), so its average launch duration over the timed region is ms_per_step.
-        # Algorithmic bytes per launch = feature tiles + structure blobs read once
-        # + per-graph gradient rows written and re-read by the in-kernel reduction + parameters / Adam state.
-        pb0 = packed[0]
-        n_par = int(eng.params.numel)
-        blob_bytes = 4 * (32 * B + 9 * pb0.N + 5 * B + 3 * pb0.E)
-        alg = 4 * pb0.N * cfg['feat'] + blob_bytes + 2 * 4 * B * (n_par + 4) + 3 * 4 * n_par
-        us = 1e3 * t_dev / K
+        # Bytes per launch: step_bytes().
         step_kernel = eng.step_kernel_name()
+        compact = step_kernel == 'ginet_graph_step2_kernel' and getattr(eng, 'head_v2', False)
+        alg, impl_bytes = step_bytes(batches[0], packed[0].N, packed[0].E, cfg['feat'], B, int(eng.params.numel),
+                                     eng.spec.Hd * eng.spec.C2 - eng.spec.C2 if compact else 0)
+        us = 1e3 * t_dev / K
         traffic, traffic_src = step_kernel_traffic(step_kernel, args.workload)
         line['roofline'] = {
             'bound': 'hbm', 'kernel': step_kernel, 'achieved': alg / (us * 1e-6) / 1e9, 'peak': hbm, 'unit': 'GB/s',
             'frac': alg / (us * 1e-6) / 1e9 / hbm, 'traffic': traffic, 'traffic_source': traffic_src,
-            'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg, 'launch_us': us,
-            'launches_per_step': kernels_per_step,
-            'note': 'whole-step kernel at batch %d: latency / issue bound by construction (SURVEY fact 10, %d KB per '
-                    'graph); the HBM-bound stream-scale kernel of the path is reported under aggregation_stream'
-                    % (B, alg // B // 1024),
+            'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg,
+            'algorithmic_bytes': 'SURVEY 8d, ideally fused step: 2 x (4nF + 16e + 4e.ne + 8n + 8K0 + 8n + 4.out) per graph '
+                                 '= %.1f KB per graph' % (alg / B / 1e3),
+            # what THIS kernel moves through L2 per launch: feature tiles + structure blobs read once + the per-graph
+            # gradient rows it writes and re-reads in its reduction + parameters / Adam state
+            'implementation_bytes_per_launch': impl_bytes,
+            'launch_us': us, 'launches_per_step': kernels_per_step,
+            'note': 'whole-step kernel at batch %d: latency / issue bound by construction (SURVEY fact 10); the HBM-bound '
+                    'stream-scale kernel of the path is reported under aggregation_stream' % B,
             'aggregation_stream': agg,
         }
         dense = dense_roofline()

@@ -63,3 +63,19 @@ def test_product_arm_refuses_to_run_without_cuda():
     r = _run(['--gpus', '1', '--steps', '2', '--warmup', '1'])
     assert r.returncode != 0
     assert 'no CPU fallback' in r.stderr
+
+
+def test_step_bytes_follow_the_survey_figure():
+    """roofline.achieved of the step kernel is SURVEY 8d's algorithmic figure (49.2 KB per cfg2 graph forward, x 2)
+    times the graphs of a launch; the implementation bytes shrink by the fc1.weight rows with head v2."""
+    import bench
+    cfg = bench.workload_config('cfg2', None)
+    _graphs, batches = bench.make_pool(cfg, 1, seed=0)
+    b = batches[0]
+    N, E = int(b.x.size(0)), int(b.edge_index.size(1))
+    alg, impl = bench.step_bytes(b, N, E, cfg['feat'], 64, 10697)
+    k0 = int(b.cluster1.numel())
+    assert alg == 2 * (64 * (25600 + 16000 + 4000 + 1600 + 1600 + 4) + 8 * k0)
+    assert abs(alg / 64 / 2 - 49204) < 200                      # SURVEY 8d: ~49.2 KB per graph (K0 ~ 50)
+    alg2, impl2 = bench.step_bytes(b, N, E, cfg['feat'], 64, 10697, 128 * 64 - 64)
+    assert alg2 == alg and impl - impl2 == 2 * 4 * 64 * (128 * 64 - 64)
