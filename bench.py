@@ -394,7 +394,8 @@ def _profile_csv_metric(path, kernel_substr, metrics):
 def step_kernel_traffic(kernel, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
     `ncu --set full` capture of this workload (profiles/); (None, reason) when there is none."""
-    for name in ('r2_step_%s_ncu_raw.csv' % workload, 'r1_cluster_step_kernels_ncu_raw.csv' if workload == 'cfg2' else ''):
+    for name in ('r2_final3_step_%s_ncu_raw.csv' % workload, 'r2_step_%s_ncu_raw.csv' % workload,
+                 'r1_cluster_step_kernels_ncu_raw.csv' if workload == 'cfg2' else ''):
         if not name:
             continue
         path = os.path.join(ROOT, 'profiles', name)

@@ -79,3 +79,13 @@ def test_step_bytes_follow_the_survey_figure():
     assert abs(alg / 64 / 2 - 49204) < 200                      # ~49.2 KB per graph (K0 ~ 50)
     alg2, impl2 = bench.step_bytes(b, N, E, cfg['feat'], 64, 10697, 128 * 64 - 64)
     assert alg2 == alg and impl - impl2 == 2 * 4 * 64 * (128 * 64 - 64)
+
+
+def test_step_kernel_traffic_reads_the_committed_capture():
+    """roofline.traffic = dram__bytes_read + write per launch from the committed ncu capture, tagged with its file."""
+    import bench
+    v, src = bench.step_kernel_traffic('ginet_graph_step2_kernel', 'cfg2')
+    assert src.startswith('profiles/') and os.path.exists(os.path.join(ROOT, src.split(' ')[0]))
+    assert 2e6 < v < 2e7                                         # a few MB per launch: the compulsory input bytes
+    v, src = bench.step_kernel_traffic('no_such_kernel', 'cfg2')
+    assert v is None
