@@ -113,3 +113,69 @@ def test_shard_plan_covers_every_graph_once(costs, world, balance):
     if balance and len(costs) >= world:
         loads = [sum(costs[i] for i in p) for p in parts]
         assert max(loads) <= sum(costs) / world + max(costs) * 2
+
+
+# ----------------------------------------------------------------------------------------------- oracle invariants
+def _oracle_batch(graphs):
+    from oracle import pyg_min
+    return pyg_min.Batch.from_data_list(
+        [pyg_min.Data(**{k: (g[k].clone() if torch.is_tensor(g[k]) else g[k]) for k in g.keys}) for g in graphs])
+
+
+@settings(**SET)
+@given(lo=st.integers(4, 30), span=st.integers(0, 80), count=st.integers(1, 6), seed=st.integers(0, 10 ** 6))
+def test_oracle_pooling_invariants(lo, span, count, seed):
+    """Size-independent properties of get_preloaded_cluster + community_pooling (community_pooling.py:25-30, 161-251)
+    the CUDA structure pass is held to bit for bit: dense relabelling is idempotent and order preserving, the pooled
+    edge list is sorted by (row, col), unique, free of self-loops, symmetric for symmetric input, its attributes
+    conserve the attribute mass of the edges that survive, the pooled batch vector is sorted, and every pooled
+    feature is the maximum over its cluster."""
+    from oracle import pooling, pyg_min
+    graphs, _b = _batch(lo, lo + span, count, seed, feat=4)
+    ob = _oracle_batch(graphs)
+    cl = pooling.get_preloaded_cluster(ob.cluster0.clone(), ob.batch)
+    assert torch.equal(cl, pooling.get_preloaded_cluster_closed_form(ob.cluster0.clone(), ob.batch))
+    dense, perm = pyg_min.consecutive_cluster(cl)
+    again, _ = pyg_min.consecutive_cluster(dense)
+    assert torch.equal(again, dense)                                         # idempotent
+    assert torch.equal(torch.unique(dense), torch.arange(int(dense.max()) + 1))   # no gaps
+    order = torch.argsort(cl, stable=True)
+    assert bool((dense[order][1:] >= dense[order][:-1]).all())               # order preserving
+    x0, ei0, ea0 = ob.x.clone(), ob.edge_index.clone(), ob.edge_attr.clone()
+    out = pooling.community_pooling(cl, ob)
+    K = int(dense.max()) + 1
+    assert out.x.shape == (K, x0.size(1)) and out.batch.numel() == K
+    assert bool((out.batch[1:] >= out.batch[:-1]).all())
+    for k in range(0, K, max(1, K // 7)):                                    # a few clusters: the maximum of the members
+        assert torch.equal(out.x[k], x0[dense == k].max(dim=0).values)
+    pe = out.edge_index
+    if pe.numel():
+        key = pe[0] * K + pe[1]
+        assert bool((key[1:] > key[:-1]).all())                              # sorted by (row, col) and unique
+        assert bool((pe[0] != pe[1]).all())                                  # no self-loops
+        back = pe[1] * K + pe[0]
+        assert torch.equal(torch.sort(back).values, key)                     # symmetric input stays symmetric
+    keep = dense[ei0[0]] != dense[ei0[1]]
+    assert pe.size(1) == torch.unique(dense[ei0[0]][keep] * K + dense[ei0[1]][keep]).numel()
+    torch.testing.assert_close(out.edge_attr.sum(), ea0[keep].sum(), rtol=1e-5, atol=1e-5)   # coalesce sums attributes
+
+
+@settings(**SET)
+@given(n=st.integers(1, 300), c=st.integers(1, 9), k=st.integers(1, 40), seed=st.integers(0, 10 ** 6))
+def test_oracle_scatter_reductions_against_a_loop(n, c, k, seed):
+    """scatter_sum / scatter_mean / scatter_max (torch_scatter's published semantics) against the
+    per-segment loop: sums in index order, mean over max(count, 1), max with untouched rows = 0."""
+    from oracle import pyg_min
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(n, c, generator=g)
+    idx = torch.randint(0, k, (n,), generator=g)
+    s = pyg_min.scatter_sum(src, idx, dim=0, dim_size=k)
+    m = pyg_min.scatter_mean(src, idx, dim=0, dim_size=k)
+    mx, arg = pyg_min.scatter_max(src, idx, dim=0, dim_size=k)
+    for j in range(k):
+        rows = src[idx == j]
+        torch.testing.assert_close(s[j], rows.sum(0) if rows.numel() else torch.zeros(c), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(m[j], rows.mean(0) if rows.numel() else torch.zeros(c), rtol=1e-5, atol=1e-5)
+        assert torch.equal(mx[j], rows.max(0).values if rows.numel() else torch.zeros(c))
+        if rows.numel():
+            assert torch.equal(src[arg[j], torch.arange(c)], mx[j])
