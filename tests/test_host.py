@@ -374,3 +374,34 @@ def test_named_network_entry_points_check_their_kind(lib):
             assert getattr(lib, name)(C.byref(s), None) == -1
             assert b'must carry kind %d' % kind in lib.drgnn_last_error()
         assert getattr(lib, name)(None, None) == -1
+
+
+def test_ctypes_struct_offsets_equal_the_c_compilers(lib, tmp_path):
+    """Every argument record of the C-ABI: sizeof and the offset of EVERY field as gcc lays the header's struct out
+    equal the ctypes mirror's (names and order alone would miss an int32 / int64 / pointer mix-up, which shifts every
+    later pointer).  The header is compiled as plain C99 - it is a C interface."""
+    import ctypes
+    from deeprank_gnn_b200 import _lib
+    pairs = [('drgnn_structure_io', _lib.StructureIO), ('drgnn_aggregate_args', _lib.AggregateArgs),
+             ('drgnn_linear_args', _lib.LinearArgs), ('drgnn_linear_wgrad_args', _lib.LinearWgradArgs),
+             ('drgnn_head_args', _lib.HeadArgs), ('drgnn_ginet_fused_args', _lib.GinetFusedArgs),
+             ('drgnn_ginet_step_args', _lib.GinetStepArgs), ('drgnn_net_step_args', _lib.NetStepArgs),
+             ('drgnn_peer_comm', _lib.PeerComm), ('drgnn_peer_adam_args', _lib.PeerAdamArgs),
+             ('drgnn_feed_step', _lib.FeedStep)]
+    src = ['#include <stddef.h>', '#include <stdio.h>', '#include "drgnn.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        src.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _t in cls._fields_:
+            src.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src += ['  return 0;', '}']
+    c = tmp_path / 'layout.c'
+    c.write_text('\n'.join(src))
+    exe = tmp_path / 'layout'
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(c), '-o', str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _t in cls._fields_:
+            assert int(got['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, '%s.%s' % (cname, fname)
