@@ -405,3 +405,34 @@ def test_ctypes_struct_offsets_equal_the_c_compilers(lib, tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _t in cls._fields_:
             assert int(got['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, '%s.%s' % (cname, fname)
+
+
+def test_ctypes_prototypes_equal_the_headers(lib):
+    """Every entry point: number and width class of the arguments (pointer / int32 / int64 / float) and the result
+    type declared in include/drgnn.h equal the ctypes prototype (_lib._SIGNATURES) - a call through a prototype with
+    a narrower integer or a missing argument would pass garbage in a register."""
+    import ctypes as C
+    from deeprank_gnn_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'drgnn.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    protos = re.findall(r'^\s*((?:const\s+)?[A-Za-z0-9_]+\s*\*?)\s*(drgnn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', hdr, flags=re.M)
+    assert len(protos) == len(_lib._SIGNATURES)
+
+    def klass_c(decl):
+        decl = decl.strip()
+        if '*' in decl or '[' in decl:
+            return 'ptr'
+        base = re.sub(r'\b(const|unsigned|signed)\b', '', decl).split()[0]
+        return {'int32_t': 'i32', 'int': 'i32', 'uint32_t': 'i32', 'int64_t': 'i64', 'uint64_t': 'i64', 'float': 'f32'}[base]
+
+    def klass_py(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, 'contents'):
+            return 'ptr'
+        return {C.c_int32: 'i32', C.c_int: 'i32', C.c_uint32: 'i32', C.c_int64: 'i64', C.c_uint64: 'i64', C.c_float: 'f32'}[t]
+
+    for ret, name, args in protos:
+        res, argtypes = _lib._SIGNATURES[name]
+        args = args.strip()
+        want = [] if args in ('', 'void') else [klass_c(a) for a in args.split(',')]
+        assert [klass_py(t) for t in argtypes] == want, name
+        assert klass_py(res) == klass_c(ret), name
