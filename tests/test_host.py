@@ -436,3 +436,21 @@ def test_ctypes_prototypes_equal_the_headers(lib):
         want = [] if args in ('', 'void') else [klass_c(a) for a in args.split(',')]
         assert [klass_py(t) for t in argtypes] == want, name
         assert klass_py(res) == klass_c(ret), name
+
+
+def test_library_carries_blackwell_native_sass(lib):
+    """The built library is sm_100a code with the Blackwell-only machinery the design claims (cuobjdump, no GPU):
+    tcgen05 MMA + TMEM loads + tcgen05 commit in the dense transform (UTCHMMA, LDTM, UTCBAR), TMA bulk copies and
+    mbarriers in the step / structure / aggregation kernels (UBLKCP, SYNCS), thread-block-cluster barriers
+    (UCGABAR) - and no kernel compiled for another architecture."""
+    import shutil
+    if not shutil.which('cuobjdump'):
+        pytest.skip('cuobjdump not on PATH')
+    from deeprank_gnn_b200 import _lib
+    elfs = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout.split()
+    cubins = [e for e in elfs if e.endswith('.cubin')]
+    kernels = [e for e in cubins if not e.startswith('libdrgnn.')]          # (the link step's empty stub aside)
+    assert len(kernels) >= 12 and all('.sm_100a.' in e for e in kernels), cubins
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic, least in (('UTCHMMA', 3), ('LDTM', 1), ('UTCBAR', 1), ('UBLKCP', 20), ('SYNCS', 100), ('UCGABAR', 8)):
+        assert sass.count(mnemonic) >= least, (mnemonic, sass.count(mnemonic))
